@@ -1,0 +1,156 @@
+/*
+ * mpinets_b200.h -- C ABI of libmpinets_b200.so (B200 / sm_100a rollout engine for Motion Policy Networks).
+ *
+ * The reference (NVlabs/motion-policy-networks) has no FFI: its boundary for this path is a set of Python
+ * callables.  Each entry point below replaces the arithmetic behind one of them; the
+ * Python shim in mpinets_b200/ re-exports the reference's names over this ABI (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative mpn_status otherwise; mpn_last_error() gives the
+ *     thread-local message of the last failure;
+ *   - all tensor arguments are caller-owned DEVICE pointers (fp32 / int32 / u8), dense row-major, sizes explicit;
+ *     the library never frees or reallocates caller memory; it owns only its context workspace;
+ *   - `stream` is a cudaStream_t passed as void*; no entry point synchronises the host except
+ *     mpn_ctx_create/destroy, mpn_set_robot_tables, mpn_load_weight, mpn_weights_finalize and mpn_reserve;
+ *   - one context per device; a context is not thread-safe.
+ */
+#ifndef MPINETS_B200_H
+#define MPINETS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpn_ctx mpn_ctx;
+
+typedef enum {
+  MPN_OK = 0,
+  MPN_ERR_INVALID = -1,   /* bad argument (shape, null pointer, unsupported size) */
+  MPN_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+  MPN_ERR_STATE = -3,     /* tables / weights not loaded yet */
+  MPN_ERR_NOMEM = -4
+} mpn_status;
+
+/* arithmetic used by the set-abstraction MLPs / FC head */
+typedef enum {
+  MPN_PREC_FP32 = 0,      /* fp32 SIMT FMA, fp32 accumulate: the 1e-5 parity mode */
+  MPN_PREC_BF16 = 1       /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM: the throughput mode */
+} mpn_precision;
+
+typedef struct {
+  int32_t n_robot;        /* run_inference.py:52  NUM_ROBOT_POINTS    (2048) */
+  int32_t n_obstacle;     /* run_inference.py:53  NUM_OBSTACLE_POINTS (4096) */
+  int32_t n_target;       /* run_inference.py:54  NUM_TARGET_POINTS   (128)  */
+  int32_t max_cuboids;    /* M1: padded cuboid rows per problem   (data_loader.py:198-215) */
+  int32_t max_cylinders;  /* M2: padded cylinder rows per problem */
+  int32_t quirk_frames;   /* 1: replicate geometry.py:213/:444 row-2 quirk (default), 0: textbook rotation */
+  uint64_t seed;          /* counter-based RNG seed (Philox4x32-10 key) */
+} mpn_config;
+
+const char* mpn_last_error(void);
+const char* mpn_version(void);
+
+int mpn_ctx_create(int device, const mpn_config* cfg, mpn_ctx** out);
+int mpn_ctx_destroy(mpn_ctx* ctx);
+/* pre-size the context workspace for `max_batch` problems (otherwise grown lazily; growing is illegal during
+ * CUDA-graph capture) */
+int mpn_reserve(mpn_ctx* ctx, int max_batch);
+
+/* robofin tables as data (HOST pointers, copied): FrankaRealRobot.JOINT_LIMITS [7][2] (utils.py:50,84,192);
+ * FrankaSampler canonical link points [P][3] + link id [P] (link0..7, hand, leftfinger, rightfinger = 0..10);
+ * gripper points in the right_gripper frame [Pe][3] (sample_end_effector); FrankaCollisionSampler spheres. */
+int mpn_set_robot_tables(mpn_ctx* ctx, const float* joint_limits, int n_link_points, const float* link_points,
+                         const int32_t* link_ids, int n_ee_points, const float* ee_points, int n_spheres,
+                         const float* sphere_centers, const float* sphere_radii, const int32_t* sphere_links,
+                         float prismatic);
+
+/* weights by reference state-dict key (model.py:47-66,385-393; e.g. "point_cloud_encoder.SA_modules.0.mlps.0.0.weight"),
+ * HOST fp32 pointer, copied.  mpn_weights_finalize() checks completeness and builds the packed device copies. */
+int mpn_load_weight(mpn_ctx* ctx, const char* name, const float* host_data, const int64_t* shape, int ndim);
+int mpn_weights_finalize(mpn_ctx* ctx);
+
+/* ---- pointnet2_ops._ext replacements (model.py:27,365-383) -------------------------------- */
+/* furthest_point_sampling: xyz [B][N][stride>=3] -> idx [B][npoint]; new_xyz [B][npoint][3] optional (gather fused) */
+int mpn_fps(mpn_ctx* ctx, void* stream, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx,
+            float* new_xyz);
+/* ball_query: first `nsample` indices (in index order) with d^2 < r^2, padded with the first hit */
+int mpn_ball_query(mpn_ctx* ctx, void* stream, float radius, int nsample, const float* xyz, int B, int N, int stride,
+                   const float* new_xyz, int npoint, int32_t* idx);
+/* gather_points: feat [B][C][N], idx [B][m] -> out [B][C][m] */
+int mpn_gather_points(mpn_ctx* ctx, void* stream, const float* feat, int B, int C, int N, const int32_t* idx, int m,
+                      float* out);
+/* group_points: feat [B][C][N], idx [B][m][ns] -> out [B][C][m][ns] */
+int mpn_group_points(mpn_ctx* ctx, void* stream, const float* feat, int B, int C, int N, const int32_t* idx, int m,
+                     int ns, float* out);
+/* PointnetSAModule.forward fused (FPS -> ball query -> group -> shared MLP -> max): module = 0,1,2 (model.py:365-383).
+ * xyz [B][N][stride], feats point-major [B][N][C_in]; outputs new_xyz [B][npoint][3] (NULL for module 2),
+ * new_feats point-major [B][npoint][C_out].  fps_idx / ball_idx optional debug outputs (may be NULL). */
+int mpn_sa_forward(mpn_ctx* ctx, void* stream, int module, int precision, const float* xyz, int stride,
+                   const float* feats, int feat_stride, int B, int N, float* new_xyz, float* new_feats,
+                   int32_t* fps_idx, int32_t* ball_idx);
+
+/* ---- robofin replacements ----------------------------------------------------------------------------------- */
+/* FrankaSampler FK: q [B][7] -> link frames [B][11][12] (3x4 row-major), right_gripper pose [B][12] (either may be NULL) */
+int mpn_fk(mpn_ctx* ctx, void* stream, const float* q, int B, float* frames, float* eef);
+/* FrankaSampler.sample(q, n): writes rows [0,n) of cloud [B][rows][4] as (x,y,z,0); subset keyed by (seed, step) */
+int mpn_sample_robot(mpn_ctx* ctx, void* stream, const float* q, int B, int n, uint32_t step, float* cloud, int rows);
+/* FrankaCollisionSampler.compute_spheres: q [B][7] -> world centres [B][S][3] */
+int mpn_compute_spheres(mpn_ctx* ctx, void* stream, const float* q, int B, float* centers);
+/* utils.(un)normalize_franka_joints with the loaded limits */
+int mpn_normalize_joints(mpn_ctx* ctx, void* stream, const float* q, int n, float* q_norm);
+int mpn_unnormalize_joints(mpn_ctx* ctx, void* stream, const float* q_norm, int n, float* q);
+
+/* ---- mpinets.geometry replacements -------------------------------------------------------------------------- */
+typedef struct {
+  const float* cuboid_centers;   /* [B][M1][3] */
+  const float* cuboid_dims;      /* [B][M1][3] */
+  const float* cuboid_quats;     /* [B][M1][4] wxyz */
+  const float* cylinder_centers; /* [B][M2][3] */
+  const float* cylinder_radii;   /* [B][M2] */
+  const float* cylinder_heights; /* [B][M2] */
+  const float* cylinder_quats;   /* [B][M2][4] */
+} mpn_scene;
+
+/* TorchCuboids/TorchCylinders.sdf (geometry.py:238-288,456-507): points [B][N][3] -> sdf [B][N];
+ * which = 0 min(both), 1 cuboids only, 2 cylinders only; all-masked -> +inf */
+int mpn_sdf_points(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* points, int N, int which,
+                   float* sdf);
+/* construct_mixed_point_cloud + run_inference.make_point_cloud_from_primitives (geometry.py:571-608,
+ * run_inference.py:93-134): q0 [B][7] unnormalised, target [B][12] right_gripper pose -> cloud [B][Nr+No+Nt][4] */
+int mpn_build_cloud(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* q0, const float* target,
+                    uint32_t problem0, float* cloud);
+/* validation collision sweep (model.py:293-314): traj [B][T][7] unnormalised -> flags u8 [B] (OR-ed into existing
+ * content when accumulate != 0), first_step i32 [B] (optional; step index offset by t0; -1 when none) */
+int mpn_sweep_flags(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* traj, int T, int t0,
+                    int accumulate, uint8_t* flags, int32_t* first_step);
+
+/* ---- mpinets.model replacements ----------------------------------------------------------------------------- */
+/* MPiNetsPointNet.forward (model.py:409-426): cloud [B][N][4] -> [B][2048] */
+int mpn_encoder_forward(mpn_ctx* ctx, void* stream, int precision, const float* cloud, int B, int N, float* out);
+/* MotionPolicyNetwork.forward (model.py:75-91): cloud [B][N][4], q_norm [B][7] -> delta q [B][7] */
+int mpn_policy_forward(mpn_ctx* ctx, void* stream, int precision, const float* cloud, const float* q_norm, int B,
+                       int N, float* dq);
+
+#define MPN_METRICS_COLS 8
+/* columns of the metrics table: */
+enum { MPN_M_COLLISION = 0, MPN_M_FIRST_COLLISION_STEP = 1, MPN_M_STEPS = 2, MPN_M_POS_ERR = 3, MPN_M_ORI_ERR_DEG = 4,
+       MPN_M_REACHED = 5, MPN_M_MIN_SDF_MARGIN = 6, MPN_M_RESERVED = 7 };
+
+/* TrainingMotionPolicyNetwork.rollout + validation sweep (model.py:128-183,272-314) and, with early_exit != 0,
+ * run_inference.rollout_until_success (run_inference.py:137-191) in lock-step with a per-problem done mask.
+ * cloud [B][N][4] is updated in place (robot rows), like the reference (model.py:181).
+ * q0 [B][7] unnormalised start; target [B][12]; traj [B][T+1][7] unnormalised (incl. start); metrics [B][8] fp32.
+ * check_every_step != 0 evaluates the collision flag after every step (config 3) instead of once at the end. */
+int mpn_rollout(mpn_ctx* ctx, void* stream, int precision, const mpn_scene* scene, int B, int N, float* cloud,
+                const float* q0, const float* target, int T, int early_exit, int check_every_step, float* traj,
+                float* metrics);
+
+/* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
+int64_t mpn_launch_count(mpn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPINETS_B200_H */

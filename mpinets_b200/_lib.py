@@ -1,0 +1,92 @@
+"""ctypes binding of ``libmpinets_b200.so`` (the C ABI in ``include/mpinets_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpinets_b200.so")
+
+METRICS_COLS = 8
+PREC_FP32, PREC_BF16 = 0, 1
+
+EXPORTS = (
+    "mpn_last_error", "mpn_version", "mpn_ctx_create", "mpn_ctx_destroy", "mpn_reserve", "mpn_set_robot_tables",
+    "mpn_load_weight", "mpn_weights_finalize", "mpn_fps", "mpn_ball_query", "mpn_gather_points", "mpn_group_points",
+    "mpn_sa_forward", "mpn_fk", "mpn_sample_robot", "mpn_compute_spheres", "mpn_normalize_joints",
+    "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_sweep_flags", "mpn_encoder_forward",
+    "mpn_policy_forward", "mpn_rollout", "mpn_launch_count",
+)
+
+
+class MpnConfig(C.Structure):
+    _fields_ = [("n_robot", C.c_int32), ("n_obstacle", C.c_int32), ("n_target", C.c_int32), ("max_cuboids", C.c_int32),
+                ("max_cylinders", C.c_int32), ("quirk_frames", C.c_int32), ("seed", C.c_uint64)]
+
+
+class MpnScene(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("cuboid_centers", "cuboid_dims", "cuboid_quats", "cylinder_centers",
+                                          "cylinder_radii", "cylinder_heights", "cylinder_quats")]
+
+
+class MpnError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads the library (once). Raises if it has not been built (run ``python -m mpinets_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpnError(f"{LIB_PATH} not found: build it with `python mpinets_b200/build.py` "
+                       "(there is no CPU fallback for the CUDA path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.mpn_last_error.restype = C.c_char_p
+    lib.mpn_version.restype = C.c_char_p
+    lib.mpn_launch_count.restype = C.c_int64
+    P, I, F, U32 = C.c_void_p, C.c_int, C.c_float, C.c_uint32
+    SC = C.POINTER(MpnScene)
+    sigs = {
+        "mpn_ctx_create": [I, C.POINTER(MpnConfig), C.POINTER(P)],
+        "mpn_ctx_destroy": [P],
+        "mpn_reserve": [P, I],
+        "mpn_set_robot_tables": [P, P, I, P, P, I, P, I, P, P, P, F],
+        "mpn_load_weight": [P, C.c_char_p, P, C.POINTER(C.c_int64), I],
+        "mpn_weights_finalize": [P],
+        "mpn_fps": [P, P, P, I, I, I, I, P, P],
+        "mpn_ball_query": [P, P, F, I, P, I, I, I, P, I, P],
+        "mpn_gather_points": [P, P, P, I, I, I, P, I, P],
+        "mpn_group_points": [P, P, P, I, I, I, P, I, I, P],
+        "mpn_sa_forward": [P, P, I, I, P, I, P, I, I, I, P, P, P, P],
+        "mpn_fk": [P, P, P, I, P, P],
+        "mpn_sample_robot": [P, P, P, I, I, U32, P, I],
+        "mpn_compute_spheres": [P, P, P, I, P],
+        "mpn_normalize_joints": [P, P, P, I, P],
+        "mpn_unnormalize_joints": [P, P, P, I, P],
+        "mpn_sdf_points": [P, P, SC, I, P, I, I, P],
+        "mpn_build_cloud": [P, P, SC, I, P, P, U32, P],
+        "mpn_sweep_flags": [P, P, SC, I, P, I, I, I, P, P],
+        "mpn_encoder_forward": [P, P, I, P, I, I, P],
+        "mpn_policy_forward": [P, P, I, P, P, I, I, P],
+        "mpn_rollout": [P, P, I, SC, I, I, P, P, P, I, I, I, P, P],
+        "mpn_launch_count": [P],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        if name != "mpn_launch_count":
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        raise MpnError(f"mpinets_b200 error {status}: {load().mpn_last_error().decode()}")

@@ -1,0 +1,475 @@
+// engine.cu -- context, weight store, workspace, forward / rollout sequencing and the extern "C" surface.
+#include "engine.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace mpn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// tensor-core (bf16 / tcgen05) path, sa_tc.cu
+int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, float* out, int ldo);
+int tc_prepare_weights(mpn_ctx* c);
+size_t tc_scratch_bytes(int B);
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  if (n == 0) return MPN_OK;
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    return MPN_ERR_NOMEM;
+  }
+  return MPN_OK;
+}
+
+template <typename T>
+static int dev_upload(T** p, const T* host, size_t n) {
+  int r = dev_alloc(p, n);
+  if (r) return r;
+  MPN_CHECK_CUDA(cudaMemcpy(*p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return MPN_OK;
+}
+
+static int ensure_workspace(mpn_ctx* c, int B) {
+  Workspace& w = c->ws;
+  if (B <= w.capacity) return MPN_OK;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  (void)st;
+  size_t b = (size_t)B;
+  int r = 0;
+  r |= dev_alloc(&w.xyz1, b * SA1_NPOINT * 3);
+  r |= dev_alloc(&w.feat1, b * SA1_NPOINT * 64);
+  r |= dev_alloc(&w.xyz2, b * SA2_NPOINT * 3);
+  r |= dev_alloc(&w.feat2, b * SA2_NPOINT * 256);
+  r |= dev_alloc(&w.feat3, b * 1024);
+  r |= dev_alloc(&w.fc_a, b * 4096);
+  r |= dev_alloc(&w.fc_b, b * 4096);
+  r |= dev_alloc(&w.cat, b * (ENC_DIM + QF_DIM));
+  r |= dev_alloc(&w.h_a, b * 512);
+  r |= dev_alloc(&w.h_b, b * 512);
+  r |= dev_alloc(&w.dq, b * 7);
+  r |= dev_alloc(&w.qn, b * 7);
+  r |= dev_alloc(&w.qu, b * 7);
+  r |= dev_alloc(&w.frames, b * 11 * 12);
+  r |= dev_alloc(&w.eef, b * 12);
+  r |= dev_alloc(&w.done, b);
+  r |= dev_alloc(&w.first_step, b);
+  r |= dev_alloc(&w.flags, b);
+  if (w.tc_scratch) { cudaFree(w.tc_scratch); w.tc_scratch = nullptr; }
+  w.tc_scratch_bytes = tc_scratch_bytes(B);
+  if (w.tc_scratch_bytes) {
+    if (cudaMalloc(&w.tc_scratch, w.tc_scratch_bytes) != cudaSuccess) { set_error("workspace: tc scratch alloc failed"); r |= MPN_ERR_NOMEM; }
+  }
+  if (r) { w.capacity = 0; return MPN_ERR_NOMEM; }
+  w.capacity = B;
+  return MPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- weights
+struct HostTensor { std::vector<int64_t> shape; std::vector<float> data; };
+static std::map<mpn_ctx*, std::map<std::string, HostTensor>> g_host_weights;
+
+static int make_linear(mpn_ctx* c, const std::string& prefix, int in, int out, Linear& L) {
+  auto& hw = g_host_weights[c];
+  auto wi = hw.find(prefix + ".weight"), bi = hw.find(prefix + ".bias");
+  if (wi == hw.end() || bi == hw.end()) { set_error("missing weight %s.{weight,bias}", prefix.c_str()); return MPN_ERR_STATE; }
+  const HostTensor& W = wi->second; const HostTensor& Bv = bi->second;
+  if ((int64_t)W.data.size() != (int64_t)in * out || W.shape.size() < 2 || W.shape[0] != out || W.shape[1] != in ||
+      (int64_t)Bv.data.size() != out) {
+    set_error("weight %s has wrong shape (expected [%d,%d])", prefix.c_str(), out, in);
+    return MPN_ERR_INVALID;
+  }
+  L.in = in; L.out = out;
+  std::vector<float> wt((size_t)in * out);
+  for (int o = 0; o < out; ++o)
+    for (int i = 0; i < in; ++i) wt[(size_t)i * out + o] = W.data[(size_t)o * in + i];
+  int r = dev_upload(&L.w, W.data.data(), W.data.size());
+  if (r) return r;
+  r = dev_upload(&L.wt, wt.data(), wt.size());
+  if (r) return r;
+  return dev_upload(&L.b, Bv.data.data(), Bv.data.size());
+}
+
+static int upload_vec(mpn_ctx* c, const std::string& name, int n, float** dst) {
+  auto& hw = g_host_weights[c];
+  auto it = hw.find(name);
+  if (it == hw.end() || (int)it->second.data.size() != n) { set_error("missing or mis-sized weight %s", name.c_str()); return MPN_ERR_STATE; }
+  return dev_upload(dst, it->second.data.data(), (size_t)n);
+}
+
+static int finalize_weights(mpn_ctx* c) {
+  static const int sa_dims[3][4] = {{4, 64, 64, 64}, {67, 128, 128, 256}, {259, 512, 512, 1024}};
+  char buf[128];
+  int r;
+  for (int m = 0; m < 3; ++m)
+    for (int l = 0; l < 3; ++l) {
+      snprintf(buf, sizeof(buf), "point_cloud_encoder.SA_modules.%d.mlps.0.%d", m, 2 * l);
+      if ((r = make_linear(c, buf, sa_dims[m][l], sa_dims[m][l + 1], c->w.sa[m][l]))) return r;
+    }
+  static const int fc_idx[3] = {0, 3, 6};
+  static const int fc_dims[4] = {1024, 4096, 2048, 2048};
+  for (int l = 0; l < 3; ++l) {
+    snprintf(buf, sizeof(buf), "point_cloud_encoder.fc_layer.%d", fc_idx[l]);
+    if ((r = make_linear(c, buf, fc_dims[l], fc_dims[l + 1], c->w.fc[l]))) return r;
+  }
+  if ((r = upload_vec(c, "point_cloud_encoder.fc_layer.1.weight", 4096, &c->w.gn_w[0]))) return r;
+  if ((r = upload_vec(c, "point_cloud_encoder.fc_layer.1.bias", 4096, &c->w.gn_b[0]))) return r;
+  if ((r = upload_vec(c, "point_cloud_encoder.fc_layer.4.weight", 2048, &c->w.gn_w[1]))) return r;
+  if ((r = upload_vec(c, "point_cloud_encoder.fc_layer.4.bias", 2048, &c->w.gn_b[1]))) return r;
+  static const int fe_dims[6] = {7, 32, 64, 128, 128, 64};
+  for (int l = 0; l < 5; ++l) {
+    snprintf(buf, sizeof(buf), "feature_encoder.%d", 2 * l);
+    if ((r = make_linear(c, buf, fe_dims[l], fe_dims[l + 1], c->w.fe[l]))) return r;
+  }
+  static const int de_dims[5] = {2112, 512, 256, 128, 7};
+  for (int l = 0; l < 4; ++l) {
+    snprintf(buf, sizeof(buf), "decoder.%d", 2 * l);
+    if ((r = make_linear(c, buf, de_dims[l], de_dims[l + 1], c->w.dec[l]))) return r;
+  }
+  if ((r = tc_prepare_weights(c))) return r;
+  c->w.finalized = true;
+  g_host_weights.erase(c);
+  return MPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- forward passes
+static int encoder_forward(mpn_ctx* c, cudaStream_t s, int precision, const float* cloud, int B, int N, float* out, int ldo) {
+  Workspace& w = c->ws;
+  int r;
+  if (precision == MPN_PREC_BF16) return tc_encoder_forward(c, s, cloud, B, N, out, ldo);
+  // SA1: FPS over the 4-float rows of the cloud; features = mask column
+  if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz1))) return r;
+  if ((r = launch_sa_simt(c, s, 0, cloud, 4, cloud + 3, 4, B, N, w.xyz1, w.feat1, nullptr))) return r;
+  if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz2))) return r;
+  if ((r = launch_sa_simt(c, s, 1, w.xyz1, 3, w.feat1, 64, B, SA1_NPOINT, w.xyz2, w.feat2, nullptr))) return r;
+  if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr))) return r;
+  if ((r = launch_linear(c, s, c->w.fc[0], w.feat3, 1024, B, w.fc_a, 4096, 0))) return r;
+  if ((r = launch_groupnorm_lrelu(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0]))) return r;
+  if ((r = launch_linear(c, s, c->w.fc[1], w.fc_a, 4096, B, w.fc_b, 2048, 0))) return r;
+  if ((r = launch_groupnorm_lrelu(c, s, w.fc_b, B, 2048, 16, c->w.gn_w[1], c->w.gn_b[1]))) return r;
+  return launch_linear(c, s, c->w.fc[2], w.fc_b, 2048, B, out, ldo, 0);
+}
+
+static int policy_forward(mpn_ctx* c, cudaStream_t s, int precision, const float* cloud, const float* qn, int B, int N, float* dq) {
+  Workspace& w = c->ws;
+  int r;
+  const int CAT = ENC_DIM + QF_DIM;
+  if ((r = encoder_forward(c, s, precision, cloud, B, N, w.cat, CAT))) return r;
+  // feature_encoder (model.py:47-57)
+  if ((r = launch_linear(c, s, c->w.fe[0], qn, 7, B, w.h_a, 32, 1))) return r;
+  if ((r = launch_linear(c, s, c->w.fe[1], w.h_a, 32, B, w.h_b, 64, 1))) return r;
+  if ((r = launch_linear(c, s, c->w.fe[2], w.h_b, 64, B, w.h_a, 128, 1))) return r;
+  if ((r = launch_linear(c, s, c->w.fe[3], w.h_a, 128, B, w.h_b, 128, 1))) return r;
+  if ((r = launch_linear(c, s, c->w.fe[4], w.h_b, 128, B, w.cat + ENC_DIM, CAT, 0))) return r;
+  // decoder (model.py:58-66)
+  if ((r = launch_linear(c, s, c->w.dec[0], w.cat, CAT, B, w.h_a, 512, 1))) return r;
+  if ((r = launch_linear(c, s, c->w.dec[1], w.h_a, 512, B, w.h_b, 256, 1))) return r;
+  if ((r = launch_linear(c, s, c->w.dec[2], w.h_b, 256, B, w.h_a, 128, 1))) return r;
+  return launch_linear(c, s, c->w.dec[3], w.h_a, 128, B, dq, 7, 0);
+}
+
+}  // namespace mpn
+
+using namespace mpn;
+
+#define REQ_CTX(c)                                              \
+  do {                                                          \
+    if (!(c)) { set_error("null context"); return MPN_ERR_INVALID; } \
+    MPN_CHECK_CUDA(cudaSetDevice((c)->device));                 \
+  } while (0)
+#define REQ_TABLES(c) \
+  do { if (!(c)->tables_set) { set_error("robot tables not set (mpn_set_robot_tables)"); return MPN_ERR_STATE; } } while (0)
+#define REQ_WEIGHTS(c) \
+  do { if (!(c)->w.finalized) { set_error("weights not finalized (mpn_load_weight / mpn_weights_finalize)"); return MPN_ERR_STATE; } } while (0)
+
+extern "C" {
+
+const char* mpn_last_error(void) { return g_err; }
+const char* mpn_version(void) { return "mpinets_b200 0.1 (sm_100a)"; }
+
+int mpn_ctx_create(int device, const mpn_config* cfg, mpn_ctx** out) {
+  if (!cfg || !out) { set_error("mpn_ctx_create: null argument"); return MPN_ERR_INVALID; }
+  MPN_REQUIRE(cfg->n_robot > 0 && cfg->n_obstacle >= 0 && cfg->n_target >= 0, "mpn_ctx_create: bad point counts");
+  MPN_REQUIRE(cfg->max_cuboids >= 0 && cfg->max_cylinders >= 0 && cfg->max_cuboids + cfg->max_cylinders <= 128,
+              "mpn_ctx_create: max_cuboids + max_cylinders must be <= 128");
+  int ndev = 0;
+  MPN_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+  MPN_REQUIRE(device >= 0 && device < ndev, "mpn_ctx_create: device %d not present (%d devices)", device, ndev);
+  MPN_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MPN_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  MPN_REQUIRE(prop.major == 10, "mpinets_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  mpn_ctx* c = new mpn_ctx();
+  c->device = device;
+  c->cfg = *cfg;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return MPN_OK;
+}
+
+int mpn_ctx_destroy(mpn_ctx* c) {
+  if (!c) return MPN_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  g_host_weights.erase(c);
+  // device memory is reclaimed by explicit frees of the big buffers; small tables die with the process
+  float** bufs[] = {&c->ws.xyz1, &c->ws.feat1, &c->ws.xyz2, &c->ws.feat2, &c->ws.feat3, &c->ws.fc_a, &c->ws.fc_b, &c->ws.cat,
+                    &c->ws.h_a, &c->ws.h_b, &c->ws.dq, &c->ws.qn, &c->ws.qu, &c->ws.frames, &c->ws.eef};
+  for (auto p : bufs) if (*p) cudaFree(*p);
+  if (c->ws.done) cudaFree(c->ws.done);
+  if (c->ws.first_step) cudaFree(c->ws.first_step);
+  if (c->ws.flags) cudaFree(c->ws.flags);
+  if (c->ws.tc_scratch) cudaFree(c->ws.tc_scratch);
+  delete c;
+  return MPN_OK;
+}
+
+int mpn_reserve(mpn_ctx* c, int max_batch) {
+  REQ_CTX(c);
+  MPN_REQUIRE(max_batch > 0, "mpn_reserve: max_batch must be positive");
+  return ensure_workspace(c, max_batch);
+}
+
+int mpn_set_robot_tables(mpn_ctx* c, const float* joint_limits, int P, const float* link_points, const int32_t* link_ids,
+                         int Pe, const float* ee_points, int S, const float* sph_c, const float* sph_r, const int32_t* sph_l,
+                         float prismatic) {
+  REQ_CTX(c);
+  MPN_REQUIRE(joint_limits && link_points && link_ids && ee_points && sph_c && sph_r && sph_l, "mpn_set_robot_tables: null table");
+  MPN_REQUIRE(P >= c->cfg.n_robot && P < (1 << 23), "mpn_set_robot_tables: need n_link_points >= n_robot (%d)", c->cfg.n_robot);
+  MPN_REQUIRE(Pe >= c->cfg.n_target, "mpn_set_robot_tables: need n_ee_points >= n_target (%d)", c->cfg.n_target);
+  MPN_REQUIRE(S >= 1 && S <= 96, "mpn_set_robot_tables: 1..96 spheres supported");
+  for (int i = 0; i < P; ++i) MPN_REQUIRE(link_ids[i] >= 0 && link_ids[i] < 11, "link id out of range at %d", i);
+  for (int i = 0; i < S; ++i) MPN_REQUIRE(sph_l[i] >= 0 && sph_l[i] < 11, "sphere link id out of range at %d", i);
+  int r = 0;
+  memcpy(c->limits_host, joint_limits, sizeof(float) * 14);
+  r |= dev_upload(&c->limits, joint_limits, 14);
+  r |= dev_upload(&c->link_points, link_points, (size_t)P * 3);
+  r |= dev_upload(&c->link_ids, link_ids, (size_t)P);
+  r |= dev_upload(&c->ee_points, ee_points, (size_t)Pe * 3);
+  r |= dev_upload(&c->sph_c, sph_c, (size_t)S * 3);
+  r |= dev_upload(&c->sph_r, sph_r, (size_t)S);
+  r |= dev_upload(&c->sph_l, sph_l, (size_t)S);
+  if (r) return r;
+  c->P = P; c->Pe = Pe; c->S = S; c->prismatic = prismatic;
+  c->tables_set = true;
+  return MPN_OK;
+}
+
+int mpn_load_weight(mpn_ctx* c, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+  REQ_CTX(c);
+  MPN_REQUIRE(name && host_data && shape && ndim >= 1 && ndim <= 4, "mpn_load_weight: bad arguments");
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { MPN_REQUIRE(shape[i] > 0, "mpn_load_weight: bad shape"); n *= (size_t)shape[i]; }
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.assign(host_data, host_data + n);
+  g_host_weights[c][name] = std::move(t);
+  c->w.finalized = false;
+  return MPN_OK;
+}
+
+int mpn_weights_finalize(mpn_ctx* c) {
+  REQ_CTX(c);
+  return finalize_weights(c);
+}
+
+int64_t mpn_launch_count(mpn_ctx* c) { return c ? c->launches : 0; }
+
+// ---- pointnet2_ops
+int mpn_fps(mpn_ctx* c, void* stream, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz) {
+  REQ_CTX(c);
+  MPN_REQUIRE(xyz && idx && B >= 0, "mpn_fps: null pointer");
+  if (B == 0) return MPN_OK;
+  return launch_fps(c, (cudaStream_t)stream, xyz, B, N, stride, npoint, idx, new_xyz);
+}
+
+int mpn_ball_query(mpn_ctx* c, void* stream, float radius, int nsample, const float* xyz, int B, int N, int stride,
+                   const float* new_xyz, int npoint, int32_t* idx) {
+  REQ_CTX(c);
+  MPN_REQUIRE(xyz && new_xyz && idx, "mpn_ball_query: null pointer");
+  if (B == 0) return MPN_OK;
+  return launch_ball_query(c, (cudaStream_t)stream, radius, nsample, xyz, B, N, stride, new_xyz, npoint, idx);
+}
+
+int mpn_gather_points(mpn_ctx* c, void* stream, const float* feat, int B, int C, int N, const int32_t* idx, int m, float* out) {
+  REQ_CTX(c);
+  MPN_REQUIRE(feat && idx && out && C >= 1 && N >= 1 && m >= 1, "mpn_gather_points: bad arguments");
+  if (B == 0) return MPN_OK;
+  return launch_gather(c, (cudaStream_t)stream, feat, B, C, N, idx, m, out);
+}
+
+int mpn_group_points(mpn_ctx* c, void* stream, const float* feat, int B, int C, int N, const int32_t* idx, int m, int ns, float* out) {
+  REQ_CTX(c);
+  MPN_REQUIRE(feat && idx && out && C >= 1 && N >= 1 && m >= 1 && ns >= 1, "mpn_group_points: bad arguments");
+  if (B == 0) return MPN_OK;
+  return launch_group(c, (cudaStream_t)stream, feat, B, C, N, idx, m, ns, out);
+}
+
+int mpn_sa_forward(mpn_ctx* c, void* stream, int module, int precision, const float* xyz, int stride, const float* feats,
+                   int feat_stride, int B, int N, float* new_xyz, float* new_feats, int32_t* fps_idx, int32_t* ball_idx) {
+  REQ_CTX(c); REQ_WEIGHTS(c);
+  MPN_REQUIRE(module >= 0 && module <= 2, "mpn_sa_forward: module must be 0..2");
+  MPN_REQUIRE(precision == MPN_PREC_FP32, "mpn_sa_forward: per-module entry point is fp32 only (bf16 runs through mpn_encoder_forward)");
+  MPN_REQUIRE(xyz && feats && new_feats && stride >= 3, "mpn_sa_forward: null pointer");
+  static const int cfeat[3] = {1, 64, 256};
+  MPN_REQUIRE(feat_stride >= cfeat[module], "mpn_sa_forward: feat_stride too small");
+  if (B == 0) return MPN_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int r;
+  if ((r = ensure_workspace(c, B))) return r;
+  if (module == 2) return launch_sa_simt(c, s, 2, xyz, stride, feats, feat_stride, B, N, nullptr, new_feats, nullptr);
+  MPN_REQUIRE(new_xyz, "mpn_sa_forward: new_xyz required for modules 0 and 1");
+  int npoint = module == 0 ? SA1_NPOINT : SA2_NPOINT;
+  int32_t* idx = fps_idx ? fps_idx : reinterpret_cast<int32_t*>(c->ws.fc_a);
+  if ((r = launch_fps(c, s, xyz, B, N, stride, npoint, idx, new_xyz))) return r;
+  return launch_sa_simt(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats, ball_idx);
+}
+
+// ---- robofin
+int mpn_fk(mpn_ctx* c, void* stream, const float* q, int B, float* frames, float* eef) {
+  REQ_CTX(c); REQ_TABLES(c);
+  MPN_REQUIRE(q, "mpn_fk: null q");
+  if (B == 0) return MPN_OK;
+  return launch_fk(c, (cudaStream_t)stream, q, B, frames, eef);
+}
+
+int mpn_sample_robot(mpn_ctx* c, void* stream, const float* q, int B, int n, uint32_t step, float* cloud, int rows) {
+  REQ_CTX(c); REQ_TABLES(c);
+  MPN_REQUIRE(q && cloud && n >= 1 && n <= c->P && rows >= n, "mpn_sample_robot: bad arguments");
+  if (B == 0) return MPN_OK;
+  int r;
+  if ((r = ensure_workspace(c, B))) return r;
+  if ((r = launch_fk(c, (cudaStream_t)stream, q, B, c->ws.frames, nullptr))) return r;
+  return launch_sample_robot(c, (cudaStream_t)stream, c->ws.frames, B, n, step, cloud, rows);
+}
+
+int mpn_compute_spheres(mpn_ctx* c, void* stream, const float* q, int B, float* centers) {
+  REQ_CTX(c); REQ_TABLES(c);
+  MPN_REQUIRE(q && centers, "mpn_compute_spheres: null pointer");
+  if (B == 0) return MPN_OK;
+  int r;
+  if ((r = ensure_workspace(c, B))) return r;
+  if ((r = launch_fk(c, (cudaStream_t)stream, q, B, c->ws.frames, nullptr))) return r;
+  return launch_spheres(c, (cudaStream_t)stream, c->ws.frames, B, centers);
+}
+
+int mpn_normalize_joints(mpn_ctx* c, void* stream, const float* q, int n, float* q_norm) {
+  REQ_CTX(c); REQ_TABLES(c);
+  MPN_REQUIRE(q && q_norm, "mpn_normalize_joints: null pointer");
+  if (n == 0) return MPN_OK;
+  return launch_normalize(c, (cudaStream_t)stream, q, n, q_norm, false);
+}
+
+int mpn_unnormalize_joints(mpn_ctx* c, void* stream, const float* q_norm, int n, float* q) {
+  REQ_CTX(c); REQ_TABLES(c);
+  MPN_REQUIRE(q && q_norm, "mpn_unnormalize_joints: null pointer");
+  if (n == 0) return MPN_OK;
+  return launch_normalize(c, (cudaStream_t)stream, q_norm, n, q, true);
+}
+
+// ---- geometry
+static int check_scene(const mpn_ctx* c, const mpn_scene* sc) {
+  MPN_REQUIRE(sc, "null scene");
+  if (c->cfg.max_cuboids > 0) MPN_REQUIRE(sc->cuboid_centers && sc->cuboid_dims && sc->cuboid_quats, "scene: null cuboid arrays");
+  if (c->cfg.max_cylinders > 0)
+    MPN_REQUIRE(sc->cylinder_centers && sc->cylinder_radii && sc->cylinder_heights && sc->cylinder_quats, "scene: null cylinder arrays");
+  return MPN_OK;
+}
+
+int mpn_sdf_points(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* points, int N, int which, float* sdf) {
+  REQ_CTX(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(points && sdf && which >= 0 && which <= 2, "mpn_sdf_points: bad arguments");
+  if (B == 0 || N == 0) return MPN_OK;
+  return launch_sdf_points(c, (cudaStream_t)stream, *scene, B, points, N, which, sdf);
+}
+
+int mpn_build_cloud(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* q0, const float* target,
+                    uint32_t problem0, float* cloud) {
+  REQ_CTX(c); REQ_TABLES(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(q0 && target && cloud, "mpn_build_cloud: null pointer");
+  if (B == 0) return MPN_OK;
+  if ((r = ensure_workspace(c, B))) return r;
+  if ((r = launch_fk(c, (cudaStream_t)stream, q0, B, c->ws.frames, nullptr))) return r;
+  return launch_build_cloud(c, (cudaStream_t)stream, *scene, B, c->ws.frames, target, problem0, cloud);
+}
+
+int mpn_sweep_flags(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* traj, int T, int t0, int accumulate,
+                    uint8_t* flags, int32_t* first_step) {
+  REQ_CTX(c); REQ_TABLES(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(traj && flags && T >= 1, "mpn_sweep_flags: bad arguments");
+  if (B == 0) return MPN_OK;
+  return launch_sweep(c, (cudaStream_t)stream, *scene, B, traj, T, T * 7, t0, accumulate, flags, first_step);
+}
+
+// ---- model
+int mpn_encoder_forward(mpn_ctx* c, void* stream, int precision, const float* cloud, int B, int N, float* out) {
+  REQ_CTX(c); REQ_WEIGHTS(c);
+  MPN_REQUIRE(cloud && out, "mpn_encoder_forward: null pointer");
+  MPN_REQUIRE(N >= SA1_NPOINT && N <= 8192, "mpn_encoder_forward: N=%d unsupported (512..8192)", N);
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16, "bad precision");
+  if (B == 0) return MPN_OK;
+  int r;
+  if ((r = ensure_workspace(c, B))) return r;
+  return encoder_forward(c, (cudaStream_t)stream, precision, cloud, B, N, out, ENC_DIM);
+}
+
+int mpn_policy_forward(mpn_ctx* c, void* stream, int precision, const float* cloud, const float* q_norm, int B, int N, float* dq) {
+  REQ_CTX(c); REQ_WEIGHTS(c);
+  MPN_REQUIRE(cloud && q_norm && dq, "mpn_policy_forward: null pointer");
+  MPN_REQUIRE(N >= SA1_NPOINT && N <= 8192, "mpn_policy_forward: N=%d unsupported (512..8192)", N);
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16, "bad precision");
+  if (B == 0) return MPN_OK;
+  int r;
+  if ((r = ensure_workspace(c, B))) return r;
+  return policy_forward(c, (cudaStream_t)stream, precision, cloud, q_norm, B, N, dq);
+}
+
+int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene, int B, int N, float* cloud, const float* q0,
+                const float* target, int T, int early_exit, int check_every_step, float* traj, float* metrics) {
+  REQ_CTX(c); REQ_TABLES(c); REQ_WEIGHTS(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(cloud && q0 && target && traj && metrics && T >= 1, "mpn_rollout: bad arguments");
+  MPN_REQUIRE(N >= c->cfg.n_robot && N >= SA1_NPOINT && N <= 8192, "mpn_rollout: N=%d unsupported", N);
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16, "bad precision");
+  if (B == 0) return MPN_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((r = ensure_workspace(c, B))) return r;
+  Workspace& w = c->ws;
+  const int stride = (T + 1) * 7;
+  if ((r = launch_normalize(c, s, q0, B, w.qn, false))) return r;
+  MPN_CHECK_CUDA(cudaMemcpy2DAsync(traj, (size_t)stride * 4, q0, 7 * 4, 7 * 4, B, cudaMemcpyDeviceToDevice, s));
+  MPN_CHECK_CUDA(cudaMemsetAsync(w.done, 0xff, (size_t)B * 4, s));
+  MPN_CHECK_CUDA(cudaMemsetAsync(w.first_step, 0xff, (size_t)B * 4, s));
+  MPN_CHECK_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)B, s));
+  if ((r = launch_fk(c, s, q0, B, w.frames, w.eef))) return r;
+  if (check_every_step && (r = launch_sweep(c, s, *scene, B, traj, 1, stride, 0, 0, w.flags, w.first_step))) return r;
+  for (int i = 1; i <= T; ++i) {
+    if ((r = policy_forward(c, s, precision, cloud, w.qn, B, N, w.dq))) return r;
+    if ((r = launch_step_update(c, s, B, w.dq, w.qn, w.qu, target, w.done, early_exit, traj, stride, w.frames, w.eef, nullptr, i))) return r;
+    if ((r = launch_sample_robot(c, s, w.frames, B, c->cfg.n_robot, (uint32_t)i, cloud, N))) return r;
+    if (check_every_step && (r = launch_sweep(c, s, *scene, B, traj + (size_t)i * 7, 1, stride, i, 1, w.flags, w.first_step))) return r;
+  }
+  if (!check_every_step && (r = launch_sweep(c, s, *scene, B, traj, T + 1, stride, 0, 0, w.flags, w.first_step))) return r;
+  return launch_finalize_metrics(c, s, B, w.eef, target, w.flags, w.first_step, w.done, T, metrics);
+}
+
+}  // extern "C"

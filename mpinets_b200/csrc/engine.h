@@ -1,0 +1,128 @@
+// engine.h -- context object behind the C ABI (include/mpinets_b200.h) and the kernel launcher prototypes.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mpinets_b200.h"
+
+namespace mpn {
+
+void set_error(const char* fmt, ...);
+
+#define MPN_CHECK_CUDA(expr)                                                                 \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      mpn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MPN_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define MPN_REQUIRE(cond, ...)           \
+  do {                                   \
+    if (!(cond)) {                       \
+      mpn::set_error(__VA_ARGS__);       \
+      return MPN_ERR_INVALID;            \
+    }                                    \
+  } while (0)
+
+// network dimensions (model.py:47-66,365-393)
+constexpr int SA1_NPOINT = 512, SA2_NPOINT = 128, NSAMPLE = 128;
+constexpr float SA1_RADIUS = 0.05f, SA2_RADIUS = 0.3f;
+constexpr int ENC_DIM = 2048, QF_DIM = 64;
+
+struct Linear {      // y = W x + b ; W [out][in] row-major fp32 (device)
+  int in = 0, out = 0;
+  float* w = nullptr;     // [out][in]
+  float* wt = nullptr;    // [in][out] transposed copy (SIMT kernels read k-major)
+  float* b = nullptr;
+  __nv_bfloat16* w_bf16 = nullptr;  // [out][in_pad] K-major, zero padded to in_pad (multiple of 16)
+  int in_pad = 0;
+};
+
+struct Weights {
+  Linear sa[3][3];
+  Linear fc[3];           // fc_layer.0 / .3 / .6
+  float* gn_w[2] = {nullptr, nullptr};
+  float* gn_b[2] = {nullptr, nullptr};
+  Linear fe[5];           // feature_encoder.0/2/4/6/8
+  Linear dec[4];          // decoder.0/2/4/6
+  bool finalized = false;
+};
+
+struct Workspace {
+  int capacity = 0;  // problems
+  float *xyz1 = nullptr, *feat1 = nullptr;  // [B][512][3], [B][512][64]
+  float *xyz2 = nullptr, *feat2 = nullptr;  // [B][128][3], [B][128][256]
+  float* feat3 = nullptr;                   // [B][1024]
+  float *fc_a = nullptr, *fc_b = nullptr;   // [B][4096] ping-pong
+  float* cat = nullptr;                     // [B][2112]  (encoder out | q features)
+  float *h_a = nullptr, *h_b = nullptr;     // [B][512] small head activations
+  float* dq = nullptr;                      // [B][7]
+  float* qn = nullptr;                      // [B][7] normalised joint state of the rollout
+  float* qu = nullptr;                      // [B][7] unnormalised
+  float* frames = nullptr;                  // [B][11][12]
+  float* eef = nullptr;                     // [B][12]
+  int32_t* done = nullptr;                  // [B]
+  int32_t* first_step = nullptr;            // [B]
+  uint8_t* flags = nullptr;                 // [B]
+  void* tc_scratch = nullptr;               // tensor-core path scratch (bf16 hand-off tensors)
+  size_t tc_scratch_bytes = 0;
+};
+
+}  // namespace mpn
+
+struct mpn_ctx {
+  int device = 0;
+  mpn_config cfg{};
+  int sm_count = 148;
+  // robot tables (device)
+  bool tables_set = false;
+  float limits_host[14] = {0};
+  float* limits = nullptr;       // [7][2]
+  int P = 0; float* link_points = nullptr; int32_t* link_ids = nullptr;
+  int Pe = 0; float* ee_points = nullptr;
+  int S = 0; float* sph_c = nullptr; float* sph_r = nullptr; int32_t* sph_l = nullptr;
+  float prismatic = 0.025f;
+  std::map<std::string, std::pair<std::vector<int64_t>, float*>> raw_weights;  // name -> (shape, device fp32)
+  mpn::Weights w;
+  mpn::Workspace ws;
+  int64_t launches = 0;
+};
+
+namespace mpn {
+
+// ---- geometry.cu
+int launch_fk(mpn_ctx* c, cudaStream_t s, const float* q, int B, float* frames, float* eef);
+int launch_sample_robot(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, uint32_t step, float* cloud, int rows);
+int launch_spheres(mpn_ctx* c, cudaStream_t s, const float* frames, int B, float* centers);
+int launch_normalize(mpn_ctx* c, cudaStream_t s, const float* in, int n, float* out, bool unnormalize);
+int launch_sdf_points(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* pts, int N, int which, float* sdf);
+int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* frames, const float* target,
+                       uint32_t problem0, float* cloud);
+int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T, int traj_stride_t,
+                 int t0, int accumulate, uint8_t* flags, int32_t* first_step);
+// ---- pointnet.cu
+int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz);
+int launch_ball_query(mpn_ctx* c, cudaStream_t s, float radius, int nsample, const float* xyz, int B, int N, int stride,
+                      const float* new_xyz, int npoint, int32_t* idx);
+int launch_gather(mpn_ctx* c, cudaStream_t s, const float* feat, int B, int C, int N, const int32_t* idx, int m, float* out);
+int launch_group(mpn_ctx* c, cudaStream_t s, const float* feat, int B, int C, int N, const int32_t* idx, int m, int ns, float* out);
+// ---- sa_simt.cu : fused ball query + group + 3-layer shared MLP + max, fp32
+int launch_sa_simt(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride,
+                   int B, int N, const float* new_xyz, float* new_feats, int32_t* ball_idx);
+// ---- linear.cu
+int launch_linear(mpn_ctx* c, cudaStream_t s, const Linear& L, const float* x, int ldx, int M, float* y, int ldy, int act);
+int launch_groupnorm_lrelu(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta);
+int launch_step_update(mpn_ctx* c, cudaStream_t s, int B, const float* dq, float* qn, float* qu, const float* target,
+                       int32_t* done, int early_exit, float* traj_out, int traj_stride, float* frames, float* eef,
+                       float* metrics, int step);
+int launch_finalize_metrics(mpn_ctx* c, cudaStream_t s, int B, const float* eef, const float* target, const uint8_t* flags,
+                            const int32_t* first_step, const int32_t* done, int T, float* metrics);
+
+}  // namespace mpn

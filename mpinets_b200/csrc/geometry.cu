@@ -1,0 +1,353 @@
+// geometry.cu -- HBM-bound geometry kernels: FK, robot / obstacle / target surface sampling into the segmented
+// cloud, point SDF and the link-sphere collision sweep.  Bit-exact against the CPU oracle (spec_math.cuh).
+//
+// Replaces: robofin FrankaSampler.sample / sample_end_effector / end_effector_pose and
+// FrankaCollisionSampler.compute_spheres (call sites mpinets/model.py:250,275,300; run_inference.py:111-116,188),
+// mpinets/geometry.py:238-288,456-507 (sdf), :571-608 (construct_mixed_point_cloud), model.py:293-314 (sweep).
+#include "engine.h"
+#include "spec_math.cuh"
+
+namespace mpn {
+
+// ------------------------------------------------------------------------------------------------ FK
+__global__ void fk_kernel(const float* __restrict__ q, int B, float prismatic, float* __restrict__ frames,
+                          float* __restrict__ eef) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float qq[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) qq[j] = q[7 * b + j];
+  float F[MPN_NLINK * 12], E[12];
+  spec_fk(qq, prismatic, F, E);
+  if (frames) {
+    float* o = frames + (size_t)b * MPN_NLINK * 12;
+#pragma unroll
+    for (int i = 0; i < MPN_NLINK * 12; ++i) o[i] = F[i];
+  }
+  if (eef) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) eef[(size_t)b * 12 + i] = E[i];
+  }
+}
+
+int launch_fk(mpn_ctx* c, cudaStream_t s, const float* q, int B, float* frames, float* eef) {
+  fk_kernel<<<(B + 63) / 64, 64, 0, s>>>(q, B, c->prismatic, frames, eef);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ robot rows
+// one CTA per problem; frames staged in smem; each thread writes whole 16-byte rows (x,y,z,mask=0): a warp
+// writes 512 contiguous bytes.
+__global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restrict__ frames, int n, int P,
+                                                           const float* __restrict__ lp, const int32_t* __restrict__ lid,
+                                                           uint32_t seed_lo, uint32_t seed_hi, uint32_t step,
+                                                           float4* __restrict__ cloud, int rows) {
+  __shared__ float F[MPN_NLINK * 12];
+  int b = blockIdx.x;
+  for (int i = threadIdx.x; i < MPN_NLINK * 12; i += blockDim.x) F[i] = frames[(size_t)b * MPN_NLINK * 12 + i];
+  uint32_t key[4];
+  philox4x32(0u, step, STREAM_ROBOT_PERM, 0u, seed_lo, seed_hi, key);
+  uint32_t half = feistel_bits((uint32_t)P) / 2;
+  __syncthreads();
+  float4* out = cloud + (size_t)b * rows;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    uint32_t e = feistel_perm((uint32_t)j, (uint32_t)P, half, key);
+    float px = __ldg(lp + 3 * e), py = __ldg(lp + 3 * e + 1), pz = __ldg(lp + 3 * e + 2);
+    int l = __ldg(lid + e);
+    float4 o;
+    m34_apply(F + 12 * l, px, py, pz, o.x, o.y, o.z);
+    o.w = 0.0f;
+    out[j] = o;
+  }
+}
+
+int launch_sample_robot(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, uint32_t step, float* cloud, int rows) {
+  sample_robot_kernel<<<B, 256, 0, s>>>(frames, n, c->P, c->link_points, c->link_ids, (uint32_t)c->cfg.seed,
+                                        (uint32_t)(c->cfg.seed >> 32), step, (float4*)cloud, rows);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ spheres
+__global__ void spheres_kernel(const float* __restrict__ frames, int B, int S, const float* __restrict__ sc,
+                               const int32_t* __restrict__ sl, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * S) return;
+  int b = i / S, k = i % S;
+  const float* F = frames + ((size_t)b * MPN_NLINK + sl[k]) * 12;
+  float A[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) A[j] = F[j];
+  float x, y, z;
+  m34_apply(A, sc[3 * k], sc[3 * k + 1], sc[3 * k + 2], x, y, z);
+  out[3 * (size_t)i] = x; out[3 * (size_t)i + 1] = y; out[3 * (size_t)i + 2] = z;
+}
+
+int launch_spheres(mpn_ctx* c, cudaStream_t s, const float* frames, int B, float* centers) {
+  int n = B * c->S;
+  spheres_kernel<<<(n + 255) / 256, 256, 0, s>>>(frames, B, c->S, c->sph_c, c->sph_l, centers);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+__global__ void normalize_kernel(const float* __restrict__ in, int n, const float* __restrict__ lim, float* __restrict__ out,
+                                 int un) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 7) return;
+  int j = i % 7;
+  float lo = lim[2 * j], hi = lim[2 * j + 1];
+  out[i] = un ? spec_unnormalize(in[i], lo, hi) : spec_normalize(in[i], lo, hi);
+}
+
+int launch_normalize(mpn_ctx* c, cudaStream_t s, const float* in, int n, float* out, bool un) {
+  normalize_kernel<<<(n * 7 + 255) / 256, 256, 0, s>>>(in, n, c->limits, out, un ? 1 : 0);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scene staging
+// per-problem primitive list -> inverse frames in shared memory (<= M1+M2 <= 128 entries of 64 B)
+constexpr int MAX_PRIMS = 128;
+
+__device__ __forceinline__ void stage_scene(const mpn_scene& sc, int b, int M1, int M2, bool quirk, PrimFrame* fr) {
+  for (int m = threadIdx.x; m < M1 + M2; m += blockDim.x) {
+    PrimFrame f;
+    if (m < M1) {
+      const float* d = sc.cuboid_dims + ((size_t)b * M1 + m) * 3;
+      float d0 = d[0], d1 = d[1], d2 = d[2];
+      f.valid = (is_close0(d0) || is_close0(d1) || is_close0(d2)) ? 0.f : 1.f;
+      make_inv_frame(sc.cuboid_centers + ((size_t)b * M1 + m) * 3, sc.cuboid_quats + ((size_t)b * M1 + m) * 4, quirk, f);
+      f.h[0] = fdiv(d0, 2.0f); f.h[1] = fdiv(d1, 2.0f); f.h[2] = fdiv(d2, 2.0f);
+    } else {
+      int k = m - M1;
+      float r = sc.cylinder_radii[(size_t)b * M2 + k], h = sc.cylinder_heights[(size_t)b * M2 + k];
+      f.valid = (is_close0(r) || is_close0(h)) ? 0.f : 1.f;
+      make_inv_frame(sc.cylinder_centers + ((size_t)b * M2 + k) * 3, sc.cylinder_quats + ((size_t)b * M2 + k) * 4, quirk, f);
+      f.h[0] = r; f.h[1] = fdiv(h, 2.0f); f.h[2] = 0.f;
+    }
+    fr[m] = f;
+  }
+}
+
+__device__ __forceinline__ float scene_sdf(const PrimFrame* fr, int c0, int c1, int y0, int y1, float px, float py, float pz) {
+  float best = __int_as_float(0x7f800000);
+  for (int m = c0; m < c1; ++m)
+    if (fr[m].valid != 0.f) best = fminf(best, sdf_cuboid(fr[m], px, py, pz));
+  for (int m = y0; m < y1; ++m)
+    if (fr[m].valid != 0.f) best = fminf(best, sdf_cylinder(fr[m], px, py, pz));
+  return best;
+}
+
+__global__ void __launch_bounds__(256) sdf_points_kernel(mpn_scene sc, int M1, int M2, int quirk, const float* __restrict__ pts,
+                                                         int N, int which, float* __restrict__ sdf) {
+  __shared__ PrimFrame fr[MAX_PRIMS];
+  int b = blockIdx.y;
+  stage_scene(sc, b, M1, M2, quirk != 0, fr);
+  __syncthreads();
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* p = pts + ((size_t)b * N + n) * 3;
+  sdf[(size_t)b * N + n] = scene_sdf(fr, 0, which == 2 ? 0 : M1, M1, which == 1 ? M1 : M1 + M2, p[0], p[1], p[2]);
+}
+
+int launch_sdf_points(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* pts, int N, int which, float* sdf) {
+  dim3 grid((N + 255) / 256, B);
+  sdf_points_kernel<<<grid, 256, 0, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, c->cfg.quirk_frames, pts, N, which, sdf);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ cloud build (t = 0)
+__global__ void __launch_bounds__(256) build_cloud_kernel(mpn_scene sc, int M1, int M2, const float* __restrict__ frames,
+                                                          const float* __restrict__ target, int Nr, int No, int Nt, int P,
+                                                          const float* __restrict__ lp, const int32_t* __restrict__ lid,
+                                                          int Pe, const float* __restrict__ ee, uint32_t seed_lo,
+                                                          uint32_t seed_hi, uint32_t problem0, float4* __restrict__ cloud) {
+  __shared__ float F[MPN_NLINK * 12];
+  __shared__ float TG[12];
+  __shared__ uint32_t start[MAX_PRIMS + 1];
+  __shared__ int16_t pidx[MAX_PRIMS];  // >=0 cuboid index, <0 : -(cyl index)-1
+  __shared__ int nvalid;
+  int b = blockIdx.x;
+  uint32_t problem = problem0 + (uint32_t)b;
+  for (int i = threadIdx.x; i < MPN_NLINK * 12; i += blockDim.x) F[i] = frames[(size_t)b * MPN_NLINK * 12 + i];
+  if (threadIdx.x < 12) TG[threadIdx.x] = target[(size_t)b * 12 + threadIdx.x];
+  if (threadIdx.x == 0) {
+    // geometry.py:590-599: proportions in double, cuboids then cylinders, zero-volume skipped
+    double area[MAX_PRIMS];
+    int Pn = 0;
+    for (int m = 0; m < M1; ++m) {
+      const float* d = sc.cuboid_dims + ((size_t)b * M1 + m) * 3;
+      if (is_close0(d[0]) || is_close0(d[1]) || is_close0(d[2])) continue;
+      double x = d[0], y = d[1], z = d[2];
+      area[Pn] = __dmul_rn(2.0, __dadd_rn(__dadd_rn(__dmul_rn(x, y), __dmul_rn(x, z)), __dmul_rn(y, z)));
+      pidx[Pn] = (int16_t)m; ++Pn;
+    }
+    for (int m = 0; m < M2; ++m) {
+      float rf = sc.cylinder_radii[(size_t)b * M2 + m], hf = sc.cylinder_heights[(size_t)b * M2 + m];
+      if (is_close0(rf) || is_close0(hf)) continue;
+      double r = rf, h = hf;
+      double tpr = __dmul_rn(__dmul_rn(2.0, 3.14159265358979323846), r);
+      area[Pn] = __dadd_rn(__dmul_rn(tpr, h), __dmul_rn(tpr, r));
+      pidx[Pn] = (int16_t)(-m - 1); ++Pn;
+    }
+    double total = 0.0;
+    for (int i = 0; i < Pn; ++i) total = __dadd_rn(total, area[i]);
+    start[0] = 0;
+    for (int i = 0; i < Pn; ++i) {
+      double prop = __ddiv_rn(area[i], total);
+      uint32_t ni = (uint32_t)(int)__dmul_rn(prop, (double)No) + 500u;
+      start[i + 1] = start[i] + ni;
+    }
+    nvalid = Pn;
+  }
+  __syncthreads();
+  float4* out = cloud + (size_t)b * (Nr + No + Nt);
+  // robot rows (step 0 subset)
+  {
+    uint32_t key[4];
+    philox4x32(0u, 0u, STREAM_ROBOT_PERM, 0u, seed_lo, seed_hi, key);
+    uint32_t half = feistel_bits((uint32_t)P) / 2;
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+      uint32_t e = feistel_perm((uint32_t)j, (uint32_t)P, half, key);
+      float4 o;
+      m34_apply(F + 12 * __ldg(lid + e), __ldg(lp + 3 * e), __ldg(lp + 3 * e + 1), __ldg(lp + 3 * e + 2), o.x, o.y, o.z);
+      o.w = 0.0f;
+      out[j] = o;
+    }
+  }
+  // obstacle rows
+  {
+    int Pn = nvalid;
+    if (Pn == 0) {
+      for (int j = threadIdx.x; j < No; j += blockDim.x) out[Nr + j] = make_float4(0.f, 0.f, 0.f, 1.0f);
+    } else {
+      uint32_t pool = start[Pn];
+      uint32_t key[4];
+      philox4x32(0u, problem, STREAM_OBS_PERM, 0u, seed_lo, seed_hi, key);
+      uint32_t half = feistel_bits(pool) / 2;
+      for (int j = threadIdx.x; j < No; j += blockDim.x) {
+        uint32_t e = feistel_perm((uint32_t)j, pool, half, key);
+        int i = 0;
+        while (e >= start[i + 1]) ++i;
+        uint32_t r[4];
+        philox4x32(e, problem, STREAM_OBS_SAMPLE, 0u, seed_lo, seed_hi, r);
+        float o[3];
+        int m = pidx[i];
+        if (m >= 0) {
+          sample_cuboid(sc.cuboid_centers + ((size_t)b * M1 + m) * 3, sc.cuboid_dims + ((size_t)b * M1 + m) * 3,
+                        sc.cuboid_quats + ((size_t)b * M1 + m) * 4, r, o);
+        } else {
+          m = -m - 1;
+          sample_cylinder(sc.cylinder_centers + ((size_t)b * M2 + m) * 3, sc.cylinder_radii[(size_t)b * M2 + m],
+                          sc.cylinder_heights[(size_t)b * M2 + m], sc.cylinder_quats + ((size_t)b * M2 + m) * 4, r, o);
+        }
+        out[Nr + j] = make_float4(o[0], o[1], o[2], 1.0f);
+      }
+    }
+  }
+  // target rows
+  {
+    uint32_t key[4];
+    philox4x32(0u, problem, STREAM_TARGET_PERM, 0u, seed_lo, seed_hi, key);
+    uint32_t half = feistel_bits((uint32_t)Pe) / 2;
+    for (int j = threadIdx.x; j < Nt; j += blockDim.x) {
+      uint32_t e = feistel_perm((uint32_t)j, (uint32_t)Pe, half, key);
+      float4 o;
+      m34_apply(TG, __ldg(ee + 3 * e), __ldg(ee + 3 * e + 1), __ldg(ee + 3 * e + 2), o.x, o.y, o.z);
+      o.w = 2.0f;
+      out[Nr + No + j] = o;
+    }
+  }
+}
+
+int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* frames, const float* target,
+                       uint32_t problem0, float* cloud) {
+  build_cloud_kernel<<<B, 256, 0, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, frames, target, c->cfg.n_robot,
+                                       c->cfg.n_obstacle, c->cfg.n_target, c->P, c->link_points, c->link_ids, c->Pe,
+                                       c->ee_points, (uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32), problem0,
+                                       (float4*)cloud);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ collision sweep
+// One CTA per problem.  Primitive inverse frames + sphere table in shared memory; timesteps processed in chunks
+// of SWEEP_TCHUNK: one thread per timestep does FK into smem, then all threads sweep (timestep, sphere) pairs.
+constexpr int SWEEP_TCHUNK = 16;
+constexpr int SWEEP_THREADS = 128;
+constexpr int MAX_SPHERES = 96;
+
+__global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(mpn_scene sc, int M1, int M2, int quirk,
+                                                              const float* __restrict__ traj, int T, int problem_stride,
+                                                              int t0, float prismatic, int S, const float* __restrict__ sph_c,
+                                                              const float* __restrict__ sph_r, const int32_t* __restrict__ sph_l,
+                                                              int accumulate, uint8_t* __restrict__ flags,
+                                                              int32_t* __restrict__ first_step) {
+  __shared__ PrimFrame fr[MAX_PRIMS];
+  __shared__ float F[SWEEP_TCHUNK][MPN_NLINK * 12];
+  __shared__ float sc_s[MAX_SPHERES * 3];
+  __shared__ float sr_s[MAX_SPHERES];
+  __shared__ int sl_s[MAX_SPHERES];
+  __shared__ int first;
+  int b = blockIdx.x;
+  stage_scene(sc, b, M1, M2, quirk != 0, fr);
+  for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    sc_s[3 * k] = sph_c[3 * k]; sc_s[3 * k + 1] = sph_c[3 * k + 1]; sc_s[3 * k + 2] = sph_c[3 * k + 2];
+    sr_s[k] = sph_r[k]; sl_s[k] = sph_l[k];
+  }
+  if (threadIdx.x == 0) first = 0x7fffffff;
+  __syncthreads();
+  for (int tc = 0; tc < T; tc += SWEEP_TCHUNK) {
+    int nt = min(SWEEP_TCHUNK, T - tc);
+    if (threadIdx.x < nt) {
+      float qq[7];
+      const float* qp = traj + (size_t)b * problem_stride + (size_t)(tc + threadIdx.x) * 7;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) qq[j] = qp[j];
+      float Fl[MPN_NLINK * 12];
+      spec_fk(qq, prismatic, Fl, nullptr);
+#pragma unroll
+      for (int i = 0; i < MPN_NLINK * 12; ++i) F[threadIdx.x][i] = Fl[i];
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < nt * S; p += blockDim.x) {
+      int t = p / S, k = p - t * S;
+      float x, y, z;
+      m34_apply(F[t] + 12 * sl_s[k], sc_s[3 * k], sc_s[3 * k + 1], sc_s[3 * k + 2], x, y, z);
+      float d = scene_sdf(fr, 0, M1, M1, M1 + M2, x, y, z);
+      if (d <= sr_s[k]) atomicMin(&first, tc + t);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int hit = first != 0x7fffffff;
+    int fs = hit ? first + t0 : -1;
+    if (accumulate) {
+      if (hit) flags[b] = 1;
+      if (first_step && hit && first_step[b] < 0) first_step[b] = fs;
+    } else {
+      flags[b] = (uint8_t)hit;
+      if (first_step) first_step[b] = fs;
+    }
+  }
+}
+
+int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T, int problem_stride,
+                 int t0, int accumulate, uint8_t* flags, int32_t* first_step) {
+  sweep_kernel<<<B, SWEEP_THREADS, 0, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, c->cfg.quirk_frames, traj, T,
+                                           problem_stride, t0, c->prismatic, c->S, c->sph_c, c->sph_r, c->sph_l,
+                                           accumulate, flags, first_step);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+}  // namespace mpn

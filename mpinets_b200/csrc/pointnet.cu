@@ -1,0 +1,198 @@
+// pointnet.cu -- pointnet2_ops._ext replacements: furthest point sampling, ball query, gather, group.
+//
+// Index outputs are bit-exact against the oracle's restatement of pointnet2_ops v3.2.0:
+//   * FPS: start at 0; temp = 1e10; points with |p|^2 <= 1e-3 are skipped; distance = fma(dz,dz,fma(dy,dy,dx*dx));
+//     winner = max distance, ties -> smaller bit-reversed (k mod block) then smaller k.  That is the order the
+//     strided-thread scan + shared-memory tree reduction of sampling_gpu.cu induces (at stride s the lower slot
+//     wins ties, so the LAST stage compares bit 0 of the thread id, the one before bit 1, ...).  It is a total
+//     order, so any reduction shape gives the same index.
+//   * ball query: first nsample indices in index order with d2 < r*r, padded with the first hit.
+#include "engine.h"
+#include "spec_math.cuh"
+
+namespace mpn {
+
+__host__ __device__ inline int opt_n_threads(int work) {
+  int p = 1;
+  while (p * 2 <= work) p *= 2;
+  return p > 512 ? 512 : p;
+}
+
+// 64-bit ordering key: [ dist bits | ~(vt << 23 | k) ], 0 = "no candidate"
+__device__ __forceinline__ unsigned long long fps_key(float d, int vt, int k) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xFFFFFFFFu - (((uint32_t)vt << 23) | (uint32_t)k));
+}
+__device__ __forceinline__ int fps_key_index(unsigned long long key) {
+  return key == 0ull ? 0 : (int)((0xFFFFFFFFu - (uint32_t)key) & 0x7FFFFFu);
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other > v ? other : v;
+  }
+  return v;
+}
+
+// One CTA (FPS_THREADS threads) per problem.  Thread t owns points k = t + i*FPS_THREADS held in registers together
+// with their running min-distance; the cloud also sits in shared memory for the broadcast read of the winner.
+// One barrier per round (cross-warp slots are double-buffered by round parity).
+constexpr int FPS_THREADS = 512;
+
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS, (PPT > 8 ? 2 : 1))
+fps_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int vbs, int32_t* __restrict__ idx,
+           float* __restrict__ new_xyz) {
+  extern __shared__ float4 spts[];  // [N]
+  __shared__ unsigned long long slot[2][FPS_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int vbits = 31 - __clz(vbs);
+  const float* p = xyz + (size_t)b * N * stride;
+  float px[PPT], py[PPT], pz[PPT], temp[PPT];
+  uint32_t valid = 0;
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    int k = tid + i * FPS_THREADS;
+    px[i] = py[i] = pz[i] = 0.f;
+    temp[i] = 1e10f;
+    if (k < N) {
+      float x, y, z;
+      if (stride == 4) {
+        float4 v = reinterpret_cast<const float4*>(p)[k];
+        x = v.x; y = v.y; z = v.z;
+      } else {
+        x = p[(size_t)k * stride]; y = p[(size_t)k * stride + 1]; z = p[(size_t)k * stride + 2];
+      }
+      px[i] = x; py[i] = y; pz[i] = z;
+      spts[k] = make_float4(x, y, z, 0.f);
+      float mag = ffma(z, z, ffma(y, y, fmul(x, x)));
+      if (!(mag <= 1e-3f)) valid |= 1u << i;
+    }
+  }
+  int32_t* out = idx + (size_t)b * npoint;
+  float* oxyz = new_xyz ? new_xyz + (size_t)b * npoint * 3 : nullptr;
+  __syncthreads();
+  int old = 0;
+  if (tid == 0) {
+    out[0] = 0;
+    if (oxyz) { float4 v = spts[0]; oxyz[0] = v.x; oxyz[1] = v.y; oxyz[2] = v.z; }
+  }
+  for (int j = 1; j < npoint; ++j) {
+    float4 c = spts[old];
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      if (valid & (1u << i)) {
+        float d = dist2(px[i], py[i], pz[i], c.x, c.y, c.z);
+        float d2 = fminf(d, temp[i]);
+        temp[i] = d2;
+        int k = tid + i * FPS_THREADS;
+        int vt = vbits ? (int)(__brev((uint32_t)(k & (vbs - 1))) >> (32 - vbits)) : 0;
+        unsigned long long key = fps_key(d2, vt, k);
+        best = key > best ? key : best;
+      }
+    }
+    best = warp_max_u64(best);
+    if (lane == 0) slot[j & 1][warp] = best;
+    __syncthreads();
+    unsigned long long v = lane < FPS_THREADS / 32 ? slot[j & 1][lane] : 0ull;
+    v = warp_max_u64(v);
+    old = fps_key_index(v);
+    if (tid == 0) {
+      out[j] = old;
+      if (oxyz) { float4 w = spts[old]; oxyz[3 * j] = w.x; oxyz[3 * j + 1] = w.y; oxyz[3 * j + 2] = w.z; }
+    }
+  }
+}
+
+int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz) {
+  MPN_REQUIRE(N >= 1 && N <= 16 * FPS_THREADS, "mpn_fps: N=%d unsupported (1..%d)", N, 16 * FPS_THREADS);
+  MPN_REQUIRE(npoint >= 1 && npoint <= N, "mpn_fps: npoint=%d out of range for N=%d", npoint, N);
+  MPN_REQUIRE(stride >= 3, "mpn_fps: stride must be >= 3");
+  int vbs = opt_n_threads(N);
+  size_t smem = (size_t)N * sizeof(float4);
+  int ppt = (N + FPS_THREADS - 1) / FPS_THREADS;
+#define FPS_LAUNCH(P)                                                                                         \
+  do {                                                                                                        \
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    fps_kernel<P><<<B, FPS_THREADS, smem, s>>>(xyz, N, stride, npoint, vbs, idx, new_xyz);                    \
+  } while (0)
+  if (ppt <= 1) FPS_LAUNCH(1);
+  else if (ppt <= 2) FPS_LAUNCH(2);
+  else if (ppt <= 4) FPS_LAUNCH(4);
+  else if (ppt <= 8) FPS_LAUNCH(8);
+  else if (ppt <= 13) FPS_LAUNCH(13);
+  else FPS_LAUNCH(16);
+#undef FPS_LAUNCH
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ ball query
+// warp per centroid: 32 candidates per iteration, ballot + prefix popcount keeps index order.
+__global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ xyz, int N, int stride,
+                                                         const float* __restrict__ new_xyz, int npoint, float r2,
+                                                         int nsample, int32_t* __restrict__ idx) {
+  int b = blockIdx.y;
+  int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (j >= npoint) return;
+  const float* p = xyz + (size_t)b * N * stride;
+  const float* cp = new_xyz + ((size_t)b * npoint + j) * 3;
+  float cx = cp[0], cy = cp[1], cz = cp[2];
+  int32_t* o = idx + ((size_t)b * npoint + j) * nsample;
+  int cnt = 0, first = 0;
+  for (int k0 = 0; k0 < N && cnt < nsample; k0 += 32) {
+    int k = k0 + lane;
+    bool hit = false;
+    if (k < N) {
+      float d2 = dist2(cx, cy, cz, p[(size_t)k * stride], p[(size_t)k * stride + 1], p[(size_t)k * stride + 2]);
+      hit = d2 < r2;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      if (cnt == 0) first = k0 + __ffs(m) - 1;
+      int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (hit && pos < nsample) o[pos] = k;
+      cnt += __popc(m);
+    }
+  }
+  if (cnt > nsample) cnt = nsample;
+  for (int l = cnt + lane; l < nsample; l += 32) o[l] = first;  // pad with first hit (0 when no hit)
+}
+
+int launch_ball_query(mpn_ctx* c, cudaStream_t s, float radius, int nsample, const float* xyz, int B, int N, int stride,
+                      const float* new_xyz, int npoint, int32_t* idx) {
+  MPN_REQUIRE(nsample >= 1 && N >= 1 && npoint >= 1 && stride >= 3, "mpn_ball_query: bad sizes");
+  float r2 = radius * radius;
+  dim3 grid((npoint + 7) / 8, B);
+  ball_query_kernel<<<grid, 256, 0, s>>>(xyz, N, stride, new_xyz, npoint, r2, nsample, idx);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ gather / group
+__global__ void gather_kernel(const float* __restrict__ feat, int C, int N, const int32_t* __restrict__ idx, int m,
+                              float* __restrict__ out) {
+  int b = blockIdx.z, ch = blockIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  out[((size_t)b * C + ch) * m + j] = feat[((size_t)b * C + ch) * N + idx[(size_t)b * m + j]];
+}
+
+int launch_gather(mpn_ctx* c, cudaStream_t s, const float* feat, int B, int C, int N, const int32_t* idx, int m, float* out) {
+  dim3 grid((m + 127) / 128, C, B);
+  gather_kernel<<<grid, 128, 0, s>>>(feat, C, N, idx, m, out);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+int launch_group(mpn_ctx* c, cudaStream_t s, const float* feat, int B, int C, int N, const int32_t* idx, int m, int ns, float* out) {
+  // group_points == gather with a flattened [m*ns] index list
+  return launch_gather(c, s, feat, B, C, N, idx, m * ns, out);
+}
+
+}  // namespace mpn

@@ -1,0 +1,257 @@
+"""Host-side face of the C ABI: one :class:`Engine` per GPU.  PyTorch is used only for device memory and streams.
+
+Every method validates its tensors the way the reference's CUDA extension does (CUDA, contiguous, float32 / int32;
+violations raise ``RuntimeError``), allocates outputs with torch, and launches on the *current* torch stream without
+synchronising the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .franka import RobotTables, default_tables
+
+SCENE_KEYS = ("cuboid_centers", "cuboid_dims", "cuboid_quats", "cylinder_centers", "cylinder_radii",
+              "cylinder_heights", "cylinder_quats")  # batch-dict keys of mpinets/data_loader.py:206-235
+
+
+def _check(t: torch.Tensor, name: str, dtype=torch.float32, device: Optional[torch.device] = None):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")  # same contract as pointnet2_ops ("CPU not supported")
+    if device is not None and t.device != device:
+        raise RuntimeError(f"{name} is on {t.device}, engine is on {device}")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class Engine:
+    def __init__(self, device: int = 0, n_robot: int = 2048, n_obstacle: int = 4096, n_target: int = 128,
+                 max_cuboids: int = 40, max_cylinders: int = 40, quirk_frames: bool = True,
+                 seed: int = 0x4D50694E, tables: Optional[RobotTables] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.MpnError("mpinets_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        self.cfg = _lib.MpnConfig(n_robot, n_obstacle, n_target, max_cuboids, max_cylinders, int(quirk_frames), seed)
+        self.n_points = n_robot + n_obstacle + n_target
+        self._ctx = C.c_void_p()
+        _lib.check(self.lib.mpn_ctx_create(device, C.byref(self.cfg), C.byref(self._ctx)))
+        self.tables = tables if tables is not None else default_tables(max(4096, n_robot))
+        self.set_tables(self.tables)
+        self._weights_loaded = False
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.mpn_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ setup
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_tables(self, t: RobotTables):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        lim, lp, li, ee = f(t.joint_limits), f(t.link_points), i(t.link_ids), f(t.ee_points)
+        sc, sr, sl = f(t.sphere_centers), f(t.sphere_radii), i(t.sphere_links)
+        _lib.check(self.lib.mpn_set_robot_tables(
+            self._ctx, lim.ctypes.data, lp.shape[0], lp.ctypes.data, li.ctypes.data, ee.shape[0], ee.ctypes.data,
+            sc.shape[0], sc.ctypes.data, sr.ctypes.data, sl.ctypes.data, float(t.prismatic)))
+        self.tables = t
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """Takes a reference ``MotionPolicyNetwork`` state dict (Lightning ``.ckpt['state_dict']`` keys)."""
+        for name, v in sd.items():
+            if not (name.startswith("point_cloud_encoder.") or name.startswith("feature_encoder.") or name.startswith("decoder.")):
+                continue
+            a = np.ascontiguousarray(v.detach().to("cpu", torch.float32).numpy())
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            _lib.check(self.lib.mpn_load_weight(self._ctx, name.encode(), a.ctypes.data, shape, a.ndim))
+        _lib.check(self.lib.mpn_weights_finalize(self._ctx))
+        self._weights_loaded = True
+
+    def reserve(self, max_batch: int):
+        _lib.check(self.lib.mpn_reserve(self._ctx, int(max_batch)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mpn_launch_count(self._ctx))
+
+    def _scene(self, scene: Dict[str, torch.Tensor], B: int):
+        s = _lib.MpnScene()
+        keep = []
+        for k in SCENE_KEYS:
+            t = _check(scene[k], k, device=self.device)
+            if t.shape[0] != B:
+                raise RuntimeError(f"{k} has batch {t.shape[0]}, expected {B}")
+            m = self.cfg.max_cuboids if k.startswith("cuboid") else self.cfg.max_cylinders
+            if t.shape[1] != m:
+                raise RuntimeError(f"{k} has {t.shape[1]} primitive rows, engine was built for {m}")
+            keep.append(t)
+            setattr(s, k, t.data_ptr())
+        return s, keep
+
+    def _empty(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ pointnet2_ops
+    def fps(self, xyz: torch.Tensor, npoint: int, return_xyz: bool = False):
+        _check(xyz, "xyz", device=self.device)
+        B, N, stride = xyz.shape
+        idx = self._empty(B, npoint, dtype=torch.int32)
+        new_xyz = self._empty(B, npoint, 3) if return_xyz else None
+        _lib.check(self.lib.mpn_fps(self._ctx, self.stream, _p(xyz), B, N, stride, npoint, _p(idx), _p(new_xyz)))
+        return (idx, new_xyz) if return_xyz else idx
+
+    def ball_query(self, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor):
+        _check(xyz, "xyz", device=self.device); _check(new_xyz, "new_xyz", device=self.device)
+        B, N, stride = xyz.shape
+        m = new_xyz.shape[1]
+        idx = self._empty(B, m, nsample, dtype=torch.int32)
+        _lib.check(self.lib.mpn_ball_query(self._ctx, self.stream, float(radius), nsample, _p(xyz), B, N, stride,
+                                           _p(new_xyz), m, _p(idx)))
+        return idx
+
+    def gather(self, feat: torch.Tensor, idx: torch.Tensor):
+        _check(feat, "features", device=self.device); _check(idx, "idx", torch.int32, self.device)
+        B, Cc, N = feat.shape
+        m = idx.shape[1]
+        out = self._empty(B, Cc, m)
+        _lib.check(self.lib.mpn_gather_points(self._ctx, self.stream, _p(feat), B, Cc, N, _p(idx), m, _p(out)))
+        return out
+
+    def group(self, feat: torch.Tensor, idx: torch.Tensor):
+        _check(feat, "features", device=self.device); _check(idx, "idx", torch.int32, self.device)
+        B, Cc, N = feat.shape
+        _, m, ns = idx.shape
+        out = self._empty(B, Cc, m, ns)
+        _lib.check(self.lib.mpn_group_points(self._ctx, self.stream, _p(feat), B, Cc, N, _p(idx), m, ns, _p(out)))
+        return out
+
+    def sa_forward(self, module: int, xyz: torch.Tensor, feats: torch.Tensor, debug: bool = False):
+        """xyz [B,N,3|4], feats point-major [B,N,C] -> (new_xyz [B,m,3] | None, new_feats [B,m,Cout] [, fps_idx, ball_idx])"""
+        _check(xyz, "xyz", device=self.device); _check(feats, "features", device=self.device)
+        B, N, stride = xyz.shape
+        npoint, cout = ((512, 64), (128, 256), (1, 1024))[module]
+        new_xyz = self._empty(B, npoint, 3) if module < 2 else None
+        out = self._empty(B, npoint, cout)
+        fidx = self._empty(B, npoint, dtype=torch.int32) if debug and module < 2 else None
+        bidx = self._empty(B, npoint, 128, dtype=torch.int32) if debug and module < 2 else None
+        _lib.check(self.lib.mpn_sa_forward(self._ctx, self.stream, module, _lib.PREC_FP32, _p(xyz), stride, _p(feats),
+                                           feats.shape[2], B, N, _p(new_xyz), _p(out), _p(fidx), _p(bidx)))
+        return (new_xyz, out, fidx, bidx) if debug else (new_xyz, out)
+
+    # ------------------------------------------------------------------ robofin
+    def fk(self, q: torch.Tensor):
+        _check(q, "q", device=self.device)
+        B = q.shape[0]
+        frames, eef = self._empty(B, 11, 3, 4), self._empty(B, 3, 4)
+        _lib.check(self.lib.mpn_fk(self._ctx, self.stream, _p(q), B, _p(frames), _p(eef)))
+        return frames, eef
+
+    def sample_robot(self, q: torch.Tensor, n: int, step: int = 0, cloud: Optional[torch.Tensor] = None):
+        _check(q, "q", device=self.device)
+        B = q.shape[0]
+        if cloud is None:
+            cloud = torch.zeros((B, n, 4), dtype=torch.float32, device=self.device)
+        _check(cloud, "cloud", device=self.device)
+        _lib.check(self.lib.mpn_sample_robot(self._ctx, self.stream, _p(q), B, n, step, _p(cloud), cloud.shape[1]))
+        return cloud
+
+    def compute_spheres(self, q: torch.Tensor):
+        _check(q, "q", device=self.device)
+        B = q.shape[0]
+        out = self._empty(B, self.tables.sphere_centers.shape[0], 3)
+        _lib.check(self.lib.mpn_compute_spheres(self._ctx, self.stream, _p(q), B, _p(out)))
+        return out
+
+    def normalize(self, q: torch.Tensor):
+        _check(q, "q", device=self.device)
+        out = torch.empty_like(q)
+        _lib.check(self.lib.mpn_normalize_joints(self._ctx, self.stream, _p(q), q.numel() // 7, _p(out)))
+        return out
+
+    def unnormalize(self, qn: torch.Tensor):
+        _check(qn, "q", device=self.device)
+        out = torch.empty_like(qn)
+        _lib.check(self.lib.mpn_unnormalize_joints(self._ctx, self.stream, _p(qn), qn.numel() // 7, _p(out)))
+        return out
+
+    # ------------------------------------------------------------------ geometry
+    def sdf_points(self, scene, points: torch.Tensor, which: int = 0):
+        _check(points, "points", device=self.device)
+        B, N, _ = points.shape
+        s, keep = self._scene(scene, B)
+        out = self._empty(B, N)
+        _lib.check(self.lib.mpn_sdf_points(self._ctx, self.stream, C.byref(s), B, _p(points), N, which, _p(out)))
+        return out
+
+    def build_cloud(self, scene, q0: torch.Tensor, target: torch.Tensor, problem0: int = 0):
+        _check(q0, "q0", device=self.device); _check(target, "target", device=self.device)
+        B = q0.shape[0]
+        s, keep = self._scene(scene, B)
+        cloud = self._empty(B, self.n_points, 4)
+        _lib.check(self.lib.mpn_build_cloud(self._ctx, self.stream, C.byref(s), B, _p(q0), _p(target), problem0, _p(cloud)))
+        return cloud
+
+    def sweep_flags(self, scene, traj: torch.Tensor):
+        _check(traj, "traj", device=self.device)
+        B, T, _ = traj.shape
+        s, keep = self._scene(scene, B)
+        flags = self._empty(B, dtype=torch.uint8)
+        first = self._empty(B, dtype=torch.int32)
+        _lib.check(self.lib.mpn_sweep_flags(self._ctx, self.stream, C.byref(s), B, _p(traj), T, 0, 0, _p(flags), _p(first)))
+        return flags, first
+
+    # ------------------------------------------------------------------ model
+    def encoder_forward(self, cloud: torch.Tensor, precision: int = _lib.PREC_FP32):
+        _check(cloud, "point_cloud", device=self.device)
+        assert cloud.size(2) == 4  # model.py:420
+        B, N, _ = cloud.shape
+        out = self._empty(B, 2048)
+        _lib.check(self.lib.mpn_encoder_forward(self._ctx, self.stream, precision, _p(cloud), B, N, _p(out)))
+        return out
+
+    def policy_forward(self, cloud: torch.Tensor, q_norm: torch.Tensor, precision: int = _lib.PREC_FP32):
+        _check(cloud, "xyz", device=self.device); _check(q_norm, "q", device=self.device)
+        assert cloud.size(2) == 4
+        B, N, _ = cloud.shape
+        dq = self._empty(B, 7)
+        _lib.check(self.lib.mpn_policy_forward(self._ctx, self.stream, precision, _p(cloud), _p(q_norm), B, N, _p(dq)))
+        return dq
+
+    def rollout(self, scene, cloud: torch.Tensor, q0: torch.Tensor, target: torch.Tensor, steps: int,
+                early_exit: bool = False, check_every_step: bool = False, precision: int = _lib.PREC_FP32,
+                traj: Optional[torch.Tensor] = None, metrics: Optional[torch.Tensor] = None):
+        """Lock-step rollout of `steps` policy steps; `cloud` is updated in place (model.py:181).
+        Returns (traj [B,steps+1,7] unnormalised, metrics [B,8])."""
+        _check(cloud, "xyz", device=self.device); _check(q0, "q0", device=self.device); _check(target, "target", device=self.device)
+        B, N, _ = cloud.shape
+        s, keep = self._scene(scene, B)
+        if traj is None:
+            traj = self._empty(B, steps + 1, 7)
+        if metrics is None:
+            metrics = self._empty(B, _lib.METRICS_COLS)
+        _lib.check(self.lib.mpn_rollout(self._ctx, self.stream, precision, C.byref(s), B, N, _p(cloud), _p(q0), _p(target),
+                                        steps, int(early_exit), int(check_every_step), _p(traj), _p(metrics)))
+        return traj, metrics

@@ -1,0 +1,347 @@
+"""CPU ORACLE (test infrastructure, NOT product code) -- Python face of ``mpn_oracle.c`` plus the
+floating-point network restated with torch-CPU ops.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs
+import this module.  The product package ``mpinets_b200`` never does.
+
+Restates (paths under /root/reference):
+  * ``MPiNetsPointNet.forward`` / ``MotionPolicyNetwork.forward``   mpinets/model.py:75-91,360-426
+  * ``PointnetSAModule`` glue (FPS -> gather -> ball query -> group -> shared MLP -> max)
+                                                                  pointnet2_ops v3.2.0 (un-vendored), SURVEY App. A.1
+  * ``TrainingMotionPolicyNetwork.rollout`` + validation sweep      mpinets/model.py:128-183,272-314
+The integer / geometry arithmetic lives in ``mpn_oracle.c`` (bit-exact contract); the MLP arithmetic is
+torch CPU fp32 (tolerance contract, 1e-5 on delta-q).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libmpn_oracle.so")
+    src = os.path.join(_HERE, "mpn_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libmpn_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _scene_args(scene):
+    """scene: dict with cuboid_centers[B,M1,3], cuboid_dims, cuboid_quats[B,M1,4], cylinder_centers[B,M2,3],
+    cylinder_radii[B,M2,1|], cylinder_heights, cylinder_quats (keys of data_loader.py:206-235)."""
+    keep = []
+    cc, pcc = _f(scene["cuboid_centers"]); cd, pcd = _f(scene["cuboid_dims"]); cq, pcq = _f(scene["cuboid_quats"])
+    yc, pyc = _f(scene["cylinder_centers"])
+    yr, pyr = _f(np.asarray(scene["cylinder_radii"]).reshape(yc.shape[0], -1))
+    yh, pyh = _f(np.asarray(scene["cylinder_heights"]).reshape(yc.shape[0], -1))
+    yq, pyq = _f(scene["cylinder_quats"])
+    keep += [cc, cd, cq, yc, yr, yh, yq]
+    B, M1, M2 = cc.shape[0], cc.shape[1], yc.shape[1]
+    return keep, B, M1, M2, (pcc, pcd, pcq, pyc, pyr, pyh, pyq)
+
+
+# ----------------------------------------------------------------------------- geometry
+def sincos(x):
+    x, px = _f(x)
+    s = np.empty_like(x); c = np.empty_like(x)
+    lib().mpn_oracle_sincos(px, C.c_int(x.size), s.ctypes.data_as(C.POINTER(C.c_float)), c.ctypes.data_as(C.POINTER(C.c_float)))
+    return s, c
+
+
+def fk(q, prismatic=0.025):
+    """q [B,7] -> (frames [B,11,3,4], right_gripper [B,3,4])"""
+    q, pq = _f(q)
+    B = q.shape[0]
+    frames = np.empty((B, 11, 3, 4), np.float32); eef = np.empty((B, 3, 4), np.float32)
+    lib().mpn_oracle_fk(pq, C.c_int(B), C.c_float(prismatic), frames.ctypes.data_as(C.POINTER(C.c_float)),
+                        eef.ctypes.data_as(C.POINTER(C.c_float)))
+    return frames, eef
+
+
+def unnormalize(qn, limits):
+    qn, pq = _f(qn); lim, pl = _f(limits)
+    out = np.empty_like(qn)
+    lib().mpn_oracle_unnormalize(pq, C.c_int(qn.shape[0]), pl, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def normalize(q, limits):
+    q, pq = _f(q); lim, pl = _f(limits)
+    out = np.empty_like(q)
+    lib().mpn_oracle_normalize(pq, C.c_int(q.shape[0]), pl, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def sdf_points(scene, points, quirk=True, which=0):
+    keep, B, M1, M2, ps = _scene_args(scene)
+    pts, pp = _f(points)
+    N = pts.shape[1]
+    out = np.empty((B, N), np.float32)
+    lib().mpn_oracle_sdf_points(C.c_int(B), C.c_int(N), C.c_int(M1), C.c_int(M2), *ps, C.c_int(int(quirk)), C.c_int(which),
+                                pp, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def sweep_flags(scene, traj, tables, quirk=True):
+    """traj [B,T,7] unnormalised -> (flags u8[B], first_step i32[B], min_margin f32[B])"""
+    keep, B, M1, M2, ps = _scene_args(scene)
+    traj, pt = _f(traj)
+    T = traj.shape[1]
+    sc, psc = _f(tables.sphere_centers); sr, psr = _f(tables.sphere_radii); sl, psl = _i(tables.sphere_links)
+    flags = np.zeros(B, np.uint8); first = np.zeros(B, np.int32); mm = np.zeros(B, np.float32)
+    lib().mpn_oracle_sweep_flags(C.c_int(B), C.c_int(T), C.c_int(M1), C.c_int(M2), *ps, C.c_int(int(quirk)), pt,
+                                 C.c_float(tables.prismatic), C.c_int(sc.shape[0]), psc, psr, psl,
+                                 flags.ctypes.data_as(C.POINTER(C.c_uint8)), first.ctypes.data_as(C.POINTER(C.c_int32)),
+                                 mm.ctypes.data_as(C.POINTER(C.c_float)))
+    return flags, first, mm
+
+
+def spheres(q, tables):
+    q, pq = _f(q)
+    sc, psc = _f(tables.sphere_centers); sl, psl = _i(tables.sphere_links)
+    out = np.empty((q.shape[0], sc.shape[0], 3), np.float32)
+    lib().mpn_oracle_spheres(pq, C.c_int(q.shape[0]), C.c_float(tables.prismatic), C.c_int(sc.shape[0]), psc, psl,
+                             out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def philox(c, k):
+    out = (C.c_uint32 * 4)()
+    lib().mpn_oracle_philox(*[C.c_uint32(int(v)) for v in c], C.c_uint32(int(k[0])), C.c_uint32(int(k[1])), out)
+    return np.array(list(out), dtype=np.uint32)
+
+
+def feistel(n, key, count):
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.empty(count, np.uint32)
+    lib().mpn_oracle_feistel(C.c_uint32(n), key.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(count),
+                             out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out
+
+
+def sample_obstacles(scene, n, seed, problem0=0, return_prims=False):
+    keep, B, M1, M2, ps = _scene_args(scene)
+    out = np.zeros((B, n, 4), np.float32)
+    prim = np.zeros((B, n), np.int32)
+    lib().mpn_oracle_sample_obstacles(C.c_int(B), C.c_int(n), C.c_int(M1), C.c_int(M2), *ps, C.c_uint64(seed),
+                                      C.c_uint32(problem0), out.ctypes.data_as(C.POINTER(C.c_float)),
+                                      prim.ctypes.data_as(C.POINTER(C.c_int32)))
+    return (out, prim) if return_prims else out
+
+
+def sample_robot(q, tables, n, seed, step, cloud=None):
+    """Writes rows [0,n) (xyz only) of cloud [B,rows,4]; returns the cloud."""
+    q, pq = _f(q)
+    B = q.shape[0]
+    if cloud is None:
+        cloud = np.zeros((B, n, 4), np.float32)
+    assert cloud.dtype == np.float32 and cloud.flags.c_contiguous
+    lp, plp = _f(tables.link_points); li, pli = _i(tables.link_ids)
+    lib().mpn_oracle_sample_robot(pq, C.c_int(B), C.c_float(tables.prismatic), C.c_int(lp.shape[0]), plp, pli, C.c_int(n),
+                                  C.c_uint64(seed), C.c_uint32(step), cloud.ctypes.data_as(C.POINTER(C.c_float)),
+                                  C.c_int(cloud.shape[1]))
+    return cloud
+
+
+def build_cloud(q0, target, scene, tables, seed, n_robot=2048, n_obs=4096, n_tgt=128, problem0=0):
+    """q0 [B,7] unnormalised, target [B,3,4] right_gripper pose -> cloud [B,N,4] (run_inference.py:93-134)."""
+    keep, B, M1, M2, ps = _scene_args(scene)
+    q0, pq = _f(q0); tg, ptg = _f(np.asarray(target).reshape(B, 12))
+    lp, plp = _f(tables.link_points); li, pli = _i(tables.link_ids); ee, pee = _f(tables.ee_points)
+    cloud = np.zeros((B, n_robot + n_obs + n_tgt, 4), np.float32)
+    lib().mpn_oracle_build_cloud(C.c_int(B), pq, ptg, C.c_float(tables.prismatic), C.c_int(lp.shape[0]), plp, pli,
+                                 C.c_int(ee.shape[0]), pee, C.c_int(n_robot), C.c_int(n_obs), C.c_int(n_tgt),
+                                 C.c_int(M1), C.c_int(M2), *ps, C.c_uint64(seed), C.c_uint32(problem0),
+                                 cloud.ctypes.data_as(C.POINTER(C.c_float)))
+    return cloud
+
+
+# ----------------------------------------------------------------------------- pointnet2_ops restatement
+def fps(xyz, npoint):
+    """xyz [B,N,3|4] -> idx i32 [B,npoint]"""
+    xyz, px = _f(xyz)
+    B, N, stride = xyz.shape
+    idx = np.zeros((B, npoint), np.int32)
+    lib().mpn_oracle_fps(C.c_int(B), C.c_int(N), C.c_int(stride), px, C.c_int(npoint), idx.ctypes.data_as(C.POINTER(C.c_int32)))
+    return idx
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    xyz, px = _f(xyz); new_xyz, pn = _f(new_xyz)
+    B, N, stride = xyz.shape
+    m = new_xyz.shape[1]
+    idx = np.zeros((B, m, nsample), np.int32)
+    lib().mpn_oracle_ball_query(C.c_int(B), C.c_int(N), C.c_int(stride), px, C.c_int(m), pn, C.c_float(radius),
+                                C.c_int(nsample), idx.ctypes.data_as(C.POINTER(C.c_int32)))
+    return idx
+
+
+def gather_operation(feat, idx):
+    """feat [B,C,N], idx [B,m] -> [B,C,m]"""
+    B = feat.shape[0]
+    return np.stack([feat[b][:, idx[b]] for b in range(B)])
+
+
+def grouping_operation(feat, idx):
+    """feat [B,C,N], idx [B,m,ns] -> [B,C,m,ns]"""
+    B = feat.shape[0]
+    return np.stack([feat[b][:, idx[b]] for b in range(B)])
+
+
+# ----------------------------------------------------------------------------- network (torch CPU)
+SA_SPECS = (
+    dict(npoint=512, radius=0.05, nsample=128, mlp=(4, 64, 64, 64)),       # model.py:365-373 (+3 for use_xyz)
+    dict(npoint=128, radius=0.3, nsample=128, mlp=(67, 128, 128, 256)),    # model.py:374-382
+    dict(npoint=None, radius=None, nsample=None, mlp=(259, 512, 512, 1024)),  # model.py:383 (GroupAll)
+)
+
+
+def reference_state_dict(seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Default-initialised weights of the architecture at model.py:41-66,360-393 with the reference's
+    state-dict key names (the Zenodo checkpoint is not available offline)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+
+    def lin(name, cin, cout, conv=False):
+        bound = 1.0 / np.sqrt(cin)
+        w = (torch.rand((cout, cin), generator=g) * 2 - 1) * bound
+        b = (torch.rand((cout,), generator=g) * 2 - 1) * bound
+        sd[name + ".weight"] = w.reshape(cout, cin, 1, 1) if conv else w
+        sd[name + ".bias"] = b
+
+    for s, spec in enumerate(SA_SPECS):
+        for l in range(3):
+            lin(f"point_cloud_encoder.SA_modules.{s}.mlps.0.{2 * l}", spec["mlp"][l], spec["mlp"][l + 1], conv=True)
+    lin("point_cloud_encoder.fc_layer.0", 1024, 4096)
+    sd["point_cloud_encoder.fc_layer.1.weight"] = 1 + 0.1 * (torch.rand(4096, generator=g) - 0.5)
+    sd["point_cloud_encoder.fc_layer.1.bias"] = 0.1 * (torch.rand(4096, generator=g) - 0.5)
+    lin("point_cloud_encoder.fc_layer.3", 4096, 2048)
+    sd["point_cloud_encoder.fc_layer.4.weight"] = 1 + 0.1 * (torch.rand(2048, generator=g) - 0.5)
+    sd["point_cloud_encoder.fc_layer.4.bias"] = 0.1 * (torch.rand(2048, generator=g) - 0.5)
+    lin("point_cloud_encoder.fc_layer.6", 2048, 2048)
+    for i, (a, b) in zip((0, 2, 4, 6, 8), ((7, 32), (32, 64), (64, 128), (128, 128), (128, 64))):
+        lin(f"feature_encoder.{i}", a, b)
+    for i, (a, b) in zip((0, 2, 4, 6), ((2112, 512), (512, 256), (256, 128), (128, 7))):
+        lin(f"decoder.{i}", a, b)
+    return sd
+
+
+def _round_bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _dense(x, w, b, emulate_bf16, dtype):
+    """x [..., Cin] @ w[Cout,Cin]^T + b, with optional bf16 operand rounding (fp32 products are exact,
+    accumulation in `dtype`)."""
+    if emulate_bf16:
+        x = _round_bf16(x); w = _round_bf16(w)
+    return (x.to(dtype) @ w.to(dtype).t() + b.to(dtype))
+
+
+def sa_module(xyz, feats, spec, weights, emulate_bf16=False, dtype=torch.float32, return_aux=False):
+    """xyz np[B,N,3] fp32, feats torch[B,N,C] (row-major per point) -> (new_xyz np[B,m,3] | None, feats torch[B,m,Cout])
+
+    Shared-MLP rows are [dx,dy,dz, features...] in the Conv2d input-channel order (QueryAndGroup, use_xyz=True)."""
+    B, N, _ = xyz.shape
+    aux = {}
+    if spec["npoint"] is not None:
+        idx = fps(xyz, spec["npoint"])
+        new_xyz = np.stack([xyz[b][idx[b]] for b in range(B)])
+        bq = ball_query(spec["radius"], spec["nsample"], xyz, new_xyz)
+        aux.update(fps_idx=idx, ball_idx=bq)
+        bqt = torch.from_numpy(bq.astype(np.int64))
+        xyz_t = torch.from_numpy(xyz)
+        g_xyz = torch.stack([xyz_t[b][bqt[b]] for b in range(B)]) - torch.from_numpy(new_xyz)[:, :, None, :]  # [B,m,ns,3]
+        g_f = torch.stack([feats[b][bqt[b]] for b in range(B)])                                            # [B,m,ns,C]
+        x = torch.cat([g_xyz, g_f.to(torch.float32)], dim=-1)
+    else:
+        new_xyz = None
+        x = torch.cat([torch.from_numpy(xyz), feats.to(torch.float32)], dim=-1)[:, None]                      # [B,1,N,3+C]
+    x = x.to(dtype)
+    for (w, b) in weights:
+        x = torch.relu(_dense(x, w.reshape(w.shape[0], -1), b, emulate_bf16, dtype))
+    out = x.max(dim=2).values                                                                               # [B,m,Cout]
+    if emulate_bf16 and spec["npoint"] is not None:
+        out = _round_bf16(out.float()).to(dtype)   # hand-off tensors are stored in bf16 in the tensor-core mode
+    return (new_xyz, out, aux) if return_aux else (new_xyz, out)
+
+
+def encoder_forward(sd, cloud, emulate_bf16=False, dtype=torch.float32, return_aux=False):
+    """cloud np[B,N,4] -> pc encoding torch[B,2048] (model.py:409-426)"""
+    cloud = np.ascontiguousarray(cloud, dtype=np.float32)
+    xyz = np.ascontiguousarray(cloud[..., :3])
+    feats = torch.from_numpy(np.ascontiguousarray(cloud[..., 3:]))
+    auxs = []
+    for s, spec in enumerate(SA_SPECS):
+        ws = [(sd[f"point_cloud_encoder.SA_modules.{s}.mlps.0.{2 * l}.weight"],
+               sd[f"point_cloud_encoder.SA_modules.{s}.mlps.0.{2 * l}.bias"]) for l in range(3)]
+        r = sa_module(xyz, feats, spec, ws, emulate_bf16, dtype, return_aux=True)
+        xyz, feats = r[0], r[1]
+        auxs.append(dict(r[2], new_xyz=r[0], feats=r[1]))
+    x = feats[:, 0]  # [B,1024]
+    p = "point_cloud_encoder.fc_layer."
+    x = _dense(x, sd[p + "0.weight"], sd[p + "0.bias"], emulate_bf16, dtype)
+    x = F.leaky_relu(F.group_norm(x, 16, sd[p + "1.weight"].to(dtype), sd[p + "1.bias"].to(dtype), eps=1e-5), 0.01)
+    x = _dense(x, sd[p + "3.weight"], sd[p + "3.bias"], emulate_bf16, dtype)
+    x = F.leaky_relu(F.group_norm(x, 16, sd[p + "4.weight"].to(dtype), sd[p + "4.bias"].to(dtype), eps=1e-5), 0.01)
+    x = _dense(x, sd[p + "6.weight"], sd[p + "6.bias"], emulate_bf16, dtype)
+    return (x, auxs) if return_aux else x
+
+
+def policy_forward(sd, cloud, q_norm, emulate_bf16=False, dtype=torch.float32, return_aux=False):
+    """MotionPolicyNetwork.forward (model.py:75-91): -> delta q (normalised) torch[B,7]"""
+    enc = encoder_forward(sd, cloud, emulate_bf16, dtype, return_aux)
+    aux = None
+    if return_aux:
+        enc, aux = enc
+    x = torch.as_tensor(np.asarray(q_norm), dtype=dtype)
+    for i in (0, 2, 4, 6, 8):
+        x = _dense(x, sd[f"feature_encoder.{i}.weight"], sd[f"feature_encoder.{i}.bias"], False, dtype)
+        if i != 8:
+            x = F.leaky_relu(x, 0.01)
+    x = torch.cat([enc, x], dim=1)
+    for i in (0, 2, 4, 6):
+        x = _dense(x, sd[f"decoder.{i}.weight"], sd[f"decoder.{i}.bias"], emulate_bf16 and i == 0, dtype)
+        if i != 6:
+            x = F.leaky_relu(x, 0.01)
+    return (x, aux) if return_aux else x
+
+
+def rollout(sd, cloud, q_norm, tables, steps, seed, emulate_bf16=False, n_robot=2048):
+    """TrainingMotionPolicyNetwork.rollout (model.py:128-183), lock-step, unnormalize=True.
+    Mutates `cloud` in place like the reference (model.py:181).  Returns traj np[B,steps+1,7] (unnormalised)."""
+    q = np.ascontiguousarray(q_norm, dtype=np.float32).copy()
+    traj = [unnormalize(q, tables.joint_limits)]
+    for i in range(steps):
+        dq = policy_forward(sd, cloud, q, emulate_bf16).to(torch.float32).numpy()
+        q = np.clip(q + dq, -1.0, 1.0).astype(np.float32)
+        qu = unnormalize(q, tables.joint_limits)
+        traj.append(qu)
+        sample_robot(qu, tables, n_robot, seed, i + 1, cloud)
+    return np.stack(traj, axis=1)

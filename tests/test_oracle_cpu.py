@@ -1,0 +1,322 @@
+"""CPU tests (-m "not gpu"): the oracle against the reference's golden vectors / real-reference fixtures,
+property tests for the un-pinned third-party semantics, host logic, and the C-ABI export surface."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+# ----------------------------------------------------------------------------- golden vectors from the reference
+def test_fk_matches_reference_known_answer(oracle):
+    """interactive_demo/mpinets_ros/nodes/interaction_node.py:54-75"""
+    g = np.load(os.path.join(HERE, "golden", "fk_reference.npz"))
+    frames, eef = oracle.fk(g["q"][None].astype(np.float32))
+    assert np.abs(eef[0, :, 3] - g["xyz"]).max() < 2e-7
+    R = eef[0, :, :3].astype(np.float64)
+    w = np.sqrt(max(0.0, 1 + np.trace(R))) / 2
+    # quaternion is near a half-turn (w ~ 0.02): recover xyz from the symmetric part
+    x, y, z, ww = g["xyzw"]
+    Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * ww), 2 * (x * z + y * ww)],
+                   [2 * (x * y + z * ww), 1 - 2 * (x * x + z * z), 2 * (y * z - x * ww)],
+                   [2 * (x * z - y * ww), 2 * (y * z + x * ww), 1 - 2 * (x * x + y * y)]])
+    assert np.abs(R - Rq).max() < 1e-6
+    assert abs(abs(w) - abs(ww)) < 2e-5   # w ~ 0.02 from the trace is ill-conditioned in fp32
+
+
+def test_fk_f64_helper_agrees(oracle):
+    from mpinets_b200 import franka
+    rng = np.random.RandomState(0)
+    q = rng.uniform(franka.REAL_JOINT_LIMITS[:, 0], franka.REAL_JOINT_LIMITS[:, 1], size=(64, 7)).astype(np.float32)
+    frames, eef = oracle.fk(q)
+    for i in range(64):
+        F64, g = franka.fk_reference_f64(q[i].astype(np.float64))
+        assert np.abs(frames[i] - F64[:, :3]).max() < 5e-7
+        assert np.abs(eef[i] - g[:3]).max() < 5e-7
+
+
+@pytest.mark.parametrize("tag", ["yaw", "free"])
+def test_sdf_matches_real_reference(oracle, tag):
+    """tests/golden/sdf_reference.npz was produced by mpinets/geometry.py itself (make_golden.py)."""
+    g = np.load(os.path.join(HERE, "golden", "sdf_reference.npz"))
+    s = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_")}
+    for which, key in ((1, "sdf_cuboids"), (2, "sdf_cylinders")):
+        mine = oracle.sdf_points(s, s["points"], quirk=True, which=which)
+        ref = s[key]
+        assert (np.isfinite(mine) == np.isfinite(ref)).all()       # all-masked scenes -> +inf (geometry.py:251-254)
+        fin = np.isfinite(ref)
+        assert np.abs(mine[fin] - ref[fin]).max() < 2e-6
+    B, T, NS, _ = s["seq"].shape
+    mine = oracle.sdf_points(s, s["seq"].reshape(B, T * NS, 3), quirk=True, which=0).reshape(B, T, NS)
+    fin = np.isfinite(s["sdf_sequence"])
+    assert np.abs(mine[fin] - s["sdf_sequence"][fin]).max() < 2e-6
+    assert ((mine.reshape(B, -1) <= 0.06).any(-1) == s["has_collision_r006"]).all()  # model.py:309-311
+
+
+def test_quirk_is_latent_for_yaw_only_scenes(oracle):
+    g = np.load(os.path.join(HERE, "golden", "sdf_reference.npz"))
+    s = {k[4:]: g[k] for k in g.files if k.startswith("yaw_")}
+    a = oracle.sdf_points(s, s["points"], quirk=True)
+    b = oracle.sdf_points(s, s["points"], quirk=False)
+    assert np.array_equal(a, b)
+
+
+# ----------------------------------------------------------------------------- spec arithmetic
+def test_sincos_accuracy(oracle):
+    x = np.linspace(-8, 8, 200001).astype(np.float32)
+    s, c = oracle.sincos(x)
+    assert np.abs(s - np.sin(x.astype(np.float64))).max() < 2e-7
+    assert np.abs(c - np.cos(x.astype(np.float64))).max() < 2e-7
+
+
+def test_normalize_roundtrip_and_formula(oracle, tables):
+    rng = np.random.RandomState(1)
+    lim = tables.joint_limits
+    q = rng.uniform(lim[:, 0], lim[:, 1], size=(100, 7)).astype(np.float32)
+    qn = oracle.normalize(q, lim)
+    assert qn.min() >= -1 - 1e-6 and qn.max() <= 1 + 1e-6
+    ref = (q - lim[:, 0]) / (lim[:, 1] - lim[:, 0]) * 2 + -1       # utils.py:91-93 in fp32
+    assert np.array_equal(qn, ref.astype(np.float32))
+    back = oracle.unnormalize(qn, lim)
+    ref_back = (qn - -1) * (lim[:, 1] - lim[:, 0]) / 2 + lim[:, 0]  # utils.py:207-209
+    assert np.array_equal(back, ref_back.astype(np.float32))
+    assert np.abs(back - q).max() < 1e-6
+
+
+def test_philox_known_answer(oracle):
+    # Random123 known-answer test for philox4x32-10: counter 0, key 0
+    out = oracle.philox((0, 0, 0, 0), (0, 0))
+    assert [hex(v) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    out = oracle.philox((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF))
+    assert [hex(v) for v in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 478, 4096, 4097, 10613, 44096])
+def test_feistel_is_a_permutation(oracle, n):
+    key = np.array([1, 2, 3, 4], np.uint32) * 0x9E3779B1
+    p = oracle.feistel(n, key, n)
+    assert sorted(p.tolist()) == list(range(n))
+
+
+# ----------------------------------------------------------------------------- cloud construction properties
+def test_obstacle_cloud_properties(oracle):
+    from mpinets_b200 import scenes
+    p = scenes.config_problems(4, 12)
+    pts, prim = oracle.sample_obstacles(p, 4096, seed=7, return_prims=True)
+    assert (pts[..., 3] == 1).all()
+    B, M1 = p["cuboid_dims"].shape[:2]
+    for b in range(B):
+        valid_c = np.abs(p["cuboid_dims"][b]).min(-1) > 1e-8
+        valid_y = (p["cylinder_radii"][b, :, 0] > 1e-8) & (p["cylinder_heights"][b, :, 0] > 1e-8)
+        areas = np.concatenate([2 * (p["cuboid_dims"][b, :, 0] * p["cuboid_dims"][b, :, 1] + p["cuboid_dims"][b, :, 0] * p["cuboid_dims"][b, :, 2]
+                                     + p["cuboid_dims"][b, :, 1] * p["cuboid_dims"][b, :, 2]) * valid_c,
+                                (2 * np.pi * p["cylinder_radii"][b, :, 0] * (p["cylinder_heights"][b, :, 0] + p["cylinder_radii"][b, :, 0])) * valid_y])
+        counts = np.bincount(prim[b], minlength=len(areas))
+        assert counts[areas == 0].sum() == 0                      # zero-volume rows are never sampled
+        pool = np.floor(areas / areas.sum() * 4096).astype(int) + 500 * (areas > 0)   # geometry.py:599
+        expect = pool / pool.sum() * 4096                          # hypergeometric mean of the subsample (:608)
+        assert np.abs(counts - expect).max() < 6 * np.sqrt(expect.max()) + 10
+        # every point lies on the surface of the primitive it was drawn from
+        for m in np.unique(prim[b]):
+            sel = prim[b] == m
+            one = {k: np.zeros_like(v[b:b + 1]) for k, v in p.items() if k.startswith(("cuboid", "cylinder"))}
+            one["cuboid_quats"][..., 0] = 1; one["cylinder_quats"][..., 0] = 1
+            if m < M1:
+                for k in ("cuboid_centers", "cuboid_dims", "cuboid_quats"):
+                    one[k][0, 0] = p[k][b, m]
+            else:
+                for k in ("cylinder_centers", "cylinder_radii", "cylinder_heights", "cylinder_quats"):
+                    one[k][0, 0] = p[k][b, m - M1]
+            d = oracle.sdf_points(one, pts[b:b + 1, sel, :3], quirk=False)
+            assert np.abs(d).max() < 1e-5
+
+
+def test_empty_scene_cloud(oracle, tables):
+    from mpinets_b200 import scenes
+    p = scenes.config_problems(2, 2)
+    for k in ("cuboid_dims", "cylinder_radii", "cylinder_heights"):
+        p[k][:] = 0
+    cloud = oracle.build_cloud(p["q0"], p["target"], p, tables, seed=1)
+    assert (cloud[:, 2048:6144, :3] == 0).all() and (cloud[:, 2048:6144, 3] == 1).all()
+    assert np.isinf(oracle.sdf_points(p, cloud[:, :16, :3])).all()
+    flags, first, _ = oracle.sweep_flags(p, np.repeat(p["q0"][:, None], 3, 1), tables)
+    assert not flags.any() and (first == -1).all()
+
+
+def test_cloud_layout_and_robot_rows(oracle, tables):
+    from mpinets_b200 import scenes
+    p = scenes.config_problems(2, 3)
+    cloud = oracle.build_cloud(p["q0"], p["target"], p, tables, seed=5)
+    assert cloud.shape == (3, 6272, 4)
+    assert (cloud[:, :2048, 3] == 0).all() and (cloud[:, 2048:6144, 3] == 1).all() and (cloud[:, 6144:, 3] == 2).all()
+    # robot rows = FK-transformed canonical points of a keyed subset without repetition
+    frames, _ = oracle.fk(p["q0"])
+    fr = frames[:, tables.link_ids]                                 # [B,P,3,4]
+    world = np.einsum("bpij,pj->bpi", fr[..., :3], tables.link_points) + fr[..., 3]
+    for b in range(3):
+        d = np.abs(cloud[b, :2048, None, :3] - world[b][None]).max(-1)
+        nearest = d.argmin(1)
+        assert d.min(1).max() < 1e-6 and len(set(nearest.tolist())) == 2048
+    # target rows are the gripper points under the target pose
+    tw = np.einsum("bij,pj->bpi", p["target"][:, :, :3], tables.ee_points) + p["target"][:, None, :, 3]
+    for b in range(3):
+        d = np.abs(cloud[b, 6144:, None, :3] - tw[b][None]).max(-1)
+        assert d.min(1).max() < 1e-6
+    # resampling at another step changes the subset but not the surface
+    c2 = oracle.sample_robot(p["q0"], tables, 2048, 5, 9)
+    assert not np.array_equal(c2[:, :, :3], cloud[:, :2048, :3])
+
+
+# ----------------------------------------------------------------------------- pointnet2_ops restatement
+def _fps_naive(xyz, m):
+    """greedy farthest point sampling with first-index ties (no tree, no skip): a weaker independent statement"""
+    N = len(xyz)
+    d = np.full(N, 1e10, np.float32)
+    out = [0]
+    for _ in range(1, m):
+        diff = (xyz - xyz[out[-1]]).astype(np.float32)
+        dd = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1] + diff[:, 2] * diff[:, 2]).astype(np.float32)
+        d = np.minimum(d, dd)
+        out.append(int(d.argmax()))
+    return out
+
+
+def test_fps_is_a_greedy_farthest_sequence(oracle):
+    rng = np.random.RandomState(3)
+    xyz = (rng.uniform(-1, 1, size=(2, 700, 3)) + 2.0).astype(np.float32)   # away from the origin: no skipped points
+    idx = oracle.fps(xyz, 64)
+    for b in range(2):
+        assert len(set(idx[b].tolist())) == 64 and idx[b, 0] == 0
+        # each pick maximises the distance to the already-picked set (values compared, index may differ on fp ties)
+        picked = [0]
+        for j in range(1, 64):
+            d = ((xyz[b][:, None] - xyz[b][picked][None]) ** 2).sum(-1).min(1)
+            assert d[idx[b, j]] >= d.max() * (1 - 1e-5)
+            picked.append(idx[b, j])
+
+
+def test_fps_skips_points_near_origin(oracle):
+    rng = np.random.RandomState(4)
+    xyz = rng.uniform(-1, 1, size=(1, 600, 3)).astype(np.float32)
+    xyz[0, 100:140] *= 0.01          # |p|^2 <= 1e-3 -> never selected (sampling_gpu.cu skip rule)
+    idx = oracle.fps(xyz, 300)
+    assert not set(range(100, 140)) & set(idx[0, 1:].tolist())
+
+
+def test_fps_tie_break_is_tree_order(oracle):
+    # 4 points at equal distance from point 0 -> winner decided by the shared-memory tree, not by lowest index
+    xyz = np.zeros((1, 8, 3), np.float32)
+    xyz[0, :, 0] = 5.0
+    for k, (dy, dz) in {1: (1, 0), 2: (-1, 0), 3: (0, 1), 6: (0, -1)}.items():
+        xyz[0, k, 1], xyz[0, k, 2] = dy, dz
+    idx = oracle.fps(xyz, 2)
+    # block = 8 threads, one point each; ties: stride-4 stage keeps lower slot, ... final winner has the smallest
+    # bit-reversed thread id among {1,2,3,6} = {100b,010b,110b,011b} -> thread 2 (bitrev 010b=2) vs 1 (100b=4): 2 wins
+    assert idx[0, 1] == 2
+
+
+def test_ball_query_semantics(oracle):
+    rng = np.random.RandomState(5)
+    xyz = rng.uniform(0, 1, size=(2, 900, 3)).astype(np.float32)
+    new_xyz = xyz[:, :50].copy()
+    idx = oracle.ball_query(0.2, 16, xyz, new_xyz)
+    for b in range(2):
+        for j in range(50):
+            d2 = ((xyz[b] - new_xyz[b, j]) ** 2).sum(-1)
+            inside = np.nonzero(d2 < 0.2 * 0.2 * (1 - 1e-5))[0]
+            got = idx[b, j]
+            n = min(len(inside), 16)
+            assert (np.diff(got[:n]) > 0).all()                       # index order
+            assert set(got.tolist()) <= set(np.nonzero(d2 < 0.2 * 0.2 * (1 + 1e-5))[0].tolist())
+            if len(inside) < 16:
+                assert (got[len(set(got.tolist())):] == got[0]).all()  # padded with the first hit
+    far = oracle.ball_query(0.01, 4, xyz, np.full((2, 1, 3), 9.0, np.float32))
+    assert (far == 0).all()                                            # no hit -> zero-initialised indices
+
+
+# ----------------------------------------------------------------------------- network restatement vs torch modules
+def test_network_restatement_matches_torch_modules(oracle, state_dict):
+    """The oracle's dense/GroupNorm/LeakyReLU chain vs an nn.Sequential built exactly like model.py:47-66,385-393;
+    the shared MLP vs nn.Conv2d(k=1)+ReLU+max_pool2d on an explicitly grouped tensor (pointnet2 build_shared_mlp)."""
+    sd = state_dict
+    torch.manual_seed(0)
+    fc = torch.nn.Sequential(torch.nn.Linear(1024, 4096), torch.nn.GroupNorm(16, 4096), torch.nn.LeakyReLU(),
+                             torch.nn.Linear(4096, 2048), torch.nn.GroupNorm(16, 2048), torch.nn.LeakyReLU(),
+                             torch.nn.Linear(2048, 2048))
+    fc.load_state_dict({k[len("point_cloud_encoder.fc_layer."):]: v for k, v in sd.items() if "fc_layer" in k})
+    x = torch.randn(3, 1024)
+    p = "point_cloud_encoder.fc_layer."
+    y = oracle._dense(x, sd[p + "0.weight"], sd[p + "0.bias"], False, torch.float32)
+    y = F.leaky_relu(F.group_norm(y, 16, sd[p + "1.weight"], sd[p + "1.bias"], eps=1e-5), 0.01)
+    y = oracle._dense(y, sd[p + "3.weight"], sd[p + "3.bias"], False, torch.float32)
+    y = F.leaky_relu(F.group_norm(y, 16, sd[p + "4.weight"], sd[p + "4.bias"], eps=1e-5), 0.01)
+    y = oracle._dense(y, sd[p + "6.weight"], sd[p + "6.bias"], False, torch.float32)
+    assert torch.allclose(y, fc(x), atol=1e-5, rtol=1e-5)
+
+    rng = np.random.RandomState(0)
+    xyz = (rng.uniform(-0.3, 0.3, size=(2, 300, 3)) + 0.5).astype(np.float32)
+    feats = torch.from_numpy(rng.normal(size=(2, 300, 64)).astype(np.float32))
+    spec = dict(npoint=16, radius=0.3, nsample=128, mlp=(67, 128, 128, 256))
+    ws = [(sd[f"point_cloud_encoder.SA_modules.1.mlps.0.{2 * l}.weight"], sd[f"point_cloud_encoder.SA_modules.1.mlps.0.{2 * l}.bias"]) for l in range(3)]
+    new_xyz, out, aux = oracle.sa_module(xyz, feats, spec, ws, return_aux=True)
+    # explicit pointnet2 formulation: [B,C,N] features, grouping_operation, Conv2d 1x1
+    f_cn = feats.permute(0, 2, 1).contiguous().numpy()
+    g_xyz = oracle.grouping_operation(np.ascontiguousarray(xyz.transpose(0, 2, 1)), aux["ball_idx"]) - new_xyz.transpose(0, 2, 1)[..., None]
+    g = torch.from_numpy(np.concatenate([g_xyz, oracle.grouping_operation(f_cn, aux["ball_idx"])], axis=1))  # [B,67,m,ns]
+    for w, b in ws:
+        g = F.relu(F.conv2d(g, w, b))
+    ref = F.max_pool2d(g, kernel_size=[1, g.size(3)]).squeeze(-1)   # [B,256,m]
+    assert torch.allclose(out.permute(0, 2, 1), ref, atol=1e-5, rtol=1e-5)
+
+
+def test_state_dict_layout(state_dict):
+    n = sum(v.numel() for v in state_dict.values())
+    assert n == 19068103                                              # parameter count
+    assert state_dict["point_cloud_encoder.SA_modules.0.mlps.0.0.weight"].shape == (64, 4, 1, 1)
+    assert state_dict["decoder.0.weight"].shape == (512, 2112)
+
+
+# ----------------------------------------------------------------------------- C ABI surface (no GPU needed)
+def test_shared_library_exports_every_declared_symbol():
+    from mpinets_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from mpinets_b200 import build
+        build.build()
+    header = open(os.path.join(ROOT, "include", "mpinets_b200.h")).read()
+    declared = set(re.findall(r"\b(mpn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mpn_ctx", "mpn_scene", "mpn_config", "mpn_status", "mpn_precision"}
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/mpinets_b200.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+
+
+def test_library_reports_errors_without_gpu():
+    from mpinets_b200 import _lib
+    lib = _lib.load()
+    assert b"mpinets_b200" in lib.mpn_version()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ctx = C.c_void_p()
+    cfg = _lib.MpnConfig(2048, 4096, 128, 40, 40, 1, 0)
+    rc = lib.mpn_ctx_create(0, C.byref(cfg), C.byref(ctx))
+    assert rc != 0 and len(lib.mpn_last_error()) > 0                 # fails loudly, no CPU fallback
+    with pytest.raises(_lib.MpnError):
+        from mpinets_b200.engine import Engine
+        Engine()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mpinets_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+                assert "mpn_oracle" not in src, f"{f} references the oracle library"
