@@ -150,6 +150,21 @@ int mpn_rollout(mpn_ctx* ctx, void* stream, int precision, const mpn_scene* scen
 /* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
 int64_t mpn_launch_count(mpn_ctx* ctx);
 
+/* per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline leg).
+ * mpn_profile(ctx, 1) starts recording, mpn_profile_read synchronises the device and returns, for each stage,
+ * the accumulated milliseconds and the number of timed launches since the last read. */
+#define MPN_NUM_STAGES 12
+enum { MPN_ST_FPS1 = 0, MPN_ST_SA1 = 1, MPN_ST_FPS2 = 2, MPN_ST_SA2 = 3, MPN_ST_SA3 = 4, MPN_ST_FC = 5, MPN_ST_HEADS = 6,
+       MPN_ST_UPDATE = 7, MPN_ST_SAMPLE_ROBOT = 8, MPN_ST_SWEEP = 9, MPN_ST_BUILD_CLOUD = 10, MPN_ST_OTHER = 11 };
+int mpn_profile(mpn_ctx* ctx, int enable);
+int mpn_profile_read(mpn_ctx* ctx, float* ms /*[MPN_NUM_STAGES]*/, int64_t* launches /*[MPN_NUM_STAGES]*/);
+
+/* tensor-core self-test: D[128][N] fp32 = A[128][K] bf16 * B[N][K]^T bf16 on one CTA with the smem-descriptor
+ * convention `mode` (0: interleaved LBO=K-dir; 1: interleaved, LBO/SBO swapped; 2: 128B swizzle; 3: interleaved MN-first).
+ * status (device int) is set to 1 when the MMA completion barrier timed out. */
+int mpn_tc_selftest(mpn_ctx* ctx, void* stream, const void* a_bf16, const void* b_bf16, float* d, int N, int K, int mode,
+                    int* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpinets_b200.so")
 
 METRICS_COLS = 8
+STAGES = ("fps1", "sa1", "fps2", "sa2", "sa3", "fc", "heads", "update", "sample_robot", "sweep", "build_cloud", "other")
 PREC_FP32, PREC_BF16 = 0, 1
 
 EXPORTS = (
@@ -18,7 +19,7 @@ EXPORTS = (
     "mpn_load_weight", "mpn_weights_finalize", "mpn_fps", "mpn_ball_query", "mpn_gather_points", "mpn_group_points",
     "mpn_sa_forward", "mpn_fk", "mpn_sample_robot", "mpn_compute_spheres", "mpn_normalize_joints",
     "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_sweep_flags", "mpn_encoder_forward",
-    "mpn_policy_forward", "mpn_rollout", "mpn_launch_count",
+    "mpn_policy_forward", "mpn_rollout", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest",
 )
 
 
@@ -77,6 +78,9 @@ def load():
         "mpn_policy_forward": [P, P, I, P, P, I, I, P],
         "mpn_rollout": [P, P, I, SC, I, I, P, P, P, I, I, I, P, P],
         "mpn_launch_count": [P],
+        "mpn_profile": [P, I],
+        "mpn_tc_selftest": [P, P, P, P, P, I, I, I, P],
+        "mpn_profile_read": [P, C.POINTER(C.c_float), C.POINTER(C.c_int64)],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

@@ -20,6 +20,7 @@ void set_error(const char* fmt, ...) {
 int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, float* out, int ldo);
 int tc_prepare_weights(mpn_ctx* c);
 size_t tc_scratch_bytes(int B);
+int tc_probe(mpn_ctx* c, cudaStream_t s, const void* A, const void* B, float* D, int N, int K, int mode, int* status);
 
 template <typename T>
 static int dev_alloc(T** p, size_t n) {
@@ -150,11 +151,17 @@ static int encoder_forward(mpn_ctx* c, cudaStream_t s, int precision, const floa
   int r;
   if (precision == MPN_PREC_BF16) return tc_encoder_forward(c, s, cloud, B, N, out, ldo);
   // SA1: FPS over the 4-float rows of the cloud; features = mask column
-  if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz1))) return r;
-  if ((r = launch_sa_simt(c, s, 0, cloud, 4, cloud + 3, 4, B, N, w.xyz1, w.feat1, nullptr))) return r;
-  if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz2))) return r;
-  if ((r = launch_sa_simt(c, s, 1, w.xyz1, 3, w.feat1, 64, B, SA1_NPOINT, w.xyz2, w.feat2, nullptr))) return r;
-  if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr))) return r;
+  { StageTimer t(c, s, MPN_ST_FPS1);
+    if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz1))) return r; }
+  { StageTimer t(c, s, MPN_ST_SA1);
+    if ((r = launch_sa_simt(c, s, 0, cloud, 4, cloud + 3, 4, B, N, w.xyz1, w.feat1, nullptr))) return r; }
+  { StageTimer t(c, s, MPN_ST_FPS2);
+    if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz2))) return r; }
+  { StageTimer t(c, s, MPN_ST_SA2);
+    if ((r = launch_sa_simt(c, s, 1, w.xyz1, 3, w.feat1, 64, B, SA1_NPOINT, w.xyz2, w.feat2, nullptr))) return r; }
+  { StageTimer t(c, s, MPN_ST_SA3);
+    if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr))) return r; }
+  StageTimer tfc(c, s, MPN_ST_FC);
   if ((r = launch_linear(c, s, c->w.fc[0], w.feat3, 1024, B, w.fc_a, 4096, 0))) return r;
   if ((r = launch_groupnorm_lrelu(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0]))) return r;
   if ((r = launch_linear(c, s, c->w.fc[1], w.fc_a, 4096, B, w.fc_b, 2048, 0))) return r;
@@ -168,6 +175,7 @@ static int policy_forward(mpn_ctx* c, cudaStream_t s, int precision, const float
   const int CAT = ENC_DIM + QF_DIM;
   if ((r = encoder_forward(c, s, precision, cloud, B, N, w.cat, CAT))) return r;
   // feature_encoder (model.py:47-57)
+  StageTimer th(c, s, MPN_ST_HEADS);
   if ((r = launch_linear(c, s, c->w.fe[0], qn, 7, B, w.h_a, 32, 1))) return r;
   if ((r = launch_linear(c, s, c->w.fe[1], w.h_a, 32, B, w.h_b, 64, 1))) return r;
   if ((r = launch_linear(c, s, c->w.fe[2], w.h_b, 64, B, w.h_a, 128, 1))) return r;
@@ -287,6 +295,32 @@ int mpn_weights_finalize(mpn_ctx* c) {
 
 int64_t mpn_launch_count(mpn_ctx* c) { return c ? c->launches : 0; }
 
+int mpn_tc_selftest(mpn_ctx* c, void* stream, const void* a, const void* b, float* d, int N, int K, int mode, int* status) {
+  REQ_CTX(c);
+  MPN_REQUIRE(a && b && d && status, "mpn_tc_selftest: null pointer");
+  return tc_probe(c, (cudaStream_t)stream, a, b, d, N, K, mode, status);
+}
+
+int mpn_profile(mpn_ctx* c, int enable) {
+  REQ_CTX(c);
+  c->prof = enable != 0;
+  return MPN_OK;
+}
+
+int mpn_profile_read(mpn_ctx* c, float* ms, int64_t* launches) {
+  REQ_CTX(c);
+  MPN_REQUIRE(ms && launches, "mpn_profile_read: null output");
+  MPN_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < MPN_NUM_STAGES; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  for (auto& r : c->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.stage >= 0 && r.stage < MPN_NUM_STAGES) { ms[r.stage] += t; launches[r.stage]++; }
+    c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+  }
+  c->prof_recs.clear();
+  return MPN_OK;
+}
+
 // ---- pointnet2_ops
 int mpn_fps(mpn_ctx* c, void* stream, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz) {
   REQ_CTX(c);
@@ -405,6 +439,7 @@ int mpn_build_cloud(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, con
   MPN_REQUIRE(q0 && target && cloud, "mpn_build_cloud: null pointer");
   if (B == 0) return MPN_OK;
   if ((r = ensure_workspace(c, B))) return r;
+  StageTimer t(c, (cudaStream_t)stream, MPN_ST_BUILD_CLOUD);
   if ((r = launch_fk(c, (cudaStream_t)stream, q0, B, c->ws.frames, nullptr))) return r;
   return launch_build_cloud(c, (cudaStream_t)stream, *scene, B, c->ws.frames, target, problem0, cloud);
 }
@@ -464,11 +499,19 @@ int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene,
   if (check_every_step && (r = launch_sweep(c, s, *scene, B, traj, 1, stride, 0, 0, w.flags, w.first_step))) return r;
   for (int i = 1; i <= T; ++i) {
     if ((r = policy_forward(c, s, precision, cloud, w.qn, B, N, w.dq))) return r;
-    if ((r = launch_step_update(c, s, B, w.dq, w.qn, w.qu, target, w.done, early_exit, traj, stride, w.frames, w.eef, nullptr, i))) return r;
-    if ((r = launch_sample_robot(c, s, w.frames, B, c->cfg.n_robot, (uint32_t)i, cloud, N))) return r;
-    if (check_every_step && (r = launch_sweep(c, s, *scene, B, traj + (size_t)i * 7, 1, stride, i, 1, w.flags, w.first_step))) return r;
+    { StageTimer t(c, s, MPN_ST_UPDATE);
+      if ((r = launch_step_update(c, s, B, w.dq, w.qn, w.qu, target, w.done, early_exit, traj, stride, w.frames, w.eef, nullptr, i))) return r; }
+    { StageTimer t(c, s, MPN_ST_SAMPLE_ROBOT);
+      if ((r = launch_sample_robot(c, s, w.frames, B, c->cfg.n_robot, (uint32_t)i, cloud, N))) return r; }
+    if (check_every_step) {
+      StageTimer t(c, s, MPN_ST_SWEEP);
+      if ((r = launch_sweep(c, s, *scene, B, traj + (size_t)i * 7, 1, stride, i, 1, w.flags, w.first_step))) return r;
+    }
   }
-  if (!check_every_step && (r = launch_sweep(c, s, *scene, B, traj, T + 1, stride, 0, 0, w.flags, w.first_step))) return r;
+  if (!check_every_step) {
+    StageTimer t(c, s, MPN_ST_SWEEP);
+    if ((r = launch_sweep(c, s, *scene, B, traj, T + 1, stride, 0, 0, w.flags, w.first_step))) return r;
+  }
   return launch_finalize_metrics(c, s, B, w.eef, target, w.flags, w.first_step, w.done, T, metrics);
 }
 

@@ -93,9 +93,28 @@ struct mpn_ctx {
   mpn::Weights w;
   mpn::Workspace ws;
   int64_t launches = 0;
+  // stage profiler
+  bool prof = false;
+  struct StageRec { int stage; cudaEvent_t a, b; };
+  std::vector<StageRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
 };
 
 namespace mpn {
+
+// records a CUDA-event pair around a stage on the launching stream when profiling is enabled
+struct StageTimer {
+  mpn_ctx* c; cudaStream_t s; int idx = -1;
+  StageTimer(mpn_ctx* c_, cudaStream_t s_, int stage) : c(c_), s(s_) {
+    if (!c->prof) return;
+    auto get = [&]() { cudaEvent_t e; if (c->prof_pool.empty()) cudaEventCreate(&e); else { e = c->prof_pool.back(); c->prof_pool.pop_back(); } return e; };
+    mpn_ctx::StageRec r{stage, get(), get()};
+    cudaEventRecord(r.a, s);
+    c->prof_recs.push_back(r);
+    idx = (int)c->prof_recs.size() - 1;
+  }
+  ~StageTimer() { if (idx >= 0) cudaEventRecord(c->prof_recs[idx].b, s); }
+};
 
 // ---- geometry.cu
 int launch_fk(mpn_ctx* c, cudaStream_t s, const float* q, int B, float* frames, float* eef);

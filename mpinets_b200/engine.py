@@ -97,6 +97,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.mpn_launch_count(self._ctx))
 
+    def profile(self, enable: bool = True):
+        _lib.check(self.lib.mpn_profile(self._ctx, int(enable)))
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        """Synchronises; returns {stage: {"ms": total, "launches": n}} since the last read (CUDA events on the stream)."""
+        ms = (C.c_float * len(_lib.STAGES))()
+        n = (C.c_int64 * len(_lib.STAGES))()
+        _lib.check(self.lib.mpn_profile_read(self._ctx, ms, n))
+        return {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(_lib.STAGES)}
+
     def _scene(self, scene: Dict[str, torch.Tensor], B: int):
         s = _lib.MpnScene()
         keep = []
@@ -113,6 +123,15 @@ class Engine:
 
     def _empty(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def tc_selftest(self, a: torch.Tensor, b: torch.Tensor, mode: int):
+        """D = A[128,K] @ B[N,K]^T on one CTA via tcgen05 (bf16 in, fp32 out); returns (D, timed_out)."""
+        _check(a, "a", torch.bfloat16, self.device); _check(b, "b", torch.bfloat16, self.device)
+        N, K = b.shape
+        d = torch.zeros(128, N, device=self.device)
+        st = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.mpn_tc_selftest(self._ctx, self.stream, _p(a), _p(b), _p(d), N, K, mode, _p(st)))
+        return d, bool(st.item())
 
     # ------------------------------------------------------------------ pointnet2_ops
     def fps(self, xyz: torch.Tensor, npoint: int, return_xyz: bool = False):

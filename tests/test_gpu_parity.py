@@ -1,0 +1,358 @@
+"""GPU parity tests (-m gpu): every call goes through the C ABI (mpinets_b200.engine.Engine -> libmpinets_b200.so)
+and is compared with the CPU oracle on identical seeded inputs.
+
+Bars: bit-exact for geometry (FK frames, sphere centres, cloud coordinates, SDF values), FPS / ball-query indices and
+collision flags; 1e-5 for delta-q in the fp32 mode (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import to_dev
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+DQ_TOL = 1e-5   # north_star: "delta-q within 1e-5 fp32"
+
+
+def _problems(config, B, seed=0x4D50694E, problem0=0):
+    from mpinets_b200 import scenes
+    return scenes.config_problems(config, B, seed, problem0)
+
+
+def _rand_q(tables, n, seed):
+    rng = np.random.RandomState(seed)
+    lim = tables.joint_limits
+    return rng.uniform(lim[:, 0], lim[:, 1], size=(n, 7)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- robofin replacements
+def test_fk_bit_exact(engine, oracle, tables):
+    q = _rand_q(tables, 4099, 0)
+    q[0] = np.load(os.path.join(HERE, "golden", "fk_reference.npz"))["q"]
+    frames, eef = engine.fk(torch.from_numpy(q).cuda())
+    of, oe = oracle.fk(q)
+    assert np.array_equal(frames.cpu().numpy(), of)
+    assert np.array_equal(eef.cpu().numpy(), oe)
+    g = np.load(os.path.join(HERE, "golden", "fk_reference.npz"))
+    assert np.abs(eef[0, :, 3].cpu().numpy() - g["xyz"]).max() < 2e-7   # reference known-answer pair
+
+
+def test_joint_normalisation_bit_exact(engine, oracle, tables):
+    q = _rand_q(tables, 1000, 1)
+    qn = engine.normalize(torch.from_numpy(q).cuda())
+    assert np.array_equal(qn.cpu().numpy(), oracle.normalize(q, tables.joint_limits))
+    back = engine.unnormalize(qn)
+    assert np.array_equal(back.cpu().numpy(), oracle.unnormalize(qn.cpu().numpy(), tables.joint_limits))
+
+
+def test_collision_spheres_bit_exact(engine, oracle, tables):
+    q = _rand_q(tables, 513, 2)
+    got = engine.compute_spheres(torch.from_numpy(q).cuda()).cpu().numpy()
+    assert np.array_equal(got, oracle.spheres(q, tables))
+
+
+def test_sample_robot_bit_exact(engine, oracle, tables):
+    q = _rand_q(tables, 65, 3)
+    for step, n in ((0, 2048), (17, 2048), (3, 1024)):
+        got = engine.sample_robot(torch.from_numpy(q).cuda(), n, step).cpu().numpy()
+        exp = oracle.sample_robot(q, tables, n, engine.cfg.seed, step)
+        assert np.array_equal(got, exp)
+
+
+# ----------------------------------------------------------------------------- geometry.py replacements
+@pytest.mark.parametrize("tag", ["yaw", "free"])
+def test_sdf_matches_real_reference_fixture(engine, tag):
+    """CUDA vs the values produced by the real mpinets/geometry.py (tests/golden/make_golden.py)."""
+    from mpinets_b200.engine import Engine
+    g = np.load(os.path.join(HERE, "golden", "sdf_reference.npz"))
+    s = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_")}
+    e = Engine(max_cuboids=s["cuboid_dims"].shape[1], max_cylinders=s["cylinder_radii"].shape[1], tables=engine.tables)
+    sc = to_dev(s, [k for k in s if k.startswith(("cuboid", "cylinder"))])
+    pts = torch.from_numpy(s["points"]).cuda()
+    for which, key in ((1, "sdf_cuboids"), (2, "sdf_cylinders")):
+        got = e.sdf_points(sc, pts, which).cpu().numpy()
+        fin = np.isfinite(s[key])
+        assert (np.isfinite(got) == fin).all()
+        assert np.abs(got[fin] - s[key][fin]).max() < 2e-6
+    B, T, NS, _ = s["seq"].shape
+    got = e.sdf_points(sc, torch.from_numpy(s["seq"].reshape(B, T * NS, 3)).cuda(), 0).cpu().numpy()
+    assert ((got <= 0.06).any(-1) == s["has_collision_r006"]).all()
+    e.close()
+
+
+@pytest.mark.parametrize("config", [2, 3, 4])
+def test_sdf_points_bit_exact(engine, oracle, config):
+    p = _problems(config, 64)
+    rng = np.random.RandomState(config)
+    pts = rng.uniform(-1.0, 1.5, size=(64, 777, 3)).astype(np.float32)
+    for which in (0, 1, 2):
+        got = engine.sdf_points(to_dev(p), torch.from_numpy(pts).cuda(), which).cpu().numpy()
+        exp = oracle.sdf_points(p, pts, quirk=True, which=which)
+        assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("config,B,T", [(2, 512, 50), (3, 512, 70), (4, 1024, 70)])
+def test_collision_flags_bit_exact(engine, oracle, tables, config, B, T):
+    p = _problems(config, B)
+    rng = np.random.RandomState(10 + config)
+    # config-1 style poses: linear interpolation in joint space between two in-limit configurations
+    a, b = _rand_q(tables, B, 20 + config), _rand_q(tables, B, 30 + config)
+    w = np.linspace(0, 1, T, dtype=np.float32)[None, :, None]
+    traj = (a[:, None] * (1 - w) + b[:, None] * w).astype(np.float32)
+    flags, first = engine.sweep_flags(to_dev(p), torch.from_numpy(traj).cuda())
+    oflags, ofirst, margin = oracle.sweep_flags(p, traj, tables)
+    assert np.array_equal(flags.cpu().numpy(), oflags)                 # collision-flag match == 1.0
+    assert np.array_equal(first.cpu().numpy(), ofirst)
+    assert 0.02 < oflags.mean() < 0.999                                 # the test exercises both outcomes
+
+
+def test_collision_flags_edge_cases(engine, oracle, tables):
+    p = _problems(2, 8)
+    p["cuboid_dims"][0] = 0; p["cylinder_radii"][0] = 0                 # empty scene -> never in collision
+    p["cuboid_dims"][1, :, 1] = 0                                        # every cuboid zero-volume
+    p["cylinder_heights"][2] = 0
+    p["cuboid_dims"][3] = 1e-9                                           # below isclose atol -> masked
+    p["cuboid_centers"][4, 0] = 0; p["cuboid_dims"][4, 0] = 3.0          # robot fully inside a box -> always colliding
+    traj = np.repeat(_rand_q(tables, 8, 5)[:, None], 4, 1)
+    flags, first = engine.sweep_flags(to_dev(p), torch.from_numpy(traj).cuda())
+    oflags, ofirst, _ = oracle.sweep_flags(p, traj, tables)
+    assert np.array_equal(flags.cpu().numpy(), oflags) and np.array_equal(first.cpu().numpy(), ofirst)
+    assert flags[0].item() == 0 and flags[4].item() == 1 and first[4].item() == 0
+    # T = 1 and a maximum-length rollout (150 + start, run_inference.py:55)
+    for T in (1, 151):
+        tr = np.repeat(_rand_q(tables, 8, 6)[:, None], T, 1)
+        f, _ = engine.sweep_flags(to_dev(p), torch.from_numpy(tr).cuda())
+        assert np.array_equal(f.cpu().numpy(), oracle.sweep_flags(p, tr, tables)[0])
+
+
+@pytest.mark.parametrize("config", [2, 3, 4])
+def test_build_cloud_bit_exact(engine, oracle, tables, config):
+    p = _problems(config, 48, problem0=1000)
+    cloud = engine.build_cloud(to_dev(p), torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda(), problem0=1000)
+    exp = oracle.build_cloud(p["q0"], p["target"], p, tables, engine.cfg.seed, problem0=1000)
+    assert cloud.shape == (48, 6272, 4)
+    assert np.array_equal(cloud.cpu().numpy(), exp)
+
+
+def test_build_cloud_empty_scene(engine, oracle, tables):
+    p = _problems(2, 3)
+    for k in ("cuboid_dims", "cylinder_radii", "cylinder_heights"):
+        p[k][1] = 0
+    cloud = engine.build_cloud(to_dev(p), torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda())
+    assert np.array_equal(cloud.cpu().numpy(), oracle.build_cloud(p["q0"], p["target"], p, tables, engine.cfg.seed))
+
+
+# ----------------------------------------------------------------------------- pointnet2_ops replacements
+def _clouds(engine, oracle, tables, B, config=4):
+    p = _problems(config, B)
+    return oracle.build_cloud(p["q0"], p["target"], p, tables, engine.cfg.seed), p
+
+
+def test_fps_bit_exact_on_scene_clouds(engine, oracle, tables):
+    cloud, _ = _clouds(engine, oracle, tables, 16)
+    idx, new_xyz = engine.fps(torch.from_numpy(cloud).cuda(), 512, return_xyz=True)
+    exp = oracle.fps(cloud, 512)
+    assert np.array_equal(idx.cpu().numpy(), exp)                       # FPS indices bit-exact
+    gathered = np.stack([cloud[b, exp[b], :3] for b in range(16)])
+    assert np.array_equal(new_xyz.cpu().numpy(), gathered)
+    # second level: 512 -> 128 on xyz-only rows (stride 3)
+    idx2 = engine.fps(torch.from_numpy(gathered).cuda(), 128)
+    assert np.array_equal(idx2.cpu().numpy(), oracle.fps(gathered, 128))
+
+
+@pytest.mark.parametrize("N,m", [(1, 1), (5, 3), (31, 31), (33, 8), (100, 64), (512, 128), (513, 200), (1000, 512),
+                                 (4097, 64), (6272, 512), (8192, 16)])
+def test_fps_bit_exact_sizes_ties_and_skips(engine, oracle, N, m):
+    rng = np.random.RandomState(N)
+    xyz = rng.uniform(-1, 1, size=(3, N, 3)).astype(np.float32)
+    xyz[1] = np.round(xyz[1] * 4) / 4                                   # heavy ties: winner decided by tree order
+    xyz[2, : N // 3] *= 0.02                                            # |p|^2 <= 1e-3 skip rule
+    for stride in (3, 4):
+        a = xyz if stride == 3 else np.concatenate([xyz, np.ones((3, N, 1), np.float32)], -1)
+        got = engine.fps(torch.from_numpy(np.ascontiguousarray(a)).cuda(), m).cpu().numpy()
+        assert np.array_equal(got, oracle.fps(a, m))
+
+
+def test_ball_query_bit_exact(engine, oracle, tables):
+    cloud, _ = _clouds(engine, oracle, tables, 8)
+    idx = oracle.fps(cloud, 512)
+    new_xyz = np.stack([cloud[b, idx[b], :3] for b in range(8)])
+    got = engine.ball_query(0.05, 128, torch.from_numpy(cloud).cuda(), torch.from_numpy(new_xyz).cuda())
+    assert np.array_equal(got.cpu().numpy(), oracle.ball_query(0.05, 128, cloud, new_xyz))
+    idx2 = oracle.fps(new_xyz, 128)
+    nx2 = np.stack([new_xyz[b, idx2[b]] for b in range(8)])
+    got = engine.ball_query(0.3, 128, torch.from_numpy(new_xyz).cuda(), torch.from_numpy(nx2).cuda())
+    assert np.array_equal(got.cpu().numpy(), oracle.ball_query(0.3, 128, new_xyz, nx2))
+    # more than nsample hits, no hits, ragged N
+    rng = np.random.RandomState(0)
+    xyz = rng.uniform(0, 0.2, size=(2, 777, 3)).astype(np.float32)
+    q = np.concatenate([xyz[:, :30], np.full((2, 3, 3), 5.0, np.float32)], 1)
+    got = engine.ball_query(0.1, 16, torch.from_numpy(xyz).cuda(), torch.from_numpy(q).cuda())
+    assert np.array_equal(got.cpu().numpy(), oracle.ball_query(0.1, 16, xyz, q))
+
+
+def test_gather_and_group(engine, oracle):
+    rng = np.random.RandomState(0)
+    feat = rng.normal(size=(3, 5, 200)).astype(np.float32)
+    idx = rng.randint(0, 200, size=(3, 40)).astype(np.int32)
+    gidx = rng.randint(0, 200, size=(3, 10, 16)).astype(np.int32)
+    assert np.array_equal(engine.gather(torch.from_numpy(feat).cuda(), torch.from_numpy(idx).cuda()).cpu().numpy(),
+                          oracle.gather_operation(feat, idx))
+    assert np.array_equal(engine.group(torch.from_numpy(feat).cuda(), torch.from_numpy(gidx).cuda()).cpu().numpy(),
+                          oracle.grouping_operation(feat, gidx))
+
+
+def test_ops_reject_bad_tensors(engine):
+    with pytest.raises(RuntimeError):
+        engine.fps(torch.zeros(1, 10, 3), 2)                            # CPU tensor (pointnet2_ops: CUDA only)
+    with pytest.raises(RuntimeError):
+        engine.fps(torch.zeros(1, 10, 3, dtype=torch.float64).cuda(), 2)
+    with pytest.raises(RuntimeError):
+        engine.fps(torch.zeros(1, 10, 6).cuda()[:, :, :3], 2)           # non-contiguous
+    with pytest.raises(RuntimeError):
+        engine.fps(torch.zeros(1, 10, 3).cuda(), 11)                    # npoint > N -> library error surfaces
+
+
+# ----------------------------------------------------------------------------- set abstraction + network, fp32 mode
+def test_sa_modules_fp32(engine_w, oracle, tables, state_dict):
+    cloud, _ = _clouds(engine_w, oracle, tables, 4)
+    xyz = np.ascontiguousarray(cloud[..., :3])
+    feats = torch.from_numpy(np.ascontiguousarray(cloud[..., 3:]))
+    d_xyz, d_feats = torch.from_numpy(cloud).cuda(), torch.from_numpy(np.ascontiguousarray(cloud[..., 3:])).cuda()
+    for m, spec in enumerate(oracle.SA_SPECS):
+        ws = [(state_dict[f"point_cloud_encoder.SA_modules.{m}.mlps.0.{2 * l}.weight"],
+               state_dict[f"point_cloud_encoder.SA_modules.{m}.mlps.0.{2 * l}.bias"]) for l in range(3)]
+        o_xyz, o_feats, aux = oracle.sa_module(xyz, feats, spec, ws, return_aux=True)
+        res = engine_w.sa_forward(m, d_xyz, d_feats, debug=True)
+        if m < 2:
+            assert np.array_equal(res[2].cpu().numpy(), aux["fps_idx"])
+            assert np.array_equal(res[3].cpu().numpy(), aux["ball_idx"])
+            assert np.array_equal(res[0].cpu().numpy(), o_xyz)
+        got = res[1].cpu()
+        scale = o_feats.abs().max().item()
+        assert (got - o_feats).abs().max().item() <= 2e-6 * max(1.0, scale) + 2e-6
+        xyz, feats = o_xyz, o_feats
+        d_xyz = torch.from_numpy(o_xyz).cuda() if o_xyz is not None else None
+        d_feats = o_feats.contiguous().cuda()
+
+
+def test_policy_forward_fp32_within_1e5(engine_w, oracle, tables, state_dict):
+    cloud, p = _clouds(engine_w, oracle, tables, 6)
+    qn = oracle.normalize(p["q0"], tables.joint_limits)
+    dq = engine_w.policy_forward(torch.from_numpy(cloud).cuda(), torch.from_numpy(qn).cuda()).cpu()
+    exp = oracle.policy_forward(state_dict, cloud, qn)
+    exp64 = oracle.policy_forward(state_dict, cloud, qn, dtype=torch.float64).float()
+    err = (dq - exp).abs().max().item()
+    print("delta-q max-abs-err vs fp32 oracle:", err, " vs fp64 shadow:", (dq - exp64).abs().max().item(),
+          " |dq| max:", exp.abs().max().item())
+    assert err <= DQ_TOL
+    enc = engine_w.encoder_forward(torch.from_numpy(cloud).cuda()).cpu()
+    oenc = oracle.encoder_forward(state_dict, cloud)
+    assert (enc - oenc).abs().max().item() <= 1e-5 * max(1.0, oenc.abs().max().item())
+
+
+def test_rollout_fp32(engine_w, oracle, tables, state_dict):
+    """TrainingMotionPolicyNetwork.rollout + validation sweep (model.py:128-183,293-314), 3 lock-step steps."""
+    T = 3
+    p = _problems(4, 6)
+    sc = to_dev(p)
+    q0, tg = torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda()
+    cloud = engine_w.build_cloud(sc, q0, tg)
+    ocloud = cloud.cpu().numpy().copy()
+    traj, metrics = engine_w.rollout(sc, cloud, q0, tg, T)
+    torch.cuda.synchronize()
+    otraj = oracle.rollout(state_dict, ocloud, oracle.normalize(p["q0"], tables.joint_limits), tables, T, engine_w.cfg.seed)
+    traj_h = traj.cpu().numpy()
+    assert np.array_equal(traj_h[:, 0], p["q0"])
+    # step 1 starts from identical inputs: 1e-5 in normalised units -> scaled by the joint range after unnormalising
+    rng_ = (tables.joint_limits[:, 1] - tables.joint_limits[:, 0]) / 2
+    assert (np.abs(traj_h[:, 1] - otraj[:, 1]) / rng_).max() <= DQ_TOL
+    assert (np.abs(traj_h - otraj) / rng_).max() <= 1e-3               # later steps: bounded drift (FPS picks may differ)
+    # the cloud was updated in place with the robot at the last configuration (model.py:181)
+    exp_rows = oracle.sample_robot(traj_h[:, -1], tables, 2048, engine_w.cfg.seed, T)
+    assert np.array_equal(cloud[:, :2048].cpu().numpy(), exp_rows)
+    assert np.array_equal(cloud[:, 2048:].cpu().numpy(), ocloud[:, 2048:])   # obstacle / target rows untouched
+    # collision flags of the GPU trajectory: bit-exact against the oracle sweep of the same trajectory
+    oflags, ofirst, _ = oracle.sweep_flags(p, traj_h, tables)
+    m = metrics.cpu().numpy()
+    assert np.array_equal(m[:, 0].astype(np.uint8), oflags)
+    assert np.array_equal(m[:, 1].astype(np.int32), ofirst)
+    assert (m[:, 2] == T).all()
+    # final position error column = |FK(q_T).xyz - target.xyz|
+    _, eef = oracle.fk(traj_h[:, -1])
+    assert np.abs(m[:, 3] - np.linalg.norm(eef[:, :, 3] - p["target"][:, :, 3], axis=1)).max() < 1e-5
+    # per-step checking (config 3) gives the same flags
+    cloud2 = engine_w.build_cloud(sc, q0, tg)
+    traj2, metrics2 = engine_w.rollout(sc, cloud2, q0, tg, T, check_every_step=True)
+    assert torch.equal(traj2, traj) and torch.equal(metrics2[:, :2], metrics[:, :2])
+
+
+def test_rollout_early_exit_mask(engine_w, oracle, tables):
+    """run_inference.rollout_until_success (run_inference.py:171-187): a problem whose start already satisfies the
+    1 cm / 15 deg test stops after its first step and is frozen afterwards."""
+    p = _problems(2, 4)
+    # make problem 0's target equal to where the first step lands: run one step, then use its pose as the target
+    sc = to_dev(p)
+    q0, tg = torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda()
+    cloud = engine_w.build_cloud(sc, q0, tg)
+    traj, _ = engine_w.rollout(sc, cloud.clone(), q0, tg, 1)
+    _, eef = engine_w.fk(traj[:, 1].contiguous())
+    tg2 = tg.clone(); tg2[0] = eef[0]
+    cloud = engine_w.build_cloud(sc, q0, tg)    # same cloud (target rows differ from tg2 on purpose: same policy output)
+    traj3, metrics = engine_w.rollout(sc, cloud, q0, tg2, 3, early_exit=True)
+    m = metrics.cpu().numpy()
+    assert m[0, 2] == 1 and m[0, 5] == 1                                 # stopped at step 1, reached
+    assert torch.equal(traj3[0, 1], traj3[0, 2]) and torch.equal(traj3[0, 2], traj3[0, 3])
+    assert (m[1:, 2] == 3).all()
+
+
+# ----------------------------------------------------------------------------- full-size properties (BASELINE configs)
+def test_full_size_properties(engine, oracle, tables):
+    """4096 problems (configs[1]): size-independent properties of the GPU path + spot parity on a subset."""
+    B = 4096
+    p = _problems(2, B)
+    sc = to_dev(p)
+    q0, tg = torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda()
+    cloud = engine.build_cloud(sc, q0, tg)
+    assert cloud.shape == (B, 6272, 4)
+    c = cloud.cpu().numpy()
+    assert (c[:, :2048, 3] == 0).all() and (c[:, 2048:6144, 3] == 1).all() and (c[:, 6144:, 3] == 2).all()
+    assert np.isfinite(c).all()
+    sub = np.arange(0, B, 257)
+    for i, b in enumerate(sub):   # problem index enters the RNG counter
+        e1 = oracle.build_cloud(p["q0"][b:b + 1], p["target"][b:b + 1], {k: v[b:b + 1] for k, v in p.items()}, tables,
+                                engine.cfg.seed, problem0=int(b))
+        assert np.array_equal(c[b], e1[0])
+    # obstacle points lie on the scene surface: scene sdf <= ~0 (inside another primitive allowed) and never far outside
+    sdf = engine.sdf_points(sc, cloud[:, 2048:6144, :3].contiguous()).cpu().numpy()
+    assert sdf.max() < 1e-5
+    # FPS: indices unique, start at 0, idempotent on re-run (determinism)
+    idx = engine.fps(cloud, 512)
+    idx_again = engine.fps(cloud, 512)
+    assert torch.equal(idx, idx_again)
+    ih = idx.cpu().numpy()
+    assert (ih[:, 0] == 0).all()
+    assert all(len(set(r.tolist())) == 512 for r in ih[::64])
+    assert np.array_equal(ih[sub], oracle.fps(c[sub], 512))
+
+
+# ----------------------------------------------------------------------------- tensor-core self-test
+TC_MODE = int(os.environ.get("MPN_TC_MODE", "0"))   # smem-descriptor convention used by sa_tc.cu
+
+
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 128), (256, 128), (128, 256), (16, 64)])
+def test_tcgen05_selftest_gemm(engine, N, K):
+    """single-CTA tcgen05.mma GEMM (the descriptor / TMEM conventions of the fused kernels) vs torch fp32"""
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + K)
+    a = torch.randn(128, K, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
+    ref = a.float() @ b.float().t()
+    report = {}
+    for mode in range(4):
+        d, timeout = engine.tc_selftest(a, b, mode)
+        report[mode] = ("timeout" if timeout else float((d - ref).abs().max().item()))
+    print(f"tcgen05 selftest N={N} K={K}: max-abs-err per descriptor mode: {report}")
+    assert report[TC_MODE] != "timeout" and report[TC_MODE] < 1e-2 * K ** 0.5
