@@ -162,6 +162,8 @@ int mpn_profile_read(mpn_ctx* ctx, float* ms /*[MPN_NUM_STAGES]*/, int64_t* laun
 /* tensor-core self-test: D[128][N] fp32 = A[128][K] bf16 * B[N][K]^T bf16 on one CTA with the smem-descriptor
  * convention `mode` (0: interleaved LBO=K-dir; 1: interleaved, LBO/SBO swapped; 2: 128B swizzle; 3: interleaved MN-first).
  * status (device int) is set to 1 when the MMA completion barrier timed out. */
+/* synchronises and returns the tensor-core path's sticky error flag (1 = an MMA completion barrier timed out) */
+int mpn_tc_error(mpn_ctx* ctx, int* out);
 int mpn_tc_selftest(mpn_ctx* ctx, void* stream, const void* a_bf16, const void* b_bf16, float* d, int N, int K, int mode,
                     int* status);
 

@@ -20,6 +20,9 @@ void set_error(const char* fmt, ...) {
 int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, float* out, int ldo);
 int tc_prepare_weights(mpn_ctx* c);
 size_t tc_scratch_bytes(int B);
+int* tc_error_flag(mpn_ctx* c);
+int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
+                  int N, const float* new_xyz, float* new_feats);
 int tc_probe(mpn_ctx* c, cudaStream_t s, const void* A, const void* B, float* D, int N, int K, int mode, int* status);
 
 template <typename T>
@@ -301,6 +304,14 @@ int mpn_tc_selftest(mpn_ctx* c, void* stream, const void* a, const void* b, floa
   return tc_probe(c, (cudaStream_t)stream, a, b, d, N, K, mode, status);
 }
 
+int mpn_tc_error(mpn_ctx* c, int* out) {
+  REQ_CTX(c);
+  MPN_REQUIRE(out, "mpn_tc_error: null output");
+  MPN_CHECK_CUDA(cudaDeviceSynchronize());
+  MPN_CHECK_CUDA(cudaMemcpy(out, tc_error_flag(c), sizeof(int), cudaMemcpyDeviceToHost));
+  return MPN_OK;
+}
+
 int mpn_profile(mpn_ctx* c, int enable) {
   REQ_CTX(c);
   c->prof = enable != 0;
@@ -355,7 +366,8 @@ int mpn_sa_forward(mpn_ctx* c, void* stream, int module, int precision, const fl
                    int feat_stride, int B, int N, float* new_xyz, float* new_feats, int32_t* fps_idx, int32_t* ball_idx) {
   REQ_CTX(c); REQ_WEIGHTS(c);
   MPN_REQUIRE(module >= 0 && module <= 2, "mpn_sa_forward: module must be 0..2");
-  MPN_REQUIRE(precision == MPN_PREC_FP32, "mpn_sa_forward: per-module entry point is fp32 only (bf16 runs through mpn_encoder_forward)");
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || (precision == MPN_PREC_BF16 && module < 2),
+              "mpn_sa_forward: bf16 per-module entry covers modules 0 and 1");
   MPN_REQUIRE(xyz && feats && new_feats && stride >= 3, "mpn_sa_forward: null pointer");
   static const int cfeat[3] = {1, 64, 256};
   MPN_REQUIRE(feat_stride >= cfeat[module], "mpn_sa_forward: feat_stride too small");
@@ -368,6 +380,7 @@ int mpn_sa_forward(mpn_ctx* c, void* stream, int module, int precision, const fl
   int npoint = module == 0 ? SA1_NPOINT : SA2_NPOINT;
   int32_t* idx = fps_idx ? fps_idx : reinterpret_cast<int32_t*>(c->ws.fc_a);
   if ((r = launch_fps(c, s, xyz, B, N, stride, npoint, idx, new_xyz))) return r;
+  if (precision == MPN_PREC_BF16) return tc_sa_forward(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats);
   return launch_sa_simt(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats, ball_idx);
 }
 

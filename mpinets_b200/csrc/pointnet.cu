@@ -18,25 +18,13 @@ __host__ __device__ inline int opt_n_threads(int work) {
   return p > 512 ? 512 : p;
 }
 
-// 64-bit ordering key: [ dist bits | ~(vt << 23 | k) ], 0 = "no candidate"
-__device__ __forceinline__ unsigned long long fps_key(float d, int vt, int k) {
-  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xFFFFFFFFu - (((uint32_t)vt << 23) | (uint32_t)k));
-}
-__device__ __forceinline__ int fps_key_index(unsigned long long key) {
-  return key == 0ull ? 0 : (int)((0xFFFFFFFFu - (uint32_t)key) & 0x7FFFFFu);
-}
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-    v = other > v ? other : v;
-  }
-  return v;
-}
-
+// Ordering key of a candidate: (distance bits, low word) compared lexicographically, larger wins.
+//   low = 0xFFFFFFFF - (bitrev(k mod block) << 23 | k)   (smaller bit-reversed thread id, then smaller k, wins ties)
+// "no candidate" is (0, 0) and decodes to index 0 (best = -1 / besti = 0 of the reference kernel).
 // One CTA (FPS_THREADS threads) per problem.  Thread t owns points k = t + i*FPS_THREADS held in registers together
-// with their running min-distance; the cloud also sits in shared memory for the broadcast read of the winner.
-// One barrier per round (cross-warp slots are double-buffered by round parity).
+// with their running min-distance (skipped / padding slots carry temp = -1 and can never win); the cloud also sits in
+// shared memory for the broadcast read of the winner.  Warp and CTA reductions are two redux.sync each; one barrier
+// per round (cross-warp slots are double-buffered by round parity).
 constexpr int FPS_THREADS = 512;
 
 template <int PPT>
@@ -44,17 +32,16 @@ __global__ void __launch_bounds__(FPS_THREADS, (PPT > 8 ? 2 : 1))
 fps_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int vbs, int32_t* __restrict__ idx,
            float* __restrict__ new_xyz) {
   extern __shared__ float4 spts[];  // [N]
-  __shared__ unsigned long long slot[2][FPS_THREADS / 32];
+  __shared__ uint2 slot[2][FPS_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int vbits = 31 - __clz(vbs);
   const float* p = xyz + (size_t)b * N * stride;
   float px[PPT], py[PPT], pz[PPT], temp[PPT];
-  uint32_t valid = 0;
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
     int k = tid + i * FPS_THREADS;
     px[i] = py[i] = pz[i] = 0.f;
-    temp[i] = 1e10f;
+    temp[i] = -1.0f;
     if (k < N) {
       float x, y, z;
       if (stride == 4) {
@@ -66,7 +53,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int vbs
       px[i] = x; py[i] = y; pz[i] = z;
       spts[k] = make_float4(x, y, z, 0.f);
       float mag = ffma(z, z, ffma(y, y, fmul(x, x)));
-      if (!(mag <= 1e-3f)) valid |= 1u << i;
+      if (!(mag <= 1e-3f)) temp[i] = 1e10f;
     }
   }
   int32_t* out = idx + (size_t)b * npoint;
@@ -78,26 +65,30 @@ fps_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int vbs
     if (oxyz) { float4 v = spts[0]; oxyz[0] = v.x; oxyz[1] = v.y; oxyz[2] = v.z; }
   }
   for (int j = 1; j < npoint; ++j) {
-    float4 c = spts[old];
-    unsigned long long best = 0ull;
+    const float4 c = spts[old];
+    float bd = -1.0f;
+    int bi = 0;
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
-      if (valid & (1u << i)) {
-        float d = dist2(px[i], py[i], pz[i], c.x, c.y, c.z);
-        float d2 = fminf(d, temp[i]);
-        temp[i] = d2;
-        int k = tid + i * FPS_THREADS;
-        int vt = vbits ? (int)(__brev((uint32_t)(k & (vbs - 1))) >> (32 - vbits)) : 0;
-        unsigned long long key = fps_key(d2, vt, k);
-        best = key > best ? key : best;
-      }
+      float d2 = fminf(dist2(px[i], py[i], pz[i], c.x, c.y, c.z), temp[i]);
+      temp[i] = d2;
+      if (d2 > bd) { bd = d2; bi = i; }   // strict: first (smallest k) of equal distances within the thread
     }
-    best = warp_max_u64(best);
-    if (lane == 0) slot[j & 1][warp] = best;
+    uint32_t dbits = 0u, low = 0u;
+    if (bd >= 0.0f) {
+      const int k = tid + bi * FPS_THREADS;
+      const uint32_t vt = vbits ? (__brev((uint32_t)(k & (vbs - 1))) >> (32 - vbits)) : 0u;
+      dbits = __float_as_uint(bd);
+      low = 0xFFFFFFFFu - ((vt << 23) | (uint32_t)k);
+    }
+    uint32_t m = __reduce_max_sync(0xffffffffu, dbits);
+    uint32_t l = __reduce_max_sync(0xffffffffu, dbits == m ? low : 0u);
+    if (lane == 0) slot[j & 1][warp] = make_uint2(m, l);
     __syncthreads();
-    unsigned long long v = lane < FPS_THREADS / 32 ? slot[j & 1][lane] : 0ull;
-    v = warp_max_u64(v);
-    old = fps_key_index(v);
+    uint2 v = lane < FPS_THREADS / 32 ? slot[j & 1][lane] : make_uint2(0u, 0u);
+    uint32_t M = __reduce_max_sync(0xffffffffu, v.x);
+    uint32_t L = __reduce_max_sync(0xffffffffu, v.x == M ? v.y : 0u);
+    old = (M == 0u && L == 0u) ? 0 : (int)((0xFFFFFFFFu - L) & 0x7FFFFFu);
     if (tid == 0) {
       out[j] = old;
       if (oxyz) { float4 w = spts[old]; oxyz[3 * j] = w.x; oxyz[3 * j + 1] = w.y; oxyz[3 * j + 2] = w.z; }

@@ -1,10 +1,454 @@
-// sa_tc.cu -- bf16 tcgen05 tensor-core path (placeholder until the tcgen05 kernels land).
+// sa_tc.cu -- bf16 tcgen05 tensor-core path of the PointNet++ encoder (throughput mode, MPN_PREC_BF16).
+//
+// Replaces the same reference code as sa_simt.cu (pointnet2_ops QueryAndGroup + Conv2d1x1/ReLU x3 + max_pool2d inside
+// PointnetSAModule, mpinets/model.py:365-383) with ONE fused kernel per set-abstraction level:
+//
+//   CTA = one problem, 256 threads = two independent warpgroups (WG) that ping-pong over the problem's centroids, so one
+//   WG's SIMT work (ball query, gather, epilogues) overlaps the other WG's MMAs on the single tensor pipe.
+//   per centroid, per WG:  ball query (index order kept by ballot + prefix popcount, 4 warps scan 4 segments)
+//     -> gather the 128 neighbours' rows straight into the UMMA A-operand layout in shared memory (bf16, K-major
+//        8x16B core matrices)  -> tcgen05.mma layer 1 (accumulator in TMEM)  -> epilogue: tcgen05.ld, +bias, ReLU, bf16,
+//        written back over the same smem buffer as the next layer's A operand -> layer 2 -> layer 3 -> max over the 128
+//        neighbours -> one pooled row to HBM.  Weights stay resident in shared memory for the whole CTA.
+//   Last layer of SA2 runs transposed (D^T = W3 * A^T: TMEM lane = output channel, column = neighbour) so the max-pool is a
+//   per-thread register reduction; SA1 (64 channels = half an M tile) pools with redux.sync instead.
+//
+// K order of layer 1 is [features..., dx, dy, dz, 0-pad] (a permutation of the reference's [dx,dy,dz,features] applied
+// to both operand and weight) so feature rows are copied as aligned 16-byte chunks.
 #include "engine.h"
+#include "spec_math.cuh"
+#include "tc_common.cuh"
+
 namespace mpn {
-int tc_prepare_weights(mpn_ctx*) { return MPN_OK; }
-size_t tc_scratch_bytes(int) { return 0; }
-int tc_encoder_forward(mpn_ctx*, cudaStream_t, const float*, int, int, float*, int) {
-  set_error("MPN_PREC_BF16: tensor-core path not built");
-  return MPN_ERR_STATE;
+using namespace tc;
+
+// ---------------------------------------------------------------------------------------------- weight packing
+struct TcWeights {
+  __nv_bfloat16* sa[3][3] = {{nullptr}};  // [Cout][Kpad] K-major, layer-0 K order permuted
+  int kpad[3][3] = {{0}};
+};
+static std::map<mpn_ctx*, TcWeights> g_tc;
+int* tc_error_flag(mpn_ctx* c);
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, int out, int in, int kpad, int rot, __nv_bfloat16* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out * kpad) return;
+  int o = i / kpad, k = i % kpad;
+  float v = 0.f;
+  if (k < in) {
+    int src = rot ? (k < in - 3 ? k + 3 : k - (in - 3)) : k;  // rot: [f..., dx,dy,dz] <- [dx,dy,dz, f...]
+    v = w[(size_t)o * in + src];
+  }
+  dst[i] = __float2bfloat16_rn(v);
 }
+
+int tc_prepare_weights(mpn_ctx* c) {
+  TcWeights& t = g_tc[c];
+  for (int m = 0; m < 3; ++m)
+    for (int l = 0; l < 3; ++l) {
+      const Linear& L = c->w.sa[m][l];
+      int kpad = (L.in + 15) / 16 * 16;
+      t.kpad[m][l] = kpad;
+      if (t.sa[m][l]) cudaFree(t.sa[m][l]);
+      MPN_CHECK_CUDA(cudaMalloc(&t.sa[m][l], (size_t)L.out * kpad * sizeof(__nv_bfloat16)));
+      int n = L.out * kpad;
+      pack_weight_kernel<<<(n + 255) / 256, 256>>>(L.w, L.out, L.in, kpad, (l == 0 && m > 0) ? 1 : 0, t.sa[m][l]);
+      MPN_CHECK_CUDA(cudaGetLastError());
+    }
+  MPN_CHECK_CUDA(cudaDeviceSynchronize());
+  return MPN_OK;
+}
+
+// scratch: feat1 bf16 [B][512][64] | SA3 operand rows bf16 [B*128][272] ([256 feats, x, y, z, 0-pad])
+constexpr int A3_K = 272;
+static size_t feat1_bytes(int B) { return ((size_t)B * SA1_NPOINT * 64 * sizeof(__nv_bfloat16) + 1023) / 1024 * 1024; }
+size_t tc_scratch_bytes(int B) { return feat1_bytes(B) + (size_t)B * SA2_NPOINT * A3_K * sizeof(__nv_bfloat16) + 1024; }
+
+// ---------------------------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ void wg_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+// global [rows][K] bf16 (K-major) -> smem interleaved core-matrix layout
+__device__ __forceinline__ void stage_weight(const __nv_bfloat16* __restrict__ g, int rows, int K, uint8_t* s) {
+  const int KC = K / 8;
+  for (int i = threadIdx.x; i < rows * KC; i += blockDim.x) {
+    int r = i / KC, kc = i - r * KC;
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * K + kc * 8));
+    *reinterpret_cast<uint4*>(s + kmajor_chunk_off(r, kc, KC)) = v;
+  }
+}
+
+// descriptor of K-step ks (16 elements) of a [rows][K] interleaved tile starting at row r0
+__device__ __forceinline__ uint64_t tile_desc(uint32_t base, int K, int r0, int ks) {
+  const int KC = K / 8;
+  return make_smem_desc(base + (uint32_t)((r0 >> 3) * KC * 128 + ks * 256), 128, KC * 128, LAYOUT_NONE);
+}
+
+// epilogue (standard form, thread = row): TMEM [128][NC] fp32 -> relu(acc + bias) -> bf16 -> X (next A operand, K = NC)
+template <int NC>
+__device__ __forceinline__ void epilogue_to_smem(uint32_t taddr, const float* __restrict__ bias, uint8_t* X, int row) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < NC; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t p[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int j = q * 8 + e * 2;
+        float a = fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f);
+        float b = fmaxf(__uint_as_float(v[j + 1]) + bias[c0 + j + 1], 0.f);
+        p[e] = pack_bf16(a, b);
+      }
+      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(row, (c0 >> 3) + q, NC / 8)) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+  }
+}
+
+// ball query by one warpgroup over points in shared memory (float4): same semantics as pointnet.cu
+template <int NS>
+__device__ __forceinline__ void wg_ball_query(const float4* __restrict__ pts, int N, float cx, float cy, float cz, float r2,
+                                              int* __restrict__ idx_s, int* __restrict__ wl /*[4][NS]*/, int* __restrict__ wcnt /*[4]*/,
+                                              int g, int wg_tid) {
+  const int warp = wg_tid >> 5, lane = wg_tid & 31;
+  const int seg = ((N + 3) / 4 + 31) & ~31;
+  const int k_begin = warp * seg, k_end = min(N, k_begin + seg);
+  int cnt = 0;
+  for (int k0 = k_begin; k0 < k_end && cnt < NS; k0 += 32) {
+    int k = k0 + lane;
+    bool hit = false;
+    if (k < k_end) {
+      float4 p = pts[k];
+      hit = dist2(cx, cy, cz, p.x, p.y, p.z) < r2;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    int pos = cnt + __popc(m & ((1u << lane) - 1u));
+    if (hit && pos < NS) wl[warp * NS + pos] = k;
+    cnt += __popc(m);
+  }
+  if (lane == 0) wcnt[warp] = min(cnt, NS);
+  wg_sync(g);
+  int total = 0, first = 0, base = 0;
+  bool have = false;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    int cw = wcnt[w];
+    if (w == warp) base = total;
+    if (!have && cw > 0) { first = wl[w * NS]; have = true; }
+    total += cw;
+  }
+  const int mine = wcnt[warp];
+  for (int l = lane; l < mine; l += 32)
+    if (base + l < NS) idx_s[base + l] = wl[warp * NS + l];
+  total = min(total, NS);
+  for (int l = total + wg_tid; l < NS; l += 128) idx_s[l] = first;
+  wg_sync(g);
+}
+
+// ---------------------------------------------------------------------------------------------- fused SA kernel
+// MODULE 0: SA1 (points = cloud rows float4 [N][4], feature = mask column), C = 64/64/64, KIN = 16
+// MODULE 1: SA2 (points = xyz1 [512][3], features = feat1 bf16 [512][64]), C = 128/128/256, KIN = 80
+template <int MODULE>
+struct SaCfg;
+template <>
+struct SaCfg<0> { static constexpr int KIN = 16, C1 = 64, C2 = 64, C3 = 64, NCENT = SA1_NPOINT; };
+template <>
+struct SaCfg<1> { static constexpr int KIN = 80, C1 = 128, C2 = 128, C3 = 256, NCENT = SA2_NPOINT; };
+
+template <int MODULE>
+struct SaSmem {
+  using C = SaCfg<MODULE>;
+  static constexpr int XK = (C::KIN > C::C1 ? C::KIN : C::C1) > C::C2 ? (C::KIN > C::C1 ? C::KIN : C::C1) : C::C2;
+  static constexpr size_t w1 = 0;
+  static constexpr size_t w2 = w1 + (size_t)C::C1 * C::KIN * 2;
+  static constexpr size_t w3 = w2 + (size_t)C::C2 * C::C1 * 2;
+  static constexpr size_t x0 = w3 + (size_t)C::C3 * C::C2 * 2;
+  static constexpr size_t x1 = x0 + (size_t)128 * XK * 2;
+  static constexpr size_t bias = x1 + (size_t)128 * XK * 2;                       // C1 + C2 + C3 floats
+  static constexpr size_t idx = bias + (size_t)(C::C1 + C::C2 + C::C3) * 4;       // [2][128] int
+  static constexpr size_t wl = idx + 2 * 128 * 4;                                 // [2][4][128] int
+  static constexpr size_t wcnt = wl + 2 * 4 * 128 * 4;                            // [2][4] int
+  static constexpr size_t red = wcnt + 64;                                        // [2][4][64] float (SA1 pooling)
+  static constexpr size_t bars = red + 2 * 4 * 64 * 4;                            // 2 mbarriers + tmem base
+  static constexpr size_t pts = (bars + 64 + 15) / 16 * 16;                       // float4 [N]
+  static size_t total(int N) { return pts + (size_t)N * 16 + 1024; }
+};
+
+template <int MODULE>
+__global__ void __launch_bounds__(256, 1)
+sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat16* __restrict__ feat_bf16,
+             const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
+             const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, const float* __restrict__ gb1,
+             const float* __restrict__ gb2, const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16,
+             int out_stride, int* __restrict__ err) {
+  using C = SaCfg<MODULE>;
+  using S = SaSmem<MODULE>;
+  constexpr int KIN = C::KIN, C1 = C::C1, C2 = C::C2, C3 = C::C3, NCENT = C::NCENT;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW1 = smem + S::w1;
+  uint8_t* sW2 = smem + S::w2;
+  uint8_t* sW3 = smem + S::w3;
+  float* sB1 = reinterpret_cast<float*>(smem + S::bias);
+  float* sB2 = sB1 + C1;
+  float* sB3 = sB2 + C2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 16);
+  float4* pts = reinterpret_cast<float4*>(smem + S::pts);
+
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 7;          // warpgroup
+  const int t = threadIdx.x & 127;         // thread in warpgroup == operand row / TMEM lane
+  const int wq = (threadIdx.x >> 5) & 3;   // warp's TMEM lane quarter
+  uint8_t* X = smem + (g == 0 ? S::x0 : S::x1);
+  int* idx_s = reinterpret_cast<int*>(smem + S::idx) + g * 128;
+  int* wl = reinterpret_cast<int*>(smem + S::wl) + g * 4 * 128;
+  int* wcnt = reinterpret_cast<int*>(smem + S::wcnt) + g * 4;
+  float* red = reinterpret_cast<float*>(smem + S::red) + g * 4 * 64;
+
+  // ---- one-time staging: weights, biases, points
+  stage_weight(gw1, C1, KIN, sW1);
+  stage_weight(gw2, C2, C1, sW2);
+  stage_weight(gw3, C3, C2, sW3);
+  for (int i = threadIdx.x; i < C1; i += 256) sB1[i] = gb1[i];
+  for (int i = threadIdx.x; i < C2; i += 256) sB2[i] = gb2[i];
+  for (int i = threadIdx.x; i < C3; i += 256) sB3[i] = gb3[i];
+  {
+    const float* p = xyz + (size_t)b * N * stride;
+    for (int k = threadIdx.x; k < N; k += 256) {
+      float4 v;
+      if (MODULE == 0) v = __ldg(reinterpret_cast<const float4*>(p) + k);   // (x, y, z, mask)
+      else v = make_float4(__ldg(p + (size_t)k * stride), __ldg(p + (size_t)k * stride + 1), __ldg(p + (size_t)k * stride + 2), 0.f);
+      pts[k] = v;
+    }
+  }
+  if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot + (uint32_t)g * 256;            // this WG's 256 columns
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);       // + this warp's lane quarter
+  const uint32_t aX = smem_u32(X), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  uint64_t* bar = &bars[g];
+  uint32_t phase = 0;
+  bool ok = true;
+
+  for (int j = g; j < NCENT && ok; j += 2) {
+    const float* cp = new_xyz + ((size_t)b * NCENT + j) * 3;
+    const float cx = cp[0], cy = cp[1], cz = cp[2];
+    wg_ball_query<NSAMPLE>(pts, N, cx, cy, cz, r2, idx_s, wl, wcnt, g, t);
+    // ---- gather row t of the layer-1 operand
+    {
+      const int k = idx_s[t];
+      const float4 p = pts[k];
+      const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
+      if (MODULE == 0) {
+        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KIN / 8)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u);
+        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KIN / 8)) = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        const uint4* f = reinterpret_cast<const uint4*>(feat_bf16 + ((size_t)b * N + k) * 64);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, q, KIN / 8)) = __ldg(f + q);
+        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KIN / 8)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 0.f), 0u, 0u);
+        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KIN / 8)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    wg_sync(g);
+    // ---- layer 1: D[128][C1] = A0[128][KIN] * W1[C1][KIN]^T
+    if (t == 0) {
+      tc_fence_after();
+      constexpr uint32_t id = make_idesc_bf16(128, C1);
+#pragma unroll
+      for (int ks = 0; ks < KIN / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aX, KIN, 0, ks), tile_desc(aW1, KIN, 0, ks), id, ks > 0);
+      mma_commit(bar);
+    }
+    ok = mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    epilogue_to_smem<C1>(tlane, sB1, X, t);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    wg_sync(g);
+    // ---- layer 2: D[128][C2] = A1[128][C1] * W2[C2][C1]^T
+    if (t == 0) {
+      tc_fence_after();
+      constexpr uint32_t id = make_idesc_bf16(128, C2);
+#pragma unroll
+      for (int ks = 0; ks < C1 / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aX, C1, 0, ks), tile_desc(aW2, C1, 0, ks), id, ks > 0);
+      mma_commit(bar);
+    }
+    ok = ok && mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    epilogue_to_smem<C2>(tlane, sB2, X, t);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    wg_sync(g);
+    if (MODULE == 1) {
+      // ---- layer 3 transposed: D^T[ch][nbr] = W3[ch tile][C2] * A2[128 nbr][C2]^T, two channel tiles of 128
+      if (t == 0) {
+        tc_fence_after();
+        constexpr uint32_t id = make_idesc_bf16(128, 128);
+#pragma unroll
+        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss(tmem + 128, tile_desc(aW3, C2, 0, ks), tile_desc(aX, C2, 0, ks), id, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aW3, C2, 128, ks), tile_desc(aX, C2, 0, ks), id, ks > 0);
+        mma_commit(bar);
+      }
+      ok = ok && mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+      __nv_bfloat16* o = out_bf16 + ((size_t)b * NCENT + j) * out_stride;
+#pragma unroll 1
+      for (int tile = 0; tile < 2; ++tile) {
+        float m = -3.0e38f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tlane + (tile == 0 ? 128 : 0) + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) m = fmaxf(m, __uint_as_float(v[q]));
+        }
+        o[tile * 128 + t] = __float2bfloat16_rn(fmaxf(m + sB3[tile * 128 + t], 0.f));
+      }
+      if (t < 8) {   // SA3 operand tail: [x, y, z, 0...] of this centroid (GroupAll uses uncentred xyz)
+        float v = t == 0 ? cx : (t == 1 ? cy : (t == 2 ? cz : 0.f));
+        o[C3 + t] = __float2bfloat16_rn(v);
+        o[C3 + 8 + t] = __float2bfloat16_rn(0.f);
+      }
+    } else {
+      // ---- layer 3 standard: D[128][64]; pool over rows with redux.sync on the (non-negative) post-ReLU bit patterns
+      if (t == 0) {
+        tc_fence_after();
+        constexpr uint32_t id = make_idesc_bf16(128, C3);
+#pragma unroll
+        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aX, C2, 0, ks), tile_desc(aW3, C2, 0, ks), id, ks > 0);
+        mma_commit(bar);
+      }
+      ok = ok && mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < C3; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tlane + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          float a = fmaxf(__uint_as_float(v[q]) + sB3[c0 + q], 0.f);
+          uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(a));
+          if ((t & 31) == q) red[wq * 64 + c0 + q] = __uint_as_float(mx);
+        }
+      }
+      wg_sync(g);
+      if (t < C3) {
+        float m = fmaxf(fmaxf(red[t], red[64 + t]), fmaxf(red[128 + t], red[192 + t]));
+        out_bf16[((size_t)b * NCENT + j) * out_stride + t] = __float2bfloat16_rn(m);
+      }
+    }
+    tc_fence_before();
+    wg_sync(g);   // TMEM and X are free for the next centroid of this warpgroup
+  }
+  if (!ok && t == 0) atomicExch(err, 1);
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
+// bf16 -> fp32 widening of the pooled SA2 rows for the (still fp32) group-all / FC stages
+__global__ void widen_kernel(const __nv_bfloat16* __restrict__ src, int rows, int src_stride, int cols, float* __restrict__ dst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  size_t r = i / cols, c = i % cols;
+  dst[i] = __bfloat162float(src[r * src_stride + c]);
+}
+
+int* tc_error_flag(mpn_ctx* c) {
+  static std::map<mpn_ctx*, int*> flags;
+  auto it = flags.find(c);
+  if (it != flags.end()) return it->second;
+  int* p = nullptr;
+  cudaMalloc(&p, sizeof(int));
+  cudaMemset(p, 0, sizeof(int));
+  flags[c] = p;
+  return p;
+}
+
+__global__ void narrow_kernel(const float* __restrict__ src, size_t rows, int src_stride, int cols, __nv_bfloat16* __restrict__ dst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  size_t r = i / cols, cc = i % cols;
+  dst[i] = __float2bfloat16_rn(src[r * src_stride + cc]);
+}
+
+template <int MODULE>
+static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
+                        int B, __nv_bfloat16* out, int out_stride) {
+  TcWeights& tw = g_tc[c];
+  size_t smem = SaSmem<MODULE>::total(N);
+  MPN_REQUIRE(smem <= 227 * 1024, "tensor-core SA%d: %d points do not fit shared memory", MODULE + 1, N);
+  MPN_CHECK_CUDA(cudaFuncSetAttribute(sa_tc_kernel<MODULE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const float r = MODULE == 0 ? SA1_RADIUS : SA2_RADIUS;
+  sa_tc_kernel<MODULE><<<B, 256, smem, s>>>(xyz, stride, N, feat, new_xyz, r * r, tw.sa[MODULE][0], tw.sa[MODULE][1], tw.sa[MODULE][2],
+                                            c->w.sa[MODULE][0].b, c->w.sa[MODULE][1].b, c->w.sa[MODULE][2].b, out, out_stride,
+                                            tc_error_flag(c));
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// per-module entry (tests / mpn_sa_forward with MPN_PREC_BF16): fp32 in, fp32 out, bf16 inside
+int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
+                  int N, const float* new_xyz, float* new_feats) {
+  Workspace& w = c->ws;
+  __nv_bfloat16* feat1 = reinterpret_cast<__nv_bfloat16*>(w.tc_scratch);
+  __nv_bfloat16* a3 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w.tc_scratch) + feat1_bytes(w.capacity));
+  int r;
+  if (module == 0) {
+    MPN_REQUIRE(stride == 4 && feats == xyz + 3 && feat_stride == 4, "bf16 SA1 takes the [B][N][4] cloud (features = 4th column)");
+    if ((r = launch_sa_tc<0>(c, s, xyz, 4, N, nullptr, new_xyz, B, feat1, 64))) return r;
+    size_t n = (size_t)B * SA1_NPOINT * 64;
+    widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(feat1, B * SA1_NPOINT, 64, 64, new_feats);
+  } else {
+    MPN_REQUIRE(module == 1 && N == SA1_NPOINT, "bf16 per-module entry supports modules 0 and 1 (N = 512 for module 1)");
+    size_t n = (size_t)B * N * 64;
+    narrow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(feats, (size_t)B * N, feat_stride, 64, feat1);
+    if ((r = launch_sa_tc<1>(c, s, xyz, stride, N, feat1, new_xyz, B, a3, A3_K))) return r;
+    size_t m = (size_t)B * SA2_NPOINT * 256;
+    widen_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(a3, B * SA2_NPOINT, A3_K, 256, new_feats);
+  }
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, float* out, int ldo) {
+  Workspace& w = c->ws;
+  int r;
+  __nv_bfloat16* feat1 = reinterpret_cast<__nv_bfloat16*>(w.tc_scratch);
+  __nv_bfloat16* a3 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w.tc_scratch) + feat1_bytes(w.capacity));
+  { StageTimer t(c, s, MPN_ST_FPS1);
+    if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz1))) return r; }
+  { StageTimer t(c, s, MPN_ST_SA1);
+    if ((r = launch_sa_tc<0>(c, s, cloud, 4, N, nullptr, w.xyz1, B, feat1, 64))) return r; }
+  { StageTimer t(c, s, MPN_ST_FPS2);
+    if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz2))) return r; }
+  { StageTimer t(c, s, MPN_ST_SA2);
+    if ((r = launch_sa_tc<1>(c, s, w.xyz1, 3, SA1_NPOINT, feat1, w.xyz2, B, a3, A3_K))) return r; }
+  { StageTimer t(c, s, MPN_ST_SA3);
+    size_t n = (size_t)B * SA2_NPOINT * 256;
+    widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a3, B * SA2_NPOINT, A3_K, 256, w.feat2);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr))) return r; }
+  StageTimer tfc(c, s, MPN_ST_FC);
+  if ((r = launch_linear(c, s, c->w.fc[0], w.feat3, 1024, B, w.fc_a, 4096, 0))) return r;
+  if ((r = launch_groupnorm_lrelu(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0]))) return r;
+  if ((r = launch_linear(c, s, c->w.fc[1], w.fc_a, 4096, B, w.fc_b, 2048, 0))) return r;
+  if ((r = launch_groupnorm_lrelu(c, s, w.fc_b, B, 2048, 16, c->w.gn_w[1], c->w.gn_b[1]))) return r;
+  return launch_linear(c, s, c->w.fc[2], w.fc_b, 2048, B, out, ldo, 0);
+}
+
 }  // namespace mpn

@@ -124,6 +124,11 @@ class Engine:
     def _empty(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def tc_error(self) -> bool:
+        v = C.c_int(0)
+        _lib.check(self.lib.mpn_tc_error(self._ctx, C.byref(v)))
+        return bool(v.value)
+
     def tc_selftest(self, a: torch.Tensor, b: torch.Tensor, mode: int):
         """D = A[128,K] @ B[N,K]^T on one CTA via tcgen05 (bf16 in, fp32 out); returns (D, timed_out)."""
         _check(a, "a", torch.bfloat16, self.device); _check(b, "b", torch.bfloat16, self.device)
@@ -167,17 +172,21 @@ class Engine:
         _lib.check(self.lib.mpn_group_points(self._ctx, self.stream, _p(feat), B, Cc, N, _p(idx), m, ns, _p(out)))
         return out
 
-    def sa_forward(self, module: int, xyz: torch.Tensor, feats: torch.Tensor, debug: bool = False):
+    def sa_forward(self, module: int, xyz: torch.Tensor, feats: torch.Tensor, debug: bool = False,
+                   precision: int = _lib.PREC_FP32):
         """xyz [B,N,3|4], feats point-major [B,N,C] -> (new_xyz [B,m,3] | None, new_feats [B,m,Cout] [, fps_idx, ball_idx])"""
-        _check(xyz, "xyz", device=self.device); _check(feats, "features", device=self.device)
+        _check(xyz, "xyz", device=self.device)
+        if not (feats.is_cuda and feats.dtype == torch.float32):
+            raise RuntimeError("features must be a CUDA float32 tensor")
         B, N, stride = xyz.shape
         npoint, cout = ((512, 64), (128, 256), (1, 1024))[module]
         new_xyz = self._empty(B, npoint, 3) if module < 2 else None
         out = self._empty(B, npoint, cout)
         fidx = self._empty(B, npoint, dtype=torch.int32) if debug and module < 2 else None
         bidx = self._empty(B, npoint, 128, dtype=torch.int32) if debug and module < 2 else None
-        _lib.check(self.lib.mpn_sa_forward(self._ctx, self.stream, module, _lib.PREC_FP32, _p(xyz), stride, _p(feats),
-                                           feats.shape[2], B, N, _p(new_xyz), _p(out), _p(fidx), _p(bidx)))
+        fstride = feats.stride(1) if feats.dim() == 3 else feats.shape[2]
+        _lib.check(self.lib.mpn_sa_forward(self._ctx, self.stream, module, precision, _p(xyz), stride, _p(feats),
+                                           fstride, B, N, _p(new_xyz), _p(out), _p(fidx), _p(bidx)))
         return (new_xyz, out, fidx, bidx) if debug else (new_xyz, out)
 
     # ------------------------------------------------------------------ robofin

@@ -343,7 +343,7 @@ def test_full_size_properties(engine, oracle, tables):
 TC_MODE = int(os.environ.get("MPN_TC_MODE", "0"))   # smem-descriptor convention used by sa_tc.cu
 
 
-@pytest.mark.parametrize("N,K", [(64, 64), (128, 128), (256, 128), (128, 256), (16, 64)])
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 128), (256, 128), (128, 256), (32, 64)])
 def test_tcgen05_selftest_gemm(engine, N, K):
     """single-CTA tcgen05.mma GEMM (the descriptor / TMEM conventions of the fused kernels) vs torch fp32"""
     g = torch.Generator(device="cpu").manual_seed(N * 1000 + K)
@@ -356,3 +356,56 @@ def test_tcgen05_selftest_gemm(engine, N, K):
         report[mode] = ("timeout" if timeout else float((d - ref).abs().max().item()))
     print(f"tcgen05 selftest N={N} K={K}: max-abs-err per descriptor mode: {report}")
     assert report[TC_MODE] != "timeout" and report[TC_MODE] < 1e-2 * K ** 0.5
+
+
+# ----------------------------------------------------------------------------- bf16 tensor-core mode
+# Tolerances of the throughput mode, against the oracle run with the SAME bf16 operand rounding (fp64 accumulate):
+# remaining differences are fp32-vs-fp64 accumulation order, which can flip a bf16 rounding of an intermediate
+# activation by one ulp (2^-8 relative).
+BF16_FEAT_RTOL = 2e-2
+
+
+def _sa_weights(sd, m):
+    return [(sd[f"point_cloud_encoder.SA_modules.{m}.mlps.0.{2 * l}.weight"], sd[f"point_cloud_encoder.SA_modules.{m}.mlps.0.{2 * l}.bias"])
+            for l in range(3)]
+
+
+def test_sa_modules_bf16_tensor_core(engine_w, oracle, tables, state_dict):
+    from mpinets_b200 import _lib
+    cloud, _ = _clouds(engine_w, oracle, tables, 5)
+    d_cloud = torch.from_numpy(cloud).cuda()
+    xyz = np.ascontiguousarray(cloud[..., :3])
+    feats = torch.from_numpy(np.ascontiguousarray(cloud[..., 3:]))
+    o_xyz1, o_f1, aux1 = oracle.sa_module(xyz, feats, oracle.SA_SPECS[0], _sa_weights(state_dict, 0), emulate_bf16=True,
+                                          dtype=torch.float64, return_aux=True)
+    nx, f1 = engine_w.sa_forward(0, d_cloud, d_cloud[..., 3:], precision=_lib.PREC_BF16)
+    assert not engine_w.tc_error()
+    assert np.array_equal(nx.cpu().numpy(), o_xyz1)
+    e1 = (f1.cpu().double() - o_f1).abs().max().item() / o_f1.abs().max().item()
+    print("SA1 bf16 tensor-core vs bf16-emulating oracle: rel err", e1)
+    assert e1 < BF16_FEAT_RTOL
+    # SA2 fed with the oracle's (bf16-representable) SA1 output
+    o_xyz2, o_f2, aux2 = oracle.sa_module(o_xyz1, o_f1.float(), oracle.SA_SPECS[1], _sa_weights(state_dict, 1), emulate_bf16=True,
+                                          dtype=torch.float64, return_aux=True)
+    nx2, f2 = engine_w.sa_forward(1, torch.from_numpy(o_xyz1).cuda(), o_f1.float().contiguous().cuda(), precision=_lib.PREC_BF16)
+    assert not engine_w.tc_error()
+    assert np.array_equal(nx2.cpu().numpy(), o_xyz2)
+    e2 = (f2.cpu().double() - o_f2).abs().max().item() / o_f2.abs().max().item()
+    print("SA2 bf16 tensor-core vs bf16-emulating oracle: rel err", e2)
+    assert e2 < BF16_FEAT_RTOL
+    # and against the fp32 path of the same module (sanity of the whole mode, not a parity bar)
+    _, f1_32 = engine_w.sa_forward(0, d_cloud, torch.from_numpy(np.ascontiguousarray(cloud[..., 3:])).cuda())
+    print("SA1 bf16 vs fp32 path: rel err", ((f1 - f1_32).abs().max() / f1_32.abs().max()).item())
+
+
+def test_policy_forward_bf16(engine_w, oracle, tables, state_dict):
+    from mpinets_b200 import _lib
+    cloud, p = _clouds(engine_w, oracle, tables, 6)
+    qn = oracle.normalize(p["q0"], tables.joint_limits)
+    dq = engine_w.policy_forward(torch.from_numpy(cloud).cuda(), torch.from_numpy(qn).cuda(), _lib.PREC_BF16).cpu()
+    assert not engine_w.tc_error()
+    exp32 = oracle.policy_forward(state_dict, cloud, qn)
+    expbf = oracle.policy_forward(state_dict, cloud, qn, emulate_bf16=True, dtype=torch.float64).float()
+    print("bf16 mode delta-q: max-abs-err vs bf16-emulating oracle", (dq - expbf).abs().max().item(),
+          " vs fp32 oracle", (dq - exp32).abs().max().item(), " |dq| max", exp32.abs().max().item())
+    assert (dq - exp32).abs().max().item() < 2e-2 * max(1.0, exp32.abs().max().item())
