@@ -138,6 +138,11 @@ int launch_sa_simt(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int
 // ---- linear.cu
 int launch_linear(mpn_ctx* c, cudaStream_t s, const Linear& L, const float* x, int ldx, int M, float* y, int ldy, int act);
 int launch_groupnorm_lrelu(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta);
+int launch_groupnorm_lrelu_bf16(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta,
+                                __nv_bfloat16* out);
+// ---- gemm_tc.cu (epi: 0 relu->bf16, 1 fp32, 2 relu + max over each 128-row tile -> bf16)
+int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int K, const float* bias,
+                   int M, int N, void* C, int ldc);
 int launch_step_update(mpn_ctx* c, cudaStream_t s, int B, const float* dq, float* qn, float* qu, const float* target,
                        int32_t* done, int early_exit, float* traj_out, int traj_stride, float* frames, float* eef,
                        float* metrics, int step);

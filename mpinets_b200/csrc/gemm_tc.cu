@@ -1,0 +1,175 @@
+// gemm_tc.cu -- tcgen05 GEMM for the row-shared layers of the encoder: the group-all module (SA3, model.py:383: rows =
+// B*128 points, 259->512->512->1024 + max over each problem's 128 rows) and the FC head (model.py:385-393).
+//
+//   C[M][N] = epilogue(A[M][K] * W[N][K]^T + bias)     A, W bf16 K-major in HBM, fp32 accumulate in TMEM.
+//   CTA tile 128 x 256, K staged 64 at a time through a 4-deep cp.async ring into the UMMA interleaved (8x16B core
+//   matrix) layout; one thread issues tcgen05.mma, completion per stage is tracked with tcgen05.commit -> mbarrier so a
+//   ring slot is only refilled after the MMAs that read it have retired; all 8 warps drain the 128x256 accumulator.
+//   EPI_RELU_BF16: relu -> bf16 rows;  EPI_F32: fp32 rows (GroupNorm follows);  EPI_MAXPOOL: relu + max over the tile's
+//   128 rows (= one problem) -> one bf16 row.
+#include "engine.h"
+#include "tc_common.cuh"
+
+namespace mpn {
+using namespace tc;
+
+enum { EPI_RELU_BF16 = 0, EPI_F32 = 1, EPI_MAXPOOL = 2 };
+constexpr int G_BM = 128, G_BN = 256, G_BK = 64, G_STAGES = 4;
+constexpr int G_A_BYTES = G_BM * G_BK * 2, G_W_BYTES = G_BN * G_BK * 2, G_STAGE_BYTES = G_A_BYTES + G_W_BYTES;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ W, int K, const float* __restrict__ bias,
+               int M, int N, void* __restrict__ Cout, int ldc, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t done[G_STAGES];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red[4][G_BN];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * G_BN;
+  const int nst = (K + G_BK - 1) / G_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < G_STAGES; ++s) mbar_init(&done[s], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  // stage loader: A rows m0.., W rows n0.., K chunk [st*64, st*64+64) -> interleaved layout with 8 chunks per row
+  auto load_stage = [&](int st) {
+    uint8_t* sA = smem + (size_t)(st % G_STAGES) * G_STAGE_BYTES;
+    uint8_t* sW = sA + G_A_BYTES;
+    const int k0 = st * G_BK;
+    const int kc_n = min(8, (K - k0) / 8);
+#pragma unroll
+    for (int i = 0; i < (G_BM * 8) / 256; ++i) {
+      int c = tid + i * 256, r = c >> 3, kc = c & 7;
+      if (kc < kc_n) {
+        int m = m0 + r;
+        const __nv_bfloat16* src = A + (size_t)min(m, M - 1) * lda + k0 + kc * 8;
+        cp_async16(smem_u32(sA + kmajor_chunk_off(r, kc, 8)), src, m < M ? 16u : 0u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < (G_BN * 8) / 256; ++i) {
+      int c = tid + i * 256, r = c >> 3, kc = c & 7;
+      if (kc < kc_n) cp_async16(smem_u32(sW + kmajor_chunk_off(r, kc, 8)), W + (size_t)(n0 + r) * K + k0 + kc * 8, 16u);
+    }
+  };
+
+  for (int s = 0; s < G_STAGES - 1; ++s) {
+    if (s < nst) load_stage(s);
+    cp_async_commit();
+  }
+  bool ok = true;
+  for (int it = 0; it < nst; ++it) {
+    cp_async_wait<G_STAGES - 2>();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sA = smem_u32(smem + (size_t)(it % G_STAGES) * G_STAGE_BYTES), sW = sA + G_A_BYTES;
+      const int ksteps = min(4, (K - it * G_BK) / 16);
+      constexpr uint32_t id = make_idesc_bf16(G_BM, G_BN);
+      for (int ks = 0; ks < ksteps; ++ks)
+        mma_bf16_ss(tmem, make_smem_desc(sA + ks * 256, 128, 1024, LAYOUT_NONE), make_smem_desc(sW + ks * 256, 128, 1024, LAYOUT_NONE), id,
+                    (it | ks) != 0);
+      mma_commit(&done[it % G_STAGES]);
+    }
+    const int nxt = it + G_STAGES - 1;
+    if (nxt < nst) {
+      if (it >= 1) ok = ok && mbar_wait(&done[(it - 1) % G_STAGES], ((it - 1) / G_STAGES) & 1);   // slot of stage it-1 is free
+      load_stage(nxt);
+    }
+    cp_async_commit();
+  }
+  ok = ok && mbar_wait(&done[(nst - 1) % G_STAGES], ((nst - 1) / G_STAGES) & 1);
+  tc_fence_after();
+  if (!ok && tid == 0) atomicExch(err, 1);
+
+  // ---- epilogue: warp (q = warp & 3) owns lanes 32q..32q+31, column half h = warp >> 2
+  const int q = warp & 3, h = warp >> 2, row = q * 32 + (tid & 31);
+  const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + h * 128;
+  const int m = m0 + row;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tl + c0, v);
+    tmem_ld_wait();
+    const int nb = n0 + h * 128 + c0;
+    if (EPI == EPI_RELU_BF16) {
+      if (m < M) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)m * ldc + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint32_t p[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            p[e] = pack_bf16(fmaxf(__uint_as_float(v[j + 2 * e]) + __ldg(bias + nb + j + 2 * e), 0.f),
+                             fmaxf(__uint_as_float(v[j + 2 * e + 1]) + __ldg(bias + nb + j + 2 * e + 1), 0.f));
+          *reinterpret_cast<uint4*>(o + j) = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+      }
+    } else if (EPI == EPI_F32) {
+      if (m < M) {
+        float* o = reinterpret_cast<float*>(Cout) + (size_t)m * ldc + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]) + __ldg(bias + nb + j), __uint_as_float(v[j + 1]) + __ldg(bias + nb + j + 1),
+                                                          __uint_as_float(v[j + 2]) + __ldg(bias + nb + j + 2), __uint_as_float(v[j + 3]) + __ldg(bias + nb + j + 3));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float a = m < M ? fmaxf(__uint_as_float(v[j]) + __ldg(bias + nb + j), 0.f) : 0.f;
+        uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(a));
+        if ((tid & 31) == j) red[q][h * 128 + c0 + j] = __uint_as_float(mx);
+      }
+    }
+  }
+  if (EPI == EPI_MAXPOOL) {
+    __syncthreads();
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)blockIdx.y * ldc + n0;
+    o[tid] = __float2bfloat16_rn(fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid])));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+int* tc_error_flag(mpn_ctx* c);
+
+int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int K, const float* bias,
+                   int M, int N, void* C, int ldc) {
+  MPN_REQUIRE(K % 16 == 0 && N % G_BN == 0 && lda % 8 == 0, "gemm_tc: K %% 16, N %% 256, lda %% 8 required (K=%d N=%d lda=%d)", K, N, lda);
+  MPN_REQUIRE(epi != EPI_MAXPOOL || M % G_BM == 0, "gemm_tc: max-pool epilogue needs M %% 128 == 0");
+  dim3 grid(N / G_BN, (M + G_BM - 1) / G_BM);
+  size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 1024;
+  int* err = tc_error_flag(c);
+#define GEMM_LAUNCH(E)                                                                                              \
+  do {                                                                                                              \
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gemm_tc_kernel<E><<<grid, 256, smem, s>>>(A, lda, W, K, bias, M, N, C, ldc, err);                               \
+  } while (0)
+  if (epi == EPI_RELU_BF16) GEMM_LAUNCH(EPI_RELU_BF16);
+  else if (epi == EPI_F32) GEMM_LAUNCH(EPI_F32);
+  else GEMM_LAUNCH(EPI_MAXPOOL);
+#undef GEMM_LAUNCH
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+}  // namespace mpn

@@ -71,7 +71,8 @@ int launch_linear(mpn_ctx* c, cudaStream_t s, const Linear& L, const float* x, i
 
 // GroupNorm(groups, C) (eps 1e-5, biased variance, affine) + LeakyReLU(0.01), in place.  One warp per (row, group).
 __global__ void __launch_bounds__(256) groupnorm_lrelu_kernel(float* __restrict__ x, int M, int C, int groups,
-                                                              const float* __restrict__ gamma, const float* __restrict__ beta) {
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              __nv_bfloat16* __restrict__ out_bf16) {
   int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= M * groups) return;
   int row = wid / groups, g = wid % groups, gs = C / groups;
@@ -89,13 +90,25 @@ __global__ void __launch_bounds__(256) groupnorm_lrelu_kernel(float* __restrict_
   for (int i = lane; i < gs; i += 32) {
     int ch = g * gs + i;
     float v = (p[i] - mean) * rstd * gamma[ch] + beta[ch];
-    p[i] = v > 0.f ? v : 0.01f * v;
+    v = v > 0.f ? v : 0.01f * v;
+    if (out_bf16) out_bf16[(size_t)row * C + ch] = __float2bfloat16_rn(v);
+    else p[i] = v;
   }
 }
 
 int launch_groupnorm_lrelu(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta) {
   int warps = M * groups;
-  groupnorm_lrelu_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(x, M, C, groups, gamma, beta);
+  groupnorm_lrelu_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(x, M, C, groups, gamma, beta, nullptr);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// same, reading fp32 and writing the bf16 operand of the next tensor-core GEMM
+int launch_groupnorm_lrelu_bf16(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta,
+                                __nv_bfloat16* out) {
+  int warps = M * groups;
+  groupnorm_lrelu_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(x, M, C, groups, gamma, beta, out);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

@@ -23,14 +23,18 @@ namespace mpn {
 using namespace tc;
 
 // ---------------------------------------------------------------------------------------------- weight packing
+constexpr int SA1_XK = 80, SA1_BIAS_COL = 64;   // SA1 operand rows: [64 values | 1.0 | 0 x15]
 struct TcWeights {
   __nv_bfloat16* sa[3][3] = {{nullptr}};  // [Cout][Kpad] K-major, layer-0 K order permuted
   int kpad[3][3] = {{0}};
+  __nv_bfloat16* fc[3] = {nullptr};       // [out][in]
 };
 static std::map<mpn_ctx*, TcWeights> g_tc;
 int* tc_error_flag(mpn_ctx* c);
 
-__global__ void pack_weight_kernel(const float* __restrict__ w, int out, int in, int kpad, int rot, __nv_bfloat16* __restrict__ dst) {
+// bias_col >= 0: the layer's bias is folded into the GEMM as K-column `bias_col` (the operand carries a 1.0 there)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int out, int in, int kpad, int rot, __nv_bfloat16* __restrict__ dst,
+                                   const float* __restrict__ bias = nullptr, int bias_col = -1) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= out * kpad) return;
   int o = i / kpad, k = i % kpad;
@@ -38,6 +42,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int out, int in,
   if (k < in) {
     int src = rot ? (k < in - 3 ? k + 3 : k - (in - 3)) : k;  // rot: [f..., dx,dy,dz] <- [dx,dy,dz, f...]
     v = w[(size_t)o * in + src];
+  } else if (k == bias_col) {
+    v = bias[o];
   }
   dst[i] = __float2bfloat16_rn(v);
 }
@@ -47,14 +53,23 @@ int tc_prepare_weights(mpn_ctx* c) {
   for (int m = 0; m < 3; ++m)
     for (int l = 0; l < 3; ++l) {
       const Linear& L = c->w.sa[m][l];
-      int kpad = (L.in + 15) / 16 * 16;
+      int kpad = m == 0 ? SA1_XK : (L.in + 15) / 16 * 16;   // SA1: every layer is [64][80] with the bias in column 64
       t.kpad[m][l] = kpad;
       if (t.sa[m][l]) cudaFree(t.sa[m][l]);
       MPN_CHECK_CUDA(cudaMalloc(&t.sa[m][l], (size_t)L.out * kpad * sizeof(__nv_bfloat16)));
       int n = L.out * kpad;
-      pack_weight_kernel<<<(n + 255) / 256, 256>>>(L.w, L.out, L.in, kpad, (l == 0 && m > 0) ? 1 : 0, t.sa[m][l]);
+      pack_weight_kernel<<<(n + 255) / 256, 256>>>(L.w, L.out, L.in, kpad, (l == 0 && m > 0) ? 1 : 0, t.sa[m][l],
+                                                   m == 0 ? L.b : nullptr, m == 0 ? SA1_BIAS_COL : -1);
       MPN_CHECK_CUDA(cudaGetLastError());
     }
+  for (int l = 0; l < 3; ++l) {
+    const Linear& L = c->w.fc[l];
+    if (t.fc[l]) cudaFree(t.fc[l]);
+    MPN_CHECK_CUDA(cudaMalloc(&t.fc[l], (size_t)L.out * L.in * sizeof(__nv_bfloat16)));
+    int n = L.out * L.in;
+    pack_weight_kernel<<<(n + 255) / 256, 256>>>(L.w, L.out, L.in, L.in, 0, t.fc[l]);
+    MPN_CHECK_CUDA(cudaGetLastError());
+  }
   MPN_CHECK_CUDA(cudaDeviceSynchronize());
   return MPN_OK;
 }
@@ -62,7 +77,12 @@ int tc_prepare_weights(mpn_ctx* c) {
 // scratch: feat1 bf16 [B][512][64] | SA3 operand rows bf16 [B*128][272] ([256 feats, x, y, z, 0-pad])
 constexpr int A3_K = 272;
 static size_t feat1_bytes(int B) { return ((size_t)B * SA1_NPOINT * 64 * sizeof(__nv_bfloat16) + 1023) / 1024 * 1024; }
-size_t tc_scratch_bytes(int B) { return feat1_bytes(B) + (size_t)B * SA2_NPOINT * A3_K * sizeof(__nv_bfloat16) + 1024; }
+static size_t a3_bytes(int B) { return ((size_t)B * SA2_NPOINT * A3_K * 2 + 1023) / 1024 * 1024; }
+static size_t h_bytes(int B) { return (size_t)B * SA2_NPOINT * 512 * 2; }     // SA3 hidden activations [B*128][512] bf16
+// layout: feat1 | a3 | h1 | h2 | feat3 bf16 [B][1024] | g1 bf16 [B][4096] | g2 bf16 [B][2048]
+size_t tc_scratch_bytes(int B) {
+  return feat1_bytes(B) + a3_bytes(B) + 2 * h_bytes(B) + (size_t)B * (1024 + 4096 + 2048) * 2 + 1024;
+}
 
 // ---------------------------------------------------------------------------------------------- device helpers
 __device__ __forceinline__ void wg_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
@@ -357,6 +377,201 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
   if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
+// ---------------------------------------------------------------------------------------------- SA1 (v2)
+// 512 threads = 4 warpgroups, each streaming its own centroids.  Operand rows are [64 values | 1.0 | 0-pad] (K = 80,
+// 10 core-matrix chunks) for all three layers, the 1.0 column multiplies the bias stored as weight column 64, so the
+// epilogue is tcgen05.ld -> cvt.rn.relu.bf16x2 -> st.shared.  The last layer is pooled over the 128 neighbours with a
+// signed-integer redux on the raw accumulator bits (max over non-negative floats == max over their bit patterns; a
+// negative result is clamped by the final ReLU).
+constexpr int SA1_NWG = 4;
+struct Sa1Smem {
+  static constexpr size_t w = 0;                                          // 3 x [64][80] bf16
+  static constexpr size_t x = w + 3 * 64 * SA1_XK * 2;                    // NWG x [128][80] bf16
+  static constexpr size_t idx = x + (size_t)SA1_NWG * 128 * SA1_XK * 2;   // [NWG][128] int
+  static constexpr size_t wl = idx + SA1_NWG * 128 * 4;                   // [NWG][4][128] int
+  static constexpr size_t wcnt = wl + SA1_NWG * 4 * 128 * 4;              // [NWG][4] int
+  static constexpr size_t red = wcnt + 64;                                // [NWG][4][64] int
+  static constexpr size_t bars = red + SA1_NWG * 4 * 64 * 4;              // NWG mbarriers + tmem slot
+  static constexpr size_t pts = (bars + 64 + 15) / 16 * 16;               // x[N] | y[N] | z[N] floats
+  static size_t total(int N) { return pts + (size_t)N * 12 + 1024; }
+};
+
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float first, float second) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+  return d;
+}
+__device__ __forceinline__ void wg_sync4(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+__global__ void __launch_bounds__(128 * SA1_NWG, 1)
+sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
+              const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
+              int* __restrict__ err) {
+  using S = Sa1Smem;
+  constexpr int KC = SA1_XK / 8, NS = NSAMPLE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW1 = smem + S::w;
+  uint8_t* sW2 = sW1 + 64 * SA1_XK * 2;
+  uint8_t* sW3 = sW2 + 64 * SA1_XK * 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * SA1_NWG);
+  float* px = reinterpret_cast<float*>(smem + S::pts);
+  float* py = px + N;
+  float* pz = py + N;
+
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 7, t = threadIdx.x & 127, wq = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+  uint8_t* X = smem + S::x + (size_t)g * 128 * SA1_XK * 2;
+  int* idx_s = reinterpret_cast<int*>(smem + S::idx) + g * 128;
+  int* wl = reinterpret_cast<int*>(smem + S::wl) + g * 4 * 128;
+  int* wcnt = reinterpret_cast<int*>(smem + S::wcnt) + g * 4;
+  int* red = reinterpret_cast<int*>(smem + S::red) + g * 4 * 64;
+  const float4* cl = reinterpret_cast<const float4*>(cloud) + (size_t)b * N;
+
+  stage_weight(gw1, 64, SA1_XK, sW1);
+  stage_weight(gw2, 64, SA1_XK, sW2);
+  stage_weight(gw3, 64, SA1_XK, sW3);
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    float4 v = __ldg(cl + k);
+    px[k] = v.x; py[k] = v.y; pz[k] = v.z;
+  }
+  // persistent tail of every operand row: chunk 8 = [1.0, 0...], chunk 9 = 0
+  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KC)) = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SA1_NWG; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 256);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot + (uint32_t)g * 64;
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+  const uint32_t aX = smem_u32(X), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  uint64_t* bar = &bars[g];
+  uint32_t phase = 0;
+  bool ok = true;
+  constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
+
+  for (int j = g; j < SA1_NPOINT && ok; j += SA1_NWG) {
+    const float* cp = new_xyz + ((size_t)b * SA1_NPOINT + j) * 3;
+    const float cx = cp[0], cy = cp[1], cz = cp[2];
+    // ---- ball query: warp wq scans its quarter of the cloud, 64 candidates per iteration
+    {
+      const int seg = ((N + 3) / 4 + 63) & ~63;
+      const int k_begin = wq * seg, k_end = min(N, k_begin + seg);
+      const unsigned lt = (1u << lane) - 1u;
+      int cnt = 0;
+      for (int k0 = k_begin; k0 < k_end && cnt < NS; k0 += 64) {
+        const int ka = k0 + lane, kb = ka + 32;
+        bool ha = false, hb = false;
+        if (ka < k_end) ha = dist2(cx, cy, cz, px[ka], py[ka], pz[ka]) < r2;
+        if (kb < k_end) hb = dist2(cx, cy, cz, px[kb], py[kb], pz[kb]) < r2;
+        const unsigned ma = __ballot_sync(0xffffffffu, ha), mb = __ballot_sync(0xffffffffu, hb);
+        if (ma | mb) {
+          const int pa = cnt + __popc(ma & lt), pb = cnt + __popc(ma) + __popc(mb & lt);
+          if (ha && pa < NS) wl[wq * NS + pa] = ka;
+          if (hb && pb < NS) wl[wq * NS + pb] = kb;
+          cnt += __popc(ma) + __popc(mb);
+        }
+      }
+      if (lane == 0) wcnt[wq] = min(cnt, NS);
+      wg_sync4(g);
+      int total = 0, first = 0, base = 0;
+      bool have = false;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int cw = wcnt[w];
+        if (w == wq) base = total;
+        if (!have && cw > 0) { first = wl[w * NS]; have = true; }
+        total += cw;
+      }
+      const int mine = wcnt[wq];
+      for (int l = lane; l < mine; l += 32)
+        if (base + l < NS) idx_s[base + l] = wl[wq * NS + l];
+      total = min(total, NS);
+      for (int l = total + t; l < NS; l += 128) idx_s[l] = first;
+      wg_sync4(g);
+    }
+    // ---- gather row t: [dx, dy, dz, mask, 0 x4 | 0 x8 | ... | 1, 0 x7 | 0 x8]
+    {
+      const int k = idx_s[t];
+      const float dx = fsub(px[k], cx), dy = fsub(py[k], cy), dz = fsub(pz[k], cz);
+      const float mask = __ldg(cloud + ((size_t)b * N + k) * 4 + 3);
+      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, mask), 0u, 0u);
+      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KC)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    wg_sync4(g);
+    // ---- layer 1: only K-steps 0 (inputs) and 4 (ones column -> bias) are non-zero
+    if (t == 0) {
+      tc_fence_after();
+      mma_bf16_ss(tmem, tile_desc(aX, SA1_XK, 0, 0), tile_desc(aW1, SA1_XK, 0, 0), IDESC, 0);
+      mma_bf16_ss(tmem, tile_desc(aX, SA1_XK, 0, 4), tile_desc(aW1, SA1_XK, 0, 4), IDESC, 1);
+      mma_commit(bar);
+    }
+#pragma unroll 1
+    for (int layer = 1; layer < 3; ++layer) {
+      ok = ok && mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+      // epilogue: relu + bf16 pack, 64 columns -> chunks 0..7 of this row
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tlane + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, (c0 >> 3) + q, KC)) =
+              make_uint4(cvt_relu_bf16x2(__uint_as_float(v[q * 8]), __uint_as_float(v[q * 8 + 1])),
+                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])),
+                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
+                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      wg_sync4(g);
+      if (t == 0) {
+        tc_fence_after();
+        const uint32_t aW = layer == 1 ? aW2 : aW3;
+#pragma unroll
+        for (int ks = 0; ks < SA1_XK / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aX, SA1_XK, 0, ks), tile_desc(aW, SA1_XK, 0, ks), IDESC, ks > 0);
+        mma_commit(bar);
+      }
+    }
+    ok = ok && mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    // ---- pool: max over the 128 rows of D[128][64]
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tlane + c0, v);
+      tmem_ld_wait();
+      int keep = 0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int mx = __reduce_max_sync(0xffffffffu, (int)v[q]);
+        keep = lane == q ? mx : keep;
+      }
+      red[wq * 64 + c0 + lane] = keep;
+    }
+    tc_fence_before();
+    wg_sync4(g);
+    if (t < 64) {
+      const int m = max(max(red[t], red[64 + t]), max(red[128 + t], red[192 + t]));
+      out_bf16[((size_t)b * SA1_NPOINT + j) * 64 + t] = __float2bfloat16_rn(fmaxf(__int_as_float(m), 0.f));
+    }
+  }
+  if (!ok && t == 0) atomicExch(err, 1);
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, 256);
+}
+
 // bf16 -> fp32 widening of the pooled SA2 rows for the (still fp32) group-all / FC stages
 __global__ void widen_kernel(const __nv_bfloat16* __restrict__ src, int rows, int src_stride, int cols, float* __restrict__ dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -387,6 +602,17 @@ template <int MODULE>
 static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
                         int B, __nv_bfloat16* out, int out_stride) {
   TcWeights& tw = g_tc[c];
+  if (MODULE == 0) {
+    size_t smem1 = Sa1Smem::total(N);
+    MPN_REQUIRE(smem1 <= 227 * 1024, "tensor-core SA1: %d points do not fit shared memory", N);
+    MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    sa1_tc_kernel<<<B, 128 * SA1_NWG, smem1, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
+                                                 tc_error_flag(c));
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    return MPN_OK;
+  }
   size_t smem = SaSmem<MODULE>::total(N);
   MPN_REQUIRE(smem <= 227 * 1024, "tensor-core SA%d: %d points do not fit shared memory", MODULE + 1, N);
   MPN_CHECK_CUDA(cudaFuncSetAttribute(sa_tc_kernel<MODULE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -437,18 +663,24 @@ int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, in
     if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz2))) return r; }
   { StageTimer t(c, s, MPN_ST_SA2);
     if ((r = launch_sa_tc<1>(c, s, w.xyz1, 3, SA1_NPOINT, feat1, w.xyz2, B, a3, A3_K))) return r; }
-  { StageTimer t(c, s, MPN_ST_SA3);
-    size_t n = (size_t)B * SA2_NPOINT * 256;
-    widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a3, B * SA2_NPOINT, A3_K, 256, w.feat2);
-    c->launches++;
-    MPN_CHECK_CUDA(cudaGetLastError());
-    if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr))) return r; }
+  TcWeights& tw = g_tc[c];
+  uint8_t* base = reinterpret_cast<uint8_t*>(w.tc_scratch) + feat1_bytes(w.capacity) + a3_bytes(w.capacity);
+  __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(base + h_bytes(w.capacity));
+  __nv_bfloat16* f3 = reinterpret_cast<__nv_bfloat16*>(base + 2 * h_bytes(w.capacity));
+  __nv_bfloat16* g1 = f3 + (size_t)w.capacity * 1024;
+  __nv_bfloat16* g2 = g1 + (size_t)w.capacity * 4096;
+  const int M3 = B * SA2_NPOINT;
+  { StageTimer t(c, s, MPN_ST_SA3);   // group-all module as three row-shared GEMMs; the last one pools each problem's 128 rows
+    if ((r = launch_gemm_tc(c, s, 0, a3, A3_K, tw.sa[2][0], A3_K, c->w.sa[2][0].b, M3, 512, h1, 512))) return r;
+    if ((r = launch_gemm_tc(c, s, 0, h1, 512, tw.sa[2][1], 512, c->w.sa[2][1].b, M3, 512, h2, 512))) return r;
+    if ((r = launch_gemm_tc(c, s, 2, h2, 512, tw.sa[2][2], 512, c->w.sa[2][2].b, M3, 1024, f3, 1024))) return r; }
   StageTimer tfc(c, s, MPN_ST_FC);
-  if ((r = launch_linear(c, s, c->w.fc[0], w.feat3, 1024, B, w.fc_a, 4096, 0))) return r;
-  if ((r = launch_groupnorm_lrelu(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0]))) return r;
-  if ((r = launch_linear(c, s, c->w.fc[1], w.fc_a, 4096, B, w.fc_b, 2048, 0))) return r;
-  if ((r = launch_groupnorm_lrelu(c, s, w.fc_b, B, 2048, 16, c->w.gn_w[1], c->w.gn_b[1]))) return r;
-  return launch_linear(c, s, c->w.fc[2], w.fc_b, 2048, B, out, ldo, 0);
+  if ((r = launch_gemm_tc(c, s, 1, f3, 1024, tw.fc[0], 1024, c->w.fc[0].b, B, 4096, w.fc_a, 4096))) return r;
+  if ((r = launch_groupnorm_lrelu_bf16(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0], g1))) return r;
+  if ((r = launch_gemm_tc(c, s, 1, g1, 4096, tw.fc[1], 4096, c->w.fc[1].b, B, 2048, w.fc_b, 2048))) return r;
+  if ((r = launch_groupnorm_lrelu_bf16(c, s, w.fc_b, B, 2048, 16, c->w.gn_w[1], c->w.gn_b[1], g2))) return r;
+  return launch_gemm_tc(c, s, 1, g2, 2048, tw.fc[2], 2048, c->w.fc[2].b, B, 2048, out, ldo);
 }
 
 }  // namespace mpn

@@ -1,0 +1,112 @@
+"""``mpinets.model`` surface (``/root/reference/mpinets/model.py``): PyTorch holds only the weights (same module tree and
+state-dict keys as the reference, so a Lightning checkpoint's ``state_dict`` loads unchanged); ``forward`` / ``rollout``
+run in ``libmpinets_b200.so``."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .pointnet2_modules import PointnetSAModule
+from .runtime import get_engine
+
+END_EFFECTOR_FRAME = "right_gripper"   # run_inference.py:51-55
+NUM_ROBOT_POINTS, NUM_OBSTACLE_POINTS, NUM_TARGET_POINTS, MAX_ROLLOUT_LENGTH = 2048, 4096, 128, 150
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
+
+class MPiNetsPointNet(nn.Module):
+    """model.py:355-426"""
+
+    def __init__(self):
+        super().__init__()
+        self.SA_modules = nn.ModuleList([
+            PointnetSAModule(npoint=512, radius=0.05, nsample=128, mlp=[1, 64, 64, 64], bn=False),
+            PointnetSAModule(npoint=128, radius=0.3, nsample=128, mlp=[64, 128, 128, 256], bn=False),
+            PointnetSAModule(mlp=[256, 512, 512, 1024], bn=False),
+        ])
+        self.fc_layer = nn.Sequential(nn.Linear(1024, 4096), nn.GroupNorm(16, 4096), nn.LeakyReLU(inplace=True),
+                                      nn.Linear(4096, 2048), nn.GroupNorm(16, 2048), nn.LeakyReLU(inplace=True),
+                                      nn.Linear(2048, 2048))
+
+
+class MotionPolicyNetwork(nn.Module):
+    """model.py:35-91.  ``precision``: "fp32" (1e-5 parity mode) or "bf16" (tcgen05 throughput mode)."""
+
+    def __init__(self, precision: str = "bf16"):
+        super().__init__()
+        self.point_cloud_encoder = MPiNetsPointNet()
+        self.feature_encoder = nn.Sequential(nn.Linear(7, 32), nn.LeakyReLU(), nn.Linear(32, 64), nn.LeakyReLU(),
+                                             nn.Linear(64, 128), nn.LeakyReLU(), nn.Linear(128, 128), nn.LeakyReLU(),
+                                             nn.Linear(128, 64))
+        self.decoder = nn.Sequential(nn.Linear(2048 + 64, 512), nn.LeakyReLU(), nn.Linear(512, 256), nn.LeakyReLU(),
+                                     nn.Linear(256, 128), nn.LeakyReLU(), nn.Linear(128, 7))
+        self.precision = precision
+        self._synced_device = None
+
+    # -- weights -> engine
+    def sync_engine(self, device: Optional[torch.device] = None):
+        eng = get_engine(device)
+        eng.load_state_dict(self.state_dict())
+        self._synced_device = eng.device
+        return eng
+
+    def _engine(self, like: torch.Tensor):
+        if self._synced_device != like.device:
+            return self.sync_engine(like.device)
+        return get_engine(like.device)
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._synced_device = None
+        return r
+
+    def forward(self, xyz: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+        """xyz [B,N,4], q [B,7] normalised -> delta q [B,7] (normalised space)"""
+        return self._engine(xyz).policy_forward(xyz.contiguous(), q.contiguous(), PRECISIONS[self.precision])
+
+    def encode(self, xyz: torch.Tensor) -> torch.Tensor:
+        return self._engine(xyz).encoder_forward(xyz.contiguous(), PRECISIONS[self.precision])
+
+    def rollout(self, batch: Dict[str, torch.Tensor], rollout_length: int, sampler: Optional[Callable] = None,
+                unnormalize: bool = False, scene: Optional[Dict[str, torch.Tensor]] = None) -> List[torch.Tensor]:
+        """TrainingMotionPolicyNetwork.rollout (model.py:128-183): lock-step, whole loop in one library call;
+        ``batch["xyz"]`` is updated in place.  ``sampler`` is accepted for signature compatibility (the engine resamples
+        the robot surface itself)."""
+        xyz, q = batch["xyz"], batch["configuration"]
+        if q.ndim == 1:
+            xyz, q = xyz.unsqueeze(0), q.unsqueeze(0)
+        eng = self._engine(xyz)
+        B = q.shape[0]
+        if scene is None:
+            keys = ("cuboid_centers", "cuboid_dims", "cuboid_quats", "cylinder_centers", "cylinder_radii", "cylinder_heights", "cylinder_quats")
+            scene = {k: batch[k].contiguous().float() for k in keys}
+        q0 = eng.unnormalize(q.contiguous())
+        target = batch.get("target_pose")
+        if target is None:
+            target = torch.eye(4, device=xyz.device)[:3].expand(B, 3, 4).contiguous()
+        traj, metrics = eng.rollout(scene, xyz, q0, target.contiguous(), rollout_length, precision=PRECISIONS[self.precision])
+        self.last_metrics = metrics
+        if unnormalize:
+            return [traj[:, t] for t in range(rollout_length + 1)]
+        return [eng.normalize(traj[:, t].contiguous()) for t in range(rollout_length + 1)]
+
+
+def rollout_until_success(mdl: MotionPolicyNetwork, q0: np.ndarray, target_pose: np.ndarray, point_cloud: torch.Tensor,
+                          scene: Dict[str, torch.Tensor], max_steps: int = MAX_ROLLOUT_LENGTH) -> np.ndarray:
+    """run_inference.rollout_until_success (run_inference.py:137-191) for B = 1 .. many problems in lock-step with a done
+    mask: returns the trajectories [B, T'+1, 7] truncated at each problem's stopping step (list when B > 1)."""
+    eng = mdl._engine(point_cloud)
+    q = torch.as_tensor(np.atleast_2d(q0), dtype=torch.float32, device=point_cloud.device)
+    tgt = torch.as_tensor(np.asarray(target_pose, dtype=np.float32).reshape(-1, 4, 4)[:, :3], device=point_cloud.device).contiguous()
+    traj, metrics = eng.rollout(scene, point_cloud, q, tgt, max_steps, early_exit=True, precision=PRECISIONS[mdl.precision])
+    steps = metrics[:, _lib_steps_col()].long().cpu().numpy()
+    out = [traj[b, : steps[b] + 1].cpu().numpy() for b in range(q.shape[0])]
+    return out[0] if len(out) == 1 else out
+
+
+def _lib_steps_col() -> int:
+    return 2   # MPN_M_STEPS

@@ -256,15 +256,18 @@ def _round_bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-def _dense(x, w, b, emulate_bf16, dtype):
+def _dense(x, w, b, emulate_bf16, dtype, round_bias=False):
     """x [..., Cin] @ w[Cout,Cin]^T + b, with optional bf16 operand rounding (fp32 products are exact,
-    accumulation in `dtype`)."""
+    accumulation in `dtype`).  round_bias: the bias is itself a bf16 GEMM operand (SA1 of the tensor-core mode folds
+    it into the contraction as an extra K column)."""
     if emulate_bf16:
         x = _round_bf16(x); w = _round_bf16(w)
+        if round_bias:
+            b = _round_bf16(b)
     return (x.to(dtype) @ w.to(dtype).t() + b.to(dtype))
 
 
-def sa_module(xyz, feats, spec, weights, emulate_bf16=False, dtype=torch.float32, return_aux=False):
+def sa_module(xyz, feats, spec, weights, emulate_bf16=False, dtype=torch.float32, return_aux=False, round_bias=None):
     """xyz np[B,N,3] fp32, feats torch[B,N,C] (row-major per point) -> (new_xyz np[B,m,3] | None, feats torch[B,m,Cout])
 
     Shared-MLP rows are [dx,dy,dz, features...] in the Conv2d input-channel order (QueryAndGroup, use_xyz=True)."""
@@ -284,8 +287,10 @@ def sa_module(xyz, feats, spec, weights, emulate_bf16=False, dtype=torch.float32
         new_xyz = None
         x = torch.cat([torch.from_numpy(xyz), feats.to(torch.float32)], dim=-1)[:, None]                      # [B,1,N,3+C]
     x = x.to(dtype)
+    if round_bias is None:
+        round_bias = emulate_bf16 and spec["npoint"] == 512   # SA1 of the bf16 mode (see _dense)
     for (w, b) in weights:
-        x = torch.relu(_dense(x, w.reshape(w.shape[0], -1), b, emulate_bf16, dtype))
+        x = torch.relu(_dense(x, w.reshape(w.shape[0], -1), b, emulate_bf16, dtype, round_bias))
     out = x.max(dim=2).values                                                                               # [B,m,Cout]
     if emulate_bf16 and spec["npoint"] is not None:
         out = _round_bf16(out.float()).to(dtype)   # hand-off tensors are stored in bf16 in the tensor-core mode
