@@ -28,8 +28,7 @@ template <int EPI>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ W, int K, const float* __restrict__ bias,
                int M, int N, void* __restrict__ Cout, int ldc, int* __restrict__ err) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
   __shared__ uint64_t done[G_STAGES];
   __shared__ uint32_t tmem_slot;
   __shared__ float red[4][G_BN];

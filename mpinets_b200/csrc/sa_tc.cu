@@ -205,8 +205,7 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
   using C = SaCfg<MODULE>;
   using S = SaSmem<MODULE>;
   constexpr int KIN = C::KIN, C1 = C::C1, C2 = C::C2, C3 = C::C3, NCENT = C::NCENT;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
   uint8_t* sW1 = smem + S::w1;
   uint8_t* sW2 = smem + S::w2;
   uint8_t* sW3 = smem + S::w3;
@@ -384,16 +383,18 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
 // signed-integer redux on the raw accumulator bits (max over non-negative floats == max over their bit patterns; a
 // negative result is clamped by the final ReLU).
 constexpr int SA1_NWG = 4;
+constexpr int SA1_BUCKETS = 4096, SA1_HCAP = 512;
 struct Sa1Smem {
   static constexpr size_t w = 0;                                          // 3 x [64][80] bf16
-  static constexpr size_t x = w + 3 * 64 * SA1_XK * 2;                    // NWG x [128][80] bf16
+  static constexpr size_t x = w + 3 * 64 * SA1_XK * 2;                    // NWG x [128][80] bf16 (aliased by the grid build)
   static constexpr size_t idx = x + (size_t)SA1_NWG * 128 * SA1_XK * 2;   // [NWG][128] int
-  static constexpr size_t wl = idx + SA1_NWG * 128 * 4;                   // [NWG][4][128] int
-  static constexpr size_t wcnt = wl + SA1_NWG * 4 * 128 * 4;              // [NWG][4] int
-  static constexpr size_t red = wcnt + 64;                                // [NWG][4][64] int
+  static constexpr size_t hits = idx + SA1_NWG * 128 * 4;                 // [NWG][HCAP] int  (fallback: [4][128] per-warp lists)
+  static constexpr size_t hcnt = hits + SA1_NWG * SA1_HCAP * 4;           // [NWG][2] hit counters + [NWG][4] fallback counts
+  static constexpr size_t red = hcnt + 128;                               // [NWG][4][64] int
   static constexpr size_t bars = red + SA1_NWG * 4 * 64 * 4;              // NWG mbarriers + tmem slot
-  static constexpr size_t pts = (bars + 64 + 15) / 16 * 16;               // x[N] | y[N] | z[N] floats
-  static size_t total(int N) { return pts + (size_t)N * 12 + 1024; }
+  static constexpr size_t bstart = (bars + 64 + 15) / 16 * 16;            // u16 [BUCKETS + 1]
+  static constexpr size_t pts = (bstart + (SA1_BUCKETS + 1) * 2 + 15) / 16 * 16;   // sorted x[N] | y[N] | z[N] floats | idx u16[N]
+  static size_t total(int N) { return pts + (size_t)N * 14 + 1024; }
 };
 
 __device__ __forceinline__ uint32_t cvt_relu_bf16x2(float first, float second) {
@@ -403,42 +404,87 @@ __device__ __forceinline__ uint32_t cvt_relu_bf16x2(float first, float second) {
 }
 __device__ __forceinline__ void wg_sync4(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
+// uniform hash grid: cell edge slightly above the query radius so that every point within r of a centroid lies in
+// one of the 27 cells around the centroid's cell even under fp32 rounding of the cell coordinates
+__device__ __forceinline__ int grid_coord(float v) { return (int)floorf((v + 8.0f) * (1.0f / 0.0501f)); }
+__device__ __forceinline__ uint32_t grid_bucket(int ix, int iy, int iz) {
+  return ((uint32_t)ix * 73856093u ^ (uint32_t)iy * 19349663u ^ (uint32_t)iz * 83492791u) & (SA1_BUCKETS - 1);
+}
+
 __global__ void __launch_bounds__(128 * SA1_NWG, 1)
 sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
               const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
               int* __restrict__ err) {
   using S = Sa1Smem;
   constexpr int KC = SA1_XK / 8, NS = NSAMPLE;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
   uint8_t* sW1 = smem + S::w;
   uint8_t* sW2 = sW1 + 64 * SA1_XK * 2;
   uint8_t* sW3 = sW2 + 64 * SA1_XK * 2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * SA1_NWG);
-  float* px = reinterpret_cast<float*>(smem + S::pts);
-  float* py = px + N;
-  float* pz = py + N;
+  uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + S::bstart);
+  float* sx = reinterpret_cast<float*>(smem + S::pts);
+  float* sy = sx + N;
+  float* sz = sy + N;
+  uint16_t* sidx = reinterpret_cast<uint16_t*>(sz + N);
 
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 7, t = threadIdx.x & 127, wq = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
   uint8_t* X = smem + S::x + (size_t)g * 128 * SA1_XK * 2;
   int* idx_s = reinterpret_cast<int*>(smem + S::idx) + g * 128;
-  int* wl = reinterpret_cast<int*>(smem + S::wl) + g * 4 * 128;
-  int* wcnt = reinterpret_cast<int*>(smem + S::wcnt) + g * 4;
+  int* hits = reinterpret_cast<int*>(smem + S::hits) + g * SA1_HCAP;
+  int* hcnt = reinterpret_cast<int*>(smem + S::hcnt) + g * 2;
+  int* fcnt = reinterpret_cast<int*>(smem + S::hcnt) + 2 * SA1_NWG + g * 4;
   int* red = reinterpret_cast<int*>(smem + S::red) + g * 4 * 64;
   const float4* cl = reinterpret_cast<const float4*>(cloud) + (size_t)b * N;
 
   stage_weight(gw1, 64, SA1_XK, sW1);
   stage_weight(gw2, 64, SA1_XK, sW2);
   stage_weight(gw3, 64, SA1_XK, sW3);
-  for (int k = threadIdx.x; k < N; k += blockDim.x) {
-    float4 v = __ldg(cl + k);
-    px[k] = v.x; py[k] = v.y; pz[k] = v.z;
+  // ---- hash-grid build (counting sort of the cloud by bucket); the counters alias the operand buffers
+  {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + S::x);
+    __shared__ uint32_t wsum[16];
+    for (int i = threadIdx.x; i < SA1_BUCKETS; i += blockDim.x) cnt[i] = 0u;
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const float4 v = __ldg(cl + k);
+      atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u);
+    }
+    __syncthreads();
+    constexpr int PER = SA1_BUCKETS / (128 * SA1_NWG);   // buckets per thread
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = cnt[threadIdx.x * PER + i]; sum += loc[i]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t v = lane < 16 ? wsum[lane] : 0u, iv = v;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+      if (lane < 16) wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = wsum[threadIdx.x >> 5] + inc - sum;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { bstart[threadIdx.x * PER + i] = (uint16_t)run; cnt[threadIdx.x * PER + i] = run; run += loc[i]; }
+    if (threadIdx.x == blockDim.x - 1) bstart[SA1_BUCKETS] = (uint16_t)N;
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const float4 v = __ldg(cl + k);
+      const uint32_t pos = atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u);
+      sx[pos] = v.x; sy[pos] = v.y; sz[pos] = v.z; sidx[pos] = (uint16_t)k;
+    }
+    __syncthreads();
   }
   // persistent tail of every operand row: chunk 8 = [1.0, 0...], chunk 9 = 0
   *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
   *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KC)) = make_uint4(0u, 0u, 0u, 0u);
+  if (t < 2) hcnt[t] = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < SA1_NWG; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
@@ -455,53 +501,90 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
   uint32_t phase = 0;
   bool ok = true;
   constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
+  const unsigned lt = (1u << lane) - 1u;
+  int it = 0;
 
-  for (int j = g; j < SA1_NPOINT && ok; j += SA1_NWG) {
+  for (int j = g; j < SA1_NPOINT && ok; j += SA1_NWG, ++it) {
     const float* cp = new_xyz + ((size_t)b * SA1_NPOINT + j) * 3;
     const float cx = cp[0], cy = cp[1], cz = cp[2];
-    // ---- ball query: warp wq scans its quarter of the cloud, 64 candidates per iteration
+    // ---- ball query over the 27 grid cells around the centroid (unordered hits), then rank-sort by point index
     {
-      const int seg = ((N + 3) / 4 + 63) & ~63;
-      const int k_begin = wq * seg, k_end = min(N, k_begin + seg);
-      const unsigned lt = (1u << lane) - 1u;
-      int cnt = 0;
-      for (int k0 = k_begin; k0 < k_end && cnt < NS; k0 += 64) {
-        const int ka = k0 + lane, kb = ka + 32;
-        bool ha = false, hb = false;
-        if (ka < k_end) ha = dist2(cx, cy, cz, px[ka], py[ka], pz[ka]) < r2;
-        if (kb < k_end) hb = dist2(cx, cy, cz, px[kb], py[kb], pz[kb]) < r2;
-        const unsigned ma = __ballot_sync(0xffffffffu, ha), mb = __ballot_sync(0xffffffffu, hb);
-        if (ma | mb) {
-          const int pa = cnt + __popc(ma & lt), pb = cnt + __popc(ma) + __popc(mb & lt);
-          if (ha && pa < NS) wl[wq * NS + pa] = ka;
-          if (hb && pb < NS) wl[wq * NS + pb] = kb;
-          cnt += __popc(ma) + __popc(mb);
+      int* hc = &hcnt[it & 1];
+      const int ix = grid_coord(cx), iy = grid_coord(cy), iz = grid_coord(cz);
+      uint32_t bk = 0x10000u + lane;   // lanes >= 27: unique dummies
+      if (lane < 27) bk = grid_bucket(ix + (lane % 3) - 1, iy + ((lane / 3) % 3) - 1, iz + (lane / 9) - 1);
+      const unsigned peers = __match_any_sync(0xffffffffu, bk);
+      const unsigned umask = __ballot_sync(0xffffffffu, lane < 27 && lane == __ffs(peers) - 1);
+      int ord = 0;
+      for (unsigned m = umask; m; m &= m - 1, ++ord) {
+        if ((ord & 3) != wq) continue;
+        const uint32_t bb = __shfl_sync(0xffffffffu, bk, __ffs(m) - 1);
+        const int s0 = bstart[bb], e0 = bstart[bb + 1];
+        for (int p0 = s0; p0 < e0; p0 += 32) {
+          const int p = p0 + lane;
+          const bool hit = p < e0 && dist2(cx, cy, cz, sx[p], sy[p], sz[p]) < r2;
+          const unsigned hm = __ballot_sync(0xffffffffu, hit);
+          if (hm) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(hc, __popc(hm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int pos = base + __popc(hm & lt);
+            if (hit && pos < SA1_HCAP) hits[pos] = sidx[p];
+          }
         }
       }
-      if (lane == 0) wcnt[wq] = min(cnt, NS);
       wg_sync4(g);
-      int total = 0, first = 0, base = 0;
-      bool have = false;
+      const int H = *hc;
+      if (t == 0) hcnt[(it + 1) & 1] = 0;
+      if (H <= SA1_HCAP) {
+        for (int h = t; h < H; h += 128) {
+          const int my = hits[h];
+          int rank = 0;
+          for (int i = 0; i < H; ++i) rank += hits[i] < my;
+          if (rank < NS) idx_s[rank] = my;
+        }
+        wg_sync4(g);
+        const int first = H > 0 ? idx_s[0] : 0;
+        for (int l = min(H, NS) + t; l < NS; l += 128) idx_s[l] = first;
+      } else {
+        // fallback (more hits than the list holds): pointnet2's linear scan in index order from global memory
+        int* wl = hits;
+        const int seg = ((N + 3) / 4 + 31) & ~31;
+        const int k_begin = wq * seg, k_end = min(N, k_begin + seg);
+        int cnt = 0;
+        for (int k0 = k_begin; k0 < k_end && cnt < NS; k0 += 32) {
+          const int k = k0 + lane;
+          bool hit = false;
+          if (k < k_end) { const float4 v = __ldg(cl + k); hit = dist2(cx, cy, cz, v.x, v.y, v.z) < r2; }
+          const unsigned hm = __ballot_sync(0xffffffffu, hit);
+          const int pos = cnt + __popc(hm & lt);
+          if (hit && pos < NS) wl[wq * NS + pos] = k;
+          cnt += __popc(hm);
+        }
+        if (lane == 0) fcnt[wq] = min(cnt, NS);
+        wg_sync4(g);
+        int total = 0, first = 0, base = 0;
+        bool have = false;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const int cw = wcnt[w];
-        if (w == wq) base = total;
-        if (!have && cw > 0) { first = wl[w * NS]; have = true; }
-        total += cw;
+        for (int w = 0; w < 4; ++w) {
+          const int cw = fcnt[w];
+          if (w == wq) base = total;
+          if (!have && cw > 0) { first = wl[w * NS]; have = true; }
+          total += cw;
+        }
+        const int mine = fcnt[wq];
+        for (int l = lane; l < mine; l += 32)
+          if (base + l < NS) idx_s[base + l] = wl[wq * NS + l];
+        total = min(total, NS);
+        for (int l = total + t; l < NS; l += 128) idx_s[l] = first;
       }
-      const int mine = wcnt[wq];
-      for (int l = lane; l < mine; l += 32)
-        if (base + l < NS) idx_s[base + l] = wl[wq * NS + l];
-      total = min(total, NS);
-      for (int l = total + t; l < NS; l += 128) idx_s[l] = first;
       wg_sync4(g);
     }
     // ---- gather row t: [dx, dy, dz, mask, 0 x4 | 0 x8 | ... | 1, 0 x7 | 0 x8]
     {
-      const int k = idx_s[t];
-      const float dx = fsub(px[k], cx), dy = fsub(py[k], cy), dz = fsub(pz[k], cz);
-      const float mask = __ldg(cloud + ((size_t)b * N + k) * 4 + 3);
-      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, mask), 0u, 0u);
+      const float4 p = __ldg(cl + idx_s[t]);
+      const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
+      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u);
       *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KC)) = make_uint4(0u, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();

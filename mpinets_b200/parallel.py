@@ -1,0 +1,34 @@
+"""Multi-GPU host logic: the rollout shards by problem index (no data-path collective); the only exchange is one
+all-gather of the per-problem metrics table at the end.  Backend-agnostic (nccl on GPUs, gloo in
+the CPU tests)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(rank: int, world: int, total: int) -> Tuple[int, int]:
+    """Contiguous block of problem indices owned by `rank` (blocks differ by at most one problem)."""
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_metrics(metrics: torch.Tensor, total: int) -> torch.Tensor:
+    """metrics [B_local, K] on every rank -> [total, K] on every rank, rows in global problem order."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return metrics
+    world = dist.get_world_size()
+    sizes = [shard_range(r, world, total)[1] - shard_range(r, world, total)[0] for r in range(world)]
+    if len(set(sizes)) == 1:
+        out = torch.empty(total, metrics.shape[1], dtype=metrics.dtype, device=metrics.device)
+        dist.all_gather_into_tensor(out, metrics.contiguous())
+        return out
+    pad = max(sizes)
+    buf = torch.zeros(pad, metrics.shape[1], dtype=metrics.dtype, device=metrics.device)
+    buf[: metrics.shape[0]] = metrics
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)

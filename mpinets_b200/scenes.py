@@ -158,7 +158,8 @@ GENERATORS = {"tabletop": tabletop, "cubby": cubby, "merged_cubby": lambda r: cu
 
 def make_problems(B: int, scene_types=("tabletop",), seed: int = SEED_BASE, problem0: int = 0,
                   max_cuboids: int = MAX_PRIMS, max_cylinders: int = MAX_PRIMS) -> Dict[str, np.ndarray]:
-    """B seeded problems; problem i uses scene_types[i % len] and RandomState(seed ^ hash(problem0 + i))."""
+    """B seeded problems; global problem g = problem0 + i uses scene_types[g % len] and a RandomState keyed by (seed, g),
+    so a shard generated with problem0 = rank*B equals the corresponding slice of one big batch."""
     out = dict(
         q0=np.zeros((B, 7), np.float32), q_goal=np.zeros((B, 7), np.float32), target=np.zeros((B, 3, 4), np.float32),
         cuboid_centers=np.zeros((B, max_cuboids, 3), np.float32), cuboid_dims=np.zeros((B, max_cuboids, 3), np.float32),
@@ -173,7 +174,7 @@ def make_problems(B: int, scene_types=("tabletop",), seed: int = SEED_BASE, prob
     names = list(GENERATORS)
     for i in range(B):
         rng = np.random.RandomState((seed * 1000003 + (problem0 + i) * 7919) % (2 ** 32))
-        st = scene_types[i % len(scene_types)]
+        st = scene_types[(problem0 + i) % len(scene_types)]   # depends on the GLOBAL problem index only
         cubs, cyls = GENERATORS[st](rng)
         cubs, cyls = cubs[:max_cuboids], cyls[:max_cylinders]
         out["scene_type"][i] = names.index(st)
