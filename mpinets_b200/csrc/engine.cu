@@ -21,8 +21,9 @@ int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, in
 int tc_prepare_weights(mpn_ctx* c);
 size_t tc_scratch_bytes(int B);
 int* tc_error_flag(mpn_ctx* c);
+long long* tc_timeline(mpn_ctx* c);
 int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
-                  int N, const float* new_xyz, float* new_feats);
+                  int N, const float* new_xyz, float* new_feats, int32_t* ball_idx);
 int tc_probe(mpn_ctx* c, cudaStream_t s, const void* A, const void* B, float* D, int N, int K, int mode, int* status);
 
 template <typename T>
@@ -312,6 +313,17 @@ int mpn_tc_error(mpn_ctx* c, int* out) {
   return MPN_OK;
 }
 
+int mpn_tc_timeline(mpn_ctx* c, int64_t* out16) {
+  REQ_CTX(c);
+  MPN_REQUIRE(out16, "mpn_tc_timeline: null output");
+  long long* p = tc_timeline(c);
+  MPN_REQUIRE(p, "set MPN_TC_TIMELINE=1 to enable the phase timeline");
+  MPN_CHECK_CUDA(cudaDeviceSynchronize());
+  MPN_CHECK_CUDA(cudaMemcpy(out16, p, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  MPN_CHECK_CUDA(cudaMemset(p, 0, 16 * sizeof(long long)));
+  return MPN_OK;
+}
+
 int mpn_profile(mpn_ctx* c, int enable) {
   REQ_CTX(c);
   c->prof = enable != 0;
@@ -380,7 +392,7 @@ int mpn_sa_forward(mpn_ctx* c, void* stream, int module, int precision, const fl
   int npoint = module == 0 ? SA1_NPOINT : SA2_NPOINT;
   int32_t* idx = fps_idx ? fps_idx : reinterpret_cast<int32_t*>(c->ws.fc_a);
   if ((r = launch_fps(c, s, xyz, B, N, stride, npoint, idx, new_xyz))) return r;
-  if (precision == MPN_PREC_BF16) return tc_sa_forward(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats);
+  if (precision == MPN_PREC_BF16) return tc_sa_forward(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats, ball_idx);
   return launch_sa_simt(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats, ball_idx);
 }
 

@@ -45,6 +45,8 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const uint64_t dA0 = make_smem_desc(smem_u32(smem), 128, 1024, LAYOUT_NONE);                 // stage 0 descriptors; later stages /
+  const uint64_t dW0 = make_smem_desc(smem_u32(smem) + G_A_BYTES, 128, 1024, LAYOUT_NONE);     // K-steps only add to the address field
 
   // stage loader: A rows m0.., W rows n0.., K chunk [st*64, st*64+64) -> interleaved layout with 8 chunks per row
   auto load_stage = [&](int st) {
@@ -79,12 +81,15 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t sA = smem_u32(smem + (size_t)(it % G_STAGES) * G_STAGE_BYTES), sW = sA + G_A_BYTES;
+      const uint32_t soff = (uint32_t)(it % G_STAGES) * (G_STAGE_BYTES / 16);
       const int ksteps = min(4, (K - it * G_BK) / 16);
       constexpr uint32_t id = make_idesc_bf16(G_BM, G_BN);
-      for (int ks = 0; ks < ksteps; ++ks)
-        mma_bf16_ss(tmem, make_smem_desc(sA + ks * 256, 128, 1024, LAYOUT_NONE), make_smem_desc(sW + ks * 256, 128, 1024, LAYOUT_NONE), id,
-                    (it | ks) != 0);
+      if (ksteps == 4) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_bf16_ss_off(tmem, dA0, soff + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
+      } else {
+        for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss_off(tmem, dA0, soff + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
+      }
       mma_commit(&done[it % G_STAGES]);
     }
     const int nxt = it + G_STAGES - 1;

@@ -31,6 +31,7 @@ struct TcWeights {
 };
 static std::map<mpn_ctx*, TcWeights> g_tc;
 int* tc_error_flag(mpn_ctx* c);
+long long* tc_timeline(mpn_ctx* c);
 
 // bias_col >= 0: the layer's bias is folded into the GEMM as K-column `bias_col` (the operand carries a 1.0 there)
 __global__ void pack_weight_kernel(const float* __restrict__ w, int out, int in, int kpad, int rot, __nv_bfloat16* __restrict__ dst,
@@ -195,14 +196,23 @@ struct SaSmem {
   static size_t total(int N) { return pts + (size_t)N * 16 + 1024; }
 };
 
+// optional per-phase cycle accounting (thread 0 of warpgroup 0 of CTA 0): tl[i] += cycles of phase i
+#define TL_MARK(i)                                                     \
+  do {                                                                 \
+    if (tl && blockIdx.x == 0 && threadIdx.x == 0) {                   \
+      long long _n = clock64(); tl[i] += _n - tl_prev; tl_prev = _n;   \
+    }                                                                  \
+  } while (0)
+
 template <int MODULE>
 __global__ void __launch_bounds__(256, 1)
 sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat16* __restrict__ feat_bf16,
              const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
              const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, const float* __restrict__ gb1,
              const float* __restrict__ gb2, const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16,
-             int out_stride, int* __restrict__ err) {
+             int out_stride, int* __restrict__ err, int32_t* __restrict__ ball_idx, long long* __restrict__ tl) {
   using C = SaCfg<MODULE>;
+  long long tl_prev = clock64();
   using S = SaSmem<MODULE>;
   constexpr int KIN = C::KIN, C1 = C::C1, C2 = C::C2, C3 = C::C3, NCENT = C::NCENT;
   extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
@@ -251,6 +261,10 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
   const uint32_t tmem = *tmem_slot + (uint32_t)g * 256;            // this WG's 256 columns
   const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);       // + this warp's lane quarter
   const uint32_t aX = smem_u32(X), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  // descriptors are built once; each K-step only advances the start address by 256 B (16 units of 16 B)
+  const uint64_t dX_in = tile_desc(aX, KIN, 0, 0), dX_c1 = tile_desc(aX, C1, 0, 0), dX_c2 = tile_desc(aX, C2, 0, 0);
+  const uint64_t dW1 = tile_desc(aW1, KIN, 0, 0), dW2 = tile_desc(aW2, C1, 0, 0), dW3a = tile_desc(aW3, C2, 0, 0);
+  const uint64_t dW3b = tile_desc(aW3, C2, 128, 0);
   uint64_t* bar = &bars[g];
   uint32_t phase = 0;
   bool ok = true;
@@ -258,7 +272,10 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
   for (int j = g; j < NCENT && ok; j += 2) {
     const float* cp = new_xyz + ((size_t)b * NCENT + j) * 3;
     const float cx = cp[0], cy = cp[1], cz = cp[2];
+    TL_MARK(0);
     wg_ball_query<NSAMPLE>(pts, N, cx, cy, cz, r2, idx_s, wl, wcnt, g, t);
+    if (ball_idx) ball_idx[((size_t)b * NCENT + j) * NSAMPLE + t] = idx_s[t];
+    TL_MARK(1);
     // ---- gather row t of the layer-1 operand
     {
       const int k = idx_s[t];
@@ -275,50 +292,61 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
         *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KIN / 8)) = make_uint4(0u, 0u, 0u, 0u);
       }
     }
+    TL_MARK(2);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(g);
+    TL_MARK(3);
     // ---- layer 1: D[128][C1] = A0[128][KIN] * W1[C1][KIN]^T
     if (t == 0) {
       tc_fence_after();
       constexpr uint32_t id = make_idesc_bf16(128, C1);
 #pragma unroll
-      for (int ks = 0; ks < KIN / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aX, KIN, 0, ks), tile_desc(aW1, KIN, 0, ks), id, ks > 0);
+      for (int ks = 0; ks < KIN / 16; ++ks) mma_bf16_ss_off(tmem, dX_in, ks * 16, dW1, ks * 16, id, ks > 0);
       mma_commit(bar);
     }
+    TL_MARK(4);
     ok = mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
+    TL_MARK(5);
     epilogue_to_smem<C1>(tlane, sB1, X, t);
+    TL_MARK(6);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(g);
+    TL_MARK(7);
     // ---- layer 2: D[128][C2] = A1[128][C1] * W2[C2][C1]^T
     if (t == 0) {
       tc_fence_after();
       constexpr uint32_t id = make_idesc_bf16(128, C2);
 #pragma unroll
-      for (int ks = 0; ks < C1 / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aX, C1, 0, ks), tile_desc(aW2, C1, 0, ks), id, ks > 0);
+      for (int ks = 0; ks < C1 / 16; ++ks) mma_bf16_ss_off(tmem, dX_c1, ks * 16, dW2, ks * 16, id, ks > 0);
       mma_commit(bar);
     }
+    TL_MARK(8);
     ok = ok && mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
+    TL_MARK(9);
     epilogue_to_smem<C2>(tlane, sB2, X, t);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(g);
+    TL_MARK(10);
     if (MODULE == 1) {
       // ---- layer 3 transposed: D^T[ch][nbr] = W3[ch tile][C2] * A2[128 nbr][C2]^T, two channel tiles of 128
       if (t == 0) {
         tc_fence_after();
         constexpr uint32_t id = make_idesc_bf16(128, 128);
 #pragma unroll
-        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss(tmem + 128, tile_desc(aW3, C2, 0, ks), tile_desc(aX, C2, 0, ks), id, ks > 0);
+        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss_off(tmem + 128, dW3a, ks * 16, dX_c2, ks * 16, id, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aW3, C2, 128, ks), tile_desc(aX, C2, 0, ks), id, ks > 0);
+        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss_off(tmem, dW3b, ks * 16, dX_c2, ks * 16, id, ks > 0);
         mma_commit(bar);
       }
+      TL_MARK(11);
       ok = ok && mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
+      TL_MARK(12);
       __nv_bfloat16* o = out_bf16 + ((size_t)b * NCENT + j) * out_stride;
 #pragma unroll 1
       for (int tile = 0; tile < 2; ++tile) {
@@ -344,7 +372,7 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
         tc_fence_after();
         constexpr uint32_t id = make_idesc_bf16(128, C3);
 #pragma unroll
-        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aX, C2, 0, ks), tile_desc(aW3, C2, 0, ks), id, ks > 0);
+        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss_off(tmem, dX_c2, ks * 16, dW3a, ks * 16, id, ks > 0);
         mma_commit(bar);
       }
       ok = ok && mbar_wait(bar, phase); phase ^= 1;
@@ -367,8 +395,10 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
         out_bf16[((size_t)b * NCENT + j) * out_stride + t] = __float2bfloat16_rn(m);
       }
     }
+    TL_MARK(13);
     tc_fence_before();
     wg_sync(g);   // TMEM and X are free for the next centroid of this warpgroup
+    TL_MARK(14);
   }
   if (!ok && t == 0) atomicExch(err, 1);
   tc_fence_before();
@@ -414,7 +444,7 @@ __device__ __forceinline__ uint32_t grid_bucket(int ix, int iy, int iz) {
 __global__ void __launch_bounds__(128 * SA1_NWG, 1)
 sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
               const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
-              int* __restrict__ err) {
+              int* __restrict__ err, int32_t* __restrict__ ball_idx) {
   using S = Sa1Smem;
   constexpr int KC = SA1_XK / 8, NS = NSAMPLE;
   extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
@@ -496,7 +526,8 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot + (uint32_t)g * 64;
   const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
-  const uint32_t aX = smem_u32(X), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  const uint64_t dX = tile_desc(smem_u32(X), SA1_XK, 0, 0), dW1 = tile_desc(smem_u32(sW1), SA1_XK, 0, 0);
+  const uint64_t dW2 = tile_desc(smem_u32(sW2), SA1_XK, 0, 0), dW3 = tile_desc(smem_u32(sW3), SA1_XK, 0, 0);
   uint64_t* bar = &bars[g];
   uint32_t phase = 0;
   bool ok = true;
@@ -514,29 +545,38 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
       uint32_t bk = 0x10000u + lane;   // lanes >= 27: unique dummies
       if (lane < 27) bk = grid_bucket(ix + (lane % 3) - 1, iy + ((lane / 3) % 3) - 1, iz + (lane / 9) - 1);
       const unsigned peers = __match_any_sync(0xffffffffu, bk);
-      const unsigned umask = __ballot_sync(0xffffffffu, lane < 27 && lane == __ffs(peers) - 1);
-      int ord = 0;
-      for (unsigned m = umask; m; m &= m - 1, ++ord) {
-        if ((ord & 3) != wq) continue;
-        const uint32_t bb = __shfl_sync(0xffffffffu, bk, __ffs(m) - 1);
-        const int s0 = bstart[bb], e0 = bstart[bb + 1];
-        for (int p0 = s0; p0 < e0; p0 += 32) {
-          const int p = p0 + lane;
-          const bool hit = p < e0 && dist2(cx, cy, cz, sx[p], sy[p], sz[p]) < r2;
+      const bool leader = lane < 27 && lane == __ffs(peers) - 1;   // one lane per distinct bucket
+      int s0 = 0, n0 = 0;
+      if (leader) { s0 = bstart[bk]; n0 = bstart[bk + 1] - s0; }
+      int incl = n0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      const int C = __shfl_sync(0xffffffffu, incl, 31);            // candidates in the 27 cells (same in every warp)
+      int* cand = hits + SA1_HCAP / 2;
+      if (C <= SA1_HCAP / 2) {
+        if ((lane & 3) == wq)                                      // expand (start, count) runs into a flat candidate list
+          for (int i = 0, o = incl - n0; i < n0; ++i) cand[o + i] = s0 + i;
+        wg_sync4(g);
+        for (int c0 = 0; c0 < C; c0 += 128) {                      // every thread tests one candidate
+          const int ci = c0 + t;
+          bool hit = false;
+          int p = 0;
+          if (ci < C) { p = cand[ci]; hit = dist2(cx, cy, cz, sx[p], sy[p], sz[p]) < r2; }
           const unsigned hm = __ballot_sync(0xffffffffu, hit);
           if (hm) {
             int base = 0;
             if (lane == 0) base = atomicAdd(hc, __popc(hm));
             base = __shfl_sync(0xffffffffu, base, 0);
-            const int pos = base + __popc(hm & lt);
-            if (hit && pos < SA1_HCAP) hits[pos] = sidx[p];
+            if (hit) hits[base + __popc(hm & lt)] = sidx[p];
           }
         }
+      } else if (t == 0) {
+        *hc = SA1_HCAP + 1;                                        // too dense for the lists: take the linear-scan path
       }
       wg_sync4(g);
       const int H = *hc;
       if (t == 0) hcnt[(it + 1) & 1] = 0;
-      if (H <= SA1_HCAP) {
+      if (H <= SA1_HCAP / 2) {
         for (int h = t; h < H; h += 128) {
           const int my = hits[h];
           int rank = 0;
@@ -580,6 +620,7 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
       }
       wg_sync4(g);
     }
+    if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = idx_s[t];
     // ---- gather row t: [dx, dy, dz, mask, 0 x4 | 0 x8 | ... | 1, 0 x7 | 0 x8]
     {
       const float4 p = __ldg(cl + idx_s[t]);
@@ -593,8 +634,8 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
     // ---- layer 1: only K-steps 0 (inputs) and 4 (ones column -> bias) are non-zero
     if (t == 0) {
       tc_fence_after();
-      mma_bf16_ss(tmem, tile_desc(aX, SA1_XK, 0, 0), tile_desc(aW1, SA1_XK, 0, 0), IDESC, 0);
-      mma_bf16_ss(tmem, tile_desc(aX, SA1_XK, 0, 4), tile_desc(aW1, SA1_XK, 0, 4), IDESC, 1);
+      mma_bf16_ss_off(tmem, dX, 0, dW1, 0, IDESC, 0);
+      mma_bf16_ss_off(tmem, dX, 64, dW1, 64, IDESC, 1);
       mma_commit(bar);
     }
 #pragma unroll 1
@@ -620,9 +661,9 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
       wg_sync4(g);
       if (t == 0) {
         tc_fence_after();
-        const uint32_t aW = layer == 1 ? aW2 : aW3;
+        const uint64_t dW = layer == 1 ? dW2 : dW3;
 #pragma unroll
-        for (int ks = 0; ks < SA1_XK / 16; ++ks) mma_bf16_ss(tmem, tile_desc(aX, SA1_XK, 0, ks), tile_desc(aW, SA1_XK, 0, ks), IDESC, ks > 0);
+        for (int ks = 0; ks < SA1_XK / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW, ks * 16, IDESC, ks > 0);
         mma_commit(bar);
       }
     }
@@ -663,6 +704,20 @@ __global__ void widen_kernel(const __nv_bfloat16* __restrict__ src, int rows, in
   dst[i] = __bfloat162float(src[r * src_stride + c]);
 }
 
+// phase timeline buffer (16 x int64 cycles), enabled by MPN_TC_TIMELINE=1 in the environment
+long long* tc_timeline(mpn_ctx* c) {
+  static std::map<mpn_ctx*, long long*> bufs;
+  static const bool on = getenv("MPN_TC_TIMELINE") != nullptr;
+  if (!on) return nullptr;
+  auto it = bufs.find(c);
+  if (it != bufs.end()) return it->second;
+  long long* p = nullptr;
+  cudaMalloc(&p, 16 * sizeof(long long));
+  cudaMemset(p, 0, 16 * sizeof(long long));
+  bufs[c] = p;
+  return p;
+}
+
 int* tc_error_flag(mpn_ctx* c) {
   static std::map<mpn_ctx*, int*> flags;
   auto it = flags.find(c);
@@ -683,7 +738,7 @@ __global__ void narrow_kernel(const float* __restrict__ src, size_t rows, int sr
 
 template <int MODULE>
 static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
-                        int B, __nv_bfloat16* out, int out_stride) {
+                        int B, __nv_bfloat16* out, int out_stride, int32_t* ball_idx = nullptr) {
   TcWeights& tw = g_tc[c];
   if (MODULE == 0) {
     size_t smem1 = Sa1Smem::total(N);
@@ -691,7 +746,7 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
     MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     sa1_tc_kernel<<<B, 128 * SA1_NWG, smem1, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
-                                                 tc_error_flag(c));
+                                                 tc_error_flag(c), ball_idx);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;
@@ -702,7 +757,7 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
   const float r = MODULE == 0 ? SA1_RADIUS : SA2_RADIUS;
   sa_tc_kernel<MODULE><<<B, 256, smem, s>>>(xyz, stride, N, feat, new_xyz, r * r, tw.sa[MODULE][0], tw.sa[MODULE][1], tw.sa[MODULE][2],
                                             c->w.sa[MODULE][0].b, c->w.sa[MODULE][1].b, c->w.sa[MODULE][2].b, out, out_stride,
-                                            tc_error_flag(c));
+                                            tc_error_flag(c), ball_idx, tc_timeline(c));
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
@@ -710,21 +765,21 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
 
 // per-module entry (tests / mpn_sa_forward with MPN_PREC_BF16): fp32 in, fp32 out, bf16 inside
 int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
-                  int N, const float* new_xyz, float* new_feats) {
+                  int N, const float* new_xyz, float* new_feats, int32_t* ball_idx) {
   Workspace& w = c->ws;
   __nv_bfloat16* feat1 = reinterpret_cast<__nv_bfloat16*>(w.tc_scratch);
   __nv_bfloat16* a3 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w.tc_scratch) + feat1_bytes(w.capacity));
   int r;
   if (module == 0) {
     MPN_REQUIRE(stride == 4 && feats == xyz + 3 && feat_stride == 4, "bf16 SA1 takes the [B][N][4] cloud (features = 4th column)");
-    if ((r = launch_sa_tc<0>(c, s, xyz, 4, N, nullptr, new_xyz, B, feat1, 64))) return r;
+    if ((r = launch_sa_tc<0>(c, s, xyz, 4, N, nullptr, new_xyz, B, feat1, 64, ball_idx))) return r;
     size_t n = (size_t)B * SA1_NPOINT * 64;
     widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(feat1, B * SA1_NPOINT, 64, 64, new_feats);
   } else {
     MPN_REQUIRE(module == 1 && N == SA1_NPOINT, "bf16 per-module entry supports modules 0 and 1 (N = 512 for module 1)");
     size_t n = (size_t)B * N * 64;
     narrow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(feats, (size_t)B * N, feat_stride, 64, feat1);
-    if ((r = launch_sa_tc<1>(c, s, xyz, stride, N, feat1, new_xyz, B, a3, A3_K))) return r;
+    if ((r = launch_sa_tc<1>(c, s, xyz, stride, N, feat1, new_xyz, B, a3, A3_K, ball_idx))) return r;
     size_t m = (size_t)B * SA2_NPOINT * 256;
     widen_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(a3, B * SA2_NPOINT, A3_K, 256, new_feats);
   }

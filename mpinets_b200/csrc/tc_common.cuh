@@ -81,6 +81,20 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same MMA with the two smem descriptors given as a precomputed 64-bit base plus a 16-byte-unit offset added to the
+// start-address field (bits 0..13): building descriptors once and only adding per K-step keeps the single issuing
+// thread's instruction chain short (a full descriptor rebuild per MMA costs ~200 cycles of dependent ALU work).
+__device__ __forceinline__ void mma_bf16_ss_off(uint32_t d_tmem, uint64_t adesc, uint32_t aoff16, uint64_t bdesc, uint32_t boff16,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "add.u64 da, %1, %5;\n\t"
+      "add.u64 db, %2, %6;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "l"((uint64_t)aoff16), "l"((uint64_t)boff16)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -124,6 +124,11 @@ class Engine:
     def _empty(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def tc_timeline(self):
+        out = (C.c_int64 * 16)()
+        _lib.check(self.lib.mpn_tc_timeline(self._ctx, out))
+        return list(out)
+
     def tc_error(self) -> bool:
         v = C.c_int(0)
         _lib.check(self.lib.mpn_tc_error(self._ctx, C.byref(v)))
@@ -133,10 +138,12 @@ class Engine:
         """D = A[128,K] @ B[N,K]^T on one CTA via tcgen05 (bf16 in, fp32 out); returns (D, timed_out)."""
         _check(a, "a", torch.bfloat16, self.device); _check(b, "b", torch.bfloat16, self.device)
         N, K = b.shape
-        d = torch.zeros(128, N, device=self.device)
+        d = torch.zeros(128 * N + 16, device=self.device)
         st = torch.zeros(1, dtype=torch.int32, device=self.device)
         _lib.check(self.lib.mpn_tc_selftest(self._ctx, self.stream, _p(a), _p(b), _p(d), N, K, mode, _p(st)))
-        return d, bool(st.item())
+        if mode & 0x100:
+            return d[128 * N:128 * N + 8].cpu().tolist(), bool(st.item())
+        return d[:128 * N].view(128, N), bool(st.item())
 
     # ------------------------------------------------------------------ pointnet2_ops
     def fps(self, xyz: torch.Tensor, npoint: int, return_xyz: bool = False):

@@ -24,3 +24,9 @@ torch.cuda.synchronize()
 st = eng.profile_read()
 print({k: round(v["ms"] / max(v["launches"], 1), 4) for k, v in st.items() if v["launches"]})
 print("tc_error", eng.tc_error())
+if os.environ.get("MPN_TC_TIMELINE"):
+    tl = eng.tc_timeline()
+    names = ["loop/top", "ball query", "gather", "fence+sync", "issue L1", "wait L1", "ep1", "fence+sync", "issue L2", "wait L2",
+             "ep2+fence+sync", "issue L3", "wait L3", "ep3", "sync"]
+    n = 64 * reps  # centroids of warpgroup 0 per launch x launches
+    print("SA2 timeline (cycles per centroid, CTA0/WG0):", {k: int(v / n) for k, v in zip(names, tl)}, "total", int(sum(tl) / n))

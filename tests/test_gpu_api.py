@@ -1,0 +1,110 @@
+"""GPU tests (-m gpu) of the reference-facing Python surface: the same call patterns the reference uses
+(`/root/reference/mpinets/model.py`, `run_inference.py`, `loss.py`) against the shim modules in `mpinets_b200/`."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _problems(B, config=4):
+    from mpinets_b200 import scenes
+    return scenes.config_problems(config, B)
+
+
+def test_pointnet2_utils_surface(oracle):
+    """model.py:27 imports PointnetSAModule from pointnet2_ops; its glue calls these functions with these layouts."""
+    from mpinets_b200 import pointnet2_utils as pu
+    rng = np.random.RandomState(0)
+    xyz = torch.from_numpy((rng.uniform(-1, 1, size=(2, 900, 3)) + 2).astype(np.float32)).cuda()
+    feats = torch.from_numpy(rng.normal(size=(2, 5, 900)).astype(np.float32)).cuda()
+    idx = pu.furthest_point_sample(xyz, 64)
+    assert idx.dtype == torch.int32 and idx.shape == (2, 64)
+    assert np.array_equal(idx.cpu().numpy(), oracle.fps(xyz.cpu().numpy(), 64))
+    new_xyz = pu.gather_operation(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()   # _PointnetSAModuleBase.forward
+    assert new_xyz.shape == (2, 64, 3)
+    bq = pu.ball_query(0.4, 16, xyz, new_xyz)
+    assert np.array_equal(bq.cpu().numpy(), oracle.ball_query(0.4, 16, xyz.cpu().numpy(), new_xyz.cpu().numpy()))
+    grouped = pu.QueryAndGroup(0.4, 16)(xyz, new_xyz, feats)
+    assert grouped.shape == (2, 3 + 5, 64, 16)
+    ref = np.concatenate([oracle.grouping_operation(xyz.cpu().numpy().transpose(0, 2, 1), bq.cpu().numpy())
+                          - new_xyz.cpu().numpy().transpose(0, 2, 1)[..., None],
+                          oracle.grouping_operation(feats.cpu().numpy(), bq.cpu().numpy())], axis=1)
+    assert np.array_equal(grouped.cpu().numpy(), ref)
+    assert pu.GroupAll()(xyz, None, feats).shape == (2, 8, 1, 900)
+    with pytest.raises(RuntimeError):
+        pu.furthest_point_sample(xyz.cpu(), 4)           # "CPU tensors not supported" (model.py:417)
+
+
+def test_geometry_surface(oracle):
+    """model.py:281-312 / loss.py:72-88: TorchCuboids / TorchCylinders built from the batch dict, .sdf and .sdf_sequence"""
+    from mpinets_b200.geometry import TorchCuboids, TorchCylinders
+    p = _problems(5)
+    t = to_dev(p)
+    cub = TorchCuboids(t["cuboid_centers"], t["cuboid_dims"], t["cuboid_quats"])
+    cyl = TorchCylinders(t["cylinder_centers"], t["cylinder_radii"], t["cylinder_heights"], t["cylinder_quats"])
+    rng = np.random.RandomState(1)
+    pts = rng.uniform(-1, 1.5, size=(5, 300, 3)).astype(np.float32)
+    sdf = torch.minimum(cub.sdf(torch.from_numpy(pts).cuda()), cyl.sdf(torch.from_numpy(pts).cuda()))   # loss.py:84
+    assert np.array_equal(sdf.cpu().numpy(), oracle.sdf_points(p, pts))
+    seq = torch.from_numpy(pts.reshape(5, 10, 30, 3)).cuda()
+    sq = torch.minimum(cub.sdf_sequence(seq), cyl.sdf_sequence(seq))                                     # model.py:304-307
+    assert sq.shape == (5, 10, 30) and np.array_equal(sq.cpu().numpy().reshape(5, 300), oracle.sdf_points(p, pts))
+    empty = TorchCylinders(t["cylinder_centers"], torch.zeros_like(t["cylinder_radii"]), t["cylinder_heights"], t["cylinder_quats"])
+    assert torch.isinf(empty.sdf(torch.from_numpy(pts).cuda())).all()                                    # geometry.py:465-468
+
+
+def test_samplers_and_utils_surface(oracle, tables):
+    """model.py:267-275,300-303; utils.py"""
+    from mpinets_b200.robofin_shim import FrankaSampler, FrankaCollisionSampler
+    from mpinets_b200 import utils
+    rng = np.random.RandomState(2)
+    lim = tables.joint_limits
+    q = torch.from_numpy(rng.uniform(lim[:, 0], lim[:, 1], size=(9, 7)).astype(np.float32)).cuda()
+    s = FrankaSampler("cuda:0", use_cache=True)
+    pc = s.sample(q, 2048)
+    assert pc.shape == (9, 2048, 3)
+    pose = s.end_effector_pose(q)
+    assert pose.shape == (9, 4, 4) and np.array_equal(pose[:, :3].cpu().numpy(), oracle.fk(q.cpu().numpy())[1])
+    ee = s.sample_end_effector(pose, num_points=128)
+    assert ee.shape == (9, 128, 3)
+    groups = FrankaCollisionSampler("cuda:0", with_base_link=False).compute_spheres(q)
+    assert sum(c.shape[1] for _, c in groups) == tables.sphere_centers.shape[0]
+    assert sorted(set(round(r, 4) for r, _ in groups)) == sorted(set(round(float(r), 4) for r in tables.sphere_radii))
+    qn = utils.normalize_franka_joints(q)
+    assert np.array_equal(qn.cpu().numpy(), oracle.normalize(q.cpu().numpy(), lim))
+    assert np.array_equal(utils.unnormalize_franka_joints(qn).cpu().numpy(), oracle.unnormalize(qn.cpu().numpy(), lim))
+    with pytest.raises(NotImplementedError):
+        utils.normalize_franka_joints([0.0] * 7)             # utils.py:126-127
+
+
+def test_model_surface(oracle, tables, state_dict):
+    """MotionPolicyNetwork: reference state-dict keys load unchanged; forward / rollout keep the reference contracts."""
+    from mpinets_b200.model import MotionPolicyNetwork
+    from mpinets_b200.runtime import get_engine
+    mdl = MotionPolicyNetwork(precision="fp32")
+    assert set(mdl.state_dict().keys()) == set(state_dict.keys())
+    mdl.load_state_dict(state_dict)
+    mdl = mdl.cuda()
+    p = _problems(4)
+    eng = get_engine(torch.device("cuda", 0))
+    sc = to_dev(p)
+    q0 = torch.from_numpy(p["q0"]).cuda()
+    tg = torch.from_numpy(p["target"]).cuda()
+    xyz = eng.build_cloud({k: sc[k] for k in sc if k.startswith(("cuboid", "cylinder"))}, q0, tg)
+    qn = eng.normalize(q0)
+    dq = mdl(xyz, qn)                                                                              # model.py:75-91
+    exp = oracle.policy_forward(state_dict, xyz.cpu().numpy(), qn.cpu().numpy())
+    assert dq.shape == (4, 7) and (dq.cpu() - exp).abs().max().item() <= 1e-5
+    batch = dict(xyz=xyz, configuration=qn, **{k: sc[k] for k in sc if k.startswith(("cuboid", "cylinder"))})
+    before = xyz.clone()
+    traj = mdl.rollout(batch, 2, sampler=None, unnormalize=True)                                   # model.py:128-183
+    assert len(traj) == 3 and traj[0].shape == (4, 7)
+    assert torch.equal(traj[0], eng.unnormalize(qn))
+    assert not torch.equal(batch["xyz"][:, :2048], before[:, :2048])                               # in-place update (model.py:181)
+    assert torch.equal(batch["xyz"][:, 2048:], before[:, 2048:])
+    mdl.precision = "bf16"
+    dq16 = mdl(before, qn)
+    assert (dq16.cpu() - exp).abs().max().item() < 2e-2

@@ -378,18 +378,22 @@ def test_sa_modules_bf16_tensor_core(engine_w, oracle, tables, state_dict):
     feats = torch.from_numpy(np.ascontiguousarray(cloud[..., 3:]))
     o_xyz1, o_f1, aux1 = oracle.sa_module(xyz, feats, oracle.SA_SPECS[0], _sa_weights(state_dict, 0), emulate_bf16=True,
                                           dtype=torch.float64, return_aux=True)
-    nx, f1 = engine_w.sa_forward(0, d_cloud, d_cloud[..., 3:], precision=_lib.PREC_BF16)
+    nx, f1, fi1, bi1 = engine_w.sa_forward(0, d_cloud, d_cloud[..., 3:], precision=_lib.PREC_BF16, debug=True)
     assert not engine_w.tc_error()
     assert np.array_equal(nx.cpu().numpy(), o_xyz1)
+    assert np.array_equal(fi1.cpu().numpy(), aux1["fps_idx"])
+    assert np.array_equal(bi1.cpu().numpy(), aux1["ball_idx"])          # hash-grid ball query: index lists bit-exact
     e1 = (f1.cpu().double() - o_f1).abs().max().item() / o_f1.abs().max().item()
     print("SA1 bf16 tensor-core vs bf16-emulating oracle: rel err", e1)
     assert e1 < BF16_FEAT_RTOL
     # SA2 fed with the oracle's (bf16-representable) SA1 output
     o_xyz2, o_f2, aux2 = oracle.sa_module(o_xyz1, o_f1.float(), oracle.SA_SPECS[1], _sa_weights(state_dict, 1), emulate_bf16=True,
                                           dtype=torch.float64, return_aux=True)
-    nx2, f2 = engine_w.sa_forward(1, torch.from_numpy(o_xyz1).cuda(), o_f1.float().contiguous().cuda(), precision=_lib.PREC_BF16)
+    nx2, f2, fi2, bi2 = engine_w.sa_forward(1, torch.from_numpy(o_xyz1).cuda(), o_f1.float().contiguous().cuda(),
+                                            precision=_lib.PREC_BF16, debug=True)
     assert not engine_w.tc_error()
     assert np.array_equal(nx2.cpu().numpy(), o_xyz2)
+    assert np.array_equal(bi2.cpu().numpy(), aux2["ball_idx"])
     e2 = (f2.cpu().double() - o_f2).abs().max().item() / o_f2.abs().max().item()
     print("SA2 bf16 tensor-core vs bf16-emulating oracle: rel err", e2)
     assert e2 < BF16_FEAT_RTOL
@@ -409,3 +413,29 @@ def test_policy_forward_bf16(engine_w, oracle, tables, state_dict):
     print("bf16 mode delta-q: max-abs-err vs bf16-emulating oracle", (dq - expbf).abs().max().item(),
           " vs fp32 oracle", (dq - exp32).abs().max().item(), " |dq| max", exp32.abs().max().item())
     assert (dq - exp32).abs().max().item() < 2e-2 * max(1.0, exp32.abs().max().item())
+
+
+def test_tensor_core_ball_query_dense_and_fallback(engine_w, oracle):
+    """SA1's hash-grid ball query against pointnet2 semantics on adversarial clouds: > 128 hits (first-128-in-index-order
+    selection by rank), > 512 hits (linear-scan fallback), points exactly on cell boundaries, far-away outliers."""
+    from mpinets_b200 import _lib
+    rng = np.random.RandomState(7)
+    N = 6272
+    cloud = np.zeros((3, N, 4), np.float32)
+    cloud[..., :3] = rng.uniform(-1.0, 1.5, size=(3, N, 3))
+    # FPS always starts at row 0, so clusters that contain row 0 are guaranteed to hold a centroid
+    cloud[0, 0:300, :3] = 0.5 + rng.uniform(-0.02, 0.02, size=(300, 3))        # 300 points in a 4 cm cube  (> 128 hits)
+    cloud[1, 0:1500, :3] = -0.3 + rng.uniform(-0.015, 0.015, size=(1500, 3))    # 1500 points in a 3 cm cube (> 512 hits)
+    cloud[2, :, :3] = np.round(cloud[2, :, :3] / 0.0501) * 0.0501               # everything on grid-cell corners
+    cloud[2, 5, :3] = [7.5, -7.9, 30.0]                                          # outliers far outside the scene
+    cloud[..., 3] = rng.randint(0, 3, size=(3, N))
+    idx = oracle.fps(cloud, 512)
+    new_xyz = np.stack([cloud[b, idx[b], :3] for b in range(3)])
+    exp = oracle.ball_query(0.05, 128, cloud, new_xyz)
+    d = torch.from_numpy(cloud).cuda()
+    nx, f1, fi, bi = engine_w.sa_forward(0, d, d[..., 3:], precision=_lib.PREC_BF16, debug=True)
+    assert not engine_w.tc_error()
+    assert np.array_equal(fi.cpu().numpy(), idx)
+    assert np.array_equal(bi.cpu().numpy(), exp)
+    counts = np.array([[len(set(r.tolist())) for r in exp[b]] for b in range(3)])
+    assert counts[0].max() == 128 and counts[1].max() == 128                      # the dense cases were exercised
