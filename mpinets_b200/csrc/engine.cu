@@ -319,8 +319,8 @@ int mpn_tc_timeline(mpn_ctx* c, int64_t* out16) {
   long long* p = tc_timeline(c);
   MPN_REQUIRE(p, "set MPN_TC_TIMELINE=1 to enable the phase timeline");
   MPN_CHECK_CUDA(cudaDeviceSynchronize());
-  MPN_CHECK_CUDA(cudaMemcpy(out16, p, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  MPN_CHECK_CUDA(cudaMemset(p, 0, 16 * sizeof(long long)));
+  MPN_CHECK_CUDA(cudaMemcpy(out16, p, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  MPN_CHECK_CUDA(cudaMemset(p, 0, 32 * sizeof(long long)));
   return MPN_OK;
 }
 

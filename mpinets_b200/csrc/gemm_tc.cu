@@ -32,7 +32,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
   __shared__ uint64_t done[G_STAGES];
   __shared__ uint32_t tmem_slot;
   __shared__ float red[4][G_BN];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * G_BN;
   const int nst = (K + G_BK - 1) / G_BK;
 
@@ -79,8 +79,11 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
     cp_async_wait<G_STAGES - 2>();
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      uint32_t el;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(el));
+      if (el) {
       const uint32_t soff = (uint32_t)(it % G_STAGES) * (G_STAGE_BYTES / 16);
       const int ksteps = min(4, (K - it * G_BK) / 16);
       constexpr uint32_t id = make_idesc_bf16(G_BM, G_BN);
@@ -91,6 +94,8 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
         for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss_off(tmem, dA0, soff + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
       }
       mma_commit(&done[it % G_STAGES]);
+      }
+      __syncwarp();
     }
     const int nxt = it + G_STAGES - 1;
     if (nxt < nst) {

@@ -55,12 +55,15 @@ int tc_prepare_weights(mpn_ctx* c) {
     for (int l = 0; l < 3; ++l) {
       const Linear& L = c->w.sa[m][l];
       int kpad = m == 0 ? SA1_XK : (L.in + 15) / 16 * 16;   // SA1: every layer is [64][80] with the bias in column 64
+      int bias_col = m == 0 ? SA1_BIAS_COL : -1;
+      if (m == 1 && l == 0) bias_col = 67;                  // SA2 layer 1: [f0..f63, dx, dy, dz, bias, 0 x12]
+      if (m == 1 && l == 1) { kpad = 144; bias_col = 128; } // SA2 layer 2: [128 weights, bias, 0 x15]
       t.kpad[m][l] = kpad;
       if (t.sa[m][l]) cudaFree(t.sa[m][l]);
       MPN_CHECK_CUDA(cudaMalloc(&t.sa[m][l], (size_t)L.out * kpad * sizeof(__nv_bfloat16)));
       int n = L.out * kpad;
       pack_weight_kernel<<<(n + 255) / 256, 256>>>(L.w, L.out, L.in, kpad, (l == 0 && m > 0) ? 1 : 0, t.sa[m][l],
-                                                   m == 0 ? L.b : nullptr, m == 0 ? SA1_BIAS_COL : -1);
+                                                   bias_col >= 0 ? L.b : nullptr, bias_col);
       MPN_CHECK_CUDA(cudaGetLastError());
     }
   for (int l = 0; l < 3; ++l) {
@@ -167,36 +170,30 @@ __device__ __forceinline__ void wg_ball_query(const float4* __restrict__ pts, in
   wg_sync(g);
 }
 
-// ---------------------------------------------------------------------------------------------- fused SA kernel
-// MODULE 0: SA1 (points = cloud rows float4 [N][4], feature = mask column), C = 64/64/64, KIN = 16
-// MODULE 1: SA2 (points = xyz1 [512][3], features = feat1 bf16 [512][64]), C = 128/128/256, KIN = 80
-template <int MODULE>
-struct SaCfg;
-template <>
-struct SaCfg<0> { static constexpr int KIN = 16, C1 = 64, C2 = 64, C3 = 64, NCENT = SA1_NPOINT; };
-template <>
-struct SaCfg<1> { static constexpr int KIN = 80, C1 = 128, C2 = 128, C3 = 256, NCENT = SA2_NPOINT; };
-
-template <int MODULE>
-struct SaSmem {
-  using C = SaCfg<MODULE>;
-  static constexpr int XK = (C::KIN > C::C1 ? C::KIN : C::C1) > C::C2 ? (C::KIN > C::C1 ? C::KIN : C::C1) : C::C2;
-  static constexpr size_t w1 = 0;
-  static constexpr size_t w2 = w1 + (size_t)C::C1 * C::KIN * 2;
-  static constexpr size_t w3 = w2 + (size_t)C::C2 * C::C1 * 2;
-  static constexpr size_t x0 = w3 + (size_t)C::C3 * C::C2 * 2;
-  static constexpr size_t x1 = x0 + (size_t)128 * XK * 2;
-  static constexpr size_t bias = x1 + (size_t)128 * XK * 2;                       // C1 + C2 + C3 floats
-  static constexpr size_t idx = bias + (size_t)(C::C1 + C::C2 + C::C3) * 4;       // [2][128] int
-  static constexpr size_t wl = idx + 2 * 128 * 4;                                 // [2][4][128] int
-  static constexpr size_t wcnt = wl + 2 * 4 * 128 * 4;                            // [2][4] int
-  static constexpr size_t red = wcnt + 64;                                        // [2][4][64] float (SA1 pooling)
-  static constexpr size_t bars = red + 2 * 4 * 64 * 4;                            // 2 mbarriers + tmem base
-  static constexpr size_t pts = (bars + 64 + 15) / 16 * 16;                       // float4 [N]
-  static size_t total(int N) { return pts + (size_t)N * 16 + 1024; }
+// ---------------------------------------------------------------------------------------------- SA2
+// points = xyz1 [512][3] fp32, features = feat1 [512][64] bf16, 128 centroids, radius 0.3, MLP 67 -> 128 -> 128 -> 256.
+// 256 threads = 2 warpgroups, each streaming its own centroids.  Every operand row lives in one persistent smem layout
+// of 18 K-chunks: [chunks 0..15: data | chunk 16: 1.0, 0 x7 | chunk 17: 0], so that
+//   layer 1 reads K-steps 0..4  = [f0..f63 | dx dy dz 1 0 0 0 0 | 0 x8]         (bias = weight column 67)
+//   layer 2 reads K-steps 0..8  = [128 activations | 1 0 ... 0]                  (bias = weight column 128)
+//   layer 3 (transposed, D^T = W3 * A2^T) reads K-steps 0..7; its bias is added after the max-pool.
+// Epilogues of layers 1 and 2 are tcgen05.ld -> cvt.rn.relu.bf16x2 -> st.shared.
+constexpr int SA2_KC = 18, SA2_K1 = 80, SA2_K2 = 144, SA2_K3 = 128;
+struct Sa2Smem {
+  static constexpr size_t w1 = 0;                                     // [128][80]
+  static constexpr size_t w2 = w1 + 128 * SA2_K1 * 2;                 // [128][144]
+  static constexpr size_t w3 = w2 + 128 * SA2_K2 * 2;                 // [256][128]
+  static constexpr size_t x = w3 + 256 * SA2_K3 * 2;                  // 2 x [128][144]
+  static constexpr size_t b3 = x + 2 * 128 * SA2_KC * 16;             // [256] float
+  static constexpr size_t idx = b3 + 256 * 4;                         // [2][128] int
+  static constexpr size_t wl = idx + 2 * 128 * 4;                     // [2][4][128] int
+  static constexpr size_t wcnt = wl + 2 * 4 * 128 * 4;                // [2][4] int
+  static constexpr size_t bars = wcnt + 64;                           // 2 mbarriers + tmem slot
+  static constexpr size_t pts = (bars + 64 + 15) / 16 * 16;           // float4 [512]
+  static constexpr size_t total = pts + SA1_NPOINT * 16 + 256;
 };
 
-// optional per-phase cycle accounting (thread 0 of warpgroup 0 of CTA 0): tl[i] += cycles of phase i
+// optional per-phase cycle accounting (thread 0 of CTA 0): tl[i] += cycles of phase i
 #define TL_MARK(i)                                                     \
   do {                                                                 \
     if (tl && blockIdx.x == 0 && threadIdx.x == 0) {                   \
@@ -204,196 +201,194 @@ struct SaSmem {
     }                                                                  \
   } while (0)
 
-template <int MODULE>
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float first, float second) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+  return d;
+}
+// one lane of a converged warp (the MMA issuer); the enclosing branch must be warp-uniform
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+// TMEM [128 lanes][NC cols] fp32 (bias already inside the accumulator) -> relu -> bf16 -> chunks 0..NC/8-1 of row `row`
+template <int NC, int KCX>
+__device__ __forceinline__ void epilogue_pack_relu(uint32_t taddr, uint8_t* X, int row) {
+#pragma unroll
+  for (int c0 = 0; c0 < NC; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(row, (c0 >> 3) + q, KCX)) =
+          make_uint4(cvt_relu_bf16x2(__uint_as_float(v[q * 8]), __uint_as_float(v[q * 8 + 1])),
+                     cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])),
+                     cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
+                     cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
+  }
+}
+
 __global__ void __launch_bounds__(256, 1)
-sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat16* __restrict__ feat_bf16,
-             const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
-             const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, const float* __restrict__ gb1,
-             const float* __restrict__ gb2, const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16,
-             int out_stride, int* __restrict__ err, int32_t* __restrict__ ball_idx, long long* __restrict__ tl) {
-  using C = SaCfg<MODULE>;
+sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __restrict__ feat_bf16, const float* __restrict__ new_xyz,
+              float r2, const __nv_bfloat16* __restrict__ gw1, const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3,
+              const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16, int out_stride, int* __restrict__ err,
+              int32_t* __restrict__ ball_idx, long long* __restrict__ tl) {
+  using S = Sa2Smem;
+  constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT;
   long long tl_prev = clock64();
-  using S = SaSmem<MODULE>;
-  constexpr int KIN = C::KIN, C1 = C::C1, C2 = C::C2, C3 = C::C3, NCENT = C::NCENT;
-  extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW1 = smem + S::w1;
   uint8_t* sW2 = smem + S::w2;
   uint8_t* sW3 = smem + S::w3;
-  float* sB1 = reinterpret_cast<float*>(smem + S::bias);
-  float* sB2 = sB1 + C1;
-  float* sB3 = sB2 + C2;
+  float* sB3 = reinterpret_cast<float*>(smem + S::b3);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 16);
   float4* pts = reinterpret_cast<float4*>(smem + S::pts);
 
   const int b = blockIdx.x;
-  const int g = threadIdx.x >> 7;          // warpgroup
-  const int t = threadIdx.x & 127;         // thread in warpgroup == operand row / TMEM lane
-  const int wq = (threadIdx.x >> 5) & 3;   // warp's TMEM lane quarter
-  uint8_t* X = smem + (g == 0 ? S::x0 : S::x1);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
+  const int g = warp >> 2, wq = warp & 3;
+  const int t = threadIdx.x & 127;
+  uint8_t* X = smem + S::x + (size_t)g * 128 * SA2_KC * 16;
   int* idx_s = reinterpret_cast<int*>(smem + S::idx) + g * 128;
   int* wl = reinterpret_cast<int*>(smem + S::wl) + g * 4 * 128;
   int* wcnt = reinterpret_cast<int*>(smem + S::wcnt) + g * 4;
-  float* red = reinterpret_cast<float*>(smem + S::red) + g * 4 * 64;
 
-  // ---- one-time staging: weights, biases, points
-  stage_weight(gw1, C1, KIN, sW1);
-  stage_weight(gw2, C2, C1, sW2);
-  stage_weight(gw3, C3, C2, sW3);
-  for (int i = threadIdx.x; i < C1; i += 256) sB1[i] = gb1[i];
-  for (int i = threadIdx.x; i < C2; i += 256) sB2[i] = gb2[i];
-  for (int i = threadIdx.x; i < C3; i += 256) sB3[i] = gb3[i];
+  stage_weight(gw1, 128, SA2_K1, sW1);
+  stage_weight(gw2, 128, SA2_K2, sW2);
+  stage_weight(gw3, 256, SA2_K3, sW3);
+  for (int i = threadIdx.x; i < 256; i += 256) sB3[i] = gb3[i];
   {
     const float* p = xyz + (size_t)b * N * stride;
-    for (int k = threadIdx.x; k < N; k += 256) {
-      float4 v;
-      if (MODULE == 0) v = __ldg(reinterpret_cast<const float4*>(p) + k);   // (x, y, z, mask)
-      else v = make_float4(__ldg(p + (size_t)k * stride), __ldg(p + (size_t)k * stride + 1), __ldg(p + (size_t)k * stride + 2), 0.f);
-      pts[k] = v;
-    }
+    for (int k = threadIdx.x; k < N; k += 256)
+      pts[k] = make_float4(__ldg(p + (size_t)k * stride), __ldg(p + (size_t)k * stride + 1), __ldg(p + (size_t)k * stride + 2), 0.f);
   }
+  // persistent tail of every operand row
+  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 16, SA2_KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 17, SA2_KC)) = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-  if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot + (uint32_t)g * 256;            // this WG's 256 columns
-  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);       // + this warp's lane quarter
-  const uint32_t aX = smem_u32(X), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-  // descriptors are built once; each K-step only advances the start address by 256 B (16 units of 16 B)
-  const uint64_t dX_in = tile_desc(aX, KIN, 0, 0), dX_c1 = tile_desc(aX, C1, 0, 0), dX_c2 = tile_desc(aX, C2, 0, 0);
-  const uint64_t dW1 = tile_desc(aW1, KIN, 0, 0), dW2 = tile_desc(aW2, C1, 0, 0), dW3a = tile_desc(aW3, C2, 0, 0);
-  const uint64_t dW3b = tile_desc(aW3, C2, 128, 0);
+  const uint32_t tmem = *tmem_slot + (uint32_t)g * 256;
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+  // descriptors built once; K-steps only add to the start-address field
+  const uint64_t dX = make_smem_desc(smem_u32(X), 128, SA2_KC * 128, LAYOUT_NONE);
+  const uint64_t dW1 = make_smem_desc(smem_u32(sW1), 128, (SA2_K1 / 8) * 128, LAYOUT_NONE);
+  const uint64_t dW2 = make_smem_desc(smem_u32(sW2), 128, (SA2_K2 / 8) * 128, LAYOUT_NONE);
+  const uint64_t dW3 = make_smem_desc(smem_u32(sW3), 128, (SA2_K3 / 8) * 128, LAYOUT_NONE);
+  constexpr uint32_t W3_TILE1 = (128 / 8) * (SA2_K3 / 8) * 128 / 16;   // rows 128..255 of W3, in 16-byte units
+  constexpr uint32_t ID128 = make_idesc_bf16(128, 128);
   uint64_t* bar = &bars[g];
   uint32_t phase = 0;
   bool ok = true;
 
-  for (int j = g; j < NCENT && ok; j += 2) {
-    const float* cp = new_xyz + ((size_t)b * NCENT + j) * 3;
-    const float cx = cp[0], cy = cp[1], cz = cp[2];
-    TL_MARK(0);
+  // software pipeline: the ball query and the feature-row loads of the NEXT centroid are issued while layer 3 of the
+  // current one runs on the tensor pipe; the rows wait in registers until the operand buffer is free again.
+  float cx, cy, cz, dx, dy, dz;
+  uint4 fr[8];
+  auto prefetch = [&](int jn) {
+    const float* cp = new_xyz + ((size_t)b * NCENT + jn) * 3;
+    cx = cp[0]; cy = cp[1]; cz = cp[2];
     wg_ball_query<NSAMPLE>(pts, N, cx, cy, cz, r2, idx_s, wl, wcnt, g, t);
-    if (ball_idx) ball_idx[((size_t)b * NCENT + j) * NSAMPLE + t] = idx_s[t];
-    TL_MARK(1);
-    // ---- gather row t of the layer-1 operand
-    {
-      const int k = idx_s[t];
-      const float4 p = pts[k];
-      const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
-      if (MODULE == 0) {
-        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KIN / 8)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u);
-        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KIN / 8)) = make_uint4(0u, 0u, 0u, 0u);
-      } else {
-        const uint4* f = reinterpret_cast<const uint4*>(feat_bf16 + ((size_t)b * N + k) * 64);
+    if (ball_idx) ball_idx[((size_t)b * NCENT + jn) * NSAMPLE + t] = idx_s[t];
+    const int k = idx_s[t];
+    const float4 p = pts[k];
+    dx = fsub(p.x, cx); dy = fsub(p.y, cy); dz = fsub(p.z, cz);
+    const uint4* f = reinterpret_cast<const uint4*>(feat_bf16 + ((size_t)b * N + k) * 64);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, q, KIN / 8)) = __ldg(f + q);
-        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KIN / 8)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 0.f), 0u, 0u);
-        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KIN / 8)) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
+    for (int q = 0; q < 8; ++q) fr[q] = __ldg(f + q);
+  };
+  if (g < NCENT) prefetch(g);
+  for (int j = g; j < NCENT && ok; j += 2) {
+    const float ccx = cx, ccy = cy, ccz = cz;   // this centroid (the prefetch below overwrites cx..)
+    TL_MARK(0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, q, SA2_KC)) = fr[q];
+    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, SA2_KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 1.0f), 0u, 0u);
+    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, SA2_KC)) = make_uint4(0u, 0u, 0u, 0u);
     TL_MARK(2);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(g);
     TL_MARK(3);
-    // ---- layer 1: D[128][C1] = A0[128][KIN] * W1[C1][KIN]^T
-    if (t == 0) {
+    if (wq == 0) {   // layer 1: D[nbr][128] = A0 * W1^T
       tc_fence_after();
-      constexpr uint32_t id = make_idesc_bf16(128, C1);
+      if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < KIN / 16; ++ks) mma_bf16_ss_off(tmem, dX_in, ks * 16, dW1, ks * 16, id, ks > 0);
-      mma_commit(bar);
+        for (int ks = 0; ks < SA2_K1 / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW1, ks * 16, ID128, ks > 0);
+        mma_commit(bar);
+      }
+      __syncwarp();
     }
     TL_MARK(4);
     ok = mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
     TL_MARK(5);
-    epilogue_to_smem<C1>(tlane, sB1, X, t);
+    epilogue_pack_relu<128, SA2_KC>(tlane, X, t);
     TL_MARK(6);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(g);
     TL_MARK(7);
-    // ---- layer 2: D[128][C2] = A1[128][C1] * W2[C2][C1]^T
-    if (t == 0) {
+    if (wq == 0) {   // layer 2: D[nbr][128] = [A1 | 1] * [W2 | b2]^T
       tc_fence_after();
-      constexpr uint32_t id = make_idesc_bf16(128, C2);
+      if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < C1 / 16; ++ks) mma_bf16_ss_off(tmem, dX_c1, ks * 16, dW2, ks * 16, id, ks > 0);
-      mma_commit(bar);
+        for (int ks = 0; ks < SA2_K2 / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW2, ks * 16, ID128, ks > 0);
+        mma_commit(bar);
+      }
+      __syncwarp();
     }
     TL_MARK(8);
     ok = ok && mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
     TL_MARK(9);
-    epilogue_to_smem<C2>(tlane, sB2, X, t);
+    epilogue_pack_relu<128, SA2_KC>(tlane, X, t);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync(g);
     TL_MARK(10);
-    if (MODULE == 1) {
-      // ---- layer 3 transposed: D^T[ch][nbr] = W3[ch tile][C2] * A2[128 nbr][C2]^T, two channel tiles of 128
-      if (t == 0) {
-        tc_fence_after();
-        constexpr uint32_t id = make_idesc_bf16(128, 128);
+    if (wq == 0) {   // layer 3 transposed: D^T[ch][nbr] = W3[ch tile] * A2^T ; tile 0 -> cols 128.., tile 1 -> cols 0..
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss_off(tmem + 128, dW3a, ks * 16, dX_c2, ks * 16, id, ks > 0);
+        for (int ks = 0; ks < SA2_K3 / 16; ++ks) mma_bf16_ss_off(tmem + 128, dW3, ks * 16, dX, ks * 16, ID128, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss_off(tmem, dW3b, ks * 16, dX_c2, ks * 16, id, ks > 0);
+        for (int ks = 0; ks < SA2_K3 / 16; ++ks) mma_bf16_ss_off(tmem, dW3, W3_TILE1 + ks * 16, dX, ks * 16, ID128, ks > 0);
         mma_commit(bar);
       }
-      TL_MARK(11);
-      ok = ok && mbar_wait(bar, phase); phase ^= 1;
-      tc_fence_after();
-      TL_MARK(12);
-      __nv_bfloat16* o = out_bf16 + ((size_t)b * NCENT + j) * out_stride;
+      __syncwarp();
+    }
+    TL_MARK(11);
+    if (j + 2 < NCENT) prefetch(j + 2);   // overlaps the layer-3 MMAs
+    TL_MARK(1);
+    ok = ok && mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    TL_MARK(12);
+    __nv_bfloat16* o = out_bf16 + ((size_t)b * NCENT + j) * out_stride;
 #pragma unroll 1
-      for (int tile = 0; tile < 2; ++tile) {
-        float m = -3.0e38f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tlane + (tile == 0 ? 128 : 0) + c0, v);
-          tmem_ld_wait();
+    for (int tile = 0; tile < 2; ++tile) {
+      float m = -3.0e38f;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) m = fmaxf(m, __uint_as_float(v[q]));
-        }
-        o[tile * 128 + t] = __float2bfloat16_rn(fmaxf(m + sB3[tile * 128 + t], 0.f));
-      }
-      if (t < 8) {   // SA3 operand tail: [x, y, z, 0...] of this centroid (GroupAll uses uncentred xyz)
-        float v = t == 0 ? cx : (t == 1 ? cy : (t == 2 ? cz : 0.f));
-        o[C3 + t] = __float2bfloat16_rn(v);
-        o[C3 + 8 + t] = __float2bfloat16_rn(0.f);
-      }
-    } else {
-      // ---- layer 3 standard: D[128][64]; pool over rows with redux.sync on the (non-negative) post-ReLU bit patterns
-      if (t == 0) {
-        tc_fence_after();
-        constexpr uint32_t id = make_idesc_bf16(128, C3);
-#pragma unroll
-        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16_ss_off(tmem, dX_c2, ks * 16, dW3a, ks * 16, id, ks > 0);
-        mma_commit(bar);
-      }
-      ok = ok && mbar_wait(bar, phase); phase ^= 1;
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < C3; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tlane + c0, v);
+      for (int c0 = 0; c0 < 128; c0 += 64) {
+        uint32_t v[32], u[32];
+        tmem_ld32(tlane + (tile == 0 ? 128 : 0) + c0, v);
+        tmem_ld32(tlane + (tile == 0 ? 128 : 0) + c0 + 32, u);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          float a = fmaxf(__uint_as_float(v[q]) + sB3[c0 + q], 0.f);
-          uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(a));
-          if ((t & 31) == q) red[wq * 64 + c0 + q] = __uint_as_float(mx);
-        }
+        for (int q = 0; q < 32; ++q) m = fmaxf(m, fmaxf(__uint_as_float(v[q]), __uint_as_float(u[q])));
       }
-      wg_sync(g);
-      if (t < C3) {
-        float m = fmaxf(fmaxf(red[t], red[64 + t]), fmaxf(red[128 + t], red[192 + t]));
-        out_bf16[((size_t)b * NCENT + j) * out_stride + t] = __float2bfloat16_rn(m);
-      }
+      o[tile * 128 + t] = __float2bfloat16_rn(fmaxf(m + sB3[tile * 128 + t], 0.f));
+    }
+    if (t < 8) {   // SA3 operand tail: [x, y, z, 0...] of this centroid (GroupAll uses uncentred xyz)
+      float v = t == 0 ? ccx : (t == 1 ? ccy : (t == 2 ? ccz : 0.f));
+      o[256 + t] = __float2bfloat16_rn(v);
+      o[256 + 8 + t] = __float2bfloat16_rn(0.f);
     }
     TL_MARK(13);
     tc_fence_before();
@@ -403,7 +398,7 @@ sa_tc_kernel(const float* __restrict__ xyz, int stride, int N, const __nv_bfloat
   if (!ok && t == 0) atomicExch(err, 1);
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, 512);
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
 // ---------------------------------------------------------------------------------------------- SA1 (v2)
@@ -417,8 +412,8 @@ constexpr int SA1_BUCKETS = 4096, SA1_HCAP = 512;
 struct Sa1Smem {
   static constexpr size_t w = 0;                                          // 3 x [64][80] bf16
   static constexpr size_t x = w + 3 * 64 * SA1_XK * 2;                    // NWG x [128][80] bf16 (aliased by the grid build)
-  static constexpr size_t idx = x + (size_t)SA1_NWG * 128 * SA1_XK * 2;   // [NWG][128] int
-  static constexpr size_t hits = idx + SA1_NWG * 128 * 4;                 // [NWG][HCAP] int  (fallback: [4][128] per-warp lists)
+  static constexpr size_t idx = x + (size_t)SA1_NWG * 128 * SA1_XK * 2;   // [NWG][4 warps][128] u16 result lists
+  static constexpr size_t hits = idx + SA1_NWG * 4 * 128 * 2;             // [NWG][4 warps][256] u16 candidates / hits
   static constexpr size_t hcnt = hits + SA1_NWG * SA1_HCAP * 4;           // [NWG][2] hit counters + [NWG][4] fallback counts
   static constexpr size_t red = hcnt + 128;                               // [NWG][4][64] int
   static constexpr size_t bars = red + SA1_NWG * 4 * 64 * 4;              // NWG mbarriers + tmem slot
@@ -427,11 +422,6 @@ struct Sa1Smem {
   static size_t total(int N) { return pts + (size_t)N * 14 + 1024; }
 };
 
-__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float first, float second) {
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
-  return d;
-}
 __device__ __forceinline__ void wg_sync4(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
 // uniform hash grid: cell edge slightly above the query radius so that every point within r of a centroid lies in
@@ -444,8 +434,9 @@ __device__ __forceinline__ uint32_t grid_bucket(int ix, int iy, int iz) {
 __global__ void __launch_bounds__(128 * SA1_NWG, 1)
 sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
               const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
-              int* __restrict__ err, int32_t* __restrict__ ball_idx) {
+              int* __restrict__ err, int32_t* __restrict__ ball_idx, long long* __restrict__ tl) {
   using S = Sa1Smem;
+  long long tl_prev = clock64();
   constexpr int KC = SA1_XK / 8, NS = NSAMPLE;
   extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
   uint8_t* sW1 = smem + S::w;
@@ -460,7 +451,8 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
   uint16_t* sidx = reinterpret_cast<uint16_t*>(sz + N);
 
   const int b = blockIdx.x;
-  const int g = threadIdx.x >> 7, t = threadIdx.x & 127, wq = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
+  const int g = warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
   uint8_t* X = smem + S::x + (size_t)g * 128 * SA1_XK * 2;
   int* idx_s = reinterpret_cast<int*>(smem + S::idx) + g * 128;
   int* hits = reinterpret_cast<int*>(smem + S::hits) + g * SA1_HCAP;
@@ -535,13 +527,19 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
   const unsigned lt = (1u << lane) - 1u;
   int it = 0;
 
-  for (int j = g; j < SA1_NPOINT && ok; j += SA1_NWG, ++it) {
-    const float* cp = new_xyz + ((size_t)b * SA1_NPOINT + j) * 3;
-    const float cx = cp[0], cy = cp[1], cz = cp[2];
-    // ---- ball query over the 27 grid cells around the centroid (unordered hits), then rank-sort by point index
+  // Each round a warpgroup takes 4 consecutive centroids: warp w runs the whole ball query of centroid base + w on its
+  // own (grid cells -> candidates -> hits -> rank by point index), with no block-level synchronisation inside; the
+  // warpgroup then pushes the 4 centroids through the MLP one after the other.
+  uint16_t* wcand = reinterpret_cast<uint16_t*>(smem + S::hits) + (size_t)(g * 4 + wq) * 256;   // candidates, then hits (in place)
+  uint16_t* widx = reinterpret_cast<uint16_t*>(smem + S::idx) + (size_t)(g * 4 + wq) * 128;      // this warp's result list
+  const uint16_t* gidx = reinterpret_cast<const uint16_t*>(smem + S::idx) + (size_t)g * 4 * 128;
+  for (int base = g * 4; base < SA1_NPOINT && ok; base += SA1_NWG * 4) {
+    TL_MARK(16);
     {
-      int* hc = &hcnt[it & 1];
-      const int ix = grid_coord(cx), iy = grid_coord(cy), iz = grid_coord(cz);
+      const int jc = base + wq;
+      const float* cpw = new_xyz + ((size_t)b * SA1_NPOINT + jc) * 3;
+      const float qx = cpw[0], qy = cpw[1], qz = cpw[2];
+      const int ix = grid_coord(qx), iy = grid_coord(qy), iz = grid_coord(qz);
       uint32_t bk = 0x10000u + lane;   // lanes >= 27: unique dummies
       if (lane < 27) bk = grid_bucket(ix + (lane % 3) - 1, iy + ((lane / 3) % 3) - 1, iz + (lane / 9) - 1);
       const unsigned peers = __match_any_sync(0xffffffffu, bk);
@@ -551,97 +549,84 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
       int incl = n0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-      const int C = __shfl_sync(0xffffffffu, incl, 31);            // candidates in the 27 cells (same in every warp)
-      int* cand = hits + SA1_HCAP / 2;
-      if (C <= SA1_HCAP / 2) {
-        if ((lane & 3) == wq)                                      // expand (start, count) runs into a flat candidate list
-          for (int i = 0, o = incl - n0; i < n0; ++i) cand[o + i] = s0 + i;
-        wg_sync4(g);
-        for (int c0 = 0; c0 < C; c0 += 128) {                      // every thread tests one candidate
-          const int ci = c0 + t;
+      const int C = __shfl_sync(0xffffffffu, incl, 31);            // candidates in the 27 cells
+      if (C <= 256) {
+        for (int i = 0, o = incl - n0; i < n0; ++i) wcand[o + i] = (uint16_t)(s0 + i);
+        __syncwarp();
+        int H = 0;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          const int ci = c0 + lane;
           bool hit = false;
           int p = 0;
-          if (ci < C) { p = cand[ci]; hit = dist2(cx, cy, cz, sx[p], sy[p], sz[p]) < r2; }
+          if (ci < C) { p = wcand[ci]; hit = dist2(qx, qy, qz, sx[p], sy[p], sz[p]) < r2; }
           const unsigned hm = __ballot_sync(0xffffffffu, hit);
-          if (hm) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(hc, __popc(hm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (hit) hits[base + __popc(hm & lt)] = sidx[p];
-          }
+          if (hit) wcand[H + __popc(hm & lt)] = sidx[p];           // in place: write position <= read position
+          H += __popc(hm);
+          __syncwarp();
         }
-      } else if (t == 0) {
-        *hc = SA1_HCAP + 1;                                        // too dense for the lists: take the linear-scan path
-      }
-      wg_sync4(g);
-      const int H = *hc;
-      if (t == 0) hcnt[(it + 1) & 1] = 0;
-      if (H <= SA1_HCAP / 2) {
-        for (int h = t; h < H; h += 128) {
-          const int my = hits[h];
+        for (int h = lane; h < H; h += 32) {
+          const int my = wcand[h];
           int rank = 0;
-          for (int i = 0; i < H; ++i) rank += hits[i] < my;
-          if (rank < NS) idx_s[rank] = my;
+          for (int i = 0; i < H; ++i) rank += wcand[i] < my;
+          if (rank < NS) widx[rank] = (uint16_t)my;
         }
-        wg_sync4(g);
-        const int first = H > 0 ? idx_s[0] : 0;
-        for (int l = min(H, NS) + t; l < NS; l += 128) idx_s[l] = first;
+        __syncwarp();
+        const uint16_t first = H > 0 ? widx[0] : (uint16_t)0;
+        for (int l = min(H, NS) + lane; l < NS; l += 32) widx[l] = first;
       } else {
-        // fallback (more hits than the list holds): pointnet2's linear scan in index order from global memory
-        int* wl = hits;
-        const int seg = ((N + 3) / 4 + 31) & ~31;
-        const int k_begin = wq * seg, k_end = min(N, k_begin + seg);
+        // very dense neighbourhood: pointnet2's linear scan in index order, straight from global memory
         int cnt = 0;
-        for (int k0 = k_begin; k0 < k_end && cnt < NS; k0 += 32) {
+        uint16_t first = 0;
+        for (int k0 = 0; k0 < N && cnt < NS; k0 += 32) {
           const int k = k0 + lane;
           bool hit = false;
-          if (k < k_end) { const float4 v = __ldg(cl + k); hit = dist2(cx, cy, cz, v.x, v.y, v.z) < r2; }
+          if (k < N) { const float4 v = __ldg(cl + k); hit = dist2(qx, qy, qz, v.x, v.y, v.z) < r2; }
           const unsigned hm = __ballot_sync(0xffffffffu, hit);
+          if (hm && cnt == 0) first = (uint16_t)(k0 + __ffs(hm) - 1);
           const int pos = cnt + __popc(hm & lt);
-          if (hit && pos < NS) wl[wq * NS + pos] = k;
+          if (hit && pos < NS) widx[pos] = (uint16_t)k;
           cnt += __popc(hm);
         }
-        if (lane == 0) fcnt[wq] = min(cnt, NS);
-        wg_sync4(g);
-        int total = 0, first = 0, base = 0;
-        bool have = false;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const int cw = fcnt[w];
-          if (w == wq) base = total;
-          if (!have && cw > 0) { first = wl[w * NS]; have = true; }
-          total += cw;
-        }
-        const int mine = fcnt[wq];
-        for (int l = lane; l < mine; l += 32)
-          if (base + l < NS) idx_s[base + l] = wl[wq * NS + l];
-        total = min(total, NS);
-        for (int l = total + t; l < NS; l += 128) idx_s[l] = first;
+        for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
       }
-      wg_sync4(g);
     }
-    if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = idx_s[t];
+    wg_sync4(g);
+    TL_MARK(17);
+#pragma unroll 1
+    for (int cc = 0; cc < 4 && ok; ++cc) {
+    const int j = base + cc;
+    const float* cp = new_xyz + ((size_t)b * SA1_NPOINT + j) * 3;
+    const float cx = cp[0], cy = cp[1], cz = cp[2];
+    const int kk = gidx[cc * 128 + t];
+    if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = kk;
     // ---- gather row t: [dx, dy, dz, mask, 0 x4 | 0 x8 | ... | 1, 0 x7 | 0 x8]
     {
-      const float4 p = __ldg(cl + idx_s[t]);
+      const float4 p = __ldg(cl + kk);
       const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
       *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u);
       *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KC)) = make_uint4(0u, 0u, 0u, 0u);
     }
+    TL_MARK(18);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_sync4(g);
+    TL_MARK(19);
     // ---- layer 1: only K-steps 0 (inputs) and 4 (ones column -> bias) are non-zero
-    if (t == 0) {
+    if (wq == 0) {
       tc_fence_after();
-      mma_bf16_ss_off(tmem, dX, 0, dW1, 0, IDESC, 0);
-      mma_bf16_ss_off(tmem, dX, 64, dW1, 64, IDESC, 1);
-      mma_commit(bar);
+      if (elect_one()) {
+        mma_bf16_ss_off(tmem, dX, 0, dW1, 0, IDESC, 0);
+        mma_bf16_ss_off(tmem, dX, 64, dW1, 64, IDESC, 1);
+        mma_commit(bar);
+      }
+      __syncwarp();
     }
+    TL_MARK(20);
 #pragma unroll 1
     for (int layer = 1; layer < 3; ++layer) {
       ok = ok && mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
+      TL_MARK(21);
       // epilogue: relu + bf16 pack, 64 columns -> chunks 0..7 of this row
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -656,19 +641,26 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
                          cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
                          cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
       }
+      TL_MARK(22);
       fence_proxy_async_smem();
       tc_fence_before();
       wg_sync4(g);
-      if (t == 0) {
+      TL_MARK(23);
+      if (wq == 0) {
         tc_fence_after();
         const uint64_t dW = layer == 1 ? dW2 : dW3;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < SA1_XK / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW, ks * 16, IDESC, ks > 0);
-        mma_commit(bar);
+          for (int ks = 0; ks < SA1_XK / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW, ks * 16, IDESC, ks > 0);
+          mma_commit(bar);
+        }
+        __syncwarp();
       }
+      TL_MARK(24);
     }
     ok = ok && mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
+    TL_MARK(25);
     // ---- pool: max over the 128 rows of D[128][64]
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -689,6 +681,9 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
       const int m = max(max(red[t], red[64 + t]), max(red[128 + t], red[192 + t]));
       out_bf16[((size_t)b * SA1_NPOINT + j) * 64 + t] = __float2bfloat16_rn(fmaxf(__int_as_float(m), 0.f));
     }
+    TL_MARK(26);
+    }
+    wg_sync4(g);   // result lists are rewritten by the next round
   }
   if (!ok && t == 0) atomicExch(err, 1);
   tc_fence_before();
@@ -704,7 +699,7 @@ __global__ void widen_kernel(const __nv_bfloat16* __restrict__ src, int rows, in
   dst[i] = __bfloat162float(src[r * src_stride + c]);
 }
 
-// phase timeline buffer (16 x int64 cycles), enabled by MPN_TC_TIMELINE=1 in the environment
+// phase timeline buffer (32 x int64 cycles: 0..15 SA2, 16..31 SA1), enabled by MPN_TC_TIMELINE=1 in the environment
 long long* tc_timeline(mpn_ctx* c) {
   static std::map<mpn_ctx*, long long*> bufs;
   static const bool on = getenv("MPN_TC_TIMELINE") != nullptr;
@@ -712,8 +707,8 @@ long long* tc_timeline(mpn_ctx* c) {
   auto it = bufs.find(c);
   if (it != bufs.end()) return it->second;
   long long* p = nullptr;
-  cudaMalloc(&p, 16 * sizeof(long long));
-  cudaMemset(p, 0, 16 * sizeof(long long));
+  cudaMalloc(&p, 32 * sizeof(long long));
+  cudaMemset(p, 0, 32 * sizeof(long long));
   bufs[c] = p;
   return p;
 }
@@ -746,18 +741,16 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
     MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     sa1_tc_kernel<<<B, 128 * SA1_NWG, smem1, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
-                                                 tc_error_flag(c), ball_idx);
+                                                 tc_error_flag(c), ball_idx, tc_timeline(c));
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;
   }
-  size_t smem = SaSmem<MODULE>::total(N);
-  MPN_REQUIRE(smem <= 227 * 1024, "tensor-core SA%d: %d points do not fit shared memory", MODULE + 1, N);
-  MPN_CHECK_CUDA(cudaFuncSetAttribute(sa_tc_kernel<MODULE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const float r = MODULE == 0 ? SA1_RADIUS : SA2_RADIUS;
-  sa_tc_kernel<MODULE><<<B, 256, smem, s>>>(xyz, stride, N, feat, new_xyz, r * r, tw.sa[MODULE][0], tw.sa[MODULE][1], tw.sa[MODULE][2],
-                                            c->w.sa[MODULE][0].b, c->w.sa[MODULE][1].b, c->w.sa[MODULE][2].b, out, out_stride,
-                                            tc_error_flag(c), ball_idx, tc_timeline(c));
+  MPN_REQUIRE(N == SA1_NPOINT, "tensor-core SA2 expects the 512 SA1 centroids as input points");
+  size_t smem = Sa2Smem::total;
+  MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sa2_tc_kernel<<<B, 256, smem, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.sa[1][1], tw.sa[1][2],
+                                     c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx, tc_timeline(c));
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

@@ -125,7 +125,7 @@ class Engine:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     def tc_timeline(self):
-        out = (C.c_int64 * 16)()
+        out = (C.c_int64 * 32)()
         _lib.check(self.lib.mpn_tc_timeline(self._ctx, out))
         return list(out)
 
