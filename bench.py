@@ -39,6 +39,12 @@ BYTES_PER_STEP = {"sample_robot": 2048 * 16 + 11 * 48, "sweep": 28 + 3200 + 1, "
                   "fps1": 6272 * 16 + 512 * 16, "fps2": 512 * 12 + 128 * 16}
 
 
+def load_traffic():
+    """per-problem DRAM bytes (read + write) of each stage's dominant kernel from the committed ncu --set full capture"""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -150,6 +156,7 @@ def main():
     import torch.distributed as dist
     from mpinets_b200 import scenes, _lib
     from mpinets_b200.engine import Engine
+    from mpinets_b200.parallel import gather_metrics, shard_range
     from oracle import oracle as O   # only for reference_state_dict (weights init) and the cpu_baseline leg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,7 +181,9 @@ def main():
     prec = _lib.PREC_BF16 if precision == "bf16" else _lib.PREC_FP32
 
     # ---- problems: host (pinned) SoA, shard = rank's contiguous block of problem indices
-    p = scenes.config_problems(2, B, problem0=rank * B)
+    lo, hi = shard_range(rank, world, world * B)
+    assert (lo, hi) == (rank * B, (rank + 1) * B)
+    p = scenes.config_problems(2, B, problem0=lo)
     host = {k: torch.from_numpy(np.ascontiguousarray(p[k])).pin_memory() for k in scenes.SCENE_KEYS + ("q0", "target")}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
 
@@ -204,8 +213,7 @@ def main():
     ev0.record()
     eng.rollout(sc, cloud, d["q0"], d["target"], K, check_every_step=True, precision=prec, traj=traj, metrics=metrics)
     if world > 1:
-        gathered = torch.empty(world * B, _lib.METRICS_COLS, device="cuda")
-        dist.all_gather_into_tensor(gathered, metrics)   # the single collective: final metrics table
+        gathered = gather_metrics(metrics, world * B)    # the single collective: final metrics table (NCCL all-gather)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -245,19 +253,26 @@ def main():
         per_stage = {k: (v["ms"] / max(v["launches"], 1)) for k, v in stages.items() if v["launches"]}
         total_stage_ms = sum(v["ms"] for v in stages.values())
         dom = max((k for k in per_stage if k in FLOP_PER_STEP or k in BYTES_PER_STEP), key=lambda k: stages[k]["ms"])
+        traffic = load_traffic()
+        dom_traffic = traffic[dom]["dram_bytes_per_problem"] * B if dom in traffic else None
         if dom in FLOP_PER_STEP:
             ach = FLOP_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e12
             peak = peaks["bf16_sustained"]
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                    "traffic": dom_traffic, "peak_source": peaks["source"] + ", sustained bf16",
                     "algorithmic_flop_per_launch": FLOP_PER_STEP[dom] * B, "avg_launch_ms": per_stage[dom],
                     "share_of_step": stages[dom]["ms"] / total_stage_ms}
         else:
             ach = BYTES_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "frac": ach / peaks["hbm_gbs"], "traffic": dom_traffic, "peak_source": peaks["source"],
                     "algorithmic_bytes_per_launch": BYTES_PER_STEP[dom] * B, "avg_launch_ms": per_stage[dom],
                     "share_of_step": stages[dom]["ms"] / total_stage_ms}
+        tensor_kernels = {}
+        for k in ("sa1", "sa2", "sa3", "fc"):
+            if k in per_stage:
+                tf = FLOP_PER_STEP[k] * B / (per_stage[k] / 1000.0) / 1e12
+                tensor_kernels[k] = {"TFLOPs": tf, "frac_of_bf16_sustained": tf / peaks["bf16_sustained"], "ms": per_stage[k]}
         hbm_kernels = {}
         for k in ("sample_robot", "sweep", "fps1"):
             if k in per_stage:
@@ -277,7 +292,7 @@ def main():
                     "ms_total": e2e_ms},
             "roofline": roof,
             "stage_ms_per_step": {k: v["ms"] / K for k, v in stages.items() if v["launches"]},
-            "hbm_kernels": hbm_kernels,
+            "hbm_kernels": hbm_kernels, "tensor_kernels": tensor_kernels,
             "tensor_flops_per_step": FLOP_TOTAL * B,
             "achieved_tflops_whole_step": FLOP_TOTAL * B * K * world / (ms / 1000.0) / 1e12,
             "collision_rate": float(metrics[:, 0].mean().item()),
