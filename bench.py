@@ -100,6 +100,8 @@ def cpu_oracle_steps_per_sec(n_problems: int, steps: int, bf16: bool, seed: int)
     import torch
     from mpinets_b200 import scenes, franka
     from oracle import oracle as O
+    if torch.get_num_threads() < (os.cpu_count() or 1):      # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every host core
+        torch.set_num_threads(os.cpu_count() or 1)
     tables = franka.default_tables()
     sd = O.reference_state_dict(0)
     p = scenes.config_problems(2, n_problems)
@@ -140,6 +142,7 @@ def run_reference(args):
 
 
 def main():
+    os.environ["NCCL_DEBUG"] = os.environ.get("MPN_NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

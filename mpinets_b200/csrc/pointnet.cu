@@ -64,6 +64,10 @@ fps_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int vbs
     out[0] = 0;
     if (oxyz) { float4 v = spts[0]; oxyz[0] = v.x; oxyz[1] = v.y; oxyz[2] = v.z; }
   }
+  // tie word of slot i of this thread: low(i) = 0xFFFFFFFF - (vt << 23 | (tid + i*FPS_THREADS)).  When the virtual
+  // block equals the real one (N >= 512) vt is a per-thread constant and low(i) = low0 - i*FPS_THREADS.
+  const bool fast_tie = vbs == FPS_THREADS;
+  const uint32_t low0 = 0xFFFFFFFFu - (((__brev((uint32_t)tid) >> 23) << 23) | (uint32_t)tid);
   for (int j = 1; j < npoint; ++j) {
     const float4 c = spts[old];
     float bd = -1.0f;
@@ -72,14 +76,18 @@ fps_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int vbs
     for (int i = 0; i < PPT; ++i) {
       float d2 = fminf(dist2(px[i], py[i], pz[i], c.x, c.y, c.z), temp[i]);
       temp[i] = d2;
-      if (d2 > bd) { bd = d2; bi = i; }   // strict: first (smallest k) of equal distances within the thread
+      if (d2 > bd) { bd = d2; bi = i * FPS_THREADS; }   // strict: first (smallest k) of equal distances within the thread
     }
     uint32_t dbits = 0u, low = 0u;
     if (bd >= 0.0f) {
-      const int k = tid + bi * FPS_THREADS;
-      const uint32_t vt = vbits ? (__brev((uint32_t)(k & (vbs - 1))) >> (32 - vbits)) : 0u;
       dbits = __float_as_uint(bd);
-      low = 0xFFFFFFFFu - ((vt << 23) | (uint32_t)k);
+      if (fast_tie) {
+        low = low0 - (uint32_t)bi;
+      } else {
+        const int k = tid + bi;
+        const uint32_t vt = vbits ? (__brev((uint32_t)(k & (vbs - 1))) >> (32 - vbits)) : 0u;
+        low = 0xFFFFFFFFu - ((vt << 23) | (uint32_t)k);
+      }
     }
     uint32_t m = __reduce_max_sync(0xffffffffu, dbits);
     uint32_t l = __reduce_max_sync(0xffffffffu, dbits == m ? low : 0u);

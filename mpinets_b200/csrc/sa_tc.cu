@@ -409,15 +409,15 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
 // negative result is clamped by the final ReLU).
 constexpr int SA1_NWG = 4;
 constexpr int SA1_BUCKETS = 4096, SA1_HCAP = 512;
+constexpr int SA1_THREADS = 128 * SA1_NWG + 32 * SA1_NWG;   // 4 warpgroups of 4 row warps + one ball-query producer warp each
 struct Sa1Smem {
   static constexpr size_t w = 0;                                          // 3 x [64][80] bf16
   static constexpr size_t x = w + 3 * 64 * SA1_XK * 2;                    // NWG x [128][80] bf16 (aliased by the grid build)
-  static constexpr size_t idx = x + (size_t)SA1_NWG * 128 * SA1_XK * 2;   // [NWG][4 warps][128] u16 result lists
-  static constexpr size_t hits = idx + SA1_NWG * 4 * 128 * 2;             // [NWG][4 warps][256] u16 candidates / hits
-  static constexpr size_t hcnt = hits + SA1_NWG * SA1_HCAP * 4;           // [NWG][2] hit counters + [NWG][4] fallback counts
-  static constexpr size_t red = hcnt + 128;                               // [NWG][4][64] int
-  static constexpr size_t bars = red + SA1_NWG * 4 * 64 * 4;              // NWG mbarriers + tmem slot
-  static constexpr size_t bstart = (bars + 64 + 15) / 16 * 16;            // u16 [BUCKETS + 1]
+  static constexpr size_t idx = x + (size_t)SA1_NWG * 128 * SA1_XK * 2;   // [NWG][2 slots][4][128] u16 neighbour lists
+  static constexpr size_t hits = idx + SA1_NWG * 2 * 4 * 128 * 2;         // [NWG][256] u16 candidates / hits of the producer warp
+  static constexpr size_t red = hits + SA1_NWG * 256 * 2;                 // [NWG][4][64] int
+  static constexpr size_t bars = red + SA1_NWG * 4 * 64 * 4;              // mbarriers: mma[NWG], full[NWG][2], empty[NWG][2]; tmem slot
+  static constexpr size_t bstart = (bars + 256 + 15) / 16 * 16;           // u16 [BUCKETS + 1]
   static constexpr size_t pts = (bstart + (SA1_BUCKETS + 1) * 2 + 15) / 16 * 16;   // sorted x[N] | y[N] | z[N] floats | idx u16[N]
   static size_t total(int N) { return pts + (size_t)N * 14 + 1024; }
 };
@@ -431,7 +431,7 @@ __device__ __forceinline__ uint32_t grid_bucket(int ix, int iy, int iz) {
   return ((uint32_t)ix * 73856093u ^ (uint32_t)iy * 19349663u ^ (uint32_t)iz * 83492791u) & (SA1_BUCKETS - 1);
 }
 
-__global__ void __launch_bounds__(128 * SA1_NWG, 1)
+__global__ void __launch_bounds__(SA1_THREADS, 1)
 sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
               const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
               int* __restrict__ err, int32_t* __restrict__ ball_idx, long long* __restrict__ tl) {
@@ -443,7 +443,9 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
   uint8_t* sW2 = sW1 + 64 * SA1_XK * 2;
   uint8_t* sW3 = sW2 + 64 * SA1_XK * 2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * SA1_NWG);
+  uint64_t* full_bars = bars + SA1_NWG;            // [NWG][2]: neighbour lists of a round are ready
+  uint64_t* empty_bars = bars + 3 * SA1_NWG;       // [NWG][2]: the round's lists have been consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * 5 * SA1_NWG);
   uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + S::bstart);
   float* sx = reinterpret_cast<float*>(smem + S::pts);
   float* sy = sx + N;
@@ -452,12 +454,10 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
 
   const int b = blockIdx.x;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
-  const int g = warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
+  const bool producer = warp >= 4 * SA1_NWG;                         // warps 16..19: ball-query producers
+  const int g = producer ? warp - 4 * SA1_NWG : warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
   uint8_t* X = smem + S::x + (size_t)g * 128 * SA1_XK * 2;
-  int* idx_s = reinterpret_cast<int*>(smem + S::idx) + g * 128;
-  int* hits = reinterpret_cast<int*>(smem + S::hits) + g * SA1_HCAP;
-  int* hcnt = reinterpret_cast<int*>(smem + S::hcnt) + g * 2;
-  int* fcnt = reinterpret_cast<int*>(smem + S::hcnt) + 2 * SA1_NWG + g * 4;
+  uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::idx) + (size_t)g * 2 * 4 * 128;   // [2 slots][4][128]
   int* red = reinterpret_cast<int*>(smem + S::red) + g * 4 * 64;
   const float4* cl = reinterpret_cast<const float4*>(cloud) + (size_t)b * N;
 
@@ -475,14 +475,15 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
       atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u);
     }
     __syncthreads();
-    constexpr int PER = SA1_BUCKETS / (128 * SA1_NWG);   // buckets per thread
+    constexpr int PER = SA1_BUCKETS / 512;               // buckets per scanning thread (threads 0..511 scan)
+    const bool scanner = threadIdx.x < 512;
     uint32_t loc[PER], sum = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { loc[i] = cnt[threadIdx.x * PER + i]; sum += loc[i]; }
+    for (int i = 0; i < PER; ++i) { loc[i] = scanner ? cnt[threadIdx.x * PER + i] : 0u; sum += loc[i]; }
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-    if (lane == 31) wsum[threadIdx.x >> 5] = inc;
+    if (lane == 31 && scanner) wsum[threadIdx.x >> 5] = inc;
     __syncthreads();
     if (threadIdx.x < 32) {
       uint32_t v = lane < 16 ? wsum[lane] : 0u, iv = v;
@@ -491,10 +492,12 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
       if (lane < 16) wsum[lane] = iv - v;
     }
     __syncthreads();
-    uint32_t run = wsum[threadIdx.x >> 5] + inc - sum;
+    if (scanner) {
+      uint32_t run = wsum[threadIdx.x >> 5] + inc - sum;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { bstart[threadIdx.x * PER + i] = (uint16_t)run; cnt[threadIdx.x * PER + i] = run; run += loc[i]; }
-    if (threadIdx.x == blockDim.x - 1) bstart[SA1_BUCKETS] = (uint16_t)N;
+      for (int i = 0; i < PER; ++i) { bstart[threadIdx.x * PER + i] = (uint16_t)run; cnt[threadIdx.x * PER + i] = run; run += loc[i]; }
+    }
+    if (threadIdx.x == 0) bstart[SA1_BUCKETS] = (uint16_t)N;
     __syncthreads();
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
       const float4 v = __ldg(cl + k);
@@ -504,11 +507,12 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
     __syncthreads();
   }
   // persistent tail of every operand row: chunk 8 = [1.0, 0...], chunk 9 = 0
-  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KC)) = make_uint4(0u, 0u, 0u, 0u);
-  if (t < 2) hcnt[t] = 0;
+  if (!producer) {
+    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KC)) = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SA1_NWG; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5 * SA1_NWG; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 256);
@@ -525,18 +529,21 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
   bool ok = true;
   constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
   const unsigned lt = (1u << lane) - 1u;
-  int it = 0;
 
-  // Each round a warpgroup takes 4 consecutive centroids: warp w runs the whole ball query of centroid base + w on its
-  // own (grid cells -> candidates -> hits -> rank by point index), with no block-level synchronisation inside; the
-  // warpgroup then pushes the 4 centroids through the MLP one after the other.
-  uint16_t* wcand = reinterpret_cast<uint16_t*>(smem + S::hits) + (size_t)(g * 4 + wq) * 256;   // candidates, then hits (in place)
-  uint16_t* widx = reinterpret_cast<uint16_t*>(smem + S::idx) + (size_t)(g * 4 + wq) * 128;      // this warp's result list
-  const uint16_t* gidx = reinterpret_cast<const uint16_t*>(smem + S::idx) + (size_t)g * 4 * 128;
-  for (int base = g * 4; base < SA1_NPOINT && ok; base += SA1_NWG * 4) {
-    TL_MARK(16);
+  // Ball queries run on a dedicated producer warp per warpgroup, two rounds (of 4 centroids) ahead of the MLP through a
+  // 2-slot ring of neighbour lists guarded by full/empty mbarriers, so the query latency overlaps the tensor pipeline.
+  uint16_t* wcand = reinterpret_cast<uint16_t*>(smem + S::hits) + (size_t)g * 256;   // producer: candidates, then hits (in place)
+  uint64_t* fullb = full_bars + g * 2;
+  uint64_t* emptyb = empty_bars + g * 2;
+  if (producer) {
+    int r = 0;
+    for (int base = g * 4; base < SA1_NPOINT; base += SA1_NWG * 4, ++r) {
+      const int slot = r & 1;
+      if (r >= 2) mbar_wait(&emptyb[slot], ((r >> 1) - 1) & 1);
+      for (int cc = 0; cc < 4; ++cc) {
+        const int jc = base + cc;
+        uint16_t* widx = lists + (slot * 4 + cc) * 128;
     {
-      const int jc = base + wq;
       const float* cpw = new_xyz + ((size_t)b * SA1_NPOINT + jc) * 3;
       const float qx = cpw[0], qy = cpw[1], qz = cpw[2];
       const int ix = grid_coord(qx), iy = grid_coord(qy), iz = grid_coord(qz);
@@ -590,18 +597,30 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
         for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
       }
     }
-    wg_sync4(g);
+        __syncwarp();
+      }
+      if (lane == 0) mbar_arrive(&fullb[slot]);
+    }
+  } else {
+  int r = 0;
+  for (int base = g * 4; base < SA1_NPOINT && ok; base += SA1_NWG * 4, ++r) {
+    const int slot = r & 1;
+    const uint16_t* gidx = lists + slot * 4 * 128;
+    TL_MARK(16);
+    ok = mbar_wait(&fullb[slot], (r >> 1) & 1);
     TL_MARK(17);
+    // the gathered point of the next centroid is fetched (global / L2) while the current one is in the tensor pipe
+    float4 pn = __ldg(cl + gidx[t]);
+    const float* cpn = new_xyz + ((size_t)b * SA1_NPOINT + base) * 3;
+    float nx = cpn[0], ny = cpn[1], nz = cpn[2];
 #pragma unroll 1
     for (int cc = 0; cc < 4 && ok; ++cc) {
     const int j = base + cc;
-    const float* cp = new_xyz + ((size_t)b * SA1_NPOINT + j) * 3;
-    const float cx = cp[0], cy = cp[1], cz = cp[2];
-    const int kk = gidx[cc * 128 + t];
-    if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = kk;
+    const float cx = nx, cy = ny, cz = nz;
+    const float4 p = pn;
+    if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = gidx[cc * 128 + t];
     // ---- gather row t: [dx, dy, dz, mask, 0 x4 | 0 x8 | ... | 1, 0 x7 | 0 x8]
     {
-      const float4 p = __ldg(cl + kk);
       const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
       *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u);
       *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KC)) = make_uint4(0u, 0u, 0u, 0u);
@@ -620,6 +639,11 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
         mma_commit(bar);
       }
       __syncwarp();
+    }
+    if (cc < 3) {
+      pn = __ldg(cl + gidx[(cc + 1) * 128 + t]);
+      const float* cq = new_xyz + ((size_t)b * SA1_NPOINT + j + 1) * 3;
+      nx = cq[0]; ny = cq[1]; nz = cq[2];
     }
     TL_MARK(20);
 #pragma unroll 1
@@ -683,7 +707,9 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
     }
     TL_MARK(26);
     }
-    wg_sync4(g);   // result lists are rewritten by the next round
+    wg_sync4(g);
+    if (t == 0) mbar_arrive(&emptyb[slot]);   // the producer may refill this slot
+  }
   }
   if (!ok && t == 0) atomicExch(err, 1);
   tc_fence_before();
@@ -740,7 +766,7 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     MPN_REQUIRE(smem1 <= 227 * 1024, "tensor-core SA1: %d points do not fit shared memory", N);
     MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
     MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    sa1_tc_kernel<<<B, 128 * SA1_NWG, smem1, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
+    sa1_tc_kernel<<<B, SA1_THREADS, smem1, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
                                                  tc_error_flag(c), ball_idx, tc_timeline(c));
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
