@@ -2,8 +2,8 @@
 // B*128 points, 259->512->512->1024 + max over each problem's 128 rows) and the FC head (model.py:385-393).
 //
 //   C[M][N] = epilogue(A[M][K] * W[N][K]^T + bias)     A, W bf16 K-major in HBM, fp32 accumulate in TMEM.
-//   CTA tile 128 x 256, K staged 64 at a time through a 4-deep cp.async ring into the UMMA interleaved (8x16B core
-//   matrix) layout; one thread issues tcgen05.mma, completion per stage is tracked with tcgen05.commit -> mbarrier so a
+//   CTA tile 256 x 256 (two 128-row MMA sub-tiles that share every weight stage), K staged 64 at a time through a 3-deep
+//   cp.async ring into the UMMA interleaved (8x16B core matrix) layout; one thread issues tcgen05.mma, completion per stage is tracked with tcgen05.commit -> mbarrier so a
 //   ring slot is only refilled after the MMAs that read it have retired; all 8 warps drain the 128x256 accumulator.
 //   EPI_RELU_BF16: relu -> bf16 rows;  EPI_F32: fp32 rows (GroupNorm follows);  EPI_MAXPOOL: relu + max over the tile's
 //   128 rows (= one problem) -> one bf16 row.
@@ -14,7 +14,7 @@ namespace mpn {
 using namespace tc;
 
 enum { EPI_RELU_BF16 = 0, EPI_F32 = 1, EPI_MAXPOOL = 2 };
-constexpr int G_BM = 128, G_BN = 256, G_BK = 64, G_STAGES = 4;
+constexpr int G_BM = 256, G_BN = 256, G_BK = 64, G_STAGES = 3;   // G_BM = 2 x 128-row MMA tiles
 constexpr int G_A_BYTES = G_BM * G_BK * 2, G_W_BYTES = G_BN * G_BK * 2, G_STAGE_BYTES = G_A_BYTES + G_W_BYTES;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -40,7 +40,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
     for (int s = 0; s < G_STAGES; ++s) mbar_init(&done[s], 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -86,12 +86,16 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
       if (el) {
       const uint32_t soff = (uint32_t)(it % G_STAGES) * (G_STAGE_BYTES / 16);
       const int ksteps = min(4, (K - it * G_BK) / 16);
-      constexpr uint32_t id = make_idesc_bf16(G_BM, G_BN);
+      constexpr uint32_t id = make_idesc_bf16(128, G_BN);
+      constexpr uint32_t SUB1 = (128 / 8) * 8 * 128 / 16;   // rows 128..255 of the A stage, in 16-byte units
       if (ksteps == 4) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) mma_bf16_ss_off(tmem, dA0, soff + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_bf16_ss_off(tmem + 256, dA0, soff + SUB1 + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
       } else {
         for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss_off(tmem, dA0, soff + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
+        for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss_off(tmem + 256, dA0, soff + SUB1 + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
       }
       mma_commit(&done[it % G_STAGES]);
       }
@@ -110,8 +114,10 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
 
   // ---- epilogue: warp (q = warp & 3) owns lanes 32q..32q+31, column half h = warp >> 2
   const int q = warp & 3, h = warp >> 2, row = q * 32 + (tid & 31);
-  const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + h * 128;
-  const int m = m0 + row;
+#pragma unroll 1
+  for (int sub = 0; sub < 2; ++sub) {
+  const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + sub * 256 + h * 128;
+  const int m = m0 + sub * 128 + row;
 #pragma unroll 1
   for (int c0 = 0; c0 < 128; c0 += 32) {
     uint32_t v[32];
@@ -150,12 +156,17 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
   }
   if (EPI == EPI_MAXPOOL) {
     __syncthreads();
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)blockIdx.y * ldc + n0;
-    o[tid] = __float2bfloat16_rn(fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid])));
+    const int prob = blockIdx.y * 2 + sub;   // one pooled row per 128-row sub-tile (= one problem)
+    if (prob * 128 < M) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)prob * ldc + n0;
+      o[tid] = __float2bfloat16_rn(fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid])));
+    }
+    __syncthreads();
+  }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 int* tc_error_flag(mpn_ctx* c);
@@ -163,7 +174,7 @@ int* tc_error_flag(mpn_ctx* c);
 int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int K, const float* bias,
                    int M, int N, void* C, int ldc) {
   MPN_REQUIRE(K % 16 == 0 && N % G_BN == 0 && lda % 8 == 0, "gemm_tc: K %% 16, N %% 256, lda %% 8 required (K=%d N=%d lda=%d)", K, N, lda);
-  MPN_REQUIRE(epi != EPI_MAXPOOL || M % G_BM == 0, "gemm_tc: max-pool epilogue needs M %% 128 == 0");
+  MPN_REQUIRE(epi != EPI_MAXPOOL || M % 128 == 0, "gemm_tc: max-pool epilogue needs M %% 128 == 0");
   dim3 grid(N / G_BN, (M + G_BM - 1) / G_BM);
   size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 1024;
   int* err = tc_error_flag(c);
