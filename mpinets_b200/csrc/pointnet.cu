@@ -9,6 +9,7 @@
 //   * ball query: first nsample indices in index order with d2 < r*r, padded with the first hit.
 #include "engine.h"
 #include "spec_math.cuh"
+#include <cstdlib>
 
 namespace mpn {
 
@@ -104,6 +105,161 @@ fps_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int vbs
   }
 }
 
+// ------------------------------------------------------------------------------------------------ pruned FPS
+// Exact FPS with warp-level pruning for large clouds (N in (8*512, 13*512]).  Points are counting-sorted by a 12-bit
+// Morton cell so that every warp owns a spatially compact set (13 per thread, in registers, with their tie words).
+// Round j only has to touch a warp if some point of it can get closer to the new centroid c than its current
+// min-distance:  dist(c, bounding_box_w)^2 < max_p temp[p].  max_p temp[p] is exactly the warp's cached best distance, so a
+// warp that fails the (conservatively rounded) test keeps every temp[] and its cached (distance, tie word) unchanged.
+// The selected indices are identical to the unpruned kernel: same distances, same total order on (distance, tie word).
+constexpr int FPSP_CELLS = 4096;
+
+__device__ __forceinline__ uint32_t f2ord(float f) { uint32_t b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t o) { uint32_t b = o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu); return __uint_as_float(b); }
+__device__ __forceinline__ uint32_t spread4(uint32_t v) { return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6); }
+
+template <int THREADS, int FPSP_PPT>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_pruned_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int32_t* __restrict__ idx, float* __restrict__ new_xyz) {
+  extern __shared__ float4 spts[];                         // [N] original order (winner broadcast + setup)
+  __shared__ uint2 slot[2][THREADS / 32];
+  __shared__ uint32_t bb[6];                                // ordered-int min x,y,z / max x,y,z
+  __shared__ uint32_t wsum[THREADS / 32];
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(spts + N);   // [CELLS] histogram / cursors
+  uint16_t* order = reinterpret_cast<uint16_t*>(cnt + FPSP_CELLS);   // [N] sorted position -> original index
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = xyz + (size_t)b * N * stride;
+  // ---- load + bounding box
+  if (tid < 3) bb[tid] = 0xFFFFFFFFu;
+  if (tid >= 3 && tid < 6) bb[tid] = 0u;
+  for (int i = tid; i < FPSP_CELLS; i += THREADS) cnt[i] = 0u;
+  __syncthreads();
+  {
+    uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+    for (int k = tid; k < N; k += THREADS) {
+      float x, y, z;
+      if (stride == 4) { float4 v = reinterpret_cast<const float4*>(p)[k]; x = v.x; y = v.y; z = v.z; }
+      else { x = p[(size_t)k * stride]; y = p[(size_t)k * stride + 1]; z = p[(size_t)k * stride + 2]; }
+      spts[k] = make_float4(x, y, z, 0.f);
+      uint32_t o[3] = {f2ord(x), f2ord(y), f2ord(z)};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], o[a]); mx[a] = max(mx[a], o[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      uint32_t m0 = __reduce_min_sync(0xffffffffu, mn[a]), m1 = __reduce_max_sync(0xffffffffu, mx[a]);
+      if (lane == 0) { atomicMin(&bb[a], m0); atomicMax(&bb[3 + a], m1); }
+    }
+  }
+  __syncthreads();
+  const float lo_x = ord2f(bb[0]), lo_y = ord2f(bb[1]), lo_z = ord2f(bb[2]);
+  const float sx_ = 15.999f / fmaxf(ord2f(bb[3]) - lo_x, 1e-6f), sy_ = 15.999f / fmaxf(ord2f(bb[4]) - lo_y, 1e-6f),
+              sz_ = 15.999f / fmaxf(ord2f(bb[5]) - lo_z, 1e-6f);
+  auto cell_of = [&](const float4& v) -> uint32_t {
+    uint32_t cx = (uint32_t)min(15, max(0, (int)((v.x - lo_x) * sx_))), cy = (uint32_t)min(15, max(0, (int)((v.y - lo_y) * sy_))),
+             cz = (uint32_t)min(15, max(0, (int)((v.z - lo_z) * sz_)));
+    return spread4(cx) | (spread4(cy) << 1) | (spread4(cz) << 2);
+  };
+  // ---- counting sort by Morton cell
+  for (int k = tid; k < N; k += THREADS) atomicAdd(&cnt[cell_of(spts[k])], 1u);
+  __syncthreads();
+  {
+    constexpr int PER = FPSP_CELLS / THREADS;
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = cnt[tid * PER + i]; sum += loc[i]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t v = lane < THREADS / 32 ? wsum[lane] : 0u, iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+      if (lane < THREADS / 32) wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = wsum[warp] + inc - sum;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { cnt[tid * PER + i] = run; run += loc[i]; }
+  }
+  __syncthreads();
+  for (int k = tid; k < N; k += THREADS) order[atomicAdd(&cnt[cell_of(spts[k])], 1u)] = (uint16_t)k;
+  __syncthreads();
+  // ---- registers: thread t owns sorted positions [13t, 13t+13)
+  float px[FPSP_PPT], py[FPSP_PPT], pz[FPSP_PPT], temp[FPSP_PPT];
+  uint32_t low[FPSP_PPT];
+  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+#pragma unroll
+  for (int i = 0; i < FPSP_PPT; ++i) {
+    const int sidx = tid * FPSP_PPT + i;
+    px[i] = py[i] = pz[i] = 0.f; temp[i] = -1.0f; low[i] = 0u;
+    if (sidx < N) {
+      const int k = order[sidx];
+      const float4 v = spts[k];
+      px[i] = v.x; py[i] = v.y; pz[i] = v.z;
+      low[i] = 0xFFFFFFFFu - (((__brev((uint32_t)(k & 511)) >> 23) << 23) | (uint32_t)k);
+      const float mag = ffma(v.z, v.z, ffma(v.y, v.y, fmul(v.x, v.x)));
+      if (!(mag <= 1e-3f)) temp[i] = 1e10f;
+      uint32_t o[3] = {f2ord(v.x), f2ord(v.y), f2ord(v.z)};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], o[a]); mx[a] = max(mx[a], o[a]); }
+    }
+  }
+  // warp bounding box (slightly inflated); an empty warp gets an inverted box far away and never updates
+  float wlo[3], whi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const uint32_t m0 = __reduce_min_sync(0xffffffffu, mn[a]), m1 = __reduce_max_sync(0xffffffffu, mx[a]);
+    const float l = m0 <= m1 ? ord2f(m0) : 1e30f, h = m0 <= m1 ? ord2f(m1) : 1e30f;
+    wlo[a] = l - (fabsf(l) * 1e-5f + 1e-6f);
+    whi[a] = h + (fabsf(h) * 1e-5f + 1e-6f);
+  }
+  int32_t* out = idx + (size_t)b * npoint;
+  float* oxyz = new_xyz ? new_xyz + (size_t)b * npoint * 3 : nullptr;
+  int old = 0;
+  if (tid == 0) {
+    out[0] = 0;
+    if (oxyz) { float4 v = spts[0]; oxyz[0] = v.x; oxyz[1] = v.y; oxyz[2] = v.z; }
+  }
+  uint32_t wm = 0x7F800000u, wl_ = 0u;   // cached warp best (distance bits, tie word); +inf forces the first update
+  for (int j = 1; j < npoint; ++j) {
+    const float4 c = spts[old];
+    // can any point of this warp get closer to c than its current min-distance?
+    // squared distance from c to the warp's box: a lower bound of every point's distance (0 inside the box)
+    const float gx = fmaxf(0.f, fmaxf(wlo[0] - c.x, c.x - whi[0])), gy = fmaxf(0.f, fmaxf(wlo[1] - c.y, c.y - whi[1])),
+                gz = fmaxf(0.f, fmaxf(wlo[2] - c.z, c.z - whi[2]));
+    const bool skip = (gx * gx + gy * gy + gz * gz) * 0.9999f > __uint_as_float(wm);
+    if (!skip) {
+      float bd = -1.0f;
+      uint32_t bl = 0u;
+#pragma unroll
+      for (int i = 0; i < FPSP_PPT; ++i) {
+        const float d2 = fminf(dist2(px[i], py[i], pz[i], c.x, c.y, c.z), temp[i]);
+        temp[i] = d2;
+        const bool better = d2 > bd || (d2 == bd && low[i] > bl);
+        bd = better ? d2 : bd;
+        bl = better ? low[i] : bl;
+      }
+      const uint32_t dbits = bd >= 0.0f ? __float_as_uint(bd) : 0u;
+      const uint32_t lw = bd >= 0.0f ? bl : 0u;
+      wm = __reduce_max_sync(0xffffffffu, dbits);
+      wl_ = __reduce_max_sync(0xffffffffu, dbits == wm ? lw : 0u);
+    }
+    if (lane == 0) slot[j & 1][warp] = make_uint2(wm, wl_);
+    __syncthreads();
+    const uint2 v = lane < THREADS / 32 ? slot[j & 1][lane] : make_uint2(0u, 0u);
+    const uint32_t M = __reduce_max_sync(0xffffffffu, v.x);
+    const uint32_t L = __reduce_max_sync(0xffffffffu, v.x == M ? v.y : 0u);
+    old = (M == 0u && L == 0u) ? 0 : (int)((0xFFFFFFFFu - L) & 0x7FFFFFu);
+    if (tid == 0) {
+      out[j] = old;
+      if (oxyz) { float4 w = spts[old]; oxyz[3 * j] = w.x; oxyz[3 * j + 1] = w.y; oxyz[3 * j + 2] = w.z; }
+    }
+  }
+}
+
 int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz) {
   MPN_REQUIRE(N >= 1 && N <= 16 * FPS_THREADS, "mpn_fps: N=%d unsupported (1..%d)", N, 16 * FPS_THREADS);
   MPN_REQUIRE(npoint >= 1 && npoint <= N, "mpn_fps: npoint=%d out of range for N=%d", npoint, N);
@@ -111,6 +267,21 @@ int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int s
   int vbs = opt_n_threads(N);
   size_t smem = (size_t)N * sizeof(float4);
   int ppt = (N + FPS_THREADS - 1) / FPS_THREADS;
+  static const bool no_prune = getenv("MPN_FPS_NO_PRUNE") != nullptr;
+  if (!no_prune && ppt > 8 && ppt <= 13 && npoint >= 64) {   // large clouds: exact pruned variant
+    size_t smem_p = smem + FPSP_CELLS * sizeof(uint32_t) + (size_t)N * sizeof(uint16_t) + 16;
+    static const bool wide = getenv("MPN_FPS_WIDE") != nullptr;   // 1024 threads x 7 points (32 prune regions) instead of 512 x 13
+    if (wide && N <= 7 * 1024) {
+      MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<1024, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+      fps_pruned_kernel<1024, 7><<<B, 1024, smem_p, s>>>(xyz, N, stride, npoint, idx, new_xyz);
+    } else {
+      MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<512, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+      fps_pruned_kernel<512, 13><<<B, 512, smem_p, s>>>(xyz, N, stride, npoint, idx, new_xyz);
+    }
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    return MPN_OK;
+  }
 #define FPS_LAUNCH(P)                                                                                         \
   do {                                                                                                        \
     MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
