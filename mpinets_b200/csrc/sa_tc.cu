@@ -230,7 +230,8 @@ __device__ __forceinline__ void epilogue_pack_relu(uint32_t taddr, uint8_t* X, i
   }
 }
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int SA2_THREADS = 256 + 64;   // 2 warpgroups of 4 row warps + one MMA-issue warp each
+__global__ void __launch_bounds__(SA2_THREADS, 1)
 sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __restrict__ feat_bf16, const float* __restrict__ new_xyz,
               float r2, const __nv_bfloat16* __restrict__ gw1, const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3,
               const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16, int out_stride, int* __restrict__ err,
@@ -244,12 +245,14 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
   uint8_t* sW3 = smem + S::w3;
   float* sB3 = reinterpret_cast<float*>(smem + S::b3);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 16);
+  uint64_t* ready_bars = bars + 2;                 // [2]: operand of the next layer is in shared memory (128 row-thread arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 32);
   float4* pts = reinterpret_cast<float4*>(smem + S::pts);
 
   const int b = blockIdx.x;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
-  const int g = warp >> 2, wq = warp & 3;
+  const bool issuer = warp >= 8;                                     // warps 8, 9: MMA issue warps of warpgroups 0, 1
+  const int g = issuer ? warp - 8 : warp >> 2, wq = warp & 3;
   const int t = threadIdx.x & 127;
   uint8_t* X = smem + S::x + (size_t)g * 128 * SA2_KC * 16;
   int* idx_s = reinterpret_cast<int*>(smem + S::idx) + g * 128;
@@ -259,16 +262,21 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
   stage_weight(gw1, 128, SA2_K1, sW1);
   stage_weight(gw2, 128, SA2_K2, sW2);
   stage_weight(gw3, 256, SA2_K3, sW3);
-  for (int i = threadIdx.x; i < 256; i += 256) sB3[i] = gb3[i];
+  for (int i = threadIdx.x; i < 256; i += SA2_THREADS) sB3[i] = gb3[i];
   {
     const float* p = xyz + (size_t)b * N * stride;
-    for (int k = threadIdx.x; k < N; k += 256)
+    for (int k = threadIdx.x; k < N; k += SA2_THREADS)
       pts[k] = make_float4(__ldg(p + (size_t)k * stride), __ldg(p + (size_t)k * stride + 1), __ldg(p + (size_t)k * stride + 2), 0.f);
   }
   // persistent tail of every operand row
-  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 16, SA2_KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 17, SA2_KC)) = make_uint4(0u, 0u, 0u, 0u);
-  if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  if (!issuer) {
+    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 16, SA2_KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 17, SA2_KC)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&ready_bars[0], 128); mbar_init(&ready_bars[1], 128);
+    mbar_fence_init();
+  }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -284,8 +292,38 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
   constexpr uint32_t W3_TILE1 = (128 / 8) * (SA2_K3 / 8) * 128 / 16;   // rows 128..255 of W3, in 16-byte units
   constexpr uint32_t ID128 = make_idesc_bf16(128, 128);
   uint64_t* bar = &bars[g];
+  uint64_t* ready = &ready_bars[g];
   uint32_t phase = 0;
   bool ok = true;
+
+  if (issuer) {
+    // ---- MMA issue warp: for every centroid of the warpgroup, wait for the operand of each layer and issue its MMAs.
+    // Issuing blocks while the tensor pipe drains its queue; keeping it off the row warps lets them prefetch meanwhile.
+    uint32_t rphase = 0;
+    for (int j = g; j < NCENT && ok; j += 2) {
+#pragma unroll 1
+      for (int layer = 0; layer < 3; ++layer) {
+        ok = mbar_wait(ready, rphase); rphase ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
+          if (layer == 0) {
+#pragma unroll
+            for (int ks = 0; ks < SA2_K1 / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW1, ks * 16, ID128, ks > 0);
+          } else if (layer == 1) {
+#pragma unroll
+            for (int ks = 0; ks < SA2_K2 / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW2, ks * 16, ID128, ks > 0);
+          } else {   // transposed: D^T[ch][nbr] = W3[ch tile] * A2^T ; tile 0 -> cols 128.., tile 1 -> cols 0..
+#pragma unroll
+            for (int ks = 0; ks < SA2_K3 / 16; ++ks) mma_bf16_ss_off(tmem + 128, dW3, ks * 16, dX, ks * 16, ID128, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < SA2_K3 / 16; ++ks) mma_bf16_ss_off(tmem, dW3, W3_TILE1 + ks * 16, dX, ks * 16, ID128, ks > 0);
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
 
   // software pipeline: the ball query and the feature-row loads of the NEXT centroid are issued while layer 3 of the
   // current one runs on the tensor pipe; the rows wait in registers until the operand buffer is free again.
@@ -314,17 +352,8 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
     TL_MARK(2);
     fence_proxy_async_smem();
     tc_fence_before();
-    wg_sync(g);
+    mbar_arrive(ready);   // layer 1 operand complete (the issue warp waits for all 128 rows)
     TL_MARK(3);
-    if (wq == 0) {   // layer 1: D[nbr][128] = A0 * W1^T
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < SA2_K1 / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW1, ks * 16, ID128, ks > 0);
-        mma_commit(bar);
-      }
-      __syncwarp();
-    }
     TL_MARK(4);
     ok = mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
@@ -333,17 +362,8 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
     TL_MARK(6);
     fence_proxy_async_smem();
     tc_fence_before();
-    wg_sync(g);
+    mbar_arrive(ready);   // layer 2 operand complete
     TL_MARK(7);
-    if (wq == 0) {   // layer 2: D[nbr][128] = [A1 | 1] * [W2 | b2]^T
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < SA2_K2 / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW2, ks * 16, ID128, ks > 0);
-        mma_commit(bar);
-      }
-      __syncwarp();
-    }
     TL_MARK(8);
     ok = ok && mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
@@ -351,19 +371,8 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
     epilogue_pack_relu<128, SA2_KC>(tlane, X, t);
     fence_proxy_async_smem();
     tc_fence_before();
-    wg_sync(g);
+    mbar_arrive(ready);   // layer 3 operand complete
     TL_MARK(10);
-    if (wq == 0) {   // layer 3 transposed: D^T[ch][nbr] = W3[ch tile] * A2^T ; tile 0 -> cols 128.., tile 1 -> cols 0..
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < SA2_K3 / 16; ++ks) mma_bf16_ss_off(tmem + 128, dW3, ks * 16, dX, ks * 16, ID128, ks > 0);
-#pragma unroll
-        for (int ks = 0; ks < SA2_K3 / 16; ++ks) mma_bf16_ss_off(tmem, dW3, W3_TILE1 + ks * 16, dX, ks * 16, ID128, ks > 0);
-        mma_commit(bar);
-      }
-      __syncwarp();
-    }
     TL_MARK(11);
     if (j + 2 < NCENT) prefetch(j + 2);   // overlaps the layer-3 MMAs
     TL_MARK(1);
@@ -391,11 +400,11 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
       o[256 + 8 + t] = __float2bfloat16_rn(0.f);
     }
     TL_MARK(13);
-    tc_fence_before();
-    wg_sync(g);   // TMEM and X are free for the next centroid of this warpgroup
+    tc_fence_before();   // orders this thread's TMEM reads before its next arrival on `ready`
     TL_MARK(14);
   }
-  if (!ok && t == 0) atomicExch(err, 1);
+  }
+  if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
@@ -775,7 +784,7 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
   MPN_REQUIRE(N == SA1_NPOINT, "tensor-core SA2 expects the 512 SA1 centroids as input points");
   size_t smem = Sa2Smem::total;
   MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sa2_tc_kernel<<<B, 256, smem, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.sa[1][1], tw.sa[1][2],
+  sa2_tc_kernel<<<B, SA2_THREADS, smem, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.sa[1][1], tw.sa[1][2],
                                      c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx, tc_timeline(c));
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
