@@ -100,8 +100,8 @@ def cpu_oracle_steps_per_sec(n_problems: int, steps: int, bf16: bool, seed: int)
     import torch
     from mpinets_b200 import scenes, franka
     from oracle import oracle as O
-    if torch.get_num_threads() < (os.cpu_count() or 1):      # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every host core
-        torch.set_num_threads(os.cpu_count() or 1)
+    if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:   # torchrun pins OMP_NUM_THREADS=1: undo it for the CPU arm
+        torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))      # (physical cores; SMT siblings only slow the GEMMs down)
     tables = franka.default_tables()
     sd = O.reference_state_dict(0)
     p = scenes.config_problems(2, n_problems)

@@ -50,8 +50,6 @@ static int dev_upload(T** p, const T* host, size_t n) {
 static int ensure_workspace(mpn_ctx* c, int B) {
   Workspace& w = c->ws;
   if (B <= w.capacity) return MPN_OK;
-  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  (void)st;
   size_t b = (size_t)B;
   int r = 0;
   r |= dev_alloc(&w.xyz1, b * SA1_NPOINT * 3);

@@ -89,7 +89,6 @@ struct mpn_ctx {
   int Pe = 0; float* ee_points = nullptr;
   int S = 0; float* sph_c = nullptr; float* sph_r = nullptr; int32_t* sph_l = nullptr;
   float prismatic = 0.025f;
-  std::map<std::string, std::pair<std::vector<int64_t>, float*>> raw_weights;  // name -> (shape, device fp32)
   mpn::Weights w;
   mpn::Workspace ws;
   int64_t launches = 0;

@@ -1,20 +1,22 @@
 // sa_tc.cu -- bf16 tcgen05 tensor-core path of the PointNet++ encoder (throughput mode, MPN_PREC_BF16).
 //
 // Replaces the same reference code as sa_simt.cu (pointnet2_ops QueryAndGroup + Conv2d1x1/ReLU x3 + max_pool2d inside
-// PointnetSAModule, mpinets/model.py:365-383) with ONE fused kernel per set-abstraction level:
+// PointnetSAModule, mpinets/model.py:365-383) with ONE fused kernel per set-abstraction level (sa1_tc_kernel,
+// sa2_tc_kernel); the group-all level and the FC head run on the tcgen05 GEMM of gemm_tc.cu.
 //
-//   CTA = one problem, 256 threads = two independent warpgroups (WG) that ping-pong over the problem's centroids, so one
-//   WG's SIMT work (ball query, gather, epilogues) overlaps the other WG's MMAs on the single tensor pipe.
-//   per centroid, per WG:  ball query (index order kept by ballot + prefix popcount, 4 warps scan 4 segments)
-//     -> gather the 128 neighbours' rows straight into the UMMA A-operand layout in shared memory (bf16, K-major
-//        8x16B core matrices)  -> tcgen05.mma layer 1 (accumulator in TMEM)  -> epilogue: tcgen05.ld, +bias, ReLU, bf16,
-//        written back over the same smem buffer as the next layer's A operand -> layer 2 -> layer 3 -> max over the 128
-//        neighbours -> one pooled row to HBM.  Weights stay resident in shared memory for the whole CTA.
-//   Last layer of SA2 runs transposed (D^T = W3 * A^T: TMEM lane = output channel, column = neighbour) so the max-pool is a
-//   per-thread register reduction; SA1 (64 channels = half an M tile) pools with redux.sync instead.
-//
-// K order of layer 1 is [features..., dx, dy, dz, 0-pad] (a permutation of the reference's [dx,dy,dz,features] applied
-// to both operand and weight) so feature rows are copied as aligned 16-byte chunks.
+//   CTA = one problem.  Row warpgroups (128 threads = the 128 neighbour rows = the 128 TMEM lanes) stream centroids
+//   independently, so one group's SIMT phases overlap another group's MMAs on the SM's single tensor pipe.
+//   per centroid:  ball query (pointnet2 semantics kept bit-exact: first 128 hits in index order, first-hit padding)
+//     -> gather the neighbours' rows straight into the UMMA operand layout in shared memory (bf16, K-major 8x16 B core
+//        matrices, bias carried by a column of ones)  -> tcgen05.mma (accumulator in TMEM)  -> epilogue: tcgen05.ld,
+//        cvt.rn.relu.bf16x2, st.shared over the SAME buffer (the previous operand is dead once its MMA retired)
+//     -> layer 2 -> layer 3 -> max over the 128 neighbours -> one pooled bf16 row to HBM.
+//   SA2: last layer transposed (TMEM lane = channel) so the max-pool is a per-thread reduction; ball query and feature
+//        prefetch of the next centroid are issued while layer 3 runs; MMAs are issued by a dedicated warp per group.
+//   SA1: exact hash-grid ball query on a producer warp per group (2-slot list ring, full/empty mbarriers); integer
+//        redux.sync max-pool.
+//   K order of layer 1 is [features..., dx, dy, dz, 1, 0-pad] (a permutation of the reference's [dx,dy,dz,features]
+//   applied to both operand and weight) so feature rows are copied as aligned 16-byte chunks.
 #include "engine.h"
 #include "spec_math.cuh"
 #include "tc_common.cuh"
@@ -105,29 +107,6 @@ __device__ __forceinline__ void stage_weight(const __nv_bfloat16* __restrict__ g
 __device__ __forceinline__ uint64_t tile_desc(uint32_t base, int K, int r0, int ks) {
   const int KC = K / 8;
   return make_smem_desc(base + (uint32_t)((r0 >> 3) * KC * 128 + ks * 256), 128, KC * 128, LAYOUT_NONE);
-}
-
-// epilogue (standard form, thread = row): TMEM [128][NC] fp32 -> relu(acc + bias) -> bf16 -> X (next A operand, K = NC)
-template <int NC>
-__device__ __forceinline__ void epilogue_to_smem(uint32_t taddr, const float* __restrict__ bias, uint8_t* X, int row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < NC; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(taddr + c0, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t p[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        int j = q * 8 + e * 2;
-        float a = fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f);
-        float b = fmaxf(__uint_as_float(v[j + 1]) + bias[c0 + j + 1], 0.f);
-        p[e] = pack_bf16(a, b);
-      }
-      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(row, (c0 >> 3) + q, NC / 8)) = make_uint4(p[0], p[1], p[2], p[3]);
-    }
-  }
 }
 
 // ball query by one warpgroup over points in shared memory (float4): same semantics as pointnet.cu
@@ -417,7 +396,7 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
 // signed-integer redux on the raw accumulator bits (max over non-negative floats == max over their bit patterns; a
 // negative result is clamped by the final ReLU).
 constexpr int SA1_NWG = 4;
-constexpr int SA1_BUCKETS = 4096, SA1_HCAP = 512;
+constexpr int SA1_BUCKETS = 4096;
 constexpr int SA1_THREADS = 128 * SA1_NWG + 32 * SA1_NWG;   // 4 warpgroups of 4 row warps + one ball-query producer warp each
 struct Sa1Smem {
   static constexpr size_t w = 0;                                          // 3 x [64][80] bf16
