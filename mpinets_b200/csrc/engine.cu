@@ -273,6 +273,7 @@ int mpn_set_robot_tables(mpn_ctx* c, const float* joint_limits, int P, const flo
   r |= dev_upload(&c->sph_l, sph_l, (size_t)S);
   if (r) return r;
   c->P = P; c->Pe = Pe; c->S = S; c->prismatic = prismatic;
+  if ((r = pack_link_table(c))) return r;
   c->tables_set = true;
   return MPN_OK;
 }
@@ -519,7 +520,7 @@ int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene,
   MPN_CHECK_CUDA(cudaMemsetAsync(w.first_step, 0xff, (size_t)B * 4, s));
   MPN_CHECK_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)B, s));
   if ((r = launch_fk(c, s, q0, B, w.frames, w.eef))) return r;
-  if (check_every_step && (r = launch_sweep(c, s, *scene, B, traj, 1, stride, 0, 0, w.flags, w.first_step))) return r;
+  if (check_every_step && (r = launch_sweep(c, s, *scene, B, traj, 1, stride, 0, 0, w.flags, w.first_step, w.frames))) return r;
   for (int i = 1; i <= T; ++i) {
     if ((r = policy_forward(c, s, precision, cloud, w.qn, B, N, w.dq))) return r;
     { StageTimer t(c, s, MPN_ST_UPDATE);
@@ -528,7 +529,7 @@ int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene,
       if ((r = launch_sample_robot(c, s, w.frames, B, c->cfg.n_robot, (uint32_t)i, cloud, N))) return r; }
     if (check_every_step) {
       StageTimer t(c, s, MPN_ST_SWEEP);
-      if ((r = launch_sweep(c, s, *scene, B, traj + (size_t)i * 7, 1, stride, i, 1, w.flags, w.first_step))) return r;
+      if ((r = launch_sweep(c, s, *scene, B, traj + (size_t)i * 7, 1, stride, i, 1, w.flags, w.first_step, w.frames))) return r;
     }
   }
   if (!check_every_step) {

@@ -86,6 +86,7 @@ struct mpn_ctx {
   float limits_host[14] = {0};
   float* limits = nullptr;       // [7][2]
   int P = 0; float* link_points = nullptr; int32_t* link_ids = nullptr;
+  float* link_table4 = nullptr;  // [P] float4 (x, y, z, link id bits): one gather per robot row
   int Pe = 0; float* ee_points = nullptr;
   int S = 0; float* sph_c = nullptr; float* sph_r = nullptr; int32_t* sph_l = nullptr;
   float prismatic = 0.025f;
@@ -118,13 +119,14 @@ struct StageTimer {
 // ---- geometry.cu
 int launch_fk(mpn_ctx* c, cudaStream_t s, const float* q, int B, float* frames, float* eef);
 int launch_sample_robot(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, uint32_t step, float* cloud, int rows);
+int pack_link_table(mpn_ctx* c);
 int launch_spheres(mpn_ctx* c, cudaStream_t s, const float* frames, int B, float* centers);
 int launch_normalize(mpn_ctx* c, cudaStream_t s, const float* in, int n, float* out, bool unnormalize);
 int launch_sdf_points(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* pts, int N, int which, float* sdf);
 int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* frames, const float* target,
                        uint32_t problem0, float* cloud);
 int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T, int traj_stride_t,
-                 int t0, int accumulate, uint8_t* flags, int32_t* first_step);
+                 int t0, int accumulate, uint8_t* flags, int32_t* first_step, const float* frames_in = nullptr);
 // ---- pointnet.cu
 int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz);
 int launch_ball_query(mpn_ctx* c, cudaStream_t s, float radius, int nsample, const float* xyz, int B, int N, int stride,

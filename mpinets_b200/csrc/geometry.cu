@@ -38,12 +38,17 @@ int launch_fk(mpn_ctx* c, cudaStream_t s, const float* q, int B, float* frames, 
 }
 
 // ------------------------------------------------------------------------------------------------ robot rows
-// one CTA per problem; frames staged in smem; each thread writes whole 16-byte rows (x,y,z,mask=0): a warp
-// writes 512 contiguous bytes.
+// one CTA per problem; frames staged in smem; the canonical table is packed as float4 (x, y, z, link id) so a row costs
+// one 16-byte gather (the 64 KB table lives in L1/L2) and one 16-byte row store (a warp writes 512 contiguous bytes);
+// 8 rows per thread are processed with all their loads in flight.
+__global__ void pack_link_table_kernel(const float* __restrict__ lp, const int32_t* __restrict__ lid, int P, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) out[i] = make_float4(lp[3 * i], lp[3 * i + 1], lp[3 * i + 2], __int_as_float(lid[i]));
+}
+
 __global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restrict__ frames, int n, int P,
-                                                           const float* __restrict__ lp, const int32_t* __restrict__ lid,
-                                                           uint32_t seed_lo, uint32_t seed_hi, uint32_t step,
-                                                           float4* __restrict__ cloud, int rows) {
+                                                           const float4* __restrict__ table, uint32_t seed_lo, uint32_t seed_hi,
+                                                           uint32_t step, float4* __restrict__ cloud, int rows) {
   __shared__ float F[MPN_NLINK * 12];
   int b = blockIdx.x;
   for (int i = threadIdx.x; i < MPN_NLINK * 12; i += blockDim.x) F[i] = frames[(size_t)b * MPN_NLINK * 12 + i];
@@ -52,22 +57,41 @@ __global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restri
   uint32_t half = feistel_bits((uint32_t)P) / 2;
   __syncthreads();
   float4* out = cloud + (size_t)b * rows;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    uint32_t e = feistel_perm((uint32_t)j, (uint32_t)P, half, key);
-    float px = __ldg(lp + 3 * e), py = __ldg(lp + 3 * e + 1), pz = __ldg(lp + 3 * e + 2);
-    int l = __ldg(lid + e);
-    float4 o;
-    m34_apply(F + 12 * l, px, py, pz, o.x, o.y, o.z);
-    o.w = 0.0f;
-    out[j] = o;
+  constexpr int U = 8;
+  for (int j0 = threadIdx.x; j0 < n; j0 += blockDim.x * U) {
+    float4 t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int j = j0 + u * blockDim.x;
+      if (j < n) t[u] = __ldg(table + feistel_perm((uint32_t)j, (uint32_t)P, half, key));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int j = j0 + u * blockDim.x;
+      if (j < n) {
+        float4 o;
+        m34_apply(F + 12 * __float_as_int(t[u].w), t[u].x, t[u].y, t[u].z, o.x, o.y, o.z);
+        o.w = 0.0f;
+        out[j] = o;
+      }
+    }
   }
 }
 
 int launch_sample_robot(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, uint32_t step, float* cloud, int rows) {
-  sample_robot_kernel<<<B, 256, 0, s>>>(frames, n, c->P, c->link_points, c->link_ids, (uint32_t)c->cfg.seed,
+  sample_robot_kernel<<<B, 256, 0, s>>>(frames, n, c->P, reinterpret_cast<const float4*>(c->link_table4), (uint32_t)c->cfg.seed,
                                         (uint32_t)(c->cfg.seed >> 32), step, (float4*)cloud, rows);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+int pack_link_table(mpn_ctx* c) {
+  if (c->link_table4) cudaFree(c->link_table4);
+  MPN_CHECK_CUDA(cudaMalloc(&c->link_table4, (size_t)c->P * sizeof(float4)));
+  pack_link_table_kernel<<<(c->P + 255) / 256, 256>>>(c->link_points, c->link_ids, c->P, reinterpret_cast<float4*>(c->link_table4));
+  MPN_CHECK_CUDA(cudaGetLastError());
+  MPN_CHECK_CUDA(cudaDeviceSynchronize());
   return MPN_OK;
 }
 
@@ -290,7 +314,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(mpn_scene sc, int 
                                                               int t0, float prismatic, int S, const float* __restrict__ sph_c,
                                                               const float* __restrict__ sph_r, const int32_t* __restrict__ sph_l,
                                                               int accumulate, uint8_t* __restrict__ flags,
-                                                              int32_t* __restrict__ first_step) {
+                                                              int32_t* __restrict__ first_step, const float* __restrict__ frames_in) {
   __shared__ PrimFrame fr[MAX_PRIMS];
   __shared__ float F[SWEEP_TCHUNK][MPN_NLINK * 12];
   __shared__ float sc_s[MAX_SPHERES * 3];
@@ -307,7 +331,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(mpn_scene sc, int 
   __syncthreads();
   for (int tc = 0; tc < T; tc += SWEEP_TCHUNK) {
     int nt = min(SWEEP_TCHUNK, T - tc);
-    if (threadIdx.x < nt) {
+    if (frames_in) {   // T == 1: link frames of this configuration were already produced by the step update (same spec FK)
+      for (int i = threadIdx.x; i < MPN_NLINK * 12; i += blockDim.x) F[0][i] = frames_in[(size_t)b * MPN_NLINK * 12 + i];
+    } else if (threadIdx.x < nt) {
       float qq[7];
       const float* qp = traj + (size_t)b * problem_stride + (size_t)(tc + threadIdx.x) * 7;
 #pragma unroll
@@ -341,10 +367,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(mpn_scene sc, int 
 }
 
 int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T, int problem_stride,
-                 int t0, int accumulate, uint8_t* flags, int32_t* first_step) {
+                 int t0, int accumulate, uint8_t* flags, int32_t* first_step, const float* frames_in) {
+  if (T != 1) frames_in = nullptr;
   sweep_kernel<<<B, SWEEP_THREADS, 0, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, c->cfg.quirk_frames, traj, T,
                                            problem_stride, t0, c->prismatic, c->S, c->sph_c, c->sph_r, c->sph_l,
-                                           accumulate, flags, first_step);
+                                           accumulate, flags, first_step, frames_in);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

@@ -17,6 +17,8 @@
 //        redux.sync max-pool.
 //   K order of layer 1 is [features..., dx, dy, dz, 1, 0-pad] (a permutation of the reference's [dx,dy,dz,features]
 //   applied to both operand and weight) so feature rows are copied as aligned 16-byte chunks.
+#include <cstdlib>
+
 #include "engine.h"
 #include "spec_math.cuh"
 #include "tc_common.cuh"
@@ -30,6 +32,7 @@ struct TcWeights {
   __nv_bfloat16* sa[3][3] = {{nullptr}};  // [Cout][Kpad] K-major, layer-0 K order permuted
   int kpad[3][3] = {{0}};
   __nv_bfloat16* fc[3] = {nullptr};       // [out][in]
+  __nv_bfloat16* w2_nofold = nullptr;     // SA2 layer 2 as plain [128][128] (3-warpgroup variant adds the bias in the epilogue)
 };
 static std::map<mpn_ctx*, TcWeights> g_tc;
 int* tc_error_flag(mpn_ctx* c);
@@ -68,6 +71,13 @@ int tc_prepare_weights(mpn_ctx* c) {
                                                    bias_col >= 0 ? L.b : nullptr, bias_col);
       MPN_CHECK_CUDA(cudaGetLastError());
     }
+  {
+    const Linear& L = c->w.sa[1][1];
+    if (t.w2_nofold) cudaFree(t.w2_nofold);
+    MPN_CHECK_CUDA(cudaMalloc(&t.w2_nofold, (size_t)L.out * L.in * sizeof(__nv_bfloat16)));
+    pack_weight_kernel<<<(L.out * L.in + 255) / 256, 256>>>(L.w, L.out, L.in, L.in, 0, t.w2_nofold);
+    MPN_CHECK_CUDA(cudaGetLastError());
+  }
   for (int l = 0; l < 3; ++l) {
     const Linear& L = c->w.fc[l];
     if (t.fc[l]) cudaFree(t.fc[l]);
@@ -382,6 +392,222 @@ sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __
     tc_fence_before();   // orders this thread's TMEM reads before its next arrival on `ready`
     TL_MARK(14);
   }
+  }
+  if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- SA2, 3 warpgroups
+// Variant of sa2_tc_kernel with THREE row warpgroups per CTA (3 centroids in flight instead of 2).  To fit shared memory
+// the operand rows shrink to 128 K-columns (32 KB per group): layer 1 keeps its bias in the free column 67, layer 2 adds
+// its bias in the epilogue (fp32), and the ball query is done by one warp per centroid over the smem-resident xyz
+// (index order falls out of the in-order scan, no merge lists).  TMEM: 128 columns per group, so the transposed last
+// layer runs as two sequential channel tiles.
+constexpr int SA2W_NWG = 3, SA2W_KC = 16, SA2W_THREADS = 128 * SA2W_NWG;
+struct Sa2wSmem {
+  static constexpr size_t w1 = 0;                                     // [128][80]
+  static constexpr size_t w2 = w1 + 128 * 80 * 2;                     // [128][128]
+  static constexpr size_t w3 = w2 + 128 * 128 * 2;                    // [256][128]
+  static constexpr size_t x = w3 + 256 * 128 * 2;                     // NWG x [128][128] bf16
+  static constexpr size_t b2 = x + (size_t)SA2W_NWG * 128 * 128 * 2;  // [128] float
+  static constexpr size_t b3 = b2 + 128 * 4;                          // [256] float
+  static constexpr size_t pts = b3 + 256 * 4;                         // x[512] | y[512] | z[512]
+  static constexpr size_t lists = pts + 3 * SA1_NPOINT * 4;           // [NWG][2 slots][4][128] u16
+  static constexpr size_t bars = lists + (size_t)SA2W_NWG * 2 * 4 * 128 * 2;   // NWG mbarriers + tmem slot
+  static constexpr size_t total = bars + 64;
+};
+
+__global__ void __launch_bounds__(SA2W_THREADS, 1)
+sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __restrict__ feat_bf16, const float* __restrict__ new_xyz,
+                float r2, const __nv_bfloat16* __restrict__ gw1, const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3,
+                const float* __restrict__ gb2, const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16, int out_stride,
+                int* __restrict__ err, int32_t* __restrict__ ball_idx) {
+  using S = Sa2wSmem;
+  constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT, KC = SA2W_KC;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW1 = smem + S::w1;
+  uint8_t* sW2 = smem + S::w2;
+  uint8_t* sW3 = smem + S::w3;
+  float* sB2 = reinterpret_cast<float*>(smem + S::b2);
+  float* sB3 = reinterpret_cast<float*>(smem + S::b3);
+  float* px = reinterpret_cast<float*>(smem + S::pts);
+  float* py = px + N;
+  float* pz = py + N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * SA2W_NWG);
+
+  const int b = blockIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int g = warp >> 2, wq = warp & 3, lane = threadIdx.x & 31;
+  const int t = threadIdx.x & 127;
+  uint8_t* X = smem + S::x + (size_t)g * 128 * 128 * 2;
+  uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 2 * 4 * 128;
+
+  stage_weight(gw1, 128, 80, sW1);
+  stage_weight(gw2, 128, 128, sW2);
+  stage_weight(gw3, 256, 128, sW3);
+  for (int i = threadIdx.x; i < 128; i += SA2W_THREADS) sB2[i] = gb2[i];
+  for (int i = threadIdx.x; i < 256; i += SA2W_THREADS) sB3[i] = gb3[i];
+  {
+    const float* p = xyz + (size_t)b * N * stride;
+    for (int k = threadIdx.x; k < N; k += SA2W_THREADS) {
+      px[k] = __ldg(p + (size_t)k * stride); py[k] = __ldg(p + (size_t)k * stride + 1); pz[k] = __ldg(p + (size_t)k * stride + 2);
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SA2W_NWG; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot + (uint32_t)g * 128;
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+  const uint64_t dX = make_smem_desc(smem_u32(X), 128, KC * 128, LAYOUT_NONE);
+  const uint64_t dW1 = make_smem_desc(smem_u32(sW1), 128, 10 * 128, LAYOUT_NONE);
+  const uint64_t dW2 = make_smem_desc(smem_u32(sW2), 128, 16 * 128, LAYOUT_NONE);
+  const uint64_t dW3 = make_smem_desc(smem_u32(sW3), 128, 16 * 128, LAYOUT_NONE);
+  constexpr uint32_t W3_TILE1 = (128 / 8) * 16 * 128 / 16;
+  constexpr uint32_t ID128 = make_idesc_bf16(128, 128);
+  uint64_t* bar = &bars[g];
+  uint32_t phase = 0;
+  bool ok = true;
+  const unsigned lt = (1u << lane) - 1u;
+
+  // one warp = one centroid: in-order scan of the 512 points, first 128 hits, first-hit padding (pointnet2 semantics)
+  auto bq_round = [&](int base, int slot) {
+    const int jc = base + wq;
+    if (jc < NCENT) {
+      const float* cp = new_xyz + ((size_t)b * NCENT + jc) * 3;
+      const float qx = cp[0], qy = cp[1], qz = cp[2];
+      uint16_t* out = lists + (slot * 4 + wq) * 128;
+      int cnt = 0, first = 0;
+#pragma unroll 4
+      for (int k0 = 0; k0 < N; k0 += 32) {
+        const int k = k0 + lane;
+        const bool hit = dist2(qx, qy, qz, px[k], py[k], pz[k]) < r2;
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (cnt == 0 && hm) first = k0 + __ffs(hm) - 1;
+        const int pos = cnt + __popc(hm & lt);
+        if (hit && pos < NSAMPLE) out[pos] = (uint16_t)k;
+        cnt += __popc(hm);
+      }
+      for (int l = min(cnt, NSAMPLE) + lane; l < NSAMPLE; l += 32) out[l] = (uint16_t)first;
+    }
+  };
+  float cx, cy, cz, dx, dy, dz;
+  uint4 fr[8];
+  auto prefetch = [&](int jn, int slot, int cc) {
+    const float* cp = new_xyz + ((size_t)b * NCENT + jn) * 3;
+    cx = cp[0]; cy = cp[1]; cz = cp[2];
+    const int k = lists[(slot * 4 + cc) * 128 + t];
+    if (ball_idx) ball_idx[((size_t)b * NCENT + jn) * NSAMPLE + t] = k;
+    dx = fsub(px[k], cx); dy = fsub(py[k], cy); dz = fsub(pz[k], cz);
+    const uint4* f = reinterpret_cast<const uint4*>(feat_bf16 + ((size_t)b * N + k) * 64);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) fr[q] = __ldg(f + q);
+  };
+  auto issue = [&](uint64_t da, uint32_t aoff, uint64_t db, uint32_t boff, int ksteps) {
+    if (wq == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss_off(tmem, da, aoff + ks * 16, db, boff + ks * 16, ID128, ks > 0);
+        mma_commit(bar);
+      }
+      __syncwarp();
+    }
+  };
+
+  // centroids of warpgroup g: rounds of 4 consecutive centroids, rounds interleaved over the warpgroups
+  int r = 0;
+  const int base0 = g * 4;
+  if (base0 < NCENT) {
+    bq_round(base0, 0);
+    wg_sync(g);
+    prefetch(base0, 0, 0);
+  }
+  for (int base = base0; base < NCENT && ok; base += SA2W_NWG * 4, ++r) {
+    const int slot = r & 1;
+#pragma unroll 1
+    for (int cc = 0; cc < 4 && ok; ++cc) {
+      const int j = base + cc;
+      if (j >= NCENT) break;
+      const float ccx = cx, ccy = cy, ccz = cz;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, q, KC)) = fr[q];
+      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 1.0f), 0u, 0u);
+      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KC)) = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      wg_sync(g);
+      issue(dX, 0, dW1, 0, 5);                                  // layer 1: K = 80 (bias in column 67)
+      ok = mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+      epilogue_pack_relu<128, KC>(tlane, X, t);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      wg_sync(g);
+      issue(dX, 0, dW2, 0, 8);                                  // layer 2: K = 128, bias added below
+      ok = ok && mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tlane + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* bb = sB2 + c0 + q * 8;
+          *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, (c0 >> 3) + q, KC)) =
+              make_uint4(cvt_relu_bf16x2(__uint_as_float(v[q * 8]) + bb[0], __uint_as_float(v[q * 8 + 1]) + bb[1]),
+                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 2]) + bb[2], __uint_as_float(v[q * 8 + 3]) + bb[3]),
+                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 4]) + bb[4], __uint_as_float(v[q * 8 + 5]) + bb[5]),
+                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 6]) + bb[6], __uint_as_float(v[q * 8 + 7]) + bb[7]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      wg_sync(g);
+      issue(dW3, 0, dX, 0, 8);                                  // layer 3, channel tile 0 (transposed)
+      // next centroid: its ball-query round (if this was the last of the round) and its feature rows, under the MMAs
+      {
+        int jn = j + 1, nslot = slot, ncc = cc + 1;
+        if (cc == 3) { jn = base + SA2W_NWG * 4; nslot = slot ^ 1; ncc = 0; }
+        if (jn < NCENT) {
+          if (cc == 3) { bq_round(jn, nslot); wg_sync(g); }
+          prefetch(jn, nslot, ncc);
+        }
+      }
+      __nv_bfloat16* o = out_bf16 + ((size_t)b * NCENT + j) * out_stride;
+#pragma unroll 1
+      for (int tile = 0; tile < 2; ++tile) {
+        ok = ok && mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        float m = -3.0e38f;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 64) {
+          uint32_t v[32], u[32];
+          tmem_ld32(tlane + c0, v);
+          tmem_ld32(tlane + c0 + 32, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) m = fmaxf(m, fmaxf(__uint_as_float(v[q]), __uint_as_float(u[q])));
+        }
+        o[tile * 128 + t] = __float2bfloat16_rn(fmaxf(m + sB3[tile * 128 + t], 0.f));
+        tc_fence_before();
+        wg_sync(g);                                             // every lane of the accumulator has been read
+        if (tile == 0) issue(dW3, W3_TILE1, dX, 0, 8);           // channel tile 1 into the same TMEM columns
+      }
+      if (t < 8) {
+        float v = t == 0 ? ccx : (t == 1 ? ccy : (t == 2 ? ccz : 0.f));
+        o[256 + t] = __float2bfloat16_rn(v);
+        o[256 + 8 + t] = __float2bfloat16_rn(0.f);
+      }
+    }
   }
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
@@ -761,6 +987,16 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     return MPN_OK;
   }
   MPN_REQUIRE(N == SA1_NPOINT, "tensor-core SA2 expects the 512 SA1 centroids as input points");
+  static const bool three = getenv("MPN_SA2_3WG") != nullptr;
+  if (three) {
+    size_t smem3 = Sa2wSmem::total;
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2w3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    sa2w3_tc_kernel<<<B, SA2W_THREADS, smem3, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.w2_nofold,
+                                                   tw.sa[1][2], c->w.sa[1][1].b, c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    return MPN_OK;
+  }
   size_t smem = Sa2Smem::total;
   MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sa2_tc_kernel<<<B, SA2_THREADS, smem, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.sa[1][1], tw.sa[1][2],
