@@ -931,6 +931,254 @@ sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ 
   if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, 256);
 }
 
+// ---------------------------------------------------------------------------------------------- SA1, 6 warpgroups
+// Variant of sa1_tc_kernel with SIX row warpgroups per CTA (6 centroids in flight instead of 4).  Shared memory is freed
+// by keeping only the hash grid's index structure on chip (bucket starts + point indices); candidate coordinates are
+// gathered from the problem's cloud in L2.  Every warp runs the complete ball query of one centroid of its group's next
+// round (cells -> candidates -> hits -> rank by point index), so there are no block-level syncs inside the query.
+template <int SA1W_NWG>
+struct Sa1wSmem {
+  static constexpr size_t w = 0;                                           // 3 x [64][80] bf16
+  static constexpr size_t x = w + 3 * 64 * SA1_XK * 2;                     // NWG x [128][80] bf16 (aliased by the grid build)
+  static constexpr size_t lists = x + (size_t)SA1W_NWG * 128 * SA1_XK * 2; // [NWG][4][128] u16
+  static constexpr size_t cand = lists + SA1W_NWG * 4 * 128 * 2;           // [NWG][4][256] u16
+  static constexpr size_t red = cand + SA1W_NWG * 4 * 256 * 2;             // [NWG][4][64] int
+  static constexpr size_t bars = red + SA1W_NWG * 4 * 64 * 4;              // NWG mbarriers + tmem slot
+  static constexpr size_t bstart = (bars + 64 + 15) / 16 * 16;             // u16 [BUCKETS + 1]
+  static constexpr size_t sidx = (bstart + (SA1_BUCKETS + 1) * 2 + 15) / 16 * 16;   // u16 [N]
+  static size_t total(int N) { return sidx + (size_t)N * 2 + 64; }
+};
+
+template <int SA1W_NWG>
+__global__ void __launch_bounds__(128 * SA1W_NWG, 1)
+sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
+                const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
+                int* __restrict__ err, int32_t* __restrict__ ball_idx) {
+  using S = Sa1wSmem<SA1W_NWG>;
+  constexpr int KC = SA1_XK / 8, NS = NSAMPLE;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW1 = smem + S::w;
+  uint8_t* sW2 = sW1 + 64 * SA1_XK * 2;
+  uint8_t* sW3 = sW2 + 64 * SA1_XK * 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * SA1W_NWG);
+  uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + S::bstart);
+  uint16_t* sidx = reinterpret_cast<uint16_t*>(smem + S::sidx);
+
+  const int b = blockIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int g = warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
+  uint8_t* X = smem + S::x + (size_t)g * 128 * SA1_XK * 2;
+  uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 4 * 128;
+  uint16_t* wcand = reinterpret_cast<uint16_t*>(smem + S::cand) + (size_t)(g * 4 + wq) * 256;
+  int* red = reinterpret_cast<int*>(smem + S::red) + g * 4 * 64;
+  const float4* cl = reinterpret_cast<const float4*>(cloud) + (size_t)b * N;
+
+  stage_weight(gw1, 64, SA1_XK, sW1);
+  stage_weight(gw2, 64, SA1_XK, sW2);
+  stage_weight(gw3, 64, SA1_XK, sW3);
+  // ---- hash-grid build: counting sort of point indices by bucket (counters alias the operand buffers)
+  {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + S::x);
+    __shared__ uint32_t wsum[16];
+    for (int i = threadIdx.x; i < SA1_BUCKETS; i += blockDim.x) cnt[i] = 0u;
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const float4 v = __ldg(cl + k);
+      atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u);
+    }
+    __syncthreads();
+    constexpr int PER = SA1_BUCKETS / 512;
+    const bool scanner = threadIdx.x < 512;
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = scanner ? cnt[threadIdx.x * PER + i] : 0u; sum += loc[i]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31 && scanner) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t v = lane < 16 ? wsum[lane] : 0u, iv = v;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+      if (lane < 16) wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    if (scanner) {
+      uint32_t run = wsum[threadIdx.x >> 5] + inc - sum;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { bstart[threadIdx.x * PER + i] = (uint16_t)run; cnt[threadIdx.x * PER + i] = run; run += loc[i]; }
+    }
+    if (threadIdx.x == 0) bstart[SA1_BUCKETS] = (uint16_t)N;
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const float4 v = __ldg(cl + k);
+      sidx[atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u)] = (uint16_t)k;
+    }
+    __syncthreads();
+  }
+  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KC)) = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SA1W_NWG; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot + (uint32_t)g * 64;
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+  const uint64_t dX = tile_desc(smem_u32(X), SA1_XK, 0, 0), dW1 = tile_desc(smem_u32(sW1), SA1_XK, 0, 0);
+  const uint64_t dW2 = tile_desc(smem_u32(sW2), SA1_XK, 0, 0), dW3 = tile_desc(smem_u32(sW3), SA1_XK, 0, 0);
+  uint64_t* bar = &bars[g];
+  uint32_t phase = 0;
+  bool ok = true;
+  constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
+  const unsigned lt = (1u << lane) - 1u;
+
+  // complete ball query of centroid jc by this warp -> lists[wq][0..127]
+  auto warp_ball_query = [&](int jc) {
+    uint16_t* widx = lists + wq * 128;
+    const float* cpw = new_xyz + ((size_t)b * SA1_NPOINT + jc) * 3;
+    const float qx = cpw[0], qy = cpw[1], qz = cpw[2];
+    const int ix = grid_coord(qx), iy = grid_coord(qy), iz = grid_coord(qz);
+    uint32_t bk = 0x10000u + lane;
+    if (lane < 27) bk = grid_bucket(ix + (lane % 3) - 1, iy + ((lane / 3) % 3) - 1, iz + (lane / 9) - 1);
+    const unsigned peers = __match_any_sync(0xffffffffu, bk);
+    const bool leader = lane < 27 && lane == __ffs(peers) - 1;
+    int s0 = 0, n0 = 0;
+    if (leader) { s0 = bstart[bk]; n0 = bstart[bk + 1] - s0; }
+    int incl = n0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int C = __shfl_sync(0xffffffffu, incl, 31);
+    if (C <= 256) {
+      for (int i = 0, o = incl - n0; i < n0; ++i) wcand[o + i] = sidx[s0 + i];   // candidates by ORIGINAL point index
+      __syncwarp();
+      int H = 0;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int ci = c0 + lane;
+        bool hit = false;
+        int k = 0;
+        if (ci < C) { k = wcand[ci]; const float4 v = __ldg(cl + k); hit = dist2(qx, qy, qz, v.x, v.y, v.z) < r2; }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hit) wcand[H + __popc(hm & lt)] = (uint16_t)k;         // in place: write position <= read position
+        H += __popc(hm);
+        __syncwarp();
+      }
+      for (int h = lane; h < H; h += 32) {
+        const int my = wcand[h];
+        int rank = 0;
+        for (int i = 0; i < H; ++i) rank += wcand[i] < my;
+        if (rank < NS) widx[rank] = (uint16_t)my;
+      }
+      __syncwarp();
+      const uint16_t first = H > 0 ? widx[0] : (uint16_t)0;
+      for (int l = min(H, NS) + lane; l < NS; l += 32) widx[l] = first;
+    } else {
+      int cnt = 0;
+      uint16_t first = 0;
+      for (int k0 = 0; k0 < N && cnt < NS; k0 += 32) {
+        const int k = k0 + lane;
+        bool hit = false;
+        if (k < N) { const float4 v = __ldg(cl + k); hit = dist2(qx, qy, qz, v.x, v.y, v.z) < r2; }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm && cnt == 0) first = (uint16_t)(k0 + __ffs(hm) - 1);
+        const int pos = cnt + __popc(hm & lt);
+        if (hit && pos < NS) widx[pos] = (uint16_t)k;
+        cnt += __popc(hm);
+      }
+      for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
+    }
+    __syncwarp();
+  };
+  auto issue = [&](uint64_t dW, bool first_layer) {
+    if (wq == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        if (first_layer) {
+          mma_bf16_ss_off(tmem, dX, 0, dW, 0, IDESC, 0);
+          mma_bf16_ss_off(tmem, dX, 64, dW, 64, IDESC, 1);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < SA1_XK / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW, ks * 16, IDESC, ks > 0);
+        }
+        mma_commit(bar);
+      }
+      __syncwarp();
+    }
+  };
+
+  for (int base = g * 4; base < SA1_NPOINT && ok; base += SA1W_NWG * 4) {
+    if (base + wq < SA1_NPOINT) warp_ball_query(base + wq);
+    wg_sync(g);
+    float4 pn = __ldg(cl + lists[t]);
+    const float* cpn = new_xyz + ((size_t)b * SA1_NPOINT + base) * 3;
+    float nx = cpn[0], ny = cpn[1], nz = cpn[2];
+#pragma unroll 1
+    for (int cc = 0; cc < 4 && ok; ++cc) {
+      const int j = base + cc;
+      if (j >= SA1_NPOINT) break;
+      const float cx = nx, cy = ny, cz = nz;
+      const float4 p = pn;
+      if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = lists[cc * 128 + t];
+      {
+        const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
+        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u);
+        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KC)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      wg_sync(g);
+      issue(dW1, true);
+      if (cc < 3 && j + 1 < SA1_NPOINT) {   // next centroid's gathered point and coordinates, under the MMAs
+        pn = __ldg(cl + lists[(cc + 1) * 128 + t]);
+        const float* cq = new_xyz + ((size_t)b * SA1_NPOINT + j + 1) * 3;
+        nx = cq[0]; ny = cq[1]; nz = cq[2];
+      }
+#pragma unroll 1
+      for (int layer = 1; layer < 3; ++layer) {
+        ok = ok && mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        epilogue_pack_relu<64, KC>(tlane, X, t);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        wg_sync(g);
+        issue(layer == 1 ? dW2 : dW3, false);
+      }
+      ok = ok && mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tlane + c0, v);
+        tmem_ld_wait();
+        int keep = 0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int mx = __reduce_max_sync(0xffffffffu, (int)v[q]);
+          keep = lane == q ? mx : keep;
+        }
+        red[wq * 64 + c0 + lane] = keep;
+      }
+      tc_fence_before();
+      wg_sync(g);
+      if (t < 64) {
+        const int m = max(max(red[t], red[64 + t]), max(red[128 + t], red[192 + t]));
+        out_bf16[((size_t)b * SA1_NPOINT + j) * 64 + t] = __float2bfloat16_rn(fmaxf(__int_as_float(m), 0.f));
+      }
+    }
+    wg_sync(g);   // the lists are rewritten by the next round
+  }
+  if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
 // bf16 -> fp32 widening of the pooled SA2 rows for the (still fp32) group-all / FC stages
 __global__ void widen_kernel(const __nv_bfloat16* __restrict__ src, int rows, int src_stride, int cols, float* __restrict__ dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -975,6 +1223,29 @@ template <int MODULE>
 static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
                         int B, __nv_bfloat16* out, int out_stride, int32_t* ball_idx = nullptr) {
   TcWeights& tw = g_tc[c];
+  // SA1 variants: default = 6 row warpgroups with the grid index on chip; MPN_SA1_WG=7 tries 7 groups (<= 73 registers),
+  // MPN_SA1_WG=4 selects the 4-group kernel with producer warps and the sorted cloud in shared memory.
+  static const int sa1_wg = getenv("MPN_SA1_WG") ? atoi(getenv("MPN_SA1_WG")) : 6;
+  if (MODULE == 0 && sa1_wg != 4) {
+    MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
+    MPN_REQUIRE(N < 65536, "tensor-core SA1: at most 65535 points");
+    if (sa1_wg == 7) {
+      size_t smem7 = Sa1wSmem<7>::total(N);
+      MPN_REQUIRE(smem7 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
+      MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1w_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));
+      sa1w_tc_kernel<7><<<B, 128 * 7, smem7, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
+                                                  tc_error_flag(c), ball_idx);
+    } else {
+      size_t smem6 = Sa1wSmem<6>::total(N);
+      MPN_REQUIRE(smem6 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
+      MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1w_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+      sa1w_tc_kernel<6><<<B, 128 * 6, smem6, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
+                                                  tc_error_flag(c), ball_idx);
+    }
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    return MPN_OK;
+  }
   if (MODULE == 0) {
     size_t smem1 = Sa1Smem::total(N);
     MPN_REQUIRE(smem1 <= 227 * 1024, "tensor-core SA1: %d points do not fit shared memory", N);
@@ -987,7 +1258,7 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     return MPN_OK;
   }
   MPN_REQUIRE(N == SA1_NPOINT, "tensor-core SA2 expects the 512 SA1 centroids as input points");
-  static const bool three = getenv("MPN_SA2_3WG") != nullptr;
+  static const bool three = getenv("MPN_SA2_2WG") == nullptr;   // default: 3 warpgroups; MPN_SA2_2WG=1 selects the 2-group kernel
   if (three) {
     size_t smem3 = Sa2wSmem::total;
     MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2w3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));

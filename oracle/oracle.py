@@ -287,8 +287,8 @@ def sa_module(xyz, feats, spec, weights, emulate_bf16=False, dtype=torch.float32
         new_xyz = None
         x = torch.cat([torch.from_numpy(xyz), feats.to(torch.float32)], dim=-1)[:, None]                      # [B,1,N,3+C]
     x = x.to(dtype)
-    if round_bias is None:   # biases that the bf16 mode folds into the contraction (see _dense): SA1 all, SA2 layers 1-2
-        round_bias = {512: (True, True, True), 128: (True, True, False)}.get(spec["npoint"], (False,) * 3) if emulate_bf16 else (False,) * 3
+    if round_bias is None:   # biases that the bf16 mode folds into the contraction (see _dense): SA1 all layers, SA2 layer 1
+        round_bias = {512: (True, True, True), 128: (True, False, False)}.get(spec["npoint"], (False,) * 3) if emulate_bf16 else (False,) * 3
     for (w, b), rb in zip(weights, round_bias):
         x = torch.relu(_dense(x, w.reshape(w.shape[0], -1), b, emulate_bf16, dtype, rb))
     out = x.max(dim=2).values                                                                               # [B,m,Cout]
