@@ -1223,13 +1223,13 @@ template <int MODULE>
 static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
                         int B, __nv_bfloat16* out, int out_stride, int32_t* ball_idx = nullptr) {
   TcWeights& tw = g_tc[c];
-  // SA1 variants: default = 6 row warpgroups with the grid index on chip; MPN_SA1_WG=7 tries 7 groups (<= 73 registers),
+  // SA1 variants: default = 7 row warpgroups (72 registers) with the grid index on chip; MPN_SA1_WG=6 uses 6 groups,
   // MPN_SA1_WG=4 selects the 4-group kernel with producer warps and the sorted cloud in shared memory.
-  static const int sa1_wg = getenv("MPN_SA1_WG") ? atoi(getenv("MPN_SA1_WG")) : 6;
+  static const int sa1_wg = getenv("MPN_SA1_WG") ? atoi(getenv("MPN_SA1_WG")) : 7;
   if (MODULE == 0 && sa1_wg != 4) {
     MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
     MPN_REQUIRE(N < 65536, "tensor-core SA1: at most 65535 points");
-    if (sa1_wg == 7) {
+    if (sa1_wg != 6) {
       size_t smem7 = Sa1wSmem<7>::total(N);
       MPN_REQUIRE(smem7 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
       MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1w_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));
