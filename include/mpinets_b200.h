@@ -147,6 +147,25 @@ int mpn_rollout(mpn_ctx* ctx, void* stream, int precision, const mpn_scene* scen
                 const float* q0, const float* target, int T, int early_exit, int check_every_step, float* traj,
                 float* metrics);
 
+/* Evaluator.evaluate_trajectory, the device-computable subset (metrics.py:311-322 joint limits, :340-384 final position /
+ * orientation / region, :411-434 end-effector path lengths, :487-523 the success conjunction), for B trajectories at once.
+ *   traj [B][n_poses_max][7] unnormalised (mpn_rollout's layout with n_poses_max = T+1); num_poses i32 [B] (optional:
+ *   valid poses per trajectory, e.g. steps+1 after an early exit; NULL = all); target [B][12] right_gripper pose.
+ *   target_volume / negative_volumes: per-problem primitive lists in mpn_scene layout with their own row counts
+ *   ([B][tv_cuboids][..] etc.; zero-volume rows = padding; either may be NULL with counts 0 -> region test passes).
+ *   They are geometrout primitives in the reference, so their frames use textbook rotations regardless of quirk_frames.
+ * Differences from the reference, by construction: "collision" is the validation sphere sweep (model.py:293-314) instead of
+ * Bullet; "self_collision" is a sphere-sphere test between collision spheres whose link groups (link1..6, {link7, hand,
+ * fingers}) are >= 2 apart, standing in for robofin's FrankaSelfCollisionChecker; SPARC smoothness is not computed. */
+#define MPN_EVAL_COLS 16
+enum { MPN_E_COLLISION = 0, MPN_E_JOINT_LIMIT_VIOLATION = 1, MPN_E_SELF_COLLISION = 2, MPN_E_PHYSICAL_VIOLATIONS = 3,
+       MPN_E_POSITION_ERROR_CM = 4, MPN_E_ORIENTATION_ERROR_DEG = 5, MPN_E_EFF_POSITION_PATH_LENGTH = 6,
+       MPN_E_EFF_ORIENTATION_PATH_LENGTH_DEG = 7, MPN_E_CORRECT_FINAL_REGION = 8, MPN_E_SUCCESS = 9, MPN_E_NUM_STEPS = 10,
+       MPN_E_FIRST_COLLISION_STEP = 11, MPN_E_CONFIG_PATH_LENGTH = 12, MPN_E_MAX_COLLISION_DEPTH = 13 };
+int mpn_evaluate(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* traj, int n_poses_max,
+                 const int32_t* num_poses, const float* target, const mpn_scene* target_volume, int tv_cuboids,
+                 int tv_cylinders, const mpn_scene* negative_volumes, int nv_cuboids, int nv_cylinders, float* eval);
+
 /* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
 int64_t mpn_launch_count(mpn_ctx* ctx);
 

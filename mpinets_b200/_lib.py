@@ -13,12 +13,17 @@ LIB_PATH = os.path.join(_HERE, "libmpinets_b200.so")
 METRICS_COLS = 8
 STAGES = ("fps1", "sa1", "fps2", "sa2", "sa3", "fc", "heads", "update", "sample_robot", "sweep", "build_cloud", "other")
 PREC_FP32, PREC_BF16 = 0, 1
+EVAL_COLS = 16
+# columns of mpn_evaluate's table; names follow Evaluator.evaluate_trajectory's add_metric keys (metrics.py:470-523)
+EVAL_COLUMNS = ("collision", "joint_limit_violation", "self_collision", "physical_violations", "position_error",
+                "orientation_error", "eff_position_path_length", "eff_orientation_path_length", "correct_final_region",
+                "success", "num_steps", "first_collision_step", "config_path_length", "max_collision_depth")
 
 EXPORTS = (
     "mpn_last_error", "mpn_version", "mpn_ctx_create", "mpn_ctx_destroy", "mpn_reserve", "mpn_set_robot_tables",
     "mpn_load_weight", "mpn_weights_finalize", "mpn_fps", "mpn_ball_query", "mpn_gather_points", "mpn_group_points",
     "mpn_sa_forward", "mpn_fk", "mpn_sample_robot", "mpn_compute_spheres", "mpn_normalize_joints",
-    "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_sweep_flags", "mpn_encoder_forward",
+    "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_sweep_flags", "mpn_evaluate", "mpn_encoder_forward",
     "mpn_policy_forward", "mpn_rollout", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error", "mpn_tc_timeline",
 )
 
@@ -74,6 +79,7 @@ def load():
         "mpn_sdf_points": [P, P, SC, I, P, I, I, P],
         "mpn_build_cloud": [P, P, SC, I, P, P, U32, P],
         "mpn_sweep_flags": [P, P, SC, I, P, I, I, I, P, P],
+        "mpn_evaluate": [P, P, SC, I, P, I, P, P, SC, I, I, SC, I, I, P],
         "mpn_encoder_forward": [P, P, I, P, I, I, P],
         "mpn_policy_forward": [P, P, I, P, P, I, I, P],
         "mpn_rollout": [P, P, I, SC, I, I, P, P, P, I, I, I, P, P],

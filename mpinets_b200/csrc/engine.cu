@@ -478,6 +478,38 @@ int mpn_sweep_flags(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, con
   return launch_sweep(c, (cudaStream_t)stream, *scene, B, traj, T, T * 7, t0, accumulate, flags, first_step);
 }
 
+int mpn_evaluate(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* traj, int n_poses_max,
+                 const int32_t* num_poses, const float* target, const mpn_scene* target_volume, int tv_cuboids, int tv_cylinders,
+                 const mpn_scene* negative_volumes, int nv_cuboids, int nv_cylinders, float* eval) {
+  REQ_CTX(c); REQ_TABLES(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(traj && target && eval, "mpn_evaluate: null pointer");
+  MPN_REQUIRE(n_poses_max >= 1 && n_poses_max <= 2048, "mpn_evaluate: 1 <= n_poses_max <= 2048");
+  MPN_REQUIRE(tv_cuboids >= 0 && tv_cylinders >= 0 && nv_cuboids >= 0 && nv_cylinders >= 0, "mpn_evaluate: negative volume count");
+  MPN_REQUIRE(tv_cuboids + tv_cylinders == 0 || target_volume, "mpn_evaluate: target_volume is null");
+  MPN_REQUIRE(nv_cuboids + nv_cylinders == 0 || negative_volumes, "mpn_evaluate: negative_volumes is null");
+  if (target_volume) {
+    MPN_REQUIRE(tv_cuboids == 0 || (target_volume->cuboid_centers && target_volume->cuboid_dims && target_volume->cuboid_quats),
+                "mpn_evaluate: target_volume cuboid arrays missing");
+    MPN_REQUIRE(tv_cylinders == 0 || (target_volume->cylinder_centers && target_volume->cylinder_radii &&
+                                      target_volume->cylinder_heights && target_volume->cylinder_quats),
+                "mpn_evaluate: target_volume cylinder arrays missing");
+  }
+  if (negative_volumes) {
+    MPN_REQUIRE(nv_cuboids == 0 || (negative_volumes->cuboid_centers && negative_volumes->cuboid_dims && negative_volumes->cuboid_quats),
+                "mpn_evaluate: negative_volumes cuboid arrays missing");
+    MPN_REQUIRE(nv_cylinders == 0 || (negative_volumes->cylinder_centers && negative_volumes->cylinder_radii &&
+                                      negative_volumes->cylinder_heights && negative_volumes->cylinder_quats),
+                "mpn_evaluate: negative_volumes cylinder arrays missing");
+  }
+  if (B == 0) return MPN_OK;
+  mpn_scene none{};
+  return launch_evaluate(c, (cudaStream_t)stream, *scene, B, traj, n_poses_max, num_poses, target,
+                         target_volume ? *target_volume : none, tv_cuboids, tv_cylinders,
+                         negative_volumes ? *negative_volumes : none, nv_cuboids, nv_cylinders, eval);
+}
+
 // ---- model
 int mpn_encoder_forward(mpn_ctx* c, void* stream, int precision, const float* cloud, int B, int N, float* out) {
   REQ_CTX(c); REQ_WEIGHTS(c);

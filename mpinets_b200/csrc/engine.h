@@ -127,6 +127,8 @@ int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, c
                        uint32_t problem0, float* cloud);
 int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T, int traj_stride_t,
                  int t0, int accumulate, uint8_t* flags, int32_t* first_step, const float* frames_in = nullptr);
+int launch_evaluate(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T1, const int32_t* num_poses,
+                    const float* target, const mpn_scene& tv, int V1, int V2, const mpn_scene& nv, int N1, int N2, float* out);
 // ---- pointnet.cu
 int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz);
 int launch_ball_query(mpn_ctx* c, cudaStream_t s, float radius, int nsample, const float* xyz, int B, int N, int stride,

@@ -24,6 +24,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ uint32_t cvt_relu_pack(float first, float second) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+  return d;
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ W, int K, const float* __restrict__ bias,
@@ -31,11 +37,13 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
   extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
   __shared__ uint64_t done[G_STAGES];
   __shared__ uint32_t tmem_slot;
-  __shared__ float red[4][G_BN];
+  __shared__ int red[4][G_BN];
+  __shared__ __align__(16) float sbias[G_BN];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * G_BN;
   const int nst = (K + G_BK - 1) / G_BK;
 
+  sbias[tid] = bias[n0 + tid];   // 256 threads == G_BN columns
   if (tid == 0) {
     for (int s = 0; s < G_STAGES; ++s) mbar_init(&done[s], 1);
     mbar_fence_init();
@@ -48,7 +56,10 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
   const uint64_t dA0 = make_smem_desc(smem_u32(smem), 128, 1024, LAYOUT_NONE);                 // stage 0 descriptors; later stages /
   const uint64_t dW0 = make_smem_desc(smem_u32(smem) + G_A_BYTES, 128, 1024, LAYOUT_NONE);     // K-steps only add to the address field
 
-  // stage loader: A rows m0.., W rows n0.., K chunk [st*64, st*64+64) -> interleaved layout with 8 chunks per row
+  // stage loader: A rows m0.., W rows n0.., K chunk [st*64, st*64+64) -> interleaved layout with 8 chunks per row.
+  // Lane mapping: each quarter-warp (the unit the 16-byte shared-memory write is served in) covers 8 consecutive rows of
+  // one chunk column -> 8 distinct 16-byte bank groups (a row-major lane order put all 8 lanes on the same group: an
+  // 8-way conflict on every LDGSTS write); the warp as a whole reads 8 rows x 64 contiguous bytes, full 32-byte sectors.
   auto load_stage = [&](int st) {
     uint8_t* sA = smem + (size_t)(st % G_STAGES) * G_STAGE_BYTES;
     uint8_t* sW = sA + G_A_BYTES;
@@ -56,7 +67,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
     const int kc_n = min(8, (K - k0) / 8);
 #pragma unroll
     for (int i = 0; i < (G_BM * 8) / 256; ++i) {
-      int c = tid + i * 256, r = c >> 3, kc = c & 7;
+      const int c = tid + i * 256, r = ((c >> 6) << 3) | (c & 7), kc = (((c >> 5) & 1) << 2) | ((c >> 3) & 3);
       if (kc < kc_n) {
         int m = m0 + r;
         const __nv_bfloat16* src = A + (size_t)min(m, M - 1) * lda + k0 + kc * 8;
@@ -65,7 +76,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
     }
 #pragma unroll
     for (int i = 0; i < (G_BN * 8) / 256; ++i) {
-      int c = tid + i * 256, r = c >> 3, kc = c & 7;
+      const int c = tid + i * 256, r = ((c >> 6) << 3) | (c & 7), kc = (((c >> 5) & 1) << 2) | ((c >> 3) & 3);
       if (kc < kc_n) cp_async16(smem_u32(sW + kmajor_chunk_off(r, kc, 8)), W + (size_t)(n0 + r) * K + k0 + kc * 8, 16u);
     }
   };
@@ -112,57 +123,68 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
   tc_fence_after();
   if (!ok && tid == 0) atomicExch(err, 1);
 
-  // ---- epilogue: warp (q = warp & 3) owns lanes 32q..32q+31, column half h = warp >> 2
+  // ---- epilogue: warp (q = warp & 3) owns lanes 32q..32q+31, column half h = warp >> 2.  The bias tile sits in shared
+  // memory (staged at kernel start) and is read with 16-byte broadcast loads.
   const int q = warp & 3, h = warp >> 2, row = q * 32 + (tid & 31);
 #pragma unroll 1
   for (int sub = 0; sub < 2; ++sub) {
-  const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + sub * 256 + h * 128;
-  const int m = m0 + sub * 128 + row;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + sub * 256 + h * 128;
+    const int m = m0 + sub * 128 + row;
 #pragma unroll 1
-  for (int c0 = 0; c0 < 128; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(tl + c0, v);
-    tmem_ld_wait();
-    const int nb = n0 + h * 128 + c0;
-    if (EPI == EPI_RELU_BF16) {
-      if (m < M) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)m * ldc + nb;
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tl + c0, v);
+      tmem_ld_wait();
+      const int nl = h * 128 + c0;          // column inside the CTA tile
+      const float4* bt = reinterpret_cast<const float4*>(sbias + nl);
+      if (EPI == EPI_RELU_BF16) {
+        if (m < M) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)m * ldc + n0 + nl;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint32_t p[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            p[e] = pack_bf16(fmaxf(__uint_as_float(v[j + 2 * e]) + __ldg(bias + nb + j + 2 * e), 0.f),
-                             fmaxf(__uint_as_float(v[j + 2 * e + 1]) + __ldg(bias + nb + j + 2 * e + 1), 0.f));
-          *reinterpret_cast<uint4*>(o + j) = make_uint4(p[0], p[1], p[2], p[3]);
+          for (int j = 0; j < 32; j += 8) {
+            const float4 b0 = bt[j / 4], b1 = bt[j / 4 + 1];
+            *reinterpret_cast<uint4*>(o + j) =
+                make_uint4(cvt_relu_pack(__uint_as_float(v[j]) + b0.x, __uint_as_float(v[j + 1]) + b0.y),
+                           cvt_relu_pack(__uint_as_float(v[j + 2]) + b0.z, __uint_as_float(v[j + 3]) + b0.w),
+                           cvt_relu_pack(__uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y),
+                           cvt_relu_pack(__uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w));
+          }
         }
-      }
-    } else if (EPI == EPI_F32) {
-      if (m < M) {
-        float* o = reinterpret_cast<float*>(Cout) + (size_t)m * ldc + nb;
+      } else if (EPI == EPI_F32) {
+        if (m < M) {
+          float* o = reinterpret_cast<float*>(Cout) + (size_t)m * ldc + n0 + nl;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]) + __ldg(bias + nb + j), __uint_as_float(v[j + 1]) + __ldg(bias + nb + j + 1),
-                                                          __uint_as_float(v[j + 2]) + __ldg(bias + nb + j + 2), __uint_as_float(v[j + 3]) + __ldg(bias + nb + j + 3));
-      }
-    } else {
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = bt[j / 4];
+            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y,
+                                                            __uint_as_float(v[j + 2]) + bb.z, __uint_as_float(v[j + 3]) + bb.w);
+          }
+        }
+      } else {
+        // max over the tile's 128 rows: relu(max_r acc + bias) == max_r relu(acc + bias); the raw accumulators are
+        // reduced as order-preserving integers (sign-magnitude floats -> two's complement order)
+        int keep = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float a = m < M ? fmaxf(__uint_as_float(v[j]) + __ldg(bias + nb + j), 0.f) : 0.f;
-        uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(a));
-        if ((tid & 31) == j) red[q][h * 128 + c0 + j] = __uint_as_float(mx);
+        for (int j = 0; j < 32; ++j) {
+          int bits = (int)v[j];
+          bits = m < M ? (bits >= 0 ? bits : (int)(0x80000000u - (uint32_t)bits)) : (int)0x80000000;
+          const int mx = __reduce_max_sync(0xffffffffu, bits);
+          keep = (tid & 31) == j ? mx : keep;
+        }
+        red[q][nl + (tid & 31)] = keep;
       }
     }
-  }
-  if (EPI == EPI_MAXPOOL) {
-    __syncthreads();
-    const int prob = blockIdx.y * 2 + sub;   // one pooled row per 128-row sub-tile (= one problem)
-    if (prob * 128 < M) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)prob * ldc + n0;
-      o[tid] = __float2bfloat16_rn(fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid])));
+    if (EPI == EPI_MAXPOOL) {
+      __syncthreads();
+      const int prob = blockIdx.y * 2 + sub;   // one pooled row per 128-row sub-tile (= one problem)
+      if (prob * 128 < M) {
+        const int mi = max(max(red[0][tid], red[1][tid]), max(red[2][tid], red[3][tid]));
+        const int bits = mi >= 0 ? mi : (int)(0x80000000u - (uint32_t)mi);
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)prob * ldc + n0;
+        o[tid] = __float2bfloat16_rn(fmaxf(__int_as_float(bits) + sbias[tid], 0.f));
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
   }
   tc_fence_before();
   __syncthreads();

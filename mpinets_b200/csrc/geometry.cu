@@ -138,24 +138,26 @@ int launch_normalize(mpn_ctx* c, cudaStream_t s, const float* in, int n, float* 
 // per-problem primitive list -> inverse frames in shared memory (<= M1+M2 <= 128 entries of 64 B)
 constexpr int MAX_PRIMS = 128;
 
-__device__ __forceinline__ void stage_scene(const mpn_scene& sc, int b, int M1, int M2, bool quirk, PrimFrame* fr) {
-  for (int m = threadIdx.x; m < M1 + M2; m += blockDim.x) {
-    PrimFrame f;
-    if (m < M1) {
-      const float* d = sc.cuboid_dims + ((size_t)b * M1 + m) * 3;
-      float d0 = d[0], d1 = d[1], d2 = d[2];
-      f.valid = (is_close0(d0) || is_close0(d1) || is_close0(d2)) ? 0.f : 1.f;
-      make_inv_frame(sc.cuboid_centers + ((size_t)b * M1 + m) * 3, sc.cuboid_quats + ((size_t)b * M1 + m) * 4, quirk, f);
-      f.h[0] = fdiv(d0, 2.0f); f.h[1] = fdiv(d1, 2.0f); f.h[2] = fdiv(d2, 2.0f);
-    } else {
-      int k = m - M1;
-      float r = sc.cylinder_radii[(size_t)b * M2 + k], h = sc.cylinder_heights[(size_t)b * M2 + k];
-      f.valid = (is_close0(r) || is_close0(h)) ? 0.f : 1.f;
-      make_inv_frame(sc.cylinder_centers + ((size_t)b * M2 + k) * 3, sc.cylinder_quats + ((size_t)b * M2 + k) * 4, quirk, f);
-      f.h[0] = r; f.h[1] = fdiv(h, 2.0f); f.h[2] = 0.f;
-    }
-    fr[m] = f;
+__device__ __forceinline__ PrimFrame prim_frame_of(const mpn_scene& sc, int b, int M1, int M2, int m, bool quirk) {
+  PrimFrame f;
+  if (m < M1) {
+    const float* d = sc.cuboid_dims + ((size_t)b * M1 + m) * 3;
+    float d0 = d[0], d1 = d[1], d2 = d[2];
+    f.valid = (is_close0(d0) || is_close0(d1) || is_close0(d2)) ? 0.f : 1.f;
+    make_inv_frame(sc.cuboid_centers + ((size_t)b * M1 + m) * 3, sc.cuboid_quats + ((size_t)b * M1 + m) * 4, quirk, f);
+    f.h[0] = fdiv(d0, 2.0f); f.h[1] = fdiv(d1, 2.0f); f.h[2] = fdiv(d2, 2.0f);
+  } else {
+    int k = m - M1;
+    float r = sc.cylinder_radii[(size_t)b * M2 + k], h = sc.cylinder_heights[(size_t)b * M2 + k];
+    f.valid = (is_close0(r) || is_close0(h)) ? 0.f : 1.f;
+    make_inv_frame(sc.cylinder_centers + ((size_t)b * M2 + k) * 3, sc.cylinder_quats + ((size_t)b * M2 + k) * 4, quirk, f);
+    f.h[0] = r; f.h[1] = fdiv(h, 2.0f); f.h[2] = 0.f;
   }
+  return f;
+}
+
+__device__ __forceinline__ void stage_scene(const mpn_scene& sc, int b, int M1, int M2, bool quirk, PrimFrame* fr) {
+  for (int m = threadIdx.x; m < M1 + M2; m += blockDim.x) fr[m] = prim_frame_of(sc, b, M1, M2, m, quirk);
 }
 
 __device__ __forceinline__ float scene_sdf(const PrimFrame* fr, int c0, int c1, int y0, int y1, float px, float py, float pz) {
@@ -372,6 +374,180 @@ int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const f
   sweep_kernel<<<B, SWEEP_THREADS, 0, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, c->cfg.quirk_frames, traj, T,
                                            problem_stride, t0, c->prismatic, c->S, c->sph_c, c->sph_r, c->sph_l,
                                            accumulate, flags, first_step, frames_in);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ trajectory evaluation
+// Evaluator.evaluate_trajectory's device-computable subset (metrics.py:311-322,340-384,411-434,487-523).  One CTA per
+// problem; poses in chunks of EVAL_TCHUNK: one thread per pose does FK + the joint-limit test, all threads then sweep
+// (pose, sphere) pairs against the scene and (pose, sphere, sphere) pairs against each other.  Step lengths are written
+// to shared memory and summed by thread 0 in pose order, which is the order the oracle adds them in.
+constexpr int EVAL_TCHUNK = 16;
+constexpr int EVAL_THREADS = 128;
+
+// rotation angle (degrees) of A * B^T: atan2(|antisymmetric part| / 2, (trace - 1) / 2)
+__device__ __forceinline__ float rel_angle_deg(const float* A, const float* Bp) {
+  float R[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = ffma(A[4 * i + 2], Bp[4 * j + 2], ffma(A[4 * i + 1], Bp[4 * j + 1], fmul(A[4 * i], Bp[4 * j])));
+  float ax = fsub(R[7], R[5]), ay = fsub(R[2], R[6]), az = fsub(R[3], R[1]);
+  float s = fmul(0.5f, fsqrt(ffma(az, az, ffma(ay, ay, fmul(ax, ax)))));
+  float c = fmul(0.5f, fsub(fadd(fadd(R[0], R[4]), R[8]), 1.0f));
+  return fmul(atan2f(s, c), 57.29577951308232f);
+}
+
+__device__ __forceinline__ int link_group(int link) { return link < 7 ? link : 7; }
+
+__global__ void __launch_bounds__(EVAL_THREADS)
+evaluate_kernel(mpn_scene sc, int M1, int M2, int quirk, const float* __restrict__ traj, int T1,
+                const int32_t* __restrict__ num_poses, const float* __restrict__ target, const float* __restrict__ lim,
+                float prismatic, int S, const float* __restrict__ sph_c, const float* __restrict__ sph_r,
+                const int32_t* __restrict__ sph_l, mpn_scene tv, int V1, int V2, mpn_scene nv, int N1, int N2,
+                float* __restrict__ out) {
+  extern __shared__ float dyn[];                 // eef poses [T1][12] | step lengths pos/ori/config [3][T1]
+  __shared__ PrimFrame fr[MAX_PRIMS];
+  __shared__ float F[EVAL_TCHUNK][MPN_NLINK * 12];
+  __shared__ float W[EVAL_TCHUNK][MAX_SPHERES * 3];
+  __shared__ float sc_s[MAX_SPHERES * 3];
+  __shared__ float sr_s[MAX_SPHERES];
+  __shared__ int sl_s[MAX_SPHERES];
+  __shared__ int first, jl, selfc, depth_bits;
+  float* E = dyn;
+  float* Lp = dyn + (size_t)T1 * 12;
+  float* Lo = Lp + T1;
+  float* Lc = Lo + T1;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  stage_scene(sc, b, M1, M2, quirk != 0, fr);
+  for (int k = tid; k < S; k += blockDim.x) {
+    sc_s[3 * k] = sph_c[3 * k]; sc_s[3 * k + 1] = sph_c[3 * k + 1]; sc_s[3 * k + 2] = sph_c[3 * k + 2];
+    sr_s[k] = sph_r[k]; sl_s[k] = sph_l[k];
+  }
+  if (tid == 0) { first = 0x7fffffff; jl = 0; selfc = 0; depth_bits = 0; }
+  int n = num_poses ? num_poses[b] : T1;
+  n = max(1, min(n, T1));
+  __syncthreads();
+  const float* tb = traj + (size_t)b * T1 * 7;
+  for (int tc = 0; tc < n; tc += EVAL_TCHUNK) {
+    const int nt = min(EVAL_TCHUNK, n - tc);
+    if (tid < nt) {
+      float qq[7];
+      const float* qp = tb + (size_t)(tc + tid) * 7;
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        qq[j] = qp[j];
+        bad |= qq[j] < lim[2 * j] || qq[j] > lim[2 * j + 1];
+      }
+      if (bad) jl = 1;
+      float Fl[MPN_NLINK * 12], El[12];
+      spec_fk(qq, prismatic, Fl, El);
+#pragma unroll
+      for (int i = 0; i < MPN_NLINK * 12; ++i) F[tid][i] = Fl[i];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) E[(size_t)(tc + tid) * 12 + i] = El[i];
+    }
+    __syncthreads();
+    float pen_max = 0.f;
+    for (int p = tid; p < nt * S; p += blockDim.x) {
+      int t = p / S, k = p - t * S;
+      float x, y, z;
+      m34_apply(F[t] + 12 * sl_s[k], sc_s[3 * k], sc_s[3 * k + 1], sc_s[3 * k + 2], x, y, z);
+      W[t][3 * k] = x; W[t][3 * k + 1] = y; W[t][3 * k + 2] = z;
+      float d = scene_sdf(fr, 0, M1, M1, M1 + M2, x, y, z);
+      if (d <= sr_s[k]) atomicMin(&first, tc + t);
+      pen_max = fmaxf(pen_max, fsub(sr_s[k], d));
+    }
+    if (pen_max > 0.f) atomicMax(&depth_bits, __float_as_int(pen_max));   // non-negative floats order like ints
+    __syncthreads();
+    const int pairs = S * S;
+    for (int p = tid; p < nt * pairs; p += blockDim.x) {
+      int t = p / pairs, r = p - t * pairs;
+      int i = r / S, j = r - i * S;
+      if (j <= i) continue;
+      int g = link_group(sl_s[i]) - link_group(sl_s[j]);
+      if (g < 0) g = -g;
+      if (g < 2) continue;
+      float dx = fsub(W[t][3 * i], W[t][3 * j]), dy = fsub(W[t][3 * i + 1], W[t][3 * j + 1]), dz = fsub(W[t][3 * i + 2], W[t][3 * j + 2]);
+      float dist = fsqrt(ffma(dz, dz, ffma(dy, dy, fmul(dx, dx))));
+      if (dist < fadd(sr_s[i], sr_s[j])) selfc = 1;
+    }
+    __syncthreads();
+  }
+  for (int t = 1 + tid; t < n; t += blockDim.x) {
+    const float* a = E + (size_t)t * 12;
+    const float* p = a - 12;
+    float dx = fsub(a[3], p[3]), dy = fsub(a[7], p[7]), dz = fsub(a[11], p[11]);
+    Lp[t] = fsqrt(ffma(dz, dz, ffma(dy, dy, fmul(dx, dx))));
+    Lo[t] = rel_angle_deg(a, p);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { float dq = fsub(tb[(size_t)t * 7 + j], tb[(size_t)(t - 1) * 7 + j]); acc = ffma(dq, dq, acc); }
+    Lc[t] = fsqrt(acc);
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  float pos_path = 0.f, ori_path = 0.f, cfg_path = 0.f;
+  for (int t = 1; t < n; ++t) { pos_path = fadd(pos_path, Lp[t]); ori_path = fadd(ori_path, Lo[t]); cfg_path = fadd(cfg_path, Lc[t]); }
+  const float* last = E + (size_t)(n - 1) * 12;
+  const float* Tg = target + (size_t)b * 12;
+  float dx = fsub(last[3], Tg[3]), dy = fsub(last[7], Tg[7]), dz = fsub(last[11], Tg[11]);
+  float pos_cm = fmul(100.0f, fsqrt(ffma(dz, dz, ffma(dy, dy, fmul(dx, dx)))));
+  float ori = rel_angle_deg(last, Tg);
+  // metrics.py:497-504: negative volumes containing the target are dropped; final xyz inside the target volume and
+  // outside every remaining negative volume.  geometrout primitives -> textbook rotations.
+  bool region = true;
+  if (V1 + V2 > 0) {
+    float best = __int_as_float(0x7f800000);
+    for (int m = 0; m < V1 + V2; ++m) {
+      PrimFrame f = prim_frame_of(tv, b, V1, V2, m, false);
+      if (f.valid == 0.f) continue;
+      best = fminf(best, m < V1 ? sdf_cuboid(f, last[3], last[7], last[11]) : sdf_cylinder(f, last[3], last[7], last[11]));
+    }
+    if (!(best <= 0.f)) region = false;
+  }
+  for (int m = 0; m < N1 + N2; ++m) {
+    PrimFrame f = prim_frame_of(nv, b, N1, N2, m, false);
+    if (f.valid == 0.f) continue;
+    float at_target = m < N1 ? sdf_cuboid(f, Tg[3], Tg[7], Tg[11]) : sdf_cylinder(f, Tg[3], Tg[7], Tg[11]);
+    float at_final = m < N1 ? sdf_cuboid(f, last[3], last[7], last[11]) : sdf_cylinder(f, last[3], last[7], last[11]);
+    if (at_target > 0.f && !(at_final > 0.f)) region = false;
+  }
+  const bool hit = first != 0x7fffffff;
+  const bool physical = hit || jl || selfc;
+  float* o = out + (size_t)b * MPN_EVAL_COLS;
+#pragma unroll
+  for (int i = 0; i < MPN_EVAL_COLS; ++i) o[i] = 0.f;
+  o[MPN_E_COLLISION] = hit ? 1.f : 0.f;
+  o[MPN_E_JOINT_LIMIT_VIOLATION] = jl ? 1.f : 0.f;
+  o[MPN_E_SELF_COLLISION] = selfc ? 1.f : 0.f;
+  o[MPN_E_PHYSICAL_VIOLATIONS] = physical ? 1.f : 0.f;
+  o[MPN_E_POSITION_ERROR_CM] = pos_cm;
+  o[MPN_E_ORIENTATION_ERROR_DEG] = ori;
+  o[MPN_E_EFF_POSITION_PATH_LENGTH] = pos_path;
+  o[MPN_E_EFF_ORIENTATION_PATH_LENGTH_DEG] = ori_path;
+  o[MPN_E_CORRECT_FINAL_REGION] = region ? 1.f : 0.f;
+  o[MPN_E_SUCCESS] = (pos_cm < 1.0f && region && ori < 15.0f && !physical) ? 1.f : 0.f;
+  o[MPN_E_NUM_STEPS] = (float)n;
+  o[MPN_E_FIRST_COLLISION_STEP] = hit ? (float)first : -1.f;
+  o[MPN_E_CONFIG_PATH_LENGTH] = cfg_path;
+  o[MPN_E_MAX_COLLISION_DEPTH] = __int_as_float(depth_bits);
+}
+
+int launch_evaluate(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T1, const int32_t* num_poses,
+                    const float* target, const mpn_scene& tv, int V1, int V2, const mpn_scene& nv, int N1, int N2, float* out) {
+  size_t dyn = (size_t)T1 * 15 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 15 * (int)sizeof(float)));
+    attr_set = true;
+  }
+  evaluate_kernel<<<B, EVAL_THREADS, dyn, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, c->cfg.quirk_frames, traj, T1,
+                                               num_poses, target, c->limits, c->prismatic, c->S, c->sph_c, c->sph_r, c->sph_l,
+                                               tv, V1, V2, nv, N1, N2, out);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

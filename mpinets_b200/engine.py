@@ -258,6 +258,45 @@ class Engine:
         _lib.check(self.lib.mpn_sweep_flags(self._ctx, self.stream, C.byref(s), B, _p(traj), T, 0, 0, _p(flags), _p(first)))
         return flags, first
 
+    def _volumes(self, vol: Optional[Dict[str, torch.Tensor]], B: int):
+        """optional primitive lists of the region test -> (MpnScene or None, n_cuboids, n_cylinders, keep-alive)"""
+        if vol is None:
+            return None, 0, 0, []
+        s = _lib.MpnScene()
+        keep, n1, n2 = [], 0, 0
+        for k in SCENE_KEYS:
+            if k not in vol or vol[k] is None:
+                continue
+            t = _check(vol[k], k, device=self.device)
+            if t.shape[0] != B:
+                raise RuntimeError(f"{k} has batch {t.shape[0]}, expected {B}")
+            keep.append(t)
+            setattr(s, k, t.data_ptr())
+        if "cuboid_centers" in vol and vol["cuboid_centers"] is not None:
+            n1 = vol["cuboid_centers"].shape[1]
+        if "cylinder_centers" in vol and vol["cylinder_centers"] is not None:
+            n2 = vol["cylinder_centers"].shape[1]
+        return s, n1, n2, keep
+
+    def evaluate(self, scene, traj: torch.Tensor, target: torch.Tensor, num_poses: Optional[torch.Tensor] = None,
+                 target_volume: Optional[Dict[str, torch.Tensor]] = None,
+                 negative_volumes: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        """Evaluator.evaluate_trajectory for B trajectories (metrics.py:447-523): traj [B,T+1,7] -> eval [B,16]
+        (columns: mpinets_b200._lib.EVAL_COLUMNS)."""
+        _check(traj, "traj", device=self.device); _check(target, "target", device=self.device)
+        B, T1, _ = traj.shape
+        s, keep = self._scene(scene, B)
+        if num_poses is not None:
+            _check(num_poses, "num_poses", torch.int32, self.device)
+        tv, v1, v2, k1 = self._volumes(target_volume, B)
+        nv, n1, n2, k2 = self._volumes(negative_volumes, B)
+        out = self._empty(B, _lib.EVAL_COLS)
+        _lib.check(self.lib.mpn_evaluate(self._ctx, self.stream, C.byref(s), B, _p(traj), T1,
+                                         _p(num_poses) if num_poses is not None else None, _p(target),
+                                         C.byref(tv) if tv is not None else None, v1, v2,
+                                         C.byref(nv) if nv is not None else None, n1, n2, _p(out)))
+        return out
+
     # ------------------------------------------------------------------ model
     def encoder_forward(self, cloud: torch.Tensor, precision: int = _lib.PREC_FP32):
         _check(cloud, "point_cloud", device=self.device)

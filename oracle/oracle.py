@@ -122,6 +122,49 @@ def sweep_flags(scene, traj, tables, quirk=True):
     return flags, first, mm
 
 
+EVAL_COLS = 16
+
+
+def _volume_args(vol, B):
+    """optional region-test primitive lists -> (keep, n_cuboids, n_cylinders, 7 pointers)"""
+    nullp = C.POINTER(C.c_float)()
+    if vol is None:
+        return [], 0, 0, (nullp,) * 7
+    keep, n1, n2 = [], 0, 0
+    ptrs = [nullp] * 7
+    if vol.get("cuboid_centers") is not None:
+        cc, p0 = _f(vol["cuboid_centers"]); cd, p1 = _f(vol["cuboid_dims"]); cq, p2 = _f(vol["cuboid_quats"])
+        keep += [cc, cd, cq]; ptrs[0:3] = [p0, p1, p2]; n1 = cc.shape[1]
+        assert cc.shape[0] == B
+    if vol.get("cylinder_centers") is not None:
+        yc, p3 = _f(vol["cylinder_centers"])
+        yr, p4 = _f(np.asarray(vol["cylinder_radii"]).reshape(B, -1)); yh, p5 = _f(np.asarray(vol["cylinder_heights"]).reshape(B, -1))
+        yq, p6 = _f(vol["cylinder_quats"])
+        keep += [yc, yr, yh, yq]; ptrs[3:7] = [p3, p4, p5, p6]; n2 = yc.shape[1]
+    return keep, n1, n2, tuple(ptrs)
+
+
+def evaluate(scene, traj, target, tables, num_poses=None, target_volume=None, negative_volumes=None, quirk=True):
+    """Evaluator.evaluate_trajectory subset (metrics.py:311-322,340-384,411-434,487-523): traj [B,T1,7] -> [B,16]"""
+    keep, B, M1, M2, ps = _scene_args(scene)
+    traj, pt = _f(traj); target, ptg = _f(np.asarray(target).reshape(B, 12))
+    T1 = traj.shape[1]
+    lim, pl = _f(tables.joint_limits)
+    sc, psc = _f(tables.sphere_centers); sr, psr = _f(tables.sphere_radii); sl, psl = _i(tables.sphere_links)
+    if num_poses is not None:
+        npz, pn = _i(num_poses)
+    else:
+        pn = C.POINTER(C.c_int32)()
+    k1, v1, v2, pv = _volume_args(target_volume, B)
+    k2, n1, n2, pnv = _volume_args(negative_volumes, B)
+    out = np.zeros((B, EVAL_COLS), np.float32)
+    lib().mpn_oracle_evaluate(C.c_int(B), C.c_int(T1), C.c_int(M1), C.c_int(M2), *ps, C.c_int(int(quirk)), pt, pn, ptg, pl,
+                              C.c_float(tables.prismatic), C.c_int(sc.shape[0]), psc, psr, psl,
+                              C.c_int(v1), C.c_int(v2), *pv, C.c_int(n1), C.c_int(n2), *pnv,
+                              out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
 def spheres(q, tables):
     q, pq = _f(q)
     sc, psc = _f(tables.sphere_centers); sl, psl = _i(tables.sphere_links)

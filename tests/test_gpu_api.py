@@ -108,3 +108,26 @@ def test_model_surface(oracle, tables, state_dict):
     mdl.precision = "bf16"
     dq16 = mdl(before, qn)
     assert (dq16.cpu() - exp).abs().max().item() < 2e-2
+
+
+def test_evaluator_surface(tables, oracle):
+    """metrics.py:Evaluator usage in run_inference.py:452-516: create_new_group -> evaluate_trajectory(...) per problem
+    -> print_group_metrics; here one call evaluates the whole batch."""
+    from mpinets_b200.metrics import Evaluator
+    p = _problems(12)
+    T1 = 11
+    w = np.linspace(0.0, 1.0, T1, dtype=np.float32)[None, :, None]
+    traj = torch.from_numpy((p["q0"][:, None] * (1 - w) + p["q_goal"][:, None] * w).astype(np.float32)).cuda().contiguous()
+    ev = Evaluator()
+    ev.create_new_group("tabletop")
+    table = ev.evaluate_trajectories(traj, 0.1, torch.from_numpy(p["target"]).cuda(), to_dev(p))
+    assert table.shape == (12, 16)
+    g = ev.groups["tabletop"]
+    assert len(g["success"]) == 12 and all(isinstance(v, bool) for v in g["success"])
+    m = Evaluator.metrics(g)
+    exp = oracle.evaluate(p, traj.cpu().numpy(), p["target"], tables)
+    assert m["total"] == 12 and abs(m["success"] - 100 * exp[:, 9].mean()) < 1e-9
+    assert abs(m["env collision"] - 100 * exp[:, 0].mean()) < 1e-9
+    assert m["1 cm"] == 100.0                                  # joint-space interpolation ends exactly on the target
+    ev.print_group_metrics()
+    ev.print_overall_metrics()

@@ -439,3 +439,74 @@ def test_tensor_core_ball_query_dense_and_fallback(engine_w, oracle):
     assert np.array_equal(bi.cpu().numpy(), exp)
     counts = np.array([[len(set(r.tolist())) for r in exp[b]] for b in range(3)])
     assert counts[0].max() == 128 and counts[1].max() == 128                      # the dense cases were exercised
+
+
+# ----------------------------------------------------------------------------- Evaluator subset (metrics.py:311-523)
+def _eval_case(B=24, T1=21, seed=5):
+    p = _problems(4, B)
+    w = np.linspace(0.0, 1.0, T1, dtype=np.float32)[None, :, None]
+    traj = (p["q0"][:, None, :] * (1 - w) + p["q_goal"][:, None, :] * w).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    traj[1, -1] += 0.2
+    traj[2, 5, 3] = 0.5
+    traj[3, :, :] = np.array([1.638, 1.227, 0.041, -3.039, 0.047, 1.604, 0.314], np.float32) + 0.01 * rng.standard_normal((T1, 7)).astype(np.float32)
+    num = np.full(B, T1, np.int32); num[4] = 7; num[7] = 1
+    unit = np.tile(np.array([1, 0, 0, 0], np.float32), (B, 1, 1))
+    yaw = rng.uniform(-np.pi, np.pi, B)
+    quat = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], -1).astype(np.float32)[:, None]
+    tv = dict(cuboid_centers=p["target"][:, None, :3, 3].copy(), cuboid_dims=np.full((B, 1, 3), 0.1, np.float32), cuboid_quats=quat)
+    tv["cuboid_centers"][5, 0, 0] += 1.0
+    nv = dict(cuboid_centers=np.repeat(p["target"][:, None, :3, 3], 2, axis=1) + np.array([[0.3, 0, 0], [0, 0.02, 0]], np.float32),
+              cuboid_dims=np.full((B, 2, 3), 0.2, np.float32), cuboid_quats=np.repeat(unit, 2, axis=1),
+              cylinder_centers=p["target"][:, None, :3, 3] + np.array([0, 0, 0.12], np.float32),
+              cylinder_radii=np.full((B, 1, 1), 0.05, np.float32), cylinder_heights=np.full((B, 1, 1), 0.1, np.float32),
+              cylinder_quats=unit.copy())
+    nv["cuboid_dims"][6, 0] = 1.0
+    nv["cuboid_dims"][::2, 1] = 0.0       # padding rows
+    nv["cylinder_heights"][8] = 0.3       # now contains the target itself -> dropped (metrics.py:497-499)
+    from mpinets_b200.franka import fk_reference_f64
+    nv["cuboid_centers"][1, 0] = fk_reference_f64(traj[1, -1].astype(np.float64))[1][:3, 3]   # final pose of the miss
+    nv["cuboid_dims"][1, 0] = 0.05        # -> final xyz inside a negative volume that does not contain the target
+    return p, np.ascontiguousarray(traj), num, tv, nv
+
+
+def test_evaluate_matches_oracle(engine, oracle, tables):
+    p, traj, num, tv, nv = _eval_case()
+    sc = to_dev(p)
+    dev = lambda d: {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in d.items()}  # noqa: E731
+    tg = torch.from_numpy(p["target"]).cuda()
+    for kw_g, kw_o in (
+        (dict(num_poses=torch.from_numpy(num).cuda(), target_volume=dev(tv), negative_volumes=dev(nv)),
+         dict(num_poses=num, target_volume=tv, negative_volumes=nv)),
+        (dict(), dict()),
+        (dict(target_volume=dev(tv)), dict(target_volume=tv)),
+        (dict(negative_volumes=dev(nv)), dict(negative_volumes=nv)),
+    ):
+        got = engine.evaluate(sc, torch.from_numpy(traj).cuda(), tg, **kw_g).cpu().numpy()
+        exp = oracle.evaluate(p, traj, p["target"], tables, **kw_o)
+        flag_cols = [0, 1, 2, 3, 8, 9, 10, 11]
+        assert np.array_equal(got[:, flag_cols], exp[:, flag_cols])          # flags / counts: bit-exact
+        assert np.array_equal(got[:, [4, 6, 12, 13]], exp[:, [4, 6, 12, 13]])  # spec-arithmetic lengths: bit-exact
+        assert np.abs(got[:, [5, 7]] - exp[:, [5, 7]]).max() < 1e-3            # atan2f: library ulps
+        assert (got[:, 14:] == 0).all()
+    assert got[1, 8] == 0 and got[0, 8] == 1 and got[8, 8] == 1   # negative-volume-only run: row 1 ends in the wrong region
+    assert got.shape == (traj.shape[0], 16)
+
+
+def test_evaluate_after_rollout(engine_w, oracle, tables):
+    """mpn_rollout's trajectory buffer feeds mpn_evaluate directly; its collision / position columns agree with the
+    rollout's own metrics table."""
+    T = 3
+    p = _problems(3, 8)
+    sc = to_dev(p)
+    q0, tg = torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda()
+    cloud = engine_w.build_cloud(sc, q0, tg)
+    traj, metrics = engine_w.rollout(sc, cloud, q0, tg, T)
+    ev = engine_w.evaluate(sc, traj, tg).cpu().numpy()
+    m = metrics.cpu().numpy()
+    assert np.array_equal(ev[:, 0], m[:, 0]) and np.array_equal(ev[:, 11], m[:, 1])
+    assert np.abs(ev[:, 4] - 100 * m[:, 3]).max() < 1e-3
+    assert np.abs(ev[:, 5] - m[:, 4]).max() < 0.1
+    assert (ev[:, 10] == T + 1).all()
+    exp = oracle.evaluate(p, traj.cpu().numpy(), p["target"], tables)
+    assert np.array_equal(ev[:, [0, 1, 2, 3, 8, 9, 10, 11]], exp[:, [0, 1, 2, 3, 8, 9, 10, 11]])

@@ -320,3 +320,94 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
                 assert "mpn_oracle" not in src, f"{f} references the oracle library"
+
+
+# ----------------------------------------------------------------------------- Evaluator subset (metrics.py:311-523)
+from mpinets_b200 import scenes  # noqa: E402
+from mpinets_b200.franka import fk_reference_f64  # noqa: E402
+
+
+def _eval_inputs(B=10, T1=21, seed=5):
+    """joint-space interpolation q0 -> q_goal (reaches the target exactly) with a few rows perturbed"""
+    p = scenes.config_problems(4, B)
+    w = np.linspace(0.0, 1.0, T1, dtype=np.float32)[None, :, None]
+    traj = (p["q0"][:, None, :] * (1 - w) + p["q_goal"][:, None, :] * w).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    traj[1, -1] += 0.2                       # misses the target
+    traj[2, 5, 3] = 0.5                      # joint 4 upper limit is -0.0698 -> violation
+    traj[3, :, :] = np.array([1.638, 1.227, 0.041, -3.039, 0.047, 1.604, 0.314], np.float32) + 0.01 * rng.standard_normal((T1, 7)).astype(np.float32)
+    return p, np.ascontiguousarray(traj)
+
+
+def _angle_deg_f64(A, B):
+    R = A[:3, :3].astype(np.float64) @ B[:3, :3].astype(np.float64).T
+    return np.degrees(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))
+
+
+def test_oracle_evaluate_matches_float64_numpy(oracle, tables):
+    p, traj = _eval_inputs()
+    B, T1, _ = traj.shape
+    num = np.full(B, T1, np.int32); num[4] = 7
+    tv = dict(cuboid_centers=p["target"][:, None, :3, 3].copy(), cuboid_dims=np.full((B, 1, 3), 0.1, np.float32),
+              cuboid_quats=np.tile(np.array([1, 0, 0, 0], np.float32), (B, 1, 1)))
+    tv["cuboid_centers"][5, 0, 0] += 1.0     # final pose is outside its target volume
+    nv = dict(cuboid_centers=p["target"][:, None, :3, 3].copy() + np.array([0.3, 0, 0], np.float32),
+              cuboid_dims=np.full((B, 1, 3), 0.2, np.float32), cuboid_quats=tv["cuboid_quats"].copy())
+    nv["cuboid_dims"][6] = 1.0               # contains the target itself -> dropped by metrics.py:497-499
+    ev = oracle.evaluate(p, traj, p["target"], tables, num_poses=num, target_volume=tv, negative_volumes=nv)
+    col = {k: i for i, k in enumerate(("collision", "joint_limit_violation", "self_collision", "physical_violations",
+                                       "position_error", "orientation_error", "eff_position_path_length",
+                                       "eff_orientation_path_length", "correct_final_region", "success", "num_steps",
+                                       "first_collision_step", "config_path_length", "max_collision_depth"))}
+    flags, first, _ = oracle.sweep_flags(p, traj, tables)
+    lim = tables.joint_limits
+    for b in range(B):
+        n = int(num[b])
+        eef = np.stack([fk_reference_f64(traj[b, t].astype(np.float64))[1] for t in range(n)])
+        tg = np.eye(4); tg[:3] = p["target"][b]
+        assert abs(ev[b, col["position_error"]] - 100 * np.linalg.norm(eef[-1, :3, 3] - tg[:3, 3])) < 2e-3
+        assert abs(ev[b, col["orientation_error"]] - _angle_deg_f64(eef[-1], tg)) < 5e-2
+        steps = np.linalg.norm(np.diff(eef[:, :3, 3], axis=0), axis=1).sum()
+        assert abs(ev[b, col["eff_position_path_length"]] - steps) < 1e-4
+        ori = sum(_angle_deg_f64(eef[t + 1], eef[t]) for t in range(n - 1))
+        assert abs(ev[b, col["eff_orientation_path_length"]] - ori) < 0.05 * max(1, n / 10)
+        cfg = np.linalg.norm(np.diff(traj[b, :n].astype(np.float64), axis=0), axis=1).sum()
+        assert abs(ev[b, col["config_path_length"]] - cfg) < 1e-4
+        jl = bool(((traj[b, :n] < lim[:, 0]) | (traj[b, :n] > lim[:, 1])).any())
+        assert bool(ev[b, col["joint_limit_violation"]]) == jl
+        assert ev[b, col["num_steps"]] == n
+        if n == T1:
+            assert bool(ev[b, col["collision"]]) == bool(flags[b]) and int(ev[b, col["first_collision_step"]]) == int(first[b])
+        phys = ev[b, col["collision"]] or ev[b, col["joint_limit_violation"]] or ev[b, col["self_collision"]]
+        assert bool(ev[b, col["physical_violations"]]) == bool(phys)
+        succ = (ev[b, col["position_error"]] < 1 and ev[b, col["orientation_error"]] < 15 and ev[b, col["correct_final_region"]]
+                and not phys)
+        assert bool(ev[b, col["success"]]) == bool(succ)
+    assert ev[2, col["joint_limit_violation"]] == 1 and ev[0, col["joint_limit_violation"]] == 0
+    assert ev[0, col["position_error"]] < 1e-2 and ev[1, col["position_error"]] > 1.0
+    assert ev[5, col["correct_final_region"]] == 0 and ev[0, col["correct_final_region"]] == 1
+    assert ev[6, col["correct_final_region"]] == 1       # the negative volume that swallows the target is ignored
+    assert ev[3, col["self_collision"]] == 1             # elbow fully flexed: gripper spheres 7.5 cm inside the link-2 spheres
+    # max_collision_depth is the deepest sphere penetration r - sdf over the trajectory (0 when never in contact)
+    assert ((ev[:, col["max_collision_depth"]] >= 0) & ((ev[:, col["max_collision_depth"]] > 0) | (ev[:, col["collision"]] == 0))).all()
+
+
+def test_oracle_evaluate_region_against_reference_sdf(oracle, tables):
+    """the region test's cuboid SDF equals the real TorchCuboids.sdf for yaw-only volumes (fixture from geometry.py)"""
+    p, traj = _eval_inputs(B=4, T1=8)
+    B = 4
+    rng = np.random.default_rng(0)
+    for trial in range(8):
+        yaw = rng.uniform(-np.pi, np.pi, B)
+        quat = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], -1).astype(np.float32)[:, None]
+        dims = rng.uniform(0.05, 0.4, (B, 1, 3)).astype(np.float32)
+        fin = np.stack([fk_reference_f64(traj[b, -1].astype(np.float64))[1][:3, 3] for b in range(B)]).astype(np.float32)
+        cen = (fin + rng.uniform(-0.2, 0.2, (B, 3))).astype(np.float32)[:, None]
+        tv = dict(cuboid_centers=cen, cuboid_dims=dims, cuboid_quats=quat)
+        ev = oracle.evaluate(p, traj, p["target"], tables, target_volume=tv)
+        sc = dict(p); sc.update(cuboid_centers=cen, cuboid_dims=dims, cuboid_quats=quat)
+        sc["cylinder_centers"] = np.zeros((B, 1, 3), np.float32); sc["cylinder_radii"] = np.zeros((B, 1, 1), np.float32)
+        sc["cylinder_heights"] = np.zeros((B, 1, 1), np.float32); sc["cylinder_quats"] = np.tile(np.array([1, 0, 0, 0], np.float32), (B, 1, 1))
+        fin_spec = oracle.fk(traj[:, -1])[1][:, :3, 3]
+        sdf = oracle.sdf_points(sc, fin_spec[:, None, :], quirk=False, which=1)[:, 0]
+        assert ((sdf <= 0) == (ev[:, 8] > 0)).all()
