@@ -166,6 +166,23 @@ int mpn_evaluate(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, cons
                  const int32_t* num_poses, const float* target, const mpn_scene* target_volume, int tv_cuboids,
                  int tv_cylinders, const mpn_scene* negative_volumes, int nv_cuboids, int nv_cylinders, float* eval);
 
+/* ---- training losses (mpinets/loss.py), forward value + analytic gradient; all pointers are device pointers ----------
+ * collision_loss (loss.py:47-94): loss[0] = mean over B*N of max(0, margin - sdf(points[b][n])) with the scene sdf of
+ * geometry.py:238-288,456-507 (F.hinge_embedding_loss with target -1; the reference uses margin 0.03).
+ * grad_points (optional, [B][N][3]) = d loss / d points with torch autograd's conventions. */
+int mpn_collision_loss(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, int N, const float* points, float margin,
+                       float* loss, float* grad_points);
+/* point_match_loss (loss.py:31-44): loss[0] = mse_mean(a, b) + l1_mean(a, b) over n floats; grad_a optional [n] */
+int mpn_point_match_loss(mpn_ctx* ctx, void* stream, int64_t n, const float* a, const float* b, float* loss, float* grad_a);
+/* CollisionAndBCLossContainer.__call__ (loss.py:111-166): input_normalized / target_normalized [B][7] in [-1, 1] ->
+ * unnormalise -> FK -> the fixed n_points robot cloud (FrankaSampler(num_fixed_points = n_points, with_base_link = False):
+ * here the first n_points entries of a seeded permutation of the link table's non-base rows) -> losses[0] = collision
+ * loss, losses[1] = point-match loss.  grad_input (optional, [B][7]) = d(w_collision * losses[0] + w_bc * losses[1]) /
+ * d input_normalized (model.py:232-236 uses the weights of jobconfig.yaml:24-25). */
+int mpn_bc_collision_losses(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* input_normalized,
+                            const float* target_normalized, int n_points, float margin, float w_collision, float w_bc,
+                            float* losses, float* grad_input);
+
 /* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
 int64_t mpn_launch_count(mpn_ctx* ctx);
 
@@ -183,9 +200,9 @@ int mpn_profile_read(mpn_ctx* ctx, float* ms /*[MPN_NUM_STAGES]*/, int64_t* laun
  * status (device int) is set to 1 when the MMA completion barrier timed out. */
 /* synchronises and returns the tensor-core path's sticky error flag (1 = an MMA completion barrier timed out) */
 int mpn_tc_error(mpn_ctx* ctx, int* out);
-/* debug: per-phase cycle totals of the SA tensor-core kernels (CTA 0, warpgroup 0; [0,16) SA2, [16,32) SA1), enabled by
- * MPN_TC_TIMELINE=1 in the environment; out must hold 32 values */
-int mpn_tc_timeline(mpn_ctx* ctx, int64_t* out32);
+/* debug: per-phase cycle totals of the tensor-core kernels (CTA 0, warpgroup 0; [0,16) SA2, [16,32) SA1, [32,48) the
+ * row GEMM), enabled by MPN_TC_TIMELINE=1 in the environment; out must hold 48 values */
+int mpn_tc_timeline(mpn_ctx* ctx, int64_t* out48);
 int mpn_tc_selftest(mpn_ctx* ctx, void* stream, const void* a_bf16, const void* b_bf16, float* d, int N, int K, int mode,
                     int* status);
 

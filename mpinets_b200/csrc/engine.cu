@@ -242,6 +242,9 @@ int mpn_ctx_destroy(mpn_ctx* c) {
   if (c->ws.first_step) cudaFree(c->ws.first_step);
   if (c->ws.flags) cudaFree(c->ws.flags);
   if (c->ws.tc_scratch) cudaFree(c->ws.tc_scratch);
+  if (c->link_table4) cudaFree(c->link_table4);
+  if (c->robot_sel4) cudaFree(c->robot_sel4);
+  if (c->loss_partial) cudaFree(c->loss_partial);
   delete c;
   return MPN_OK;
 }
@@ -273,6 +276,8 @@ int mpn_set_robot_tables(mpn_ctx* c, const float* joint_limits, int P, const flo
   r |= dev_upload(&c->sph_l, sph_l, (size_t)S);
   if (r) return r;
   c->P = P; c->Pe = Pe; c->S = S; c->prismatic = prismatic;
+  c->n_base_points = 0;
+  while (c->n_base_points < P && link_ids[c->n_base_points] == 0) ++c->n_base_points;
   if ((r = pack_link_table(c))) return r;
   c->tables_set = true;
   return MPN_OK;
@@ -318,8 +323,8 @@ int mpn_tc_timeline(mpn_ctx* c, int64_t* out16) {
   long long* p = tc_timeline(c);
   MPN_REQUIRE(p, "set MPN_TC_TIMELINE=1 to enable the phase timeline");
   MPN_CHECK_CUDA(cudaDeviceSynchronize());
-  MPN_CHECK_CUDA(cudaMemcpy(out16, p, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
-  MPN_CHECK_CUDA(cudaMemset(p, 0, 32 * sizeof(long long)));
+  MPN_CHECK_CUDA(cudaMemcpy(out16, p, 48 * sizeof(long long), cudaMemcpyDeviceToHost));
+  MPN_CHECK_CUDA(cudaMemset(p, 0, 48 * sizeof(long long)));
   return MPN_OK;
 }
 
@@ -508,6 +513,33 @@ int mpn_evaluate(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const 
   return launch_evaluate(c, (cudaStream_t)stream, *scene, B, traj, n_poses_max, num_poses, target,
                          target_volume ? *target_volume : none, tv_cuboids, tv_cylinders,
                          negative_volumes ? *negative_volumes : none, nv_cuboids, nv_cylinders, eval);
+}
+
+// ---- losses (loss.py)
+int mpn_collision_loss(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, int N, const float* points, float margin, float* loss,
+                       float* grad_points) {
+  REQ_CTX(c); REQ_TABLES(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(points && loss && B >= 1 && N >= 1, "mpn_collision_loss: bad arguments");
+  return launch_collision_loss(c, (cudaStream_t)stream, *scene, B, N, points, margin, loss, grad_points);
+}
+
+int mpn_point_match_loss(mpn_ctx* c, void* stream, int64_t n, const float* a, const float* b, float* loss, float* grad_a) {
+  REQ_CTX(c);
+  MPN_REQUIRE(a && b && loss && n >= 1, "mpn_point_match_loss: bad arguments");
+  return launch_point_match_loss(c, (cudaStream_t)stream, (size_t)n, a, b, loss, grad_a);
+}
+
+int mpn_bc_collision_losses(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* input_normalized,
+                            const float* target_normalized, int n_points, float margin, float w_collision, float w_bc, float* losses,
+                            float* grad_input) {
+  REQ_CTX(c); REQ_TABLES(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(input_normalized && target_normalized && losses && B >= 1, "mpn_bc_collision_losses: bad arguments");
+  return launch_bc_collision_losses(c, (cudaStream_t)stream, *scene, B, input_normalized, target_normalized, n_points, margin,
+                                    w_collision, w_bc, losses, grad_input);
 }
 
 // ---- model

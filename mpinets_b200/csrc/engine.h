@@ -87,6 +87,9 @@ struct mpn_ctx {
   float* limits = nullptr;       // [7][2]
   int P = 0; float* link_points = nullptr; int32_t* link_ids = nullptr;
   float* link_table4 = nullptr;  // [P] float4 (x, y, z, link id bits): one gather per robot row
+  float* robot_sel4 = nullptr;   // [P] float4: this step's permuted subset of link_table4 (shared by the whole batch)
+  int n_base_points = 0;         // leading link-0 rows of the table (FrankaSampler(with_base_link=False) skips them)
+  float* loss_partial = nullptr; size_t loss_partial_cap = 0;   // per-CTA partial sums of the loss kernels
   int Pe = 0; float* ee_points = nullptr;
   int S = 0; float* sph_c = nullptr; float* sph_r = nullptr; int32_t* sph_l = nullptr;
   float prismatic = 0.025f;
@@ -129,6 +132,12 @@ int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const f
                  int t0, int accumulate, uint8_t* flags, int32_t* first_step, const float* frames_in = nullptr);
 int launch_evaluate(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T1, const int32_t* num_poses,
                     const float* target, const mpn_scene& tv, int V1, int V2, const mpn_scene& nv, int N1, int N2, float* out);
+// ---- loss.cu
+int launch_collision_loss(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int N, const float* points, float margin, float* loss,
+                          float* grad_points);
+int launch_point_match_loss(mpn_ctx* c, cudaStream_t s, size_t n, const float* a, const float* b, float* loss, float* grad_a);
+int launch_bc_collision_losses(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* input_norm, const float* target_norm,
+                               int n_points, float margin, float w_collision, float w_bc, float* losses, float* grad_input);
 // ---- pointnet.cu
 int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz);
 int launch_ball_query(mpn_ctx* c, cudaStream_t s, float radius, int nsample, const float* xyz, int B, int N, int stride,

@@ -14,11 +14,12 @@ namespace mpn {
 using namespace tc;
 
 enum { EPI_RELU_BF16 = 0, EPI_F32 = 1, EPI_MAXPOOL = 2 };
-constexpr int G_BM = 256, G_BN = 256, G_BK = 64, G_STAGES = 3;   // G_BM = 2 x 128-row MMA tiles
-constexpr int G_A_BYTES = G_BM * G_BK * 2, G_W_BYTES = G_BN * G_BK * 2, G_STAGE_BYTES = G_A_BYTES + G_W_BYTES;
+constexpr int G_BN = 256;   // CTA tile = G_BM x 256 with G_BM = 128 or 256 (one or two 128-row MMA tiles sharing every weight stage)
+// K staging is a template parameter pair: (G_BK, G_STAGES) = (64, 3) or (32, 6) -- the same 192 KB ring, but the deeper
+// ring keeps five stages of loads in flight behind the one being multiplied instead of two.
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -30,10 +31,13 @@ __device__ __forceinline__ uint32_t cvt_relu_pack(float first, float second) {
   return d;
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(256, 1)
+template <int EPI, int G_BM, int G_BK, int G_STAGES>
+__global__ void __launch_bounds__(256, G_BM == 128 ? 2 : 1)
 gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ W, int K, const float* __restrict__ bias,
-               int M, int N, void* __restrict__ Cout, int ldc, int* __restrict__ err) {
+               int M, int N, void* __restrict__ Cout, int ldc, int* __restrict__ err, long long* __restrict__ tl) {
+  constexpr int G_KC = G_BK / 8, G_KS = G_BK / 16;   // 16-byte chunks / MMA K-steps per stage row
+  constexpr int G_A_BYTES = G_BM * G_BK * 2, G_W_BYTES = G_BN * G_BK * 2, G_STAGE_BYTES = G_A_BYTES + G_W_BYTES;
+  static_assert(G_KC == 4 || G_KC == 8, "stage K must be 32 or 64");
   extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
   __shared__ uint64_t done[G_STAGES];
   __shared__ uint32_t tmem_slot;
@@ -42,19 +46,23 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * G_BN;
   const int nst = (K + G_BK - 1) / G_BK;
+  long long tl_prev = clock64();
+  const bool tl_on = tl != nullptr && M > 65536 && blockIdx.x == 0 && blockIdx.y == 64 && threadIdx.x == 0;   // a mid-grid tile of the big row GEMMs
+#define GT_MARK(i) do { if (tl_on) { long long _n = clock64(); tl[32 + (i)] += _n - tl_prev; tl_prev = _n; } } while (0)
 
   sbias[tid] = bias[n0 + tid];   // 256 threads == G_BN columns
   if (tid == 0) {
     for (int s = 0; s < G_STAGES; ++s) mbar_init(&done[s], 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  constexpr int G_SUBS = G_BM / 128;
+  if (warp == 0) tmem_alloc(&tmem_slot, 256 * G_SUBS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint64_t dA0 = make_smem_desc(smem_u32(smem), 128, 1024, LAYOUT_NONE);                 // stage 0 descriptors; later stages /
-  const uint64_t dW0 = make_smem_desc(smem_u32(smem) + G_A_BYTES, 128, 1024, LAYOUT_NONE);     // K-steps only add to the address field
+  const uint64_t dA0 = make_smem_desc(smem_u32(smem), 128, G_KC * 128, LAYOUT_NONE);                 // stage 0 descriptors; later stages /
+  const uint64_t dW0 = make_smem_desc(smem_u32(smem) + G_A_BYTES, 128, G_KC * 128, LAYOUT_NONE);     // K-steps only add to the address field
 
   // stage loader: A rows m0.., W rows n0.., K chunk [st*64, st*64+64) -> interleaved layout with 8 chunks per row.
   // Lane mapping: each quarter-warp (the unit the 16-byte shared-memory write is served in) covers 8 consecutive rows of
@@ -64,20 +72,24 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
     uint8_t* sA = smem + (size_t)(st % G_STAGES) * G_STAGE_BYTES;
     uint8_t* sW = sA + G_A_BYTES;
     const int k0 = st * G_BK;
-    const int kc_n = min(8, (K - k0) / 8);
+    const int kc_n = min(G_KC, (K - k0) / 8);
 #pragma unroll
-    for (int i = 0; i < (G_BM * 8) / 256; ++i) {
-      const int c = tid + i * 256, r = ((c >> 6) << 3) | (c & 7), kc = (((c >> 5) & 1) << 2) | ((c >> 3) & 3);
+    for (int i = 0; i < (G_BM * G_KC) / 256; ++i) {
+      const int c = tid + i * 256;
+      const int r = G_KC == 8 ? (((c >> 6) << 3) | (c & 7)) : (((c >> 5) << 3) | (c & 7));
+      const int kc = G_KC == 8 ? ((((c >> 5) & 1) << 2) | ((c >> 3) & 3)) : ((c >> 3) & 3);
       if (kc < kc_n) {
         int m = m0 + r;
         const __nv_bfloat16* src = A + (size_t)min(m, M - 1) * lda + k0 + kc * 8;
-        cp_async16(smem_u32(sA + kmajor_chunk_off(r, kc, 8)), src, m < M ? 16u : 0u);
+        cp_async16(smem_u32(sA + kmajor_chunk_off(r, kc, G_KC)), src, m < M ? 16u : 0u);
       }
     }
 #pragma unroll
-    for (int i = 0; i < (G_BN * 8) / 256; ++i) {
-      const int c = tid + i * 256, r = ((c >> 6) << 3) | (c & 7), kc = (((c >> 5) & 1) << 2) | ((c >> 3) & 3);
-      if (kc < kc_n) cp_async16(smem_u32(sW + kmajor_chunk_off(r, kc, 8)), W + (size_t)(n0 + r) * K + k0 + kc * 8, 16u);
+    for (int i = 0; i < (G_BN * G_KC) / 256; ++i) {
+      const int c = tid + i * 256;
+      const int r = G_KC == 8 ? (((c >> 6) << 3) | (c & 7)) : (((c >> 5) << 3) | (c & 7));
+      const int kc = G_KC == 8 ? ((((c >> 5) & 1) << 2) | ((c >> 3) & 3)) : ((c >> 3) & 3);
+      if (kc < kc_n) cp_async16(smem_u32(sW + kmajor_chunk_off(r, kc, G_KC)), W + (size_t)(n0 + r) * K + k0 + kc * 8, 16u);
     }
   };
 
@@ -86,48 +98,57 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
     cp_async_commit();
   }
   bool ok = true;
+  GT_MARK(0);   // prologue: barriers, TMEM alloc, first loads issued
   for (int it = 0; it < nst; ++it) {
     cp_async_wait<G_STAGES - 2>();
+    GT_MARK(1);   // waiting for this stage's loads
     fence_proxy_async_smem();
     __syncthreads();
+    GT_MARK(2);   // fence + block sync
     if (warp == 0) {
       tc_fence_after();
       uint32_t el;
       asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(el));
       if (el) {
       const uint32_t soff = (uint32_t)(it % G_STAGES) * (G_STAGE_BYTES / 16);
-      const int ksteps = min(4, (K - it * G_BK) / 16);
+      const int ksteps = min(G_KS, (K - it * G_BK) / 16);
       constexpr uint32_t id = make_idesc_bf16(128, G_BN);
-      constexpr uint32_t SUB1 = (128 / 8) * 8 * 128 / 16;   // rows 128..255 of the A stage, in 16-byte units
-      if (ksteps == 4) {
+      constexpr uint32_t SUB1 = (128 / 8) * G_KC * 128 / 16;   // rows 128..255 of the A stage, in 16-byte units
+      if (ksteps == G_KS) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_bf16_ss_off(tmem, dA0, soff + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
+        for (int ks = 0; ks < G_KS; ++ks) mma_bf16_ss_off(tmem, dA0, soff + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma_bf16_ss_off(tmem + 256, dA0, soff + SUB1 + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
+        for (int ks = 0; ks < G_KS; ++ks)
+          if (G_SUBS == 2) mma_bf16_ss_off(tmem + 256, dA0, soff + SUB1 + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
       } else {
         for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss_off(tmem, dA0, soff + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
-        for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss_off(tmem + 256, dA0, soff + SUB1 + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
+        for (int ks = 0; ks < ksteps; ++ks)
+          if (G_SUBS == 2) mma_bf16_ss_off(tmem + 256, dA0, soff + SUB1 + ks * 16, dW0, soff + ks * 16, id, (it | ks) != 0);
       }
       mma_commit(&done[it % G_STAGES]);
       }
       __syncwarp();
     }
+    GT_MARK(3);   // MMA issue (thread 0 is the warp-0 lane that may be elected)
     const int nxt = it + G_STAGES - 1;
     if (nxt < nst) {
       if (it >= 1) ok = ok && mbar_wait(&done[(it - 1) % G_STAGES], ((it - 1) / G_STAGES) & 1);   // slot of stage it-1 is free
+      GT_MARK(4);   // waiting for the previous stage's MMAs
       load_stage(nxt);
+      GT_MARK(5);   // issuing the next loads
     }
     cp_async_commit();
   }
   ok = ok && mbar_wait(&done[(nst - 1) % G_STAGES], ((nst - 1) / G_STAGES) & 1);
   tc_fence_after();
+  GT_MARK(6);   // drain: last MMAs
   if (!ok && tid == 0) atomicExch(err, 1);
 
   // ---- epilogue: warp (q = warp & 3) owns lanes 32q..32q+31, column half h = warp >> 2.  The bias tile sits in shared
   // memory (staged at kernel start) and is read with 16-byte broadcast loads.
   const int q = warp & 3, h = warp >> 2, row = q * 32 + (tid & 31);
 #pragma unroll 1
-  for (int sub = 0; sub < 2; ++sub) {
+  for (int sub = 0; sub < G_SUBS; ++sub) {
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + sub * 256 + h * 128;
     const int m = m0 + sub * 128 + row;
 #pragma unroll 1
@@ -176,7 +197,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
     }
     if (EPI == EPI_MAXPOOL) {
       __syncthreads();
-      const int prob = blockIdx.y * 2 + sub;   // one pooled row per 128-row sub-tile (= one problem)
+      const int prob = blockIdx.y * G_SUBS + sub;   // one pooled row per 128-row sub-tile (= one problem)
       if (prob * 128 < M) {
         const int mi = max(max(red[0][tid], red[1][tid]), max(red[2][tid], red[3][tid]));
         const int bits = mi >= 0 ? mi : (int)(0x80000000u - (uint32_t)mi);
@@ -186,28 +207,44 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16
       __syncthreads();
     }
   }
+  GT_MARK(7);   // epilogue
+  if (tl_on) tl[32 + 8] += 1;
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, 256 * G_SUBS);
+#undef GT_MARK
 }
 
 int* tc_error_flag(mpn_ctx* c);
+long long* tc_timeline(mpn_ctx* c);
 
 int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int K, const float* bias,
                    int M, int N, void* C, int ldc) {
   MPN_REQUIRE(K % 16 == 0 && N % G_BN == 0 && lda % 8 == 0, "gemm_tc: K %% 16, N %% 256, lda %% 8 required (K=%d N=%d lda=%d)", K, N, lda);
   MPN_REQUIRE(epi != EPI_MAXPOOL || M % 128 == 0, "gemm_tc: max-pool epilogue needs M %% 128 == 0");
-  dim3 grid(N / G_BN, (M + G_BM - 1) / G_BM);
-  size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 1024;
+  // Tile shapes: 128 x 256 with 4 stages of K=32 (96 KB, 256 TMEM columns) so that TWO CTAs share an SM and one tile's
+  // prologue / epilogue overlaps the other's main loop; MPN_GEMM_TILE=256 selects the 256 x 256 tile (one CTA per SM,
+  // 6 stages of K=32), MPN_GEMM_TILE=25664 the same with 3 stages of K=64.
+  static const int tile = getenv("MPN_GEMM_TILE") ? atoi(getenv("MPN_GEMM_TILE")) : 128;
+  const int bm = tile == 128 ? 128 : 256;
+  dim3 grid(N / G_BN, (M + bm - 1) / bm);
   int* err = tc_error_flag(c);
-#define GEMM_LAUNCH(E)                                                                                              \
-  do {                                                                                                              \
-    MPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    gemm_tc_kernel<E><<<grid, 256, smem, s>>>(A, lda, W, K, bias, M, N, C, ldc, err);                               \
+#define GEMM_LAUNCH_T(E, BM, BK, ST)                                                                                            \
+  do {                                                                                                                          \
+    const size_t smem = (size_t)ST * (BM + G_BN) * BK * 2 + 1024;                                                               \
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<E, BM, BK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gemm_tc_kernel<E, BM, BK, ST><<<grid, 256, smem, s>>>(A, lda, W, K, bias, M, N, C, ldc, err, tc_timeline(c));               \
+  } while (0)
+#define GEMM_LAUNCH(E)                                \
+  do {                                                \
+    if (tile == 128) GEMM_LAUNCH_T(E, 128, 32, 4);    \
+    else if (tile == 25664) GEMM_LAUNCH_T(E, 256, 64, 3); \
+    else GEMM_LAUNCH_T(E, 256, 32, 6);                \
   } while (0)
   if (epi == EPI_RELU_BF16) GEMM_LAUNCH(EPI_RELU_BF16);
   else if (epi == EPI_F32) GEMM_LAUNCH(EPI_F32);
   else GEMM_LAUNCH(EPI_MAXPOOL);
+#undef GEMM_LAUNCH_T
 #undef GEMM_LAUNCH
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());

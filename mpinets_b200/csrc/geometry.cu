@@ -6,6 +6,7 @@
 // mpinets/geometry.py:238-288,456-507 (sdf), :571-608 (construct_mixed_point_cloud), model.py:293-314 (sweep).
 #include "engine.h"
 #include "spec_math.cuh"
+#include "scene.cuh"
 
 namespace mpn {
 
@@ -46,15 +47,24 @@ __global__ void pack_link_table_kernel(const float* __restrict__ lp, const int32
   if (i < P) out[i] = make_float4(lp[3 * i], lp[3 * i + 1], lp[3 * i + 2], __int_as_float(lid[i]));
 }
 
-__global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restrict__ frames, int n, int P,
-                                                           const float4* __restrict__ table, uint32_t seed_lo, uint32_t seed_hi,
-                                                           uint32_t step, float4* __restrict__ cloud, int rows) {
+// The random subset of FrankaSampler.sample is one np.random.choice shared by the whole batch, so the
+// permutation is evaluated once per step into `sel` (n float4 rows, 32 KB: L1/L2 resident) instead of once per problem;
+// the per-problem kernel is then a pure streaming pass: coalesced 16-byte reads of `sel`, the link frame from shared
+// memory, coalesced 16-byte row writes.
+__global__ void robot_subset_kernel(int n, int P, const float4* __restrict__ table, uint32_t seed_lo, uint32_t seed_hi, uint32_t step,
+                                    float4* __restrict__ sel) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint32_t key[4];
+  philox4x32(0u, step, STREAM_ROBOT_PERM, 0u, seed_lo, seed_hi, key);
+  sel[j] = __ldg(table + feistel_perm((uint32_t)j, (uint32_t)P, feistel_bits((uint32_t)P) / 2, key));
+}
+
+__global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restrict__ frames, int n, const float4* __restrict__ sel,
+                                                           float4* __restrict__ cloud, int rows) {
   __shared__ float F[MPN_NLINK * 12];
   int b = blockIdx.x;
   for (int i = threadIdx.x; i < MPN_NLINK * 12; i += blockDim.x) F[i] = frames[(size_t)b * MPN_NLINK * 12 + i];
-  uint32_t key[4];
-  philox4x32(0u, step, STREAM_ROBOT_PERM, 0u, seed_lo, seed_hi, key);
-  uint32_t half = feistel_bits((uint32_t)P) / 2;
   __syncthreads();
   float4* out = cloud + (size_t)b * rows;
   constexpr int U = 8;
@@ -63,7 +73,7 @@ __global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restri
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       int j = j0 + u * blockDim.x;
-      if (j < n) t[u] = __ldg(table + feistel_perm((uint32_t)j, (uint32_t)P, half, key));
+      if (j < n) t[u] = __ldg(sel + j);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -79,9 +89,11 @@ __global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restri
 }
 
 int launch_sample_robot(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, uint32_t step, float* cloud, int rows) {
-  sample_robot_kernel<<<B, 256, 0, s>>>(frames, n, c->P, reinterpret_cast<const float4*>(c->link_table4), (uint32_t)c->cfg.seed,
-                                        (uint32_t)(c->cfg.seed >> 32), step, (float4*)cloud, rows);
-  c->launches++;
+  MPN_REQUIRE(n <= c->P, "sample_robot: %d points requested, the link table has %d", n, c->P);
+  robot_subset_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, c->P, reinterpret_cast<const float4*>(c->link_table4), (uint32_t)c->cfg.seed,
+                                                     (uint32_t)(c->cfg.seed >> 32), step, reinterpret_cast<float4*>(c->robot_sel4));
+  sample_robot_kernel<<<B, 256, 0, s>>>(frames, n, reinterpret_cast<const float4*>(c->robot_sel4), (float4*)cloud, rows);
+  c->launches += 2;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
 }
@@ -89,6 +101,8 @@ int launch_sample_robot(mpn_ctx* c, cudaStream_t s, const float* frames, int B, 
 int pack_link_table(mpn_ctx* c) {
   if (c->link_table4) cudaFree(c->link_table4);
   MPN_CHECK_CUDA(cudaMalloc(&c->link_table4, (size_t)c->P * sizeof(float4)));
+  if (c->robot_sel4) cudaFree(c->robot_sel4);
+  MPN_CHECK_CUDA(cudaMalloc(&c->robot_sel4, (size_t)c->P * sizeof(float4)));
   pack_link_table_kernel<<<(c->P + 255) / 256, 256>>>(c->link_points, c->link_ids, c->P, reinterpret_cast<float4*>(c->link_table4));
   MPN_CHECK_CUDA(cudaGetLastError());
   MPN_CHECK_CUDA(cudaDeviceSynchronize());
@@ -132,41 +146,6 @@ int launch_normalize(mpn_ctx* c, cudaStream_t s, const float* in, int n, float* 
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ scene staging
-// per-problem primitive list -> inverse frames in shared memory (<= M1+M2 <= 128 entries of 64 B)
-constexpr int MAX_PRIMS = 128;
-
-__device__ __forceinline__ PrimFrame prim_frame_of(const mpn_scene& sc, int b, int M1, int M2, int m, bool quirk) {
-  PrimFrame f;
-  if (m < M1) {
-    const float* d = sc.cuboid_dims + ((size_t)b * M1 + m) * 3;
-    float d0 = d[0], d1 = d[1], d2 = d[2];
-    f.valid = (is_close0(d0) || is_close0(d1) || is_close0(d2)) ? 0.f : 1.f;
-    make_inv_frame(sc.cuboid_centers + ((size_t)b * M1 + m) * 3, sc.cuboid_quats + ((size_t)b * M1 + m) * 4, quirk, f);
-    f.h[0] = fdiv(d0, 2.0f); f.h[1] = fdiv(d1, 2.0f); f.h[2] = fdiv(d2, 2.0f);
-  } else {
-    int k = m - M1;
-    float r = sc.cylinder_radii[(size_t)b * M2 + k], h = sc.cylinder_heights[(size_t)b * M2 + k];
-    f.valid = (is_close0(r) || is_close0(h)) ? 0.f : 1.f;
-    make_inv_frame(sc.cylinder_centers + ((size_t)b * M2 + k) * 3, sc.cylinder_quats + ((size_t)b * M2 + k) * 4, quirk, f);
-    f.h[0] = r; f.h[1] = fdiv(h, 2.0f); f.h[2] = 0.f;
-  }
-  return f;
-}
-
-__device__ __forceinline__ void stage_scene(const mpn_scene& sc, int b, int M1, int M2, bool quirk, PrimFrame* fr) {
-  for (int m = threadIdx.x; m < M1 + M2; m += blockDim.x) fr[m] = prim_frame_of(sc, b, M1, M2, m, quirk);
-}
-
-__device__ __forceinline__ float scene_sdf(const PrimFrame* fr, int c0, int c1, int y0, int y1, float px, float py, float pz) {
-  float best = __int_as_float(0x7f800000);
-  for (int m = c0; m < c1; ++m)
-    if (fr[m].valid != 0.f) best = fminf(best, sdf_cuboid(fr[m], px, py, pz));
-  for (int m = y0; m < y1; ++m)
-    if (fr[m].valid != 0.f) best = fminf(best, sdf_cylinder(fr[m], px, py, pz));
-  return best;
 }
 
 __global__ void __launch_bounds__(256) sdf_points_kernel(mpn_scene sc, int M1, int M2, int quirk, const float* __restrict__ pts,
@@ -323,8 +302,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(mpn_scene sc, int 
   __shared__ float sr_s[MAX_SPHERES];
   __shared__ int sl_s[MAX_SPHERES];
   __shared__ int first;
+  __shared__ int counts[2], wcnt[SWEEP_THREADS / 32];
   int b = blockIdx.x;
-  stage_scene(sc, b, M1, M2, quirk != 0, fr);
+  stage_scene_compact(sc, b, M1, M2, quirk != 0, fr, counts, wcnt);
+  const int nc = counts[0], ny = counts[1];
   for (int k = threadIdx.x; k < S; k += blockDim.x) {
     sc_s[3 * k] = sph_c[3 * k]; sc_s[3 * k + 1] = sph_c[3 * k + 1]; sc_s[3 * k + 2] = sph_c[3 * k + 2];
     sr_s[k] = sph_r[k]; sl_s[k] = sph_l[k];
@@ -346,11 +327,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(mpn_scene sc, int 
       for (int i = 0; i < MPN_NLINK * 12; ++i) F[threadIdx.x][i] = Fl[i];
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < nt * S; p += blockDim.x) {
-      int t = p / S, k = p - t * S;
+    // (timestep, sphere, primitive slice) items: "min over primitives <= r" is "any primitive <= r", so when a chunk has
+    // fewer pairs than threads (the per-step check, T = 1) each pair is split over two halves of the primitive list
+    const int nsl = (nt * S * 2 <= (int)blockDim.x) ? 2 : 1;
+    for (int p = threadIdx.x; p < nt * S * nsl; p += blockDim.x) {
+      const int sl = p / (nt * S), pr = p - sl * nt * S;
+      const int t = pr / S, k = pr - t * S;
       float x, y, z;
       m34_apply(F[t] + 12 * sl_s[k], sc_s[3 * k], sc_s[3 * k + 1], sc_s[3 * k + 2], x, y, z);
-      float d = scene_sdf(fr, 0, M1, M1, M1 + M2, x, y, z);
+      const float d = scene_sdf_packed(fr, nc * sl / nsl, nc * (sl + 1) / nsl, nc + ny * sl / nsl, nc + ny * (sl + 1) / nsl, x, y, z);
       if (d <= sr_s[k]) atomicMin(&first, tc + t);
     }
     __syncthreads();

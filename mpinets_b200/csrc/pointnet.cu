@@ -232,19 +232,28 @@ fps_pruned_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, 
                 gz = fmaxf(0.f, fmaxf(wlo[2] - c.z, c.z - whi[2]));
     const bool skip = (gx * gx + gy * gy + gz * gz) * 0.9999f > __uint_as_float(wm);
     if (!skip) {
-      float bd = -1.0f;
-      uint32_t bl = 0u;
+      // (distance, tie word) maximum of the thread's points as two short trees instead of one 13-deep compare/select chain:
+      // the largest distance first, then the largest tie word among the points that attain it (same lexicographic winner)
 #pragma unroll
-      for (int i = 0; i < FPSP_PPT; ++i) {
-        const float d2 = fminf(dist2(px[i], py[i], pz[i], c.x, c.y, c.z), temp[i]);
-        temp[i] = d2;
-        const bool better = d2 > bd || (d2 == bd && low[i] > bl);
-        bd = better ? d2 : bd;
-        bl = better ? low[i] : bl;
-      }
+      for (int i = 0; i < FPSP_PPT; ++i) temp[i] = fminf(dist2(px[i], py[i], pz[i], c.x, c.y, c.z), temp[i]);
+      float m[FPSP_PPT];
+#pragma unroll
+      for (int i = 0; i < FPSP_PPT; ++i) m[i] = temp[i];
+#pragma unroll
+      for (int w = 1; w < FPSP_PPT; w <<= 1)
+#pragma unroll
+        for (int i = 0; i + w < FPSP_PPT; i += 2 * w) m[i] = fmaxf(m[i], m[i + w]);
+      const float bd = m[0];
       const uint32_t dbits = bd >= 0.0f ? __float_as_uint(bd) : 0u;
-      const uint32_t lw = bd >= 0.0f ? bl : 0u;
       wm = __reduce_max_sync(0xffffffffu, dbits);
+      uint32_t t[FPSP_PPT];
+#pragma unroll
+      for (int i = 0; i < FPSP_PPT; ++i) t[i] = temp[i] == bd ? low[i] : 0u;
+#pragma unroll
+      for (int w = 1; w < FPSP_PPT; w <<= 1)
+#pragma unroll
+        for (int i = 0; i + w < FPSP_PPT; i += 2 * w) t[i] = max(t[i], t[i + w]);
+      const uint32_t lw = bd >= 0.0f ? t[0] : 0u;
       wl_ = __reduce_max_sync(0xffffffffu, dbits == wm ? lw : 0u);
     }
     if (lane == 0) slot[j & 1][warp] = make_uint2(wm, wl_);

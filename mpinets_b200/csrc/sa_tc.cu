@@ -1195,8 +1195,8 @@ long long* tc_timeline(mpn_ctx* c) {
   auto it = bufs.find(c);
   if (it != bufs.end()) return it->second;
   long long* p = nullptr;
-  cudaMalloc(&p, 32 * sizeof(long long));
-  cudaMemset(p, 0, 32 * sizeof(long long));
+  cudaMalloc(&p, 48 * sizeof(long long));
+  cudaMemset(p, 0, 48 * sizeof(long long));
   bufs[c] = p;
   return p;
 }

@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t feistel_perm(uint32_t x, uint32_t n, uint32_
   return x;
 }
 
-enum { STREAM_OBS_PERM = 1, STREAM_OBS_SAMPLE = 2, STREAM_ROBOT_PERM = 3, STREAM_TARGET_PERM = 4 };
+enum { STREAM_OBS_PERM = 1, STREAM_OBS_SAMPLE = 2, STREAM_ROBOT_PERM = 3, STREAM_TARGET_PERM = 4, STREAM_FIXED_PERM = 5 };
 
 // ---- surface sampling (geometrout 0.0.3.4 semantics re-specified, DESIGN.md "RNG")
 __device__ __forceinline__ void rot_apply(const float* R, const float* c, float lx, float ly, float lz, float* o) {

@@ -125,7 +125,7 @@ class Engine:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     def tc_timeline(self):
-        out = (C.c_int64 * 32)()
+        out = (C.c_int64 * 48)()
         _lib.check(self.lib.mpn_tc_timeline(self._ctx, out))
         return list(out)
 
@@ -296,6 +296,40 @@ class Engine:
                                          C.byref(tv) if tv is not None else None, v1, v2,
                                          C.byref(nv) if nv is not None else None, n1, n2, _p(out)))
         return out
+
+    # ------------------------------------------------------------------ losses (loss.py)
+    def collision_loss(self, scene, points: torch.Tensor, margin: float = 0.03, need_grad: bool = False):
+        """loss.collision_loss (loss.py:47-94): points [B,N,3] -> (loss [1], grad_points [B,N,3] or None)"""
+        _check(points, "input_pc", device=self.device)
+        B, N, _ = points.shape
+        s, keep = self._scene(scene, B)
+        loss = self._empty(1)
+        grad = self._empty(B, N, 3) if need_grad else None
+        _lib.check(self.lib.mpn_collision_loss(self._ctx, self.stream, C.byref(s), B, N, _p(points), margin, _p(loss), _p(grad)))
+        return loss, grad
+
+    def point_match_loss(self, a: torch.Tensor, b: torch.Tensor, need_grad: bool = False):
+        """loss.point_match_loss (loss.py:31-44) -> (loss [1], grad_a or None)"""
+        _check(a, "input_pc", device=self.device); _check(b, "target_pc", device=self.device)
+        if a.shape != b.shape:
+            raise RuntimeError(f"point clouds differ in shape: {tuple(a.shape)} vs {tuple(b.shape)}")
+        loss = self._empty(1)
+        grad = torch.empty_like(a) if need_grad else None
+        _lib.check(self.lib.mpn_point_match_loss(self._ctx, self.stream, a.numel(), _p(a), _p(b), _p(loss), _p(grad)))
+        return loss, grad
+
+    def bc_collision_losses(self, scene, input_normalized: torch.Tensor, target_normalized: torch.Tensor, n_points: int = 1024,
+                            margin: float = 0.03, w_collision: float = 1.0, w_bc: float = 1.0, need_grad: bool = False):
+        """CollisionAndBCLossContainer.__call__ (loss.py:111-166) -> (losses [2] = (collision, point match), grad_input)"""
+        _check(input_normalized, "input_normalized", device=self.device)
+        _check(target_normalized, "target_normalized", device=self.device)
+        B = input_normalized.shape[0]
+        s, keep = self._scene(scene, B)
+        losses = self._empty(2)
+        grad = self._empty(B, 7) if need_grad else None
+        _lib.check(self.lib.mpn_bc_collision_losses(self._ctx, self.stream, C.byref(s), B, _p(input_normalized), _p(target_normalized),
+                                                    n_points, margin, w_collision, w_bc, _p(losses), _p(grad)))
+        return losses, grad
 
     # ------------------------------------------------------------------ model
     def encoder_forward(self, cloud: torch.Tensor, precision: int = _lib.PREC_FP32):

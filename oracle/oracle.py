@@ -125,6 +125,55 @@ def sweep_flags(scene, traj, tables, quirk=True):
 EVAL_COLS = 16
 
 
+# ----------------------------------------------------------------------------- losses (loss.py)
+def collision_loss(scene, points, margin=0.03, quirk=True, need_grad=True):
+    """loss.collision_loss (loss.py:47-94): points [B,N,3] -> (loss, grad_points [B,N,3])"""
+    keep, B, M1, M2, ps = _scene_args(scene)
+    pts, pp = _f(points)
+    N = pts.shape[1]
+    loss = C.c_float(0.0)
+    grad = np.zeros_like(pts) if need_grad else None
+    lib().mpn_oracle_collision_loss(C.c_int(B), C.c_int(N), C.c_int(M1), C.c_int(M2), *ps, C.c_int(int(quirk)), pp, C.c_float(margin),
+                                    C.byref(loss), grad.ctypes.data_as(C.POINTER(C.c_float)) if need_grad else C.POINTER(C.c_float)())
+    return float(loss.value), grad
+
+
+def point_match_loss(a, b, need_grad=True):
+    """loss.point_match_loss (loss.py:31-44) -> (loss, grad_a)"""
+    a, pa = _f(a); b, pb = _f(b)
+    loss = C.c_float(0.0)
+    grad = np.zeros_like(a) if need_grad else None
+    lib().mpn_oracle_point_match_loss(C.c_size_t(a.size), pa, pb, C.byref(loss),
+                                      grad.ctypes.data_as(C.POINTER(C.c_float)) if need_grad else C.POINTER(C.c_float)())
+    return float(loss.value), grad
+
+
+def fixed_robot_points(q, tables, n, seed):
+    """FrankaSampler(num_fixed_points=n, with_base_link=False).sample(q) stand-in (loss.py:141-153): (points [B,n,3], table rows [n])"""
+    q, pq = _f(q)
+    lp, plp = _f(tables.link_points); lid, plid = _i(tables.link_ids)
+    out = np.empty((q.shape[0], n, 3), np.float32); idx = np.empty(n, np.int32)
+    lib().mpn_oracle_fixed_robot_points(pq, C.c_int(q.shape[0]), C.c_float(tables.prismatic), C.c_int(lp.shape[0]), plp, plid, C.c_int(n),
+                                        C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32(seed >> 32),
+                                        out.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int32)))
+    return out, idx
+
+
+def bc_collision_losses(scene, input_norm, target_norm, tables, seed, n=1024, margin=0.03, w_collision=1.0, w_bc=1.0, quirk=True):
+    """CollisionAndBCLossContainer.__call__ (loss.py:111-166) -> (losses [2], grad_input [B,7])"""
+    keep, B, M1, M2, ps = _scene_args(scene)
+    qi, pqi = _f(input_norm); qt, pqt = _f(target_norm)
+    lim, pl = _f(tables.joint_limits)
+    lp, plp = _f(tables.link_points); lid, plid = _i(tables.link_ids)
+    losses = np.zeros(2, np.float32); grad = np.zeros((B, 7), np.float32)
+    lib().mpn_oracle_bc_collision_losses(C.c_int(B), C.c_int(M1), C.c_int(M2), *ps, C.c_int(int(quirk)), pqi, pqt, pl,
+                                         C.c_float(tables.prismatic), C.c_int(lp.shape[0]), plp, plid, C.c_int(n),
+                                         C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32(seed >> 32), C.c_float(margin),
+                                         C.c_float(w_collision), C.c_float(w_bc), losses.ctypes.data_as(C.POINTER(C.c_float)),
+                                         grad.ctypes.data_as(C.POINTER(C.c_float)))
+    return losses, grad
+
+
 def _volume_args(vol, B):
     """optional region-test primitive lists -> (keep, n_cuboids, n_cylinders, 7 pointers)"""
     nullp = C.POINTER(C.c_float)()

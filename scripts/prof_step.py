@@ -33,3 +33,6 @@ if os.environ.get("MPN_TC_TIMELINE"):
     n1 = ["top", "ball query", "gather", "fence+sync", "issue L1", "wait(x2)", "ep(x2)", "fence+sync(x2)", "issue(x2)", "wait L3", "pool"]
     n = 128 * reps
     print("SA1 cycles/centroid (CTA0/WG0):", {k: int(v / n) for k, v in zip(n1, tl[16:27])}, "total", int(sum(tl[16:32]) / n))
+    ng = ["prologue", "wait loads", "fence+sync", "mma issue", "wait prev mma", "issue loads", "drain", "epilogue"]
+    k = max(tl[40], 1)
+    print("GEMM cycles per CTA-0 tile (all row-GEMM launches):", {a: int(v / k) for a, v in zip(ng, tl[32:40])}, "tiles", tl[40])

@@ -6,6 +6,9 @@ Run here only (``/root/reference`` does not exist on the GPU box):  python tests
   the ``has_collision`` reduction of ``mpinets/model.py:301-312`` on seeded random scenes.  ``geometrout`` is not
   installable here, so ``geometrout.primitive`` is stubbed with three empty classes (geometry.py only uses them
   for type annotations and the unused ``.geometrout()`` helpers).
+* ``loss_reference.npz`` -- ``mpinets/loss.py`` ``collision_loss`` and ``point_match_loss`` (the real functions, imported
+  with ``robofin`` / ``mpinets.utils`` stubbed: neither is touched by these two functions) on seeded scenes and points,
+  with ``torch.autograd`` gradients w.r.t. the input cloud.
 * ``fk_reference.npz``   -- the FK known-answer pair of ``interactive_demo/mpinets_ros/nodes/interaction_node.py:54-75``
   (parsed from the file, not retyped).
 """
@@ -34,6 +37,52 @@ def load_reference_geometry():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference_loss(geo):
+    """the real mpinets/loss.py; its module-level imports of robofin / mpinets.utils are satisfied by stubs"""
+    pkg = types.ModuleType("mpinets")
+    pkg.geometry = geo
+    pkg.utils = types.ModuleType("mpinets.utils")
+    rob = types.ModuleType("robofin"); pc = types.ModuleType("robofin.pointcloud"); pct = types.ModuleType("robofin.pointcloud.torch")
+    pct.FrankaSampler = type("FrankaSampler", (), {})
+    sys.modules.update({"mpinets": pkg, "mpinets.geometry": geo, "mpinets.utils": pkg.utils, "robofin": rob,
+                        "robofin.pointcloud": pc, "robofin.pointcloud.torch": pct})
+    spec = importlib.util.spec_from_file_location("ref_loss", os.path.join(REF, "mpinets", "loss.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def loss_fixtures(geo):
+    loss = load_reference_loss(geo)
+    out = {}
+    for tag, yaw_only in (("yaw", True), ("free", False)):
+        rng = np.random.RandomState(777 + yaw_only)
+        B, M1, M2, N = 5, 6, 4, 300
+        s = random_scenes(rng, B, M1, M2, yaw_only)
+        # points concentrated around the primitives so that many fall inside the 3 cm margin / inside the volumes
+        anchors = np.concatenate([s["cuboid_centers"], s["cylinder_centers"]], axis=1)
+        pick = rng.randint(anchors.shape[1], size=(B, N))
+        pts = (np.take_along_axis(anchors, pick[..., None], axis=1) + rng.normal(scale=0.25, size=(B, N, 3))).astype(np.float32)
+        tp = torch.from_numpy(pts).requires_grad_(True)
+        t = {k: torch.from_numpy(v) for k, v in s.items()}
+        val = loss.collision_loss(tp, t["cuboid_centers"], t["cuboid_dims"], t["cuboid_quats"], t["cylinder_centers"],
+                                  t["cylinder_radii"], t["cylinder_heights"], t["cylinder_quats"])
+        val.backward()
+        out.update({f"{tag}_{k}": v for k, v in s.items()})
+        out[f"{tag}_points"] = pts
+        out[f"{tag}_collision_loss"] = np.float32(val.item())
+        out[f"{tag}_collision_grad"] = tp.grad.numpy().copy()
+        other = (pts + rng.normal(scale=0.05, size=pts.shape)).astype(np.float32)
+        ta = torch.from_numpy(pts).requires_grad_(True)
+        pm = loss.point_match_loss(ta, torch.from_numpy(other))
+        pm.backward()
+        out[f"{tag}_other"] = other
+        out[f"{tag}_point_match_loss"] = np.float32(pm.item())
+        out[f"{tag}_point_match_grad"] = ta.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "loss_reference.npz"), **out)
+    print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if "loss" in k})
 
 
 def random_scenes(rng, B, M1, M2, yaw_only):
@@ -83,6 +132,8 @@ def main():
         radius = 0.06
         out[f"{tag}_has_collision_r006"] = torch.any(sq.reshape(B, -1) <= radius, dim=-1).numpy()  # model.py:309-311
     np.savez_compressed(os.path.join(HERE, "sdf_reference.npz"), **out)
+
+    loss_fixtures(geo)
 
     src = open(os.path.join(REF, "interactive_demo/mpinets_ros/nodes/interaction_node.py")).read()
 

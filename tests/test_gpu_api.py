@@ -126,8 +126,39 @@ def test_evaluator_surface(tables, oracle):
     assert len(g["success"]) == 12 and all(isinstance(v, bool) for v in g["success"])
     m = Evaluator.metrics(g)
     exp = oracle.evaluate(p, traj.cpu().numpy(), p["target"], tables)
-    assert m["total"] == 12 and abs(m["success"] - 100 * exp[:, 9].mean()) < 1e-9
-    assert abs(m["env collision"] - 100 * exp[:, 0].mean()) < 1e-9
+    assert m["total"] == 12 and abs(m["success"] - 100 * np.count_nonzero(exp[:, 9]) / 12) < 1e-9
+    assert abs(m["env collision"] - 100 * np.count_nonzero(exp[:, 0]) / 12) < 1e-9
     assert m["1 cm"] == 100.0                                  # joint-space interpolation ends exactly on the target
     ev.print_group_metrics()
     ev.print_overall_metrics()
+
+
+def test_loss_surface(tables, oracle):
+    """loss.py call patterns of model.py:222-236: container(y_hat, 7 scene tensors, supervision) -> two scalars that are
+    weighted, summed and back-propagated into the network output."""
+    from mpinets_b200 import loss as L
+    from mpinets_b200.runtime import get_engine
+    p = _problems(16)
+    sc = to_dev(p)
+    rng = np.random.default_rng(0)
+    y_hat = torch.from_numpy(rng.uniform(-0.8, 0.8, (16, 7)).astype(np.float32)).cuda().requires_grad_(True)
+    sup = (y_hat.detach() + 0.03).clamp(-1, 1)
+    container = L.CollisionAndBCLossContainer()
+    collision, point_match = container(y_hat, sc["cuboid_centers"], sc["cuboid_dims"], sc["cuboid_quats"], sc["cylinder_centers"],
+                                       sc["cylinder_radii"], sc["cylinder_heights"], sc["cylinder_quats"], sup)
+    assert collision.ndim == 0 and point_match.ndim == 0
+    total = 5.0 * collision + 1.0 * point_match        # jobconfig.yaml:24-25
+    total.backward()
+    ol, og = oracle.bc_collision_losses(p, y_hat.detach().cpu().numpy(), sup.cpu().numpy(), tables, get_engine().cfg.seed, 1024, 0.03, 5.0, 1.0)
+    assert abs(float(collision) - ol[0]) < 1e-6 and abs(float(point_match) - ol[1]) < 1e-6
+    assert np.abs(y_hat.grad.cpu().numpy() - og).max() < 2e-5 * np.abs(og).max() + 1e-8
+    # the standalone functions, differentiable w.r.t. the cloud (loss.py:31-94)
+    pc = torch.from_numpy(rng.uniform(-0.5, 1.0, (16, 200, 3)).astype(np.float32)).cuda().requires_grad_(True)
+    cl = L.collision_loss(pc, sc["cuboid_centers"], sc["cuboid_dims"], sc["cuboid_quats"], sc["cylinder_centers"], sc["cylinder_radii"],
+                          sc["cylinder_heights"], sc["cylinder_quats"])
+    pm = L.point_match_loss(pc, pc.detach() + 0.01)
+    (cl + pm).backward()
+    oc, ogc = oracle.collision_loss(p, pc.detach().cpu().numpy())
+    opm, ogp = oracle.point_match_loss(pc.detach().cpu().numpy(), (pc.detach() + 0.01).cpu().numpy())
+    assert abs(float(cl) - oc) < 1e-6 and abs(float(pm) - opm) < 1e-6
+    assert np.abs(pc.grad.cpu().numpy() - (ogc + ogp)).max() < 1e-5 * np.abs(ogc + ogp).max()

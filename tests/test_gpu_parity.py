@@ -510,3 +510,54 @@ def test_evaluate_after_rollout(engine_w, oracle, tables):
     assert (ev[:, 10] == T + 1).all()
     exp = oracle.evaluate(p, traj.cpu().numpy(), p["target"], tables)
     assert np.array_equal(ev[:, [0, 1, 2, 3, 8, 9, 10, 11]], exp[:, [0, 1, 2, 3, 8, 9, 10, 11]])
+
+
+# ----------------------------------------------------------------------------- losses (loss.py:31-166)
+def test_collision_and_point_match_loss_match_reference_fixture(engine, oracle):
+    """CUDA collision_loss / point_match_loss against the values and autograd gradients of the REAL mpinets/loss.py
+    (tests/golden/loss_reference.npz) and against the oracle"""
+    from mpinets_b200 import scenes
+    from mpinets_b200.engine import Engine
+    g = np.load(os.path.join(HERE, "golden", "loss_reference.npz"))
+    M1, M2 = g["yaw_cuboid_centers"].shape[1], g["yaw_cylinder_centers"].shape[1]
+    eng = Engine(max_cuboids=M1, max_cylinders=M2)       # the fixture's scenes have 6 + 4 primitive rows
+    for tag in ("yaw", "free"):
+        sc = {k: g[f"{tag}_{k}"] for k in scenes.SCENE_KEYS}
+        pts = g[f"{tag}_points"]
+        loss, grad = eng.collision_loss(to_dev(sc), torch.from_numpy(pts).cuda(), 0.03, need_grad=True)
+        ref_g = g[f"{tag}_collision_grad"]
+        assert abs(float(loss) - float(g[f"{tag}_collision_loss"])) < 5e-7
+        gh = grad.cpu().numpy()
+        assert np.array_equal(gh != 0, ref_g != 0)                       # same points inside the margin
+        assert np.abs(gh - ref_g).max() < 1e-5 * np.abs(ref_g).max()
+        oval, ograd = oracle.collision_loss(sc, pts)
+        assert abs(float(loss) - oval) < 5e-7 and np.abs(gh - ograd).max() < 1e-5 * np.abs(ograd).max()
+        loss2, _ = eng.collision_loss(to_dev(sc), torch.from_numpy(pts).cuda(), 0.03, need_grad=False)
+        assert torch.equal(loss, loss2)                                  # deterministic reduction
+        pl, pg = eng.point_match_loss(torch.from_numpy(pts).cuda(), torch.from_numpy(g[f"{tag}_other"]).cuda(), need_grad=True)
+        assert abs(float(pl) - float(g[f"{tag}_point_match_loss"])) < 1e-6
+        assert np.abs(pg.cpu().numpy() - g[f"{tag}_point_match_grad"]).max() < 1e-9
+
+
+def test_bc_collision_losses_match_oracle(engine, oracle, tables):
+    """CollisionAndBCLossContainer.__call__ (loss.py:111-166) on config-4 scenes: both losses and the joint-space gradient"""
+    B = 48
+    p = _problems(4, B)
+    rng = np.random.default_rng(3)
+    qi = rng.uniform(-0.9, 0.9, (B, 7)).astype(np.float32)
+    qi[: B // 2] = oracle.normalize(p["q0"][: B // 2], tables.joint_limits)      # half the batch at the scene's own start poses
+    qt = np.clip(qi + rng.normal(scale=0.05, size=qi.shape), -1, 1).astype(np.float32)
+    for wc, wb in ((5.0, 1.0), (1.0, 0.0), (0.0, 1.0)):
+        losses, grad = engine.bc_collision_losses(to_dev(p), torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda(), 1024, 0.03, wc, wb,
+                                                  need_grad=True)
+        ol, og = oracle.bc_collision_losses(p, qi, qt, tables, engine.cfg.seed, 1024, 0.03, wc, wb)
+        assert np.abs(losses.cpu().numpy() - ol).max() < 1e-6 * max(1.0, float(np.abs(ol).max())) + 2e-7
+        gh = grad.cpu().numpy()
+        assert np.abs(gh - og).max() < 2e-5 * np.abs(og).max() + 1e-8
+    # the fixed cloud the kernel uses is the documented subset: losses equal the standalone kernels on oracle-built clouds
+    xi, _ = oracle.fixed_robot_points(oracle.unnormalize(qi, tables.joint_limits), tables, 1024, engine.cfg.seed)
+    xt, _ = oracle.fixed_robot_points(oracle.unnormalize(qt, tables.joint_limits), tables, 1024, engine.cfg.seed)
+    l_c, _ = engine.collision_loss(to_dev(p), torch.from_numpy(xi).cuda())
+    l_p, _ = engine.point_match_loss(torch.from_numpy(xi).cuda(), torch.from_numpy(xt).cuda())
+    l2, _ = engine.bc_collision_losses(to_dev(p), torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda())
+    assert abs(float(l_c) - float(l2[0])) < 1e-6 and abs(float(l_p) - float(l2[1])) < 1e-6

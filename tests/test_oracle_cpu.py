@@ -411,3 +411,66 @@ def test_oracle_evaluate_region_against_reference_sdf(oracle, tables):
         fin_spec = oracle.fk(traj[:, -1])[1][:, :3, 3]
         sdf = oracle.sdf_points(sc, fin_spec[:, None, :], quirk=False, which=1)[:, 0]
         assert ((sdf <= 0) == (ev[:, 8] > 0)).all()
+
+
+# ----------------------------------------------------------------------------- losses (loss.py:31-166)
+def test_oracle_losses_match_reference_loss_py(oracle):
+    """collision_loss / point_match_loss values and autograd gradients produced by the REAL mpinets/loss.py
+    (tests/golden/make_golden.py -> loss_reference.npz)"""
+    g = np.load(os.path.join(HERE, "golden", "loss_reference.npz"))
+    for tag in ("yaw", "free"):
+        sc = {k: g[f"{tag}_{k}"] for k in scenes.SCENE_KEYS}
+        val, grad = oracle.collision_loss(sc, g[f"{tag}_points"], margin=0.03, quirk=True)
+        assert abs(val - float(g[f"{tag}_collision_loss"])) < 2e-7
+        ref = g[f"{tag}_collision_grad"]
+        assert (ref != 0).any(axis=-1).sum() > 50                         # plenty of points inside the margin
+        assert np.array_equal(grad != 0, ref != 0)                        # identical active set
+        assert np.abs(grad - ref).max() < 1e-5 * np.abs(ref).max()      # fp32 autograd vs closed form
+        val, grad = oracle.point_match_loss(g[f"{tag}_points"], g[f"{tag}_other"])
+        assert abs(val - float(g[f"{tag}_point_match_loss"])) < 1e-7
+        assert np.abs(grad - g[f"{tag}_point_match_grad"]).max() < 1e-9
+
+
+def test_oracle_fixed_robot_cloud_properties(oracle, tables):
+    """FrankaSampler(num_fixed_points=1024, with_base_link=False) stand-in: fixed, duplicate-free, no base-link rows,
+    and equal to FK applied to those table rows"""
+    q = np.array([[0.1, -0.5, 0.2, -2.0, 0.3, 1.5, 0.7], [-1.0, 0.4, 1.1, -1.2, -0.6, 2.2, -0.3]], np.float32)
+    pts, idx = oracle.fixed_robot_points(q, tables, 1024, 0x4D50694E)
+    pts2, idx2 = oracle.fixed_robot_points(q[::-1].copy(), tables, 1024, 0x4D50694E)
+    assert np.array_equal(idx, idx2) and np.array_equal(pts[0], pts2[1])
+    assert len(set(idx.tolist())) == 1024 and (tables.link_ids[idx] != 0).all()
+    frames, _ = oracle.fk(q)
+    for b in range(2):
+        F = frames[b][tables.link_ids[idx]]
+        ref = np.einsum("nij,nj->ni", F[:, :, :3].astype(np.float64), tables.link_points[idx].astype(np.float64)) + F[:, :, 3]
+        assert np.abs(pts[b] - ref).max() < 1e-6
+
+
+def test_oracle_bc_collision_losses_gradient(oracle, tables):
+    """CollisionAndBCLossContainer (loss.py:111-166): values equal the two standalone losses on the fixed clouds; the analytic
+    gradient w.r.t. input_normalized matches central finite differences of the loss itself"""
+    p = scenes.config_problems(4, 6)
+    seed = 0x4D50694E
+    rng = np.random.default_rng(3)
+    qi = rng.uniform(-0.9, 0.9, (6, 7)).astype(np.float32)
+    qt = np.clip(qi + rng.normal(scale=0.05, size=qi.shape), -1, 1).astype(np.float32)
+    losses, grad = oracle.bc_collision_losses(p, qi, qt, tables, seed, w_collision=5.0, w_bc=1.0)
+    xi, _ = oracle.fixed_robot_points(oracle.unnormalize(qi, tables.joint_limits), tables, 1024, seed)
+    xt, _ = oracle.fixed_robot_points(oracle.unnormalize(qt, tables.joint_limits), tables, 1024, seed)
+    assert abs(losses[0] - oracle.collision_loss(p, xi)[0]) < 1e-7
+    assert abs(losses[1] - oracle.point_match_loss(xi, xt)[0]) < 1e-7
+
+    def total(qn):
+        l, _ = oracle.bc_collision_losses(p, qn.astype(np.float32), qt, tables, seed, w_collision=5.0, w_bc=1.0)
+        return 5.0 * float(l[0]) + float(l[1])
+    eps = 5e-4
+    fd = np.zeros((6, 7))
+    for b in range(6):
+        for j in range(7):
+            d = np.zeros_like(qi); d[b, j] = eps
+            fd[b, j] = (total(qi + d) - total(qi - d)) / (2 * eps)
+    rel = np.linalg.norm(fd - grad, axis=1) / np.linalg.norm(grad, axis=1)
+    assert rel.max() < 0.02          # fp32 losses with |.| / hinge kinks differenced at 5e-4: < 1 % noise; a wrong Jacobian term is O(1)
+    # the collision part on its own is non-trivial for at least one of the problems
+    _, gc = oracle.bc_collision_losses(p, qi, qt, tables, seed, w_collision=1.0, w_bc=0.0)
+    assert (np.abs(gc).max(axis=1) > 1e-3).sum() >= 1
