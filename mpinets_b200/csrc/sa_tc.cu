@@ -195,12 +195,6 @@ __device__ __forceinline__ uint32_t cvt_relu_bf16x2(float first, float second) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
   return d;
 }
-// one lane of a converged warp (the MMA issuer); the enclosing branch must be warp-uniform
-__device__ __forceinline__ bool elect_one() {
-  uint32_t p;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
-  return p != 0;
-}
 // TMEM [128 lanes][NC cols] fp32 (bias already inside the accumulator) -> relu -> bf16 -> chunks 0..NC/8-1 of row `row`
 template <int NC, int KCX>
 __device__ __forceinline__ void epilogue_pack_relu(uint32_t taddr, uint8_t* X, int row) {

@@ -150,7 +150,7 @@ def test_loss_surface(tables, oracle):
     total = 5.0 * collision + 1.0 * point_match        # jobconfig.yaml:24-25
     total.backward()
     ol, og = oracle.bc_collision_losses(p, y_hat.detach().cpu().numpy(), sup.cpu().numpy(), tables, get_engine().cfg.seed, 1024, 0.03, 5.0, 1.0)
-    assert abs(float(collision) - ol[0]) < 1e-6 and abs(float(point_match) - ol[1]) < 1e-6
+    assert abs(collision.item() - ol[0]) < 1e-6 and abs(point_match.item() - ol[1]) < 1e-6
     assert np.abs(y_hat.grad.cpu().numpy() - og).max() < 2e-5 * np.abs(og).max() + 1e-8
     # the standalone functions, differentiable w.r.t. the cloud (loss.py:31-94)
     pc = torch.from_numpy(rng.uniform(-0.5, 1.0, (16, 200, 3)).astype(np.float32)).cuda().requires_grad_(True)
@@ -160,5 +160,5 @@ def test_loss_surface(tables, oracle):
     (cl + pm).backward()
     oc, ogc = oracle.collision_loss(p, pc.detach().cpu().numpy())
     opm, ogp = oracle.point_match_loss(pc.detach().cpu().numpy(), (pc.detach() + 0.01).cpu().numpy())
-    assert abs(float(cl) - oc) < 1e-6 and abs(float(pm) - opm) < 1e-6
+    assert abs(cl.item() - oc) < 1e-6 and abs(pm.item() - opm) < 1e-6
     assert np.abs(pc.grad.cpu().numpy() - (ogc + ogp)).max() < 1e-5 * np.abs(ogc + ogp).max()
