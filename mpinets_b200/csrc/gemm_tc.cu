@@ -302,8 +302,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   if (!ok && (tid & 31) == 0) atomicExch(err, 1);
 
-  // ---- epilogue (identical to the cp.async variant): warp q = warp & 3 owns TMEM lanes 32q.., column half h = warp >> 2
+  // ---- epilogue: warp q = warp & 3 owns TMEM lanes 32q.., column half h = warp >> 2.  A thread holds one output ROW, so
+  // storing straight from registers would touch 32 different rows per instruction (32 half-used sectors, ~8k cycles per
+  // tile).  Rows therefore go through the (now idle) operand ring, 16-byte chunks XOR-swizzled by row so that both the
+  // row-per-thread writes and the row-per-warp reads are conflict-free, and leave as full 512-byte row segments.
   const int q = warp & 3, h = warp >> 2, row = q * 32 + (tid & 31);
+  constexpr int ROW_CHUNKS = EPI == EPI_F32 ? 64 : 32;   // 16-byte chunks per 256-column output row
 #pragma unroll 1
   for (int sub = 0; sub < 2; ++sub) {
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + sub * 256 + h * 128;
@@ -316,27 +320,26 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int nl = h * 128 + c0;
       const float4* bt = reinterpret_cast<const float4*>(sbias + nl);
       if (EPI == EPI_RELU_BF16) {
-        if (m < M) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)m * ldc + n0 + nl;
+        uint8_t* rowp = smem + (size_t)row * (ROW_CHUNKS * 16);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const float4 b0 = bt[j / 4], b1 = bt[j / 4 + 1];
-            *reinterpret_cast<uint4*>(o + j) =
-                make_uint4(cvt_relu_pack(__uint_as_float(v[j]) + b0.x, __uint_as_float(v[j + 1]) + b0.y),
-                           cvt_relu_pack(__uint_as_float(v[j + 2]) + b0.z, __uint_as_float(v[j + 3]) + b0.w),
-                           cvt_relu_pack(__uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y),
-                           cvt_relu_pack(__uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w));
-          }
+        for (int j = 0; j < 32; j += 8) {
+          const float4 b0 = bt[j / 4], b1 = bt[j / 4 + 1];
+          const int chunk = (nl + j) >> 3;
+          *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(cvt_relu_pack(__uint_as_float(v[j]) + b0.x, __uint_as_float(v[j + 1]) + b0.y),
+                         cvt_relu_pack(__uint_as_float(v[j + 2]) + b0.z, __uint_as_float(v[j + 3]) + b0.w),
+                         cvt_relu_pack(__uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y),
+                         cvt_relu_pack(__uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w));
         }
       } else if (EPI == EPI_F32) {
-        if (m < M) {
-          float* o = reinterpret_cast<float*>(Cout) + (size_t)m * ldc + n0 + nl;
+        uint8_t* rowp = smem + (size_t)row * (ROW_CHUNKS * 16);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bb = bt[j / 4];
-            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y,
-                                                            __uint_as_float(v[j + 2]) + bb.z, __uint_as_float(v[j + 3]) + bb.w);
-          }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = bt[j / 4];
+          const int chunk = (nl + j) >> 2;
+          *reinterpret_cast<float4*>(rowp + ((chunk ^ (row & 7)) << 4)) =
+              make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y, __uint_as_float(v[j + 2]) + bb.z,
+                          __uint_as_float(v[j + 3]) + bb.w);
         }
       } else {
         int keep = 0;
@@ -350,8 +353,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         red[q][nl + (tid & 31)] = keep;
       }
     }
+    __syncthreads();
     if (EPI == EPI_MAXPOOL) {
-      __syncthreads();
       const int prob = blockIdx.y * 2 + sub;
       if (prob * 128 < M) {
         const int mi = max(max(red[0][tid], red[1][tid]), max(red[2][tid], red[3][tid]));
@@ -359,8 +362,23 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)prob * ldc + n0;
         o[tid] = __float2bfloat16_rn(fmaxf(__int_as_float(bits) + sbias[tid], 0.f));
       }
-      __syncthreads();
+    } else {
+      // warp w streams rows w, w + 8, ... of this 128-row sub-tile: one row = ROW_CHUNKS x 16 B, a lane per chunk
+      const int lane = tid & 31;
+      constexpr int ESZ = EPI == EPI_F32 ? 4 : 2;
+      for (int rr = warp; rr < 128; rr += 8) {
+        const int mr = m0 + sub * 128 + rr;
+        if (mr >= M) break;
+        const uint8_t* rowp = smem + (size_t)rr * (ROW_CHUNKS * 16);
+        uint8_t* o = reinterpret_cast<uint8_t*>(Cout) + ((size_t)mr * ldc + n0) * ESZ;
+#pragma unroll
+        for (int cc = 0; cc < ROW_CHUNKS; cc += 32) {
+          const int chunk = cc + lane;
+          *reinterpret_cast<uint4*>(o + chunk * 16) = *reinterpret_cast<const uint4*>(rowp + ((chunk ^ (rr & 7)) << 4));
+        }
+      }
     }
+    __syncthreads();
   }
   tc_fence_before();
   __syncthreads();

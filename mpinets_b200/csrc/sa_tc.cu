@@ -1014,9 +1014,13 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
   }
   *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
   *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KC)) = make_uint4(0u, 0u, 0u, 0u);
+  __shared__ int round_ctr[1 + 8];
+  int* next_round = round_ctr;
+  int* rsel = round_ctr + 1;
   if (threadIdx.x == 0) {
     for (int i = 0; i < SA1W_NWG; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
+    *next_round = SA1W_NWG;
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();
@@ -1106,7 +1110,10 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
     }
   };
 
-  for (int base = g * 4; base < SA1_NPOINT && ok; base += SA1W_NWG * 4) {
+  // rounds of 4 centroids are handed out dynamically (shared counter): ball-query cost varies with the local point density,
+  // and with a static stride the groups finish up to several rounds apart and idle at the CTA's final barrier
+  for (int round = g; round * 4 < SA1_NPOINT && ok;) {
+    const int base = round * 4;
     if (base + wq < SA1_NPOINT) warp_ball_query(base + wq);
     wg_sync(g);
     float4 pn = __ldg(cl + lists[t]);
@@ -1165,7 +1172,9 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
         out_bf16[((size_t)b * SA1_NPOINT + j) * 64 + t] = __float2bfloat16_rn(fmaxf(__int_as_float(m), 0.f));
       }
     }
+    if (t == 0) rsel[g] = atomicAdd(next_round, 1);
     wg_sync(g);   // the lists are rewritten by the next round
+    round = rsel[g];
   }
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
