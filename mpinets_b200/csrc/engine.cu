@@ -244,6 +244,7 @@ int mpn_ctx_destroy(mpn_ctx* c) {
   if (c->ws.tc_scratch) cudaFree(c->ws.tc_scratch);
   if (c->link_table4) cudaFree(c->link_table4);
   if (c->robot_sel4) cudaFree(c->robot_sel4);
+  if (c->robot_sel_steps) cudaFree(c->robot_sel_steps);
   if (c->loss_partial) cudaFree(c->loss_partial);
   delete c;
   return MPN_OK;
@@ -585,12 +586,13 @@ int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene,
   MPN_CHECK_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)B, s));
   if ((r = launch_fk(c, s, q0, B, w.frames, w.eef))) return r;
   if (check_every_step && (r = launch_sweep(c, s, *scene, B, traj, 1, stride, 0, 0, w.flags, w.first_step, w.frames))) return r;
+  if ((r = launch_robot_subsets(c, s, c->cfg.n_robot, 1u, T))) return r;   // the per-step robot subsets, all at once
   for (int i = 1; i <= T; ++i) {
     if ((r = policy_forward(c, s, precision, cloud, w.qn, B, N, w.dq))) return r;
     { StageTimer t(c, s, MPN_ST_UPDATE);
       if ((r = launch_step_update(c, s, B, w.dq, w.qn, w.qu, target, w.done, early_exit, traj, stride, w.frames, w.eef, nullptr, i))) return r; }
     { StageTimer t(c, s, MPN_ST_SAMPLE_ROBOT);
-      if ((r = launch_sample_robot(c, s, w.frames, B, c->cfg.n_robot, (uint32_t)i, cloud, N))) return r; }
+      if ((r = launch_sample_robot_slab(c, s, w.frames, B, c->cfg.n_robot, i - 1, cloud, N))) return r; }
     if (check_every_step) {
       StageTimer t(c, s, MPN_ST_SWEEP);
       if ((r = launch_sweep(c, s, *scene, B, traj + (size_t)i * 7, 1, stride, i, 1, w.flags, w.first_step, w.frames))) return r;

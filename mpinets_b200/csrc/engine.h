@@ -88,6 +88,7 @@ struct mpn_ctx {
   int P = 0; float* link_points = nullptr; int32_t* link_ids = nullptr;
   float* link_table4 = nullptr;  // [P] float4 (x, y, z, link id bits): one gather per robot row
   float* robot_sel4 = nullptr;   // [P] float4: this step's permuted subset of link_table4 (shared by the whole batch)
+  float* robot_sel_steps = nullptr; size_t robot_sel_steps_cap = 0;   // [steps][n] float4 slabs of a whole rollout
   int n_base_points = 0;         // leading link-0 rows of the table (FrankaSampler(with_base_link=False) skips them)
   float* loss_partial = nullptr; size_t loss_partial_cap = 0;   // per-CTA partial sums of the loss kernels
   int Pe = 0; float* ee_points = nullptr;
@@ -122,6 +123,8 @@ struct StageTimer {
 // ---- geometry.cu
 int launch_fk(mpn_ctx* c, cudaStream_t s, const float* q, int B, float* frames, float* eef);
 int launch_sample_robot(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, uint32_t step, float* cloud, int rows);
+int launch_robot_subsets(mpn_ctx* c, cudaStream_t s, int n, uint32_t step0, int count);
+int launch_sample_robot_slab(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, int slab, float* cloud, int rows);
 int pack_link_table(mpn_ctx* c);
 int launch_spheres(mpn_ctx* c, cudaStream_t s, const float* frames, int B, float* centers);
 int launch_normalize(mpn_ctx* c, cudaStream_t s, const float* in, int n, float* out, bool unnormalize);

@@ -51,13 +51,14 @@ __global__ void pack_link_table_kernel(const float* __restrict__ lp, const int32
 // permutation is evaluated once per step into `sel` (n float4 rows, 32 KB: L1/L2 resident) instead of once per problem;
 // the per-problem kernel is then a pure streaming pass: coalesced 16-byte reads of `sel`, the link frame from shared
 // memory, coalesced 16-byte row writes.
-__global__ void robot_subset_kernel(int n, int P, const float4* __restrict__ table, uint32_t seed_lo, uint32_t seed_hi, uint32_t step,
+__global__ void robot_subset_kernel(int n, int P, const float4* __restrict__ table, uint32_t seed_lo, uint32_t seed_hi, uint32_t step0,
                                     float4* __restrict__ sel) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  const uint32_t step = step0 + blockIdx.y;     // blockIdx.y: consecutive steps of a rollout, one [n] slab each
   uint32_t key[4];
   philox4x32(0u, step, STREAM_ROBOT_PERM, 0u, seed_lo, seed_hi, key);
-  sel[j] = __ldg(table + feistel_perm((uint32_t)j, (uint32_t)P, feistel_bits((uint32_t)P) / 2, key));
+  sel[(size_t)blockIdx.y * n + j] = __ldg(table + feistel_perm((uint32_t)j, (uint32_t)P, feistel_bits((uint32_t)P) / 2, key));
 }
 
 __global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restrict__ frames, int n, const float4* __restrict__ sel,
@@ -90,10 +91,36 @@ __global__ void __launch_bounds__(256) sample_robot_kernel(const float* __restri
 
 int launch_sample_robot(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, uint32_t step, float* cloud, int rows) {
   MPN_REQUIRE(n <= c->P, "sample_robot: %d points requested, the link table has %d", n, c->P);
-  robot_subset_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, c->P, reinterpret_cast<const float4*>(c->link_table4), (uint32_t)c->cfg.seed,
-                                                     (uint32_t)(c->cfg.seed >> 32), step, reinterpret_cast<float4*>(c->robot_sel4));
+  robot_subset_kernel<<<dim3((n + 255) / 256, 1), 256, 0, s>>>(n, c->P, reinterpret_cast<const float4*>(c->link_table4), (uint32_t)c->cfg.seed,
+                                                              (uint32_t)(c->cfg.seed >> 32), step, reinterpret_cast<float4*>(c->robot_sel4));
   sample_robot_kernel<<<B, 256, 0, s>>>(frames, n, reinterpret_cast<const float4*>(c->robot_sel4), (float4*)cloud, rows);
   c->launches += 2;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// rollout form: the subsets of steps step0 .. step0 + count - 1 in ONE launch (they depend on the step index only), then one
+// streaming kernel per step reading its slab
+int launch_robot_subsets(mpn_ctx* c, cudaStream_t s, int n, uint32_t step0, int count) {
+  MPN_REQUIRE(n <= c->P, "sample_robot: %d points requested, the link table has %d", n, c->P);
+  const size_t need = (size_t)count * n;
+  if (c->robot_sel_steps_cap < need) {
+    if (c->robot_sel_steps) cudaFree(c->robot_sel_steps);
+    c->robot_sel_steps = nullptr; c->robot_sel_steps_cap = 0;
+    MPN_CHECK_CUDA(cudaMalloc(&c->robot_sel_steps, need * sizeof(float4)));
+    c->robot_sel_steps_cap = need;
+  }
+  robot_subset_kernel<<<dim3((n + 255) / 256, count), 256, 0, s>>>(n, c->P, reinterpret_cast<const float4*>(c->link_table4),
+                                                                  (uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32), step0,
+                                                                  reinterpret_cast<float4*>(c->robot_sel_steps));
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+int launch_sample_robot_slab(mpn_ctx* c, cudaStream_t s, const float* frames, int B, int n, int slab, float* cloud, int rows) {
+  sample_robot_kernel<<<B, 256, 0, s>>>(frames, n, reinterpret_cast<const float4*>(c->robot_sel_steps) + (size_t)slab * n, (float4*)cloud, rows);
+  c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
 }

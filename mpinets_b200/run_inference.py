@@ -1,0 +1,53 @@
+"""Batched counterpart of ``mpinets/run_inference.py`` (``calculate_metrics``, run_inference.py:426-516): every problem of a
+``ProblemSet`` is stepped in lock-step on the GPU (``rollout_until_success`` semantics: at most 150 steps, per-problem stop at
+1 cm / 15 degrees, run_inference.py:137-191) and evaluated by the device-side ``Evaluator``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .metrics import Evaluator
+from .model import MAX_ROLLOUT_LENGTH, PRECISIONS, MotionPolicyNetwork
+from .mpinets_types import PlanningProblem, ProblemSet, flatten_problem_set, problems_to_soa
+from .scenes import SCENE_KEYS
+
+
+def run_problems(mdl: MotionPolicyNetwork, problems: Sequence[PlanningProblem], device: Optional[torch.device] = None,
+                 max_steps: int = MAX_ROLLOUT_LENGTH, dt: float = 0.08, evaluator: Optional[Evaluator] = None,
+                 problem0: int = 0) -> Dict[str, torch.Tensor]:
+    """clouds (make_point_cloud_from_primitives, run_inference.py:93-134) -> rollout_until_success -> evaluate_trajectory
+    for the whole list at once.  Returns the trajectories, the number of poses of each, and the 16-column evaluation table."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    soa = problems_to_soa(problems)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+    scene = {k: dev(soa[k]) for k in SCENE_KEYS}
+    q0, target = dev(soa["q0"]), dev(soa["target"])
+    eng = mdl.sync_engine(device)
+    cloud = eng.build_cloud(scene, q0, target, problem0=problem0)
+    traj, metrics = eng.rollout(scene, cloud, q0, target, max_steps, early_exit=True, precision=PRECISIONS[mdl.precision])
+    num_poses = (metrics[:, 2].to(torch.int32) + 1).contiguous()          # MPN_M_STEPS + the start configuration
+    ev = evaluator or Evaluator(eng)
+    table = ev.evaluate_trajectories(traj, dt, target, scene, target_volume={k: dev(v) for k, v in soa["target_volume"].items()},
+                                     target_negative_volumes={k: dev(v) for k, v in soa["negative_volumes"].items()},
+                                     num_poses=num_poses)
+    return dict(trajectories=traj, num_poses=num_poses, eval=table, rollout_metrics=metrics)
+
+
+def calculate_metrics(mdl: MotionPolicyNetwork, problem_set: ProblemSet, device: Optional[torch.device] = None,
+                      max_steps: int = MAX_ROLLOUT_LENGTH) -> Evaluator:
+    """run_inference.calculate_metrics (run_inference.py:426-516): one metric group per (environment, problem type)"""
+    ev = Evaluator()
+    flat = flatten_problem_set(problem_set)
+    groups: Dict[str, List[int]] = {}
+    for i, (env, kind, _) in enumerate(flat):
+        groups.setdefault(f"{env}, {kind}", []).append(i)
+    offset = 0
+    for key, idx in groups.items():
+        ev.create_new_group(key)
+        run_problems(mdl, [flat[i][2] for i in idx], device, max_steps, evaluator=ev, problem0=offset)
+        offset += len(idx)
+    return ev

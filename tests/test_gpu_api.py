@@ -162,3 +162,22 @@ def test_loss_surface(tables, oracle):
     opm, ogp = oracle.point_match_loss(pc.detach().cpu().numpy(), (pc.detach() + 0.01).cpu().numpy())
     assert abs(cl.item() - oc) < 1e-6 and abs(pm.item() - opm) < 1e-6
     assert np.abs(pc.grad.cpu().numpy() - (ogc + ogp)).max() < 1e-5 * np.abs(ogc + ogp).max()
+
+
+def test_run_inference_surface(state_dict):
+    """run_inference.calculate_metrics (run_inference.py:426-516) over a ProblemSet of PlanningProblem records: clouds,
+    rollout_until_success semantics and evaluation for every group, on the device"""
+    from mpinets_b200 import mpinets_types as T
+    from mpinets_b200.model import MotionPolicyNetwork
+    from mpinets_b200.run_inference import calculate_metrics, run_problems
+    probs = T.soa_to_problems(_problems(6))
+    mdl = MotionPolicyNetwork(precision="bf16")
+    mdl.load_state_dict(state_dict)
+    out = run_problems(mdl, probs, max_steps=4)
+    assert out["trajectories"].shape == (6, 5, 7) and out["eval"].shape == (6, 16)
+    assert (out["num_poses"] >= 2).all() and (out["num_poses"] <= 5).all()
+    assert torch.equal(out["eval"][:, 10].to(torch.int32), out["num_poses"])
+    ev = calculate_metrics(mdl, {"tabletop": {"task_oriented": probs[:4]}, "cubby": {"neutral_start": probs[4:]}}, max_steps=3)
+    assert list(ev.groups) == ["tabletop, task_oriented", "cubby, neutral_start"]
+    assert len(ev.groups["tabletop, task_oriented"]["success"]) == 4 and len(ev.groups["cubby, neutral_start"]["success"]) == 2
+    ev.print_overall_metrics()

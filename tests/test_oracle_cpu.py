@@ -474,3 +474,32 @@ def test_oracle_bc_collision_losses_gradient(oracle, tables):
     # the collision part on its own is non-trivial for at least one of the problems
     _, gc = oracle.bc_collision_losses(p, qi, qt, tables, seed, w_collision=1.0, w_bc=0.0)
     assert (np.abs(gc).max(axis=1) > 1e-3).sum() >= 1
+
+
+# ----------------------------------------------------------------------------- PlanningProblem -> SoA (mpinets_types.py:34-48)
+def test_planning_problem_records_to_soa():
+    from mpinets_b200 import mpinets_types as T
+    p = scenes.config_problems(4, 7)
+    probs = T.soa_to_problems(p)
+    assert all(isinstance(x, T.PlanningProblem) for x in probs) and len(probs[0].obstacles) > 0
+    probs[2].target_negative_volumes = [T.Cuboid([0.5, 0, 0.3], [0.2, 0.2, 0.2]), T.Cylinder([0.4, 0.1, 0.2], 0.05, 0.3)]
+    probs[3].target_volume = T.Cylinder(probs[3].target.xyz, 0.1, 0.2)
+    s = T.problems_to_soa(probs)
+    assert np.array_equal(s["q0"], p["q0"]) and np.abs(s["target"] - p["target"]).max() < 1e-6
+    for b in range(7):   # the valid primitives survive in order; padding rows are zero-volume with unit quaternions
+        for fam, dimkey in (("cuboid", "cuboid_dims"), ("cylinder", "cylinder_radii")):
+            keep_a = ~np.isclose(p[dimkey][b].reshape(p[dimkey].shape[1], -1), 0).any(axis=1)
+            keep_b = ~np.isclose(s[dimkey][b].reshape(s[dimkey].shape[1], -1), 0).any(axis=1)
+            if fam == "cylinder":
+                keep_a &= ~np.isclose(p["cylinder_heights"][b, :, 0], 0); keep_b &= ~np.isclose(s["cylinder_heights"][b, :, 0], 0)
+            assert np.allclose(p[f"{fam}_centers"][b][keep_a], s[f"{fam}_centers"][b][keep_b])
+            assert np.allclose(p[f"{fam}_quats"][b][keep_a], s[f"{fam}_quats"][b][keep_b], atol=1e-6)
+            assert (s[f"{fam}_quats"][b][~keep_b] == np.array([1, 0, 0, 0], np.float32)).all()
+    assert s["negative_volumes"]["cuboid_dims"].shape == (7, 1, 3) and s["negative_volumes"]["cylinder_radii"].shape == (7, 1, 1)
+    assert s["negative_volumes"]["cylinder_radii"][2, 0, 0] == np.float32(0.05) and s["negative_volumes"]["cuboid_dims"][0].max() == 0
+    assert s["target_volume"]["cylinder_radii"][3, 0, 0] == np.float32(0.1) and s["target_volume"]["cuboid_dims"][3].max() == 0
+    with pytest.raises(ValueError):
+        T.primitives_to_soa([[T.Cuboid([0, 0, 0], [1, 1, 1])] * 3], 2, 2)
+    ps = {"tabletop": {"task_oriented": probs[:3], "neutral_start": probs[3:5]}, "cubby": {"task_oriented": probs[5:]}}
+    flat = T.flatten_problem_set(ps)
+    assert [(e, k) for e, k, _ in flat] == [("tabletop", "task_oriented")] * 3 + [("tabletop", "neutral_start")] * 2 + [("cubby", "task_oriented")] * 2
