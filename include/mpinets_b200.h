@@ -166,6 +166,12 @@ int mpn_evaluate(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, cons
                  const int32_t* num_poses, const float* target, const mpn_scene* target_volume, int tv_cuboids,
                  int tv_cylinders, const mpn_scene* negative_volumes, int nv_cuboids, int nv_cylinders, float* eval);
 
+/* third_party/sparc.py:48-140 (spectral arc length; Evaluator.calculate_smoothness, metrics.py:387-409) for B speed profiles:
+ * movement [B][n_max] (num_samples i32 [B] optional: valid prefix per row), fs sampling frequency; the reference's
+ * defaults are padlevel 4, fc 10.0, amp_th 0.05.  sal [B]; 0 for an all-zero profile (sparc.py:95-97). */
+int mpn_sparc(mpn_ctx* ctx, void* stream, int B, int n_max, const float* movement, const int32_t* num_samples, float fs,
+              int padlevel, float fc, float amp_th, float* sal);
+
 /* ---- training losses (mpinets/loss.py), forward value + analytic gradient; all pointers are device pointers ----------
  * collision_loss (loss.py:47-94): loss[0] = mean over B*N of max(0, margin - sdf(points[b][n])) with the scene sdf of
  * geometry.py:238-288,456-507 (F.hinge_embedding_loss with target -1; the reference uses margin 0.03).

@@ -516,6 +516,14 @@ int mpn_evaluate(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const 
                          negative_volumes ? *negative_volumes : none, nv_cuboids, nv_cylinders, eval);
 }
 
+int mpn_sparc(mpn_ctx* c, void* stream, int B, int n_max, const float* movement, const int32_t* num_samples, float fs, int padlevel,
+              float fc, float amp_th, float* sal) {
+  REQ_CTX(c);
+  MPN_REQUIRE(movement && sal && B >= 0 && n_max >= 1 && padlevel >= 0 && fs > 0.f, "mpn_sparc: bad arguments");
+  if (B == 0) return MPN_OK;
+  return launch_sparc(c, (cudaStream_t)stream, B, n_max, movement, num_samples, fs, padlevel, fc, amp_th, sal);
+}
+
 // ---- losses (loss.py)
 int mpn_collision_loss(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, int N, const float* points, float margin, float* loss,
                        float* grad_points) {

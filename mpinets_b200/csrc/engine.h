@@ -135,6 +135,8 @@ int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const f
                  int t0, int accumulate, uint8_t* flags, int32_t* first_step, const float* frames_in = nullptr);
 int launch_evaluate(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T1, const int32_t* num_poses,
                     const float* target, const mpn_scene& tv, int V1, int V2, const mpn_scene& nv, int N1, int N2, float* out);
+int launch_sparc(mpn_ctx* c, cudaStream_t s, int B, int n_max, const float* movement, const int32_t* num, float fs, int padlevel, float fc,
+                 float amp_th, float* out);
 // ---- loss.cu
 int launch_collision_loss(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int N, const float* points, float margin, float* loss,
                           float* grad_points);

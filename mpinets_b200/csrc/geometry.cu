@@ -565,4 +565,114 @@ int launch_evaluate(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, cons
   return MPN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ SPARC smoothness
+// third_party/sparc.py:48-140 (Evaluator.calculate_smoothness, metrics.py:387-409) for B speed profiles at once.
+// One CTA per profile: zero-padded DFT length nfft = 2^(ceil(log2 n) + padlevel) evaluated directly for the bins with
+// f = k fs / nfft <= fc (twiddles from a shared-memory table indexed by k t mod nfft), magnitudes normalised by the
+// spectrum's maximum, the amplitude-threshold window [first, last] bin >= amp_th, and the arc length over that window.
+constexpr int SPARC_THREADS = 256;
+
+__global__ void __launch_bounds__(SPARC_THREADS)
+sparc_kernel(const float* __restrict__ movement, int n_max, const int32_t* __restrict__ num, float fs, int padlevel, float fc, float amp_th,
+             int nfft_cap, float* __restrict__ out) {
+  extern __shared__ float sp[];   // cos[nfft] | sin[nfft] | mag[nfft] | m[n_max]
+  __shared__ float redf[SPARC_THREADS / 32];
+  __shared__ int redi[2][SPARC_THREADS / 32];
+  __shared__ float s_max;
+  __shared__ int s_first, s_last, s_any;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int n = num ? num[b] : n_max;
+  n = max(0, min(n, n_max));
+  const float* mv = movement + (size_t)b * n_max;
+  int lg = 0;
+  while ((1 << lg) < n) ++lg;
+  const int nfft = 1 << (lg + padlevel);
+  if (n < 1 || nfft > nfft_cap) { if (tid == 0) out[b] = n < 1 ? 0.f : __int_as_float(0x7fc00000); return; }
+  float* ct = sp;
+  float* st = ct + nfft_cap;
+  float* mag = st + nfft_cap;
+  float* m = mag + nfft_cap;
+  int nz = 0;
+  for (int t = tid; t < n; t += blockDim.x) { const float v = mv[t]; m[t] = v; nz |= fabsf(v) > 1e-8f; }   // np.allclose(movement, 0)
+  for (int k = tid; k < nfft; k += blockDim.x) { float sv, cv; sincospif(2.0f * (float)k / (float)nfft, &sv, &cv); ct[k] = cv; st[k] = sv; }
+  if (tid == 0) s_any = 0;
+  __syncthreads();
+  if (nz) atomicOr(&s_any, 1);
+  __syncthreads();
+  if (!s_any) { if (tid == 0) out[b] = 0.f; return; }
+  // bins with f[k] = k * (fs / nfft) <= fc, f = np.arange(0, fs, fs / nfft)
+  const float df = fs / (float)nfft;
+  int kc = min(nfft - 1, (int)floorf(fc / df));
+  while (kc > 0 && (float)kc * df > fc) --kc;
+  while (kc + 1 < nfft && (float)(kc + 1) * df <= fc) ++kc;
+  // the maximum of the whole spectrum: by symmetry bins 0 .. nfft/2; evaluate max(kc, nfft/2) bins, keep 0 .. kc
+  const int kend = max(kc, nfft / 2);
+  float lmax = 0.f;
+  for (int k = tid; k <= kend; k += blockDim.x) {
+    float re = 0.f, im = 0.f;
+    int ph = 0;                                  // (k * t) mod nfft, advanced incrementally
+    for (int t = 0; t < n; ++t) {
+      re = fmaf(m[t], ct[ph], re); im = fmaf(-m[t], st[ph], im);
+      ph += k; if (ph >= nfft) ph -= nfft;
+    }
+    const float a = sqrtf(re * re + im * im);
+    if (k <= kc) mag[k] = a;
+    lmax = fmaxf(lmax, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if (lane == 0) redf[warp] = lmax;
+  __syncthreads();
+  if (tid == 0) { float v = 0.f; for (int w = 0; w < SPARC_THREADS / 32; ++w) v = fmaxf(v, redf[w]); s_max = v; }
+  __syncthreads();
+  const float inv = 1.0f / s_max;
+  int first = 0x7fffffff, last = -1;
+  for (int k = tid; k <= kc; k += blockDim.x) {
+    const float v = mag[k] * inv;
+    mag[k] = v;
+    if (v >= amp_th) { first = min(first, k); last = max(last, k); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { first = min(first, __shfl_xor_sync(0xffffffffu, first, o)); last = max(last, __shfl_xor_sync(0xffffffffu, last, o)); }
+  if (lane == 0) { redi[0][warp] = first; redi[1][warp] = last; }
+  __syncthreads();
+  if (tid == 0) {
+    int f0 = 0x7fffffff, l0 = -1;
+    for (int w = 0; w < SPARC_THREADS / 32; ++w) { f0 = min(f0, redi[0][w]); l0 = max(l0, redi[1][w]); }
+    s_first = f0; s_last = l0;
+  }
+  __syncthreads();
+  const int k0 = s_first, k1 = s_last;
+  if (k1 <= k0) { if (tid == 0) out[b] = 0.f; return; }   // a one-bin window has no arc
+  const float dfn = 1.0f / (float)(k1 - k0);               // diff(f_sel) / (f_sel[-1] - f_sel[0]) on the uniform grid
+  float acc = 0.f;
+  for (int k = k0 + tid; k < k1; k += blockDim.x) {
+    const float dm = mag[k + 1] - mag[k];
+    acc += sqrtf(dfn * dfn + dm * dm);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) redf[warp] = acc;
+  __syncthreads();
+  if (tid == 0) { float v = 0.f; for (int w = 0; w < SPARC_THREADS / 32; ++w) v += redf[w]; out[b] = -v; }
+}
+
+int launch_sparc(mpn_ctx* c, cudaStream_t s, int B, int n_max, const float* movement, const int32_t* num, float fs, int padlevel, float fc,
+                 float amp_th, float* out) {
+  int lg = 0;
+  while ((1 << lg) < n_max) ++lg;
+  const int nfft_cap = 1 << (lg + padlevel);
+  MPN_REQUIRE(nfft_cap <= 16384, "sparc: padded length %d exceeds 16384 (n_max=%d, padlevel=%d)", nfft_cap, n_max, padlevel);
+  const size_t smem = ((size_t)3 * nfft_cap + n_max) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(sparc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  sparc_kernel<<<B, SPARC_THREADS, smem, s>>>(movement, n_max, num, fs, padlevel, fc, amp_th, nfft_cap, out);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
 }  // namespace mpn

@@ -297,6 +297,17 @@ class Engine:
                                          C.byref(nv) if nv is not None else None, n1, n2, _p(out)))
         return out
 
+    def sparc(self, movement: torch.Tensor, fs: float, num_samples: Optional[torch.Tensor] = None, padlevel: int = 4, fc: float = 10.0,
+              amp_th: float = 0.05) -> torch.Tensor:
+        """third_party/sparc.py for B speed profiles [B, n] -> spectral arc length [B]"""
+        _check(movement, "movement", device=self.device)
+        B, n = movement.shape
+        if num_samples is not None:
+            _check(num_samples, "num_samples", torch.int32, self.device)
+        out = self._empty(B)
+        _lib.check(self.lib.mpn_sparc(self._ctx, self.stream, B, n, _p(movement), _p(num_samples), fs, padlevel, fc, amp_th, _p(out)))
+        return out
+
     # ------------------------------------------------------------------ losses (loss.py)
     def collision_loss(self, scene, points: torch.Tensor, margin: float = 0.03, need_grad: bool = False):
         """loss.collision_loss (loss.py:47-94): points [B,N,3] -> (loss [1], grad_points [B,N,3] or None)"""

@@ -3,9 +3,9 @@
 The reference evaluates one trajectory at a time on the CPU (Bullet collision checks, numpy FK, metrics.py:436-523);
 here B trajectories are evaluated by one kernel launch and appended to the current metric group under the same keys
 `add_metric` uses (metrics.py:470-523), so `Evaluator.metrics(group)` aggregates exactly like the reference's
-(metrics.py:566-664).  Not computed on the device: SPARC smoothness (metrics.py:387-409) and Bullet collision depths;
-`collision` is the validation sphere sweep of model.py:293-314 and `self_collision` a sphere-sphere stand-in (see
-include/mpinets_b200.h).
+(metrics.py:566-664).  SPARC smoothness (metrics.py:387-409) runs on the device too (`mpn_sparc`; the speed profiles are
+formed with torch ops from the trajectory and one batched FK).  Not reproduced: Bullet collision depths; `collision` is the
+validation sphere sweep of model.py:293-314 and `self_collision` a sphere-sphere stand-in (see include/mpinets_b200.h).
 """
 from __future__ import annotations
 
@@ -50,6 +50,7 @@ class Evaluator:
                              negative_volumes=target_negative_volumes)
         host = table.cpu().numpy()
         B = host.shape[0]
+        config_sparc, eff_sparc = self.calculate_smoothness(trajectories, dt, num_poses, eng)
         g = self.current_group
         booleans = ("collision", "joint_limit_violation", "self_collision", "physical_violations", "success")
         for i, name in enumerate(_lib.EVAL_COLUMNS):
@@ -60,14 +61,29 @@ class Evaluator:
             g[name] = g.get(name, []) + vals
         g["time"] = g.get("time", []) + ([float(t) for t in time] if time is not None else [float(dt) * n for n in host[:, 10]])
         g["collision_depths"] = g.get("collision_depths", []) + [[float(d)] if d > 0 else [] for d in host[:, 13]]
-        nan = [float("nan")] * B
-        g["config_smoothness"] = g.get("config_smoothness", []) + nan     # SPARC is not computed on the device
-        g["eff_smoothness"] = g.get("eff_smoothness", []) + nan
+        g["config_smoothness"] = g.get("config_smoothness", []) + [float(v) for v in config_sparc.cpu().numpy()]
+        g["eff_smoothness"] = g.get("eff_smoothness", []) + [float(v) for v in eff_sparc.cpu().numpy()]
         return table
 
     @staticmethod
+    def calculate_smoothness(trajectories: torch.Tensor, dt: float, num_poses: Optional[torch.Tensor] = None, engine=None):
+        """metrics.py:387-409 for a batch: SPARC of the configuration-space speed |dq|/dt and of the end-effector speed
+        |d xyz(right_gripper)|/dt; returns (config_sparc [B], eff_sparc [B])"""
+        eng = engine or get_engine(trajectories.device)
+        B, T1, _ = trajectories.shape
+        if T1 < 2:
+            z = torch.zeros(B, device=trajectories.device)
+            return z, z
+        cfg_speed = (torch.linalg.norm(torch.diff(trajectories, dim=1), dim=2) / dt).contiguous()
+        _, eef = eng.fk(trajectories.reshape(B * T1, 7).contiguous())
+        pos = eef[:, :, 3].reshape(B, T1, 3)
+        eff_speed = (torch.linalg.norm(torch.diff(pos, dim=1), dim=2) / dt).contiguous()
+        n = None if num_poses is None else (num_poses - 1).clamp(min=0).to(torch.int32).contiguous()
+        return eng.sparc(cfg_speed, 1.0 / dt, n), eng.sparc(eff_speed, 1.0 / dt, n)
+
+    @staticmethod
     def metrics(group: Dict[str, Any]) -> Dict[str, Any]:
-        """metrics.py:566-664 (same keys; the SPARC entries are NaN)"""
+        """metrics.py:566-664 (same keys)"""
         success = np.asarray(group["success"], dtype=bool)
         pos, ori = np.asarray(group["position_error"]), np.asarray(group["orientation_error"])
         times, steps = np.asarray(group["time"]), np.asarray(group["num_steps"])
@@ -94,9 +110,10 @@ class Evaluator:
             "15 deg": percent_true(ori < 15),
             "30 deg": percent_true(ori < 30),
             "165 deg": percent_true(ori > 165),
-            "is smooth": float("nan"),
-            "average config sparc": float("nan"),
-            "average eff sparc": float("nan"),
+            "is smooth": percent_true(np.logical_and(np.asarray(group["config_smoothness"]) < -1.6,
+                                                     np.asarray(group["eff_smoothness"]) < -1.6)),
+            "average config sparc": float(np.mean(group["config_smoothness"])),
+            "average eff sparc": float(np.mean(group["eff_smoothness"])),
             "eff position path length": mean_std(ppl[success]),
             "eff orientation path length": mean_std(opl[success]),
         }
@@ -115,6 +132,9 @@ class Evaluator:
         print(f"% With Self Collision: {m['self collision']:4.2f}")
         print(f"% With Joint Limit Violations: {m['joint violation']:4.2f}")
         print(f"% With Physical Violations: {m['physical violations']:4.2f}")
+        print(f"Average Config SPARC: {m['average config sparc']:4.2f}")
+        print(f"Average End Eff SPARC: {m['average eff sparc']:4.2f}")
+        print(f"% Smooth: {m['is smooth']:4.2f}")
         print(f"Average End Eff Position Path Length: {m['eff position path length'][0]:4.2f} ± {m['eff position path length'][1]:4.2f}")
         print(f"Average End Eff Orientation Path Length: {m['eff orientation path length'][0]:4.2f} ± {m['eff orientation path length'][1]:4.2f}")
 

@@ -125,6 +125,26 @@ def sweep_flags(scene, traj, tables, quirk=True):
 EVAL_COLS = 16
 
 
+# ----------------------------------------------------------------------------- SPARC (third_party/sparc.py:48-140)
+def sparc(movement, fs, padlevel=4, fc=10.0, amp_th=0.05):
+    """spectral arc length of one speed profile, float64, line by line after sparc.py (returns only `sal`)"""
+    movement = np.asarray(movement, dtype=np.float64)
+    if np.allclose(movement, 0):                                       # sparc.py:95-97
+        return 0.0
+    nfft = int(pow(2, np.ceil(np.log2(len(movement))) + padlevel))     # :99
+    f = np.arange(0, fs, fs / nfft)                                    # :102
+    Mf = abs(np.fft.fft(movement, nfft))                               # :104
+    Mf = Mf / max(Mf)                                                  # :105
+    sel = (f <= fc).nonzero()                                          # :112
+    f_sel, Mf_sel = f[sel], Mf[sel]
+    inx = (Mf_sel >= amp_th).nonzero()[0]                              # :119
+    rng = range(inx[0], inx[-1] + 1)
+    f_sel, Mf_sel = f_sel[rng], Mf_sel[rng]
+    if len(f_sel) < 2:
+        return 0.0
+    return float(-np.sum(np.sqrt(np.power(np.diff(f_sel) / (f_sel[-1] - f_sel[0]), 2) + np.power(np.diff(Mf_sel), 2))))   # :125-129
+
+
 # ----------------------------------------------------------------------------- losses (loss.py)
 def collision_loss(scene, points, margin=0.03, quirk=True, need_grad=True):
     """loss.collision_loss (loss.py:47-94): points [B,N,3] -> (loss, grad_points [B,N,3])"""

@@ -9,6 +9,8 @@ Run here only (``/root/reference`` does not exist on the GPU box):  python tests
 * ``loss_reference.npz`` -- ``mpinets/loss.py`` ``collision_loss`` and ``point_match_loss`` (the real functions, imported
   with ``robofin`` / ``mpinets.utils`` stubbed: neither is touched by these two functions) on seeded scenes and points,
   with ``torch.autograd`` gradients w.r.t. the input cloud.
+* ``sparc_reference.npz`` -- ``mpinets/third_party/sparc.py`` ``sparc`` (imports as-is) on its own doctest input
+  (sparc.py:87-91, -1.41403) and on seeded speed profiles shaped like rollouts (dt = 0.08, 20..150 samples).
 * ``fk_reference.npz``   -- the FK known-answer pair of ``interactive_demo/mpinets_ros/nodes/interaction_node.py:54-75``
   (parsed from the file, not retyped).
 """
@@ -85,6 +87,27 @@ def loss_fixtures(geo):
     print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if "loss" in k})
 
 
+def sparc_fixtures():
+    spec = importlib.util.spec_from_file_location("ref_sparc", os.path.join(REF, "mpinets", "third_party", "sparc.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    t = np.arange(-1, 1, 0.01)
+    move = np.exp(-5 * pow(t, 2))
+    doc, _, _ = mod.sparc(move, fs=100.0)
+    rng = np.random.RandomState(42)
+    n_max, B = 150, 24
+    profiles = np.zeros((B, n_max), np.float32); num = np.zeros(B, np.int32); sal = np.zeros(B)
+    for b in range(B):
+        n = int(rng.randint(20, n_max + 1)); num[b] = n
+        tt = np.linspace(0, 1, n)
+        v = np.sin(np.pi * tt) ** 2 * rng.uniform(0.2, 2.0) + 0.05 * rng.uniform(0, 1) * np.abs(rng.normal(size=n)) * (b % 3 != 0)
+        profiles[b, :n] = v
+        sal[b] = mod.sparc(profiles[b, :n].astype(np.float64), 1.0 / 0.08)[0]
+    np.savez_compressed(os.path.join(HERE, "sparc_reference.npz"), doctest_move=move, doctest_sal=doc, profiles=profiles, num=num,
+                        sal=sal, fs=1.0 / 0.08)
+    print("sparc doctest", doc, "profiles", sal[:4])
+
+
 def random_scenes(rng, B, M1, M2, yaw_only):
     def quats(n):
         if yaw_only:
@@ -134,6 +157,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "sdf_reference.npz"), **out)
 
     loss_fixtures(geo)
+    sparc_fixtures()
 
     src = open(os.path.join(REF, "interactive_demo/mpinets_ros/nodes/interaction_node.py")).read()
 

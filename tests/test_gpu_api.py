@@ -129,6 +129,14 @@ def test_evaluator_surface(tables, oracle):
     assert m["total"] == 12 and abs(m["success"] - 100 * np.count_nonzero(exp[:, 9]) / 12) < 1e-9
     assert abs(m["env collision"] - 100 * np.count_nonzero(exp[:, 0]) / 12) < 1e-9
     assert m["1 cm"] == 100.0                                  # joint-space interpolation ends exactly on the target
+    # SPARC columns (metrics.py:387-409) against the oracle's restatement of sparc.py on float64 speed profiles
+    from mpinets_b200.franka import fk_reference_f64
+    th = traj.cpu().numpy().astype(np.float64)
+    for b in (0, 5, 11):
+        cfg = np.linalg.norm(np.diff(th[b], axis=0) / 0.1, axis=1)
+        eff = np.linalg.norm(np.diff(np.stack([fk_reference_f64(q)[1][:3, 3] for q in th[b]]), axis=0) / 0.1, axis=1)
+        assert abs(g["config_smoothness"][b] - oracle.sparc(cfg, 10.0)) < 2e-3
+        assert abs(g["eff_smoothness"][b] - oracle.sparc(eff, 10.0)) < 2e-3
     ev.print_group_metrics()
     ev.print_overall_metrics()
 

@@ -561,3 +561,18 @@ def test_bc_collision_losses_match_oracle(engine, oracle, tables):
     l_p, _ = engine.point_match_loss(torch.from_numpy(xi).cuda(), torch.from_numpy(xt).cuda())
     l2, _ = engine.bc_collision_losses(to_dev(p), torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda())
     assert abs(float(l_c) - float(l2[0])) < 1e-6 and abs(float(l_p) - float(l2[1])) < 1e-6
+
+
+def test_sparc_matches_reference_fixture(engine, oracle):
+    """mpn_sparc against outputs of the REAL third_party/sparc.py (tests/golden/sparc_reference.npz) and the oracle"""
+    g = np.load(os.path.join(HERE, "golden", "sparc_reference.npz"))
+    got = engine.sparc(torch.from_numpy(g["profiles"]).cuda(), float(g["fs"]), torch.from_numpy(g["num"]).cuda()).cpu().numpy()
+    assert np.abs(got - g["sal"]).max() < 2e-4                       # fp32 DFT vs float64 numpy FFT
+    doc = g["doctest_move"].astype(np.float32)[None]                  # sparc.py:87-91
+    sal = engine.sparc(torch.from_numpy(np.ascontiguousarray(doc)).cuda(), 100.0)
+    assert "%.4f" % float(sal[0]) == "-1.4140"
+    rng = np.random.default_rng(1)
+    prof = np.abs(rng.normal(size=(9, 70))).astype(np.float32); prof[3] = 0.0
+    got = engine.sparc(torch.from_numpy(prof).cuda(), 12.5).cpu().numpy()
+    exp = np.array([oracle.sparc(prof[b], 12.5) for b in range(9)])
+    assert got[3] == 0.0 and np.abs(got - exp).max() < 5e-4

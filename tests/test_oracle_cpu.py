@@ -503,3 +503,15 @@ def test_planning_problem_records_to_soa():
     ps = {"tabletop": {"task_oriented": probs[:3], "neutral_start": probs[3:5]}, "cubby": {"task_oriented": probs[5:]}}
     flat = T.flatten_problem_set(ps)
     assert [(e, k) for e, k, _ in flat] == [("tabletop", "task_oriented")] * 3 + [("tabletop", "neutral_start")] * 2 + [("cubby", "task_oriented")] * 2
+
+
+# ----------------------------------------------------------------------------- SPARC (third_party/sparc.py)
+def test_oracle_sparc_matches_reference(oracle):
+    """the reference's own doctest value (sparc.py:87-91) and outputs of the real sparc() on rollout-shaped speed profiles"""
+    g = np.load(os.path.join(HERE, "golden", "sparc_reference.npz"))
+    assert "%.5f" % oracle.sparc(g["doctest_move"], 100.0) == "-1.41403"
+    assert abs(oracle.sparc(g["doctest_move"], 100.0) - float(g["doctest_sal"])) < 1e-12
+    for b in range(g["profiles"].shape[0]):
+        n = int(g["num"][b])
+        assert abs(oracle.sparc(g["profiles"][b, :n], float(g["fs"])) - g["sal"][b]) < 1e-12
+    assert oracle.sparc(np.zeros(30), 12.5) == 0.0
