@@ -206,9 +206,6 @@ int mpn_profile_read(mpn_ctx* ctx, float* ms /*[MPN_NUM_STAGES]*/, int64_t* laun
  * status (device int) is set to 1 when the MMA completion barrier timed out. */
 /* synchronises and returns the tensor-core path's sticky error flag (1 = an MMA completion barrier timed out) */
 int mpn_tc_error(mpn_ctx* ctx, int* out);
-/* debug: per-phase cycle totals of the tensor-core kernels (CTA 0, warpgroup 0; [0,16) SA2, [16,32) SA1, [32,48) the
- * row GEMM), enabled by MPN_TC_TIMELINE=1 in the environment; out must hold 48 values */
-int mpn_tc_timeline(mpn_ctx* ctx, int64_t* out48);
 int mpn_tc_selftest(mpn_ctx* ctx, void* stream, const void* a_bf16, const void* b_bf16, float* d, int N, int K, int mode,
                     int* status);
 

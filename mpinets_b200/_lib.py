@@ -24,7 +24,7 @@ EXPORTS = (
     "mpn_load_weight", "mpn_weights_finalize", "mpn_fps", "mpn_ball_query", "mpn_gather_points", "mpn_group_points",
     "mpn_sa_forward", "mpn_fk", "mpn_sample_robot", "mpn_compute_spheres", "mpn_normalize_joints",
     "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_sweep_flags", "mpn_evaluate", "mpn_sparc", "mpn_collision_loss", "mpn_point_match_loss", "mpn_bc_collision_losses", "mpn_encoder_forward",
-    "mpn_policy_forward", "mpn_rollout", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error", "mpn_tc_timeline",
+    "mpn_policy_forward", "mpn_rollout", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error",
 )
 
 
@@ -90,7 +90,6 @@ def load():
         "mpn_launch_count": [P],
         "mpn_profile": [P, I],
         "mpn_tc_error": [P, C.POINTER(C.c_int)],
-        "mpn_tc_timeline": [P, C.POINTER(C.c_int64)],
         "mpn_tc_selftest": [P, P, P, P, P, I, I, I, P],
         "mpn_profile_read": [P, C.POINTER(C.c_float), C.POINTER(C.c_int64)],
     }

@@ -21,7 +21,6 @@ int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, in
 int tc_prepare_weights(mpn_ctx* c);
 size_t tc_scratch_bytes(int B);
 int* tc_error_flag(mpn_ctx* c);
-long long* tc_timeline(mpn_ctx* c);
 int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
                   int N, const float* new_xyz, float* new_feats, int32_t* ball_idx);
 int tc_probe(mpn_ctx* c, cudaStream_t s, const void* A, const void* B, float* D, int N, int K, int mode, int* status);
@@ -315,17 +314,6 @@ int mpn_tc_error(mpn_ctx* c, int* out) {
   MPN_REQUIRE(out, "mpn_tc_error: null output");
   MPN_CHECK_CUDA(cudaDeviceSynchronize());
   MPN_CHECK_CUDA(cudaMemcpy(out, tc_error_flag(c), sizeof(int), cudaMemcpyDeviceToHost));
-  return MPN_OK;
-}
-
-int mpn_tc_timeline(mpn_ctx* c, int64_t* out16) {
-  REQ_CTX(c);
-  MPN_REQUIRE(out16, "mpn_tc_timeline: null output");
-  long long* p = tc_timeline(c);
-  MPN_REQUIRE(p, "set MPN_TC_TIMELINE=1 to enable the phase timeline");
-  MPN_CHECK_CUDA(cudaDeviceSynchronize());
-  MPN_CHECK_CUDA(cudaMemcpy(out16, p, 48 * sizeof(long long), cudaMemcpyDeviceToHost));
-  MPN_CHECK_CUDA(cudaMemset(p, 0, 48 * sizeof(long long)));
   return MPN_OK;
 }
 

@@ -279,14 +279,8 @@ int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int s
   static const bool no_prune = getenv("MPN_FPS_NO_PRUNE") != nullptr;
   if (!no_prune && ppt > 8 && ppt <= 13 && npoint >= 64) {   // large clouds: exact pruned variant
     size_t smem_p = smem + FPSP_CELLS * sizeof(uint32_t) + (size_t)N * sizeof(uint16_t) + 16;
-    static const bool wide = getenv("MPN_FPS_WIDE") != nullptr;   // 1024 threads x 7 points (32 prune regions) instead of 512 x 13
-    if (wide && N <= 7 * 1024) {
-      MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<1024, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-      fps_pruned_kernel<1024, 7><<<B, 1024, smem_p, s>>>(xyz, N, stride, npoint, idx, new_xyz);
-    } else {
-      MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<512, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-      fps_pruned_kernel<512, 13><<<B, 512, smem_p, s>>>(xyz, N, stride, npoint, idx, new_xyz);
-    }
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<512, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    fps_pruned_kernel<512, 13><<<B, 512, smem_p, s>>>(xyz, N, stride, npoint, idx, new_xyz);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;

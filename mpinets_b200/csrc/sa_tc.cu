@@ -36,7 +36,6 @@ struct TcWeights {
 };
 static std::map<mpn_ctx*, TcWeights> g_tc;
 int* tc_error_flag(mpn_ctx* c);
-long long* tc_timeline(mpn_ctx* c);
 
 // bias_col >= 0: the layer's bias is folded into the GEMM as K-column `bias_col` (the operand carries a 1.0 there)
 __global__ void pack_weight_kernel(const float* __restrict__ w, int out, int in, int kpad, int rot, __nv_bfloat16* __restrict__ dst,
@@ -119,77 +118,7 @@ __device__ __forceinline__ uint64_t tile_desc(uint32_t base, int K, int r0, int 
   return make_smem_desc(base + (uint32_t)((r0 >> 3) * KC * 128 + ks * 256), 128, KC * 128, LAYOUT_NONE);
 }
 
-// ball query by one warpgroup over points in shared memory (float4): same semantics as pointnet.cu
-template <int NS>
-__device__ __forceinline__ void wg_ball_query(const float4* __restrict__ pts, int N, float cx, float cy, float cz, float r2,
-                                              int* __restrict__ idx_s, int* __restrict__ wl /*[4][NS]*/, int* __restrict__ wcnt /*[4]*/,
-                                              int g, int wg_tid) {
-  const int warp = wg_tid >> 5, lane = wg_tid & 31;
-  const int seg = ((N + 3) / 4 + 31) & ~31;
-  const int k_begin = warp * seg, k_end = min(N, k_begin + seg);
-  int cnt = 0;
-  for (int k0 = k_begin; k0 < k_end && cnt < NS; k0 += 32) {
-    int k = k0 + lane;
-    bool hit = false;
-    if (k < k_end) {
-      float4 p = pts[k];
-      hit = dist2(cx, cy, cz, p.x, p.y, p.z) < r2;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    int pos = cnt + __popc(m & ((1u << lane) - 1u));
-    if (hit && pos < NS) wl[warp * NS + pos] = k;
-    cnt += __popc(m);
-  }
-  if (lane == 0) wcnt[warp] = min(cnt, NS);
-  wg_sync(g);
-  int total = 0, first = 0, base = 0;
-  bool have = false;
-#pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    int cw = wcnt[w];
-    if (w == warp) base = total;
-    if (!have && cw > 0) { first = wl[w * NS]; have = true; }
-    total += cw;
-  }
-  const int mine = wcnt[warp];
-  for (int l = lane; l < mine; l += 32)
-    if (base + l < NS) idx_s[base + l] = wl[warp * NS + l];
-  total = min(total, NS);
-  for (int l = total + wg_tid; l < NS; l += 128) idx_s[l] = first;
-  wg_sync(g);
-}
-
-// ---------------------------------------------------------------------------------------------- SA2
-// points = xyz1 [512][3] fp32, features = feat1 [512][64] bf16, 128 centroids, radius 0.3, MLP 67 -> 128 -> 128 -> 256.
-// 256 threads = 2 warpgroups, each streaming its own centroids.  Every operand row lives in one persistent smem layout
-// of 18 K-chunks: [chunks 0..15: data | chunk 16: 1.0, 0 x7 | chunk 17: 0], so that
-//   layer 1 reads K-steps 0..4  = [f0..f63 | dx dy dz 1 0 0 0 0 | 0 x8]         (bias = weight column 67)
-//   layer 2 reads K-steps 0..8  = [128 activations | 1 0 ... 0]                  (bias = weight column 128)
-//   layer 3 (transposed, D^T = W3 * A2^T) reads K-steps 0..7; its bias is added after the max-pool.
-// Epilogues of layers 1 and 2 are tcgen05.ld -> cvt.rn.relu.bf16x2 -> st.shared.
-constexpr int SA2_KC = 18, SA2_K1 = 80, SA2_K2 = 144, SA2_K3 = 128;
-struct Sa2Smem {
-  static constexpr size_t w1 = 0;                                     // [128][80]
-  static constexpr size_t w2 = w1 + 128 * SA2_K1 * 2;                 // [128][144]
-  static constexpr size_t w3 = w2 + 128 * SA2_K2 * 2;                 // [256][128]
-  static constexpr size_t x = w3 + 256 * SA2_K3 * 2;                  // 2 x [128][144]
-  static constexpr size_t b3 = x + 2 * 128 * SA2_KC * 16;             // [256] float
-  static constexpr size_t idx = b3 + 256 * 4;                         // [2][128] int
-  static constexpr size_t wl = idx + 2 * 128 * 4;                     // [2][4][128] int
-  static constexpr size_t wcnt = wl + 2 * 4 * 128 * 4;                // [2][4] int
-  static constexpr size_t bars = wcnt + 64;                           // 2 mbarriers + tmem slot
-  static constexpr size_t pts = (bars + 64 + 15) / 16 * 16;           // float4 [512]
-  static constexpr size_t total = pts + SA1_NPOINT * 16 + 256;
-};
-
-// optional per-phase cycle accounting (thread 0 of CTA 0): tl[i] += cycles of phase i
-#define TL_MARK(i)                                                     \
-  do {                                                                 \
-    if (tl && blockIdx.x == 0 && threadIdx.x == 0) {                   \
-      long long _n = clock64(); tl[i] += _n - tl_prev; tl_prev = _n;   \
-    }                                                                  \
-  } while (0)
-
+// ---------------------------------------------------------------------------------------------- shared helpers of the SA kernels
 __device__ __forceinline__ uint32_t cvt_relu_bf16x2(float first, float second) {
   uint32_t d;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
@@ -211,186 +140,6 @@ __device__ __forceinline__ void epilogue_pack_relu(uint32_t taddr, uint8_t* X, i
                      cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
                      cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
   }
-}
-
-constexpr int SA2_THREADS = 256 + 64;   // 2 warpgroups of 4 row warps + one MMA-issue warp each
-__global__ void __launch_bounds__(SA2_THREADS, 1)
-sa2_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __restrict__ feat_bf16, const float* __restrict__ new_xyz,
-              float r2, const __nv_bfloat16* __restrict__ gw1, const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3,
-              const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16, int out_stride, int* __restrict__ err,
-              int32_t* __restrict__ ball_idx, long long* __restrict__ tl) {
-  using S = Sa2Smem;
-  constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT;
-  long long tl_prev = clock64();
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sW1 = smem + S::w1;
-  uint8_t* sW2 = smem + S::w2;
-  uint8_t* sW3 = smem + S::w3;
-  float* sB3 = reinterpret_cast<float*>(smem + S::b3);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
-  uint64_t* ready_bars = bars + 2;                 // [2]: operand of the next layer is in shared memory (128 row-thread arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 32);
-  float4* pts = reinterpret_cast<float4*>(smem + S::pts);
-
-  const int b = blockIdx.x;
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
-  const bool issuer = warp >= 8;                                     // warps 8, 9: MMA issue warps of warpgroups 0, 1
-  const int g = issuer ? warp - 8 : warp >> 2, wq = warp & 3;
-  const int t = threadIdx.x & 127;
-  uint8_t* X = smem + S::x + (size_t)g * 128 * SA2_KC * 16;
-  int* idx_s = reinterpret_cast<int*>(smem + S::idx) + g * 128;
-  int* wl = reinterpret_cast<int*>(smem + S::wl) + g * 4 * 128;
-  int* wcnt = reinterpret_cast<int*>(smem + S::wcnt) + g * 4;
-
-  stage_weight(gw1, 128, SA2_K1, sW1);
-  stage_weight(gw2, 128, SA2_K2, sW2);
-  stage_weight(gw3, 256, SA2_K3, sW3);
-  for (int i = threadIdx.x; i < 256; i += SA2_THREADS) sB3[i] = gb3[i];
-  {
-    const float* p = xyz + (size_t)b * N * stride;
-    for (int k = threadIdx.x; k < N; k += SA2_THREADS)
-      pts[k] = make_float4(__ldg(p + (size_t)k * stride), __ldg(p + (size_t)k * stride + 1), __ldg(p + (size_t)k * stride + 2), 0.f);
-  }
-  // persistent tail of every operand row
-  if (!issuer) {
-    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 16, SA2_KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 17, SA2_KC)) = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&ready_bars[0], 128); mbar_init(&ready_bars[1], 128);
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot + (uint32_t)g * 256;
-  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
-  // descriptors built once; K-steps only add to the start-address field
-  const uint64_t dX = make_smem_desc(smem_u32(X), 128, SA2_KC * 128, LAYOUT_NONE);
-  const uint64_t dW1 = make_smem_desc(smem_u32(sW1), 128, (SA2_K1 / 8) * 128, LAYOUT_NONE);
-  const uint64_t dW2 = make_smem_desc(smem_u32(sW2), 128, (SA2_K2 / 8) * 128, LAYOUT_NONE);
-  const uint64_t dW3 = make_smem_desc(smem_u32(sW3), 128, (SA2_K3 / 8) * 128, LAYOUT_NONE);
-  constexpr uint32_t W3_TILE1 = (128 / 8) * (SA2_K3 / 8) * 128 / 16;   // rows 128..255 of W3, in 16-byte units
-  constexpr uint32_t ID128 = make_idesc_bf16(128, 128);
-  uint64_t* bar = &bars[g];
-  uint64_t* ready = &ready_bars[g];
-  uint32_t phase = 0;
-  bool ok = true;
-
-  if (issuer) {
-    // ---- MMA issue warp: for every centroid of the warpgroup, wait for the operand of each layer and issue its MMAs.
-    // Issuing blocks while the tensor pipe drains its queue; keeping it off the row warps lets them prefetch meanwhile.
-    uint32_t rphase = 0;
-    for (int j = g; j < NCENT && ok; j += 2) {
-#pragma unroll 1
-      for (int layer = 0; layer < 3; ++layer) {
-        ok = mbar_wait(ready, rphase); rphase ^= 1;
-        tc_fence_after();
-        if (elect_one()) {
-          if (layer == 0) {
-#pragma unroll
-            for (int ks = 0; ks < SA2_K1 / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW1, ks * 16, ID128, ks > 0);
-          } else if (layer == 1) {
-#pragma unroll
-            for (int ks = 0; ks < SA2_K2 / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW2, ks * 16, ID128, ks > 0);
-          } else {   // transposed: D^T[ch][nbr] = W3[ch tile] * A2^T ; tile 0 -> cols 128.., tile 1 -> cols 0..
-#pragma unroll
-            for (int ks = 0; ks < SA2_K3 / 16; ++ks) mma_bf16_ss_off(tmem + 128, dW3, ks * 16, dX, ks * 16, ID128, ks > 0);
-#pragma unroll
-            for (int ks = 0; ks < SA2_K3 / 16; ++ks) mma_bf16_ss_off(tmem, dW3, W3_TILE1 + ks * 16, dX, ks * 16, ID128, ks > 0);
-          }
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-
-  // software pipeline: the ball query and the feature-row loads of the NEXT centroid are issued while layer 3 of the
-  // current one runs on the tensor pipe; the rows wait in registers until the operand buffer is free again.
-  float cx, cy, cz, dx, dy, dz;
-  uint4 fr[8];
-  auto prefetch = [&](int jn) {
-    const float* cp = new_xyz + ((size_t)b * NCENT + jn) * 3;
-    cx = cp[0]; cy = cp[1]; cz = cp[2];
-    wg_ball_query<NSAMPLE>(pts, N, cx, cy, cz, r2, idx_s, wl, wcnt, g, t);
-    if (ball_idx) ball_idx[((size_t)b * NCENT + jn) * NSAMPLE + t] = idx_s[t];
-    const int k = idx_s[t];
-    const float4 p = pts[k];
-    dx = fsub(p.x, cx); dy = fsub(p.y, cy); dz = fsub(p.z, cz);
-    const uint4* f = reinterpret_cast<const uint4*>(feat_bf16 + ((size_t)b * N + k) * 64);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) fr[q] = __ldg(f + q);
-  };
-  if (g < NCENT) prefetch(g);
-  for (int j = g; j < NCENT && ok; j += 2) {
-    const float ccx = cx, ccy = cy, ccz = cz;   // this centroid (the prefetch below overwrites cx..)
-    TL_MARK(0);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, q, SA2_KC)) = fr[q];
-    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, SA2_KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 1.0f), 0u, 0u);
-    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, SA2_KC)) = make_uint4(0u, 0u, 0u, 0u);
-    TL_MARK(2);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(ready);   // layer 1 operand complete (the issue warp waits for all 128 rows)
-    TL_MARK(3);
-    TL_MARK(4);
-    ok = mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
-    TL_MARK(5);
-    epilogue_pack_relu<128, SA2_KC>(tlane, X, t);
-    TL_MARK(6);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(ready);   // layer 2 operand complete
-    TL_MARK(7);
-    TL_MARK(8);
-    ok = ok && mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
-    TL_MARK(9);
-    epilogue_pack_relu<128, SA2_KC>(tlane, X, t);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(ready);   // layer 3 operand complete
-    TL_MARK(10);
-    TL_MARK(11);
-    if (j + 2 < NCENT) prefetch(j + 2);   // overlaps the layer-3 MMAs
-    TL_MARK(1);
-    ok = ok && mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
-    TL_MARK(12);
-    __nv_bfloat16* o = out_bf16 + ((size_t)b * NCENT + j) * out_stride;
-#pragma unroll 1
-    for (int tile = 0; tile < 2; ++tile) {
-      float m = -3.0e38f;
-#pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 64) {
-        uint32_t v[32], u[32];
-        tmem_ld32(tlane + (tile == 0 ? 128 : 0) + c0, v);
-        tmem_ld32(tlane + (tile == 0 ? 128 : 0) + c0 + 32, u);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) m = fmaxf(m, fmaxf(__uint_as_float(v[q]), __uint_as_float(u[q])));
-      }
-      o[tile * 128 + t] = __float2bfloat16_rn(fmaxf(m + sB3[tile * 128 + t], 0.f));
-    }
-    if (t < 8) {   // SA3 operand tail: [x, y, z, 0...] of this centroid (GroupAll uses uncentred xyz)
-      float v = t == 0 ? ccx : (t == 1 ? ccy : (t == 2 ? ccz : 0.f));
-      o[256 + t] = __float2bfloat16_rn(v);
-      o[256 + 8 + t] = __float2bfloat16_rn(0.f);
-    }
-    TL_MARK(13);
-    tc_fence_before();   // orders this thread's TMEM reads before its next arrival on `ready`
-    TL_MARK(14);
-  }
-  }
-  if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
 // ---------------------------------------------------------------------------------------------- SA2, 3 warpgroups
@@ -609,320 +358,14 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
-// ---------------------------------------------------------------------------------------------- SA1 (v2)
-// 512 threads = 4 warpgroups, each streaming its own centroids.  Operand rows are [64 values | 1.0 | 0-pad] (K = 80,
-// 10 core-matrix chunks) for all three layers, the 1.0 column multiplies the bias stored as weight column 64, so the
-// epilogue is tcgen05.ld -> cvt.rn.relu.bf16x2 -> st.shared.  The last layer is pooled over the 128 neighbours with a
-// signed-integer redux on the raw accumulator bits (max over non-negative floats == max over their bit patterns; a
-// negative result is clamped by the final ReLU).
-constexpr int SA1_NWG = 4;
+// ---------------------------------------------------------------------------------------------- SA1
 constexpr int SA1_BUCKETS = 4096;
-constexpr int SA1_THREADS = 128 * SA1_NWG + 32 * SA1_NWG;   // 4 warpgroups of 4 row warps + one ball-query producer warp each
-struct Sa1Smem {
-  static constexpr size_t w = 0;                                          // 3 x [64][80] bf16
-  static constexpr size_t x = w + 3 * 64 * SA1_XK * 2;                    // NWG x [128][80] bf16 (aliased by the grid build)
-  static constexpr size_t idx = x + (size_t)SA1_NWG * 128 * SA1_XK * 2;   // [NWG][2 slots][4][128] u16 neighbour lists
-  static constexpr size_t hits = idx + SA1_NWG * 2 * 4 * 128 * 2;         // [NWG][256] u16 candidates / hits of the producer warp
-  static constexpr size_t red = hits + SA1_NWG * 256 * 2;                 // [NWG][4][64] int
-  static constexpr size_t bars = red + SA1_NWG * 4 * 64 * 4;              // mbarriers: mma[NWG], full[NWG][2], empty[NWG][2]; tmem slot
-  static constexpr size_t bstart = (bars + 256 + 15) / 16 * 16;           // u16 [BUCKETS + 1]
-  static constexpr size_t pts = (bstart + (SA1_BUCKETS + 1) * 2 + 15) / 16 * 16;   // sorted x[N] | y[N] | z[N] floats | idx u16[N]
-  static size_t total(int N) { return pts + (size_t)N * 14 + 1024; }
-};
-
-__device__ __forceinline__ void wg_sync4(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
 // uniform hash grid: cell edge slightly above the query radius so that every point within r of a centroid lies in
 // one of the 27 cells around the centroid's cell even under fp32 rounding of the cell coordinates
 __device__ __forceinline__ int grid_coord(float v) { return (int)floorf((v + 8.0f) * (1.0f / 0.0501f)); }
 __device__ __forceinline__ uint32_t grid_bucket(int ix, int iy, int iz) {
   return ((uint32_t)ix * 73856093u ^ (uint32_t)iy * 19349663u ^ (uint32_t)iz * 83492791u) & (SA1_BUCKETS - 1);
-}
-
-__global__ void __launch_bounds__(SA1_THREADS, 1)
-sa1_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
-              const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
-              int* __restrict__ err, int32_t* __restrict__ ball_idx, long long* __restrict__ tl) {
-  using S = Sa1Smem;
-  long long tl_prev = clock64();
-  constexpr int KC = SA1_XK / 8, NS = NSAMPLE;
-  extern __shared__ __align__(1024) uint8_t smem[];   // (the no-swizzle operand layout only needs 16-byte alignment)
-  uint8_t* sW1 = smem + S::w;
-  uint8_t* sW2 = sW1 + 64 * SA1_XK * 2;
-  uint8_t* sW3 = sW2 + 64 * SA1_XK * 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
-  uint64_t* full_bars = bars + SA1_NWG;            // [NWG][2]: neighbour lists of a round are ready
-  uint64_t* empty_bars = bars + 3 * SA1_NWG;       // [NWG][2]: the round's lists have been consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * 5 * SA1_NWG);
-  uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + S::bstart);
-  float* sx = reinterpret_cast<float*>(smem + S::pts);
-  float* sy = sx + N;
-  float* sz = sy + N;
-  uint16_t* sidx = reinterpret_cast<uint16_t*>(sz + N);
-
-  const int b = blockIdx.x;
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
-  const bool producer = warp >= 4 * SA1_NWG;                         // warps 16..19: ball-query producers
-  const int g = producer ? warp - 4 * SA1_NWG : warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
-  uint8_t* X = smem + S::x + (size_t)g * 128 * SA1_XK * 2;
-  uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::idx) + (size_t)g * 2 * 4 * 128;   // [2 slots][4][128]
-  int* red = reinterpret_cast<int*>(smem + S::red) + g * 4 * 64;
-  const float4* cl = reinterpret_cast<const float4*>(cloud) + (size_t)b * N;
-
-  stage_weight(gw1, 64, SA1_XK, sW1);
-  stage_weight(gw2, 64, SA1_XK, sW2);
-  stage_weight(gw3, 64, SA1_XK, sW3);
-  // ---- hash-grid build (counting sort of the cloud by bucket); the counters alias the operand buffers
-  {
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + S::x);
-    __shared__ uint32_t wsum[16];
-    for (int i = threadIdx.x; i < SA1_BUCKETS; i += blockDim.x) cnt[i] = 0u;
-    __syncthreads();
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
-      const float4 v = __ldg(cl + k);
-      atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u);
-    }
-    __syncthreads();
-    constexpr int PER = SA1_BUCKETS / 512;               // buckets per scanning thread (threads 0..511 scan)
-    const bool scanner = threadIdx.x < 512;
-    uint32_t loc[PER], sum = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) { loc[i] = scanner ? cnt[threadIdx.x * PER + i] : 0u; sum += loc[i]; }
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-    if (lane == 31 && scanner) wsum[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t v = lane < 16 ? wsum[lane] : 0u, iv = v;
-#pragma unroll
-      for (int o = 1; o < 16; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
-      if (lane < 16) wsum[lane] = iv - v;
-    }
-    __syncthreads();
-    if (scanner) {
-      uint32_t run = wsum[threadIdx.x >> 5] + inc - sum;
-#pragma unroll
-      for (int i = 0; i < PER; ++i) { bstart[threadIdx.x * PER + i] = (uint16_t)run; cnt[threadIdx.x * PER + i] = run; run += loc[i]; }
-    }
-    if (threadIdx.x == 0) bstart[SA1_BUCKETS] = (uint16_t)N;
-    __syncthreads();
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
-      const float4 v = __ldg(cl + k);
-      const uint32_t pos = atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u);
-      sx[pos] = v.x; sy[pos] = v.y; sz[pos] = v.z; sidx[pos] = (uint16_t)k;
-    }
-    __syncthreads();
-  }
-  // persistent tail of every operand row: chunk 8 = [1.0, 0...], chunk 9 = 0
-  if (!producer) {
-    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 9, KC)) = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 5 * SA1_NWG; ++i) mbar_init(&bars[i], 1);
-    mbar_fence_init();
-  }
-  if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 256);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot + (uint32_t)g * 64;
-  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
-  const uint64_t dX = tile_desc(smem_u32(X), SA1_XK, 0, 0), dW1 = tile_desc(smem_u32(sW1), SA1_XK, 0, 0);
-  const uint64_t dW2 = tile_desc(smem_u32(sW2), SA1_XK, 0, 0), dW3 = tile_desc(smem_u32(sW3), SA1_XK, 0, 0);
-  uint64_t* bar = &bars[g];
-  uint32_t phase = 0;
-  bool ok = true;
-  constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
-  const unsigned lt = (1u << lane) - 1u;
-
-  // Ball queries run on a dedicated producer warp per warpgroup, two rounds (of 4 centroids) ahead of the MLP through a
-  // 2-slot ring of neighbour lists guarded by full/empty mbarriers, so the query latency overlaps the tensor pipeline.
-  uint16_t* wcand = reinterpret_cast<uint16_t*>(smem + S::hits) + (size_t)g * 256;   // producer: candidates, then hits (in place)
-  uint64_t* fullb = full_bars + g * 2;
-  uint64_t* emptyb = empty_bars + g * 2;
-  if (producer) {
-    int r = 0;
-    for (int base = g * 4; base < SA1_NPOINT; base += SA1_NWG * 4, ++r) {
-      const int slot = r & 1;
-      if (r >= 2) mbar_wait(&emptyb[slot], ((r >> 1) - 1) & 1);
-      for (int cc = 0; cc < 4; ++cc) {
-        const int jc = base + cc;
-        uint16_t* widx = lists + (slot * 4 + cc) * 128;
-    {
-      const float* cpw = new_xyz + ((size_t)b * SA1_NPOINT + jc) * 3;
-      const float qx = cpw[0], qy = cpw[1], qz = cpw[2];
-      const int ix = grid_coord(qx), iy = grid_coord(qy), iz = grid_coord(qz);
-      uint32_t bk = 0x10000u + lane;   // lanes >= 27: unique dummies
-      if (lane < 27) bk = grid_bucket(ix + (lane % 3) - 1, iy + ((lane / 3) % 3) - 1, iz + (lane / 9) - 1);
-      const unsigned peers = __match_any_sync(0xffffffffu, bk);
-      const bool leader = lane < 27 && lane == __ffs(peers) - 1;   // one lane per distinct bucket
-      int s0 = 0, n0 = 0;
-      if (leader) { s0 = bstart[bk]; n0 = bstart[bk + 1] - s0; }
-      int incl = n0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-      const int C = __shfl_sync(0xffffffffu, incl, 31);            // candidates in the 27 cells
-      if (C <= 256) {
-        for (int i = 0, o = incl - n0; i < n0; ++i) wcand[o + i] = (uint16_t)(s0 + i);
-        __syncwarp();
-        int H = 0;
-        for (int c0 = 0; c0 < C; c0 += 32) {
-          const int ci = c0 + lane;
-          bool hit = false;
-          int p = 0;
-          if (ci < C) { p = wcand[ci]; hit = dist2(qx, qy, qz, sx[p], sy[p], sz[p]) < r2; }
-          const unsigned hm = __ballot_sync(0xffffffffu, hit);
-          if (hit) wcand[H + __popc(hm & lt)] = sidx[p];           // in place: write position <= read position
-          H += __popc(hm);
-          __syncwarp();
-        }
-        for (int h = lane; h < H; h += 32) {
-          const int my = wcand[h];
-          int rank = 0;
-          for (int i = 0; i < H; ++i) rank += wcand[i] < my;
-          if (rank < NS) widx[rank] = (uint16_t)my;
-        }
-        __syncwarp();
-        const uint16_t first = H > 0 ? widx[0] : (uint16_t)0;
-        for (int l = min(H, NS) + lane; l < NS; l += 32) widx[l] = first;
-      } else {
-        // very dense neighbourhood: pointnet2's linear scan in index order, straight from global memory
-        int cnt = 0;
-        uint16_t first = 0;
-        for (int k0 = 0; k0 < N && cnt < NS; k0 += 32) {
-          const int k = k0 + lane;
-          bool hit = false;
-          if (k < N) { const float4 v = __ldg(cl + k); hit = dist2(qx, qy, qz, v.x, v.y, v.z) < r2; }
-          const unsigned hm = __ballot_sync(0xffffffffu, hit);
-          if (hm && cnt == 0) first = (uint16_t)(k0 + __ffs(hm) - 1);
-          const int pos = cnt + __popc(hm & lt);
-          if (hit && pos < NS) widx[pos] = (uint16_t)k;
-          cnt += __popc(hm);
-        }
-        for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
-      }
-    }
-        __syncwarp();
-      }
-      if (lane == 0) mbar_arrive(&fullb[slot]);
-    }
-  } else {
-  int r = 0;
-  for (int base = g * 4; base < SA1_NPOINT && ok; base += SA1_NWG * 4, ++r) {
-    const int slot = r & 1;
-    const uint16_t* gidx = lists + slot * 4 * 128;
-    TL_MARK(16);
-    ok = mbar_wait(&fullb[slot], (r >> 1) & 1);
-    TL_MARK(17);
-    // the gathered point of the next centroid is fetched (global / L2) while the current one is in the tensor pipe
-    float4 pn = __ldg(cl + gidx[t]);
-    const float* cpn = new_xyz + ((size_t)b * SA1_NPOINT + base) * 3;
-    float nx = cpn[0], ny = cpn[1], nz = cpn[2];
-#pragma unroll 1
-    for (int cc = 0; cc < 4 && ok; ++cc) {
-    const int j = base + cc;
-    const float cx = nx, cy = ny, cz = nz;
-    const float4 p = pn;
-    if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = gidx[cc * 128 + t];
-    // ---- gather row t: [dx, dy, dz, mask, 0 x4 | 0 x8 | ... | 1, 0 x7 | 0 x8]
-    {
-      const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
-      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u);
-      *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KC)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    TL_MARK(18);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    wg_sync4(g);
-    TL_MARK(19);
-    // ---- layer 1: only K-steps 0 (inputs) and 4 (ones column -> bias) are non-zero
-    if (wq == 0) {
-      tc_fence_after();
-      if (elect_one()) {
-        mma_bf16_ss_off(tmem, dX, 0, dW1, 0, IDESC, 0);
-        mma_bf16_ss_off(tmem, dX, 64, dW1, 64, IDESC, 1);
-        mma_commit(bar);
-      }
-      __syncwarp();
-    }
-    if (cc < 3) {
-      pn = __ldg(cl + gidx[(cc + 1) * 128 + t]);
-      const float* cq = new_xyz + ((size_t)b * SA1_NPOINT + j + 1) * 3;
-      nx = cq[0]; ny = cq[1]; nz = cq[2];
-    }
-    TL_MARK(20);
-#pragma unroll 1
-    for (int layer = 1; layer < 3; ++layer) {
-      ok = ok && mbar_wait(bar, phase); phase ^= 1;
-      tc_fence_after();
-      TL_MARK(21);
-      // epilogue: relu + bf16 pack, 64 columns -> chunks 0..7 of this row
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tlane + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, (c0 >> 3) + q, KC)) =
-              make_uint4(cvt_relu_bf16x2(__uint_as_float(v[q * 8]), __uint_as_float(v[q * 8 + 1])),
-                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])),
-                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
-                         cvt_relu_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
-      }
-      TL_MARK(22);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      wg_sync4(g);
-      TL_MARK(23);
-      if (wq == 0) {
-        tc_fence_after();
-        const uint64_t dW = layer == 1 ? dW2 : dW3;
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < SA1_XK / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW, ks * 16, IDESC, ks > 0);
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
-      TL_MARK(24);
-    }
-    ok = ok && mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
-    TL_MARK(25);
-    // ---- pool: max over the 128 rows of D[128][64]
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tlane + c0, v);
-      tmem_ld_wait();
-      int keep = 0;
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const int mx = __reduce_max_sync(0xffffffffu, (int)v[q]);
-        keep = lane == q ? mx : keep;
-      }
-      red[wq * 64 + c0 + lane] = keep;
-    }
-    tc_fence_before();
-    wg_sync4(g);
-    if (t < 64) {
-      const int m = max(max(red[t], red[64 + t]), max(red[128 + t], red[192 + t]));
-      out_bf16[((size_t)b * SA1_NPOINT + j) * 64 + t] = __float2bfloat16_rn(fmaxf(__int_as_float(m), 0.f));
-    }
-    TL_MARK(26);
-    }
-    wg_sync4(g);
-    if (t == 0) mbar_arrive(&emptyb[slot]);   // the producer may refill this slot
-  }
-  }
-  if (!ok && t == 0) atomicExch(err, 1);
-  tc_fence_before();
-  __syncthreads();
-  if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, 256);
 }
 
 // ---------------------------------------------------------------------------------------------- SA1, 6 warpgroups
@@ -1190,20 +633,6 @@ __global__ void widen_kernel(const __nv_bfloat16* __restrict__ src, int rows, in
   dst[i] = __bfloat162float(src[r * src_stride + c]);
 }
 
-// phase timeline buffer (32 x int64 cycles: 0..15 SA2, 16..31 SA1), enabled by MPN_TC_TIMELINE=1 in the environment
-long long* tc_timeline(mpn_ctx* c) {
-  static std::map<mpn_ctx*, long long*> bufs;
-  static const bool on = getenv("MPN_TC_TIMELINE") != nullptr;
-  if (!on) return nullptr;
-  auto it = bufs.find(c);
-  if (it != bufs.end()) return it->second;
-  long long* p = nullptr;
-  cudaMalloc(&p, 48 * sizeof(long long));
-  cudaMemset(p, 0, 48 * sizeof(long long));
-  bufs[c] = p;
-  return p;
-}
-
 int* tc_error_flag(mpn_ctx* c) {
   static std::map<mpn_ctx*, int*> flags;
   auto it = flags.find(c);
@@ -1226,10 +655,9 @@ template <int MODULE>
 static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
                         int B, __nv_bfloat16* out, int out_stride, int32_t* ball_idx = nullptr) {
   TcWeights& tw = g_tc[c];
-  // SA1 variants: default = 7 row warpgroups (72 registers) with the grid index on chip; MPN_SA1_WG=6 uses 6 groups,
-  // MPN_SA1_WG=4 selects the 4-group kernel with producer warps and the sorted cloud in shared memory.
+  // SA1: 7 row warpgroups (72 registers) with the grid index on chip; MPN_SA1_WG=6 runs 6 groups (A/B switch)
   static const int sa1_wg = getenv("MPN_SA1_WG") ? atoi(getenv("MPN_SA1_WG")) : 7;
-  if (MODULE == 0 && sa1_wg != 4) {
+  if (MODULE == 0) {
     MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
     MPN_REQUIRE(N < 65536, "tensor-core SA1: at most 65535 points");
     if (sa1_wg != 6) {
@@ -1249,20 +677,8 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;
   }
-  if (MODULE == 0) {
-    size_t smem1 = Sa1Smem::total(N);
-    MPN_REQUIRE(smem1 <= 227 * 1024, "tensor-core SA1: %d points do not fit shared memory", N);
-    MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
-    MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    sa1_tc_kernel<<<B, SA1_THREADS, smem1, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
-                                                 tc_error_flag(c), ball_idx, tc_timeline(c));
-    c->launches++;
-    MPN_CHECK_CUDA(cudaGetLastError());
-    return MPN_OK;
-  }
   MPN_REQUIRE(N == SA1_NPOINT, "tensor-core SA2 expects the 512 SA1 centroids as input points");
-  static const bool three = getenv("MPN_SA2_2WG") == nullptr;   // default: 3 warpgroups; MPN_SA2_2WG=1 selects the 2-group kernel
-  if (three) {
+  {
     size_t smem3 = Sa2wSmem::total;
     MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2w3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     sa2w3_tc_kernel<<<B, SA2W_THREADS, smem3, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.w2_nofold,
@@ -1271,13 +687,6 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;
   }
-  size_t smem = Sa2Smem::total;
-  MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sa2_tc_kernel<<<B, SA2_THREADS, smem, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.sa[1][1], tw.sa[1][2],
-                                     c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx, tc_timeline(c));
-  c->launches++;
-  MPN_CHECK_CUDA(cudaGetLastError());
-  return MPN_OK;
 }
 
 // per-module entry (tests / mpn_sa_forward with MPN_PREC_BF16): fp32 in, fp32 out, bf16 inside

@@ -124,11 +124,6 @@ class Engine:
     def _empty(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
-    def tc_timeline(self):
-        out = (C.c_int64 * 48)()
-        _lib.check(self.lib.mpn_tc_timeline(self._ctx, out))
-        return list(out)
-
     def tc_error(self) -> bool:
         v = C.c_int(0)
         _lib.check(self.lib.mpn_tc_error(self._ctx, C.byref(v)))
