@@ -121,6 +121,13 @@ int mpn_sdf_points(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, co
  * run_inference.py:93-134): q0 [B][7] unnormalised, target [B][12] right_gripper pose -> cloud [B][Nr+No+Nt][4] */
 int mpn_build_cloud(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* q0, const float* target,
                     uint32_t problem0, float* cloud);
+/* run_inference.make_point_cloud_from_problem (run_inference.py:58-90), for problems that carry an obstacle point cloud
+ * (PlanningProblem.obstacle_point_cloud, mpinets_types.py:44): obstacle rows = a random subset WITHOUT replacement of
+ * obstacle_points [B][max_points][3] restricted to the first obstacle_counts[b] rows (counts >= n_obstacle, as
+ * np.random.choice(replace=False) requires; smaller counts wrap around instead of raising). */
+int mpn_build_cloud_from_points(mpn_ctx* ctx, void* stream, int B, const float* q0, const float* target,
+                                const float* obstacle_points, const int32_t* obstacle_counts, int max_points,
+                                uint32_t problem0, float* cloud);
 /* validation collision sweep (model.py:293-314): traj [B][T][7] unnormalised -> flags u8 [B] (OR-ed into existing
  * content when accumulate != 0), first_step i32 [B] (optional; step index offset by t0; -1 when none) */
 int mpn_sweep_flags(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* traj, int T, int t0,

@@ -462,6 +462,20 @@ int mpn_build_cloud(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, con
   return launch_build_cloud(c, (cudaStream_t)stream, *scene, B, c->ws.frames, target, problem0, cloud);
 }
 
+int mpn_build_cloud_from_points(mpn_ctx* c, void* stream, int B, const float* q0, const float* target, const float* obstacle_points,
+                                const int32_t* obstacle_counts, int max_points, uint32_t problem0, float* cloud) {
+  REQ_CTX(c); REQ_TABLES(c);
+  MPN_REQUIRE(q0 && target && cloud && obstacle_points && obstacle_counts && max_points >= 1, "mpn_build_cloud_from_points: bad arguments");
+  if (B == 0) return MPN_OK;
+  int r;
+  if ((r = ensure_workspace(c, B))) return r;
+  StageTimer t(c, (cudaStream_t)stream, MPN_ST_BUILD_CLOUD);
+  if ((r = launch_fk(c, (cudaStream_t)stream, q0, B, c->ws.frames, nullptr))) return r;
+  mpn_scene none{};
+  return launch_build_cloud(c, (cudaStream_t)stream, none, B, c->ws.frames, target, problem0, cloud, obstacle_points, obstacle_counts,
+                            max_points);
+}
+
 int mpn_sweep_flags(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* traj, int T, int t0, int accumulate,
                     uint8_t* flags, int32_t* first_step) {
   REQ_CTX(c); REQ_TABLES(c);

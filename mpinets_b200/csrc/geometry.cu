@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(256) build_cloud_kernel(mpn_scene sc, int M1, 
                                                           const float* __restrict__ target, int Nr, int No, int Nt, int P,
                                                           const float* __restrict__ lp, const int32_t* __restrict__ lid,
                                                           int Pe, const float* __restrict__ ee, uint32_t seed_lo,
-                                                          uint32_t seed_hi, uint32_t problem0, float4* __restrict__ cloud) {
+                                                          uint32_t seed_hi, uint32_t problem0, float4* __restrict__ cloud,
+                                                          const float* __restrict__ obs_points, const int32_t* __restrict__ obs_count,
+                                                          int obs_max) {
   __shared__ float F[MPN_NLINK * 12];
   __shared__ float TG[12];
   __shared__ uint32_t start[MAX_PRIMS + 1];
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(256) build_cloud_kernel(mpn_scene sc, int M1, 
   uint32_t problem = problem0 + (uint32_t)b;
   for (int i = threadIdx.x; i < MPN_NLINK * 12; i += blockDim.x) F[i] = frames[(size_t)b * MPN_NLINK * 12 + i];
   if (threadIdx.x < 12) TG[threadIdx.x] = target[(size_t)b * 12 + threadIdx.x];
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !obs_points) {
     // geometry.py:590-599: proportions in double, cuboids then cylinders, zero-volume skipped
     double area[MAX_PRIMS];
     int Pn = 0;
@@ -255,7 +257,22 @@ __global__ void __launch_bounds__(256) build_cloud_kernel(mpn_scene sc, int M1, 
     }
   }
   // obstacle rows
-  {
+  if (obs_points) {
+    // run_inference.make_point_cloud_from_problem (run_inference.py:58-90): a subset without replacement of a given cloud
+    const int cnt = min(obs_count[b], obs_max);
+    uint32_t key[4];
+    philox4x32(0u, problem, STREAM_OBS_PERM, 0u, seed_lo, seed_hi, key);
+    const uint32_t half = feistel_bits((uint32_t)max(cnt, 1)) / 2;
+    const float* src = obs_points + (size_t)b * obs_max * 3;
+    for (int j = threadIdx.x; j < No; j += blockDim.x) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 1.0f);
+      if (cnt > 0) {
+        const uint32_t e = feistel_perm((uint32_t)(j % cnt), (uint32_t)cnt, half, key);
+        o.x = src[3 * e]; o.y = src[3 * e + 1]; o.z = src[3 * e + 2];
+      }
+      out[Nr + j] = o;
+    }
+  } else {
     int Pn = nvalid;
     if (Pn == 0) {
       for (int j = threadIdx.x; j < No; j += blockDim.x) out[Nr + j] = make_float4(0.f, 0.f, 0.f, 1.0f);
@@ -300,11 +317,11 @@ __global__ void __launch_bounds__(256) build_cloud_kernel(mpn_scene sc, int M1, 
 }
 
 int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* frames, const float* target,
-                       uint32_t problem0, float* cloud) {
+                       uint32_t problem0, float* cloud, const float* obs_points, const int32_t* obs_count, int obs_max) {
   build_cloud_kernel<<<B, 256, 0, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, frames, target, c->cfg.n_robot,
                                        c->cfg.n_obstacle, c->cfg.n_target, c->P, c->link_points, c->link_ids, c->Pe,
                                        c->ee_points, (uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32), problem0,
-                                       (float4*)cloud);
+                                       (float4*)cloud, obs_points, obs_count, obs_max);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

@@ -244,6 +244,20 @@ class Engine:
         _lib.check(self.lib.mpn_build_cloud(self._ctx, self.stream, C.byref(s), B, _p(q0), _p(target), problem0, _p(cloud)))
         return cloud
 
+    def build_cloud_from_points(self, q0: torch.Tensor, target: torch.Tensor, obstacle_points: torch.Tensor,
+                                obstacle_counts: torch.Tensor, problem0: int = 0):
+        """run_inference.make_point_cloud_from_problem (run_inference.py:58-90): obstacle_points [B,P,3], counts i32 [B]"""
+        _check(q0, "q0", device=self.device); _check(target, "target", device=self.device)
+        _check(obstacle_points, "obstacle_points", device=self.device)
+        _check(obstacle_counts, "obstacle_counts", torch.int32, self.device)
+        B = q0.shape[0]
+        if obstacle_points.shape[0] != B or obstacle_points.shape[2] != 3:
+            raise RuntimeError(f"obstacle_points must be [B, P, 3], got {tuple(obstacle_points.shape)}")
+        cloud = self._empty(B, self.n_points, 4)
+        _lib.check(self.lib.mpn_build_cloud_from_points(self._ctx, self.stream, B, _p(q0), _p(target), _p(obstacle_points),
+                                                        _p(obstacle_counts), obstacle_points.shape[1], problem0, _p(cloud)))
+        return cloud
+
     def sweep_flags(self, scene, traj: torch.Tensor):
         _check(traj, "traj", device=self.device)
         B, T, _ = traj.shape

@@ -151,6 +151,16 @@ def problems_to_soa(problems: Sequence[PlanningProblem], max_cuboids: int = 40, 
                 max(1, max(sum(_is_cylinder(o) for o in g) for g in groups)))
     out["target_volume"] = primitives_to_soa(tv, *counts(tv))
     out["negative_volumes"] = primitives_to_soa(nv, *counts(nv))
+    # problems that carry a sensed obstacle cloud (mpinets_types.py:44; filled by convert_primitive_problems_to_depth,
+    # run_inference.py:194-257): padded [B, Pmax, 3] + valid counts for mpn_build_cloud_from_points
+    clouds = [None if p.obstacle_point_cloud is None else np.asarray(p.obstacle_point_cloud, dtype=np.float32)[:, :3] for p in problems]
+    if all(c is not None for c in clouds) and B > 0:
+        pmax = max(len(c) for c in clouds)
+        pts = np.zeros((B, pmax, 3), np.float32)
+        for b, c in enumerate(clouds):
+            pts[b, : len(c)] = c
+        out["obstacle_points"] = pts
+        out["obstacle_counts"] = np.array([len(c) for c in clouds], np.int32)
     assert out["q0"].shape == (B, 7)
     return out
 

@@ -27,7 +27,10 @@ def run_problems(mdl: MotionPolicyNetwork, problems: Sequence[PlanningProblem], 
     scene = {k: dev(soa[k]) for k in SCENE_KEYS}
     q0, target = dev(soa["q0"]), dev(soa["target"])
     eng = mdl.sync_engine(device)
-    cloud = eng.build_cloud(scene, q0, target, problem0=problem0)
+    if "obstacle_points" in soa:     # make_point_cloud_from_problem (run_inference.py:58-90): sensed obstacle clouds
+        cloud = eng.build_cloud_from_points(q0, target, dev(soa["obstacle_points"]), dev(soa["obstacle_counts"]), problem0=problem0)
+    else:                            # make_point_cloud_from_primitives (run_inference.py:93-134)
+        cloud = eng.build_cloud(scene, q0, target, problem0=problem0)
     traj, metrics = eng.rollout(scene, cloud, q0, target, max_steps, early_exit=True, precision=PRECISIONS[mdl.precision])
     num_poses = (metrics[:, 2].to(torch.int32) + 1).contiguous()          # MPN_M_STEPS + the start configuration
     ev = evaluator or Evaluator(eng)

@@ -294,6 +294,20 @@ def build_cloud(q0, target, scene, tables, seed, n_robot=2048, n_obs=4096, n_tgt
     return cloud
 
 
+def build_cloud_from_points(q0, target, obs_points, obs_count, tables, seed, n_robot=2048, n_obs=4096, n_tgt=128, problem0=0):
+    """run_inference.make_point_cloud_from_problem (run_inference.py:58-90): obstacle rows = random subset of a given cloud"""
+    q0, pq = _f(q0); B = q0.shape[0]
+    tg, ptg = _f(np.asarray(target).reshape(B, 12))
+    op, pop = _f(obs_points); oc, poc = _i(obs_count)
+    lp, plp = _f(tables.link_points); li, pli = _i(tables.link_ids); ee, pee = _f(tables.ee_points)
+    cloud = np.zeros((B, n_robot + n_obs + n_tgt, 4), np.float32)
+    lib().mpn_oracle_build_cloud_from_points(C.c_int(B), pq, ptg, C.c_float(tables.prismatic), C.c_int(lp.shape[0]), plp, pli,
+                                             C.c_int(ee.shape[0]), pee, C.c_int(n_robot), C.c_int(n_obs), C.c_int(n_tgt),
+                                             C.c_int(op.shape[1]), pop, poc, C.c_uint64(seed), C.c_uint32(problem0),
+                                             cloud.ctypes.data_as(C.POINTER(C.c_float)))
+    return cloud
+
+
 # ----------------------------------------------------------------------------- pointnet2_ops restatement
 def fps(xyz, npoint):
     """xyz [B,N,3|4] -> idx i32 [B,npoint]"""

@@ -189,3 +189,9 @@ def test_run_inference_surface(state_dict):
     assert list(ev.groups) == ["tabletop, task_oriented", "cubby, neutral_start"]
     assert len(ev.groups["tabletop, task_oriented"]["success"]) == 4 and len(ev.groups["cubby, neutral_start"]["success"]) == 2
     ev.print_overall_metrics()
+    # problems that carry a sensed obstacle cloud go through make_point_cloud_from_problem (run_inference.py:58-90)
+    rng = np.random.default_rng(0)
+    for q in probs:
+        q.obstacle_point_cloud = rng.uniform(-1, 1, (int(rng.integers(4096, 6000)), 3)).astype(np.float32)
+    out2 = run_problems(mdl, probs, max_steps=2)
+    assert out2["trajectories"].shape == (6, 3, 7) and torch.isfinite(out2["eval"]).all()

@@ -576,3 +576,15 @@ def test_sparc_matches_reference_fixture(engine, oracle):
     got = engine.sparc(torch.from_numpy(prof).cuda(), 12.5).cpu().numpy()
     exp = np.array([oracle.sparc(prof[b], 12.5) for b in range(9)])
     assert got[3] == 0.0 and np.abs(got - exp).max() < 5e-4
+
+
+def test_build_cloud_from_obstacle_points_bit_exact(engine, oracle, tables):
+    """mpn_build_cloud_from_points (run_inference.make_point_cloud_from_problem, run_inference.py:58-90)"""
+    p = _problems(2, 5)
+    rng = np.random.default_rng(0)
+    counts = np.array([9000, 4096, 5000, 4097, 8191], np.int32)
+    pts = rng.uniform(-1, 1, (5, 9000, 3)).astype(np.float32)
+    got = engine.build_cloud_from_points(torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda(),
+                                         torch.from_numpy(pts).cuda(), torch.from_numpy(counts).cuda(), problem0=11).cpu().numpy()
+    exp = oracle.build_cloud_from_points(p["q0"], p["target"], pts, counts, tables, engine.cfg.seed, problem0=11)
+    assert np.array_equal(got, exp)

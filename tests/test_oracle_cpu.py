@@ -515,3 +515,22 @@ def test_oracle_sparc_matches_reference(oracle):
         n = int(g["num"][b])
         assert abs(oracle.sparc(g["profiles"][b, :n], float(g["fs"])) - g["sal"][b]) < 1e-12
     assert oracle.sparc(np.zeros(30), 12.5) == 0.0
+
+
+def test_oracle_cloud_from_obstacle_points(oracle, tables):
+    """make_point_cloud_from_problem (run_inference.py:58-90): the obstacle rows are a duplicate-free subset of the given
+    cloud; robot and target rows are the ones of the primitive-based build"""
+    p = scenes.config_problems(2, 3)
+    rng = np.random.default_rng(0)
+    counts = np.array([9000, 4096, 5000], np.int32)
+    pts = rng.uniform(-1, 1, (3, 9000, 3)).astype(np.float32)
+    seed = 0x4D50694E
+    c = oracle.build_cloud_from_points(p["q0"], p["target"], pts, counts, tables, seed, problem0=5)
+    ref = oracle.build_cloud(p["q0"], p["target"], p, tables, seed, problem0=5)
+    assert np.array_equal(c[:, :2048], ref[:, :2048]) and np.array_equal(c[:, 6144:], ref[:, 6144:])
+    assert (c[:, 2048:6144, 3] == 1).all()
+    for b in range(3):
+        rows = {tuple(r) for r in c[b, 2048:6144, :3]}
+        pool = {tuple(r) for r in pts[b, : counts[b]]}
+        assert len(rows) == 4096 and rows <= pool            # without replacement, only from the valid prefix
+    assert not np.array_equal(c[0, 2048:6144], oracle.build_cloud_from_points(p["q0"], p["target"], pts, counts, tables, seed, problem0=6)[0, 2048:6144])
