@@ -196,6 +196,32 @@ int mpn_bc_collision_losses(mpn_ctx* ctx, void* stream, const mpn_scene* scene, 
                             const float* target_normalized, int n_points, float margin, float w_collision, float w_bc,
                             float* losses, float* grad_input);
 
+/* ---- training step (TrainingMotionPolicyNetwork.training_step, model.py:185-240) ------------------------------------------
+ * Parameters live in ONE flat fp32 device vector in state-dict order (SA_modules.{0,1,2}.mlps.0.{0,2,4}.{weight,bias},
+ * fc_layer.{0,1,3,4,6}, feature_encoder.{0..8}, decoder.{0..6}), every tensor starting at a multiple of 4 floats;
+ * gradients use the same layout, so the host all-reduces one vector (DDP, run_training.py:71-77) and the optimiser is one
+ * pass.  mpn_param_info enumerates the tensors (returns MPN_ERR_INVALID past the last index). */
+int64_t mpn_param_count(mpn_ctx* ctx);
+int mpn_param_info(mpn_ctx* ctx, int index, char* name, int name_cap, int64_t* offset, int64_t* numel);
+int mpn_get_params(mpn_ctx* ctx, void* stream, float* dst /* device [param_count] */);
+int mpn_set_params(mpn_ctx* ctx, void* stream, const float* src /* device [param_count] */);
+/* rebuilds the packed bf16 tensor-core copies from the fp32 parameters (after optimisation, before MPN_PREC_BF16 inference);
+ * synchronises the device */
+int mpn_weights_sync(mpn_ctx* ctx);
+/* forward (fp32, state saved for the backward pass) -> y_hat = clamp(q_norm + net(cloud, q_norm), -1, 1) (model.py:202) ->
+ * losses[0] = collision loss, losses[1] = point-match loss of CollisionAndBCLossContainer (loss.py:111-166) against
+ * `supervision` [B][7] -> grads [param_count] = d(w_collision * losses[0] + w_bc * losses[1]) / d parameters (overwritten;
+ * NULL: forward + losses only).  cloud [B][N][4], q_norm [B][7] in [-1, 1]; y_hat [B][7] optional output.
+ * The reference's values: n_loss_points 1024, margin 0.03 (loss.py:92,109), w_collision 5, w_bc 1 (jobconfig.yaml:24-25). */
+int mpn_train_step_grads(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, int N, const float* cloud,
+                         const float* q_norm, const float* supervision, int n_loss_points, float margin, float w_collision,
+                         float w_bc, float* losses, float* y_hat, float* grads);
+/* torch.nn.utils.clip_grad_norm_(max_norm = clip_norm; <= 0 disables; run_training.py:112 uses 1.0) followed by
+ * torch.optim.Adam (model.py:68-73: lr 1e-4, betas (0.9, 0.999), eps 1e-8) on the flat vector; `step` counts from 1;
+ * grad_norm (optional, device float) receives the total gradient norm before clipping. */
+int mpn_adam_step(mpn_ctx* ctx, void* stream, const float* grads, float lr, float beta1, float beta2, float eps,
+                  float clip_norm, int step, float* grad_norm);
+
 /* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
 int64_t mpn_launch_count(mpn_ctx* ctx);
 

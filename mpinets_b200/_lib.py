@@ -24,7 +24,8 @@ EXPORTS = (
     "mpn_load_weight", "mpn_weights_finalize", "mpn_fps", "mpn_ball_query", "mpn_gather_points", "mpn_group_points",
     "mpn_sa_forward", "mpn_fk", "mpn_sample_robot", "mpn_compute_spheres", "mpn_normalize_joints",
     "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_build_cloud_from_points", "mpn_sweep_flags", "mpn_evaluate", "mpn_sparc", "mpn_collision_loss", "mpn_point_match_loss", "mpn_bc_collision_losses", "mpn_encoder_forward",
-    "mpn_policy_forward", "mpn_rollout", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error",
+    "mpn_policy_forward", "mpn_rollout", "mpn_param_count", "mpn_param_info", "mpn_get_params", "mpn_set_params", "mpn_weights_sync",
+    "mpn_train_step_grads", "mpn_adam_step", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error",
 )
 
 
@@ -57,6 +58,7 @@ def load():
     lib.mpn_last_error.restype = C.c_char_p
     lib.mpn_version.restype = C.c_char_p
     lib.mpn_launch_count.restype = C.c_int64
+    lib.mpn_param_count.restype = C.c_int64
     P, I, F, U32 = C.c_void_p, C.c_int, C.c_float, C.c_uint32
     SC = C.POINTER(MpnScene)
     sigs = {
@@ -89,6 +91,13 @@ def load():
         "mpn_policy_forward": [P, P, I, P, P, I, I, P],
         "mpn_rollout": [P, P, I, SC, I, I, P, P, P, I, I, I, P, P],
         "mpn_launch_count": [P],
+        "mpn_param_count": [P],
+        "mpn_param_info": [P, I, C.c_char_p, I, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+        "mpn_get_params": [P, P, P],
+        "mpn_set_params": [P, P, P],
+        "mpn_weights_sync": [P],
+        "mpn_train_step_grads": [P, P, SC, I, I, P, P, P, I, F, F, F, P, P, P],
+        "mpn_adam_step": [P, P, P, F, F, F, F, F, I, P],
         "mpn_profile": [P, I],
         "mpn_tc_error": [P, C.POINTER(C.c_int)],
         "mpn_tc_selftest": [P, P, P, P, P, I, I, I, P],
@@ -97,7 +106,7 @@ def load():
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        if name != "mpn_launch_count":
+        if name not in ("mpn_launch_count", "mpn_param_count"):
             fn.restype = C.c_int
     _lib = lib
     return lib

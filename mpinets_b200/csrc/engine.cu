@@ -83,38 +83,72 @@ static int ensure_workspace(mpn_ctx* c, int B) {
 struct HostTensor { std::vector<int64_t> shape; std::vector<float> data; };
 static std::map<mpn_ctx*, std::map<std::string, HostTensor>> g_host_weights;
 
-static int make_linear(mpn_ctx* c, const std::string& prefix, int in, int out, Linear& L) {
-  auto& hw = g_host_weights[c];
-  auto wi = hw.find(prefix + ".weight"), bi = hw.find(prefix + ".bias");
-  if (wi == hw.end() || bi == hw.end()) { set_error("missing weight %s.{weight,bias}", prefix.c_str()); return MPN_ERR_STATE; }
-  const HostTensor& W = wi->second; const HostTensor& Bv = bi->second;
-  if ((int64_t)W.data.size() != (int64_t)in * out || W.shape.size() < 2 || W.shape[0] != out || W.shape[1] != in ||
-      (int64_t)Bv.data.size() != out) {
-    set_error("weight %s has wrong shape (expected [%d,%d])", prefix.c_str(), out, in);
-    return MPN_ERR_INVALID;
-  }
-  L.in = in; L.out = out;
-  std::vector<float> wt((size_t)in * out);
-  for (int o = 0; o < out; ++o)
-    for (int i = 0; i < in; ++i) wt[(size_t)i * out + o] = W.data[(size_t)o * in + i];
-  int r = dev_upload(&L.w, W.data.data(), W.data.size());
-  if (r) return r;
-  r = dev_upload(&L.wt, wt.data(), wt.size());
-  if (r) return r;
-  return dev_upload(&L.b, Bv.data.data(), Bv.data.size());
+// Tensors live in one flat fp32 buffer (Weights::params) in state-dict order, each 4-float aligned, so the optimiser and
+// the gradient all-reduce see a single vector; Linear::w / ::b and gn_w / gn_b point into it.
+struct ParamPlan { std::string name; int64_t numel; };
+
+static std::vector<ParamPlan> param_plan() {
+  static const int sa_dims[3][4] = {{4, 64, 64, 64}, {67, 128, 128, 256}, {259, 512, 512, 1024}};
+  std::vector<ParamPlan> v;
+  char buf[128];
+  auto lin = [&](const char* prefix, int in, int out) {
+    v.push_back({std::string(prefix) + ".weight", (int64_t)in * out});
+    v.push_back({std::string(prefix) + ".bias", out});
+  };
+  for (int m = 0; m < 3; ++m)
+    for (int l = 0; l < 3; ++l) {
+      snprintf(buf, sizeof(buf), "point_cloud_encoder.SA_modules.%d.mlps.0.%d", m, 2 * l);
+      lin(buf, sa_dims[m][l], sa_dims[m][l + 1]);
+    }
+  lin("point_cloud_encoder.fc_layer.0", 1024, 4096);
+  lin("point_cloud_encoder.fc_layer.1", 1, 4096);     // GroupNorm weight / bias
+  lin("point_cloud_encoder.fc_layer.3", 4096, 2048);
+  lin("point_cloud_encoder.fc_layer.4", 1, 2048);
+  lin("point_cloud_encoder.fc_layer.6", 2048, 2048);
+  static const int fe_dims[6] = {7, 32, 64, 128, 128, 64};
+  for (int l = 0; l < 5; ++l) { snprintf(buf, sizeof(buf), "feature_encoder.%d", 2 * l); lin(buf, fe_dims[l], fe_dims[l + 1]); }
+  static const int de_dims[5] = {2112, 512, 256, 128, 7};
+  for (int l = 0; l < 4; ++l) { snprintf(buf, sizeof(buf), "decoder.%d", 2 * l); lin(buf, de_dims[l], de_dims[l + 1]); }
+  return v;
 }
 
-static int upload_vec(mpn_ctx* c, const std::string& name, int n, float** dst) {
-  auto& hw = g_host_weights[c];
-  auto it = hw.find(name);
-  if (it == hw.end() || (int)it->second.data.size() != n) { set_error("missing or mis-sized weight %s", name.c_str()); return MPN_ERR_STATE; }
-  return dev_upload(dst, it->second.data.data(), (size_t)n);
+static float* param_ptr(mpn_ctx* c, const std::string& name) {
+  for (auto& p : c->w.info) if (p.name == name) return c->w.params + p.offset;
+  return nullptr;
+}
+
+static int make_linear(mpn_ctx* c, const std::string& prefix, int in, int out, Linear& L) {
+  L.in = in; L.out = out;
+  L.w = param_ptr(c, prefix + ".weight");
+  L.b = param_ptr(c, prefix + ".bias");
+  if (!L.w || !L.b) { set_error("internal: no parameter slot for %s", prefix.c_str()); return MPN_ERR_STATE; }
+  return dev_alloc(&L.wt, (size_t)in * out);
 }
 
 static int finalize_weights(mpn_ctx* c) {
+  auto& hw = g_host_weights[c];
+  // flat buffer
+  std::vector<ParamPlan> plan = param_plan();
+  c->w.info.clear();
+  int64_t off = 0;
+  for (auto& p : plan) { c->w.info.push_back({p.name, off, p.numel}); off += (p.numel + 3) / 4 * 4; }
+  std::vector<float> flat((size_t)off, 0.f);
+  for (auto& p : c->w.info) {
+    auto it = hw.find(p.name);
+    if (it == hw.end()) { set_error("missing weight %s", p.name.c_str()); return MPN_ERR_STATE; }
+    if ((int64_t)it->second.data.size() != p.numel) {
+      set_error("weight %s has %zu elements, expected %lld", p.name.c_str(), it->second.data.size(), (long long)p.numel);
+      return MPN_ERR_INVALID;
+    }
+    memcpy(flat.data() + p.offset, it->second.data.data(), sizeof(float) * (size_t)p.numel);
+  }
+  c->w.n_params = off;
+  int r = dev_upload(&c->w.params, flat.data(), flat.size());
+  if (r) return r;
+  free_train_ws(c);   // optimiser state belongs to the previous parameter vector
+
   static const int sa_dims[3][4] = {{4, 64, 64, 64}, {67, 128, 128, 256}, {259, 512, 512, 1024}};
   char buf[128];
-  int r;
   for (int m = 0; m < 3; ++m)
     for (int l = 0; l < 3; ++l) {
       snprintf(buf, sizeof(buf), "point_cloud_encoder.SA_modules.%d.mlps.0.%d", m, 2 * l);
@@ -126,10 +160,10 @@ static int finalize_weights(mpn_ctx* c) {
     snprintf(buf, sizeof(buf), "point_cloud_encoder.fc_layer.%d", fc_idx[l]);
     if ((r = make_linear(c, buf, fc_dims[l], fc_dims[l + 1], c->w.fc[l]))) return r;
   }
-  if ((r = upload_vec(c, "point_cloud_encoder.fc_layer.1.weight", 4096, &c->w.gn_w[0]))) return r;
-  if ((r = upload_vec(c, "point_cloud_encoder.fc_layer.1.bias", 4096, &c->w.gn_b[0]))) return r;
-  if ((r = upload_vec(c, "point_cloud_encoder.fc_layer.4.weight", 2048, &c->w.gn_w[1]))) return r;
-  if ((r = upload_vec(c, "point_cloud_encoder.fc_layer.4.bias", 2048, &c->w.gn_b[1]))) return r;
+  c->w.gn_w[0] = param_ptr(c, "point_cloud_encoder.fc_layer.1.weight");
+  c->w.gn_b[0] = param_ptr(c, "point_cloud_encoder.fc_layer.1.bias");
+  c->w.gn_w[1] = param_ptr(c, "point_cloud_encoder.fc_layer.4.weight");
+  c->w.gn_b[1] = param_ptr(c, "point_cloud_encoder.fc_layer.4.bias");
   static const int fe_dims[6] = {7, 32, 64, 128, 128, 64};
   for (int l = 0; l < 5; ++l) {
     snprintf(buf, sizeof(buf), "feature_encoder.%d", 2 * l);
@@ -140,6 +174,7 @@ static int finalize_weights(mpn_ctx* c) {
     snprintf(buf, sizeof(buf), "decoder.%d", 2 * l);
     if ((r = make_linear(c, buf, de_dims[l], de_dims[l + 1], c->w.dec[l]))) return r;
   }
+  if ((r = refresh_transposes(c, 0))) return r;
   if ((r = tc_prepare_weights(c))) return r;
   c->w.finalized = true;
   g_host_weights.erase(c);
@@ -245,6 +280,8 @@ int mpn_ctx_destroy(mpn_ctx* c) {
   if (c->robot_sel4) cudaFree(c->robot_sel4);
   if (c->robot_sel_steps) cudaFree(c->robot_sel_steps);
   if (c->loss_partial) cudaFree(c->loss_partial);
+  free_train_ws(c);
+  if (c->w.params) cudaFree(c->w.params);
   delete c;
   return MPN_OK;
 }
@@ -574,6 +611,60 @@ int mpn_policy_forward(mpn_ctx* c, void* stream, int precision, const float* clo
   int r;
   if ((r = ensure_workspace(c, B))) return r;
   return policy_forward(c, (cudaStream_t)stream, precision, cloud, q_norm, B, N, dq);
+}
+
+// ---- training step (model.py:185-240, 68-73; run_training.py:112)
+int64_t mpn_param_count(mpn_ctx* c) { return (c && c->w.finalized) ? c->w.n_params : 0; }
+
+int mpn_param_info(mpn_ctx* c, int index, char* name, int name_cap, int64_t* offset, int64_t* numel) {
+  REQ_CTX(c); REQ_WEIGHTS(c);
+  if (index < 0 || index >= (int)c->w.info.size()) return MPN_ERR_INVALID;   // end-of-list marker, no message
+  const ParamInfo& p = c->w.info[index];
+  if (name && name_cap > 0) { strncpy(name, p.name.c_str(), (size_t)name_cap - 1); name[name_cap - 1] = 0; }
+  if (offset) *offset = p.offset;
+  if (numel) *numel = p.numel;
+  return MPN_OK;
+}
+
+int mpn_get_params(mpn_ctx* c, void* stream, float* dst) {
+  REQ_CTX(c); REQ_WEIGHTS(c);
+  MPN_REQUIRE(dst, "mpn_get_params: null destination");
+  MPN_CHECK_CUDA(cudaMemcpyAsync(dst, c->w.params, (size_t)c->w.n_params * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MPN_OK;
+}
+
+int mpn_set_params(mpn_ctx* c, void* stream, const float* src) {
+  REQ_CTX(c); REQ_WEIGHTS(c);
+  MPN_REQUIRE(src, "mpn_set_params: null source");
+  MPN_CHECK_CUDA(cudaMemcpyAsync(c->w.params, src, (size_t)c->w.n_params * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return refresh_transposes(c, (cudaStream_t)stream);
+}
+
+int mpn_weights_sync(mpn_ctx* c) {
+  REQ_CTX(c); REQ_WEIGHTS(c);
+  MPN_CHECK_CUDA(cudaDeviceSynchronize());
+  return tc_prepare_weights(c);
+}
+
+int mpn_train_step_grads(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, int N, const float* cloud, const float* q_norm,
+                         const float* supervision, int n_loss_points, float margin, float w_collision, float w_bc, float* losses,
+                         float* y_hat, float* grads) {
+  REQ_CTX(c); REQ_TABLES(c); REQ_WEIGHTS(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(cloud && q_norm && supervision && losses && B >= 1, "mpn_train_step_grads: bad arguments");
+  MPN_REQUIRE(N >= SA1_NPOINT && N <= 8192, "mpn_train_step_grads: N=%d unsupported (512..8192)", N);
+  MPN_REQUIRE(n_loss_points >= 1, "mpn_train_step_grads: n_loss_points must be positive");
+  if ((r = ensure_workspace(c, B))) return r;
+  return train_step_grads(c, (cudaStream_t)stream, *scene, B, N, cloud, q_norm, supervision, n_loss_points, margin, w_collision, w_bc,
+                          losses, y_hat, grads);
+}
+
+int mpn_adam_step(mpn_ctx* c, void* stream, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm,
+                  int step, float* grad_norm) {
+  REQ_CTX(c); REQ_WEIGHTS(c);
+  MPN_REQUIRE(grads && step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "mpn_adam_step: bad arguments");
+  return adam_step(c, (cudaStream_t)stream, grads, lr, beta1, beta2, eps, clip_norm, step, grad_norm);
 }
 
 int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene, int B, int N, float* cloud, const float* q0,

@@ -45,7 +45,12 @@ struct Linear {      // y = W x + b ; W [out][in] row-major fp32 (device)
   int in_pad = 0;
 };
 
+struct ParamInfo { std::string name; int64_t offset; int64_t numel; };
+
 struct Weights {
+  float* params = nullptr;        // flat fp32 master copy of every tensor, state-dict order, each tensor 4-float aligned
+  int64_t n_params = 0;           // floats in `params` (padding included)
+  std::vector<ParamInfo> info;
   Linear sa[3][3];
   Linear fc[3];           // fc_layer.0 / .3 / .6
   float* gn_w[2] = {nullptr, nullptr};
@@ -75,6 +80,28 @@ struct Workspace {
   size_t tc_scratch_bytes = 0;
 };
 
+// buffers of the training step (train.cu): everything the backward pass needs from the forward pass, for B samples,
+// plus the per-chunk compacted-row scratch of the set-abstraction backward
+struct TrainWs {
+  int capacity = 0, chunk = 0, n_points = 0;
+  int32_t *fps_idx = nullptr;                     // [B][512] scratch
+  int32_t *ball1 = nullptr, *ball2 = nullptr;     // [B][512][128], [B][128][128]
+  uint8_t *arg1 = nullptr, *arg2 = nullptr, *arg3 = nullptr;   // pooled-row index per (group, channel)
+  float *z1 = nullptr, *a1 = nullptr, *z2 = nullptr, *a2 = nullptr;   // FC head: pre-GroupNorm / post-LeakyReLU
+  float *st1 = nullptr, *st2 = nullptr;           // GroupNorm (mean, rstd) [B][16][2]
+  float *f[4] = {nullptr, nullptr, nullptr, nullptr};   // feature_encoder activations [B][32|64|128|128]
+  float *d[3] = {nullptr, nullptr, nullptr};      // decoder activations [B][512|256|128]
+  float *yhat = nullptr, *gy = nullptr;           // [B][7]
+  float *ga = nullptr, *gb = nullptr;             // gradient ping-pong [B][4096]
+  float *gcat = nullptr;                          // [B][2112]
+  float *gfeat3 = nullptr, *gfeat2 = nullptr, *gfeat1 = nullptr;   // [B][1024], [B][128][256], [B][512][64]
+  // per chunk
+  float *X = nullptr, *H1 = nullptr, *H2 = nullptr;
+  int32_t* src = nullptr; uint8_t* slot = nullptr;
+  float* partial = nullptr; size_t partial_floats = 0;   // split-reduction partials of the weight-gradient kernels
+  float* adam_m = nullptr; float* adam_v = nullptr; float* norm = nullptr;
+};
+
 }  // namespace mpn
 
 struct mpn_ctx {
@@ -96,6 +123,7 @@ struct mpn_ctx {
   float prismatic = 0.025f;
   mpn::Weights w;
   mpn::Workspace ws;
+  mpn::TrainWs tw;
   int64_t launches = 0;
   // stage profiler
   bool prof = false;
@@ -152,10 +180,16 @@ int launch_gather(mpn_ctx* c, cudaStream_t s, const float* feat, int B, int C, i
 int launch_group(mpn_ctx* c, cudaStream_t s, const float* feat, int B, int C, int N, const int32_t* idx, int m, int ns, float* out);
 // ---- sa_simt.cu : fused ball query + group + 3-layer shared MLP + max, fp32
 int launch_sa_simt(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride,
-                   int B, int N, const float* new_xyz, float* new_feats, int32_t* ball_idx);
+                   int B, int N, const float* new_xyz, float* new_feats, int32_t* ball_idx, uint8_t* arg_out = nullptr);
 // ---- linear.cu
 int launch_linear(mpn_ctx* c, cudaStream_t s, const Linear& L, const float* x, int ldx, int M, float* y, int ldy, int act);
+// Y[M][N] = act(X[M][K] * Wm[N][K]^T + bias) (* f'(mask) when mask != null: mask_mode 1 LeakyReLU(0.01), 2 ReLU); Y may alias mask
+int launch_linear_ex(mpn_ctx* c, cudaStream_t s, const float* X, int ldx, const float* Wm, int ldw, const float* bias, int64_t M, int N,
+                     int K, float* Y, int ldy, int act, const float* mask = nullptr, int ldmask = 0, int mask_mode = 0);
 int launch_groupnorm_lrelu(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta);
+// training forward: out-of-place, keeps the pre-norm input and the per-(row, group) statistics
+int launch_groupnorm_lrelu_train(mpn_ctx* c, cudaStream_t s, const float* z, int M, int C, int groups, const float* gamma,
+                                 const float* beta, float* out, float* stats);
 int launch_groupnorm_lrelu_bf16(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta,
                                 __nv_bfloat16* out);
 // ---- gemm_tc.cu (epi: 0 relu->bf16, 1 fp32, 2 relu + max over each 128-row tile -> bf16)
@@ -166,5 +200,13 @@ int launch_step_update(mpn_ctx* c, cudaStream_t s, int B, const float* dq, float
                        float* metrics, int step);
 int launch_finalize_metrics(mpn_ctx* c, cudaStream_t s, int B, const float* eef, const float* target, const uint8_t* flags,
                             const int32_t* first_step, const int32_t* done, int T, float* metrics);
+// ---- train.cu : training step (model.py:185-240) in fp32 -- forward with saved state, losses, backward, Adam
+int train_step_grads(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int N, const float* cloud, const float* q_norm,
+                     const float* supervision, int n_loss_points, float margin, float w_collision, float w_bc, float* losses,
+                     float* y_hat, float* grads);
+int adam_step(mpn_ctx* c, cudaStream_t s, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm,
+              int step, float* grad_norm_out);
+int refresh_transposes(mpn_ctx* c, cudaStream_t s);
+void free_train_ws(mpn_ctx* c);
 
 }  // namespace mpn

@@ -9,12 +9,17 @@ namespace mpn {
 // Y[M][N] = act(X[M][K] * W[N][K]^T + b).  64x64x16 tiles, 256 threads, 4x4 micro-tiles, fp32 FMA.
 constexpr int GT = 64, GK = 16;
 
-__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
-                                                     const float* __restrict__ bias, int M, int N, int K,
-                                                     float* __restrict__ Y, int ldy, int act) {
+// blockIdx.x = row tile (M can be millions of compacted rows in the training backward), blockIdx.y = column tile.
+// mask (optional): the result is multiplied by the activation derivative taken from mask[m][n] (1: LeakyReLU(0.01) of a
+// post-activation value, 2: ReLU); Y may alias mask (each element is read, then written, by the same thread).
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                                                     const float* __restrict__ bias, long long M, int N, int K,
+                                                     float* Y, int ldy, int act, const float* mask, int ldmask,
+                                                     int mask_mode) {
   __shared__ float xs[GK][GT + 4];
   __shared__ float ws[GK][GT + 4];
-  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  const long long m0 = (long long)blockIdx.x * GT;
+  const int n0 = blockIdx.y * GT;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   float acc[4][4];
 #pragma unroll
@@ -26,9 +31,10 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ X
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       int k = k0 + lk + u;
-      int m = m0 + lr, n = n0 + lr;
+      long long m = m0 + lr;
+      int n = n0 + lr;
       xs[lk + u][lr] = (m < M && k < K) ? X[(size_t)m * ldx + k] : 0.f;
-      ws[lk + u][lr] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+      ws[lk + u][lr] = (n < N && k < K) ? W[(size_t)n * ldw + k] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -47,32 +53,44 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ X
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int m = m0 + ty * 4 + i;
+    long long m = m0 + ty * 4 + i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n >= N) continue;
-      float v = acc[i][j] + bias[n];
+      float v = bias ? acc[i][j] + bias[n] : acc[i][j];
       if (act == 1) v = v > 0.f ? v : 0.01f * v;
       else if (act == 2) v = fmaxf(v, 0.f);
+      if (mask) {
+        float a = mask[(size_t)m * ldmask + n];
+        if (mask_mode == 1) v = a > 0.f ? v : 0.01f * v;
+        else v = a > 0.f ? v : 0.f;
+      }
       Y[(size_t)m * ldy + n] = v;
     }
   }
 }
 
-int launch_linear(mpn_ctx* c, cudaStream_t s, const Linear& L, const float* x, int ldx, int M, float* y, int ldy, int act) {
-  dim3 grid((L.out + GT - 1) / GT, (M + GT - 1) / GT);
-  linear_kernel<<<grid, 256, 0, s>>>(x, ldx, L.w, L.b, M, L.out, L.in, y, ldy, act);
+int launch_linear_ex(mpn_ctx* c, cudaStream_t s, const float* X, int ldx, const float* Wm, int ldw, const float* bias, int64_t M, int N,
+                     int K, float* Y, int ldy, int act, const float* mask, int ldmask, int mask_mode) {
+  if (M <= 0) return MPN_OK;
+  dim3 grid((unsigned)((M + GT - 1) / GT), (N + GT - 1) / GT);
+  linear_kernel<<<grid, 256, 0, s>>>(X, ldx, Wm, ldw, bias, (long long)M, N, K, Y, ldy, act, mask, ldmask, mask_mode);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
 }
 
+int launch_linear(mpn_ctx* c, cudaStream_t s, const Linear& L, const float* x, int ldx, int M, float* y, int ldy, int act) {
+  return launch_linear_ex(c, s, x, ldx, L.w, L.in, L.b, M, L.out, L.in, y, ldy, act);
+}
+
 // GroupNorm(groups, C) (eps 1e-5, biased variance, affine) + LeakyReLU(0.01), in place.  One warp per (row, group).
 __global__ void __launch_bounds__(256) groupnorm_lrelu_kernel(float* __restrict__ x, int M, int C, int groups,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              __nv_bfloat16* __restrict__ out_bf16) {
+                                                              __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32 = nullptr,
+                                                              float* __restrict__ stats = nullptr) {
   int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= M * groups) return;
   int row = wid / groups, g = wid % groups, gs = C / groups;
@@ -87,11 +105,13 @@ __global__ void __launch_bounds__(256) groupnorm_lrelu_kernel(float* __restrict_
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   float rstd = 1.0f / sqrtf(sq / (float)gs + 1e-5f);
+  if (stats && lane == 0) { stats[2 * (size_t)wid] = mean; stats[2 * (size_t)wid + 1] = rstd; }
   for (int i = lane; i < gs; i += 32) {
     int ch = g * gs + i;
     float v = (p[i] - mean) * rstd * gamma[ch] + beta[ch];
     v = v > 0.f ? v : 0.01f * v;
     if (out_bf16) out_bf16[(size_t)row * C + ch] = __float2bfloat16_rn(v);
+    else if (out_f32) out_f32[(size_t)row * C + ch] = v;
     else p[i] = v;
   }
 }
@@ -99,6 +119,15 @@ __global__ void __launch_bounds__(256) groupnorm_lrelu_kernel(float* __restrict_
 int launch_groupnorm_lrelu(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta) {
   int warps = M * groups;
   groupnorm_lrelu_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(x, M, C, groups, gamma, beta, nullptr);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+int launch_groupnorm_lrelu_train(mpn_ctx* c, cudaStream_t s, const float* z, int M, int C, int groups, const float* gamma,
+                                 const float* beta, float* out, float* stats) {
+  int warps = M * groups;
+  groupnorm_lrelu_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(const_cast<float*>(z), M, C, groups, gamma, beta, nullptr, out, stats);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

@@ -17,7 +17,7 @@ constexpr int SA_THREADS = 256;
 template <int K, int NOUT, int R, bool LAST>
 __device__ __forceinline__ void mlp_layer(const float* __restrict__ act_in, const float* __restrict__ wt,
                                           const float* __restrict__ bias, float* __restrict__ act_out,
-                                          float* __restrict__ omax) {
+                                          float* __restrict__ omax, int* __restrict__ oarg = nullptr, int row_base = 0) {
   constexpr int RG = R / 8;                 // row groups (8 rows per thread)
   constexpr int CG = SA_THREADS / RG;       // column groups
   constexpr int CH = (NOUT < CG * 8) ? NOUT : CG * 8;  // columns per chunk
@@ -64,12 +64,28 @@ __device__ __forceinline__ void mlp_layer(const float* __restrict__ act_in, cons
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         float m = acc[0][j];
+        if (oarg == nullptr) {
 #pragma unroll
-        for (int i = 1; i < 8; ++i) m = fmaxf(m, acc[i][j]);
-        m = fmaxf(m, 0.f);
+          for (int i = 1; i < 8; ++i) m = fmaxf(m, acc[i][j]);
+          m = fmaxf(m, 0.f);
 #pragma unroll
-        for (int o = RG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (rg == 0) omax[c0 + j] = fmaxf(omax[c0 + j], m);
+          for (int o = RG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (rg == 0) omax[c0 + j] = fmaxf(omax[c0 + j], m);
+        } else {
+          // training forward: also the pooled row (first occurrence of the maximum, like max_pool2d's argmax)
+          int mi = 0;
+#pragma unroll
+          for (int i = 1; i < 8; ++i)
+            if (acc[i][j] > m) { m = acc[i][j]; mi = i; }
+          mi += r0 + row_base;
+#pragma unroll
+          for (int o = RG / 2; o > 0; o >>= 1) {
+            float om = __shfl_xor_sync(0xffffffffu, m, o);
+            int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+          }
+          if (rg == 0 && m > omax[c0 + j]) { omax[c0 + j] = m; oarg[c0 + j] = mi; }
+        }
       }
     }
   }
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(SA_THREADS) sa_group_kernel(const float* __res
                                                               const float* __restrict__ feats, int feat_stride, int N,
                                                               const float* __restrict__ new_xyz, int npoint, float r2,
                                                               SaWeights W, float* __restrict__ out,
-                                                              int32_t* __restrict__ ball_idx) {
+                                                              int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out) {
   constexpr int R = NSAMPLE, CIN = 3 + CFEAT;
   constexpr int CA = (CIN > C2 ? CIN : C2), CB = C1;
   extern __shared__ __align__(16) float smem[];
@@ -139,11 +155,13 @@ __global__ void __launch_bounds__(SA_THREADS) sa_group_kernel(const float* __res
   int* idx_s = reinterpret_cast<int*>(omax + C3);  // [R]
   int* wl = idx_s + R;                             // [8][R]
   int* wcnt = wl + 8 * R;                          // [8]
+  int* oarg = arg_out ? wcnt + 8 : nullptr;        // [C3] (training forward only)
   const int b = blockIdx.y, j = blockIdx.x;
   const float* p = xyz + (size_t)b * N * stride;
   const float* cp = new_xyz + ((size_t)b * npoint + j) * 3;
   const float cx = cp[0], cy = cp[1], cz = cp[2];
   for (int c = threadIdx.x; c < C3; c += SA_THREADS) omax[c] = 0.f;  // post-ReLU values are >= 0
+  if (oarg) for (int c = threadIdx.x; c < C3; c += SA_THREADS) oarg[c] = 0;
   cta_ball_query<R>(p, N, stride, cx, cy, cz, r2, idx_s, wl, wcnt);
   if (ball_idx)
     for (int l = threadIdx.x; l < R; l += SA_THREADS) ball_idx[((size_t)b * npoint + j) * R + l] = idx_s[l];
@@ -172,25 +190,29 @@ __global__ void __launch_bounds__(SA_THREADS) sa_group_kernel(const float* __res
   __syncthreads();
   mlp_layer<C1, C2, R, false>(bufB, W.wt[1], W.b[1], bufA, nullptr);
   __syncthreads();
-  mlp_layer<C2, C3, R, true>(bufA, W.wt[2], W.b[2], nullptr, omax);
+  mlp_layer<C2, C3, R, true>(bufA, W.wt[2], W.b[2], nullptr, omax, oarg, 0);
   __syncthreads();
   float* o = out + ((size_t)b * npoint + j) * C3;
   for (int c = threadIdx.x; c < C3; c += SA_THREADS) o[c] = omax[c];
+  if (oarg) for (int c = threadIdx.x; c < C3; c += SA_THREADS) arg_out[((size_t)b * npoint + j) * C3 + c] = (uint8_t)oarg[c];
 }
 
 // GroupAll module (model.py:383): rows = all N points (xyz NOT centred), tiles of 32 rows, grid (B).
 template <int CFEAT, int C1, int C2, int C3>
 __global__ void __launch_bounds__(SA_THREADS) sa_all_kernel(const float* __restrict__ xyz, int stride,
                                                             const float* __restrict__ feats, int feat_stride, int N,
-                                                            SaWeights W, float* __restrict__ out) {
+                                                            SaWeights W, float* __restrict__ out,
+                                                            uint8_t* __restrict__ arg_out) {
   constexpr int R = 32, CIN = 3 + CFEAT;
   constexpr int CA = (CIN > C2 ? CIN : C2), CB = C1;
   extern __shared__ __align__(16) float smem[];
   float* bufA = smem;
   float* bufB = bufA + CA * R;
   float* omax = bufB + CB * R;
+  int* oarg = arg_out ? reinterpret_cast<int*>(omax + C3) : nullptr;   // [C3] (training forward only)
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C3; c += SA_THREADS) omax[c] = 0.f;
+  if (oarg) for (int c = threadIdx.x; c < C3; c += SA_THREADS) oarg[c] = 0;
   for (int t0 = 0; t0 < N; t0 += R) {
     __syncthreads();
     {
@@ -209,37 +231,38 @@ __global__ void __launch_bounds__(SA_THREADS) sa_all_kernel(const float* __restr
     __syncthreads();
     mlp_layer<C1, C2, R, false>(bufB, W.wt[1], W.b[1], bufA, nullptr);
     __syncthreads();
-    mlp_layer<C2, C3, R, true>(bufA, W.wt[2], W.b[2], nullptr, omax);
+    mlp_layer<C2, C3, R, true>(bufA, W.wt[2], W.b[2], nullptr, omax, oarg, t0);
   }
   __syncthreads();
   float* o = out + (size_t)b * C3;
   for (int c = threadIdx.x; c < C3; c += SA_THREADS) o[c] = omax[c];
+  if (oarg) for (int c = threadIdx.x; c < C3; c += SA_THREADS) arg_out[(size_t)b * C3 + c] = (uint8_t)min(oarg[c], N - 1);
 }
 
 int launch_sa_simt(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride,
-                   int B, int N, const float* new_xyz, float* new_feats, int32_t* ball_idx) {
+                   int B, int N, const float* new_xyz, float* new_feats, int32_t* ball_idx, uint8_t* arg_out) {
   SaWeights W;
   for (int l = 0; l < 3; ++l) { W.wt[l] = c->w.sa[module][l].wt; W.b[l] = c->w.sa[module][l].b; }
   if (module == 0) {
     constexpr int CA = 64, CB = 64, C3 = 64, R = NSAMPLE;
-    size_t smem = (size_t)(CA * R + CB * R + C3) * 4 + (size_t)(R + 8 * R + 8) * 4;
+    size_t smem = (size_t)(CA * R + CB * R + C3) * 4 + (size_t)(R + 8 * R + 8 + C3) * 4;
     auto k = sa_group_kernel<1, 64, 64, 64>;
     MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<dim3(SA1_NPOINT, B), SA_THREADS, smem, s>>>(xyz, stride, feats, feat_stride, N, new_xyz, SA1_NPOINT,
-                                                     SA1_RADIUS * SA1_RADIUS, W, new_feats, ball_idx);
+                                                     SA1_RADIUS * SA1_RADIUS, W, new_feats, ball_idx, arg_out);
   } else if (module == 1) {
     constexpr int CA = 128, CB = 128, C3 = 256, R = NSAMPLE;
-    size_t smem = (size_t)(CA * R + CB * R + C3) * 4 + (size_t)(R + 8 * R + 8) * 4;
+    size_t smem = (size_t)(CA * R + CB * R + C3) * 4 + (size_t)(R + 8 * R + 8 + C3) * 4;
     auto k = sa_group_kernel<64, 128, 128, 256>;
     MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<dim3(SA2_NPOINT, B), SA_THREADS, smem, s>>>(xyz, stride, feats, feat_stride, N, new_xyz, SA2_NPOINT,
-                                                     SA2_RADIUS * SA2_RADIUS, W, new_feats, ball_idx);
+                                                     SA2_RADIUS * SA2_RADIUS, W, new_feats, ball_idx, arg_out);
   } else {
     constexpr int CA = 512, CB = 512, C3 = 1024, R = 32;
-    size_t smem = (size_t)(CA * R + CB * R + C3) * 4;
+    size_t smem = (size_t)(CA * R + CB * R + C3 + C3) * 4;
     auto k = sa_all_kernel<256, 512, 512, 1024>;
     MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<B, SA_THREADS, smem, s>>>(xyz, stride, feats, feat_stride, N, W, new_feats);
+    k<<<B, SA_THREADS, smem, s>>>(xyz, stride, feats, feat_stride, N, W, new_feats, arg_out);
   }
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,841 @@
+// train.cu -- the training step of the policy (config 5), fp32: forward with saved state, the two losses, the backward pass
+// through the Δq head, the FC head (GroupNorm) and the three set-abstraction levels, gradient clipping and Adam.
+//
+// Replaces, for one data-parallel rank, TrainingMotionPolicyNetwork.training_step (mpinets/model.py:185-240:
+// y_hat = clamp(q + net(xyz, q), -1, 1); losses of loss.py:111-166; weights 1 / 5 of jobconfig.yaml:24-25), the
+// torch.autograd graph under it (pointnet2_ops' group_points_grad / max_pool2d backward included),
+// configure_optimizers (model.py:68-73: Adam, lr 1e-4) and the Trainer's gradient_clip_val (run_training.py:112).
+// The DDP all-reduce stays outside: gradients come back as ONE flat fp32 vector in the layout of the parameter vector
+// (engine.cu), which the host reduces with NCCL before calling adam_step.
+//
+// Set-abstraction backward.  The pooled output of a group depends on ONE neighbour row per output channel, so after the
+// max-pool only the rows that won at least one channel ("active" rows: <= min(128, C3) of the 128) carry gradient.  The
+// forward kernels record the winning row per (group, channel); the backward
+//   1. compacts each group's active rows into SLOTS fixed slots (64 for SA1, 128 for SA2 / SA3)        sa_prepare_kernel
+//   2. gathers their operand rows [dx,dy,dz,features] and recomputes layers 1-2 for those rows only    sa_gather_kernel + GEMM
+//   3. layer 3: dZ2[slot] = sum over the channels pooled from that slot of g_c W3[c], masked by ReLU;
+//      dW3[c] += g_c H2[slot_c] -- weight-stationary, accumulators in registers, W3 in shared memory   sa_l3_bwd_kernel
+//   4. layers 2 and 1 are dense GEMMs over the compacted rows (data gradient, weight gradient)          linear_kernel / wgrad_kernel
+//   5. the feature part of dX is scatter-added to the previous level's feature gradient                 sa_scatter_add_kernel
+// in chunks of samples, so the compacted-row scratch stays a few GB.  Weight-gradient reductions are two-level and
+// ordered (partials per CTA, then a fixed-order sum): apart from the scatter-add atomics the step is deterministic.
+#include <algorithm>
+#include <cstdlib>
+
+#include "engine.h"
+
+namespace mpn {
+
+// ---------------------------------------------------------------------------------------------- weight gradient GEMM
+// pW[split][n][k] = sum over the split's rows m of dY[m][n] * X[m][k];  pb[split][n] = sum_m dY[m][n]
+constexpr int WT = 64, WM = 16;
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx,
+                                                    long long M, int N, int K, long long rows_per_split,
+                                                    float* __restrict__ pW, float* __restrict__ pb) {
+  __shared__ __align__(16) float ys[WM][WT + 4];
+  __shared__ __align__(16) float xs[WM][WT + 4];
+  const int nt = (N + WT - 1) / WT;
+  const int n0 = (blockIdx.x % nt) * WT, k0 = (blockIdx.x / nt) * WT;
+  const int split = blockIdx.y;
+  const long long m_begin = (long long)split * rows_per_split;
+  const long long m_end = min(M, m_begin + rows_per_split);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // ty -> 4 rows of dW (n), tx -> 4 columns (k)
+  const int lm = threadIdx.x / 16, lc = threadIdx.x % 16;  // loader: row lm, columns lc + 16 u
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  const bool do_bias = pb != nullptr && k0 == 0 && threadIdx.x < WT;
+  for (long long m0 = m_begin; m0 < m_end; m0 += WM) {
+    const long long m = m0 + lm;
+    const bool mv = m < m_end;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int cc = lc + 16 * u;
+      ys[lm][cc] = (mv && n0 + cc < N) ? dY[(size_t)m * ldy + n0 + cc] : 0.f;
+      xs[lm][cc] = (mv && k0 + cc < K) ? X[(size_t)m * ldx + k0 + cc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < WM; ++mm) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&ys[mm][ty * 4]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&xs[mm][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    if (do_bias) {
+#pragma unroll
+      for (int mm = 0; mm < WM; ++mm) bsum += ys[mm][threadIdx.x];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) pW[((size_t)split * N + n) * K + k] = acc[i][j];
+    }
+  }
+  if (do_bias && n0 + (int)threadIdx.x < N) pb[(size_t)split * N + n0 + threadIdx.x] = bsum;
+}
+
+// dst[i] (+)= sum_s p[s][i], s in order
+__global__ void reduce_partials_kernel(const float* __restrict__ p, int splits, long long n, float* __restrict__ dst, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += p[(size_t)sp * n + i];
+  dst[i] = accumulate ? dst[i] + s : s;
+}
+
+static int reduce_partials(mpn_ctx* c, cudaStream_t s, const float* p, int splits, long long n, float* dst, int accumulate) {
+  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, splits, n, dst, accumulate);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// gW[N][K] += dY^T X, gb[N] += column sums of dY (gb may be null)
+static int wgrad(mpn_ctx* c, cudaStream_t s, const float* dY, int ldy, const float* X, int ldx, long long M, int N, int K, float* gW,
+                 float* gb) {
+  if (M <= 0) return MPN_OK;
+  TrainWs& t = c->tw;
+  const int tiles = ((N + WT - 1) / WT) * ((K + WT - 1) / WT);
+  long long splits = (2LL * c->sm_count + tiles - 1) / tiles;
+  splits = std::min(splits, (M + 255) / 256);
+  const long long per = (long long)N * K + N;
+  splits = std::max(1LL, std::min(splits, (long long)(t.partial_floats / per)));
+  MPN_REQUIRE((size_t)per <= t.partial_floats, "wgrad: partial buffer too small");
+  long long rps = ((M + splits - 1) / splits + WM - 1) / WM * WM;
+  splits = (M + rps - 1) / rps;
+  float* pW = t.partial;
+  float* pb = gb ? pW + (size_t)splits * N * K : nullptr;
+  wgrad_kernel<<<dim3(tiles, (unsigned)splits), 256, 0, s>>>(dY, ldy, X, ldx, M, N, K, rps, pW, pb);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  int r;
+  if ((r = reduce_partials(c, s, pW, (int)splits, (long long)N * K, gW, 1))) return r;
+  if (gb && (r = reduce_partials(c, s, pb, (int)splits, N, gb, 1))) return r;
+  return MPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm + LeakyReLU backward
+// y = xhat * gamma + beta, a = lrelu(y); dy = da * lrelu'(y).  Parameter gradients: partial sums over a split of rows.
+__global__ void __launch_bounds__(256) gn_param_grad_kernel(const float* __restrict__ z, const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ da, int M, int C, int groups, int rows_per_split,
+                                                            float* __restrict__ pG, float* __restrict__ pB) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  const int split = blockIdx.y, gs = C / groups, grp = ch / gs;
+  const int r0 = split * rows_per_split, r1 = min(M, r0 + rows_per_split);
+  const float gm = gamma[ch], bt = beta[ch];
+  float sg = 0.f, sb = 0.f;
+  for (int row = r0; row < r1; ++row) {
+    const float mean = stats[2 * ((size_t)row * groups + grp)], rstd = stats[2 * ((size_t)row * groups + grp) + 1];
+    const float xh = (z[(size_t)row * C + ch] - mean) * rstd;
+    const float y = xh * gm + bt;
+    const float dy = da[(size_t)row * C + ch] * (y > 0.f ? 1.0f : 0.01f);
+    sg = fmaf(dy, xh, sg);
+    sb += dy;
+  }
+  pG[(size_t)split * C + ch] = sg;
+  pB[(size_t)split * C + ch] = sb;
+}
+
+// one warp per (row, group): g (in: da, out: dz) = rstd * (gamma dy - mean(gamma dy) - xhat mean(gamma dy xhat))
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ stats,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ g,
+                                                     int M, int C, int groups) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= M * groups) return;
+  const int row = wid / groups, grp = wid % groups, gs = C / groups;
+  const float mean = stats[2 * (size_t)wid], rstd = stats[2 * (size_t)wid + 1];
+  const float* zp = z + (size_t)row * C + (size_t)grp * gs;
+  float* gp = g + (size_t)row * C + (size_t)grp * gs;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < gs; i += 32) {
+    const int ch = grp * gs + i;
+    const float xh = (zp[i] - mean) * rstd;
+    const float y = xh * gamma[ch] + beta[ch];
+    const float gd = gamma[ch] * (gp[i] * (y > 0.f ? 1.0f : 0.01f));
+    s1 += gd;
+    s2 = fmaf(gd, xh, s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  const float m1 = s1 / (float)gs, m2 = s2 / (float)gs;
+  for (int i = lane; i < gs; i += 32) {
+    const int ch = grp * gs + i;
+    const float xh = (zp[i] - mean) * rstd;
+    const float y = xh * gamma[ch] + beta[ch];
+    const float gd = gamma[ch] * (gp[i] * (y > 0.f ? 1.0f : 0.01f));
+    gp[i] = rstd * (gd - m1 - xh * m2);
+  }
+}
+
+static int gn_backward(mpn_ctx* c, cudaStream_t s, const float* z, const float* stats, const float* gamma, const float* beta, float* g,
+                       int M, int C, float* g_gamma, float* g_beta) {
+  TrainWs& t = c->tw;
+  int splits = std::max(1, std::min(32, M / 64));
+  int rps = (M + splits - 1) / splits;
+  splits = (M + rps - 1) / rps;
+  float* pG = t.partial;
+  float* pB = pG + (size_t)splits * C;
+  gn_param_grad_kernel<<<dim3((C + 255) / 256, splits), 256, 0, s>>>(z, stats, gamma, beta, g, M, C, 16, rps, pG, pB);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  int r;
+  if ((r = reduce_partials(c, s, pG, splits, C, g_gamma, 1))) return r;
+  if ((r = reduce_partials(c, s, pB, splits, C, g_beta, 1))) return r;
+  const int warps = M * 16;
+  gn_bwd_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(z, stats, gamma, beta, g, M, C, 16);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- set-abstraction backward
+// One warp per group: masks the pooled-output gradient (ReLU / zero gradient), finds the active rows, assigns slots.
+template <int C3, int SLOTS>
+__global__ void __launch_bounds__(256) sa_prepare_kernel(const uint8_t* __restrict__ arg, float* __restrict__ g,
+                                                         const float* __restrict__ out, const int32_t* __restrict__ ball, int G,
+                                                         uint8_t* __restrict__ slot_of_ch, int32_t* __restrict__ src) {
+  __shared__ unsigned mask_s[8][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.x * 8 + warp;
+  if (grp >= G) return;
+  unsigned* mk = mask_s[warp];
+  if (lane < 4) mk[lane] = 0u;
+  __syncwarp();
+  const size_t gc = (size_t)grp * C3;
+  for (int ch = lane; ch < C3; ch += 32) {
+    const float gv = g[gc + ch];
+    const bool act = gv != 0.f && out[gc + ch] > 0.f;
+    if (!act) {
+      g[gc + ch] = 0.f;
+    } else {
+      const int r = arg[gc + ch] & 127;
+      atomicOr(&mk[r >> 5], 1u << (r & 31));
+    }
+  }
+  __syncwarp();
+  const unsigned m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
+  const int b1 = __popc(m0), b2 = b1 + __popc(m1), b3 = b2 + __popc(m2);
+  auto slot_of_row = [&](int r) {
+    const int wd = r >> 5;
+    const unsigned w = wd == 0 ? m0 : wd == 1 ? m1 : wd == 2 ? m2 : m3;
+    const int base = wd == 0 ? 0 : wd == 1 ? b1 : wd == 2 ? b2 : b3;
+    return base + __popc(w & ((1u << (r & 31)) - 1u));
+  };
+  for (int sl = lane; sl < SLOTS; sl += 32) src[(size_t)grp * SLOTS + sl] = -1;
+  __syncwarp();
+#pragma unroll
+  for (int wd = 0; wd < 4; ++wd) {
+    const unsigned w = wd == 0 ? m0 : wd == 1 ? m1 : wd == 2 ? m2 : m3;
+    if ((w >> lane) & 1u) {
+      const int r = wd * 32 + lane;
+      const int sl = slot_of_row(r);
+      if (sl < SLOTS) src[(size_t)grp * SLOTS + sl] = ball ? ball[(size_t)grp * NSAMPLE + r] : r;
+    }
+  }
+  for (int ch = lane; ch < C3; ch += 32) {
+    int sl = 255;
+    if (g[gc + ch] != 0.f) {
+      sl = slot_of_row(arg[gc + ch] & 127);
+      if (sl >= SLOTS) { sl = 255; g[gc + ch] = 0.f; }
+    }
+    slot_of_ch[gc + ch] = (uint8_t)sl;
+  }
+}
+
+// X[row][:] = [p[src] - centroid | features[src] | 0-pad]; empty slots -> zero rows
+template <int CFEAT, int CINP, bool CENTER>
+__global__ void __launch_bounds__(256) sa_gather_kernel(const int32_t* __restrict__ src, long long R, int slots, int npoint,
+                                                        const float* __restrict__ xyz, int stride, int N, const float* __restrict__ feats,
+                                                        int fstride, const float* __restrict__ new_xyz, float* __restrict__ X) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * CINP) return;
+  const long long row = i / CINP;
+  const int k = (int)(i - row * CINP);
+  const long long grp = row / slots;
+  const long long b = grp / npoint;
+  const int si = src[row];
+  float v = 0.f;
+  if (si >= 0 && k < 3 + CFEAT) {
+    if (k < 3) {
+      v = xyz[((size_t)b * N + si) * stride + k];
+      if (CENTER) v -= new_xyz[(size_t)grp * 3 + k];
+    } else {
+      v = feats[((size_t)b * N + si) * fstride + (k - 3)];
+    }
+  }
+  X[i] = v;
+}
+
+// Layer 3 of a grouped level, persistent CTAs (W3 resident in shared memory, dW3 / db3 accumulators in registers):
+//   H2 (in: relu activations of the group's slots, out: dZ2);  pW[cta][C3][C2], pb[cta][C3] partial sums.
+template <int C2, int C3, int SLOTS>
+__global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict__ geff, const uint8_t* __restrict__ slot_of_ch,
+                                                        const float* __restrict__ W3, float* __restrict__ H2, int G,
+                                                        float* __restrict__ pW, float* __restrict__ pb) {
+  constexpr int T = 512, Q = T / C2, CPT = C3 / Q, PER = SLOTS / 32;
+  static_assert(T % C2 == 0 && C3 % Q == 0 && SLOTS % 32 == 0 && SLOTS <= 128 && C3 <= T, "layout");
+  extern __shared__ __align__(16) float sm[];
+  float* W3s = sm;                                  // [C3][C2]
+  float* Hs = W3s + C3 * C2;                        // [SLOTS][C2]
+  float* gs = Hs + SLOTS * C2;                      // [C3]
+  int* sl = reinterpret_cast<int*>(gs + C3);        // [C3]
+  int* cnt = sl + C3;                               // [SLOTS]
+  int* start = cnt + SLOTS;                         // [SLOTS + 1]
+  int* chl = start + SLOTS + 1;                     // [C3]
+  const int tid = threadIdx.x, j = tid % C2, q = tid / C2;
+  float accW[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) accW[i] = 0.f;
+  float accb = 0.f;
+  for (int i = tid; i < C3 * C2; i += T) W3s[i] = W3[i];
+  for (int grp = blockIdx.x; grp < G; grp += gridDim.x) {
+    __syncthreads();
+    for (int c = tid; c < C3; c += T) {
+      gs[c] = geff[(size_t)grp * C3 + c];
+      sl[c] = slot_of_ch[(size_t)grp * C3 + c];
+    }
+    float* Hg = H2 + (size_t)grp * SLOTS * C2;
+    for (int i = tid; i < SLOTS * C2; i += T) Hs[i] = Hg[i];
+    __syncthreads();
+    // channel lists per slot, in channel order (deterministic)
+    if (tid < SLOTS) {
+      int n = 0;
+      for (int c = 0; c < C3; ++c) n += (sl[c] == tid) ? 1 : 0;
+      cnt[tid] = n;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int loc[PER], sum = 0;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) { loc[u] = cnt[tid * PER + u]; sum += loc[u]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      int ex = incl - sum;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) { start[tid * PER + u] = ex; ex += loc[u]; }
+      if (tid == 31) start[SLOTS] = incl;
+    }
+    __syncthreads();
+    if (tid < SLOTS) {
+      int p = start[tid];
+      for (int c = 0; c < C3; ++c)
+        if (sl[c] == tid) chl[p++] = c;
+    }
+    __syncthreads();
+    // dZ2[slot] = (sum over the slot's channels of g_c W3[c]) masked by ReLU
+    for (int s = q; s < SLOTS; s += Q) {
+      float a = 0.f;
+      const int e1 = start[s + 1];
+      for (int e = start[s]; e < e1; ++e) {
+        const int c = chl[e];
+        a = fmaf(gs[c], W3s[c * C2 + j], a);
+      }
+      Hg[(size_t)s * C2 + j] = Hs[s * C2 + j] > 0.f ? a : 0.f;
+    }
+    // dW3[c] += g_c H2[slot_c]
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int c = q * CPT + i;
+      const int s = sl[c];
+      if (s != 255) accW[i] = fmaf(gs[c], Hs[s * C2 + j], accW[i]);
+    }
+    if (tid < C3) accb += gs[tid];
+  }
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) pW[(size_t)blockIdx.x * C3 * C2 + (size_t)(q * CPT + i) * C2 + j] = accW[i];
+  if (tid < C3) pb[(size_t)blockIdx.x * C3 + tid] = accb;
+}
+
+// group-all level (C3 = 1024, C2 = 512): dW3 partials over a split of samples; grid (C3 / 8, splits), thread = column
+__global__ void __launch_bounds__(512) sa3_dw3_kernel(const float* __restrict__ geff, const uint8_t* __restrict__ slot_of_ch,
+                                                      const float* __restrict__ H2, int B, int per_split, float* __restrict__ pW) {
+  constexpr int C2 = 512, C3 = 1024, SLOTS = 128;
+  const int c0 = blockIdx.x * 8, split = blockIdx.y, j = threadIdx.x;
+  const int b0 = split * per_split, b1 = min(B, b0 + per_split);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int b = b0; b < b1; ++b) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int s = slot_of_ch[(size_t)b * C3 + c0 + i];
+      if (s != 255) acc[i] = fmaf(geff[(size_t)b * C3 + c0 + i], H2[((size_t)b * SLOTS + s) * C2 + j], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pW[((size_t)split * C3 + c0 + i) * C2 + j] = acc[i];
+}
+
+// group-all level: H2 (in: activations, out: dZ2) for one sample per CTA; W3 read from L2
+__global__ void __launch_bounds__(512) sa3_dz2_kernel(const float* __restrict__ geff, const uint8_t* __restrict__ slot_of_ch,
+                                                      const float* __restrict__ W3, float* __restrict__ H2) {
+  constexpr int C2 = 512, C3 = 1024, SLOTS = 128;
+  __shared__ float gs[C3];
+  __shared__ uint8_t sl[C3];
+  __shared__ int cnt[SLOTS], start[SLOTS + 1];
+  __shared__ short chl[C3];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  for (int c = tid; c < C3; c += 512) { gs[c] = geff[(size_t)b * C3 + c]; sl[c] = slot_of_ch[(size_t)b * C3 + c]; }
+  __syncthreads();
+  if (tid < SLOTS) {
+    int n = 0;
+    for (int c = 0; c < C3; ++c) n += (sl[c] == tid) ? 1 : 0;
+    cnt[tid] = n;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    int loc[4], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { loc[u] = cnt[tid * 4 + u]; sum += loc[u]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += v;
+    }
+    int ex = incl - sum;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { start[tid * 4 + u] = ex; ex += loc[u]; }
+    if (tid == 31) start[SLOTS] = incl;
+  }
+  __syncthreads();
+  if (tid < SLOTS) {
+    int p = start[tid];
+    for (int c = 0; c < C3; ++c)
+      if (sl[c] == tid) chl[p++] = (short)c;
+  }
+  __syncthreads();
+  float* Hb = H2 + (size_t)b * SLOTS * C2;
+  for (int s = 0; s < SLOTS; ++s) {
+    float a = 0.f;
+    const int e1 = start[s + 1];
+    for (int e = start[s]; e < e1; ++e) {
+      const int c = chl[e];
+      a = fmaf(gs[c], __ldg(W3 + (size_t)c * C2 + tid), a);
+    }
+    const float h = Hb[(size_t)s * C2 + tid];
+    Hb[(size_t)s * C2 + tid] = h > 0.f ? a : 0.f;
+  }
+}
+
+// column sums of Y[M][N] (ordered): one CTA per 32 columns, 8 row lanes
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Y, int ld, int M, int N, float* __restrict__ dst) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  float s = 0.f;
+  if (col < N)
+    for (int m = rl; m < M; m += 8) s += Y[(size_t)m * ld + col];
+  red[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && col < N) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tsum += red[i][threadIdx.x];
+    dst[col] += tsum;
+  }
+}
+
+// previous level's feature gradient: dfeat[b][src][f] += dX[row][f]   (pointnet2's group_points_grad)
+__global__ void __launch_bounds__(256) sa_scatter_add_kernel(const float* __restrict__ dX, const int32_t* __restrict__ src, long long R,
+                                                             int slots, int npoint, int N, int CF, float* __restrict__ dfeat) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * CF) return;
+  const long long row = i / CF;
+  const int f = (int)(i - row * CF);
+  const int si = src[row];
+  if (si < 0) return;
+  const long long b = (row / slots) / npoint;
+  atomicAdd(dfeat + ((size_t)b * N + si) * CF + f, dX[i]);
+}
+
+// ---------------------------------------------------------------------------------------------- small elementwise kernels
+__global__ void yhat_kernel(const float* __restrict__ qn, const float* __restrict__ dq, int n, float* __restrict__ yhat) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) yhat[i] = fminf(1.0f, fmaxf(-1.0f, __fadd_rn(qn[i], dq[i])));
+}
+// torch.clamp backward: the gradient passes where min <= x <= max
+__global__ void clamp_bwd_kernel(const float* __restrict__ qn, const float* __restrict__ dq, int n, float* __restrict__ g) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = __fadd_rn(qn[i], dq[i]);
+  if (!(x >= -1.0f && x <= 1.0f)) g[i] = 0.f;
+}
+__global__ void transpose_kernel(const float* __restrict__ w, int out, int in, float* __restrict__ wt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out * in) return;
+  int o = i / in, k = i - o * in;
+  wt[(size_t)k * out + o] = w[i];
+}
+
+// ---------------------------------------------------------------------------------------------- optimiser
+constexpr int NORM_CTAS = 512;
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)NORM_CTAS * 256) s = fmaf(g[i], g[i], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(NORM_CTAS) sumsq_final_kernel(const float* __restrict__ partial, float* __restrict__ norm) {
+  __shared__ float red[NORM_CTAS];
+  red[threadIdx.x] = partial[threadIdx.x];
+  __syncthreads();
+  for (int o = NORM_CTAS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norm[0] = sqrtf(red[0]);
+}
+// torch.optim.Adam (no weight decay, no amsgrad) after torch.nn.utils.clip_grad_norm_(max_norm = clip)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float clip, const float* __restrict__ norm) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float scale = 1.0f;
+  if (clip > 0.f) scale = fminf(1.0f, clip / (norm[0] + 1e-6f));
+  const float gi = g[i] * scale;
+  const float mi = m[i] + (1.0f - b1) * (gi - m[i]);
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+int refresh_transposes(mpn_ctx* c, cudaStream_t s) {
+  Weights& W = c->w;
+  std::vector<Linear*> all;
+  for (int m = 0; m < 3; ++m) for (int l = 0; l < 3; ++l) all.push_back(&W.sa[m][l]);
+  for (int l = 0; l < 3; ++l) all.push_back(&W.fc[l]);
+  for (int l = 0; l < 5; ++l) all.push_back(&W.fe[l]);
+  for (int l = 0; l < 4; ++l) all.push_back(&W.dec[l]);
+  for (Linear* L : all) {
+    const int n = L->in * L->out;
+    transpose_kernel<<<(n + 255) / 256, 256, 0, s>>>(L->w, L->out, L->in, L->wt);
+    c->launches++;
+  }
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- workspace
+template <typename T>
+static int talloc(T** p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (cudaMalloc((void**)p, n * sizeof(T)) != cudaSuccess) {
+    set_error("training workspace: cudaMalloc(%zu bytes) failed", n * sizeof(T));
+    return MPN_ERR_NOMEM;
+  }
+  return MPN_OK;
+}
+
+void free_train_ws(mpn_ctx* c) {
+  TrainWs& t = c->tw;
+  void** ptrs[] = {(void**)&t.fps_idx, (void**)&t.ball1, (void**)&t.ball2, (void**)&t.arg1, (void**)&t.arg2, (void**)&t.arg3,
+                   (void**)&t.z1, (void**)&t.a1, (void**)&t.z2, (void**)&t.a2, (void**)&t.st1, (void**)&t.st2, (void**)&t.f[0],
+                   (void**)&t.f[1], (void**)&t.f[2], (void**)&t.f[3], (void**)&t.d[0], (void**)&t.d[1], (void**)&t.d[2],
+                   (void**)&t.yhat, (void**)&t.gy, (void**)&t.ga, (void**)&t.gb, (void**)&t.gcat, (void**)&t.gfeat3, (void**)&t.gfeat2,
+                   (void**)&t.gfeat1, (void**)&t.X, (void**)&t.H1, (void**)&t.H2, (void**)&t.src, (void**)&t.slot, (void**)&t.partial,
+                   (void**)&t.adam_m, (void**)&t.adam_v, (void**)&t.norm};
+  for (auto p : ptrs)
+    if (*p) { cudaFree(*p); *p = nullptr; }
+  t.capacity = 0; t.chunk = 0; t.partial_floats = 0;
+}
+
+static int train_chunk_size(int B) {
+  int chunk = 256;
+  if (const char* e = getenv("MPN_TRAIN_CHUNK")) chunk = std::max(1, atoi(e));
+  return std::min(B, chunk);
+}
+
+static int ensure_train_ws(mpn_ctx* c, int B, int N) {
+  TrainWs& t = c->tw;
+  const int chunk = train_chunk_size(B);
+  if (B <= t.capacity && chunk <= t.chunk && N <= t.n_points) return MPN_OK;
+  float* keep_m = t.adam_m; float* keep_v = t.adam_v; float* keep_n = t.norm;   // optimiser state survives a resize
+  t.adam_m = t.adam_v = t.norm = nullptr;
+  free_train_ws(c);
+  t.adam_m = keep_m; t.adam_v = keep_v; t.norm = keep_n;
+  const size_t b = (size_t)B, k = (size_t)chunk;
+  int r = 0;
+  r |= talloc(&t.fps_idx, b * SA1_NPOINT);
+  r |= talloc(&t.ball1, b * SA1_NPOINT * NSAMPLE);
+  r |= talloc(&t.ball2, b * SA2_NPOINT * NSAMPLE);
+  r |= talloc(&t.arg1, b * SA1_NPOINT * 64);
+  r |= talloc(&t.arg2, b * SA2_NPOINT * 256);
+  r |= talloc(&t.arg3, b * 1024);
+  r |= talloc(&t.z1, b * 4096); r |= talloc(&t.a1, b * 4096);
+  r |= talloc(&t.z2, b * 2048); r |= talloc(&t.a2, b * 2048);
+  r |= talloc(&t.st1, b * 32); r |= talloc(&t.st2, b * 32);
+  r |= talloc(&t.f[0], b * 32); r |= talloc(&t.f[1], b * 64); r |= talloc(&t.f[2], b * 128); r |= talloc(&t.f[3], b * 128);
+  r |= talloc(&t.d[0], b * 512); r |= talloc(&t.d[1], b * 256); r |= talloc(&t.d[2], b * 128);
+  r |= talloc(&t.yhat, b * 7); r |= talloc(&t.gy, b * 7);
+  r |= talloc(&t.ga, b * 4096); r |= talloc(&t.gb, b * 4096);
+  r |= talloc(&t.gcat, b * (ENC_DIM + QF_DIM));
+  r |= talloc(&t.gfeat3, b * 1024);
+  r |= talloc(&t.gfeat2, b * SA2_NPOINT * 256);
+  r |= talloc(&t.gfeat1, b * SA1_NPOINT * 64);
+  // compacted rows of one chunk: SA1 512 x 64 slots x (4 | 64 | 64), SA2 128 x 128 x (68 | 128 | 128), SA3 128 x (260 | 512 | 512)
+  r |= talloc(&t.X, k * SA2_NPOINT * 128 * 68);
+  r |= talloc(&t.H1, k * SA2_NPOINT * 128 * 128);
+  r |= talloc(&t.H2, k * SA2_NPOINT * 128 * 128);
+  r |= talloc(&t.src, k * SA1_NPOINT * 64);
+  r |= talloc(&t.slot, k * SA1_NPOINT * 64);
+  t.partial_floats = (size_t)8 << 20;
+  r |= talloc(&t.partial, t.partial_floats);
+  if (r) { free_train_ws(c); return MPN_ERR_NOMEM; }
+  t.capacity = B; t.chunk = chunk; t.n_points = N;
+  return MPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- forward (saves state)
+static int train_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, const float* qn, int B, int N) {
+  Workspace& w = c->ws;
+  TrainWs& t = c->tw;
+  const Weights& W = c->w;
+  const int CAT = ENC_DIM + QF_DIM;
+  int r;
+  if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, t.fps_idx, w.xyz1))) return r;
+  if ((r = launch_sa_simt(c, s, 0, cloud, 4, cloud + 3, 4, B, N, w.xyz1, w.feat1, t.ball1, t.arg1))) return r;
+  if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, t.fps_idx, w.xyz2))) return r;
+  if ((r = launch_sa_simt(c, s, 1, w.xyz1, 3, w.feat1, 64, B, SA1_NPOINT, w.xyz2, w.feat2, t.ball2, t.arg2))) return r;
+  if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr, t.arg3))) return r;
+  if ((r = launch_linear(c, s, W.fc[0], w.feat3, 1024, B, t.z1, 4096, 0))) return r;
+  if ((r = launch_groupnorm_lrelu_train(c, s, t.z1, B, 4096, 16, W.gn_w[0], W.gn_b[0], t.a1, t.st1))) return r;
+  if ((r = launch_linear(c, s, W.fc[1], t.a1, 4096, B, t.z2, 2048, 0))) return r;
+  if ((r = launch_groupnorm_lrelu_train(c, s, t.z2, B, 2048, 16, W.gn_w[1], W.gn_b[1], t.a2, t.st2))) return r;
+  if ((r = launch_linear(c, s, W.fc[2], t.a2, 2048, B, w.cat, CAT, 0))) return r;
+  if ((r = launch_linear(c, s, W.fe[0], qn, 7, B, t.f[0], 32, 1))) return r;
+  if ((r = launch_linear(c, s, W.fe[1], t.f[0], 32, B, t.f[1], 64, 1))) return r;
+  if ((r = launch_linear(c, s, W.fe[2], t.f[1], 64, B, t.f[2], 128, 1))) return r;
+  if ((r = launch_linear(c, s, W.fe[3], t.f[2], 128, B, t.f[3], 128, 1))) return r;
+  if ((r = launch_linear(c, s, W.fe[4], t.f[3], 128, B, w.cat + ENC_DIM, CAT, 0))) return r;
+  if ((r = launch_linear(c, s, W.dec[0], w.cat, CAT, B, t.d[0], 512, 1))) return r;
+  if ((r = launch_linear(c, s, W.dec[1], t.d[0], 512, B, t.d[1], 256, 1))) return r;
+  if ((r = launch_linear(c, s, W.dec[2], t.d[1], 256, B, t.d[2], 128, 1))) return r;
+  return launch_linear(c, s, W.dec[3], t.d[2], 128, B, w.dq, 7, 0);
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+static inline float* gw(const mpn_ctx* c, float* grads, const Linear& L) { return grads + (L.w - c->w.params); }
+static inline float* gbias(const mpn_ctx* c, float* grads, const Linear& L) { return grads + (L.b - c->w.params); }
+
+// one dense layer: gW, gb += ; gX[M][in] = (gY W) * f'(a_in)  (mask_mode 0: none)
+static int dense_backward(mpn_ctx* c, cudaStream_t s, const Linear& L, float* grads, const float* gY, int ldgy, const float* a_in,
+                          int lda, int M, float* gX, int ldgx, int mask_mode) {
+  int r;
+  if ((r = wgrad(c, s, gY, ldgy, a_in, lda, M, L.out, L.in, gw(c, grads, L), gbias(c, grads, L)))) return r;
+  if (!gX) return MPN_OK;
+  return launch_linear_ex(c, s, gY, ldgy, L.wt, L.out, nullptr, M, L.in, L.out, gX, ldgx, 0, mask_mode ? a_in : nullptr, lda, mask_mode);
+}
+
+template <int C2, int C3, int SLOTS>
+static int launch_sa_l3(mpn_ctx* c, cudaStream_t s, const float* geff, const uint8_t* slot, const Linear& L3, float* H2, int G,
+                        float* grads) {
+  TrainWs& t = c->tw;
+  auto k = sa_l3_bwd_kernel<C2, C3, SLOTS>;
+  const size_t smem = (size_t)(C3 * C2 + SLOTS * C2 + C3) * 4 + (size_t)(C3 + SLOTS + SLOTS + 1 + C3) * 4;
+  MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = smem > 100 * 1024 ? 1 : 2;
+  int grid = std::min(G, c->sm_count * per_sm);
+  const size_t per = (size_t)C3 * C2 + C3;
+  grid = (int)std::min<size_t>(grid, t.partial_floats / per);
+  float* pW = t.partial;
+  float* pb = pW + (size_t)grid * C3 * C2;
+  k<<<grid, 512, smem, s>>>(geff, slot, L3.w, H2, G, pW, pb);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  int r;
+  if ((r = reduce_partials(c, s, pW, grid, (long long)C3 * C2, gw(c, grads, L3), 1))) return r;
+  return reduce_partials(c, s, pb, grid, C3, gbias(c, grads, L3), 1);
+}
+
+// module m backward over samples [b0, b0 + bc): g = d loss / d pooled output [bc][npoint][C3] (masked in place)
+static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, int N_in, const float* xyz, int stride,
+                             const float* feats, int fstride, const float* new_xyz, const int32_t* ball, const uint8_t* arg,
+                             float* g, const float* out, float* grads, float* dfeat_prev) {
+  TrainWs& t = c->tw;
+  const Linear* L = c->w.sa[m];
+  static const int NPOINT[3] = {SA1_NPOINT, SA2_NPOINT, 1}, SLOTS[3] = {64, 128, 128}, CFEAT[3] = {1, 64, 256}, CINP[3] = {4, 68, 260};
+  const int npoint = NPOINT[m], slots = SLOTS[m], C1 = L[0].out, C2 = L[1].out, C3 = L[2].out, CIN = L[0].in;
+  const int G = bc * npoint;
+  const long long R = (long long)G * slots;
+  int r;
+  // per-chunk views
+  const float* xyz_c = xyz + (size_t)b0 * N_in * stride;
+  const float* feats_c = feats + (size_t)b0 * N_in * fstride;
+  const float* nx_c = new_xyz ? new_xyz + (size_t)b0 * npoint * 3 : nullptr;
+  const int32_t* ball_c = ball ? ball + (size_t)b0 * npoint * NSAMPLE : nullptr;
+  const uint8_t* arg_c = arg + (size_t)b0 * npoint * C3;
+  float* g_c = g + (size_t)b0 * npoint * C3;
+  const float* out_c = out + (size_t)b0 * npoint * C3;
+  // 1. active rows -> slots
+  {
+    const int grid = (G + 7) / 8;
+    if (m == 0) sa_prepare_kernel<64, 64><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
+    else if (m == 1) sa_prepare_kernel<256, 128><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
+    else sa_prepare_kernel<1024, 128><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, nullptr, G, t.slot, t.src);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  }
+  // 2. operand rows, layers 1-2 recomputed for the active rows
+  {
+    const long long n = R * CINP[m];
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (m == 0) sa_gather_kernel<1, 4, true><<<grid, 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, stride, N_in, feats_c, fstride, nx_c, t.X);
+    else if (m == 1) sa_gather_kernel<64, 68, true><<<grid, 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, stride, N_in, feats_c, fstride, nx_c, t.X);
+    else sa_gather_kernel<256, 260, false><<<grid, 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, stride, N_in, feats_c, fstride, nullptr, t.X);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  }
+  if ((r = launch_linear_ex(c, s, t.X, CINP[m], L[0].w, CIN, L[0].b, R, C1, CIN, t.H1, C1, 2))) return r;
+  if ((r = launch_linear_ex(c, s, t.H1, C1, L[1].w, C1, L[1].b, R, C2, C1, t.H2, C2, 2))) return r;
+  // 3. layer 3 (sparse): H2 <- dZ2, gW3 / gb3
+  if (m == 0) {
+    if ((r = launch_sa_l3<64, 64, 64>(c, s, g_c, t.slot, L[2], t.H2, G, grads))) return r;
+  } else if (m == 1) {
+    if ((r = launch_sa_l3<128, 256, 128>(c, s, g_c, t.slot, L[2], t.H2, G, grads))) return r;
+  } else {
+    int splits = std::max(1, std::min(8, bc / 16));
+    int per = (bc + splits - 1) / splits;
+    splits = (bc + per - 1) / per;
+    sa3_dw3_kernel<<<dim3(1024 / 8, splits), 512, 0, s>>>(g_c, t.slot, t.H2, bc, per, t.partial);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    if ((r = reduce_partials(c, s, t.partial, splits, 1024LL * 512, gw(c, grads, L[2]), 1))) return r;
+    colsum_kernel<<<1024 / 32, 256, 0, s>>>(g_c, 1024, bc, 1024, gbias(c, grads, L[2]));
+    c->launches++;
+    sa3_dz2_kernel<<<bc, 512, 0, s>>>(g_c, t.slot, L[2].w, t.H2);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  }
+  // 4. layer 2: gW2 += dZ2^T H1 ; dZ1 = (dZ2 W2) * relu'(H1), in place over H1
+  if ((r = wgrad(c, s, t.H2, C2, t.H1, C1, R, C2, C1, gw(c, grads, L[1]), gbias(c, grads, L[1])))) return r;
+  if ((r = launch_linear_ex(c, s, t.H2, C2, L[1].wt, C2, nullptr, R, C1, C2, t.H1, C1, 0, t.H1, C1, 2))) return r;
+  //    layer 1: gW1 += dZ1^T X
+  if ((r = wgrad(c, s, t.H1, C1, t.X, CINP[m], R, C1, CIN, gw(c, grads, L[0]), gbias(c, grads, L[0])))) return r;
+  // 5. feature part of dX = dZ1 W1[:, 3:]  ->  previous level's feature gradient
+  if (m == 2) {
+    float* dst = dfeat_prev + (size_t)b0 * SA2_NPOINT * 256;   // group-all: rows are the SA2 centroids themselves
+    // empty slots do not occur here only if every row is active; rows are addressed through src, so scatter (no collisions)
+    if ((r = launch_linear_ex(c, s, t.H1, C1, L[0].wt + (size_t)3 * C1, C1, nullptr, R, CFEAT[m], C1, t.H2, CFEAT[m], 0))) return r;
+    const long long n = R * CFEAT[m];
+    sa_scatter_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t.H2, t.src, R, slots, npoint, SA2_NPOINT, CFEAT[m], dst);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  } else if (m == 1) {
+    float* dst = dfeat_prev + (size_t)b0 * SA1_NPOINT * 64;
+    if ((r = launch_linear_ex(c, s, t.H1, C1, L[0].wt + (size_t)3 * C1, C1, nullptr, R, CFEAT[m], C1, t.H2, CFEAT[m], 0))) return r;
+    const long long n = R * CFEAT[m];
+    sa_scatter_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t.H2, t.src, R, slots, npoint, SA1_NPOINT, CFEAT[m], dst);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  }
+  return MPN_OK;
+}
+
+int train_step_grads(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int N, const float* cloud, const float* q_norm,
+                     const float* supervision, int n_loss_points, float margin, float w_collision, float w_bc, float* losses,
+                     float* y_hat, float* grads) {
+  int r;
+  if ((r = ensure_train_ws(c, B, N))) return r;
+  Workspace& w = c->ws;
+  TrainWs& t = c->tw;
+  const Weights& W = c->w;
+  const int CAT = ENC_DIM + QF_DIM;
+  if ((r = train_forward(c, s, cloud, q_norm, B, N))) return r;
+  // y_hat = clamp(q + net(xyz, q), -1, 1) (model.py:202); losses + d(weighted loss) / d y_hat
+  yhat_kernel<<<(B * 7 + 255) / 256, 256, 0, s>>>(q_norm, w.dq, B * 7, t.yhat);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  if (y_hat) MPN_CHECK_CUDA(cudaMemcpyAsync(y_hat, t.yhat, (size_t)B * 7 * 4, cudaMemcpyDeviceToDevice, s));
+  if ((r = launch_bc_collision_losses(c, s, sc, B, t.yhat, supervision, n_loss_points, margin, w_collision, w_bc, losses, t.gy))) return r;
+  if (!grads) return MPN_OK;
+  clamp_bwd_kernel<<<(B * 7 + 255) / 256, 256, 0, s>>>(q_norm, w.dq, B * 7, t.gy);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  MPN_CHECK_CUDA(cudaMemsetAsync(grads, 0, (size_t)c->w.n_params * 4, s));
+  // decoder (model.py:58-66): 2112 -> 512 -> 256 -> 128 -> 7, LeakyReLU between
+  if ((r = dense_backward(c, s, W.dec[3], grads, t.gy, 7, t.d[2], 128, B, t.ga, 128, 1))) return r;
+  if ((r = dense_backward(c, s, W.dec[2], grads, t.ga, 128, t.d[1], 256, B, t.gb, 256, 1))) return r;
+  if ((r = dense_backward(c, s, W.dec[1], grads, t.gb, 256, t.d[0], 512, B, t.ga, 512, 1))) return r;
+  if ((r = dense_backward(c, s, W.dec[0], grads, t.ga, 512, w.cat, CAT, B, t.gcat, CAT, 0))) return r;
+  // feature_encoder (model.py:47-57): 7 -> 32 -> 64 -> 128 -> 128 -> 64
+  if ((r = dense_backward(c, s, W.fe[4], grads, t.gcat + ENC_DIM, CAT, t.f[3], 128, B, t.ga, 128, 1))) return r;
+  if ((r = dense_backward(c, s, W.fe[3], grads, t.ga, 128, t.f[2], 128, B, t.gb, 128, 1))) return r;
+  if ((r = dense_backward(c, s, W.fe[2], grads, t.gb, 128, t.f[1], 64, B, t.ga, 64, 1))) return r;
+  if ((r = dense_backward(c, s, W.fe[1], grads, t.ga, 64, t.f[0], 32, B, t.gb, 32, 1))) return r;
+  if ((r = dense_backward(c, s, W.fe[0], grads, t.gb, 32, q_norm, 7, B, nullptr, 0, 0))) return r;
+  // FC head (model.py:385-393)
+  if ((r = dense_backward(c, s, W.fc[2], grads, t.gcat, CAT, t.a2, 2048, B, t.ga, 2048, 0))) return r;
+  if ((r = gn_backward(c, s, t.z2, t.st2, W.gn_w[1], W.gn_b[1], t.ga, B, 2048, grads + (W.gn_w[1] - W.params), grads + (W.gn_b[1] - W.params)))) return r;
+  if ((r = dense_backward(c, s, W.fc[1], grads, t.ga, 2048, t.a1, 4096, B, t.gb, 4096, 0))) return r;
+  if ((r = gn_backward(c, s, t.z1, t.st1, W.gn_w[0], W.gn_b[0], t.gb, B, 4096, grads + (W.gn_w[0] - W.params), grads + (W.gn_b[0] - W.params)))) return r;
+  if ((r = dense_backward(c, s, W.fc[0], grads, t.gb, 4096, w.feat3, 1024, B, t.gfeat3, 1024, 0))) return r;
+  // set abstraction levels, last to first, in chunks of samples
+  MPN_CHECK_CUDA(cudaMemsetAsync(t.gfeat2, 0, (size_t)B * SA2_NPOINT * 256 * 4, s));
+  MPN_CHECK_CUDA(cudaMemsetAsync(t.gfeat1, 0, (size_t)B * SA1_NPOINT * 64 * 4, s));
+  const int chunk = t.chunk;
+  for (int b0 = 0; b0 < B; b0 += chunk)
+    if ((r = sa_backward_chunk(c, s, 2, b0, std::min(chunk, B - b0), SA2_NPOINT, w.xyz2, 3, w.feat2, 256, nullptr, nullptr, t.arg3,
+                               t.gfeat3, w.feat3, grads, t.gfeat2))) return r;
+  for (int b0 = 0; b0 < B; b0 += chunk)
+    if ((r = sa_backward_chunk(c, s, 1, b0, std::min(chunk, B - b0), SA1_NPOINT, w.xyz1, 3, w.feat1, 64, w.xyz2, t.ball2, t.arg2,
+                               t.gfeat2, w.feat2, grads, t.gfeat1))) return r;
+  for (int b0 = 0; b0 < B; b0 += chunk)
+    if ((r = sa_backward_chunk(c, s, 0, b0, std::min(chunk, B - b0), N, cloud, 4, cloud + 3, 4, w.xyz1, t.ball1, t.arg1, t.gfeat1,
+                               w.feat1, grads, nullptr))) return r;
+  return MPN_OK;
+}
+
+int adam_step(mpn_ctx* c, cudaStream_t s, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm,
+              int step, float* grad_norm_out) {
+  TrainWs& t = c->tw;
+  const long long n = c->w.n_params;
+  if (!t.adam_m) {
+    int r = 0;
+    r |= talloc(&t.adam_m, (size_t)n);
+    r |= talloc(&t.adam_v, (size_t)n);
+    r |= talloc(&t.norm, (size_t)NORM_CTAS + 1);
+    if (r) return MPN_ERR_NOMEM;
+    MPN_CHECK_CUDA(cudaMemsetAsync(t.adam_m, 0, (size_t)n * 4, s));
+    MPN_CHECK_CUDA(cudaMemsetAsync(t.adam_v, 0, (size_t)n * 4, s));
+  }
+  sumsq_partial_kernel<<<NORM_CTAS, 256, 0, s>>>(grads, n, t.norm + 1);
+  sumsq_final_kernel<<<1, NORM_CTAS, 0, s>>>(t.norm + 1, t.norm);
+  c->launches += 2;
+  if (grad_norm_out) MPN_CHECK_CUDA(cudaMemcpyAsync(grad_norm_out, t.norm, 4, cudaMemcpyDeviceToDevice, s));
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->w.params, grads, t.adam_m, t.adam_v, n, lr, beta1, beta2, eps, bc1,
+                                                          sqrtf(bc2), clip_norm, t.norm);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return refresh_transposes(c, s);
+}
+
+}  // namespace mpn

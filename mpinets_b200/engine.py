@@ -383,3 +383,91 @@ class Engine:
         _lib.check(self.lib.mpn_rollout(self._ctx, self.stream, precision, C.byref(s), B, N, _p(cloud), _p(q0), _p(target),
                                         steps, int(early_exit), int(check_every_step), _p(traj), _p(metrics)))
         return traj, metrics
+
+    # ------------------------------------------------------------------ training (model.py:185-240, 68-73)
+    @property
+    def param_count(self) -> int:
+        return int(self.lib.mpn_param_count(self._ctx))
+
+    def param_layout(self):
+        """[(state-dict key, offset, numel)] of the flat parameter / gradient vector"""
+        out, i = [], 0
+        name = C.create_string_buffer(160)
+        off, n = C.c_int64(0), C.c_int64(0)
+        while self.lib.mpn_param_info(self._ctx, i, name, 160, C.byref(off), C.byref(n)) == 0:
+            out.append((name.value.decode(), int(off.value), int(n.value)))
+            i += 1
+        if not out:
+            raise _lib.MpnError("no parameters: load a state dict first")
+        return out
+
+    def get_params(self) -> torch.Tensor:
+        p = self._empty(self.param_count)
+        _lib.check(self.lib.mpn_get_params(self._ctx, self.stream, _p(p)))
+        return p
+
+    def set_params(self, flat: torch.Tensor):
+        _check(flat, "params", device=self.device)
+        if flat.numel() != self.param_count:
+            raise RuntimeError(f"params has {flat.numel()} elements, expected {self.param_count}")
+        _lib.check(self.lib.mpn_set_params(self._ctx, self.stream, _p(flat)))
+
+    def weights_sync(self):
+        """rebuild the packed bf16 tensor-core weights from the fp32 parameters (after optimisation steps)"""
+        _lib.check(self.lib.mpn_weights_sync(self._ctx))
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """The current parameters under the reference's state-dict keys (Conv2d weights as [Cout, Cin, 1, 1])."""
+        flat = self.get_params()
+        sd = {}
+        lay = self.param_layout()
+        sizes = {k: m for (k, o, m) in lay}
+        for name, off, n in lay:
+            t = flat[off:off + n].clone()
+            if name.endswith(".weight") and ".fc_layer.1." not in name and ".fc_layer.4." not in name:
+                out_f = sizes[name[:-len("weight")] + "bias"]
+                t = t.view(out_f, n // out_f)
+                if ".SA_modules." in name:
+                    t = t.view(out_f, n // out_f, 1, 1)
+            sd[name] = t
+        return sd
+
+    def unflatten(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """views of a flat parameter / gradient vector by state-dict key (2-D weights)"""
+        lay = self.param_layout()
+        sizes = {k: m for (k, o, m) in lay}
+        out = {}
+        for name, off, n in lay:
+            t = flat[off:off + n]
+            if name.endswith(".weight") and ".fc_layer.1." not in name and ".fc_layer.4." not in name:
+                t = t.view(sizes[name[:-len("weight")] + "bias"], -1)
+            out[name] = t
+        return out
+
+    def train_step_grads(self, scene, cloud: torch.Tensor, q_norm: torch.Tensor, supervision: torch.Tensor,
+                         n_loss_points: int = 1024, margin: float = 0.03, w_collision: float = 5.0, w_bc: float = 1.0,
+                         grads: Optional[torch.Tensor] = None, need_grad: bool = True):
+        """training_step (model.py:185-240) up to the gradients: returns (losses [2] = (collision, point match),
+        y_hat [B,7], grads [param_count] or None).  fp32."""
+        _check(cloud, "xyz", device=self.device); _check(q_norm, "configuration", device=self.device)
+        _check(supervision, "supervision", device=self.device)
+        assert cloud.size(2) == 4
+        B, N, _ = cloud.shape
+        s, keep = self._scene(scene, B)
+        losses, y_hat = self._empty(2), self._empty(B, 7)
+        if need_grad and grads is None:
+            grads = self._empty(self.param_count)
+        if grads is not None:
+            _check(grads, "grads", device=self.device)
+        _lib.check(self.lib.mpn_train_step_grads(self._ctx, self.stream, C.byref(s), B, N, _p(cloud), _p(q_norm), _p(supervision),
+                                                 n_loss_points, margin, w_collision, w_bc, _p(losses), _p(y_hat),
+                                                 _p(grads) if need_grad else None))
+        return losses, y_hat, (grads if need_grad else None)
+
+    def adam_step(self, grads: torch.Tensor, step: int, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                  clip_norm: float = 1.0) -> torch.Tensor:
+        """clip_grad_norm_(clip_norm) + torch.optim.Adam on the flat vector; returns the pre-clip gradient norm [1]"""
+        _check(grads, "grads", device=self.device)
+        norm = self._empty(1)
+        _lib.check(self.lib.mpn_adam_step(self._ctx, self.stream, _p(grads), lr, betas[0], betas[1], eps, clip_norm, int(step), _p(norm)))
+        return norm

@@ -110,3 +110,78 @@ def rollout_until_success(mdl: MotionPolicyNetwork, q0: np.ndarray, target_pose:
 
 def _lib_steps_col() -> int:
     return 2   # MPN_M_STEPS
+
+
+class FlatAdam:
+    """``configure_optimizers`` (model.py:68-73: ``torch.optim.Adam(self.parameters(), lr=1e-4)``) plus the Trainer's
+    ``gradient_clip_val=1.0`` (run_training.py:112) and the DDP gradient averaging (run_training.py:71-77), on the engine's
+    flat parameter vector: ``step()`` = all-reduce-mean (when torch.distributed is initialised) -> clip -> Adam."""
+
+    def __init__(self, module: "TrainingMotionPolicyNetwork", lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 clip_norm: float = 1.0):
+        self.module, self.lr, self.betas, self.eps, self.clip_norm = module, lr, betas, eps, clip_norm
+        self.steps = 0
+        self.last_grad_norm = None
+
+    def zero_grad(self, set_to_none: bool = True):
+        pass   # the training step overwrites the gradient vector
+
+    def step(self):
+        from .parallel import allreduce_mean_
+        m = self.module
+        if m.grads is None:
+            raise RuntimeError("FlatAdam.step() before training_step()")
+        allreduce_mean_(m.grads)
+        self.steps += 1
+        eng = get_engine(m.grads.device)
+        self.last_grad_norm = eng.adam_step(m.grads, self.steps, self.lr, self.betas, self.eps, self.clip_norm)
+        m._dirty = True
+
+
+class TrainingMotionPolicyNetwork(MotionPolicyNetwork):
+    """model.py:94-352, the training side: ``training_step`` runs forward + losses + backward in the library (fp32) and
+    leaves the gradient of ``point_match_loss_weight * point_match + collision_loss_weight * collision`` in ``self.grads``
+    (flat, ``Engine.unflatten`` gives per-key views); ``configure_optimizers().step()`` applies it.  The nn.Module copies of
+    the weights are refreshed lazily (``pull_weights``)."""
+
+    def __init__(self, num_robot_points: int = NUM_ROBOT_POINTS, point_match_loss_weight: float = 1.0,
+                 collision_loss_weight: float = 5.0, precision: str = "fp32"):
+        super().__init__(precision)
+        self.num_robot_points = num_robot_points
+        self.point_match_loss_weight = point_match_loss_weight
+        self.collision_loss_weight = collision_loss_weight
+        self.grads: Optional[torch.Tensor] = None
+        self.logged: Dict[str, torch.Tensor] = {}
+        self._dirty = False
+
+    def configure_optimizers(self) -> FlatAdam:
+        return FlatAdam(self, lr=1e-4)
+
+    def log(self, name: str, value: torch.Tensor):
+        self.logged[name] = value
+
+    def training_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0) -> torch.Tensor:
+        """batch keys of data_loader.py:153-280: xyz [B,N,4], configuration [B,7], supervision [B,7], the seven primitive
+        tensors.  Returns the weighted loss (model.py:235-238)."""
+        xyz, q = batch["xyz"].contiguous(), batch["configuration"].contiguous()
+        eng = self._engine(xyz)
+        keys = ("cuboid_centers", "cuboid_dims", "cuboid_quats", "cylinder_centers", "cylinder_radii", "cylinder_heights", "cylinder_quats")
+        scene = {k: batch[k].contiguous().float() for k in keys}
+        losses, y_hat, self.grads = eng.train_step_grads(scene, xyz, q, batch["supervision"].contiguous(),
+                                                         w_collision=self.collision_loss_weight, w_bc=self.point_match_loss_weight,
+                                                         grads=self.grads)
+        self.log("point_match_loss", losses[1])
+        self.log("collision_loss", losses[0])
+        val_loss = self.point_match_loss_weight * losses[1] + self.collision_loss_weight * losses[0]
+        self.log("val_loss", val_loss)
+        return val_loss
+
+    def pull_weights(self):
+        """copy the engine's (optimised) parameters back into this module and refresh the bf16 tensor-core copies"""
+        dev = self._synced_device
+        if dev is None:
+            return
+        eng = get_engine(dev)
+        nn.Module.load_state_dict(self, {k: v for k, v in eng.state_dict().items()}, strict=False)
+        eng.weights_sync()
+        self._dirty = False

@@ -32,3 +32,13 @@ def gather_metrics(metrics: torch.Tensor, total: int) -> torch.Tensor:
     parts = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(parts, buf)
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    """DDP gradient averaging (run_training.py:71-77: DDPStrategy) on the flat gradient vector of the training step:
+    one all-reduce of 19.07 M floats, in place.  No-op for a single process."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(dist.get_world_size())
+    return flat

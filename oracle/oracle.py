@@ -476,3 +476,38 @@ def rollout(sd, cloud, q_norm, tables, steps, seed, emulate_bf16=False, n_robot=
         traj.append(qu)
         sample_robot(qu, tables, n_robot, seed, i + 1, cloud)
     return np.stack(traj, axis=1)
+
+
+# ----------------------------------------------------------------------------- training step (model.py:185-240)
+def train_step_grads(sd, cloud, q_norm, supervision, scene, tables, seed, n_points=1024, margin=0.03, w_collision=5.0, w_bc=1.0,
+                     dtype=torch.float32):
+    """TrainingMotionPolicyNetwork.training_step up to the parameter gradients.
+
+    y_hat = clamp(q + net(xyz, q), -1, 1) (model.py:202); (collision, point match) = CollisionAndBCLossContainer(y_hat, ...,
+    supervision) (loss.py:111-166, restated in C with its analytic d loss / d y_hat); the network backward is torch.autograd
+    over the torch restatement above (index gather = pointnet2 grouping, amax = max_pool2d).
+    Returns (losses np[2], y_hat np[B,7], grads {state-dict key: np array in the key's shape}, g_y np[B,7])."""
+    p = OrderedDict((k, v.detach().clone().to(dtype).requires_grad_(True)) for k, v in sd.items())
+    q = torch.as_tensor(np.asarray(q_norm), dtype=dtype)
+    dq = policy_forward(p, cloud, np.asarray(q_norm, dtype=np.float32), False, dtype)
+    y_hat = torch.clamp(q + dq, min=-1, max=1)
+    yh = y_hat.detach().to(torch.float32).numpy()
+    losses, g_y = bc_collision_losses(scene, yh, np.asarray(supervision, dtype=np.float32), tables, seed, n_points, margin,
+                                      w_collision, w_bc)
+    y_hat.backward(torch.from_numpy(g_y).to(dtype))
+    grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v)).detach().to(torch.float64).numpy()) for k, v in p.items())
+    return losses, yh, grads, g_y
+
+
+def adam_reference(params, grads, steps, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, clip_norm=1.0):
+    """torch.nn.utils.clip_grad_norm_ + torch.optim.Adam (model.py:68-73, run_training.py:112) applied `steps` times with
+    the same gradients: params / grads {key: np array} -> ({key: np array}, [grad norms])"""
+    ps = [torch.nn.Parameter(torch.as_tensor(np.asarray(v), dtype=torch.float32).clone()) for v in params.values()]
+    opt = torch.optim.Adam(ps, lr=lr, betas=betas, eps=eps)
+    norms = []
+    for _ in range(steps):
+        for p_, g in zip(ps, grads.values()):
+            p_.grad = torch.as_tensor(np.asarray(g), dtype=torch.float32).reshape(p_.shape).clone()
+        norms.append(float(torch.nn.utils.clip_grad_norm_(ps, clip_norm)) if clip_norm and clip_norm > 0 else 0.0)
+        opt.step()
+    return OrderedDict((k, p_.detach().numpy()) for k, p_ in zip(params.keys(), ps)), norms

@@ -1,0 +1,163 @@
+"""GPU parity tests of the training step (-m gpu; SURVEY.md section 8 row a21, BASELINE config 5): mpn_train_step_grads /
+mpn_adam_step through the C ABI against the CPU oracle (torch.autograd over the torch restatement of the network, the C
+restatement of CollisionAndBCLossContainer, torch.optim.Adam + clip_grad_norm_).
+
+Tolerance: the reference gradient is the oracle in float64.  Per tensor the bar is max|g - g_ref| <= tol * max|g_ref| with
+tol = max(1e-3, 10 x the oracle's own float32-vs-float64 difference for that tensor): the max-pool routes each channel's
+gradient to ONE neighbour row, and in SA1 (dense 5 cm balls) near-ties between rows flip with the last bits of the
+activations, which moves the first SA1 layers' gradients by ~5e-3 between torch-fp32 and torch-fp64 themselves
+(everywhere else the two agree to ~5e-7).  Losses 1e-6, y_hat 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import to_dev
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 1e-3
+
+
+def _batch(oracle, tables, B, seed=0, config=4):
+    from mpinets_b200 import scenes
+    p = scenes.config_problems(config, B, 0x4D50694E, 0)
+    rng = np.random.default_rng(seed)
+    cloud = oracle.build_cloud(p["q0"], p["target"], p, tables, 0x4D50694E)
+    qn = oracle.normalize(p["q0"], tables.joint_limits)
+    # supervision a step away; move part of the batch to random poses so the collision hinge is active somewhere
+    qn[B // 2:] = rng.uniform(-0.9, 0.9, (B - B // 2, 7)).astype(np.float32)
+    q_un = oracle.unnormalize(qn, tables.joint_limits)
+    oracle.sample_robot(q_un, tables, 2048, 0x4D50694E, 0, cloud)
+    sup = np.clip(qn + rng.normal(scale=0.05, size=qn.shape), -1, 1).astype(np.float32)
+    return p, cloud, qn, sup
+
+
+def _compare_grads(eng, flat, ref, ref32, tol=GRAD_TOL):
+    got = {k: v.cpu().numpy() for k, v in eng.unflatten(flat).items()}
+    report, bad = [], []
+    for k, r in ref.items():
+        g = got[k].reshape(r.shape)
+        scale = float(np.abs(r).max())
+        err = float(np.abs(g - r).max())
+        floor = float(np.abs(ref32[k] - r).max()) / max(scale, 1e-30)     # the oracle's own fp32 sensitivity
+        report.append((k, scale, err, err / max(scale, 1e-30), floor))
+        if not err <= max(tol, 10.0 * floor) * scale + 1e-9:
+            bad.append(k)
+    return report, bad
+
+
+def _dump(name, report):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", name), "w") as f:
+        for k, scale, err, rel, floor in report:
+            f.write(f"{k:60s} max|ref| {scale:.3e}  max|err| {err:.3e}  rel {rel:.2e}  oracle fp32-vs-fp64 {floor:.2e}\n")
+
+
+@pytest.mark.parametrize("chunk", [256, 2])
+def test_train_step_grads_match_oracle(engine_w, oracle, tables, state_dict, chunk):
+    """forward + losses + backward of training_step (model.py:185-240) vs torch.autograd, every parameter tensor;
+    chunk=2 runs the set-abstraction backward over several sample chunks (3 samples -> 2 + 1)"""
+    B = 3
+    p, cloud, qn, sup = _batch(oracle, tables, B)
+    os.environ["MPN_TRAIN_CHUNK"] = str(chunk)
+    try:
+        losses, y_hat, grads = engine_w.train_step_grads(to_dev(p), torch.from_numpy(cloud).cuda(), torch.from_numpy(qn).cuda(),
+                                                         torch.from_numpy(sup).cuda())
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("MPN_TRAIN_CHUNK", None)
+    ol, oy, og, _ = oracle.train_step_grads(state_dict, cloud, qn, sup, p, tables, engine_w.cfg.seed, dtype=torch.float64)
+    _, _, og32, _ = oracle.train_step_grads(state_dict, cloud, qn, sup, p, tables, engine_w.cfg.seed, dtype=torch.float32)
+    report, bad = _compare_grads(engine_w, grads, og, og32)
+    _dump(f"train_grads_chunk{chunk}.txt", report)
+    assert np.abs(y_hat.cpu().numpy() - oy).max() < 1e-5
+    assert np.abs(losses.cpu().numpy() - ol).max() < 1e-6 * max(1.0, float(np.abs(ol).max())) + 2e-7
+    assert ol[0] > 0 and ol[1] > 0, "the fixture should exercise both losses"
+    assert not bad, f"gradient mismatch in {bad}: " + "; ".join(f"{k} rel {r:.1e}" for k, _, _, r, _ in report if k in bad)
+    # padding floats between tensors stay zero
+    lay = engine_w.param_layout()
+    used = torch.zeros(engine_w.param_count, dtype=torch.bool, device="cuda")
+    for _, off, n in lay:
+        used[off:off + n] = True
+    assert float(grads[~used].abs().sum()) == 0.0
+
+
+def test_train_forward_equals_policy_forward(engine_w, oracle, tables):
+    """the training forward is the fp32 parity path: y_hat == clamp(q + mpn_policy_forward(fp32)) bit for bit"""
+    B = 5
+    p, cloud, qn, sup = _batch(oracle, tables, B, seed=1)
+    c = torch.from_numpy(cloud).cuda()
+    q = torch.from_numpy(qn).cuda()
+    losses, y_hat, _ = engine_w.train_step_grads(to_dev(p), c, q, torch.from_numpy(sup).cuda(), need_grad=False)
+    dq = engine_w.policy_forward(c, q)
+    assert torch.equal(y_hat, torch.clamp(q + dq, -1, 1))
+    l2, _ = engine_w.bc_collision_losses(to_dev(p), y_hat, torch.from_numpy(sup).cuda())
+    assert torch.equal(l2, losses)
+
+
+def test_train_step_is_deterministic_up_to_scatter_atomics(engine_w, oracle, tables):
+    B = 4
+    p, cloud, qn, sup = _batch(oracle, tables, B, seed=2)
+    args = (to_dev(p), torch.from_numpy(cloud).cuda(), torch.from_numpy(qn).cuda(), torch.from_numpy(sup).cuda())
+    _, _, g1 = engine_w.train_step_grads(*args)
+    g1 = g1.clone()
+    _, _, g2 = engine_w.train_step_grads(*args)
+    v1, v2 = engine_w.unflatten(g1), engine_w.unflatten(g2)
+    for k in v1:
+        if ".SA_modules.0." in k:      # below the feature scatter-add (float atomics): equal to rounding only
+            assert float((v1[k] - v2[k]).abs().max()) <= 1e-5 * float(v1[k].abs().max()) + 1e-12, k
+        else:
+            assert torch.equal(v1[k], v2[k]), k
+
+
+def test_adam_step_matches_torch(engine, oracle, state_dict):
+    """clip_grad_norm_(1.0) + Adam(lr 1e-4) on the flat vector vs torch.optim.Adam, three steps"""
+    engine.load_state_dict(state_dict)
+    lay = engine.param_layout()
+    n = engine.param_count
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    grads = torch.zeros(n, device="cuda")
+    ref_g = {}
+    for k, off, m in lay:
+        g = torch.randn(m, generator=gen, device="cuda") * 1e-3
+        grads[off:off + m] = g
+        ref_g[k] = g.cpu().numpy()
+    norms = [float(engine.adam_step(grads, step=i + 1, lr=1e-4, clip_norm=1.0)) for i in range(3)]
+    got = engine.state_dict()
+    ref_p, ref_norms = oracle.adam_reference({k: state_dict[k].numpy() for k, _, _ in lay}, ref_g, 3, lr=1e-4, clip_norm=1.0)
+    assert np.allclose(norms, ref_norms, rtol=1e-5)
+    assert ref_norms[0] > 1.0, "the fixture should exercise clipping"
+    for k, _, _ in lay:
+        a, b = got[k].cpu().numpy().reshape(-1), ref_p[k].reshape(-1)
+        assert np.abs(a - b).max() < 2e-7 + 1e-6 * np.abs(b).max(), k
+        assert np.abs(a - state_dict[k].numpy().reshape(-1)).max() > 1e-5, k     # it moved
+    engine.load_state_dict(state_dict)
+
+
+def test_training_loop_reduces_loss_and_weights_round_trip(oracle, tables, state_dict):
+    """TrainingMotionPolicyNetwork.training_step + configure_optimizers().step() (model.py:68-73,185-240) through the
+    reference-shaped host API; after pull_weights() the fp32 forward uses the optimised weights (oracle forward agrees)"""
+    from mpinets_b200 import model as M
+    from mpinets_b200.runtime import get_engine
+    B = 6
+    p, cloud, qn, sup = _batch(oracle, tables, B, seed=3)
+    net = M.TrainingMotionPolicyNetwork()
+    net.load_state_dict({k: v.clone() for k, v in state_dict.items()})
+    batch = dict(to_dev(p), xyz=torch.from_numpy(cloud).cuda(), configuration=torch.from_numpy(qn).cuda(),
+                 supervision=torch.from_numpy(sup).cuda())
+    opt = net.configure_optimizers()
+    opt.lr = 1e-3
+    losses = []
+    for it in range(6):
+        losses.append(float(net.training_step(batch, it)))
+        opt.step()
+    assert losses[-1] < losses[0], losses
+    assert float(opt.last_grad_norm) > 0
+    net.pull_weights()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    dq = net.forward(batch["xyz"], batch["configuration"]).cpu().numpy()      # default precision of the training module: fp32
+    odq = oracle.policy_forward(sd, cloud, qn).numpy()
+    assert np.abs(dq - odq).max() < 1e-5
+    assert np.abs(odq - oracle.policy_forward(state_dict, cloud, qn).numpy()).max() > 1e-4   # the weights did change
+    get_engine(batch["xyz"].device).load_state_dict(state_dict)
