@@ -216,6 +216,10 @@ int mpn_weights_sync(mpn_ctx* ctx);
 int mpn_train_step_grads(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, int N, const float* cloud,
                          const float* q_norm, const float* supervision, int n_loss_points, float margin, float w_collision,
                          float w_bc, float* losses, float* y_hat, float* grads);
+/* the max-pool routing of the last training step: for module 0 / 1 / 2 the neighbour row (0..127, in ball-query order;
+ * group-all: the SA2 centroid) that won each output channel, u8 [B][512][64] / [B][128][256] / [B][1024] (device).  The
+ * backward pass sends each channel's gradient to exactly this row (max_pool2d backward); parity tests replay it. */
+int mpn_train_pooled_rows(mpn_ctx* ctx, void* stream, int module, int B, uint8_t* dst);
 /* torch.nn.utils.clip_grad_norm_(max_norm = clip_norm; <= 0 disables; run_training.py:112 uses 1.0) followed by
  * torch.optim.Adam (model.py:68-73: lr 1e-4, betas (0.9, 0.999), eps 1e-8) on the flat vector; `step` counts from 1;
  * grad_norm (optional, device float) receives the total gradient norm before clipping. */

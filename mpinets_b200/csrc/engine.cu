@@ -660,6 +660,16 @@ int mpn_train_step_grads(mpn_ctx* c, void* stream, const mpn_scene* scene, int B
                           losses, y_hat, grads);
 }
 
+int mpn_train_pooled_rows(mpn_ctx* c, void* stream, int module, int B, uint8_t* dst) {
+  REQ_CTX(c);
+  MPN_REQUIRE(module >= 0 && module <= 2 && dst, "mpn_train_pooled_rows: bad arguments");
+  MPN_REQUIRE(B >= 1 && B <= c->tw.capacity, "mpn_train_pooled_rows: no training step of >= %d samples has run", B);
+  const uint8_t* src = module == 0 ? c->tw.arg1 : module == 1 ? c->tw.arg2 : c->tw.arg3;
+  const size_t per = module == 0 ? (size_t)SA1_NPOINT * 64 : module == 1 ? (size_t)SA2_NPOINT * 256 : 1024;
+  MPN_CHECK_CUDA(cudaMemcpyAsync(dst, src, per * B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MPN_OK;
+}
+
 int mpn_adam_step(mpn_ctx* c, void* stream, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm,
                   int step, float* grad_norm) {
   REQ_CTX(c); REQ_WEIGHTS(c);

@@ -606,7 +606,7 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
   r |= talloc(&t.H2, k * SA2_NPOINT * 128 * 128);
   r |= talloc(&t.src, k * SA1_NPOINT * 64);
   r |= talloc(&t.slot, k * SA1_NPOINT * 64);
-  t.partial_floats = (size_t)8 << 20;
+  t.partial_floats = (size_t)20 << 20;   // >= the largest single weight tensor (fc_layer.3: 8.4 M) + bias
   r |= talloc(&t.partial, t.partial_floats);
   if (r) { free_train_ws(c); return MPN_ERR_NOMEM; }
   t.capacity = B; t.chunk = chunk; t.n_points = N;

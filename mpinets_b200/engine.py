@@ -464,6 +464,15 @@ class Engine:
                                                  _p(grads) if need_grad else None))
         return losses, y_hat, (grads if need_grad else None)
 
+    def train_pooled_rows(self, B: int):
+        """max-pool routing of the last training step: (u8 [B,512,64], u8 [B,128,256], u8 [B,1024])"""
+        outs = []
+        for m, shape in enumerate(((B, 512, 64), (B, 128, 256), (B, 1024))):
+            t = self._empty(*shape, dtype=torch.uint8)
+            _lib.check(self.lib.mpn_train_pooled_rows(self._ctx, self.stream, m, B, _p(t)))
+            outs.append(t)
+        return tuple(outs)
+
     def adam_step(self, grads: torch.Tensor, step: int, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                   clip_norm: float = 1.0) -> torch.Tensor:
         """clip_grad_norm_(clip_norm) + torch.optim.Adam on the flat vector; returns the pre-clip gradient norm [1]"""

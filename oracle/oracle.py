@@ -393,7 +393,7 @@ def _dense(x, w, b, emulate_bf16, dtype, round_bias=False):
     return (x.to(dtype) @ w.to(dtype).t() + b.to(dtype))
 
 
-def sa_module(xyz, feats, spec, weights, emulate_bf16=False, dtype=torch.float32, return_aux=False, round_bias=None):
+def sa_module(xyz, feats, spec, weights, emulate_bf16=False, dtype=torch.float32, return_aux=False, round_bias=None, pool_idx=None):
     """xyz np[B,N,3] fp32, feats torch[B,N,C] (row-major per point) -> (new_xyz np[B,m,3] | None, feats torch[B,m,Cout])
 
     Shared-MLP rows are [dx,dy,dz, features...] in the Conv2d input-channel order (QueryAndGroup, use_xyz=True)."""
@@ -417,13 +417,20 @@ def sa_module(xyz, feats, spec, weights, emulate_bf16=False, dtype=torch.float32
         round_bias = {512: (True, True, True), 128: (True, False, False)}.get(spec["npoint"], (False,) * 3) if emulate_bf16 else (False,) * 3
     for (w, b), rb in zip(weights, round_bias):
         x = torch.relu(_dense(x, w.reshape(w.shape[0], -1), b, emulate_bf16, dtype, rb))
-    out = x.max(dim=2).values                                                                               # [B,m,Cout]
+    if pool_idx is None:
+        out = x.max(dim=2).values                                                                           # [B,m,Cout]
+    else:
+        # replay a given max-pool routing (row per channel): same forward value when the routing is valid, and the
+        # backward sends each channel's gradient to exactly that row -- removes near-tie argmax flips from gradient parity
+        pi = torch.as_tensor(np.asarray(pool_idx), dtype=torch.int64).reshape(x.shape[0], x.shape[1], 1, x.shape[3])
+        out = x.gather(2, pi)[:, :, 0]
+        aux.update(pool_gap=(x.max(dim=2).values - out).detach(), pool_argmax=x.argmax(dim=2).detach())
     if emulate_bf16 and spec["npoint"] is not None:
         out = _round_bf16(out.float()).to(dtype)   # hand-off tensors are stored in bf16 in the tensor-core mode
     return (new_xyz, out, aux) if return_aux else (new_xyz, out)
 
 
-def encoder_forward(sd, cloud, emulate_bf16=False, dtype=torch.float32, return_aux=False):
+def encoder_forward(sd, cloud, emulate_bf16=False, dtype=torch.float32, return_aux=False, pool_idx=None):
     """cloud np[B,N,4] -> pc encoding torch[B,2048] (model.py:409-426)"""
     cloud = np.ascontiguousarray(cloud, dtype=np.float32)
     xyz = np.ascontiguousarray(cloud[..., :3])
@@ -432,7 +439,7 @@ def encoder_forward(sd, cloud, emulate_bf16=False, dtype=torch.float32, return_a
     for s, spec in enumerate(SA_SPECS):
         ws = [(sd[f"point_cloud_encoder.SA_modules.{s}.mlps.0.{2 * l}.weight"],
                sd[f"point_cloud_encoder.SA_modules.{s}.mlps.0.{2 * l}.bias"]) for l in range(3)]
-        r = sa_module(xyz, feats, spec, ws, emulate_bf16, dtype, return_aux=True)
+        r = sa_module(xyz, feats, spec, ws, emulate_bf16, dtype, return_aux=True, pool_idx=None if pool_idx is None else pool_idx[s])
         xyz, feats = r[0], r[1]
         auxs.append(dict(r[2], new_xyz=r[0], feats=r[1]))
     x = feats[:, 0]  # [B,1024]
@@ -445,9 +452,9 @@ def encoder_forward(sd, cloud, emulate_bf16=False, dtype=torch.float32, return_a
     return (x, auxs) if return_aux else x
 
 
-def policy_forward(sd, cloud, q_norm, emulate_bf16=False, dtype=torch.float32, return_aux=False):
+def policy_forward(sd, cloud, q_norm, emulate_bf16=False, dtype=torch.float32, return_aux=False, pool_idx=None):
     """MotionPolicyNetwork.forward (model.py:75-91): -> delta q (normalised) torch[B,7]"""
-    enc = encoder_forward(sd, cloud, emulate_bf16, dtype, return_aux)
+    enc = encoder_forward(sd, cloud, emulate_bf16, dtype, return_aux, pool_idx)
     aux = None
     if return_aux:
         enc, aux = enc
@@ -480,34 +487,39 @@ def rollout(sd, cloud, q_norm, tables, steps, seed, emulate_bf16=False, n_robot=
 
 # ----------------------------------------------------------------------------- training step (model.py:185-240)
 def train_step_grads(sd, cloud, q_norm, supervision, scene, tables, seed, n_points=1024, margin=0.03, w_collision=5.0, w_bc=1.0,
-                     dtype=torch.float32):
+                     dtype=torch.float32, pool_idx=None, return_aux=False):
     """TrainingMotionPolicyNetwork.training_step up to the parameter gradients.
 
     y_hat = clamp(q + net(xyz, q), -1, 1) (model.py:202); (collision, point match) = CollisionAndBCLossContainer(y_hat, ...,
     supervision) (loss.py:111-166, restated in C with its analytic d loss / d y_hat); the network backward is torch.autograd
     over the torch restatement above (index gather = pointnet2 grouping, amax = max_pool2d).
-    Returns (losses np[2], y_hat np[B,7], grads {state-dict key: np array in the key's shape}, g_y np[B,7])."""
+    pool_idx (optional, 3 arrays): replay this max-pool routing instead of torch's own argmax (see sa_module).
+    Returns (losses np[2], y_hat np[B,7], grads {state-dict key: np array in the key's shape}, g_y np[B,7][, aux])."""
     p = OrderedDict((k, v.detach().clone().to(dtype).requires_grad_(True)) for k, v in sd.items())
     q = torch.as_tensor(np.asarray(q_norm), dtype=dtype)
-    dq = policy_forward(p, cloud, np.asarray(q_norm, dtype=np.float32), False, dtype)
+    dq = policy_forward(p, cloud, np.asarray(q_norm, dtype=np.float32), False, dtype, return_aux, pool_idx)
+    aux = None
+    if return_aux:
+        dq, aux = dq
     y_hat = torch.clamp(q + dq, min=-1, max=1)
     yh = y_hat.detach().to(torch.float32).numpy()
     losses, g_y = bc_collision_losses(scene, yh, np.asarray(supervision, dtype=np.float32), tables, seed, n_points, margin,
                                       w_collision, w_bc)
     y_hat.backward(torch.from_numpy(g_y).to(dtype))
     grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v)).detach().to(torch.float64).numpy()) for k, v in p.items())
-    return losses, yh, grads, g_y
+    return (losses, yh, grads, g_y, aux) if return_aux else (losses, yh, grads, g_y)
 
 
 def adam_reference(params, grads, steps, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, clip_norm=1.0):
     """torch.nn.utils.clip_grad_norm_ + torch.optim.Adam (model.py:68-73, run_training.py:112) applied `steps` times with
     the same gradients: params / grads {key: np array} -> ({key: np array}, [grad norms])"""
-    ps = [torch.nn.Parameter(torch.as_tensor(np.asarray(v), dtype=torch.float32).clone()) for v in params.values()]
+    # float64: torch's CPU float32 norm reduction is itself ~1.6e-4 off the exact norm on 19 M elements
+    ps = [torch.nn.Parameter(torch.as_tensor(np.asarray(v), dtype=torch.float64).clone()) for v in params.values()]
     opt = torch.optim.Adam(ps, lr=lr, betas=betas, eps=eps)
     norms = []
     for _ in range(steps):
         for p_, g in zip(ps, grads.values()):
-            p_.grad = torch.as_tensor(np.asarray(g), dtype=torch.float32).reshape(p_.shape).clone()
+            p_.grad = torch.as_tensor(np.asarray(g), dtype=torch.float64).reshape(p_.shape).clone()
         norms.append(float(torch.nn.utils.clip_grad_norm_(ps, clip_norm)) if clip_norm and clip_norm > 0 else 0.0)
         opt.step()
     return OrderedDict((k, p_.detach().numpy()) for k, p_ in zip(params.keys(), ps)), norms
