@@ -128,6 +128,18 @@ int mpn_build_cloud(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, c
 int mpn_build_cloud_from_points(mpn_ctx* ctx, void* stream, int B, const float* q0, const float* target,
                                 const float* obstacle_points, const int32_t* obstacle_counts, int max_points,
                                 uint32_t problem0, float* cloud);
+/* Depth-camera obstacle clouds: stand-in for run_inference.convert_primitive_problems_to_depth (run_inference.py:194-257),
+ * which renders the primitives (robot removed) with Bullet from the fixed evaluation cameras of :215-243 and un-projects the
+ * depth image (robofin.bullet.get_pointcloud_from_camera, un-vendored).  Here each pixel's ray is intersected analytically
+ * with every valid cuboid / cylinder; the nearest hit with depth in [near_depth, far_depth] gives one world point.
+ *   camera: camera->world pose(s), 3x4 row-major, [12] shared or [B][12] (per_problem_camera != 0); OpenGL camera frame
+ *   (x right, y up, looking along -z: the convention under which the poses of run_inference.py:215-243 face their scenes);
+ *   pixel (row, col), row 0 at the top, looks along ((2 (col + .5) / W - 1) tan_half_fov_x, -(2 (row + .5) / H - 1)
+ *   tan_half_fov_y, -1).  points [B][W*H][3]: the hits compacted to the front in pixel order; counts i32 [B].
+ * The result feeds mpn_build_cloud_from_points. */
+int mpn_render_depth_cloud(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* camera,
+                           int per_problem_camera, int width, int height, float tan_half_fov_x, float tan_half_fov_y,
+                           float near_depth, float far_depth, float* points, int32_t* counts);
 /* validation collision sweep (model.py:293-314): traj [B][T][7] unnormalised -> flags u8 [B] (OR-ed into existing
  * content when accumulate != 0), first_step i32 [B] (optional; step index offset by t0; -1 when none) */
 int mpn_sweep_flags(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* traj, int T, int t0,

@@ -513,6 +513,21 @@ int mpn_build_cloud_from_points(mpn_ctx* c, void* stream, int B, const float* q0
                             max_points);
 }
 
+int mpn_render_depth_cloud(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* camera, int per_problem_camera,
+                           int width, int height, float tan_half_fov_x, float tan_half_fov_y, float near_depth, float far_depth,
+                           float* points, int32_t* counts) {
+  REQ_CTX(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(camera && points && counts, "mpn_render_depth_cloud: null pointer");
+  MPN_REQUIRE(width >= 1 && height >= 1 && (int64_t)width * height <= (1 << 24), "mpn_render_depth_cloud: bad image size");
+  MPN_REQUIRE(tan_half_fov_x > 0.f && tan_half_fov_y > 0.f && near_depth >= 0.f && far_depth > near_depth,
+              "mpn_render_depth_cloud: bad intrinsics");
+  if (B == 0) return MPN_OK;
+  return launch_render_depth(c, (cudaStream_t)stream, *scene, B, camera, per_problem_camera, width, height, tan_half_fov_x,
+                             tan_half_fov_y, near_depth, far_depth, points, counts);
+}
+
 int mpn_sweep_flags(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* traj, int T, int t0, int accumulate,
                     uint8_t* flags, int32_t* first_step) {
   REQ_CTX(c); REQ_TABLES(c);

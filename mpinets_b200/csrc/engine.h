@@ -166,6 +166,8 @@ int launch_evaluate(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, cons
                     const float* target, const mpn_scene& tv, int V1, int V2, const mpn_scene& nv, int N1, int N2, float* out);
 int launch_sparc(mpn_ctx* c, cudaStream_t s, int B, int n_max, const float* movement, const int32_t* num, float fs, int padlevel, float fc,
                  float amp_th, float* out);
+int launch_render_depth(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* camera, int per_problem_camera, int W, int H,
+                        float sx, float sy, float tnear, float tfar, float* points, int32_t* counts);
 // ---- loss.cu
 int launch_collision_loss(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int N, const float* points, float margin, float* loss,
                           float* grad_points);

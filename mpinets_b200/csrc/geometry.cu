@@ -692,4 +692,113 @@ int launch_sparc(mpn_ctx* c, cudaStream_t s, int B, int n_max, const float* move
   return MPN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- depth-camera clouds
+// Stand-in for run_inference.convert_primitive_problems_to_depth (run_inference.py:194-257: Bullet renders a depth image of
+// the primitives from a fixed camera, robot removed, and un-projects it).  Here every pixel's ray is intersected
+// analytically with the scene's cuboids and cylinders in their own frames (the frames of the SDF, so a hit has sdf = 0);
+// the nearest hit with camera depth in [near, far] becomes one world point.  Camera frame: OpenGL convention (x right, y up,
+// looking along -z) -- the one under which the reference's evaluation cameras (run_inference.py:215-243) face their scenes;
+// ray direction (u sx, -v sy, -1) with v growing downwards, so the ray parameter IS the depth.  Spec arithmetic throughout (bit-exact vs the oracle).
+__device__ __forceinline__ float ray_cuboid(const PrimFrame& f, const float* o, const float* d, float tnear, float tfar) {
+  float t0 = tnear, t1 = tfar;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float ol = fadd(dot3(f.R[3 * i], f.R[3 * i + 1], f.R[3 * i + 2], o[0], o[1], o[2]), f.Rt[i]);
+    const float dl = dot3(f.R[3 * i], f.R[3 * i + 1], f.R[3 * i + 2], d[0], d[1], d[2]);
+    if (dl == 0.0f) {
+      if (fabsf(ol) > f.h[i]) return __int_as_float(0x7f800000);
+      continue;
+    }
+    const float inv = fdiv(1.0f, dl);
+    const float ta = fmul(fsub(-f.h[i], ol), inv), tb = fmul(fsub(f.h[i], ol), inv);
+    t0 = fmaxf(t0, fminf(ta, tb));
+    t1 = fminf(t1, fmaxf(ta, tb));
+  }
+  return t0 <= t1 ? t0 : __int_as_float(0x7f800000);
+}
+
+__device__ __forceinline__ float ray_cylinder(const PrimFrame& f, const float* o, const float* d, float tnear, float tfar) {
+  float ol[3], dl[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    ol[i] = fadd(dot3(f.R[3 * i], f.R[3 * i + 1], f.R[3 * i + 2], o[0], o[1], o[2]), f.Rt[i]);
+    dl[i] = dot3(f.R[3 * i], f.R[3 * i + 1], f.R[3 * i + 2], d[0], d[1], d[2]);
+  }
+  const float r2 = fmul(f.h[0], f.h[0]), hh = f.h[1];
+  float best = __int_as_float(0x7f800000);
+  const float a = ffma(dl[1], dl[1], fmul(dl[0], dl[0]));
+  if (a > 0.0f) {                                     // side wall, entry point
+    const float bq = ffma(ol[1], dl[1], fmul(ol[0], dl[0]));
+    const float cq = fsub(ffma(ol[1], ol[1], fmul(ol[0], ol[0])), r2);
+    const float disc = fsub(fmul(bq, bq), fmul(a, cq));
+    if (disc >= 0.0f) {
+      const float t = fdiv(fsub(-bq, fsqrt(disc)), a);
+      const float z = ffma(t, dl[2], ol[2]);
+      if (t >= tnear && t <= tfar && fabsf(z) <= hh) best = t;
+    }
+  }
+  if (dl[2] != 0.0f) {                                // the two caps
+    const float inv = fdiv(1.0f, dl[2]);
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      const float t = fmul(fsub(sgn ? -hh : hh, ol[2]), inv);
+      const float x = ffma(t, dl[0], ol[0]), y = ffma(t, dl[1], ol[1]);
+      if (t >= tnear && t <= tfar && ffma(y, y, fmul(x, x)) <= r2) best = fminf(best, t);
+    }
+  }
+  return best;
+}
+
+// CTA per problem; hit pixels are compacted to the front of points[b] in pixel (row-major) order.
+__global__ void __launch_bounds__(256) render_depth_kernel(mpn_scene sc, int M1, int M2, int quirk, const float* __restrict__ camera,
+                                                           int camera_stride, int W, int H, float du, float dv, float sx, float sy,
+                                                           float tnear, float tfar, float* __restrict__ points,
+                                                           int32_t* __restrict__ counts) {
+  __shared__ PrimFrame fr[MAX_PRIMS];
+  __shared__ int cnts[2], wcnt[8], wtot[8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  stage_scene_compact(sc, b, M1, M2, quirk != 0, fr, cnts, wcnt);
+  const int nc = cnts[0], ny = cnts[1];
+  const float* C = camera + (size_t)b * camera_stride;
+  const float o[3] = {C[3], C[7], C[11]};
+  float* out = points + (size_t)b * W * H * 3;
+  int base = 0;
+  for (int p0 = 0; p0 < W * H; p0 += 256) {
+    const int pix = p0 + threadIdx.x;
+    float t = __int_as_float(0x7f800000), d[3] = {0.f, 0.f, 0.f};
+    if (pix < W * H) {
+      const int row = pix / W, col = pix - row * W;
+      const float u = ffma((float)col + 0.5f, du, -1.0f), v = ffma((float)row + 0.5f, dv, -1.0f);
+      const float dcx = fmul(u, sx), dcy = fmul(v, sy);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) d[i] = fsub(ffma(-C[4 * i + 1], dcy, fmul(C[4 * i], dcx)), C[4 * i + 2]);
+      for (int m = 0; m < nc; ++m) t = fminf(t, ray_cuboid(fr[m], o, d, tnear, tfar));
+      for (int m = nc; m < nc + ny; ++m) t = fminf(t, ray_cylinder(fr[m], o, d, tnear, tfar));
+    }
+    const bool hit = t <= tfar;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) wtot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < warp) off += wtot[w]; tot += wtot[w]; }
+    if (hit) {
+      float* q = out + (size_t)(off + __popc(bal & ((1u << lane) - 1u))) * 3;
+      q[0] = ffma(t, d[0], o[0]); q[1] = ffma(t, d[1], o[1]); q[2] = ffma(t, d[2], o[2]);
+    }
+    base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[b] = base;
+}
+
+int launch_render_depth(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* camera, int per_problem_camera, int W, int H,
+                        float sx, float sy, float tnear, float tfar, float* points, int32_t* counts) {
+  render_depth_kernel<<<B, 256, 0, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, c->cfg.quirk_frames, camera,
+                                        per_problem_camera ? 12 : 0, W, H, 2.0f / (float)W, 2.0f / (float)H, sx, sy, tnear, tfar, points, counts);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
 }  // namespace mpn

@@ -258,6 +258,24 @@ class Engine:
                                                         _p(obstacle_counts), obstacle_points.shape[1], problem0, _p(cloud)))
         return cloud
 
+    def render_depth_cloud(self, scene, camera: torch.Tensor, width: int = 640, height: int = 480, fov_y_deg: float = 60.0,
+                           near: float = 0.01, far: float = 10.0):
+        """Partial-view obstacle clouds (run_inference.convert_primitive_problems_to_depth, run_inference.py:194-257):
+        camera [3,4] or [B,3,4] camera->world -> (points [B, W*H, 3] with the hits first, counts i32 [B])."""
+        import math
+        _check(camera, "camera", device=self.device)
+        B = scene["cuboid_centers"].shape[0]
+        s, keep = self._scene(scene, B)
+        per = camera.dim() == 3
+        if per and camera.shape[0] != B:
+            raise RuntimeError(f"camera has batch {camera.shape[0]}, expected {B}")
+        ty = math.tan(math.radians(fov_y_deg) / 2.0)
+        pts = self._empty(B, width * height, 3)
+        cnt = self._empty(B, dtype=torch.int32)
+        _lib.check(self.lib.mpn_render_depth_cloud(self._ctx, self.stream, C.byref(s), B, _p(camera), int(per), width, height,
+                                                   ty * width / height, ty, near, far, _p(pts), _p(cnt)))
+        return pts, cnt
+
     def sweep_flags(self, scene, traj: torch.Tensor):
         _check(traj, "traj", device=self.device)
         B, T, _ = traj.shape

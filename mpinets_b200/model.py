@@ -185,3 +185,32 @@ class TrainingMotionPolicyNetwork(MotionPolicyNetwork):
         nn.Module.load_state_dict(self, {k: v for k, v in eng.state_dict().items()}, strict=False)
         eng.weights_sync()
         self._dirty = False
+
+    # -- validation (model.py:252-352)
+    VALIDATION_ROLLOUT_LENGTH = 69   # model.py:272
+
+    def validation_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0, rollout_length: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """model.py:252-318 in one library call: 69-step lock-step rollout, final end-effector error against
+        batch["target_position"] [B,3], link-sphere SDF sweep over the 70 configurations -> avg_target_error,
+        avg_collision_rate.  batch["xyz"] is updated in place like the reference's rollout."""
+        T = self.VALIDATION_ROLLOUT_LENGTH if rollout_length is None else rollout_length
+        xyz, q = batch["xyz"], batch["configuration"].contiguous()
+        eng = self._engine(xyz)
+        B = q.shape[0]
+        keys = ("cuboid_centers", "cuboid_dims", "cuboid_quats", "cylinder_centers", "cylinder_radii", "cylinder_heights", "cylinder_quats")
+        scene = {k: batch[k].contiguous().float() for k in keys}
+        target = torch.eye(4, device=xyz.device)[:3].repeat(B, 1, 1)
+        target[:, :, 3] = batch["target_position"]
+        traj, metrics = eng.rollout(scene, xyz, eng.unnormalize(q), target.contiguous(), T, precision=PRECISIONS[self.precision])
+        position_error = metrics[:, 3]       # MPN_M_POS_ERR: ||eff(rollout[-1]) - target_position||
+        has_collision = metrics[:, 0] > 0    # MPN_M_COLLISION: any sphere, any of the T + 1 configurations, sdf <= radius
+        self.last_rollout = traj
+        return {"avg_target_error": position_error.mean(), "avg_collision_rate": torch.count_nonzero(has_collision) / B}
+
+    def validation_step_end(self, batch_parts: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return {"avg_target_error": torch.mean(batch_parts["avg_target_error"]),
+                "avg_collision_rate": torch.mean(batch_parts["avg_collision_rate"])}
+
+    def validation_epoch_end(self, validation_step_outputs):
+        self.log("avg_target_error", torch.mean(torch.stack([x["avg_target_error"] for x in validation_step_outputs])))
+        self.log("avg_collision_rate", torch.mean(torch.stack([x["avg_collision_rate"] for x in validation_step_outputs])))

@@ -54,3 +54,46 @@ def calculate_metrics(mdl: MotionPolicyNetwork, problem_set: ProblemSet, device:
         run_problems(mdl, [flat[i][2] for i in idx], device, max_steps, evaluator=ev, problem0=offset)
         offset += len(idx)
     return ev
+
+
+# camera->world poses of the evaluation views (run_inference.py:215-243 builds SE3(xyz, quaternion).inverse = world->camera)
+_EVAL_CAMERAS = {
+    "dresser": ((0.08307640315968651, 1.986952324350807, 0.9996085854670145),
+                (-0.10162310189063647, -0.06726290364234049, 0.5478233048853433, 0.8276702686337273)),
+    "cubby": ((0.08307640315968651, 1.986952324350807, 0.9996085854670145),
+              (-0.10162310189063647, -0.06726290364234049, 0.5478233048853433, 0.8276702686337273)),
+    "tabletop": ((1.5031788593125708, -1.817341016921562, 1.278088299149147),
+                 (0.8687241016192855, 0.4180885960330695, 0.11516106409944685, 0.23928704613569252)),
+}
+
+
+def eval_camera(environment_type: str) -> np.ndarray:
+    """camera->world [3,4] of the view the reference evaluates `environment_type` with (run_inference.py:215-247)"""
+    from .mpinets_types import SE3
+    for key, (xyz, quat) in _EVAL_CAMERAS.items():
+        if key in environment_type:
+            return SE3(xyz, quat).matrix[:3].astype(np.float32)
+    raise NotImplementedError(f"Camera angle is not implemented for environment type: {environment_type}")   # run_inference.py:244-247
+
+
+def convert_primitive_problems_to_depth(problems: ProblemSet, device: Optional[torch.device] = None, width: int = 640,
+                                        height: int = 480, fov_y_deg: float = 60.0, near: float = 0.01, far: float = 10.0,
+                                        engine=None):
+    """run_inference.convert_primitive_problems_to_depth (run_inference.py:194-257), in place: every problem gets an
+    ``obstacle_point_cloud`` seen from its environment's evaluation camera.  The reference renders with Bullet and removes
+    the robot; here the primitives are ray-cast analytically on the GPU (``mpn_render_depth_cloud``), one launch per
+    environment type."""
+    from .runtime import get_engine
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    eng = engine or get_engine(device)
+    for environment_type, scene_sets in problems.items():
+        cam = torch.from_numpy(eval_camera(environment_type)).to(device).contiguous()
+        plist = [p for problem_set in scene_sets.values() for p in problem_set]
+        if not plist:
+            continue
+        soa = problems_to_soa(plist)
+        scene = {k: torch.from_numpy(np.ascontiguousarray(soa[k])).to(device) for k in SCENE_KEYS}
+        pts, cnt = eng.render_depth_cloud(scene, cam, width, height, fov_y_deg, near, far)
+        pts, cnt = pts.cpu().numpy(), cnt.cpu().numpy()
+        for i, p in enumerate(plist):
+            p.obstacle_point_cloud = pts[i, :cnt[i]].copy()

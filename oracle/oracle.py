@@ -523,3 +523,30 @@ def adam_reference(params, grads, steps, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, 
         norms.append(float(torch.nn.utils.clip_grad_norm_(ps, clip_norm)) if clip_norm and clip_norm > 0 else 0.0)
         opt.step()
     return OrderedDict((k, p_.detach().numpy()) for k, p_ in zip(params.keys(), ps)), norms
+
+
+# ----------------------------------------------------------------------------- depth-camera clouds (run_inference.py:194-257)
+# the evaluation cameras of run_inference.py:215-243 (world->camera = SE3(xyz, quaternion wxyz).inverse there; these are the
+# un-inverted camera->world poses)
+EVAL_CAMERAS = {
+    "dresser": ([0.08307640315968651, 1.986952324350807, 0.9996085854670145],
+                [-0.10162310189063647, -0.06726290364234049, 0.5478233048853433, 0.8276702686337273]),
+    "cubby": ([0.08307640315968651, 1.986952324350807, 0.9996085854670145],
+              [-0.10162310189063647, -0.06726290364234049, 0.5478233048853433, 0.8276702686337273]),
+    "tabletop": ([1.5031788593125708, -1.817341016921562, 1.278088299149147],
+                 [0.8687241016192855, 0.4180885960330695, 0.11516106409944685, 0.23928704613569252]),
+}
+
+
+def render_depth_cloud(scene, camera, width, height, fov_y_deg=60.0, near=0.01, far=10.0, quirk=True):
+    """camera np[3,4] or [B,3,4] camera->world (GL frame: y up, looks along -z) -> (points [B, W*H, 3] hits first in pixel order, counts i32 [B])"""
+    keep, B, M1, M2, ps = _scene_args(scene)
+    cam, pc = _f(np.asarray(camera).reshape(-1, 12))
+    per = int(cam.shape[0] > 1)
+    ty = np.tan(np.radians(fov_y_deg) / 2.0)
+    pts = np.zeros((B, width * height, 3), np.float32); cnt = np.zeros(B, np.int32)
+    lib().mpn_oracle_render_depth_cloud(C.c_int(B), C.c_int(M1), C.c_int(M2), *ps, C.c_int(int(quirk)), pc, C.c_int(per),
+                                        C.c_int(width), C.c_int(height), C.c_float(ty * width / height), C.c_float(ty),
+                                        C.c_float(near), C.c_float(far), pts.ctypes.data_as(C.POINTER(C.c_float)),
+                                        cnt.ctypes.data_as(C.POINTER(C.c_int32)))
+    return pts, cnt

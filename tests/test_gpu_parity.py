@@ -588,3 +588,33 @@ def test_build_cloud_from_obstacle_points_bit_exact(engine, oracle, tables):
                                          torch.from_numpy(pts).cuda(), torch.from_numpy(counts).cuda(), problem0=11).cpu().numpy()
     exp = oracle.build_cloud_from_points(p["q0"], p["target"], pts, counts, tables, engine.cfg.seed, problem0=11)
     assert np.array_equal(got, exp)
+
+
+def test_depth_render_bit_exact_and_feeds_cloud_build(engine, oracle, tables):
+    """mpn_render_depth_cloud (run_inference.convert_primitive_problems_to_depth stand-in) vs the oracle ray caster: counts
+    and hit coordinates bit-exact, shared and per-problem cameras; the result feeds make_point_cloud_from_problem"""
+    from mpinets_b200.run_inference import eval_camera
+    B, W, H = 6, 96, 72
+    for config, env in ((2, "tabletop"), (3, "dresser")):
+        p = _problems(config, B)
+        cam = eval_camera(env)
+        pts, cnt = engine.render_depth_cloud(to_dev(p), torch.from_numpy(cam).cuda(), W, H)
+        opts, ocnt = oracle.render_depth_cloud(p, cam, W, H)
+        assert np.array_equal(cnt.cpu().numpy(), ocnt)
+        got = pts.cpu().numpy()
+        for b in range(B):
+            assert np.array_equal(got[b, :ocnt[b]], opts[b, :ocnt[b]])
+    cams = np.stack([cam] * B)
+    cams[:, :, 3] += np.linspace(0, 0.2, B, dtype=np.float32)[:, None]
+    pts2, cnt2 = engine.render_depth_cloud(to_dev(p), torch.from_numpy(cams).cuda(), W, H)
+    opts2, ocnt2 = oracle.render_depth_cloud(p, cams, W, H)
+    assert np.array_equal(cnt2.cpu().numpy(), ocnt2)
+    assert np.array_equal(pts2.cpu().numpy()[1, :ocnt2[1]], opts2[1, :ocnt2[1]])
+    # depth clouds with >= 4096 points feed the cloud builder (run_inference.py:58-90)
+    big, bcnt = engine.render_depth_cloud(to_dev(p), torch.from_numpy(cam).cuda(), 320, 240)
+    assert int(bcnt.min()) >= 4096
+    q0, tg = torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(np.ascontiguousarray(p["target"])).cuda()
+    cloud = engine.build_cloud_from_points(q0, tg, big, bcnt)
+    obig, obcnt = oracle.render_depth_cloud(p, cam, 320, 240)
+    ocloud = oracle.build_cloud_from_points(p["q0"], p["target"], obig, obcnt, tables, engine.cfg.seed)
+    assert np.array_equal(cloud.cpu().numpy(), ocloud)

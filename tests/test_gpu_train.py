@@ -186,3 +186,25 @@ def test_training_loop_reduces_loss_and_weights_round_trip(oracle, tables, state
     assert np.abs(dq - odq).max() < 1e-5
     assert np.abs(odq - oracle.policy_forward(state_dict, cloud, qn).numpy()).max() > 1e-4   # the weights did change
     get_engine(batch["xyz"].device).load_state_dict(state_dict)
+
+
+def test_validation_step_matches_oracle(oracle, tables, state_dict):
+    """validation_step (model.py:252-318): rollout -> final end-effector error + sphere-sweep collision rate, against the
+    oracle's rollout + FK + sweep (3 steps instead of 69 to keep the CPU side short; same code path)"""
+    from mpinets_b200 import model as M
+    B, T = 6, 3
+    p, cloud, qn, _ = _batch(oracle, tables, B, seed=5)
+    net = M.TrainingMotionPolicyNetwork()
+    net.load_state_dict({k: v.clone() for k, v in state_dict.items()})
+    tp = p["target"].reshape(B, 3, 4)[:, :, 3].copy()
+    batch = dict(to_dev(p), xyz=torch.from_numpy(cloud.copy()).cuda(), configuration=torch.from_numpy(qn).cuda(),
+                 target_position=torch.from_numpy(np.ascontiguousarray(tp)).cuda())
+    out = net.validation_step(batch, 0, rollout_length=T)
+    oc = cloud.copy()
+    otraj = oracle.rollout(state_dict, oc, qn, tables, T, 0x4D50694E)
+    flags = oracle.sweep_flags(p, otraj, tables)[0]
+    _, eef = oracle.fk(otraj[:, -1])
+    err = np.linalg.norm(eef[:, :, 3] - tp, axis=1)
+    assert abs(float(out["avg_collision_rate"]) - flags.mean()) < 1e-6
+    assert abs(float(out["avg_target_error"]) - err.mean()) < 1e-4
+    assert np.abs(net.last_rollout.cpu().numpy() - otraj).max() < 1e-4

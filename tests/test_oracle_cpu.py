@@ -534,3 +534,45 @@ def test_oracle_cloud_from_obstacle_points(oracle, tables):
         pool = {tuple(r) for r in pts[b, : counts[b]]}
         assert len(rows) == 4096 and rows <= pool            # without replacement, only from the valid prefix
     assert not np.array_equal(c[0, 2048:6144], oracle.build_cloud_from_points(p["q0"], p["target"], pts, counts, tables, seed, problem0=6)[0, 2048:6144])
+
+
+# ----------------------------------------------------------------------------- depth-camera clouds (run_inference.py:194-257)
+def test_depth_render_known_answer_and_on_surface(oracle):
+    """unit cube 2 m in front of a camera at the origin: its front face is at depth 2; every hit lies on a primitive surface
+    (|sdf| ~ 0 with the SAME frames as the SDF), inside the frustum, and hits are in pixel order"""
+    shapes = dict(cuboid_centers=(1, 40, 3), cuboid_dims=(1, 40, 3), cuboid_quats=(1, 40, 4), cylinder_centers=(1, 40, 3),
+                  cylinder_radii=(1, 40), cylinder_heights=(1, 40), cylinder_quats=(1, 40, 4))
+    p = {k: np.zeros(s, np.float32) for k, s in shapes.items()}
+    p["cuboid_quats"][..., 0] = 1; p["cylinder_quats"][..., 0] = 1
+    p["cuboid_centers"][0, 0] = [0, 0, 2.5]; p["cuboid_dims"][0, 0] = [1, 1, 1]
+    p["cylinder_centers"][0, 0] = [2, 0, 3]; p["cylinder_radii"][0, 0] = 0.5; p["cylinder_heights"][0, 0] = 1.0
+    cam = np.diag([1.0, -1.0, -1.0, 1.0]).astype(np.float32)[:3]   # GL camera (y up, looks along -z) turned to look along +z
+    W, H = 64, 48
+    pts, cnt = oracle.render_depth_cloud(p, cam, W, H, 60.0)
+    q = pts[0, :cnt[0]]
+    assert 0 < cnt[0] < W * H
+    assert abs(q[:, 2].min() - 2.0) < 1e-6                       # the cube's front face
+    centre = q[(np.abs(q[:, 0]) < 0.4) & (np.abs(q[:, 1]) < 0.4)]
+    assert len(centre) and np.abs(centre[:, 2] - 2.0).max() < 1e-6
+    assert np.abs(oracle.sdf_points(p, q[None])).max() < 1e-5
+    ty = np.tan(np.radians(30.0))
+    assert (np.abs(q[:, 1] / q[:, 2]) <= ty + 1e-6).all() and (np.abs(q[:, 0] / q[:, 2]) <= ty * W / H + 1e-6).all()
+    # pixel order: un-project to pixel indices, they must increase
+    col = np.floor((q[:, 0] / q[:, 2] / (ty * W / H) + 1) * W / 2).astype(int)
+    row = np.floor((q[:, 1] / q[:, 2] / ty + 1) * H / 2).astype(int)
+    assert (np.diff(row * W + col) > 0).all()
+    # nothing behind the far plane; an empty scene gives no points
+    _, c2 = oracle.render_depth_cloud(p, cam, W, H, 60.0, far=1.5)
+    assert c2[0] == 0
+
+
+def test_depth_render_eval_cameras_see_the_scenes(oracle):
+    """the reference's evaluation cameras (run_inference.py:215-243), GL convention, see the synthetic scenes of their type"""
+    from mpinets_b200 import scenes
+    from mpinets_b200.run_inference import eval_camera
+    for config, env in ((2, "tabletop"), (3, "cubby")):
+        p = scenes.config_problems(config, 3)
+        pts, cnt = oracle.render_depth_cloud(p, eval_camera(env), 80, 60)
+        assert (cnt > 200).all(), (env, cnt)
+        for b in range(3):
+            assert np.abs(oracle.sdf_points({k: v[b:b + 1] for k, v in p.items() if k in scenes.SCENE_KEYS}, pts[b:b + 1, :cnt[b]])).max() < 1e-4
