@@ -110,7 +110,7 @@ static int wgrad(mpn_ctx* c, cudaStream_t s, const float* dY, int ldy, const flo
   if (M <= 0) return MPN_OK;
   TrainWs& t = c->tw;
   const int tiles = ((N + WT - 1) / WT) * ((K + WT - 1) / WT);
-  long long splits = (2LL * c->sm_count + tiles - 1) / tiles;
+  long long splits = (8LL * c->sm_count + tiles - 1) / tiles;   // 40 registers, 17 KB smem: 8 CTAs / SM keep the FMA pipe fed
   splits = std::min(splits, (M + 255) / 256);
   const long long per = (long long)N * K + N;
   splits = std::max(1LL, std::min(splits, (long long)(t.partial_floats / per)));
