@@ -228,6 +228,15 @@ int mpn_weights_sync(mpn_ctx* ctx);
 int mpn_train_step_grads(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, int N, const float* cloud,
                          const float* q_norm, const float* supervision, int n_loss_points, float margin, float w_collision,
                          float w_bc, float* losses, float* y_hat, float* grads);
+/* Tensor-core building blocks of the training backward (train_tc.cu), exposed for their own parity tests.
+ * mpn_train_tc_gemm: C[M][N] bf16 = epi(A[M][128] bf16 * W[N][128]^T bf16 + bias), M % 128 == 0, N in {64, 128, 256};
+ *   epi 0 ReLU, 1 none, 2 no bias, multiplied by relu'(mask[M][N] bf16) (C may alias mask).
+ * mpn_train_tc_wgrad: partial[n_ctas][128][128] fp32 = per-CTA sums over row ranges of dY[r][:]^T X[r][:] (dY, X [R][128]
+ *   bf16 row-major, handed to tcgen05 as MN-major operands); the sum over the n_ctas tiles is dY^T X.  variant 0. */
+int mpn_train_tc_gemm(mpn_ctx* ctx, void* stream, int epi, const void* A, const void* W, const float* bias, const void* mask,
+                      int64_t M, int N, void* C);
+int mpn_train_tc_wgrad(mpn_ctx* ctx, void* stream, const void* dY, const void* X, int64_t R, float* partial,
+                       int64_t partial_floats, int* n_ctas, int variant);
 /* the max-pool routing of the last training step: for module 0 / 1 / 2 the neighbour row (0..127, in ball-query order;
  * group-all: the SA2 centroid) that won each output channel, u8 [B][512][64] / [B][128][256] / [B][1024] (device).  The
  * backward pass sends each channel's gradient to exactly this row (max_pool2d backward); parity tests replay it. */

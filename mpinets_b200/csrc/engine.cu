@@ -675,6 +675,23 @@ int mpn_train_step_grads(mpn_ctx* c, void* stream, const mpn_scene* scene, int B
                           losses, y_hat, grads);
 }
 
+// tensor-core building blocks of the training backward, exposed for their own parity tests
+int mpn_train_tc_gemm(mpn_ctx* c, void* stream, int epi, const void* A, const void* W, const float* bias, const void* mask, int64_t M,
+                      int N, void* C) {
+  REQ_CTX(c);
+  MPN_REQUIRE(A && W && C && epi >= 0 && epi <= 2, "mpn_train_tc_gemm: bad arguments");
+  return launch_rows_gemm_tc(c, (cudaStream_t)stream, epi, (const __nv_bfloat16*)A, (const __nv_bfloat16*)W, bias,
+                             (const __nv_bfloat16*)mask, M, N, (__nv_bfloat16*)C);
+}
+
+int mpn_train_tc_wgrad(mpn_ctx* c, void* stream, const void* dY, const void* X, int64_t R, float* partial, int64_t partial_floats,
+                       int* n_ctas, int variant) {
+  REQ_CTX(c);
+  MPN_REQUIRE(dY && X && partial && n_ctas && R >= 1 && partial_floats >= 128 * 128, "mpn_train_tc_wgrad: bad arguments");
+  return launch_wgrad_tc(c, (cudaStream_t)stream, (const __nv_bfloat16*)dY, (const __nv_bfloat16*)X, R, partial, (size_t)partial_floats,
+                         n_ctas, variant);
+}
+
 int mpn_train_pooled_rows(mpn_ctx* c, void* stream, int module, int B, uint8_t* dst) {
   REQ_CTX(c);
   MPN_REQUIRE(module >= 0 && module <= 2 && dst, "mpn_train_pooled_rows: bad arguments");

@@ -482,6 +482,23 @@ class Engine:
                                                  _p(grads) if need_grad else None))
         return losses, y_hat, (grads if need_grad else None)
 
+    def train_tc_gemm(self, A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, epi: int = 0,
+                      mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """C [M,N] bf16 = epi(A [M,128] @ W [N,128]^T + bias) on tcgen05 (train_tc.cu); epi 0 relu, 1 none, 2 relu'(mask)"""
+        _check(A, "A", torch.bfloat16, self.device); _check(W, "W", torch.bfloat16, self.device)
+        M, N = A.shape[0], W.shape[0]
+        out = self._empty(M, N, dtype=torch.bfloat16)
+        _lib.check(self.lib.mpn_train_tc_gemm(self._ctx, self.stream, epi, _p(A), _p(W), _p(bias), _p(mask), M, N, _p(out)))
+        return out
+
+    def train_tc_wgrad(self, dY: torch.Tensor, X: torch.Tensor, variant: int = 0) -> torch.Tensor:
+        """dY^T X for [R,128] bf16 operands on tcgen05 (MN-major operands) -> [128,128] fp32"""
+        _check(dY, "dY", torch.bfloat16, self.device); _check(X, "X", torch.bfloat16, self.device)
+        part = self._empty(512, 128, 128)
+        n = C.c_int(0)
+        _lib.check(self.lib.mpn_train_tc_wgrad(self._ctx, self.stream, _p(dY), _p(X), dY.shape[0], _p(part), part.numel(), C.byref(n), variant))
+        return part[: n.value].sum(dim=0)
+
     def train_pooled_rows(self, B: int):
         """max-pool routing of the last training step: (u8 [B,512,64], u8 [B,128,256], u8 [B,1024])"""
         outs = []
