@@ -220,14 +220,17 @@ int mpn_set_params(mpn_ctx* ctx, void* stream, const float* src /* device [param
 /* rebuilds the packed bf16 tensor-core copies from the fp32 parameters (after optimisation, before MPN_PREC_BF16 inference);
  * synchronises the device */
 int mpn_weights_sync(mpn_ctx* ctx);
-/* forward (fp32, state saved for the backward pass) -> y_hat = clamp(q_norm + net(cloud, q_norm), -1, 1) (model.py:202) ->
+/* forward (fp32 kernels, state saved for the backward pass) -> y_hat = clamp(q_norm + net(cloud, q_norm), -1, 1) (model.py:202) ->
  * losses[0] = collision loss, losses[1] = point-match loss of CollisionAndBCLossContainer (loss.py:111-166) against
  * `supervision` [B][7] -> grads [param_count] = d(w_collision * losses[0] + w_bc * losses[1]) / d parameters (overwritten;
  * NULL: forward + losses only).  cloud [B][N][4], q_norm [B][7] in [-1, 1]; y_hat [B][7] optional output.
- * The reference's values: n_loss_points 1024, margin 0.03 (loss.py:92,109), w_collision 5, w_bc 1 (jobconfig.yaml:24-25). */
+ * The reference's values: n_loss_points 1024, margin 0.03 (loss.py:92,109), w_collision 5, w_bc 1 (jobconfig.yaml:24-25).
+ * precision: MPN_PREC_FP32 = every GEMM of the backward in fp32 (the parity mode); MPN_PREC_BF16 = the compacted-row GEMMs
+ * of the SA1 / SA2 backward on tcgen05 with bf16 operands and fp32 accumulation (the counterpart of the reference's
+ * precision=16 autocast, run_training.py:109); parameter gradients are fp32 in both. */
 int mpn_train_step_grads(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, int N, const float* cloud,
                          const float* q_norm, const float* supervision, int n_loss_points, float margin, float w_collision,
-                         float w_bc, float* losses, float* y_hat, float* grads);
+                         float w_bc, float* losses, float* y_hat, float* grads, int precision);
 /* Tensor-core building blocks of the training backward (train_tc.cu), exposed for their own parity tests.
  * mpn_train_tc_gemm: C[M][N] bf16 = epi(A[M][128] bf16 * W[N][128]^T bf16 + bias), M % 128 == 0, N in {64, 128, 256};
  *   epi 0 ReLU, 1 none, 2 no bias, multiplied by relu'(mask[M][N] bf16) (C may alias mask).

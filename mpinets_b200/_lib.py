@@ -97,7 +97,7 @@ def load():
         "mpn_get_params": [P, P, P],
         "mpn_set_params": [P, P, P],
         "mpn_weights_sync": [P],
-        "mpn_train_step_grads": [P, P, SC, I, I, P, P, P, I, F, F, F, P, P, P],
+        "mpn_train_step_grads": [P, P, SC, I, I, P, P, P, I, F, F, F, P, P, P, I],
         "mpn_adam_step": [P, P, P, F, F, F, F, F, I, P],
         "mpn_train_pooled_rows": [P, P, I, I, P],
         "mpn_train_tc_gemm": [P, P, I, P, P, P, P, C.c_int64, I, P],

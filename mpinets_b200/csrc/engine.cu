@@ -663,16 +663,17 @@ int mpn_weights_sync(mpn_ctx* c) {
 
 int mpn_train_step_grads(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, int N, const float* cloud, const float* q_norm,
                          const float* supervision, int n_loss_points, float margin, float w_collision, float w_bc, float* losses,
-                         float* y_hat, float* grads) {
+                         float* y_hat, float* grads, int precision) {
   REQ_CTX(c); REQ_TABLES(c); REQ_WEIGHTS(c);
   int r;
   if ((r = check_scene(c, scene))) return r;
   MPN_REQUIRE(cloud && q_norm && supervision && losses && B >= 1, "mpn_train_step_grads: bad arguments");
   MPN_REQUIRE(N >= SA1_NPOINT && N <= 8192, "mpn_train_step_grads: N=%d unsupported (512..8192)", N);
   MPN_REQUIRE(n_loss_points >= 1, "mpn_train_step_grads: n_loss_points must be positive");
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16, "mpn_train_step_grads: bad precision");
   if ((r = ensure_workspace(c, B))) return r;
   return train_step_grads(c, (cudaStream_t)stream, *scene, B, N, cloud, q_norm, supervision, n_loss_points, margin, w_collision, w_bc,
-                          losses, y_hat, grads);
+                          losses, y_hat, grads, precision);
 }
 
 // tensor-core building blocks of the training backward, exposed for their own parity tests

@@ -99,6 +99,7 @@ struct TrainWs {
   float *X = nullptr, *H1 = nullptr, *H2 = nullptr;
   int32_t* src = nullptr; uint8_t* slot = nullptr;
   float* partial = nullptr; size_t partial_floats = 0;   // split-reduction partials of the weight-gradient kernels
+  __nv_bfloat16* tcw = nullptr; float* b2dup = nullptr;  // bf16 weight tiles of the tensor-core backward (rebuilt per step)
   float* adam_m = nullptr; float* adam_v = nullptr; float* norm = nullptr;
 };
 
@@ -205,7 +206,7 @@ int launch_finalize_metrics(mpn_ctx* c, cudaStream_t s, int B, const float* eef,
 // ---- train.cu : training step (model.py:185-240) in fp32 -- forward with saved state, losses, backward, Adam
 int train_step_grads(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int N, const float* cloud, const float* q_norm,
                      const float* supervision, int n_loss_points, float margin, float w_collision, float w_bc, float* losses,
-                     float* y_hat, float* grads);
+                     float* y_hat, float* grads, int precision = MPN_PREC_FP32);
 int adam_step(mpn_ctx* c, cudaStream_t s, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm,
               int step, float* grad_norm_out);
 int refresh_transposes(mpn_ctx* c, cudaStream_t s);

@@ -284,12 +284,17 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const int32_t* __restric
 
 // Layer 3 of a grouped level, persistent CTAs (W3 resident in shared memory, dW3 / db3 accumulators in registers):
 //   H2 (in: relu activations of the group's slots, out: dZ2);  pW[cta][C3][C2], pb[cta][C3] partial sums.
-template <int C2, int C3, int SLOTS>
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int C2, int C3, int SLOTS, typename T>
 __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict__ geff, const uint8_t* __restrict__ slot_of_ch,
-                                                        const float* __restrict__ W3, float* __restrict__ H2, int G,
+                                                        const float* __restrict__ W3, T* __restrict__ H2, int G,
                                                         float* __restrict__ pW, float* __restrict__ pb) {
-  constexpr int T = 512, Q = T / C2, CPT = C3 / Q, PER = SLOTS / 32;
-  static_assert(T % C2 == 0 && C3 % Q == 0 && SLOTS % 32 == 0 && SLOTS <= 128 && C3 <= T, "layout");
+  constexpr int NT = 512, Q = NT / C2, CPT = C3 / Q, PER = SLOTS / 32;
+  static_assert(NT % C2 == 0 && C3 % Q == 0 && SLOTS % 32 == 0 && SLOTS <= 128 && C3 <= NT, "layout");
   extern __shared__ __align__(16) float sm[];
   float* W3s = sm;                                  // [C3][C2]
   float* Hs = W3s + C3 * C2;                        // [SLOTS][C2]
@@ -303,15 +308,15 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < CPT; ++i) accW[i] = 0.f;
   float accb = 0.f;
-  for (int i = tid; i < C3 * C2; i += T) W3s[i] = W3[i];
+  for (int i = tid; i < C3 * C2; i += NT) W3s[i] = W3[i];
   for (int grp = blockIdx.x; grp < G; grp += gridDim.x) {
     __syncthreads();
-    for (int c = tid; c < C3; c += T) {
+    for (int c = tid; c < C3; c += NT) {
       gs[c] = geff[(size_t)grp * C3 + c];
       sl[c] = slot_of_ch[(size_t)grp * C3 + c];
     }
-    float* Hg = H2 + (size_t)grp * SLOTS * C2;
-    for (int i = tid; i < SLOTS * C2; i += T) Hs[i] = Hg[i];
+    T* Hg = H2 + (size_t)grp * SLOTS * C2;
+    for (int i = tid; i < SLOTS * C2; i += NT) Hs[i] = ldf(Hg + i);
     __syncthreads();
     // channel lists per slot, in channel order (deterministic)
     if (tid < SLOTS) {
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
         const int c = chl[e];
         a = fmaf(gs[c], W3s[c * C2 + j], a);
       }
-      Hg[(size_t)s * C2 + j] = Hs[s * C2 + j] > 0.f ? a : 0.f;
+      stf(Hg + (size_t)s * C2 + j, Hs[s * C2 + j] > 0.f ? a : 0.f);
     }
     // dW3[c] += g_c H2[slot_c]
 #pragma unroll
@@ -456,7 +461,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Y
 }
 
 // previous level's feature gradient: dfeat[b][src][f] += dX[row][f]   (pointnet2's group_points_grad)
-__global__ void __launch_bounds__(256) sa_scatter_add_kernel(const float* __restrict__ dX, const int32_t* __restrict__ src, long long R,
+template <typename T>
+__global__ void __launch_bounds__(256) sa_scatter_add_kernel(const T* __restrict__ dX, const int32_t* __restrict__ src, long long R,
                                                              int slots, int npoint, int N, int CF, float* __restrict__ dfeat) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * CF) return;
@@ -465,7 +471,166 @@ __global__ void __launch_bounds__(256) sa_scatter_add_kernel(const float* __rest
   const int si = src[row];
   if (si < 0) return;
   const long long b = (row / slots) / npoint;
-  atomicAdd(dfeat + ((size_t)b * N + si) * CF + f, dX[i]);
+  atomicAdd(dfeat + ((size_t)b * N + si) * CF + f, ldf(dX + i));
+}
+
+
+// ---------------------------------------------------------------------------------------------- bf16 / tensor-core variant
+// (MPN_PREC_BF16 training: the compacted-row GEMMs of SA1 / SA2 run on tcgen05, train_tc.cu; accumulators, the sparse layer 3,
+//  the pooled-feature gradients and every parameter gradient stay fp32)
+
+// SA2 operand rows, bf16 [R][128] = [dx dy dz | 64 features | 0 x 60 | 1]: the ones column makes column 127 of dZ1^T X the
+// bias gradient of layer 1
+__global__ void __launch_bounds__(256) sa2_gather_bf16_kernel(const int32_t* __restrict__ src, long long R, int slots, int npoint,
+                                                              const float* __restrict__ xyz, int N, const float* __restrict__ feats,
+                                                              const float* __restrict__ new_xyz, __nv_bfloat16* __restrict__ X) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * 16) return;
+  const long long row = i >> 4;
+  const int ch = (int)(i & 15);
+  const long long grp = row / slots, b = grp / npoint;
+  const int si = src[row];
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (si >= 0) {
+    const float* p = xyz + ((size_t)b * N + si) * 3;
+    const float* f = feats + ((size_t)b * N + si) * 64;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ch * 8 + j;
+      if (k < 3) v[j] = p[k] - new_xyz[(size_t)grp * 3 + k];
+      else if (k < 67) v[j] = f[k - 3];
+      else if (k == 127) v[j] = 1.0f;
+    }
+  }
+  __nv_bfloat162 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(X + (size_t)row * 128 + ch * 8) = *reinterpret_cast<uint4*>(o);
+}
+
+// SA1: operand rows X4 fp32 [R][4] = [dx dy dz mask] and layer 1 (4 -> 64, K too small for a tensor-core tile) computed on
+// the spot: H1 bf16 [R][64] = relu(W1 x + b1); empty slots give zero rows
+__global__ void __launch_bounds__(256) sa1_gather_h1_kernel(const int32_t* __restrict__ src, long long R, int npoint,
+                                                            const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz,
+                                                            const float* __restrict__ W1, const float* __restrict__ b1,
+                                                            float* __restrict__ X4, __nv_bfloat16* __restrict__ H1) {
+  __shared__ float w[256], bs[64];
+  if (threadIdx.x < 256) w[threadIdx.x] = W1[threadIdx.x];
+  if (threadIdx.x < 64) bs[threadIdx.x] = b1[threadIdx.x];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * 8) return;
+  const long long row = i >> 3;
+  const int ch = (int)(i & 7);
+  const long long grp = row / 64, b = grp / npoint;
+  const int si = src[row];
+  float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+  if (si >= 0) {
+    const float4 p = *reinterpret_cast<const float4*>(cloud + ((size_t)b * N + si) * 4);
+    x0 = p.x - new_xyz[(size_t)grp * 3]; x1 = p.y - new_xyz[(size_t)grp * 3 + 1]; x2 = p.z - new_xyz[(size_t)grp * 3 + 2]; x3 = p.w;
+  }
+  if (ch == 0) *reinterpret_cast<float4*>(X4 + (size_t)row * 4) = make_float4(x0, x1, x2, x3);
+  float h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = ch * 8 + j;
+    const float z = fmaf(w[c * 4 + 3], x3, fmaf(w[c * 4 + 2], x2, fmaf(w[c * 4 + 1], x1, fmaf(w[c * 4], x0, bs[c]))));
+    h[j] = si >= 0 ? fmaxf(z, 0.f) : 0.f;
+  }
+  __nv_bfloat162 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(h[2 * j], h[2 * j + 1]);
+  *reinterpret_cast<uint4*>(H1 + (size_t)row * 64 + ch * 8) = *reinterpret_cast<uint4*>(o);
+}
+
+// column sums of Y bf16 [R][128] over a CTA's row range -> partial[cta][128]
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ Y, long long R, long long rows_per_cta,
+                                                          float* __restrict__ partial) {
+  __shared__ float red[4][128];
+  const int cp = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
+  float s0 = 0.f, s1 = 0.f;
+  for (long long r = r0 + rl; r < r1; r += 4) {
+    const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(Y + (size_t)r * 128)[cp];
+    s0 += __low2float(v); s1 += __high2float(v);
+  }
+  red[rl][2 * cp] = s0; red[rl][2 * cp + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 128)
+    partial[(size_t)blockIdx.x * 128 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
+// gW[o][k] += sum_s P[s][o][k] (+ P[s][o + 64][k + 64] for SA1's paired rows); optional bias from column `bias_col`
+__global__ void wgrad_extract_kernel(const float* __restrict__ P, int n, int out, int in, int paired, float* __restrict__ gW, int bias_col,
+                                     float* __restrict__ gb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < out * in) {
+    const int o = i / in, k = i - o * in;
+    float s = 0.f;
+    for (int sp = 0; sp < n; ++sp) {
+      s += P[((size_t)sp * 128 + o) * 128 + k];
+      if (paired) s += P[((size_t)sp * 128 + o + 64) * 128 + k + 64];
+    }
+    gW[i] += s;
+  } else if (bias_col >= 0 && i < out * in + out) {
+    const int o = i - out * in;
+    float s = 0.f;
+    for (int sp = 0; sp < n; ++sp) s += P[((size_t)sp * 128 + o) * 128 + bias_col];
+    gb[o] += s;
+  }
+}
+__global__ void bias_extract_kernel(const float* __restrict__ P, int n, int out, int paired, float* __restrict__ gb) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out) return;
+  float s = 0.f;
+  for (int sp = 0; sp < n; ++sp) {
+    s += P[(size_t)sp * 128 + o];
+    if (paired) s += P[(size_t)sp * 128 + o + 64];
+  }
+  gb[o] += s;
+}
+
+// SA1 layer 1 (64 x 4): partial[cta][64][5] = sums over the CTA's rows of dZ1[r][c] * [x0 x1 x2 x3 1]
+__global__ void __launch_bounds__(256) sa1_wgrad1_kernel(const __nv_bfloat16* __restrict__ dZ1, const float* __restrict__ X4, long long R,
+                                                         long long rows_per_cta, float* __restrict__ partial) {
+  __shared__ float red[4][64][5];
+  const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+  for (long long r = r0 + rl; r < r1; r += 4) {
+    const float d = __bfloat162float(dZ1[(size_t)r * 64 + c]);
+    const float4 x = *reinterpret_cast<const float4*>(X4 + (size_t)r * 4);
+    a0 = fmaf(d, x.x, a0); a1 = fmaf(d, x.y, a1); a2 = fmaf(d, x.z, a2); a3 = fmaf(d, x.w, a3); a4 += d;
+  }
+  red[rl][c][0] = a0; red[rl][c][1] = a1; red[rl][c][2] = a2; red[rl][c][3] = a3; red[rl][c][4] = a4;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 320; i += 256) {
+    const int cc = i / 5, k = i - cc * 5;
+    partial[(size_t)blockIdx.x * 320 + i] = red[0][cc][k] + red[1][cc][k] + red[2][cc][k] + red[3][cc][k];
+  }
+}
+__global__ void sa1_w1_extract_kernel(const float* __restrict__ P, int n, float* __restrict__ gW, float* __restrict__ gb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 320) return;
+  float s = 0.f;
+  for (int sp = 0; sp < n; ++sp) s += P[(size_t)sp * 320 + i];
+  const int c = i / 5, k = i - c * 5;
+  if (k < 4) gW[c * 4 + k] += s; else gb[c] += s;
+}
+
+// dst bf16 [dst_rows][128]: mode 0 zero-padded copy of src[rows][cols] (row pitch ld); mode 1 block-diagonal diag(src, src)
+// of a 64 x 64 matrix (SA1's rows are processed in pairs)
+__global__ void pack_train_weight_kernel(const float* __restrict__ src, int rows, int cols, int ld, int mode, int dst_rows,
+                                         __nv_bfloat16* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dst_rows * 128) return;
+  const int r = i >> 7, c = i & 127;
+  float v = 0.f;
+  if (mode == 0) { if (r < rows && c < cols) v = src[(size_t)r * ld + c]; }
+  else if ((r >> 6) == (c >> 6)) v = src[(size_t)(r & 63) * ld + (c & 63)];
+  dst[i] = __float2bfloat16_rn(v);
 }
 
 // ---------------------------------------------------------------------------------------------- small elementwise kernels
@@ -561,6 +726,7 @@ void free_train_ws(mpn_ctx* c) {
                    (void**)&t.f[1], (void**)&t.f[2], (void**)&t.f[3], (void**)&t.d[0], (void**)&t.d[1], (void**)&t.d[2],
                    (void**)&t.yhat, (void**)&t.gy, (void**)&t.ga, (void**)&t.gb, (void**)&t.gcat, (void**)&t.gfeat3, (void**)&t.gfeat2,
                    (void**)&t.gfeat1, (void**)&t.X, (void**)&t.H1, (void**)&t.H2, (void**)&t.src, (void**)&t.slot, (void**)&t.partial,
+                   (void**)&t.tcw, (void**)&t.b2dup,
                    (void**)&t.adam_m, (void**)&t.adam_v, (void**)&t.norm};
   for (auto p : ptrs)
     if (*p) { cudaFree(*p); *p = nullptr; }
@@ -606,6 +772,8 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
   r |= talloc(&t.H2, k * SA2_NPOINT * 128 * 128);
   r |= talloc(&t.src, k * SA1_NPOINT * 64);
   r |= talloc(&t.slot, k * SA1_NPOINT * 64);
+  r |= talloc(&t.tcw, (size_t)8 * 128 * 128);
+  r |= talloc(&t.b2dup, (size_t)128);
   t.partial_floats = (size_t)20 << 20;   // >= the largest single weight tensor (fc_layer.3: 8.4 M) + bias
   r |= talloc(&t.partial, t.partial_floats);
   if (r) { free_train_ws(c); return MPN_ERR_NOMEM; }
@@ -654,11 +822,11 @@ static int dense_backward(mpn_ctx* c, cudaStream_t s, const Linear& L, float* gr
   return launch_linear_ex(c, s, gY, ldgy, L.wt, L.out, nullptr, M, L.in, L.out, gX, ldgx, 0, mask_mode ? a_in : nullptr, lda, mask_mode);
 }
 
-template <int C2, int C3, int SLOTS>
-static int launch_sa_l3(mpn_ctx* c, cudaStream_t s, const float* geff, const uint8_t* slot, const Linear& L3, float* H2, int G,
+template <int C2, int C3, int SLOTS, typename T>
+static int launch_sa_l3(mpn_ctx* c, cudaStream_t s, const float* geff, const uint8_t* slot, const Linear& L3, T* H2, int G,
                         float* grads) {
   TrainWs& t = c->tw;
-  auto k = sa_l3_bwd_kernel<C2, C3, SLOTS>;
+  auto k = sa_l3_bwd_kernel<C2, C3, SLOTS, T>;
   const size_t smem = (size_t)(C3 * C2 + SLOTS * C2 + C3) * 4 + (size_t)(C3 + SLOTS + SLOTS + 1 + C3) * 4;
   MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = smem > 100 * 1024 ? 1 : 2;
@@ -717,9 +885,9 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
   if ((r = launch_linear_ex(c, s, t.H1, C1, L[1].w, C1, L[1].b, R, C2, C1, t.H2, C2, 2))) return r;
   // 3. layer 3 (sparse): H2 <- dZ2, gW3 / gb3
   if (m == 0) {
-    if ((r = launch_sa_l3<64, 64, 64>(c, s, g_c, t.slot, L[2], t.H2, G, grads))) return r;
+    if ((r = launch_sa_l3<64, 64, 64, float>(c, s, g_c, t.slot, L[2], t.H2, G, grads))) return r;
   } else if (m == 1) {
-    if ((r = launch_sa_l3<128, 256, 128>(c, s, g_c, t.slot, L[2], t.H2, G, grads))) return r;
+    if ((r = launch_sa_l3<128, 256, 128, float>(c, s, g_c, t.slot, L[2], t.H2, G, grads))) return r;
   } else {
     int splits = std::max(1, std::min(8, bc / 16));
     int per = (bc + splits - 1) / splits;
@@ -745,15 +913,126 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
     // empty slots do not occur here only if every row is active; rows are addressed through src, so scatter (no collisions)
     if ((r = launch_linear_ex(c, s, t.H1, C1, L[0].wt + (size_t)3 * C1, C1, nullptr, R, CFEAT[m], C1, t.H2, CFEAT[m], 0))) return r;
     const long long n = R * CFEAT[m];
-    sa_scatter_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t.H2, t.src, R, slots, npoint, SA2_NPOINT, CFEAT[m], dst);
+    sa_scatter_add_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t.H2, t.src, R, slots, npoint, SA2_NPOINT, CFEAT[m], dst);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
   } else if (m == 1) {
     float* dst = dfeat_prev + (size_t)b0 * SA1_NPOINT * 64;
     if ((r = launch_linear_ex(c, s, t.H1, C1, L[0].wt + (size_t)3 * C1, C1, nullptr, R, CFEAT[m], C1, t.H2, CFEAT[m], 0))) return r;
     const long long n = R * CFEAT[m];
-    sa_scatter_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t.H2, t.src, R, slots, npoint, SA1_NPOINT, CFEAT[m], dst);
+    sa_scatter_add_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t.H2, t.src, R, slots, npoint, SA1_NPOINT, CFEAT[m], dst);
     c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  }
+  return MPN_OK;
+}
+
+
+// ---- tensor-core variant of sa_backward_chunk for SA1 (m = 0) and SA2 (m = 1)
+static int pack_w(mpn_ctx* c, cudaStream_t s, const float* src, int rows, int cols, int ld, int mode, int dst_rows, __nv_bfloat16* dst) {
+  pack_train_weight_kernel<<<(dst_rows * 128 + 255) / 256, 256, 0, s>>>(src, rows, cols, ld, mode, dst_rows, dst);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// dY^T X on tcgen05 -> gW (and the bias gradient from `bias_col` of the product, when >= 0)
+static int wgrad_tc_into(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, const __nv_bfloat16* X, long long R, int out, int in,
+                         int paired, float* gW, int bias_col, float* gb) {
+  TrainWs& t = c->tw;
+  int n = 0, r;
+  if ((r = launch_wgrad_tc(c, s, dY, X, R, t.partial, t.partial_floats, &n))) return r;
+  const int total = out * in + (bias_col >= 0 ? out : 0);
+  wgrad_extract_kernel<<<(total + 255) / 256, 256, 0, s>>>(t.partial, n, out, in, paired, gW, bias_col, gb);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+static int colsum_bf16_into(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* Y, long long R, int out, int paired, float* gb) {
+  TrainWs& t = c->tw;
+  long long ctas = std::max(1LL, std::min<long long>(4LL * c->sm_count, (R + 255) / 256));
+  long long rpc = (R + ctas - 1) / ctas;
+  ctas = (R + rpc - 1) / rpc;
+  colsum_bf16_kernel<<<(unsigned)ctas, 256, 0, s>>>(Y, R, rpc, t.partial);
+  bias_extract_kernel<<<1, 128, 0, s>>>(t.partial, (int)ctas, out, paired, gb);
+  c->launches += 2;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+static int sa_backward_chunk_tc(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, int N_in, const float* xyz, int stride,
+                                const float* feats, int fstride, const float* new_xyz, const int32_t* ball, const uint8_t* arg,
+                                float* g, const float* out, float* grads, float* dfeat_prev) {
+  TrainWs& t = c->tw;
+  const Linear* L = c->w.sa[m];
+  const int npoint = m == 0 ? SA1_NPOINT : SA2_NPOINT, slots = m == 0 ? 64 : 128, C3 = L[2].out;
+  const int G = bc * npoint;
+  const long long R = (long long)G * slots;
+  int r;
+  const float* xyz_c = xyz + (size_t)b0 * N_in * stride;
+  const float* feats_c = feats + (size_t)b0 * N_in * fstride;
+  const float* nx_c = new_xyz + (size_t)b0 * npoint * 3;
+  const int32_t* ball_c = ball + (size_t)b0 * npoint * NSAMPLE;
+  const uint8_t* arg_c = arg + (size_t)b0 * npoint * C3;
+  float* g_c = g + (size_t)b0 * npoint * C3;
+  const float* out_c = out + (size_t)b0 * npoint * C3;
+  __nv_bfloat16* Xb = reinterpret_cast<__nv_bfloat16*>(t.X);
+  __nv_bfloat16* H1b = reinterpret_cast<__nv_bfloat16*>(t.H1);
+  __nv_bfloat16* H2b = reinterpret_cast<__nv_bfloat16*>(t.H2);
+  __nv_bfloat16* Wa = t.tcw;                 // layer-2 weight            [128][128]
+  __nv_bfloat16* Wb = t.tcw + 128 * 128;     // layer-2 weight transposed [128][128]
+  __nv_bfloat16* Wc = t.tcw + 2 * 128 * 128; // SA2: layer-1 weight, K padded to 128
+  __nv_bfloat16* Wd = t.tcw + 3 * 128 * 128; // SA2: feature columns of layer 1, transposed [64][128]
+  {
+    const int grid = (G + 7) / 8;
+    if (m == 0) sa_prepare_kernel<64, 64><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
+    else sa_prepare_kernel<256, 128><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  }
+  if (m == 1) {
+    if ((r = pack_w(c, s, L[1].w, 128, 128, 128, 0, 128, Wa))) return r;
+    if ((r = pack_w(c, s, L[1].wt, 128, 128, 128, 0, 128, Wb))) return r;
+    if ((r = pack_w(c, s, L[0].w, 128, 67, 67, 0, 128, Wc))) return r;
+    if ((r = pack_w(c, s, L[0].wt + (size_t)3 * 128, 64, 128, 128, 0, 64, Wd))) return r;
+    sa2_gather_bf16_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, N_in, feats_c, nx_c, Xb);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    if ((r = launch_rows_gemm_tc(c, s, 0, Xb, Wc, L[0].b, nullptr, R, 128, H1b))) return r;
+    if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, L[1].b, nullptr, R, 128, H2b))) return r;
+    if ((r = launch_sa_l3<128, 256, 128, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads))) return r;
+    if ((r = wgrad_tc_into(c, s, H2b, H1b, R, 128, 128, 0, gw(c, grads, L[1]), -1, nullptr))) return r;
+    if ((r = colsum_bf16_into(c, s, H2b, R, 128, 0, gbias(c, grads, L[1])))) return r;
+    if ((r = launch_rows_gemm_tc(c, s, 2, H2b, Wb, nullptr, H1b, R, 128, H1b))) return r;              // dZ1 over H1
+    if ((r = wgrad_tc_into(c, s, H1b, Xb, R, 128, 67, 0, gw(c, grads, L[0]), 127, gbias(c, grads, L[0])))) return r;
+    if ((r = launch_rows_gemm_tc(c, s, 1, H1b, Wd, nullptr, nullptr, R, 64, H2b))) return r;            // dX features [R][64]
+    const long long n = R * 64;
+    sa_scatter_add_kernel<__nv_bfloat16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(H2b, t.src, R, slots, npoint, SA1_NPOINT, 64,
+                                                                                    dfeat_prev + (size_t)b0 * SA1_NPOINT * 64);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  } else {
+    if ((r = pack_w(c, s, L[1].w, 64, 64, 64, 1, 128, Wa))) return r;
+    if ((r = pack_w(c, s, L[1].wt, 64, 64, 64, 1, 128, Wb))) return r;
+    MPN_CHECK_CUDA(cudaMemcpyAsync(t.b2dup, L[1].b, 64 * 4, cudaMemcpyDeviceToDevice, s));
+    MPN_CHECK_CUDA(cudaMemcpyAsync(t.b2dup + 64, L[1].b, 64 * 4, cudaMemcpyDeviceToDevice, s));
+    float* X4 = t.X;
+    sa1_gather_h1_kernel<<<(unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(t.src, R, npoint, xyz_c, N_in, nx_c, L[0].w, L[0].b, X4, H1b);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    const long long R2 = R / 2;                                                                          // rows in pairs: [R/2][128]
+    if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, t.b2dup, nullptr, R2, 128, H2b))) return r;
+    if ((r = launch_sa_l3<64, 64, 64, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads))) return r;
+    if ((r = wgrad_tc_into(c, s, H2b, H1b, R2, 64, 64, 1, gw(c, grads, L[1]), -1, nullptr))) return r;
+    if ((r = colsum_bf16_into(c, s, H2b, R2, 64, 1, gbias(c, grads, L[1])))) return r;
+    if ((r = launch_rows_gemm_tc(c, s, 2, H2b, Wb, nullptr, H1b, R2, 128, H1b))) return r;             // dZ1 over H1
+    long long ctas = std::max(1LL, std::min<long long>(4LL * c->sm_count, (R + 1023) / 1024));
+    long long rpc = (R + ctas - 1) / ctas;
+    ctas = (R + rpc - 1) / rpc;
+    sa1_wgrad1_kernel<<<(unsigned)ctas, 256, 0, s>>>(H1b, X4, R, rpc, t.partial);
+    sa1_w1_extract_kernel<<<2, 256, 0, s>>>(t.partial, (int)ctas, gw(c, grads, L[0]), gbias(c, grads, L[0]));
+    c->launches += 2;
     MPN_CHECK_CUDA(cudaGetLastError());
   }
   return MPN_OK;
@@ -761,9 +1040,10 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
 
 int train_step_grads(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int N, const float* cloud, const float* q_norm,
                      const float* supervision, int n_loss_points, float margin, float w_collision, float w_bc, float* losses,
-                     float* y_hat, float* grads) {
+                     float* y_hat, float* grads, int precision) {
   int r;
   if ((r = ensure_train_ws(c, B, N))) return r;
+  const bool tcp = precision == MPN_PREC_BF16;
   Workspace& w = c->ws;
   TrainWs& t = c->tw;
   const Weights& W = c->w;
@@ -805,11 +1085,11 @@ int train_step_grads(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int
     if ((r = sa_backward_chunk(c, s, 2, b0, std::min(chunk, B - b0), SA2_NPOINT, w.xyz2, 3, w.feat2, 256, nullptr, nullptr, t.arg3,
                                t.gfeat3, w.feat3, grads, t.gfeat2))) return r;
   for (int b0 = 0; b0 < B; b0 += chunk)
-    if ((r = sa_backward_chunk(c, s, 1, b0, std::min(chunk, B - b0), SA1_NPOINT, w.xyz1, 3, w.feat1, 64, w.xyz2, t.ball2, t.arg2,
-                               t.gfeat2, w.feat2, grads, t.gfeat1))) return r;
+    if ((r = (tcp ? sa_backward_chunk_tc : sa_backward_chunk)(c, s, 1, b0, std::min(chunk, B - b0), SA1_NPOINT, w.xyz1, 3, w.feat1, 64,
+                                                              w.xyz2, t.ball2, t.arg2, t.gfeat2, w.feat2, grads, t.gfeat1))) return r;
   for (int b0 = 0; b0 < B; b0 += chunk)
-    if ((r = sa_backward_chunk(c, s, 0, b0, std::min(chunk, B - b0), N, cloud, 4, cloud + 3, 4, w.xyz1, t.ball1, t.arg1, t.gfeat1,
-                               w.feat1, grads, nullptr))) return r;
+    if ((r = (tcp ? sa_backward_chunk_tc : sa_backward_chunk)(c, s, 0, b0, std::min(chunk, B - b0), N, cloud, 4, cloud + 3, 4, w.xyz1,
+                                                              t.ball1, t.arg1, t.gfeat1, w.feat1, grads, nullptr))) return r;
   return MPN_OK;
 }
 

@@ -464,9 +464,10 @@ class Engine:
 
     def train_step_grads(self, scene, cloud: torch.Tensor, q_norm: torch.Tensor, supervision: torch.Tensor,
                          n_loss_points: int = 1024, margin: float = 0.03, w_collision: float = 5.0, w_bc: float = 1.0,
-                         grads: Optional[torch.Tensor] = None, need_grad: bool = True):
+                         grads: Optional[torch.Tensor] = None, need_grad: bool = True, precision: int = _lib.PREC_FP32):
         """training_step (model.py:185-240) up to the gradients: returns (losses [2] = (collision, point match),
-        y_hat [B,7], grads [param_count] or None).  fp32."""
+        y_hat [B,7], grads [param_count] or None).  precision: PREC_FP32 (parity mode) or PREC_BF16 (SA1 / SA2 backward GEMMs
+        on tcgen05, bf16 operands)."""
         _check(cloud, "xyz", device=self.device); _check(q_norm, "configuration", device=self.device)
         _check(supervision, "supervision", device=self.device)
         assert cloud.size(2) == 4
@@ -479,7 +480,7 @@ class Engine:
             _check(grads, "grads", device=self.device)
         _lib.check(self.lib.mpn_train_step_grads(self._ctx, self.stream, C.byref(s), B, N, _p(cloud), _p(q_norm), _p(supervision),
                                                  n_loss_points, margin, w_collision, w_bc, _p(losses), _p(y_hat),
-                                                 _p(grads) if need_grad else None))
+                                                 _p(grads) if need_grad else None, precision))
         return losses, y_hat, (grads if need_grad else None)
 
     def train_tc_gemm(self, A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, epi: int = 0,

@@ -169,7 +169,7 @@ class TrainingMotionPolicyNetwork(MotionPolicyNetwork):
         scene = {k: batch[k].contiguous().float() for k in keys}
         losses, y_hat, self.grads = eng.train_step_grads(scene, xyz, q, batch["supervision"].contiguous(),
                                                          w_collision=self.collision_loss_weight, w_bc=self.point_match_loss_weight,
-                                                         grads=self.grads)
+                                                         grads=self.grads, precision=PRECISIONS[self.precision])
         self.log("point_match_loss", losses[1])
         self.log("collision_loss", losses[0])
         val_loss = self.point_match_loss_weight * losses[1] + self.collision_loss_weight * losses[0]

@@ -26,10 +26,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--samples-per-gpu", type=int, default=1024)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
-    from mpinets_b200 import scenes
+    from mpinets_b200 import scenes, _lib
     from mpinets_b200.engine import Engine
     from mpinets_b200.parallel import allreduce_mean_
     from oracle import oracle as O   # weights init only
@@ -49,6 +50,7 @@ def main():
     gen = torch.Generator(device="cuda").manual_seed(rank)
     sup = torch.clamp(qn + 0.05 * torch.randn(qn.shape, generator=gen, device="cuda"), -1, 1)
     grads = torch.empty(eng.param_count, device="cuda")
+    prec = _lib.PREC_BF16 if args.precision == "bf16" else _lib.PREC_FP32
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -58,7 +60,7 @@ def main():
         e[0].record()
         eng.train_step_grads(sc, cloud, qn, sup, need_grad=False)
         e[1].record()
-        losses, _, _ = eng.train_step_grads(sc, cloud, qn, sup, grads=grads)
+        losses, _, _ = eng.train_step_grads(sc, cloud, qn, sup, grads=grads, precision=prec)
         e[2].record()
         allreduce_mean_(grads)
         e[3].record()
@@ -85,12 +87,12 @@ def main():
     t = t.cpu().numpy()
     if rank == 0:
         print(json.dumps({
-            "metric": "training samples/sec (fwd + losses + bwd + DDP all-reduce + clip + Adam), fp32", "value": world * B / (t[0] / 1000.0),
+            "metric": "training samples/sec (fwd + losses + bwd + DDP all-reduce + clip + Adam), " + args.precision, "value": world * B / (t[0] / 1000.0),
             "unit": "samples/s", "n_gpus": world, "samples_per_gpu": B, "steps": args.steps, "ms_per_step": float(t[0]),
             "phases_ms": {"forward_and_losses_only": float(t[1]), "forward_backward": float(t[2]), "grad_allreduce": float(t[3]),
                           "clip_adam_transposes": float(t[4])},
             "gpu_launches_per_step": launches / args.steps / 2,   # the forward-only probe doubles the forward launches
-            "losses": [float(x) for x in losses.cpu()], "dtype": "fp32", "data": "synthetic (config-4 scene mix)",
+            "losses": [float(x) for x in losses.cpu()], "dtype": args.precision, "data": "synthetic (config-4 scene mix)",
             "params": 19068103}))
     if world > 1:
         dist.destroy_process_group()
