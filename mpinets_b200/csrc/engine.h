@@ -212,7 +212,8 @@ int adam_step(mpn_ctx* c, cudaStream_t s, const float* grads, float lr, float be
 int refresh_transposes(mpn_ctx* c, cudaStream_t s);
 // ---- train_tc.cu : tcgen05 GEMMs over compacted rows (bf16 operands)
 int launch_rows_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
-                        const __nv_bfloat16* mask, long long M, int N, __nv_bfloat16* C);
+                        const __nv_bfloat16* mask, long long M, int N, __nv_bfloat16* C, float* pool_out = nullptr,
+                        uint8_t* pool_arg = nullptr, int paired = 0);
 int launch_wgrad_tc(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, const __nv_bfloat16* X, long long R, float* partial,
                     size_t partial_floats, int* n_ctas, int swap_lbo_sbo = 0);
 void free_train_ws(mpn_ctx* c);

@@ -512,31 +512,31 @@ __global__ void __launch_bounds__(256) sa2_gather_bf16_kernel(const int32_t* __r
 
 // SA1: operand rows X4 fp32 [R][4] = [dx dy dz mask] and layer 1 (4 -> 64, K too small for a tensor-core tile) computed on
 // the spot: H1 bf16 [R][64] = relu(W1 x + b1); empty slots give zero rows
-__global__ void __launch_bounds__(256) sa1_gather_h1_kernel(const int32_t* __restrict__ src, long long R, int npoint,
+__global__ void __launch_bounds__(256) sa1_gather_h1_kernel(const int32_t* __restrict__ src, long long R, int slots, int npoint,
                                                             const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz,
                                                             const float* __restrict__ W1, const float* __restrict__ b1,
                                                             float* __restrict__ X4, __nv_bfloat16* __restrict__ H1) {
-  __shared__ float w[256], bs[64];
-  if (threadIdx.x < 256) w[threadIdx.x] = W1[threadIdx.x];
+  __shared__ float w[4][72], bs[64];   // w[k][c], rows padded: the 8 channel-chunk threads of a row read distinct banks
+  w[threadIdx.x & 3][threadIdx.x >> 2] = W1[threadIdx.x];
   if (threadIdx.x < 64) bs[threadIdx.x] = b1[threadIdx.x];
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * 8) return;
   const long long row = i >> 3;
   const int ch = (int)(i & 7);
-  const long long grp = row / 64, b = grp / npoint;
+  const long long grp = row / slots, b = grp / npoint;
   const int si = src[row];
   float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
   if (si >= 0) {
     const float4 p = *reinterpret_cast<const float4*>(cloud + ((size_t)b * N + si) * 4);
     x0 = p.x - new_xyz[(size_t)grp * 3]; x1 = p.y - new_xyz[(size_t)grp * 3 + 1]; x2 = p.z - new_xyz[(size_t)grp * 3 + 2]; x3 = p.w;
   }
-  if (ch == 0) *reinterpret_cast<float4*>(X4 + (size_t)row * 4) = make_float4(x0, x1, x2, x3);
+  if (ch == 0 && X4) *reinterpret_cast<float4*>(X4 + (size_t)row * 4) = make_float4(x0, x1, x2, x3);
   float h[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = ch * 8 + j;
-    const float z = fmaf(w[c * 4 + 3], x3, fmaf(w[c * 4 + 2], x2, fmaf(w[c * 4 + 1], x1, fmaf(w[c * 4], x0, bs[c]))));
+    const float z = fmaf(w[3][c], x3, fmaf(w[2][c], x2, fmaf(w[1][c], x1, fmaf(w[0][c], x0, bs[c]))));
     h[j] = si >= 0 ? fmaxf(z, 0.f) : 0.f;
   }
   __nv_bfloat162 o[4];
@@ -773,7 +773,7 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
   r |= talloc(&t.src, k * SA1_NPOINT * 64);
   r |= talloc(&t.slot, k * SA1_NPOINT * 64);
   r |= talloc(&t.tcw, (size_t)8 * 128 * 128);
-  r |= talloc(&t.b2dup, (size_t)128);
+  r |= talloc(&t.b2dup, (size_t)256);
   t.partial_floats = (size_t)20 << 20;   // >= the largest single weight tensor (fc_layer.3: 8.4 M) + bias
   r |= talloc(&t.partial, t.partial_floats);
   if (r) { free_train_ws(c); return MPN_ERR_NOMEM; }
@@ -782,16 +782,87 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
 }
 
 // ---------------------------------------------------------------------------------------------- forward (saves state)
-static int train_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, const float* qn, int B, int N) {
+int pack_w(mpn_ctx* c, cudaStream_t s, const float* src, int rows, int cols, int ld, int mode, int dst_rows, __nv_bfloat16* dst);
+
+// SA1 / SA2 forward of the bf16 training mode: ball query -> gather ALL 128 neighbour rows per group -> the three layers as
+// row GEMMs on tcgen05 (the same kernels, hence the same activations, as the backward's recomputation), the last one with
+// the max-pool + winning-row epilogue.  Chunked like the backward; rows go through HBM in bf16.
+static int train_forward_sa_tc(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N) {
+  Workspace& w = c->ws;
+  TrainWs& t = c->tw;
+  const Weights& W = c->w;
+  __nv_bfloat16* Xb = reinterpret_cast<__nv_bfloat16*>(t.X);
+  __nv_bfloat16* H1b = reinterpret_cast<__nv_bfloat16*>(t.H1);
+  __nv_bfloat16* H2b = reinterpret_cast<__nv_bfloat16*>(t.H2);
+  __nv_bfloat16* Wa = t.tcw + 4 * 128 * 128;   // forward tiles live in slots 4..7 (the backward re-packs 0..3 per chunk)
+  __nv_bfloat16* Wb = t.tcw + 5 * 128 * 128;
+  __nv_bfloat16* Wc = t.tcw + 6 * 128 * 128;   // SA2 layer 3: [256][128] = slots 6, 7
+  const int chunk = t.chunk;
+  int r;
+  // ---- SA1
+  if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, t.fps_idx, w.xyz1))) return r;
+  if ((r = launch_ball_query(c, s, SA1_RADIUS, NSAMPLE, cloud, B, N, 4, w.xyz1, SA1_NPOINT, t.ball1))) return r;
+  {
+    const Linear* L = W.sa[0];
+    if ((r = pack_w(c, s, L[1].w, 64, 64, 64, 1, 128, Wa))) return r;
+    if ((r = pack_w(c, s, L[2].w, 64, 64, 64, 1, 128, Wb))) return r;
+    for (int h = 0; h < 2; ++h) {
+      MPN_CHECK_CUDA(cudaMemcpyAsync(t.b2dup + 64 * h, L[1].b, 64 * 4, cudaMemcpyDeviceToDevice, s));
+      MPN_CHECK_CUDA(cudaMemcpyAsync(t.b2dup + 128 + 64 * h, L[2].b, 64 * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      const int bc = std::min(chunk, B - b0);
+      const long long R = (long long)bc * SA1_NPOINT * NSAMPLE;
+      sa1_gather_h1_kernel<<<(unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(t.ball1 + (size_t)b0 * SA1_NPOINT * NSAMPLE, R, NSAMPLE, SA1_NPOINT,
+                                                                           cloud + (size_t)b0 * N * 4, N, w.xyz1 + (size_t)b0 * SA1_NPOINT * 3,
+                                                                           L[0].w, L[0].b, nullptr, H1b);
+      c->launches++;
+      MPN_CHECK_CUDA(cudaGetLastError());
+      if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, t.b2dup, nullptr, R / 2, 128, H2b))) return r;
+      if ((r = launch_rows_gemm_tc(c, s, 3, H2b, Wb, t.b2dup + 128, nullptr, R / 2, 128, nullptr, w.feat1 + (size_t)b0 * SA1_NPOINT * 64,
+                                   t.arg1 + (size_t)b0 * SA1_NPOINT * 64, 1))) return r;
+    }
+  }
+  // ---- SA2
+  if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, t.fps_idx, w.xyz2))) return r;
+  if ((r = launch_ball_query(c, s, SA2_RADIUS, NSAMPLE, w.xyz1, B, SA1_NPOINT, 3, w.xyz2, SA2_NPOINT, t.ball2))) return r;
+  {
+    const Linear* L = W.sa[1];
+    if ((r = pack_w(c, s, L[0].w, 128, 67, 67, 0, 128, Wa))) return r;
+    if ((r = pack_w(c, s, L[1].w, 128, 128, 128, 0, 128, Wb))) return r;
+    if ((r = pack_w(c, s, L[2].w, 256, 128, 128, 0, 256, Wc))) return r;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      const int bc = std::min(chunk, B - b0);
+      const long long R = (long long)bc * SA2_NPOINT * NSAMPLE;
+      sa2_gather_bf16_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(t.ball2 + (size_t)b0 * SA2_NPOINT * NSAMPLE, R, NSAMPLE, SA2_NPOINT,
+                                                                              w.xyz1 + (size_t)b0 * SA1_NPOINT * 3, SA1_NPOINT,
+                                                                              w.feat1 + (size_t)b0 * SA1_NPOINT * 64,
+                                                                              w.xyz2 + (size_t)b0 * SA2_NPOINT * 3, Xb);
+      c->launches++;
+      MPN_CHECK_CUDA(cudaGetLastError());
+      if ((r = launch_rows_gemm_tc(c, s, 0, Xb, Wa, L[0].b, nullptr, R, 128, H1b))) return r;
+      if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wb, L[1].b, nullptr, R, 128, H2b))) return r;
+      if ((r = launch_rows_gemm_tc(c, s, 3, H2b, Wc, L[2].b, nullptr, R, 256, nullptr, w.feat2 + (size_t)b0 * SA2_NPOINT * 256,
+                                   t.arg2 + (size_t)b0 * SA2_NPOINT * 256, 0))) return r;
+    }
+  }
+  return MPN_OK;
+}
+
+static int train_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, const float* qn, int B, int N, bool tcp) {
   Workspace& w = c->ws;
   TrainWs& t = c->tw;
   const Weights& W = c->w;
   const int CAT = ENC_DIM + QF_DIM;
   int r;
-  if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, t.fps_idx, w.xyz1))) return r;
-  if ((r = launch_sa_simt(c, s, 0, cloud, 4, cloud + 3, 4, B, N, w.xyz1, w.feat1, t.ball1, t.arg1))) return r;
-  if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, t.fps_idx, w.xyz2))) return r;
-  if ((r = launch_sa_simt(c, s, 1, w.xyz1, 3, w.feat1, 64, B, SA1_NPOINT, w.xyz2, w.feat2, t.ball2, t.arg2))) return r;
+  if (tcp) {
+    if ((r = train_forward_sa_tc(c, s, cloud, B, N))) return r;
+  } else {
+    if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, t.fps_idx, w.xyz1))) return r;
+    if ((r = launch_sa_simt(c, s, 0, cloud, 4, cloud + 3, 4, B, N, w.xyz1, w.feat1, t.ball1, t.arg1))) return r;
+    if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, t.fps_idx, w.xyz2))) return r;
+    if ((r = launch_sa_simt(c, s, 1, w.xyz1, 3, w.feat1, 64, B, SA1_NPOINT, w.xyz2, w.feat2, t.ball2, t.arg2))) return r;
+  }
   if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr, t.arg3))) return r;
   if ((r = launch_linear(c, s, W.fc[0], w.feat3, 1024, B, t.z1, 4096, 0))) return r;
   if ((r = launch_groupnorm_lrelu_train(c, s, t.z1, B, 4096, 16, W.gn_w[0], W.gn_b[0], t.a1, t.st1))) return r;
@@ -929,7 +1000,7 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
 
 
 // ---- tensor-core variant of sa_backward_chunk for SA1 (m = 0) and SA2 (m = 1)
-static int pack_w(mpn_ctx* c, cudaStream_t s, const float* src, int rows, int cols, int ld, int mode, int dst_rows, __nv_bfloat16* dst) {
+int pack_w(mpn_ctx* c, cudaStream_t s, const float* src, int rows, int cols, int ld, int mode, int dst_rows, __nv_bfloat16* dst) {
   pack_train_weight_kernel<<<(dst_rows * 128 + 255) / 256, 256, 0, s>>>(src, rows, cols, ld, mode, dst_rows, dst);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
@@ -1018,7 +1089,7 @@ static int sa_backward_chunk_tc(mpn_ctx* c, cudaStream_t s, int m, int b0, int b
     MPN_CHECK_CUDA(cudaMemcpyAsync(t.b2dup, L[1].b, 64 * 4, cudaMemcpyDeviceToDevice, s));
     MPN_CHECK_CUDA(cudaMemcpyAsync(t.b2dup + 64, L[1].b, 64 * 4, cudaMemcpyDeviceToDevice, s));
     float* X4 = t.X;
-    sa1_gather_h1_kernel<<<(unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(t.src, R, npoint, xyz_c, N_in, nx_c, L[0].w, L[0].b, X4, H1b);
+    sa1_gather_h1_kernel<<<(unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, N_in, nx_c, L[0].w, L[0].b, X4, H1b);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     const long long R2 = R / 2;                                                                          // rows in pairs: [R/2][128]
@@ -1048,7 +1119,7 @@ int train_step_grads(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int
   TrainWs& t = c->tw;
   const Weights& W = c->w;
   const int CAT = ENC_DIM + QF_DIM;
-  if ((r = train_forward(c, s, cloud, q_norm, B, N))) return r;
+  if ((r = train_forward(c, s, cloud, q_norm, B, N, tcp))) return r;
   // y_hat = clamp(q + net(xyz, q), -1, 1) (model.py:202); losses + d(weighted loss) / d y_hat
   yhat_kernel<<<(B * 7 + 255) / 256, 256, 0, s>>>(q_norm, w.dq, B * 7, t.yhat);
   c->launches++;

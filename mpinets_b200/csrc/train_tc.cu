@@ -35,20 +35,22 @@ __device__ __host__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_
   return make_idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
 }
 
-enum { EPI_RELU = 0, EPI_PLAIN = 1, EPI_MASK = 2 };
+enum { EPI_RELU = 0, EPI_PLAIN = 1, EPI_MASK = 2, EPI_POOL = 3 };
 
 template <int N>
 struct RowsCfg {
   static constexpr int NWG = N == 256 ? 2 : 4;                 // warpgroups per CTA (N TMEM columns each)
   static constexpr size_t w_bytes = (size_t)N * TK * 2;
   static constexpr size_t a_bytes = (size_t)128 * TK * 2;      // one 128-row tile
-  static constexpr size_t smem = w_bytes + NWG * a_bytes + N * 4 + 64;
+  static constexpr size_t red_bytes = (size_t)NWG * 4 * N * 4;   // EPI_POOL: per-warp column maxima (keys)
+  static constexpr size_t smem = w_bytes + NWG * a_bytes + N * 4 + 64 + red_bytes;
 };
 
 template <int N, int EPI>
 __global__ void __launch_bounds__(128 * RowsCfg<N>::NWG, 1)
 rows_gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias,
-                    const __nv_bfloat16* mask, long long ntiles, __nv_bfloat16* C, int* __restrict__ err) {
+                    const __nv_bfloat16* mask, long long ntiles, __nv_bfloat16* C, float* __restrict__ pool_out,
+                    uint8_t* __restrict__ pool_arg, int paired, int* __restrict__ err) {
   using Cfg = RowsCfg<N>;
   constexpr int NWG = Cfg::NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -56,6 +58,7 @@ rows_gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __
   uint8_t* sA = smem + Cfg::w_bytes;
   float* sbias = reinterpret_cast<float*>(sA + NWG * Cfg::a_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + N);
+  int* redk = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 64);
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;
   const int wg = warp >> 2, wq = warp & 3, t = tid & 127;
@@ -112,6 +115,47 @@ rows_gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __
     ok = mbar_wait(&bars[wg], phase) && ok;
     phase ^= 1u;
     tc_fence_after();
+    if (EPI == EPI_POOL) {
+      // ---- ReLU + max-pool over the tile's rows with the winning row (max_pool2d's argmax, first occurrence): the maximum
+      // is taken on order-preserving integer keys whose low 7 bits carry (127 - row), so one redux.sync per column gives
+      // value (to 2^-16 relative) and row at once.  Unpaired: tile = one group of 128 neighbour rows.  Paired (SA1): a tile
+      // row holds neighbours 2t (columns 0..63) and 2t + 1 (columns 64..127) and the tile spans two groups of 64 paired rows.
+      int* rk = redk + (size_t)(wg * 4 + wq) * N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t a[32];
+        tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + c0, a);
+        tmem_ld_wait();
+        const int rowcode = paired ? 2 * (t & 63) + (c0 >= 64 ? 1 : 0) : t;
+        const uint32_t low = (uint32_t)(127 - rowcode);
+        int keep = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int bits = __float_as_int(__uint_as_float(a[j]) + sbias[c0 + j]);
+          const int key = bits > 0 ? (int)(((uint32_t)bits & 0xFFFFFF80u) | low) : 0;
+          const int mx = __reduce_max_sync(0xffffffffu, key);
+          keep = lane == j ? mx : keep;
+        }
+        rk[c0 + lane] = keep;
+      }
+      tc_fence_before();
+      wgroup_sync(wg);
+      const int* r4 = redk + (size_t)(wg * 4) * N;
+      if (!paired) {
+        for (int cc = t; cc < N; cc += 128) {
+          const int k = max(max(r4[cc], r4[N + cc]), max(r4[2 * N + cc], r4[3 * N + cc]));
+          pool_out[(size_t)tile * N + cc] = __int_as_float(k & (int)0xFFFFFF80);
+          pool_arg[(size_t)tile * N + cc] = (uint8_t)(127 - (k & 127));
+        }
+      } else {
+        const int gh = t >> 6, ch = t & 63;
+        const int* ra = r4 + (size_t)(2 * gh) * N;
+        const int k = max(max(ra[ch], ra[N + ch]), max(ra[ch + 64], ra[N + ch + 64]));
+        pool_out[((size_t)tile * 2 + gh) * 64 + ch] = __int_as_float(k & (int)0xFFFFFF80);
+        pool_arg[((size_t)tile * 2 + gh) * 64 + ch] = (uint8_t)(127 - (k & 127));
+      }
+      continue;
+    }
     // ---- epilogue: thread = output row
     const size_t row = (size_t)tile * 128 + t;
     __nv_bfloat16* crow = C + row * N;
@@ -253,9 +297,11 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __res
 
 // C[M][N] (bf16) = epi(A[M][128] W[N][128]^T + bias); M % 128 == 0; epi: 0 relu, 1 plain, 2 multiply by relu'(mask[M][N])
 int launch_rows_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
-                        const __nv_bfloat16* mask, long long M, int N, __nv_bfloat16* C) {
+                        const __nv_bfloat16* mask, long long M, int N, __nv_bfloat16* C, float* pool_out, uint8_t* pool_arg,
+                        int paired) {
   MPN_REQUIRE(M % 128 == 0 && (N == 64 || N == 128 || N == 256), "rows_gemm_tc: M %% 128 == 0 and N in {64,128,256} required");
   MPN_REQUIRE(epi != EPI_MASK || mask, "rows_gemm_tc: mask epilogue without a mask");
+  MPN_REQUIRE(epi != EPI_POOL || (pool_out && pool_arg && (paired ? N == 128 : N >= 128)), "rows_gemm_tc: bad pool arguments");
   if (M == 0) return MPN_OK;
   const long long ntiles = M / 128;
   int* errf = tc_error_flag(c);
@@ -266,13 +312,14 @@ int launch_rows_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16
     MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
     const long long want = (ntiles + RowsCfg<NN>::NWG - 1) / RowsCfg<NN>::NWG;                                           \
     const int grid = (int)std::min<long long>(want, c->sm_count);                                                        \
-    k<<<grid, 128 * RowsCfg<NN>::NWG, smem, s>>>(A, W, bias, mask, ntiles, C, errf);                                     \
+    k<<<grid, 128 * RowsCfg<NN>::NWG, smem, s>>>(A, W, bias, mask, ntiles, C, pool_out, pool_arg, paired, errf);         \
   } while (0)
 #define ROWS_EPI(NN)                                       \
   do {                                                     \
     if (epi == EPI_RELU) ROWS_LAUNCH(NN, EPI_RELU);        \
     else if (epi == EPI_PLAIN) ROWS_LAUNCH(NN, EPI_PLAIN); \
-    else ROWS_LAUNCH(NN, EPI_MASK);                        \
+    else if (epi == EPI_MASK) ROWS_LAUNCH(NN, EPI_MASK);   \
+    else ROWS_LAUNCH(NN, EPI_POOL);                        \
   } while (0)
   if (N == 64) ROWS_EPI(64);
   else if (N == 128) ROWS_EPI(128);

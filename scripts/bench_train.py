@@ -58,7 +58,7 @@ def main():
     def step(i, timed=None):
         e = [ev() for _ in range(5)]
         e[0].record()
-        eng.train_step_grads(sc, cloud, qn, sup, need_grad=False)
+        eng.train_step_grads(sc, cloud, qn, sup, need_grad=False, precision=prec)
         e[1].record()
         losses, _, _ = eng.train_step_grads(sc, cloud, qn, sup, grads=grads, precision=prec)
         e[2].record()

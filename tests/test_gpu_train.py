@@ -211,28 +211,29 @@ def test_validation_step_matches_oracle(oracle, tables, state_dict):
 
 
 def test_train_step_grads_bf16_mode(engine_w, oracle, tables, state_dict):
-    """MPN_PREC_BF16 training: the SA1 / SA2 backward GEMMs on tcgen05 with bf16 operands (fp32 accumulate).  Same forward and
-    routing as the fp32 mode, so SA3 / FC / head gradients are bit-identical to it; SA1 / SA2 parameter gradients carry the
-    bf16 operand rounding (8 mantissa bits on activations and on dZ; signed sums, so the error relative to the max-norm does
-    not average away): bar 1e-1 of each tensor's max-norm against the float64 oracle under the same routing, measured
-    2e-2..5e-2 at 3 samples (gpurun_out/train_grads_bf16.txt)."""
+    """MPN_PREC_BF16 training (the counterpart of the reference's precision=16 autocast): SA1 / SA2 forward and backward GEMMs
+    on tcgen05 with bf16 operands and fp32 accumulation; SA3 / FC head / heads stay fp32.
+      * forward: y_hat within 5e-3 of the fp32 mode (|y| <= 1);
+      * routing: the pooled rows hold the oracle's maximum to bf16 accuracy (gap <= 3e-2 |max| + 1e-3);
+      * gradients vs the float64 oracle replaying that routing: bar 1.5e-1 of each tensor's max-norm (bf16 rounding of
+        activations and of dZ enters signed sums, so it does not average away; measured 2e-2..6e-2 at 3 samples,
+        gpurun_out/train_grads_bf16.txt)."""
     from mpinets_b200 import _lib
     B = 3
     p, cloud, qn, sup = _batch(oracle, tables, B)
     args = (to_dev(p), torch.from_numpy(cloud).cuda(), torch.from_numpy(qn).cuda(), torch.from_numpy(sup).cuda())
-    l32, y32, g32 = engine_w.train_step_grads(*args)
-    g32 = g32.clone()
+    l32, y32, _ = engine_w.train_step_grads(*args, need_grad=False)
     l16, y16, g16 = engine_w.train_step_grads(*args, precision=_lib.PREC_BF16)
     torch.cuda.synchronize()
     assert not engine_w.tc_error()
-    assert torch.equal(l32, l16) and torch.equal(y32, y16)
+    assert float((y32 - y16).abs().max()) < 5e-3
+    assert float((l32 - l16).abs().max()) < 1e-2 * float(l32.abs().max())
     rows = [r.cpu().numpy() for r in engine_w.train_pooled_rows(B)]
-    _, _, rg, _ = oracle.train_step_grads(state_dict, cloud, qn, sup, p, tables, engine_w.cfg.seed, dtype=torch.float64, pool_idx=rows)
-    report, bad = _compare_grads(engine_w, g16, rg, rg, tol=1e-1)
+    _, _, rg, _, aux = oracle.train_step_grads(state_dict, cloud, qn, sup, p, tables, engine_w.cfg.seed, dtype=torch.float64,
+                                               pool_idx=rows, return_aux=True)
+    for m, a in enumerate(aux):
+        gap, top = a["pool_gap"].numpy(), a["feats"].detach().numpy()
+        assert (gap <= 3e-2 * np.abs(top) + 1e-3).all(), f"SA{m + 1}: pooled row far from the maximum (gap {gap.max():.3e})"
+    report, bad = _compare_grads(engine_w, g16, rg, rg, tol=1.5e-1)
     _dump("train_grads_bf16.txt", report)
-    v32, v16 = engine_w.unflatten(g32), engine_w.unflatten(g16)
-    for k in v32:
-        if ".SA_modules.0." in k or ".SA_modules.1." in k:
-            continue
-        assert torch.equal(v32[k], v16[k]), k
     assert not bad, f"bf16-mode gradient mismatch in {bad}: " + "; ".join(f"{k} rel {r:.1e}" for k, _, _, r, _ in report if k in bad)
