@@ -124,6 +124,11 @@ __device__ __forceinline__ uint32_t cvt_relu_bf16x2(float first, float second) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
   return d;
 }
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 // TMEM [128 lanes][NC cols] fp32 (bias already inside the accumulator) -> relu -> bf16 -> chunks 0..NC/8-1 of row `row`
 template <int NC, int KCX>
 __device__ __forceinline__ void epilogue_pack_relu(uint32_t taddr, uint8_t* X, int row) {
@@ -595,24 +600,42 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
       }
       ok = ok && mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
+      // max over the 128 neighbour rows: accumulator-fragment loads (every thread: 4 rows x 16 channels, in two column halves) -> in-thread max ->
+      // ReLU + bf16x2 (monotone, so rounding before the max gives the same result) -> 3 halving butterfly steps over the 8
+      // row groups of the warp; lane L ends up with channels 2L, 2L+1 of the warp's 32 rows
+      {
+        uint32_t pk[8];
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tlane + c0, v);
-        tmem_ld_wait();
-        int keep = 0;
+        for (int h = 0; h < 2; ++h) {
+          uint32_t va[16], vb[16];
+          tmem_ld_16x256b_x4(tlane + h * 32, va);
+          tmem_ld_16x256b_x4(tlane + (16u << 16) + h * 32, vb);
+          tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const int mx = __reduce_max_sync(0xffffffffu, (int)v[q]);
-          keep = lane == q ? mx : keep;
+          for (int rep = 0; rep < 4; ++rep) {
+            const float m0 = fmaxf(fmaxf(__uint_as_float(va[rep * 4]), __uint_as_float(va[rep * 4 + 2])),
+                                   fmaxf(__uint_as_float(vb[rep * 4]), __uint_as_float(vb[rep * 4 + 2])));
+            const float m1 = fmaxf(fmaxf(__uint_as_float(va[rep * 4 + 1]), __uint_as_float(va[rep * 4 + 3])),
+                                   fmaxf(__uint_as_float(vb[rep * 4 + 1]), __uint_as_float(vb[rep * 4 + 3])));
+            pk[h * 4 + rep] = cvt_relu_bf16x2(m0, m1);
+          }
         }
-        red[wq * 64 + c0 + lane] = keep;
+#pragma unroll
+        for (int w = 4; w >= 1; w >>= 1) {
+          const bool upper = (lane & (w << 2)) != 0;
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            const uint32_t send = upper ? pk[i] : pk[i + w], keepv = upper ? pk[i + w] : pk[i];
+            pk[i] = bf16x2_max(keepv, __shfl_xor_sync(0xffffffffu, send, w << 2));
+          }
+        }
+        red[wq * 32 + lane] = (int)pk[0];
       }
       tc_fence_before();
       wg_sync(g);
-      if (t < 64) {
-        const int m = max(max(red[t], red[64 + t]), max(red[128 + t], red[192 + t]));
-        out_bf16[((size_t)b * SA1_NPOINT + j) * 64 + t] = __float2bfloat16_rn(fmaxf(__int_as_float(m), 0.f));
+      if (t < 32) {
+        const uint32_t m = bf16x2_max(bf16x2_max((uint32_t)red[t], (uint32_t)red[32 + t]), bf16x2_max((uint32_t)red[64 + t], (uint32_t)red[96 + t]));
+        reinterpret_cast<uint32_t*>(out_bf16 + ((size_t)b * SA1_NPOINT + j) * 64)[t] = m;
       }
     }
     if (t == 0) rsel[g] = atomicAdd(next_round, 1);
