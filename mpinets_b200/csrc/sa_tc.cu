@@ -388,7 +388,8 @@ struct Sa1wSmem {
   static constexpr size_t bars = red + SA1W_NWG * 4 * 64 * 4;              // NWG mbarriers + tmem slot
   static constexpr size_t bstart = (bars + 64 + 15) / 16 * 16;             // u16 [BUCKETS + 1]
   static constexpr size_t sidx = (bstart + (SA1_BUCKETS + 1) * 2 + 15) / 16 * 16;   // u16 [N]
-  static size_t total(int N) { return sidx + (size_t)N * 2 + 64; }
+  __host__ __device__ static size_t cxyz(int N) { return (sidx + (size_t)N * 2 + 64 + 15) / 16 * 16; }   // f32 [512][3] centroid coordinates
+  static size_t total(int N) { return cxyz(N) + (size_t)SA1_NPOINT * 3 * 4; }
 };
 
 template <int SA1W_NWG>
@@ -419,6 +420,8 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
   stage_weight(gw1, 64, SA1_XK, sW1);
   stage_weight(gw2, 64, SA1_XK, sW2);
   stage_weight(gw3, 64, SA1_XK, sW3);
+  float* cxyz = reinterpret_cast<float*>(smem + S::cxyz(N));
+  for (int i = threadIdx.x; i < SA1_NPOINT * 3; i += blockDim.x) cxyz[i] = __ldg(new_xyz + (size_t)b * SA1_NPOINT * 3 + i);
   // ---- hash-grid build: counting sort of point indices by bucket (counters alias the operand buffers)
   {
     uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + S::x);
@@ -488,7 +491,7 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
   // complete ball query of centroid jc by this warp -> lists[wq][0..127]
   auto warp_ball_query = [&](int jc) {
     uint16_t* widx = lists + wq * 128;
-    const float* cpw = new_xyz + ((size_t)b * SA1_NPOINT + jc) * 3;
+    const float* cpw = cxyz + jc * 3;
     const float qx = cpw[0], qy = cpw[1], qz = cpw[2];
     const int ix = grid_coord(qx), iy = grid_coord(qy), iz = grid_coord(qz);
     uint32_t bk = 0x10000u + lane;
@@ -502,17 +505,31 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
     const int C = __shfl_sync(0xffffffffu, incl, 31);
     if (C <= 256) {
-      for (int i = 0, o = incl - n0; i < n0; ++i) wcand[o + i] = sidx[s0 + i];   // candidates by ORIGINAL point index
+      {   // candidates by ORIGINAL point index
+        const int o = incl - n0;
+        int i = 0;
+        for (; i + 4 <= n0; i += 4) {
+          const uint16_t a0 = sidx[s0 + i], a1 = sidx[s0 + i + 1], a2 = sidx[s0 + i + 2], a3 = sidx[s0 + i + 3];
+          wcand[o + i] = a0; wcand[o + i + 1] = a1; wcand[o + i + 2] = a2; wcand[o + i + 3] = a3;
+        }
+        for (; i < n0; ++i) wcand[o + i] = sidx[s0 + i];
+      }
       __syncwarp();
       int H = 0;
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        const int ci = c0 + lane;
-        bool hit = false;
-        int k = 0;
-        if (ci < C) { k = wcand[ci]; const float4 v = __ldg(cl + k); hit = dist2(qx, qy, qz, v.x, v.y, v.z) < r2; }
-        const unsigned hm = __ballot_sync(0xffffffffu, hit);
-        if (hit) wcand[H + __popc(hm & lt)] = (uint16_t)k;         // in place: write position <= read position
-        H += __popc(hm);
+      for (int c0 = 0; c0 < C; c0 += 64) {   // 2 x 32 candidates with their L2 loads in flight together
+        const int ci0 = c0 + lane, ci1 = c0 + 32 + lane;
+        const int k0 = ci0 < C ? (int)wcand[ci0] : 0, k1 = ci1 < C ? (int)wcand[ci1] : 0;
+        const float4 v0 = __ldg(cl + k0);
+        float4 v1 = v0;
+        if (c0 + 32 < C) v1 = __ldg(cl + k1);
+        const bool hit0 = ci0 < C && dist2(qx, qy, qz, v0.x, v0.y, v0.z) < r2;
+        const bool hit1 = ci1 < C && dist2(qx, qy, qz, v1.x, v1.y, v1.z) < r2;
+        __syncwarp();
+        const unsigned hm0 = __ballot_sync(0xffffffffu, hit0), hm1 = __ballot_sync(0xffffffffu, hit1);
+        if (hit0) wcand[H + __popc(hm0 & lt)] = (uint16_t)k0;         // in place: write position <= read position of later batches
+        H += __popc(hm0);
+        if (hit1) wcand[H + __popc(hm1 & lt)] = (uint16_t)k1;
+        H += __popc(hm1);
         __syncwarp();
       }
       for (int h = lane; h < H; h += 32) {
@@ -565,7 +582,7 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
     if (base + wq < SA1_NPOINT) warp_ball_query(base + wq);
     wg_sync(g);
     float4 pn = __ldg(cl + lists[t]);
-    const float* cpn = new_xyz + ((size_t)b * SA1_NPOINT + base) * 3;
+    const float* cpn = cxyz + base * 3;
     float nx = cpn[0], ny = cpn[1], nz = cpn[2];
 #pragma unroll 1
     for (int cc = 0; cc < 4 && ok; ++cc) {
@@ -585,7 +602,7 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
       issue(dW1, true);
       if (cc < 3 && j + 1 < SA1_NPOINT) {   // next centroid's gathered point and coordinates, under the MMAs
         pn = __ldg(cl + lists[(cc + 1) * 128 + t]);
-        const float* cq = new_xyz + ((size_t)b * SA1_NPOINT + j + 1) * 3;
+        const float* cq = cxyz + (j + 1) * 3;
         nx = cq[0]; ny = cq[1]; nz = cq[2];
       }
 #pragma unroll 1
