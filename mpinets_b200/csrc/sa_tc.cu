@@ -53,7 +53,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int out, int in,
   dst[i] = __float2bfloat16_rn(v);
 }
 
-int tc_prepare_weights(mpn_ctx* c) {
+// (re)pack the bf16 operand copies from the fp32 master weights on stream s; buffers are allocated on first use
+static int tc_pack_weights(mpn_ctx* c, cudaStream_t s, bool sa_only) {
   TcWeights& t = g_tc[c];
   for (int m = 0; m < 3; ++m)
     for (int l = 0; l < 3; ++l) {
@@ -63,31 +64,41 @@ int tc_prepare_weights(mpn_ctx* c) {
       if (m == 1 && l == 0) bias_col = 67;                  // SA2 layer 1: [f0..f63, dx, dy, dz, bias, 0 x12]
       if (m == 1 && l == 1) { kpad = 144; bias_col = 128; } // SA2 layer 2: [128 weights, bias, 0 x15]
       t.kpad[m][l] = kpad;
-      if (t.sa[m][l]) cudaFree(t.sa[m][l]);
-      MPN_CHECK_CUDA(cudaMalloc(&t.sa[m][l], (size_t)L.out * kpad * sizeof(__nv_bfloat16)));
+      if (!t.sa[m][l]) MPN_CHECK_CUDA(cudaMalloc(&t.sa[m][l], (size_t)L.out * kpad * sizeof(__nv_bfloat16)));
       int n = L.out * kpad;
-      pack_weight_kernel<<<(n + 255) / 256, 256>>>(L.w, L.out, L.in, kpad, (l == 0 && m > 0) ? 1 : 0, t.sa[m][l],
-                                                   bias_col >= 0 ? L.b : nullptr, bias_col);
+      pack_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(L.w, L.out, L.in, kpad, (l == 0 && m > 0) ? 1 : 0, t.sa[m][l],
+                                                         bias_col >= 0 ? L.b : nullptr, bias_col);
+      c->launches++;
       MPN_CHECK_CUDA(cudaGetLastError());
     }
   {
     const Linear& L = c->w.sa[1][1];
-    if (t.w2_nofold) cudaFree(t.w2_nofold);
-    MPN_CHECK_CUDA(cudaMalloc(&t.w2_nofold, (size_t)L.out * L.in * sizeof(__nv_bfloat16)));
-    pack_weight_kernel<<<(L.out * L.in + 255) / 256, 256>>>(L.w, L.out, L.in, L.in, 0, t.w2_nofold);
+    if (!t.w2_nofold) MPN_CHECK_CUDA(cudaMalloc(&t.w2_nofold, (size_t)L.out * L.in * sizeof(__nv_bfloat16)));
+    pack_weight_kernel<<<(L.out * L.in + 255) / 256, 256, 0, s>>>(L.w, L.out, L.in, L.in, 0, t.w2_nofold);
+    c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
   }
+  if (sa_only) return MPN_OK;
   for (int l = 0; l < 3; ++l) {
     const Linear& L = c->w.fc[l];
-    if (t.fc[l]) cudaFree(t.fc[l]);
-    MPN_CHECK_CUDA(cudaMalloc(&t.fc[l], (size_t)L.out * L.in * sizeof(__nv_bfloat16)));
+    if (!t.fc[l]) MPN_CHECK_CUDA(cudaMalloc(&t.fc[l], (size_t)L.out * L.in * sizeof(__nv_bfloat16)));
     int n = L.out * L.in;
-    pack_weight_kernel<<<(n + 255) / 256, 256>>>(L.w, L.out, L.in, L.in, 0, t.fc[l]);
+    pack_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(L.w, L.out, L.in, L.in, 0, t.fc[l]);
+    c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
   }
+  return MPN_OK;
+}
+
+int tc_prepare_weights(mpn_ctx* c) {
+  int r = tc_pack_weights(c, 0, false);
+  if (r) return r;
   MPN_CHECK_CUDA(cudaDeviceSynchronize());
   return MPN_OK;
 }
+
+// after an optimizer step: refresh every bf16 copy on the training stream (no allocation, no host sync)
+int tc_refresh_weights(mpn_ctx* c, cudaStream_t s) { return tc_pack_weights(c, s, false); }
 
 // scratch: feat1 bf16 [B][512][64] | SA3 operand rows bf16 [B*128][272] ([256 feats, x, y, z, 0-pad])
 constexpr int A3_K = 272;
@@ -167,11 +178,12 @@ struct Sa2wSmem {
   static constexpr size_t total = bars + 64;
 };
 
+template <bool ARG>
 __global__ void __launch_bounds__(SA2W_THREADS, 1)
 sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __restrict__ feat_bf16, const float* __restrict__ new_xyz,
                 float r2, const __nv_bfloat16* __restrict__ gw1, const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3,
                 const float* __restrict__ gb2, const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16, int out_stride,
-                int* __restrict__ err, int32_t* __restrict__ ball_idx) {
+                int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out) {
   using S = Sa2wSmem;
   constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT, KC = SA2W_KC;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -346,6 +358,21 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
           for (int q = 0; q < 32; ++q) m = fmaxf(m, fmaxf(__uint_as_float(v[q]), __uint_as_float(u[q])));
         }
         o[tile * 128 + t] = __float2bfloat16_rn(fmaxf(m + sB3[tile * 128 + t], 0.f));
+        if constexpr (ARG) {   // training forward: the winning neighbour slot of this channel (first column attaining the maximum)
+          int arg = 0;
+#pragma unroll
+          for (int c0 = 64; c0 >= 0; c0 -= 64) {
+            uint32_t v[32], u[32];
+            tmem_ld32(tlane + c0, v);
+            tmem_ld32(tlane + c0 + 32, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 31; q >= 0; --q) arg = __uint_as_float(u[q]) == m ? c0 + 32 + q : arg;
+#pragma unroll
+            for (int q = 31; q >= 0; --q) arg = __uint_as_float(v[q]) == m ? c0 + q : arg;
+          }
+          arg_out[((size_t)b * NCENT + j) * 256 + tile * 128 + t] = (uint8_t)arg;
+        }
         tc_fence_before();
         wg_sync(g);                                             // every lane of the accumulator has been read
         if (tile == 0) issue(dW3, W3_TILE1, dX, 0, 8);           // channel tile 1 into the same TMEM columns
@@ -392,11 +419,11 @@ struct Sa1wSmem {
   static size_t total(int N) { return cxyz(N) + (size_t)SA1_NPOINT * 3 * 4; }
 };
 
-template <int SA1W_NWG>
+template <int SA1W_NWG, bool ARG = false>
 __global__ void __launch_bounds__(128 * SA1W_NWG, 1)
 sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
                 const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
-                int* __restrict__ err, int32_t* __restrict__ ball_idx) {
+                int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out = nullptr) {
   using S = Sa1wSmem<SA1W_NWG>;
   constexpr int KC = SA1_XK / 8, NS = NSAMPLE;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -653,6 +680,40 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
       if (t < 32) {
         const uint32_t m = bf16x2_max(bf16x2_max((uint32_t)red[t], (uint32_t)red[32 + t]), bf16x2_max((uint32_t)red[64 + t], (uint32_t)red[96 + t]));
         reinterpret_cast<uint32_t*>(out_bf16 + ((size_t)b * SA1_NPOINT + j) * 64)[t] = m;
+        if constexpr (ARG) red[128 + t] = (int)m;
+      }
+      if constexpr (ARG) {
+        // training forward: the winning neighbour row of every channel = the first row whose ReLU'd bf16 output equals the pooled
+        // value (channels pooled to 0 carry no gradient: row 0).  The accumulator is still in TMEM; red[160..223] = row per channel
+        if (t < 64) red[160 + t] = 255;
+        wg_sync(g);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t va[16], vb[16];
+          tmem_ld_16x256b_x4(tlane + h * 32, va);
+          tmem_ld_16x256b_x4(tlane + (16u << 16) + h * 32, vb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int rep = 0; rep < 4; ++rep) {
+            const uint32_t fin = (uint32_t)red[128 + 4 * (h * 4 + rep) + (lane & 3)];
+            const int ch0 = 8 * (h * 4 + rep) + 2 * (lane & 3);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const uint32_t* src = rr < 2 ? va : vb;
+              const int o = rep * 4 + (rr & 1) * 2;
+              const uint32_t pv = cvt_relu_bf16x2(__uint_as_float(src[o]), __uint_as_float(src[o + 1]));
+              const int row = wq * 32 + (lane >> 2) + 8 * rr;
+              if ((fin & 0xFFFFu) != 0u && (pv & 0xFFFFu) == (fin & 0xFFFFu)) atomicMin(&red[160 + ch0], row);
+              if ((fin >> 16) != 0u && (pv >> 16) == (fin >> 16)) atomicMin(&red[160 + ch0 + 1], row);
+            }
+          }
+        }
+        tc_fence_before();
+        wg_sync(g);
+        if (t < 64) {
+          const int a = red[160 + t];
+          arg_out[((size_t)b * SA1_NPOINT + j) * 64 + t] = (uint8_t)(a > 127 ? 0 : a);
+        }
       }
     }
     if (t == 0) rsel[g] = atomicAdd(next_round, 1);
@@ -693,19 +754,20 @@ __global__ void narrow_kernel(const float* __restrict__ src, size_t rows, int sr
 
 template <int MODULE>
 static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
-                        int B, __nv_bfloat16* out, int out_stride, int32_t* ball_idx = nullptr) {
+                        int B, __nv_bfloat16* out, int out_stride, int32_t* ball_idx = nullptr, uint8_t* arg_out = nullptr) {
   TcWeights& tw = g_tc[c];
   // SA1: 7 row warpgroups (72 registers) with the grid index on chip; MPN_SA1_WG=6 runs 6 groups (A/B switch)
   static const int sa1_wg = getenv("MPN_SA1_WG") ? atoi(getenv("MPN_SA1_WG")) : 7;
   if (MODULE == 0) {
     MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
     MPN_REQUIRE(N < 65536, "tensor-core SA1: at most 65535 points");
-    if (sa1_wg != 6) {
+    if (sa1_wg != 6 || arg_out) {
       size_t smem7 = Sa1wSmem<7>::total(N);
       MPN_REQUIRE(smem7 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
-      MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1w_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));
-      sa1w_tc_kernel<7><<<B, 128 * 7, smem7, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
-                                                  tc_error_flag(c), ball_idx);
+      auto kern = arg_out ? sa1w_tc_kernel<7, true> : sa1w_tc_kernel<7, false>;
+      MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));
+      kern<<<B, 128 * 7, smem7, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out, tc_error_flag(c),
+                                     ball_idx, arg_out);
     } else {
       size_t smem6 = Sa1wSmem<6>::total(N);
       MPN_REQUIRE(smem6 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
@@ -720,9 +782,10 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
   MPN_REQUIRE(N == SA1_NPOINT, "tensor-core SA2 expects the 512 SA1 centroids as input points");
   {
     size_t smem3 = Sa2wSmem::total;
-    MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2w3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    sa2w3_tc_kernel<<<B, SA2W_THREADS, smem3, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.w2_nofold,
-                                                   tw.sa[1][2], c->w.sa[1][1].b, c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx);
+    auto kern = arg_out ? sa2w3_tc_kernel<true> : sa2w3_tc_kernel<false>;
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    kern<<<B, SA2W_THREADS, smem3, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.w2_nofold, tw.sa[1][2],
+                                        c->w.sa[1][1].b, c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx, arg_out);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;
@@ -750,6 +813,28 @@ int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int 
     widen_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(a3, B * SA2_NPOINT, A3_K, 256, new_feats);
   }
   c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// SA1 + SA2 forward of the bf16 training step through the fused inference kernels (ARG variants): besides the pooled features
+// they record the ball-query indices and the winning neighbour row of every (group, channel) -- the routing the backward replays.
+// Outputs in the training step's formats: feat1 f32 [B][512][64], feat2 f32 [B][128][256], ball1 / ball2 i32, arg1 / arg2 u8.
+int tc_train_forward_sa(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, int32_t* fps_idx, float* xyz1, float* xyz2,
+                        float* feat1_f32, float* feat2_f32, int32_t* ball1, int32_t* ball2, uint8_t* arg1, uint8_t* arg2) {
+  Workspace& w = c->ws;
+  MPN_REQUIRE(B <= w.capacity, "tc_train_forward_sa: batch %d exceeds the workspace capacity %d", B, w.capacity);
+  __nv_bfloat16* feat1 = reinterpret_cast<__nv_bfloat16*>(w.tc_scratch);
+  __nv_bfloat16* a3 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w.tc_scratch) + feat1_bytes(w.capacity));
+  int r;
+  if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, fps_idx, xyz1))) return r;
+  if ((r = launch_sa_tc<0>(c, s, cloud, 4, N, nullptr, xyz1, B, feat1, 64, ball1, arg1))) return r;
+  if ((r = launch_fps(c, s, xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, fps_idx, xyz2))) return r;
+  if ((r = launch_sa_tc<1>(c, s, xyz1, 3, SA1_NPOINT, feat1, xyz2, B, a3, A3_K, ball2, arg2))) return r;
+  const size_t n1 = (size_t)B * SA1_NPOINT * 64, n2 = (size_t)B * SA2_NPOINT * 256;
+  widen_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(feat1, B * SA1_NPOINT, 64, 64, feat1_f32);
+  widen_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(a3, B * SA2_NPOINT, A3_K, 256, feat2_f32);
+  c->launches += 2;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
 }

@@ -783,6 +783,9 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
 
 // ---------------------------------------------------------------------------------------------- forward (saves state)
 int pack_w(mpn_ctx* c, cudaStream_t s, const float* src, int rows, int cols, int ld, int mode, int dst_rows, __nv_bfloat16* dst);
+int tc_train_forward_sa(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, int32_t* fps_idx, float* xyz1, float* xyz2,
+                        float* feat1_f32, float* feat2_f32, int32_t* ball1, int32_t* ball2, uint8_t* arg1, uint8_t* arg2);
+int tc_refresh_weights(mpn_ctx* c, cudaStream_t s);
 
 // SA1 / SA2 forward of the bf16 training mode: ball query -> gather ALL 128 neighbour rows per group -> the three layers as
 // row GEMMs on tcgen05 (the same kernels, hence the same activations, as the backward's recomputation), the last one with
@@ -799,6 +802,9 @@ static int train_forward_sa_tc(mpn_ctx* c, cudaStream_t s, const float* cloud, i
   __nv_bfloat16* Wc = t.tcw + 6 * 128 * 128;   // SA2 layer 3: [256][128] = slots 6, 7
   const int chunk = t.chunk;
   int r;
+  static const bool rows_fwd = getenv("MPN_TRAIN_ROWS_FWD") != nullptr;   // A/B switch: the row-GEMM forward below
+  if (!rows_fwd)
+    return tc_train_forward_sa(c, s, cloud, B, N, t.fps_idx, w.xyz1, w.xyz2, w.feat1, w.feat2, t.ball1, t.ball2, t.arg1, t.arg2);
   // ---- SA1
   if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, t.fps_idx, w.xyz1))) return r;
   if ((r = launch_ball_query(c, s, SA1_RADIUS, NSAMPLE, cloud, B, N, 4, w.xyz1, SA1_NPOINT, t.ball1))) return r;
@@ -1186,7 +1192,9 @@ int adam_step(mpn_ctx* c, cudaStream_t s, const float* grads, float lr, float be
                                                           sqrtf(bc2), clip_norm, t.norm);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
-  return refresh_transposes(c, s);
+  int r = refresh_transposes(c, s);
+  if (r) return r;
+  return tc_refresh_weights(c, s);   // bf16 operand copies of the tensor-core kernels (forward of the bf16 training mode, inference)
 }
 
 }  // namespace mpn
