@@ -197,7 +197,7 @@ int launch_groupnorm_lrelu_bf16(mpn_ctx* c, cudaStream_t s, float* x, int M, int
                                 __nv_bfloat16* out);
 // ---- gemm_tc.cu (epi: 0 relu->bf16, 1 fp32, 2 relu + max over each 128-row tile -> bf16)
 int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int K, const float* bias,
-                   int M, int N, void* C, int ldc);
+                   int M, int N, void* C, int ldc, uint8_t* arg_out = nullptr);
 int launch_step_update(mpn_ctx* c, cudaStream_t s, int B, const float* dq, float* qn, float* qu, const float* target,
                        int32_t* done, int early_exit, float* traj_out, int traj_stride, float* frames, float* eef,
                        float* metrics, int step);

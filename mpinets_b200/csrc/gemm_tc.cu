@@ -21,7 +21,7 @@
 namespace mpn {
 using namespace tc;
 
-enum { EPI_RELU_BF16 = 0, EPI_F32 = 1, EPI_MAXPOOL = 2 };
+enum { EPI_RELU_BF16 = 0, EPI_F32 = 1, EPI_MAXPOOL = 2, EPI_MAXPOOL_ARG = 3 };   // 3: max-pool + winning row per column (training)
 constexpr int G_BN = 256;
 
 __device__ __forceinline__ uint32_t cvt_relu_pack(float first, float second) {
@@ -45,7 +45,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
 template <int EPI>
 __global__ void __launch_bounds__(256, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int K, const float* __restrict__ bias,
-                int M, int N, void* __restrict__ Cout, int ldc, int* __restrict__ err) {
+                int M, int N, void* __restrict__ Cout, int ldc, int* __restrict__ err, uint8_t* __restrict__ arg_out) {
   extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles: 1024-byte aligned stage bases
   __shared__ uint64_t full[T_STAGES], empty[T_STAGES], accum;
   __shared__ uint32_t tmem_slot;
@@ -113,6 +113,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // row-per-thread writes and the row-per-warp reads are conflict-free, and leave as full 512-byte row segments.
   const int q = warp & 3, h = warp >> 2, row = q * 32 + (tid & 31);
   constexpr int ROW_CHUNKS = EPI == EPI_F32 ? 64 : 32;   // 16-byte chunks per 256-column output row
+  constexpr bool POOL = EPI == EPI_MAXPOOL || EPI == EPI_MAXPOOL_ARG;
 #pragma unroll 1
   for (int sub = 0; sub < 2; ++sub) {
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + sub * 256 + h * 128;
@@ -146,7 +147,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y, __uint_as_float(v[j + 2]) + bb.z,
                           __uint_as_float(v[j + 3]) + bb.w);
         }
-      } else {
+      } else {   // POOL
         int keep = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -159,13 +160,37 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     __syncthreads();
-    if (EPI == EPI_MAXPOOL) {
+    if (POOL) {
       const int prob = blockIdx.y * 2 + sub;
       if (prob * 128 < M) {
         const int mi = max(max(red[0][tid], red[1][tid]), max(red[2][tid], red[3][tid]));
         const int bits = mi >= 0 ? mi : (int)(0x80000000u - (uint32_t)mi);
+        const float pooled = fmaxf(__int_as_float(bits) + sbias[tid], 0.f);
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)prob * ldc + n0;
-        o[tid] = __float2bfloat16_rn(fmaxf(__int_as_float(bits) + sbias[tid], 0.f));
+        o[tid] = __float2bfloat16_rn(pooled);
+        if (EPI == EPI_MAXPOOL_ARG) { red[0][tid] = mi; red[1][tid] = pooled > 0.f; red[2][tid] = 255; }
+      }
+      if (EPI == EPI_MAXPOOL_ARG) {
+        // training forward: first row attaining the maximum of each live column (the accumulator is still in TMEM);
+        // columns pooled to 0 carry no gradient and report row 0
+        __syncthreads();
+        if (prob * 128 < M) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tl + c0, v);
+            tmem_ld_wait();
+            const int nl = h * 128 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              int bits = (int)v[j];
+              bits = bits >= 0 ? bits : (int)(0x80000000u - (uint32_t)bits);
+              if (m < M && red[1][nl + j] && bits == red[0][nl + j]) atomicMin(&red[2][nl + j], row);
+            }
+          }
+        }
+        __syncthreads();
+        if (prob * 128 < M) arg_out[(size_t)prob * N + n0 + tid] = (uint8_t)(red[2][tid] > 127 ? 0 : red[2][tid]);
       }
     } else {
       // warp w streams rows w, w + 8, ... of this 128-row sub-tile: one row = ROW_CHUNKS x 16 B, a lane per chunk
@@ -222,9 +247,10 @@ static int make_tmap(CUtensorMap* tm, const __nv_bfloat16* base, int rows, int K
 int* tc_error_flag(mpn_ctx* c);
 
 int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int K, const float* bias,
-                   int M, int N, void* C, int ldc) {
+                   int M, int N, void* C, int ldc, uint8_t* arg_out) {
   MPN_REQUIRE(K % 16 == 0 && N % G_BN == 0 && lda % 8 == 0, "gemm_tc: K %% 16, N %% 256, lda %% 8 required (K=%d N=%d lda=%d)", K, N, lda);
-  MPN_REQUIRE(epi != EPI_MAXPOOL || M % 128 == 0, "gemm_tc: max-pool epilogue needs M %% 128 == 0");
+  MPN_REQUIRE((epi != EPI_MAXPOOL && epi != EPI_MAXPOOL_ARG) || M % 128 == 0, "gemm_tc: max-pool epilogue needs M %% 128 == 0");
+  MPN_REQUIRE(epi != EPI_MAXPOOL_ARG || arg_out, "gemm_tc: the winning-row epilogue needs an output buffer");
   MPN_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm_tc: operands must be 16-byte aligned");
   CUtensorMap tmA, tmW;
   int r;
@@ -236,10 +262,11 @@ int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, 
 #define GEMM_TMA(E)                                                                                                       \
   do {                                                                                                                    \
     MPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));   \
-    gemm_tma_kernel<E><<<grid_t, 256, smem_t, s>>>(tmA, tmW, K, bias, M, N, C, ldc, errf);                                \
+    gemm_tma_kernel<E><<<grid_t, 256, smem_t, s>>>(tmA, tmW, K, bias, M, N, C, ldc, errf, arg_out);                                \
   } while (0)
   if (epi == EPI_RELU_BF16) GEMM_TMA(EPI_RELU_BF16);
   else if (epi == EPI_F32) GEMM_TMA(EPI_F32);
+  else if (epi == EPI_MAXPOOL_ARG) GEMM_TMA(EPI_MAXPOOL_ARG);
   else GEMM_TMA(EPI_MAXPOOL);
 #undef GEMM_TMA
   c->launches++;

@@ -817,24 +817,36 @@ int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int 
   return MPN_OK;
 }
 
-// SA1 + SA2 forward of the bf16 training step through the fused inference kernels (ARG variants): besides the pooled features
-// they record the ball-query indices and the winning neighbour row of every (group, channel) -- the routing the backward replays.
-// Outputs in the training step's formats: feat1 f32 [B][512][64], feat2 f32 [B][128][256], ball1 / ball2 i32, arg1 / arg2 u8.
+// Point-cloud encoder forward (SA1, SA2, group-all SA3) of the bf16 training step through the inference kernels' ARG variants:
+// besides the pooled features they record the ball-query indices and the winning neighbour row of every (group, channel) --
+// the routing the backward replays.  Outputs in the training step's formats: feat1 f32 [B][512][64], feat2 f32 [B][128][256],
+// feat3 f32 [B][1024], ball1 / ball2 i32, arg1 / arg2 / arg3 u8.
 int tc_train_forward_sa(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, int32_t* fps_idx, float* xyz1, float* xyz2,
-                        float* feat1_f32, float* feat2_f32, int32_t* ball1, int32_t* ball2, uint8_t* arg1, uint8_t* arg2) {
+                        float* feat1_f32, float* feat2_f32, float* feat3_f32, int32_t* ball1, int32_t* ball2, uint8_t* arg1,
+                        uint8_t* arg2, uint8_t* arg3) {
   Workspace& w = c->ws;
   MPN_REQUIRE(B <= w.capacity, "tc_train_forward_sa: batch %d exceeds the workspace capacity %d", B, w.capacity);
   __nv_bfloat16* feat1 = reinterpret_cast<__nv_bfloat16*>(w.tc_scratch);
   __nv_bfloat16* a3 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w.tc_scratch) + feat1_bytes(w.capacity));
+  uint8_t* base = reinterpret_cast<uint8_t*>(w.tc_scratch) + feat1_bytes(w.capacity) + a3_bytes(w.capacity);
+  __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(base + h_bytes(w.capacity));
+  __nv_bfloat16* f3 = reinterpret_cast<__nv_bfloat16*>(base + 2 * h_bytes(w.capacity));
+  TcWeights& tw = g_tc[c];
   int r;
   if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, fps_idx, xyz1))) return r;
   if ((r = launch_sa_tc<0>(c, s, cloud, 4, N, nullptr, xyz1, B, feat1, 64, ball1, arg1))) return r;
   if ((r = launch_fps(c, s, xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, fps_idx, xyz2))) return r;
   if ((r = launch_sa_tc<1>(c, s, xyz1, 3, SA1_NPOINT, feat1, xyz2, B, a3, A3_K, ball2, arg2))) return r;
-  const size_t n1 = (size_t)B * SA1_NPOINT * 64, n2 = (size_t)B * SA2_NPOINT * 256;
+  const int M3 = B * SA2_NPOINT;
+  if ((r = launch_gemm_tc(c, s, 0, a3, A3_K, tw.sa[2][0], A3_K, c->w.sa[2][0].b, M3, 512, h1, 512))) return r;
+  if ((r = launch_gemm_tc(c, s, 0, h1, 512, tw.sa[2][1], 512, c->w.sa[2][1].b, M3, 512, h2, 512))) return r;
+  if ((r = launch_gemm_tc(c, s, 3, h2, 512, tw.sa[2][2], 512, c->w.sa[2][2].b, M3, 1024, f3, 1024, arg3))) return r;
+  const size_t n1 = (size_t)B * SA1_NPOINT * 64, n2 = (size_t)B * SA2_NPOINT * 256, n3 = (size_t)B * 1024;
   widen_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(feat1, B * SA1_NPOINT, 64, 64, feat1_f32);
   widen_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(a3, B * SA2_NPOINT, A3_K, 256, feat2_f32);
-  c->launches += 2;
+  widen_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(f3, B, 1024, 1024, feat3_f32);
+  c->launches += 3;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
 }

@@ -784,7 +784,8 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
 // ---------------------------------------------------------------------------------------------- forward (saves state)
 int pack_w(mpn_ctx* c, cudaStream_t s, const float* src, int rows, int cols, int ld, int mode, int dst_rows, __nv_bfloat16* dst);
 int tc_train_forward_sa(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, int32_t* fps_idx, float* xyz1, float* xyz2,
-                        float* feat1_f32, float* feat2_f32, int32_t* ball1, int32_t* ball2, uint8_t* arg1, uint8_t* arg2);
+                        float* feat1_f32, float* feat2_f32, float* feat3_f32, int32_t* ball1, int32_t* ball2, uint8_t* arg1,
+                        uint8_t* arg2, uint8_t* arg3);
 int tc_refresh_weights(mpn_ctx* c, cudaStream_t s);
 
 // SA1 / SA2 forward of the bf16 training mode: ball query -> gather ALL 128 neighbour rows per group -> the three layers as
@@ -804,7 +805,8 @@ static int train_forward_sa_tc(mpn_ctx* c, cudaStream_t s, const float* cloud, i
   int r;
   static const bool rows_fwd = getenv("MPN_TRAIN_ROWS_FWD") != nullptr;   // A/B switch: the row-GEMM forward below
   if (!rows_fwd)
-    return tc_train_forward_sa(c, s, cloud, B, N, t.fps_idx, w.xyz1, w.xyz2, w.feat1, w.feat2, t.ball1, t.ball2, t.arg1, t.arg2);
+    return tc_train_forward_sa(c, s, cloud, B, N, t.fps_idx, w.xyz1, w.xyz2, w.feat1, w.feat2, w.feat3, t.ball1, t.ball2, t.arg1, t.arg2,
+                               t.arg3);
   // ---- SA1
   if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, t.fps_idx, w.xyz1))) return r;
   if ((r = launch_ball_query(c, s, SA1_RADIUS, NSAMPLE, cloud, B, N, 4, w.xyz1, SA1_NPOINT, t.ball1))) return r;
@@ -852,7 +854,7 @@ static int train_forward_sa_tc(mpn_ctx* c, cudaStream_t s, const float* cloud, i
                                    t.arg2 + (size_t)b0 * SA2_NPOINT * 256, 0))) return r;
     }
   }
-  return MPN_OK;
+  return launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr, t.arg3);
 }
 
 static int train_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, const float* qn, int B, int N, bool tcp) {
@@ -869,7 +871,7 @@ static int train_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, const f
     if ((r = launch_fps(c, s, w.xyz1, B, SA1_NPOINT, 3, SA2_NPOINT, t.fps_idx, w.xyz2))) return r;
     if ((r = launch_sa_simt(c, s, 1, w.xyz1, 3, w.feat1, 64, B, SA1_NPOINT, w.xyz2, w.feat2, t.ball2, t.arg2))) return r;
   }
-  if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr, t.arg3))) return r;
+  if (!tcp && (r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr, t.arg3))) return r;
   if ((r = launch_linear(c, s, W.fc[0], w.feat3, 1024, B, t.z1, 4096, 0))) return r;
   if ((r = launch_groupnorm_lrelu_train(c, s, t.z1, B, 4096, 16, W.gn_w[0], W.gn_b[0], t.a1, t.st1))) return r;
   if ((r = launch_linear(c, s, W.fc[1], t.a1, 4096, B, t.z2, 2048, 0))) return r;

