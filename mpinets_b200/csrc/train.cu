@@ -289,16 +289,27 @@ __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat16
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The group's activations H2 are staged RAW (bf16 in the tensor-core mode) by 16-byte cp.async; in the bf16 mode they are
+// double-buffered, so the next group's 32 KB arrive while this group is processed (ncu before this change: half of the
+// kernel's stall samples sat on the scalar 2-byte loads of this stage and on the barrier behind them, at one CTA per SM).
 template <int C2, int C3, int SLOTS, typename T>
 __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict__ geff, const uint8_t* __restrict__ slot_of_ch,
                                                         const float* __restrict__ W3, T* __restrict__ H2, int G,
                                                         float* __restrict__ pW, float* __restrict__ pb) {
   constexpr int NT = 512, Q = NT / C2, CPT = C3 / Q, PER = SLOTS / 32;
+  constexpr int NBUF = sizeof(T) == 2 ? 2 : 1, CHUNKS = SLOTS * C2 * (int)sizeof(T) / 16;
   static_assert(NT % C2 == 0 && C3 % Q == 0 && SLOTS % 32 == 0 && SLOTS <= 128 && C3 <= NT, "layout");
   extern __shared__ __align__(16) float sm[];
   float* W3s = sm;                                  // [C3][C2]
-  float* Hs = W3s + C3 * C2;                        // [SLOTS][C2]
-  float* gs = Hs + SLOTS * C2;                      // [C3]
+  T* Hbuf = reinterpret_cast<T*>(W3s + C3 * C2);    // [NBUF][SLOTS][C2] raw
+  float* gs = reinterpret_cast<float*>(Hbuf + (size_t)NBUF * SLOTS * C2);   // [C3]
   int* sl = reinterpret_cast<int*>(gs + C3);        // [C3]
   int* cnt = sl + C3;                               // [SLOTS]
   int* start = cnt + SLOTS;                         // [SLOTS + 1]
@@ -309,14 +320,30 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
   for (int i = 0; i < CPT; ++i) accW[i] = 0.f;
   float accb = 0.f;
   for (int i = tid; i < C3 * C2; i += NT) W3s[i] = W3[i];
-  for (int grp = blockIdx.x; grp < G; grp += gridDim.x) {
+  auto stage = [&](int grp, int buf) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(H2 + (size_t)grp * SLOTS * C2);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(Hbuf + (size_t)buf * SLOTS * C2);
+    for (int i = tid; i < CHUNKS; i += NT) cp_async16(dst + (size_t)i * 16, src + (size_t)i * 16);
+    cp_async_commit();
+  };
+  if (NBUF == 2 && (int)blockIdx.x < G) stage(blockIdx.x, 0);
+  int it = 0;
+  for (int grp = blockIdx.x; grp < G; grp += gridDim.x, ++it) {
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    const T* Hs = Hbuf + (size_t)buf * SLOTS * C2;
     __syncthreads();
     for (int c = tid; c < C3; c += NT) {
       gs[c] = geff[(size_t)grp * C3 + c];
       sl[c] = slot_of_ch[(size_t)grp * C3 + c];
     }
     T* Hg = H2 + (size_t)grp * SLOTS * C2;
-    for (int i = tid; i < SLOTS * C2; i += NT) Hs[i] = ldf(Hg + i);
+    if (NBUF == 2) {
+      const int next = grp + gridDim.x;
+      if (next < G) { stage(next, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    } else {
+      stage(grp, 0);
+      cp_async_wait<0>();
+    }
     __syncthreads();
     // channel lists per slot, in channel order (deterministic)
     if (tid < SLOTS) {
@@ -355,14 +382,14 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
         const int c = chl[e];
         a = fmaf(gs[c], W3s[c * C2 + j], a);
       }
-      stf(Hg + (size_t)s * C2 + j, Hs[s * C2 + j] > 0.f ? a : 0.f);
+      stf(Hg + (size_t)s * C2 + j, ldf(Hs + s * C2 + j) > 0.f ? a : 0.f);
     }
     // dW3[c] += g_c H2[slot_c]
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
       const int c = q * CPT + i;
       const int s = sl[c];
-      if (s != 255) accW[i] = fmaf(gs[c], Hs[s * C2 + j], accW[i]);
+      if (s != 255) accW[i] = fmaf(gs[c], ldf(Hs + s * C2 + j), accW[i]);
     }
     if (tid < C3) accb += gs[tid];
   }
@@ -906,7 +933,7 @@ static int launch_sa_l3(mpn_ctx* c, cudaStream_t s, const float* geff, const uin
                         float* grads) {
   TrainWs& t = c->tw;
   auto k = sa_l3_bwd_kernel<C2, C3, SLOTS, T>;
-  const size_t smem = (size_t)(C3 * C2 + SLOTS * C2 + C3) * 4 + (size_t)(C3 + SLOTS + SLOTS + 1 + C3) * 4;
+  const size_t smem = (size_t)(C3 * C2 + C3) * 4 + (size_t)(sizeof(T) == 2 ? 2 : 1) * SLOTS * C2 * sizeof(T) + (size_t)(C3 + SLOTS + SLOTS + 1 + C3) * 4 + 16;
   MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = smem > 100 * 1024 ? 1 : 2;
   int grid = std::min(G, c->sm_count * per_sm);
