@@ -304,15 +304,15 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
                                                         const float* __restrict__ W3, T* __restrict__ H2, int G,
                                                         float* __restrict__ pW, float* __restrict__ pb) {
   constexpr int NT = 512, Q = NT / C2, CPT = C3 / Q, PER = SLOTS / 32;
-  constexpr int NBUF = sizeof(T) == 2 ? 2 : 1, CHUNKS = SLOTS * C2 * (int)sizeof(T) / 16;
-  static_assert(NT % C2 == 0 && C3 % Q == 0 && SLOTS % 32 == 0 && SLOTS <= 128 && C3 <= NT, "layout");
+  constexpr int NBUF = sizeof(T) == 2 ? 2 : 1, CHUNKS = SLOTS * C2 * (int)sizeof(T) / 16, PARTS = NT / SLOTS, CPP = C3 / PARTS;
+  static_assert(NT % C2 == 0 && C3 % Q == 0 && SLOTS % 32 == 0 && SLOTS <= 128 && C3 <= NT && NT % SLOTS == 0 && C3 % PARTS == 0, "layout");
   extern __shared__ __align__(16) float sm[];
   float* W3s = sm;                                  // [C3][C2]
   T* Hbuf = reinterpret_cast<T*>(W3s + C3 * C2);    // [NBUF][SLOTS][C2] raw
   float* gs = reinterpret_cast<float*>(Hbuf + (size_t)NBUF * SLOTS * C2);   // [C3]
   int* sl = reinterpret_cast<int*>(gs + C3);        // [C3]
-  int* cnt = sl + C3;                               // [SLOTS]
-  int* start = cnt + SLOTS;                         // [SLOTS + 1]
+  int* cnt = sl + C3;                               // [PARTS][SLOTS]
+  int* start = cnt + NT;                            // [SLOTS + 1]
   int* chl = start + SLOTS + 1;                     // [C3]
   const int tid = threadIdx.x, j = tid % C2, q = tid / C2;
   float accW[CPT];
@@ -345,17 +345,24 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
       cp_async_wait<0>();
     }
     __syncthreads();
-    // channel lists per slot, in channel order (deterministic)
-    if (tid < SLOTS) {
+    // channel lists per slot, in channel order (deterministic): thread (slot, part) scans its share of the channels
+    {
+      const int ls = tid % SLOTS, part = tid / SLOTS;
       int n = 0;
-      for (int c = 0; c < C3; ++c) n += (sl[c] == tid) ? 1 : 0;
-      cnt[tid] = n;
+#pragma unroll 8
+      for (int c = part * CPP; c < (part + 1) * CPP; ++c) n += (sl[c] == ls) ? 1 : 0;
+      cnt[part * SLOTS + ls] = n;
     }
     __syncthreads();
     if (tid < 32) {
       int loc[PER], sum = 0;
 #pragma unroll
-      for (int u = 0; u < PER; ++u) { loc[u] = cnt[tid * PER + u]; sum += loc[u]; }
+      for (int u = 0; u < PER; ++u) {
+        int tot = 0;
+#pragma unroll
+        for (int pp = 0; pp < PARTS; ++pp) tot += cnt[pp * SLOTS + tid * PER + u];
+        loc[u] = tot; sum += tot;
+      }
       int incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -368,10 +375,13 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
       if (tid == 31) start[SLOTS] = incl;
     }
     __syncthreads();
-    if (tid < SLOTS) {
-      int p = start[tid];
-      for (int c = 0; c < C3; ++c)
-        if (sl[c] == tid) chl[p++] = c;
+    {
+      const int ls = tid % SLOTS, part = tid / SLOTS;
+      int p = start[ls];
+      for (int pp = 0; pp < part; ++pp) p += cnt[pp * SLOTS + ls];
+#pragma unroll 8
+      for (int c = part * CPP; c < (part + 1) * CPP; ++c)
+        if (sl[c] == ls) chl[p++] = c;
     }
     __syncthreads();
     // dZ2[slot] = (sum over the slot's channels of g_c W3[c]) masked by ReLU
@@ -933,7 +943,7 @@ static int launch_sa_l3(mpn_ctx* c, cudaStream_t s, const float* geff, const uin
                         float* grads) {
   TrainWs& t = c->tw;
   auto k = sa_l3_bwd_kernel<C2, C3, SLOTS, T>;
-  const size_t smem = (size_t)(C3 * C2 + C3) * 4 + (size_t)(sizeof(T) == 2 ? 2 : 1) * SLOTS * C2 * sizeof(T) + (size_t)(C3 + SLOTS + SLOTS + 1 + C3) * 4 + 16;
+  const size_t smem = (size_t)(C3 * C2 + C3) * 4 + (size_t)(sizeof(T) == 2 ? 2 : 1) * SLOTS * C2 * sizeof(T) + (size_t)(C3 + 512 + SLOTS + 1 + C3) * 4 + 16;
   MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = smem > 100 * 1024 ? 1 : 2;
   int grid = std::min(G, c->sm_count * per_sm);
