@@ -101,6 +101,8 @@ struct TrainWs {
   float* partial = nullptr; size_t partial_floats = 0;   // split-reduction partials of the weight-gradient kernels
   __nv_bfloat16* tcw = nullptr; float* b2dup = nullptr;  // bf16 weight tiles of the tensor-core backward (rebuilt per step)
   float* adam_m = nullptr; float* adam_v = nullptr; float* norm = nullptr;
+  // bf16 mode: hidden activations of the group-all level saved by the forward GEMMs, [B*128][512] each (null in the fp32 mode)
+  const __nv_bfloat16 *sa3_h1 = nullptr, *sa3_h2 = nullptr;
 };
 
 }  // namespace mpn

@@ -848,6 +848,8 @@ int tc_train_forward_sa(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, i
   widen_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(f3, B, 1024, 1024, feat3_f32);
   c->launches += 3;
   MPN_CHECK_CUDA(cudaGetLastError());
+  c->tw.sa3_h1 = h1;   // the SA3 backward reads them instead of recomputing layers 1-2
+  c->tw.sa3_h2 = h2;
   return MPN_OK;
 }
 

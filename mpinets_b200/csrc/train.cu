@@ -258,6 +258,29 @@ __global__ void __launch_bounds__(256) sa_prepare_kernel(const uint8_t* __restri
   }
 }
 
+// Group-all level with saved activations (bf16 mode): rows keep their natural order, so slot = pooled row and src = row.
+__global__ void __launch_bounds__(256) sa3_identity_prepare_kernel(const uint8_t* __restrict__ arg, float* __restrict__ g,
+                                                                   const float* __restrict__ out, int G, uint8_t* __restrict__ slot_of_ch,
+                                                                   int32_t* __restrict__ src) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)G * 128) src[i] = (int32_t)(i & 127);
+  if (i >= (size_t)G * 1024) return;
+  const bool act = g[i] != 0.f && out[i] > 0.f;
+  if (!act) g[i] = 0.f;
+  slot_of_ch[i] = act ? (uint8_t)(arg[i] & 127) : (uint8_t)255;
+}
+__global__ void __launch_bounds__(256) widen_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long n, float* __restrict__ dst) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { o[2 * k] = __uint_as_float(w[k] << 16); o[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u); }
+  *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(dst + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+
 // X[row][:] = [p[src] - centroid | features[src] | 0-pad]; empty slots -> zero rows
 template <int CFEAT, int CINP, bool CENTER>
 __global__ void __launch_bounds__(256) sa_gather_kernel(const int32_t* __restrict__ src, long long R, int slots, int npoint,
@@ -900,6 +923,7 @@ static int train_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, const f
   const Weights& W = c->w;
   const int CAT = ENC_DIM + QF_DIM;
   int r;
+  t.sa3_h1 = t.sa3_h2 = nullptr;
   if (tcp) {
     if ((r = train_forward_sa_tc(c, s, cloud, B, N))) return r;
   } else {
@@ -978,11 +1002,13 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
   const uint8_t* arg_c = arg + (size_t)b0 * npoint * C3;
   float* g_c = g + (size_t)b0 * npoint * C3;
   const float* out_c = out + (size_t)b0 * npoint * C3;
+  const bool saved = m == 2 && t.sa3_h1 && t.sa3_h2;   // bf16 mode: the forward kept the group-all level's hidden activations
   // 1. active rows -> slots
   {
     const int grid = (G + 7) / 8;
     if (m == 0) sa_prepare_kernel<64, 64><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
     else if (m == 1) sa_prepare_kernel<256, 128><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
+    else if (saved) sa3_identity_prepare_kernel<<<(unsigned)(((size_t)G * 1024 + 255) / 256), 256, 0, s>>>(arg_c, g_c, out_c, G, t.slot, t.src);
     else sa_prepare_kernel<1024, 128><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, nullptr, G, t.slot, t.src);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
@@ -997,8 +1023,17 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
   }
-  if ((r = launch_linear_ex(c, s, t.X, CINP[m], L[0].w, CIN, L[0].b, R, C1, CIN, t.H1, C1, 2))) return r;
-  if ((r = launch_linear_ex(c, s, t.H1, C1, L[1].w, C1, L[1].b, R, C2, C1, t.H2, C2, 2))) return r;
+  if (saved) {
+    const long long n = R * 512;
+    const unsigned grid = (unsigned)((n / 8 + 255) / 256);
+    widen_bf16_kernel<<<grid, 256, 0, s>>>(t.sa3_h1 + (size_t)b0 * SA2_NPOINT * 512, n, t.H1);
+    widen_bf16_kernel<<<grid, 256, 0, s>>>(t.sa3_h2 + (size_t)b0 * SA2_NPOINT * 512, n, t.H2);
+    c->launches += 2;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  } else {
+    if ((r = launch_linear_ex(c, s, t.X, CINP[m], L[0].w, CIN, L[0].b, R, C1, CIN, t.H1, C1, 2))) return r;
+    if ((r = launch_linear_ex(c, s, t.H1, C1, L[1].w, C1, L[1].b, R, C2, C1, t.H2, C2, 2))) return r;
+  }
   // 3. layer 3 (sparse): H2 <- dZ2, gW3 / gb3
   if (m == 0) {
     if ((r = launch_sa_l3<64, 64, 64, float>(c, s, g_c, t.slot, L[2], t.H2, G, grads))) return r;
