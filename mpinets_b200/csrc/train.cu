@@ -281,6 +281,29 @@ __global__ void __launch_bounds__(256) widen_bf16_kernel(const __nv_bfloat16* __
   *reinterpret_cast<float4*>(dst + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
 }
 
+__global__ void __launch_bounds__(256) pack_weight_kernel_f32(const float* __restrict__ src, int n, __nv_bfloat16* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void __launch_bounds__(256) narrow_bf16_kernel(const float* __restrict__ src, long long n, __nv_bfloat16* __restrict__ dst) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w), p2 = __floats2bfloat162_rn(b.x, b.y),
+                 p3 = __floats2bfloat162_rn(b.z, b.w);
+  *reinterpret_cast<uint4*>(dst + i) = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                                  *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+}
+// act[i] = act[i] > 0 ? g[i] : 0   (ReLU derivative applied to a data gradient, in place over the activation)
+__global__ void __launch_bounds__(256) relu_mask_kernel(float* __restrict__ act, const float* __restrict__ g, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 a = *reinterpret_cast<float4*>(act + i);
+  const float4 v = *reinterpret_cast<const float4*>(g + i);
+  a.x = a.x > 0.f ? v.x : 0.f; a.y = a.y > 0.f ? v.y : 0.f; a.z = a.z > 0.f ? v.z : 0.f; a.w = a.w > 0.f ? v.w : 0.f;
+  *reinterpret_cast<float4*>(act + i) = a;
+}
+
 // X[row][:] = [p[src] - centroid | features[src] | 0-pad]; empty slots -> zero rows
 template <int CFEAT, int CINP, bool CENTER>
 __global__ void __launch_bounds__(256) sa_gather_kernel(const int32_t* __restrict__ src, long long R, int slots, int npoint,
@@ -832,8 +855,9 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
   r |= talloc(&t.H2, k * SA2_NPOINT * 128 * 128);
   r |= talloc(&t.src, k * SA1_NPOINT * 64);
   r |= talloc(&t.slot, k * SA1_NPOINT * 64);
-  r |= talloc(&t.tcw, (size_t)8 * 128 * 128);
-  r |= talloc(&t.b2dup, (size_t)256);
+  r |= talloc(&t.tcw, (size_t)8 * 128 * 128 + 512 * 512 + 256 * 512);   // + transposed bf16 tiles of SA3 layers 2 / 1 (data gradients)
+  r |= talloc(&t.b2dup, (size_t)256 + 512);                              // + 512 zeros (bias of the data-gradient GEMMs)
+  if (!r) cudaMemset(t.b2dup, 0, (256 + 512) * sizeof(float));
   t.partial_floats = (size_t)20 << 20;   // >= the largest single weight tensor (fc_layer.3: 8.4 M) + bias
   r |= talloc(&t.partial, t.partial_floats);
   if (r) { free_train_ws(c); return MPN_ERR_NOMEM; }
@@ -1055,14 +1079,43 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
   }
   // 4. layer 2: gW2 += dZ2^T H1 ; dZ1 = (dZ2 W2) * relu'(H1), in place over H1
   if ((r = wgrad(c, s, t.H2, C2, t.H1, C1, R, C2, C1, gw(c, grads, L[1]), gbias(c, grads, L[1])))) return r;
-  if ((r = launch_linear_ex(c, s, t.H2, C2, L[1].wt, C2, nullptr, R, C1, C2, t.H1, C1, 0, t.H1, C1, 2))) return r;
+  // bf16 mode, group-all level: the two data-gradient GEMMs (R x 512 x 512, R x 256 x 512) run on the TMA / tcgen05 GEMM with
+  // transposed bf16 weight tiles; the saved activations' slots in the forward scratch hold the bf16 operands
+  __nv_bfloat16* w2t = t.tcw + 8 * 128 * 128;
+  __nv_bfloat16* w1t = w2t + 512 * 512;
+  const float* zero_bias = t.b2dup + 256;
+  if (saved) {
+    __nv_bfloat16* dz_bf = const_cast<__nv_bfloat16*>(t.sa3_h2) + (size_t)b0 * SA2_NPOINT * 512;
+    const long long n = R * 512;
+    if (b0 == 0) {   // once per step: W2^T [in][out] and the feature rows of W1^T as K-major bf16
+      pack_weight_kernel_f32<<<(512 * 512 + 255) / 256, 256, 0, s>>>(L[1].wt, 512 * 512, w2t);
+      pack_weight_kernel_f32<<<(256 * 512 + 255) / 256, 256, 0, s>>>(L[0].wt + (size_t)3 * C1, 256 * 512, w1t);
+      c->launches += 2;
+    }
+    narrow_bf16_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, s>>>(t.H2, n, dz_bf);
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    if ((r = launch_gemm_tc(c, s, 1, dz_bf, 512, w2t, 512, zero_bias, (int)R, 512, t.H2, 512))) return r;   // dZ2 W2 -> H2 (fp32)
+    relu_mask_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(t.H1, t.H2, n);                            // dZ1 over H1
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+  } else {
+    if ((r = launch_linear_ex(c, s, t.H2, C2, L[1].wt, C2, nullptr, R, C1, C2, t.H1, C1, 0, t.H1, C1, 2))) return r;
+  }
   //    layer 1: gW1 += dZ1^T X
   if ((r = wgrad(c, s, t.H1, C1, t.X, CINP[m], R, C1, CIN, gw(c, grads, L[0]), gbias(c, grads, L[0])))) return r;
   // 5. feature part of dX = dZ1 W1[:, 3:]  ->  previous level's feature gradient
   if (m == 2) {
     float* dst = dfeat_prev + (size_t)b0 * SA2_NPOINT * 256;   // group-all: rows are the SA2 centroids themselves
     // empty slots do not occur here only if every row is active; rows are addressed through src, so scatter (no collisions)
-    if ((r = launch_linear_ex(c, s, t.H1, C1, L[0].wt + (size_t)3 * C1, C1, nullptr, R, CFEAT[m], C1, t.H2, CFEAT[m], 0))) return r;
+    if (saved) {
+      __nv_bfloat16* dz1_bf = const_cast<__nv_bfloat16*>(t.sa3_h1) + (size_t)b0 * SA2_NPOINT * 512;
+      const long long n = R * 512;
+      narrow_bf16_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, s>>>(t.H1, n, dz1_bf);
+      c->launches++;
+      MPN_CHECK_CUDA(cudaGetLastError());
+      if ((r = launch_gemm_tc(c, s, 1, dz1_bf, 512, w1t, 512, zero_bias, (int)R, 256, t.H2, 256))) return r;
+    } else if ((r = launch_linear_ex(c, s, t.H1, C1, L[0].wt + (size_t)3 * C1, C1, nullptr, R, CFEAT[m], C1, t.H2, CFEAT[m], 0))) return r;
     const long long n = R * CFEAT[m];
     sa_scatter_add_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t.H2, t.src, R, slots, npoint, SA2_NPOINT, CFEAT[m], dst);
     c->launches++;
