@@ -509,6 +509,11 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
   const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
   const uint64_t dX = tile_desc(smem_u32(X), SA1_XK, 0, 0), dW1 = tile_desc(smem_u32(sW1), SA1_XK, 0, 0);
   const uint64_t dW2 = tile_desc(smem_u32(sW2), SA1_XK, 0, 0), dW3 = tile_desc(smem_u32(sW3), SA1_XK, 0, 0);
+  // layer 1 as ONE K = 16 MMA: its two core matrices along K are chunk 0 (dx dy dz w) and chunk 8 (the ones column that carries
+  // the bias) -- a leading-dimension byte offset of 8 chunks instead of 1.  Saves the zero chunk, a second MMA and their
+  // shared-memory traffic (the kernel is bound by shared-memory bandwidth: operand reads of the N = 64 MMAs + epilogue stores)
+  const uint64_t dX1 = make_smem_desc(smem_u32(X), 8 * 128, KC * 128, LAYOUT_NONE);
+  const uint64_t dW1k = make_smem_desc(smem_u32(sW1), 8 * 128, KC * 128, LAYOUT_NONE);
   uint64_t* bar = &bars[g];
   uint32_t phase = 0;
   bool ok = true;
@@ -590,8 +595,7 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
       tc_fence_after();
       if (elect_one()) {
         if (first_layer) {
-          mma_bf16_ss_off(tmem, dX, 0, dW, 0, IDESC, 0);
-          mma_bf16_ss_off(tmem, dX, 64, dW, 64, IDESC, 1);
+          mma_bf16_ss_off(tmem, dX1, 0, dW1k, 0, IDESC, 0);
         } else {
 #pragma unroll
           for (int ks = 0; ks < SA1_XK / 16; ++ks) mma_bf16_ss_off(tmem, dX, ks * 16, dW, ks * 16, IDESC, ks > 0);
@@ -621,7 +625,6 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
       {
         const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
         *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 0, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u);
-        *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 1, KC)) = make_uint4(0u, 0u, 0u, 0u);
       }
       fence_proxy_async_smem();
       tc_fence_before();
