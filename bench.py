@@ -142,7 +142,11 @@ def run_reference(args):
 
 
 def main():
-    os.environ["NCCL_DEBUG"] = os.environ.get("MPN_NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
+    # keep stdout to the single JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION / WARN / INFO
+    os.environ.pop("NCCL_DEBUG", None)
+    if os.environ.get("MPN_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["MPN_NCCL_DEBUG"]
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mpn_nccl_%h_%p.log")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

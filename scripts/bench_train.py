@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--samples-per-gpu", type=int, default=1024)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     args = ap.parse_args()
+    os.environ.pop("NCCL_DEBUG", None)   # NCCL's version banner goes to stdout; keep it to the JSON line
     import torch
     import torch.distributed as dist
     from mpinets_b200 import scenes, _lib
