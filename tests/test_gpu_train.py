@@ -213,7 +213,8 @@ def test_validation_step_matches_oracle(oracle, tables, state_dict):
 def test_train_step_grads_bf16_mode(engine_w, oracle, tables, state_dict):
     """MPN_PREC_BF16 training (the counterpart of the reference's precision=16 autocast): the point-cloud encoder's forward runs
     through the fused tensor-core kernels (SA1 / SA2 / group-all SA3 with winning-row outputs), the SA1 / SA2 backward GEMMs on
-    tcgen05 with bf16 operands and fp32 accumulation; FC head / heads / SA3 backward stay fp32.
+    tcgen05 with bf16 operands and fp32 accumulation, SA3's data-gradient GEMMs on the TMA GEMM; FC head / heads / weight gradients
+    of SA3 stay fp32.
       * forward: y_hat within 5e-3 of the fp32 mode (|y| <= 1);
       * routing: the pooled rows hold the oracle's maximum to bf16 accuracy (gap <= 3e-2 |max| + 1e-3);
       * gradients vs the float64 oracle replaying that routing.  The oracle's forward is exact, the device's carries bf16
