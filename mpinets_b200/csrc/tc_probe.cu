@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const __nv_bfloat16* __re
   const int warp = threadIdx.x >> 5;
   uint8_t* sA = smem;
   uint8_t* sB = smem + 128 * K * 2;
-  probe_stage(A, 128, K, sA, mode);
-  probe_stage(B, N, K, sB, mode);
+  probe_stage(A, 128, K, sA, mode == 4 ? 0 : mode);
+  probe_stage(B, N, K, sB, mode == 4 ? 0 : mode);
   if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
   fence_proxy_async_smem();
@@ -53,10 +53,25 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const __nv_bfloat16* __re
   long long t1 = clock64();
   __syncthreads();
   long long t2 = clock64();
+  if (mode == 4) {
+    // A from tensor memory: thread = row writes its K bf16 values (two per column) to columns 128.. of its lane
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(A + (size_t)threadIdx.x * K);
+    for (int c0 = 0; c0 < K / 2; c0 += 8) {
+      uint32_t v[8];
+      for (int j = 0; j < 8; ++j) v[j] = arow[c0 + j];
+      tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + 128 + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc_bf16(128, N);
-    for (int ks = 0; ks < K / 16; ++ks)
-      mma_bf16_ss(tmem, probe_desc(smem_u32(sA), 128, K, ks, mode), probe_desc(smem_u32(sB), N, K, ks, mode), idesc, ks > 0);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      if (mode == 4) mma_bf16_ts(tmem, tmem + 128 + ks * 8, probe_desc(smem_u32(sB), N, K, ks, 0), idesc, ks > 0);
+      else mma_bf16_ss(tmem, probe_desc(smem_u32(sA), 128, K, ks, mode), probe_desc(smem_u32(sB), N, K, ks, mode), idesc, ks > 0);
+    }
     mma_commit(&bar);
   }
   long long t3 = clock64();
@@ -72,7 +87,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const __nv_bfloat16* __re
     long long t6 = clock64();
     // second round trip: one more MMA + commit + wait (steady state, barrier phase 1)
     if (threadIdx.x == 0 && lat) {
-      mma_bf16_ss(tmem, probe_desc(smem_u32(sA), 128, K, 0, mode), probe_desc(smem_u32(sB), N, K, 0, mode),
+      mma_bf16_ss(tmem, probe_desc(smem_u32(sA), 128, K, 0, mode == 4 ? 0 : mode), probe_desc(smem_u32(sB), N, K, 0, mode == 4 ? 0 : mode),
                   make_idesc_bf16(128, N), 1);
       mma_commit(&bar);
     }
@@ -105,7 +120,8 @@ int tc_probe(mpn_ctx* c, cudaStream_t s, const void* A, const void* B, float* D,
   float* lat = nullptr;
   if (mode & 0x100) { lat = D + (size_t)128 * N; mode &= 0xff; }   // latency run: D must have 16 extra floats
   MPN_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 64 == 0 && K <= 256, "tc_probe: N in 16..256 (x16), K in 64..256 (x64)");
-  MPN_REQUIRE(mode >= 0 && mode <= 3, "tc_probe: mode 0..3");
+  MPN_REQUIRE(mode >= 0 && mode <= 4, "tc_probe: mode 0..4");
+  MPN_REQUIRE(mode != 4 || N <= 128, "tc_probe: mode 4 (A from tensor memory) keeps A in columns 128..255, so N <= 128");
   size_t smem = (size_t)(128 + N) * K * 2 + 1024;
   MPN_CHECK_CUDA(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MPN_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));

@@ -358,6 +358,20 @@ def test_tcgen05_selftest_gemm(engine, N, K):
     assert report[TC_MODE] != "timeout" and report[TC_MODE] < 1e-2 * K ** 0.5
 
 
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 128), (64, 256)])
+def test_tcgen05_selftest_a_from_tmem(engine, N, K):
+    """the same GEMM with the A operand written to tensor memory by tcgen05.st (row = lane, two bf16 per column) and read by
+    tcgen05.mma from there (selftest mode 4) -- the operand path of kernels that keep activations in TMEM between layers"""
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + K + 7)
+    a = torch.randn(128, K, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
+    ref = a.float() @ b.float().t()
+    d, timeout = engine.tc_selftest(a, b, 4)
+    err = float((d - ref).abs().max().item())
+    print(f"tcgen05 selftest (A from TMEM) N={N} K={K}: timeout={timeout} max-abs-err {err:.3e}")
+    assert not timeout and err < 1e-2 * K ** 0.5
+
+
 # ----------------------------------------------------------------------------- bf16 tensor-core mode
 # Tolerances of the throughput mode, against the oracle run with the SAME bf16 operand rounding (fp64 accumulate):
 # remaining differences are fp32-vs-fp64 accumulation order, which can flip a bf16 rounding of an intermediate
