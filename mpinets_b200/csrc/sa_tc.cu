@@ -729,6 +729,332 @@ sa1w_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
+// ---------------------------------------------------------------------------------------------- SA1, activations in TMEM
+// sa1w_tc_kernel is bound by shared-memory bandwidth: its N = 64 MMAs read 6 KB of operands per 32 tensor-pipe cycles and
+// every layer output goes registers -> st.shared -> (async proxy) -> MMA.  Here the A operand never touches shared memory:
+// the gathered rows and every layer's ReLU'd bf16 output are written to TENSOR MEMORY with tcgen05.st (row = lane, two bf16
+// per column) and tcgen05.mma reads A from there; only the 2 KB weight slices (and a constant ones tile for the bias MMA)
+// come from shared memory.  Per chain: 64 accumulator columns + 32 operand columns -> 5 chains (warpgroups) per CTA.
+// The shared memory this frees holds the problem's whole cloud (16 B rows), so the ball query's candidate tests and the
+// gathers are LDS instead of L2 round trips.
+constexpr int SA1T_NWG = 5, SA1T_COLS = 96;
+struct Sa1tSmem {
+  static constexpr size_t w = 0;                                           // 3 x [64][80] bf16
+  static constexpr size_t ones = w + 3 * 64 * SA1_XK * 2;                  // [128][16] bf16: column 0 = 1.0 (A operand of the bias MMAs)
+  static constexpr size_t cnt = ones + 128 * 16 * 2;                       // u32 [BUCKETS] grid-build counters
+  static constexpr size_t lists = cnt + SA1_BUCKETS * 4;                   // [NWG][4][128] u16
+  static constexpr size_t cand = lists + (size_t)SA1T_NWG * 4 * 128 * 2;   // [NWG][4][256] u16
+  static constexpr size_t red = cand + (size_t)SA1T_NWG * 4 * 256 * 2;     // [NWG][256] int
+  static constexpr size_t cxyz = red + (size_t)SA1T_NWG * 256 * 4;         // f32 [512][3]
+  static constexpr size_t bars = cxyz + (size_t)SA1_NPOINT * 3 * 4;
+  static constexpr size_t bstart = (bars + 64 + 15) / 16 * 16;             // u16 [BUCKETS + 1]
+  static constexpr size_t cloud = (bstart + (SA1_BUCKETS + 1) * 2 + 15) / 16 * 16;   // float4 [N]
+  __host__ __device__ static size_t sidx(int N) { return cloud + (size_t)N * 16; }      // u16 [N]
+  static size_t total(int N) { return sidx(N) + (size_t)N * 2 + 64; }
+};
+
+template <bool ARG>
+__global__ void __launch_bounds__(128 * SA1T_NWG, 1)
+sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
+               const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
+               int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out) {
+  using S = Sa1tSmem;
+  constexpr int KC = SA1_XK / 8, NS = NSAMPLE, NWG = SA1T_NWG;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW1 = smem + S::w;
+  uint8_t* sW2 = sW1 + 64 * SA1_XK * 2;
+  uint8_t* sW3 = sW2 + 64 * SA1_XK * 2;
+  uint8_t* sOnes = smem + S::ones;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * NWG);
+  uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + S::bstart);
+  float4* cl = reinterpret_cast<float4*>(smem + S::cloud);
+  uint16_t* sidx = reinterpret_cast<uint16_t*>(smem + S::sidx(N));
+  float* cxyz = reinterpret_cast<float*>(smem + S::cxyz);
+
+  const int b = blockIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int g = warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
+  uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 4 * 128;
+  uint16_t* wcand = reinterpret_cast<uint16_t*>(smem + S::cand) + (size_t)(g * 4 + wq) * 256;
+  int* red = reinterpret_cast<int*>(smem + S::red) + g * 256;
+  const float4* gcl = reinterpret_cast<const float4*>(cloud) + (size_t)b * N;
+
+  stage_weight(gw1, 64, SA1_XK, sW1);
+  stage_weight(gw2, 64, SA1_XK, sW2);
+  stage_weight(gw3, 64, SA1_XK, sW3);
+  for (int i = threadIdx.x; i < 128 * 2; i += blockDim.x)   // ones tile: chunk 0 of every row = (1, 0, ..), chunk 1 = 0
+    *reinterpret_cast<uint4*>(sOnes + kmajor_chunk_off(i >> 1, i & 1, 2)) = make_uint4((i & 1) ? 0u : 0x00003F80u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < SA1_NPOINT * 3; i += blockDim.x) cxyz[i] = __ldg(new_xyz + (size_t)b * SA1_NPOINT * 3 + i);
+  // ---- the problem's cloud -> shared memory, and the hash grid over it (counting sort of point indices by bucket)
+  {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + S::cnt);
+    __shared__ uint32_t wsum[16];
+    for (int i = threadIdx.x; i < SA1_BUCKETS; i += blockDim.x) cnt[i] = 0u;
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const float4 v = __ldg(gcl + k);
+      cl[k] = v;
+      atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u);
+    }
+    __syncthreads();
+    constexpr int PER = SA1_BUCKETS / 512;
+    const bool scanner = threadIdx.x < 512;
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = scanner ? cnt[threadIdx.x * PER + i] : 0u; sum += loc[i]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31 && scanner) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t v = lane < 16 ? wsum[lane] : 0u, iv = v;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+      if (lane < 16) wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    if (scanner) {
+      uint32_t run = wsum[threadIdx.x >> 5] + inc - sum;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { bstart[threadIdx.x * PER + i] = (uint16_t)run; cnt[threadIdx.x * PER + i] = run; run += loc[i]; }
+    }
+    if (threadIdx.x == 0) bstart[SA1_BUCKETS] = (uint16_t)N;
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const float4 v = cl[k];
+      sidx[atomicAdd(&cnt[grid_bucket(grid_coord(v.x), grid_coord(v.y), grid_coord(v.z))], 1u)] = (uint16_t)k;
+    }
+  }
+  __shared__ int round_ctr[1 + 8];
+  int* next_round = round_ctr;
+  int* rsel = round_ctr + 1;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NWG; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+    *next_round = NWG;
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemD = *tmem_slot + (uint32_t)g * SA1T_COLS;       // accumulator: 64 columns
+  const uint32_t tmemA = tmemD + 64;                                  // operand: 32 columns = 64 bf16 per row
+  const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+  const uint32_t tlane = tmemD + lane_off;
+  const uint64_t dOnes = make_smem_desc(smem_u32(sOnes), 128, 2 * 128, LAYOUT_NONE);
+  const uint64_t dW1 = tile_desc(smem_u32(sW1), SA1_XK, 0, 0), dW2 = tile_desc(smem_u32(sW2), SA1_XK, 0, 0),
+                 dW3 = tile_desc(smem_u32(sW3), SA1_XK, 0, 0);
+  uint64_t* bar = &bars[g];
+  uint32_t phase = 0;
+  bool ok = true;
+  constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
+  const unsigned lt = (1u << lane) - 1u;
+
+  // complete ball query of centroid jc by this warp -> lists[wq][0..127]   (same algorithm as sa1w_tc_kernel, cloud in smem)
+  auto warp_ball_query = [&](int jc) {
+    uint16_t* widx = lists + wq * 128;
+    const float qx = cxyz[3 * jc], qy = cxyz[3 * jc + 1], qz = cxyz[3 * jc + 2];
+    const int ix = grid_coord(qx), iy = grid_coord(qy), iz = grid_coord(qz);
+    uint32_t bk = 0x10000u + lane;
+    if (lane < 27) bk = grid_bucket(ix + (lane % 3) - 1, iy + ((lane / 3) % 3) - 1, iz + (lane / 9) - 1);
+    const unsigned peers = __match_any_sync(0xffffffffu, bk);
+    const bool leader = lane < 27 && lane == __ffs(peers) - 1;
+    int s0 = 0, n0 = 0;
+    if (leader) { s0 = bstart[bk]; n0 = bstart[bk + 1] - s0; }
+    int incl = n0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int C = __shfl_sync(0xffffffffu, incl, 31);
+    if (C <= 256) {
+      {
+        const int o = incl - n0;
+        int i = 0;
+        for (; i + 4 <= n0; i += 4) {
+          const uint16_t a0 = sidx[s0 + i], a1 = sidx[s0 + i + 1], a2 = sidx[s0 + i + 2], a3 = sidx[s0 + i + 3];
+          wcand[o + i] = a0; wcand[o + i + 1] = a1; wcand[o + i + 2] = a2; wcand[o + i + 3] = a3;
+        }
+        for (; i < n0; ++i) wcand[o + i] = sidx[s0 + i];
+      }
+      __syncwarp();
+      int H = 0;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int ci = c0 + lane;
+        bool hit = false;
+        int k = 0;
+        if (ci < C) { k = wcand[ci]; const float4 v = cl[k]; hit = dist2(qx, qy, qz, v.x, v.y, v.z) < r2; }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hit) wcand[H + __popc(hm & lt)] = (uint16_t)k;         // in place: write position <= read position
+        H += __popc(hm);
+        __syncwarp();
+      }
+      for (int h = lane; h < H; h += 32) {
+        const int my = wcand[h];
+        int rank = 0;
+        for (int i = 0; i < H; ++i) rank += wcand[i] < my;
+        if (rank < NS) widx[rank] = (uint16_t)my;
+      }
+      __syncwarp();
+      const uint16_t first = H > 0 ? widx[0] : (uint16_t)0;
+      for (int l = min(H, NS) + lane; l < NS; l += 32) widx[l] = first;
+    } else {
+      int cnt = 0;
+      uint16_t first = 0;
+      for (int k0 = 0; k0 < N && cnt < NS; k0 += 32) {
+        const int k = k0 + lane;
+        bool hit = false;
+        if (k < N) { const float4 v = cl[k]; hit = dist2(qx, qy, qz, v.x, v.y, v.z) < r2; }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm && cnt == 0) first = (uint16_t)(k0 + __ffs(hm) - 1);
+        const int pos = cnt + __popc(hm & lt);
+        if (hit && pos < NS) widx[pos] = (uint16_t)k;
+        cnt += __popc(hm);
+      }
+      for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
+    }
+    __syncwarp();
+  };
+  // one layer: bias through an SS MMA against the constant ones tile (K = 16: ones column x the weights' bias chunk), then the
+  // K-steps of the activations straight from tensor memory
+  auto issue = [&](uint64_t dW, int a_col0, int ksteps) {
+    if (wq == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        mma_bf16_ss_off(tmemD, dOnes, 0, dW, 64, IDESC, 0);
+        for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ts(tmemD, tmemA + a_col0 + ks * 8, dW + (uint64_t)(ks * 16), IDESC, 1);
+        mma_commit(bar);
+      }
+      __syncwarp();
+    }
+  };
+  // accumulator (bias inside) -> relu -> bf16 -> the operand columns of this thread's lane
+  auto epilogue_to_tmem = [&]() {
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tlane + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = cvt_relu_bf16x2(__uint_as_float(v[q * 16 + 2 * i]), __uint_as_float(v[q * 16 + 2 * i + 1]));
+        tmem_st8(tmemA + lane_off + (c0 >> 1) + q * 8, pk);
+      }
+    }
+    tmem_st_wait();
+  };
+
+  for (int round = g; round * 4 < SA1_NPOINT && ok;) {
+    const int base = round * 4;
+    if (base + wq < SA1_NPOINT) warp_ball_query(base + wq);
+    wg_sync(g);
+#pragma unroll 1
+    for (int cc = 0; cc < 4 && ok; ++cc) {
+      const int j = base + cc;
+      if (j >= SA1_NPOINT) break;
+      {
+        const int k = lists[cc * 128 + t];
+        if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = k;
+        const float4 p = cl[k];
+        const float dx = fsub(p.x, cxyz[3 * j]), dy = fsub(p.y, cxyz[3 * j + 1]), dz = fsub(p.z, cxyz[3 * j + 2]);
+        const uint32_t row[8] = {pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8(tmemA + lane_off + 24, row);          // K elements 48..63 of the operand columns: (dx dy dz w 0 ...)
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      wg_sync(g);
+      issue(dW1, 24, 1);                               // layer 1: bias + one K = 16 step against W1's chunks 0-1
+#pragma unroll 1
+      for (int layer = 1; layer < 3; ++layer) {
+        ok = ok && mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        epilogue_to_tmem();
+        tc_fence_before();
+        wg_sync(g);
+        issue(layer == 1 ? dW2 : dW3, 0, 4);
+      }
+      ok = ok && mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+      {
+        uint32_t pk[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t va[16], vb[16];
+          tmem_ld_16x256b_x4(tlane + h * 32, va);
+          tmem_ld_16x256b_x4(tlane + (16u << 16) + h * 32, vb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int rep = 0; rep < 4; ++rep) {
+            const float m0 = fmaxf(fmaxf(__uint_as_float(va[rep * 4]), __uint_as_float(va[rep * 4 + 2])),
+                                   fmaxf(__uint_as_float(vb[rep * 4]), __uint_as_float(vb[rep * 4 + 2])));
+            const float m1 = fmaxf(fmaxf(__uint_as_float(va[rep * 4 + 1]), __uint_as_float(va[rep * 4 + 3])),
+                                   fmaxf(__uint_as_float(vb[rep * 4 + 1]), __uint_as_float(vb[rep * 4 + 3])));
+            pk[h * 4 + rep] = cvt_relu_bf16x2(m0, m1);
+          }
+        }
+#pragma unroll
+        for (int w = 4; w >= 1; w >>= 1) {
+          const bool upper = (lane & (w << 2)) != 0;
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            const uint32_t send = upper ? pk[i] : pk[i + w], keepv = upper ? pk[i + w] : pk[i];
+            pk[i] = bf16x2_max(keepv, __shfl_xor_sync(0xffffffffu, send, w << 2));
+          }
+        }
+        red[wq * 32 + lane] = (int)pk[0];
+      }
+      tc_fence_before();
+      wg_sync(g);
+      if (t < 32) {
+        const uint32_t m = bf16x2_max(bf16x2_max((uint32_t)red[t], (uint32_t)red[32 + t]), bf16x2_max((uint32_t)red[64 + t], (uint32_t)red[96 + t]));
+        reinterpret_cast<uint32_t*>(out_bf16 + ((size_t)b * SA1_NPOINT + j) * 64)[t] = m;
+        if constexpr (ARG) red[128 + t] = (int)m;
+      }
+      if constexpr (ARG) {
+        if (t < 64) red[160 + t] = 255;
+        wg_sync(g);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t va[16], vb[16];
+          tmem_ld_16x256b_x4(tlane + h * 32, va);
+          tmem_ld_16x256b_x4(tlane + (16u << 16) + h * 32, vb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int rep = 0; rep < 4; ++rep) {
+            const uint32_t fin = (uint32_t)red[128 + 4 * (h * 4 + rep) + (lane & 3)];
+            const int ch0 = 8 * (h * 4 + rep) + 2 * (lane & 3);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const uint32_t* src = rr < 2 ? va : vb;
+              const int o = rep * 4 + (rr & 1) * 2;
+              const uint32_t pv = cvt_relu_bf16x2(__uint_as_float(src[o]), __uint_as_float(src[o + 1]));
+              const int row = wq * 32 + (lane >> 2) + 8 * rr;
+              if ((fin & 0xFFFFu) != 0u && (pv & 0xFFFFu) == (fin & 0xFFFFu)) atomicMin(&red[160 + ch0], row);
+              if ((fin >> 16) != 0u && (pv >> 16) == (fin >> 16)) atomicMin(&red[160 + ch0 + 1], row);
+            }
+          }
+        }
+        tc_fence_before();
+        wg_sync(g);
+        if (t < 64) {
+          const int a = red[160 + t];
+          arg_out[((size_t)b * SA1_NPOINT + j) * 64 + t] = (uint8_t)(a > 127 ? 0 : a);
+        }
+      }
+    }
+    if (t == 0) rsel[g] = atomicAdd(next_round, 1);
+    wg_sync(g);   // the lists are rewritten by the next round
+    round = rsel[g];
+  }
+  if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
 // bf16 -> fp32 widening of the pooled SA2 rows for the (still fp32) group-all / FC stages
 __global__ void widen_kernel(const __nv_bfloat16* __restrict__ src, int rows, int src_stride, int cols, float* __restrict__ dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -764,7 +1090,14 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
   if (MODULE == 0) {
     MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
     MPN_REQUIRE(N < 65536, "tensor-core SA1: at most 65535 points");
-    if (sa1_wg != 6 || arg_out) {
+    static const bool sa1_ss = getenv("MPN_SA1_SS") != nullptr;   // A/B switch: the shared-memory-operand kernel below
+    const size_t smem_t = Sa1tSmem::total(N);
+    if (!sa1_ss && smem_t + 2048 <= 227 * 1024) {
+      auto kern = arg_out ? sa1t_tc_kernel<true> : sa1t_tc_kernel<false>;
+      MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      kern<<<B, 128 * SA1T_NWG, smem_t, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
+                                             tc_error_flag(c), ball_idx, arg_out);
+    } else if (sa1_wg != 6 || arg_out) {
       size_t smem7 = Sa1wSmem<7>::total(N);
       MPN_REQUIRE(smem7 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
       auto kern = arg_out ? sa1w_tc_kernel<7, true> : sa1w_tc_kernel<7, false>;
