@@ -225,9 +225,11 @@ int mpn_weights_sync(mpn_ctx* ctx);
  * `supervision` [B][7] -> grads [param_count] = d(w_collision * losses[0] + w_bc * losses[1]) / d parameters (overwritten;
  * NULL: forward + losses only).  cloud [B][N][4], q_norm [B][7] in [-1, 1]; y_hat [B][7] optional output.
  * The reference's values: n_loss_points 1024, margin 0.03 (loss.py:92,109), w_collision 5, w_bc 1 (jobconfig.yaml:24-25).
- * precision: MPN_PREC_FP32 = every GEMM of the backward in fp32 (the parity mode); MPN_PREC_BF16 = the compacted-row GEMMs
- * of the SA1 / SA2 backward on tcgen05 with bf16 operands and fp32 accumulation (the counterpart of the reference's
- * precision=16 autocast, run_training.py:109); parameter gradients are fp32 in both. */
+ * precision: MPN_PREC_FP32 = forward and every GEMM of the backward in fp32 (the parity mode); MPN_PREC_BF16 = the counterpart of
+ * the reference's precision=16 autocast (run_training.py:109): the point-cloud encoder's forward runs through the fused
+ * tensor-core kernels (which also record the max-pool routing), the compacted-row GEMMs of the SA1 / SA2 backward and the
+ * data-gradient GEMMs of the group-all level run on tcgen05 with bf16 operands and fp32 accumulation; master weights,
+ * optimizer state and parameter gradients are fp32 in both.  mpn_adam_step refreshes the packed bf16 copies on its stream. */
 int mpn_train_step_grads(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, int N, const float* cloud,
                          const float* q_norm, const float* supervision, int n_loss_points, float margin, float w_collision,
                          float w_bc, float* losses, float* y_hat, float* grads, int precision);
