@@ -1085,31 +1085,23 @@ template <int MODULE>
 static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
                         int B, __nv_bfloat16* out, int out_stride, int32_t* ball_idx = nullptr, uint8_t* arg_out = nullptr) {
   TcWeights& tw = g_tc[c];
-  // SA1: 7 row warpgroups (72 registers) with the grid index on chip; MPN_SA1_WG=6 runs 6 groups (A/B switch)
-  static const int sa1_wg = getenv("MPN_SA1_WG") ? atoi(getenv("MPN_SA1_WG")) : 7;
   if (MODULE == 0) {
     MPN_REQUIRE(stride == 4, "tensor-core SA1 takes the [B][N][4] cloud");
     MPN_REQUIRE(N < 65536, "tensor-core SA1: at most 65535 points");
-    static const bool sa1_ss = getenv("MPN_SA1_SS") != nullptr;   // A/B switch: the shared-memory-operand kernel below
+    const bool sa1_ss = getenv("MPN_SA1_SS") != nullptr;   // A/B switch (read per launch so tests can toggle it): the shared-memory-operand kernel below
     const size_t smem_t = Sa1tSmem::total(N);
     if (!sa1_ss && smem_t + 2048 <= 227 * 1024) {
       auto kern = arg_out ? sa1t_tc_kernel<true> : sa1t_tc_kernel<false>;
       MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
       kern<<<B, 128 * SA1T_NWG, smem_t, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
                                              tc_error_flag(c), ball_idx, arg_out);
-    } else if (sa1_wg != 6 || arg_out) {
+    } else {
       size_t smem7 = Sa1wSmem<7>::total(N);
       MPN_REQUIRE(smem7 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
       auto kern = arg_out ? sa1w_tc_kernel<7, true> : sa1w_tc_kernel<7, false>;
       MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));
       kern<<<B, 128 * 7, smem7, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out, tc_error_flag(c),
                                      ball_idx, arg_out);
-    } else {
-      size_t smem6 = Sa1wSmem<6>::total(N);
-      MPN_REQUIRE(smem6 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
-      MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1w_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
-      sa1w_tc_kernel<6><<<B, 128 * 6, smem6, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
-                                                  tc_error_flag(c), ball_idx);
     }
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());

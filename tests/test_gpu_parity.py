@@ -416,6 +416,31 @@ def test_sa_modules_bf16_tensor_core(engine_w, oracle, tables, state_dict):
     print("SA1 bf16 vs fp32 path: rel err", ((f1 - f1_32).abs().max() / f1_32.abs().max()).item())
 
 
+def test_sa1_shared_memory_operand_kernel(engine_w, oracle, tables, state_dict):
+    """the predecessor / fallback SA1 kernel (operands in shared memory, MPN_SA1_SS=1; also taken when a cloud does not fit in
+    shared memory next to the weights) against the same oracle, and against the default kernel (activations in TMEM): identical
+    ball-query indices, features equal up to the accumulation order inside the tensor core"""
+    from mpinets_b200 import _lib
+    cloud, _ = _clouds(engine_w, oracle, tables, 3)
+    d_cloud = torch.from_numpy(cloud).cuda()
+    xyz = np.ascontiguousarray(cloud[..., :3])
+    feats = torch.from_numpy(np.ascontiguousarray(cloud[..., 3:]))
+    _, o_f1, aux1 = oracle.sa_module(xyz, feats, oracle.SA_SPECS[0], _sa_weights(state_dict, 0), emulate_bf16=True, dtype=torch.float64,
+                                     return_aux=True)
+    _, f_t, _, bi_t = engine_w.sa_forward(0, d_cloud, d_cloud[..., 3:], precision=_lib.PREC_BF16, debug=True)
+    os.environ["MPN_SA1_SS"] = "1"
+    try:
+        _, f_s, _, bi_s = engine_w.sa_forward(0, d_cloud, d_cloud[..., 3:], precision=_lib.PREC_BF16, debug=True)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("MPN_SA1_SS", None)
+    assert not engine_w.tc_error()
+    assert np.array_equal(bi_s.cpu().numpy(), aux1["ball_idx"]) and torch.equal(bi_s, bi_t)
+    scale = o_f1.abs().max().item()
+    assert (f_s.cpu().double() - o_f1).abs().max().item() / scale < BF16_FEAT_RTOL
+    assert (f_s - f_t).abs().max().item() / scale < 1e-2
+
+
 def test_policy_forward_bf16(engine_w, oracle, tables, state_dict):
     from mpinets_b200 import _lib
     cloud, p = _clouds(engine_w, oracle, tables, 6)
