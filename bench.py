@@ -95,47 +95,65 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_steps_per_sec(n_problems: int, steps: int, bf16: bool, seed: int):
-    """The CPU port of the same step (oracle/): torch-CPU MLPs on all host threads + C geometry. Returns (value, seconds)."""
-    import torch
-    from mpinets_b200 import scenes, franka
-    from oracle import oracle as O
-    if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:   # torchrun pins OMP_NUM_THREADS=1: undo it for the CPU arm
-        torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))      # (physical cores; SMT siblings only slow the GEMMs down)
-    tables = franka.default_tables()
-    sd = O.reference_state_dict(0)
-    p = scenes.config_problems(2, n_problems)
-    cloud = O.build_cloud(p["q0"], p["target"], p, tables, seed)
-    qn = O.normalize(p["q0"], tables.joint_limits)
-    t0 = time.perf_counter()
-    traj = O.rollout(sd, cloud, qn, tables, steps, seed, emulate_bf16=False)
-    O.sweep_flags(p, traj, tables)
-    dt = time.perf_counter() - t0
-    return n_problems * steps / dt, dt, torch.get_num_threads()
+class CpuPort:
+    """The CPU port of the same step (oracle/): torch-CPU MLPs on the host threads + C geometry.  Problems, weights and the
+    t = 0 clouds are prepared once (untimed, like the GPU arm's resident inputs); run() times rollout + collision sweep."""
+
+    def __init__(self, n_problems: int, seed: int):
+        import torch
+        from mpinets_b200 import scenes, franka
+        from oracle import oracle as O
+        if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:   # torchrun pins OMP_NUM_THREADS=1: undo it for the CPU arm
+            torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))      # (physical cores; SMT siblings only slow the GEMMs down)
+        self.O, self.n, self.seed, self.threads = O, n_problems, seed, torch.get_num_threads()
+        self.tables = franka.default_tables()
+        self.sd = O.reference_state_dict(0)
+        self.p = scenes.config_problems(2, n_problems)
+        self.cloud = O.build_cloud(self.p["q0"], self.p["target"], self.p, self.tables, seed)
+        self.qn = O.normalize(self.p["q0"], self.tables.joint_limits)
+
+    def run(self, steps: int) -> float:
+        t0 = time.perf_counter()
+        traj = self.O.rollout(self.sd, self.cloud.copy(), self.qn, self.tables, steps, self.seed, emulate_bf16=False)
+        self.O.sweep_flags(self.p, traj, self.tables)
+        return time.perf_counter() - t0
+
+
+def cpu_baseline(seed: int, budget_s: float = 10.0, n_problems: int = 16, steps: int = 4, max_calls: int = 8):
+    """bounded sample of the bench workload on the host cores: calls of (n_problems x steps) until ~budget_s of CPU work"""
+    port = CpuPort(n_problems, seed)
+    port.run(1)   # warm-up (thread pools, page faults)
+    total, calls = 0.0, 0
+    while calls < max_calls and (calls == 0 or total < budget_s):
+        total += port.run(steps)
+        calls += 1
+    done = calls * n_problems * steps
+    return {"value": done / total, "unit": "env steps/s", "cores": port.threads, "kind": "port",
+            "sample": f"{calls} x ({n_problems} problems x {steps} steps) of the same workload = {done} problem-steps in {total:.1f} s "
+                      f"(cloud build excluded), torch-CPU fp32 MLPs + C oracle geometry"}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be imported
-    (pointnet2_ops is CUDA-only; robofin/geometrout are not installable offline), so this times the oracle port."""
+    (pointnet2_ops is CUDA-only; robofin/geometrout are not installable offline), so this times the oracle port on all host
+    threads.  One bench step = one lock-step env step of a bounded sample of the workload (16 problems)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 4
-    for _ in range(min(args.warmup, 1)):
-        cpu_oracle_steps_per_sec(n, 1, False, 1)
-    vals = []
-    t_all = time.perf_counter()
+    n = 16
+    port = CpuPort(n, 1)
+    for _ in range(max(args.warmup, 1)):
+        port.run(1)
+    total = 0.0
     for _ in range(args.steps):
-        v, dt, threads = cpu_oracle_steps_per_sec(n, 1, False, 1)
-        vals.append(v)
-    total = time.perf_counter() - t_all
+        total += port.run(1)
     value = n * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": "configs[1]: tabletop problems, 6272-pt clouds, lock-step policy rollout + SDF sweep",
                        "sample": f"{n} problems x 1 step per bench step"},
-            "cpu_baseline": {"value": value, "unit": "env steps/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "env steps/s", "cores": port.threads, "kind": "port",
                              "sample": f"{n} problems x {args.steps} steps (cloud build excluded), torch-CPU MLPs + C oracle geometry"},
             "e2e": {"value": value, "unit": "env steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -319,10 +337,7 @@ def main():
             "collision_rate": float(metrics[:, 0].mean().item()),
         }
         if not args.no_cpu_baseline:
-            nb, ns = 4, 2
-            v, dt, threads = cpu_oracle_steps_per_sec(nb, ns, False, eng.cfg.seed)
-            line["cpu_baseline"] = {"value": v, "unit": "env steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{nb} problems x {ns} steps of the same workload ({dt:.1f} s), torch-CPU fp32 MLPs + C oracle geometry"}
+            line["cpu_baseline"] = cpu_baseline(eng.cfg.seed)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
