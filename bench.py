@@ -336,7 +336,7 @@ def main():
             "achieved_tflops_whole_step": FLOP_TOTAL * B * K * world / (ms / 1000.0) / 1e12,
             "collision_rate": float(metrics[:, 0].mean().item()),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only: the other ranks must not wait on 10 s of CPU work
             line["cpu_baseline"] = cpu_baseline(eng.cfg.seed)
         print(json.dumps(line))
     if world > 1:
