@@ -36,7 +36,9 @@ typedef enum {
 /* arithmetic used by the set-abstraction MLPs / FC head */
 typedef enum {
   MPN_PREC_FP32 = 0,      /* fp32 SIMT FMA, fp32 accumulate: the 1e-5 parity mode */
-  MPN_PREC_BF16 = 1       /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM: the throughput mode */
+  MPN_PREC_BF16 = 1,      /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM: the throughput mode */
+  MPN_PREC_BF16X3 = 2     /* split-bf16 operands (x = hi + lo; a*w = a_hi w_hi + a_lo w_hi + a_hi w_lo) on tcgen05, fp32 accumulate:
+                             the parity-grade tensor-core mode -- delta-q within 1e-5 of the fp32 reference (model.py:75-91 in fp32) */
 } mpn_precision;
 
 typedef struct {
@@ -271,6 +273,12 @@ int mpn_profile_read(mpn_ctx* ctx, float* ms /*[MPN_NUM_STAGES]*/, int64_t* laun
 int mpn_tc_error(mpn_ctx* ctx, int* out);
 int mpn_tc_selftest(mpn_ctx* ctx, void* stream, const void* a_bf16, const void* b_bf16, float* d, int N, int K, int mode,
                     int* status);
+
+/* GEMM self-test of the TMA / tcgen05 row GEMM (gemm_tc.cu) behind SA3 and the FC head: out[M][N] fp32 = a[M][K] * w[N][K]^T +
+ * bias, operands taken as bf16 (split = 0) or as split-bf16 (hi, lo) pairs with the three-pass product of MPN_PREC_BF16X3
+ * (split = 1).  Test entry: allocates temporaries and synchronises the stream. */
+int mpn_tc_gemm_selftest(mpn_ctx* ctx, void* stream, const float* a, const float* w, const float* bias, int M, int N, int K,
+                         float* out, int split);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libmpinets_b200.so")
 
 METRICS_COLS = 8
 STAGES = ("fps1", "sa1", "fps2", "sa2", "sa3", "fc", "heads", "update", "sample_robot", "sweep", "build_cloud", "other")
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 EVAL_COLS = 16
 # columns of mpn_evaluate's table; names follow Evaluator.evaluate_trajectory's add_metric keys (metrics.py:470-523)
 EVAL_COLUMNS = ("collision", "joint_limit_violation", "self_collision", "physical_violations", "position_error",
@@ -25,7 +26,7 @@ EXPORTS = (
     "mpn_sa_forward", "mpn_fk", "mpn_sample_robot", "mpn_compute_spheres", "mpn_normalize_joints",
     "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_build_cloud_from_points", "mpn_render_depth_cloud", "mpn_sweep_flags", "mpn_evaluate", "mpn_sparc", "mpn_collision_loss", "mpn_point_match_loss", "mpn_bc_collision_losses", "mpn_encoder_forward",
     "mpn_policy_forward", "mpn_rollout", "mpn_param_count", "mpn_param_info", "mpn_get_params", "mpn_set_params", "mpn_weights_sync",
-    "mpn_train_step_grads", "mpn_train_tc_gemm", "mpn_train_tc_wgrad", "mpn_train_pooled_rows", "mpn_adam_step", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error",
+    "mpn_train_step_grads", "mpn_train_tc_gemm", "mpn_train_tc_wgrad", "mpn_train_pooled_rows", "mpn_adam_step", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error", "mpn_tc_gemm_selftest",
 )
 
 
@@ -105,6 +106,7 @@ def load():
         "mpn_profile": [P, I],
         "mpn_tc_error": [P, C.POINTER(C.c_int)],
         "mpn_tc_selftest": [P, P, P, P, P, I, I, I, P],
+        "mpn_tc_gemm_selftest": [P, P, P, P, P, I, I, I, P, I],
         "mpn_profile_read": [P, C.POINTER(C.c_float), C.POINTER(C.c_int64)],
     }
     for name, argtypes in sigs.items():

@@ -24,6 +24,14 @@ int* tc_error_flag(mpn_ctx* c);
 int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
                   int N, const float* new_xyz, float* new_feats, int32_t* ball_idx);
 int tc_probe(mpn_ctx* c, cudaStream_t s, const void* A, const void* B, float* D, int N, int K, int mode, int* status);
+void tc_free(mpn_ctx* c);
+// split-bf16 parity-grade tensor-core path, sa_x3.cu
+int x3_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, float* out, int ldo);
+int x3_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
+                  int N, const float* new_xyz, float* new_feats, int32_t* ball_idx);
+size_t x3_scratch_bytes(int B);
+int x3_gemm_selftest(mpn_ctx* c, cudaStream_t s, const float* A, const float* W, const float* bias, int M, int N, int K, float* C, int split);
+void x3_free(mpn_ctx* c);
 
 template <typename T>
 static int dev_alloc(T** p, size_t n) {
@@ -74,6 +82,8 @@ static int ensure_workspace(mpn_ctx* c, int B) {
   if (w.tc_scratch_bytes) {
     if (cudaMalloc(&w.tc_scratch, w.tc_scratch_bytes) != cudaSuccess) { set_error("workspace: tc scratch alloc failed"); r |= MPN_ERR_NOMEM; }
   }
+  if (w.x3_scratch) { cudaFree(w.x3_scratch); w.x3_scratch = nullptr; }
+  if (cudaMalloc(&w.x3_scratch, x3_scratch_bytes(B)) != cudaSuccess) { set_error("workspace: bf16x3 scratch alloc failed"); r |= MPN_ERR_NOMEM; }
   if (r) { w.capacity = 0; return MPN_ERR_NOMEM; }
   w.capacity = B;
   return MPN_OK;
@@ -186,6 +196,7 @@ static int encoder_forward(mpn_ctx* c, cudaStream_t s, int precision, const floa
   Workspace& w = c->ws;
   int r;
   if (precision == MPN_PREC_BF16) return tc_encoder_forward(c, s, cloud, B, N, out, ldo);
+  if (precision == MPN_PREC_BF16X3) return x3_encoder_forward(c, s, cloud, B, N, out, ldo);
   // SA1: FPS over the 4-float rows of the cloud; features = mask column
   { StageTimer t(c, s, MPN_ST_FPS1);
     if ((r = launch_fps(c, s, cloud, B, N, 4, SA1_NPOINT, reinterpret_cast<int32_t*>(w.fc_a), w.xyz1))) return r; }
@@ -276,6 +287,9 @@ int mpn_ctx_destroy(mpn_ctx* c) {
   if (c->ws.first_step) cudaFree(c->ws.first_step);
   if (c->ws.flags) cudaFree(c->ws.flags);
   if (c->ws.tc_scratch) cudaFree(c->ws.tc_scratch);
+  if (c->ws.x3_scratch) cudaFree(c->ws.x3_scratch);
+  tc_free(c);
+  x3_free(c);
   if (c->link_table4) cudaFree(c->link_table4);
   if (c->robot_sel4) cudaFree(c->robot_sel4);
   if (c->robot_sel_steps) cudaFree(c->robot_sel_steps);
@@ -346,6 +360,13 @@ int mpn_tc_selftest(mpn_ctx* c, void* stream, const void* a, const void* b, floa
   return tc_probe(c, (cudaStream_t)stream, a, b, d, N, K, mode, status);
 }
 
+int mpn_tc_gemm_selftest(mpn_ctx* c, void* stream, const float* a, const float* w, const float* bias, int M, int N, int K, float* out,
+                         int split) {
+  REQ_CTX(c);
+  MPN_REQUIRE(a && w && bias && out, "mpn_tc_gemm_selftest: null pointer");
+  return x3_gemm_selftest(c, (cudaStream_t)stream, a, w, bias, M, N, K, out, split);
+}
+
 int mpn_tc_error(mpn_ctx* c, int* out) {
   REQ_CTX(c);
   MPN_REQUIRE(out, "mpn_tc_error: null output");
@@ -408,8 +429,8 @@ int mpn_sa_forward(mpn_ctx* c, void* stream, int module, int precision, const fl
                    int feat_stride, int B, int N, float* new_xyz, float* new_feats, int32_t* fps_idx, int32_t* ball_idx) {
   REQ_CTX(c); REQ_WEIGHTS(c);
   MPN_REQUIRE(module >= 0 && module <= 2, "mpn_sa_forward: module must be 0..2");
-  MPN_REQUIRE(precision == MPN_PREC_FP32 || (precision == MPN_PREC_BF16 && module < 2),
-              "mpn_sa_forward: bf16 per-module entry covers modules 0 and 1");
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || ((precision == MPN_PREC_BF16 || precision == MPN_PREC_BF16X3) && module < 2),
+              "mpn_sa_forward: the tensor-core per-module entries cover modules 0 and 1");
   MPN_REQUIRE(xyz && feats && new_feats && stride >= 3, "mpn_sa_forward: null pointer");
   static const int cfeat[3] = {1, 64, 256};
   MPN_REQUIRE(feat_stride >= cfeat[module], "mpn_sa_forward: feat_stride too small");
@@ -423,6 +444,7 @@ int mpn_sa_forward(mpn_ctx* c, void* stream, int module, int precision, const fl
   int32_t* idx = fps_idx ? fps_idx : reinterpret_cast<int32_t*>(c->ws.fc_a);
   if ((r = launch_fps(c, s, xyz, B, N, stride, npoint, idx, new_xyz))) return r;
   if (precision == MPN_PREC_BF16) return tc_sa_forward(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats, ball_idx);
+  if (precision == MPN_PREC_BF16X3) return x3_sa_forward(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats, ball_idx);
   return launch_sa_simt(c, s, module, xyz, stride, feats, feat_stride, B, N, new_xyz, new_feats, ball_idx);
 }
 
@@ -610,7 +632,7 @@ int mpn_encoder_forward(mpn_ctx* c, void* stream, int precision, const float* cl
   REQ_CTX(c); REQ_WEIGHTS(c);
   MPN_REQUIRE(cloud && out, "mpn_encoder_forward: null pointer");
   MPN_REQUIRE(N >= SA1_NPOINT && N <= 8192, "mpn_encoder_forward: N=%d unsupported (512..8192)", N);
-  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16, "bad precision");
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16 || precision == MPN_PREC_BF16X3, "bad precision");
   if (B == 0) return MPN_OK;
   int r;
   if ((r = ensure_workspace(c, B))) return r;
@@ -621,7 +643,7 @@ int mpn_policy_forward(mpn_ctx* c, void* stream, int precision, const float* clo
   REQ_CTX(c); REQ_WEIGHTS(c);
   MPN_REQUIRE(cloud && q_norm && dq, "mpn_policy_forward: null pointer");
   MPN_REQUIRE(N >= SA1_NPOINT && N <= 8192, "mpn_policy_forward: N=%d unsupported (512..8192)", N);
-  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16, "bad precision");
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16 || precision == MPN_PREC_BF16X3, "bad precision");
   if (B == 0) return MPN_OK;
   int r;
   if ((r = ensure_workspace(c, B))) return r;
@@ -717,7 +739,7 @@ int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene,
   if ((r = check_scene(c, scene))) return r;
   MPN_REQUIRE(cloud && q0 && target && traj && metrics && T >= 1, "mpn_rollout: bad arguments");
   MPN_REQUIRE(N >= c->cfg.n_robot && N >= SA1_NPOINT && N <= 8192, "mpn_rollout: N=%d unsupported", N);
-  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16, "bad precision");
+  MPN_REQUIRE(precision == MPN_PREC_FP32 || precision == MPN_PREC_BF16 || precision == MPN_PREC_BF16X3, "bad precision");
   if (B == 0) return MPN_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if ((r = ensure_workspace(c, B))) return r;

@@ -78,6 +78,7 @@ struct Workspace {
   uint8_t* flags = nullptr;                 // [B]
   void* tc_scratch = nullptr;               // tensor-core path scratch (bf16 hand-off tensors)
   size_t tc_scratch_bytes = 0;
+  void* x3_scratch = nullptr;               // split-bf16 mode scratch (sa_x3.cu)
 };
 
 // buffers of the training step (train.cu): everything the backward pass needs from the forward pass, for B samples,

@@ -90,7 +90,7 @@ int launch_linear(mpn_ctx* c, cudaStream_t s, const Linear& L, const float* x, i
 __global__ void __launch_bounds__(256) groupnorm_lrelu_kernel(float* __restrict__ x, int M, int C, int groups,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32 = nullptr,
-                                                              float* __restrict__ stats = nullptr) {
+                                                              float* __restrict__ stats = nullptr, int split = 0) {
   int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= M * groups) return;
   int row = wid / groups, g = wid % groups, gs = C / groups;
@@ -110,7 +110,12 @@ __global__ void __launch_bounds__(256) groupnorm_lrelu_kernel(float* __restrict_
     int ch = g * gs + i;
     float v = (p[i] - mean) * rstd * gamma[ch] + beta[ch];
     v = v > 0.f ? v : 0.01f * v;
-    if (out_bf16) out_bf16[(size_t)row * C + ch] = __float2bfloat16_rn(v);
+    if (out_bf16 && split) {   // [hi | lo] row of the split-bf16 GEMM that follows: pitch 2C
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out_bf16[(size_t)row * 2 * C + ch] = h;
+      out_bf16[(size_t)row * 2 * C + C + ch] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+    else if (out_bf16) out_bf16[(size_t)row * C + ch] = __float2bfloat16_rn(v);
     else if (out_f32) out_f32[(size_t)row * C + ch] = v;
     else p[i] = v;
   }
@@ -138,6 +143,16 @@ int launch_groupnorm_lrelu_bf16(mpn_ctx* c, cudaStream_t s, float* x, int M, int
                                 __nv_bfloat16* out) {
   int warps = M * groups;
   groupnorm_lrelu_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(x, M, C, groups, gamma, beta, out);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
+// same, writing the [hi | lo] split-bf16 operand rows ([M][2C]) of the bf16x3 mode
+int launch_groupnorm_lrelu_split(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta,
+                                 __nv_bfloat16* out) {
+  int warps = M * groups;
+  groupnorm_lrelu_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(x, M, C, groups, gamma, beta, out, nullptr, nullptr, 1);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

@@ -36,6 +36,7 @@ struct TcWeights {
 };
 static std::map<mpn_ctx*, TcWeights> g_tc;
 int* tc_error_flag(mpn_ctx* c);
+int x3_pack_weights(mpn_ctx* c, cudaStream_t s);   // sa_x3.cu: the split-bf16 copies are refreshed together with the bf16 ones
 
 // bias_col >= 0: the layer's bias is folded into the GEMM as K-column `bias_col` (the operand carries a 1.0 there)
 __global__ void pack_weight_kernel(const float* __restrict__ w, int out, int in, int kpad, int rot, __nv_bfloat16* __restrict__ dst,
@@ -87,7 +88,18 @@ static int tc_pack_weights(mpn_ctx* c, cudaStream_t s, bool sa_only) {
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
   }
-  return MPN_OK;
+  return x3_pack_weights(c, s);
+}
+
+void tc_free(mpn_ctx* c) {
+  auto it = g_tc.find(c);
+  if (it == g_tc.end()) return;
+  TcWeights& t = it->second;
+  for (int m = 0; m < 3; ++m)
+    for (int l = 0; l < 3; ++l) if (t.sa[m][l]) cudaFree(t.sa[m][l]);
+  for (int l = 0; l < 3; ++l) if (t.fc[l]) cudaFree(t.fc[l]);
+  if (t.w2_nofold) cudaFree(t.w2_nofold);
+  g_tc.erase(it);
 }
 
 int tc_prepare_weights(mpn_ctx* c) {

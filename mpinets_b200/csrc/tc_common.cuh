@@ -157,6 +157,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---- split-bf16 ("bf16x3") operands: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi); |x - hi - lo| <= 2^-16 |x|.
+// A product a*w is then taken as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on the bf16 tensor pipe (fp32 accumulate).
+// Packed pairs: `first` in the low half-word (K element 2j), `second` in the high half-word (K element 2j + 1).
+__device__ __forceinline__ void split_pack(float first, float second, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(second), "f"(first));
+  const float r0 = first - __uint_as_float(hi << 16), r1 = second - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void split_relu_pack(float first, float second, uint32_t& hi, uint32_t& lo) {
+  split_pack(fmaxf(first, 0.f), fmaxf(second, 0.f), hi, lo);
+}
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
 // K-major operand tile in the canonical no-swizzle ("interleaved") layout: 8x(16 B) core matrices, the core matrices of
 // one 8-row group are contiguous along K (LBO = 128 B), row groups follow at SBO = (K/8)*128 B.
 // byte offset of the 16-byte chunk holding K-elements [8*kc, 8*kc+8) of row r:

@@ -140,6 +140,15 @@ class Engine:
             return d[128 * N:128 * N + 8].cpu().tolist(), bool(st.item())
         return d[:128 * N].view(128, N), bool(st.item())
 
+    def tc_gemm_selftest(self, a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, split: bool = True) -> torch.Tensor:
+        """a [M,K] @ w [N,K]^T + bias through the TMA / tcgen05 row GEMM (fp32 in / out; bf16 or split-bf16 operands inside)"""
+        _check(a, "a", device=self.device); _check(w, "w", device=self.device); _check(bias, "bias", device=self.device)
+        M, K = a.shape
+        N = w.shape[0]
+        out = self._empty(M, N)
+        _lib.check(self.lib.mpn_tc_gemm_selftest(self._ctx, self.stream, _p(a), _p(w), _p(bias), M, N, K, _p(out), int(split)))
+        return out
+
     # ------------------------------------------------------------------ pointnet2_ops
     def fps(self, xyz: torch.Tensor, npoint: int, return_xyz: bool = False):
         _check(xyz, "xyz", device=self.device)

@@ -7,7 +7,7 @@ from mpinets_b200.engine import Engine
 from oracle import oracle as O
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
-prec = _lib.PREC_BF16 if (len(sys.argv) > 2 and sys.argv[2] == "bf16") else _lib.PREC_FP32
+prec = _lib.PRECISIONS[sys.argv[2]] if len(sys.argv) > 2 else _lib.PREC_FP32
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 eng = Engine()
 eng.load_state_dict(O.reference_state_dict(0))
@@ -22,5 +22,5 @@ for _ in range(reps):
     dq = eng.policy_forward(cloud, qn, prec)
 torch.cuda.synchronize()
 st = eng.profile_read()
-print({k: round(v["ms"] / max(v["launches"], 1), 4) for k, v in st.items() if v["launches"]})
+print(sys.argv[1:], {k: round(v["ms"] / reps, 4) for k, v in st.items() if v["launches"]})
 print("tc_error", eng.tc_error())
