@@ -1,18 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- env steps/sec of the batched MPiNets rollout hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision bf16|fp32]
+    python bench.py --gpus N --steps K --warmup W [--workload 2|3|4|5] [--precision bf16x3|bf16|fp32] [--impl reference]
 
 One "step" = one lock-step policy step over the whole per-GPU batch of PlanningProblems: PointNet++ encoder (FPS,
 ball query, grouping, shared MLPs) + delta-q head + clamp/unnormalise + FK + robot-surface resample into the cloud +
-link-sphere SDF collision check.  N = 1 workload = BASELINE.json configs[1] (4096 tabletop problems, 6272-point
-clouds); N > 1 shards 4096 problems per GPU (weak scaling, no data-path collective, one NCCL all-gather of the
-metrics table at the end).
+link-sphere SDF collision check.
 
-Printed JSON (rank 0): value = problems*K / device time of K steps with everything resident in HBM; e2e = the same
-job through the public API with HOST problem buffers (pinned H2D of the problem SoA, cloud build, K steps, D2H of
-trajectories + metrics inside the timed region); roofline = dominant kernel vs MEASURED_PEAKS.json; cpu_baseline =
-the CPU oracle port timed on this box's host cores on a bounded sample.
+Workloads (numbering of SURVEY.md section 8d = scenes.config_problems):
+  2  BASELINE configs[1]: 4096 tabletop problems per GPU                               (default at N = 1)
+  3  BASELINE configs[2]: 4096 cubby(+merged) + dresser problems, collision check every step, T = 70
+  4  BASELINE configs[3]: 4096 per GPU of the mixed thirds (tabletop / cubby / dresser), T = 70, one NCCL gather
+                                                                                        (default at N > 1: 32768 problems on 8)
+  5  BASELINE configs[4]: training step, 8192 samples per GPU, DDP all-reduce           (samples/s; --steps training steps)
+
+Printed JSON (rank 0).  `value` / `dtype` describe the PARITY-GRADE mode (bf16x3: split-bf16 operands on tcgen05, delta-q within
+1e-5 of the fp32 reference); `fast_mode` is the same job in the bf16 throughput mode with its delta-q error.  value = problems*K /
+device time of K steps with everything resident in HBM; e2e = the same job through the public API with HOST problem buffers
+(pinned H2D of the problem SoA, cloud build, K steps, D2H of trajectories + metrics inside the timed region); parity = match
+fields of the metric (collision flags, FPS indices, delta-q) against the CPU oracle, computed outside the timed regions;
+roofline = dominant kernel vs MEASURED_PEAKS.json; cpu_baseline = the CPU oracle port on this box's host cores.
 """
 from __future__ import annotations
 
@@ -35,14 +42,27 @@ PROBLEMS_PER_GPU = 4096
 FLOP_PER_STEP = {"sa1": 2 * 553_648_128, "sa2": 2 * 945_815_552, "sa3": 2 * 117_571_584, "fc": 2 * 16_777_216 + 0,
                  "heads": 2 * 1_291_904}
 FLOP_TOTAL = 2 * 1_635_159_136
+# bf16 MMA flops the bf16x3 mode actually issues per algorithmic flop (three products per MAC; SA2's first layer is evaluated per
+# point instead of per pair, so its 67-wide layer costs 1/32 of the pairwise form)
+X3_MMA_FACTOR = {"sa1": 3.0, "sa2": 3.0 * (128 * 128 + 128 * 256) / (67 * 128 + 128 * 128 + 128 * 256), "sa3": 3.0, "fc": 3.0}
 BYTES_PER_STEP = {"sample_robot": 2048 * 16 + 11 * 48, "sweep": 28 + 3200 + 1, "build_cloud": 6272 * 16,
                   "fps1": 6272 * 16 + 512 * 16, "fps2": 512 * 12 + 128 * 16}
+WORKLOADS = {
+    2: dict(baseline="configs[1]", rollout_T=50, desc="4096 tabletop PlanningProblems per GPU"),
+    3: dict(baseline="configs[2]", rollout_T=70, desc="4096 cubby(+merged) + dresser PlanningProblems per GPU, collision check every step"),
+    4: dict(baseline="configs[3]", rollout_T=70, desc="4096 mixed-scene PlanningProblems per GPU (tabletop / cubby / dresser thirds), "
+                                                      "problem-sharded, one NCCL gather of the metrics table"),
+}
 
 
 def load_traffic():
-    """per-problem DRAM bytes (read + write) of each stage's dominant kernel from the committed ncu --set full capture"""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else {}
+    """per-problem DRAM bytes (read + write) of each stage's dominant kernel from the committed ncu --set full captures"""
+    out = {}
+    for name in ("r1_traffic.json", "r2_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            out.update(json.load(open(p)))
+    return out
 
 
 def load_peaks():
@@ -66,7 +86,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -95,20 +115,25 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _host_threads():
+    import torch
+    if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:   # torchrun pins OMP_NUM_THREADS=1: undo it for the CPU arm
+        torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))      # (physical cores; SMT siblings only slow the GEMMs down)
+    return torch.get_num_threads()
+
+
 class CpuPort:
     """The CPU port of the same step (oracle/): torch-CPU MLPs on the host threads + C geometry.  Problems, weights and the
     t = 0 clouds are prepared once (untimed, like the GPU arm's resident inputs); run() times rollout + collision sweep."""
 
-    def __init__(self, n_problems: int, seed: int):
-        import torch
+    def __init__(self, n_problems: int, seed: int, config: int = 2):
         from mpinets_b200 import scenes, franka
         from oracle import oracle as O
-        if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:   # torchrun pins OMP_NUM_THREADS=1: undo it for the CPU arm
-            torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))      # (physical cores; SMT siblings only slow the GEMMs down)
-        self.O, self.n, self.seed, self.threads = O, n_problems, seed, torch.get_num_threads()
+        self.threads = _host_threads()
+        self.O, self.n, self.seed = O, n_problems, seed
         self.tables = franka.default_tables()
         self.sd = O.reference_state_dict(0)
-        self.p = scenes.config_problems(2, n_problems)
+        self.p = scenes.config_problems(config, n_problems)
         self.cloud = O.build_cloud(self.p["q0"], self.p["target"], self.p, self.tables, seed)
         self.qn = O.normalize(self.p["q0"], self.tables.joint_limits)
 
@@ -119,18 +144,73 @@ class CpuPort:
         return time.perf_counter() - t0
 
 
-def cpu_baseline(seed: int, budget_s: float = 10.0, n_problems: int = 16, steps: int = 4, max_calls: int = 8):
+def cpu_config0(reps: int = 25):
+    """BASELINE configs[0] exactly as SURVEY section 8d words it: ONE tabletop problem -- build the 4096-point obstacle cloud, then
+    the link-sphere SDF sweep of 50 poses (joint-space interpolation between two in-limit configurations), no network.
+    Oracle port at 1 thread and on all host cores (independent problems over threads; the C oracle releases the GIL), median of
+    `reps` repetitions after a warm-up."""
+    from concurrent.futures import ThreadPoolExecutor
+    from mpinets_b200 import scenes, franka
+    from oracle import oracle as O
+    tables = franka.default_tables()
+    cores = os.cpu_count() or 1
+    PER = 16                                    # problems per thread and call on the all-cores leg (amortises the Python call overhead)
+    P = scenes.config_problems(2, cores * PER)
+    arr = {k: v for k, v in P.items() if isinstance(v, np.ndarray)}
+    w = np.linspace(0.0, 1.0, 50, dtype=np.float32)[None, :, None]
+    traj = (P["q0"][:, None, :] * (1 - w) + P["q_goal"][:, None, :] * w).astype(np.float32)
+
+    def job(lo, hi):
+        p = {k: v[lo:hi] for k, v in arr.items()}
+        t0 = time.perf_counter()
+        O.sample_obstacles(p, 4096, 0x4D50694E, problem0=lo)
+        t1 = time.perf_counter()
+        O.sweep_flags(p, traj[lo:hi], tables)
+        return t1 - t0, time.perf_counter() - t1
+
+    job(0, 1)
+    single = np.array([job(0, 1) for _ in range(reps)])
+    b1, s1 = float(np.median(single[:, 0])), float(np.median(single[:, 1]))
+    walls = []
+    with ThreadPoolExecutor(cores) as ex:
+        run_all = lambda: list(ex.map(lambda i: job(i * PER, (i + 1) * PER), range(cores)))
+        run_all()
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            run_all()
+            walls.append(time.perf_counter() - t0)
+    wall = float(np.median(walls))
+    n_prims = int((np.abs(P["cuboid_dims"][0]).min(axis=1) > 1e-8).sum() + ((np.abs(P["cylinder_radii"][0]).reshape(-1) > 1e-8) &
+                                                                              (np.abs(P["cylinder_heights"][0]).reshape(-1) > 1e-8)).sum())
+    return {"workload": "configs[0]: 1 tabletop problem, 4096-pt obstacle cloud build + 50-pose x %d-sphere x %d-primitive SDF sweep, no network"
+                        % (tables.sphere_centers.shape[0], n_prims),
+            "reps": reps, "kind": "port",
+            "threads_1": {"build_cloud_ms": 1e3 * b1, "sweep_50_poses_ms": 1e3 * s1, "problems_per_s": 1.0 / (b1 + s1),
+                          "pose_checks_per_s": 50.0 / s1},
+            "all_cores": {"cores": cores, "problems_per_call_and_thread": PER, "wall_ms": 1e3 * wall, "problems_per_s": cores * PER / wall,
+                          "pose_checks_per_s": 50.0 * cores * PER / wall},
+            "reference_classes_note": "the real TorchCuboids/TorchCylinders.sdf_sequence (geometry.py:290-347,509-568) need /root/reference, "
+                                      "which does not exist on the GPU box: timed by scripts/cpu_baseline_config0.py in the build container "
+                                      "(profiles/r2_cpu_baseline_config0.json)"}
+
+
+def cpu_baseline(seed: int, config: int, budget_s: float = 10.0, n_problems: int = 16, steps: int = 4, max_calls: int = 8):
     """bounded sample of the bench workload on the host cores: calls of (n_problems x steps) until ~budget_s of CPU work"""
-    port = CpuPort(n_problems, seed)
+    port = CpuPort(n_problems, seed, config)
     port.run(1)   # warm-up (thread pools, page faults)
     total, calls = 0.0, 0
     while calls < max_calls and (calls == 0 or total < budget_s):
         total += port.run(steps)
         calls += 1
     done = calls * n_problems * steps
-    return {"value": done / total, "unit": "env steps/s", "cores": port.threads, "kind": "port",
-            "sample": f"{calls} x ({n_problems} problems x {steps} steps) of the same workload = {done} problem-steps in {total:.1f} s "
-                      f"(cloud build excluded), torch-CPU fp32 MLPs + C oracle geometry"}
+    out = {"value": done / total, "unit": "env steps/s", "cores": port.threads, "kind": "port",
+           "sample": f"{calls} x ({n_problems} problems x {steps} steps) of the same workload = {done} problem-steps in {total:.1f} s "
+                     f"(cloud build excluded), torch-CPU fp32 MLPs + C oracle geometry"}
+    try:
+        out["config0"] = cpu_config0()
+    except Exception as e:   # the baseline leg must not take the bench line down
+        out["config0"] = {"error": repr(e)}
+    return out
 
 
 def run_reference(args):
@@ -140,8 +220,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = args.workload or (2 if args.gpus == 1 else 4)
+    if wl == 5:
+        print(json.dumps({"impl": "reference", "unavailable": "the training step has no CPU reference arm (torch.autograd oracle is a test checker only)"}))
+        return
     n = 16
-    port = CpuPort(n, 1)
+    port = CpuPort(n, 1, wl)
     for _ in range(max(args.warmup, 1)):
         port.run(1)
     total = 0.0
@@ -151,7 +235,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "configs[1]: tabletop problems, 6272-pt clouds, lock-step policy rollout + SDF sweep",
+            "config": {"workload": f"{WORKLOADS[wl]['baseline']}: {WORKLOADS[wl]['desc']}; 6272-pt clouds, lock-step policy rollout + SDF sweep",
                        "sample": f"{n} problems x 1 step per bench step"},
             "cpu_baseline": {"value": value, "unit": "env steps/s", "cores": port.threads, "kind": "port",
                              "sample": f"{n} problems x {args.steps} steps (cloud build excluded), torch-CPU MLPs + C oracle geometry"},
@@ -159,31 +243,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def main():
-    # keep stdout to the single JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION / WARN / INFO
-    os.environ.pop("NCCL_DEBUG", None)
-    if os.environ.get("MPN_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = os.environ["MPN_NCCL_DEBUG"]
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mpn_nccl_%h_%p.log")
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--precision", default=os.environ.get("MPN_BENCH_PRECISION", "auto"))
-    ap.add_argument("--problems-per-gpu", type=int, default=PROBLEMS_PER_GPU)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-
+def setup_dist():
+    """torch.distributed over NCCL when launched by torchrun.  NCCL's own log lines (NCCL_DEBUG set by the caller) are sent to
+    stderr so that stdout stays the single JSON line and the communicator lines remain checkable."""
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     import torch
     import torch.distributed as dist
-    from mpinets_b200 import scenes, _lib
-    from mpinets_b200.engine import Engine
-    from mpinets_b200.parallel import gather_metrics, shard_range
-    from oracle import oracle as O   # only for reference_state_dict (weights init) and the cpu_baseline leg
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,73 +257,252 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B, K, W = args.problems_per_gpu, args.steps, max(args.warmup, 3)
+        t = torch.ones(1, device="cuda")
+        dist.all_reduce(t)   # communicator creation outside every timed region
+        assert int(t.item()) == world
+        print(f"[bench] rank {rank}/{world} on cuda:{local}: NCCL {'.'.join(map(str, torch.cuda.nccl.version()))} communicator up, "
+              f"nranks={world}", file=sys.stderr, flush=True)
+    return world, rank, local
+
+
+def roofline_of(stages, per_stage, B, peaks, mode, traffic):
+    total_stage_ms = sum(v["ms"] for v in stages.values())
+    dom = max((k for k in per_stage if k in FLOP_PER_STEP or k in BYTES_PER_STEP), key=lambda k: stages[k]["ms"])
+    tkey = dom + ("_x3" if mode == "bf16x3" else "")
+    dom_traffic = traffic[tkey]["dram_bytes_per_problem"] * B if tkey in traffic else None
+    if dom in FLOP_PER_STEP:
+        ach = FLOP_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e12
+        peak = peaks["bf16_sustained"]
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": dom_traffic, "peak_source": peaks["source"] + ", sustained bf16",
+                "algorithmic_flop_per_launch": FLOP_PER_STEP[dom] * B, "avg_launch_ms": per_stage[dom],
+                "share_of_step": stages[dom]["ms"] / total_stage_ms}
+        if mode == "bf16x3":
+            f = X3_MMA_FACTOR.get(dom, 3.0)
+            roof["note"] = ("algorithmic flops = the fp32 reference formulation; the bf16x3 mode issues %.2f bf16 MMA flops per "
+                            "algorithmic flop (a_hi w_hi + a_lo w_hi + a_hi w_lo), so the tensor pipe runs at frac x %.2f" % (f, f))
+            roof["issued_mma_frac_of_peak"] = ach * f / peak
+    else:
+        ach = BYTES_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": dom_traffic, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_launch": BYTES_PER_STEP[dom] * B, "avg_launch_ms": per_stage[dom],
+                "share_of_step": stages[dom]["ms"] / total_stage_ms}
+    return roof
+
+
+def run_training(args, world, rank, local):
+    """--workload 5 (BASELINE configs[4]): one training step = forward with saved state + both losses + backward to all 19.07 M
+    parameters (mpn_train_step_grads) -> NCCL all-reduce-mean of the flat gradient vector -> clip_grad_norm_(1.0) + Adam."""
+    import torch
+    import torch.distributed as dist
+    from mpinets_b200 import scenes, _lib
+    from mpinets_b200.engine import Engine
+    from mpinets_b200.parallel import allreduce_mean_, broadcast_params_
+    from oracle import oracle as O   # weights init only
+    B = args.samples_per_gpu
+    K, W = args.steps, max(args.warmup, 3)
+    precision = "bf16" if args.precision in ("auto", "bf16x3") else args.precision
+    prec = _lib.PRECISIONS[precision]
     eng = Engine(device=local)
     eng.load_state_dict(O.reference_state_dict(0))
-    eng.reserve(B)
-    precision = args.precision
-    if precision == "auto":
-        precision = "bf16"
-        try:
-            eng.encoder_forward(torch.zeros(1, 6272, 4, device="cuda"), _lib.PREC_BF16)
-            torch.cuda.synchronize()
-        except _lib.MpnError:
-            precision = "fp32"
-    prec = _lib.PREC_BF16 if precision == "bf16" else _lib.PREC_FP32
-
-    # ---- problems: host (pinned) SoA, shard = rank's contiguous block of problem indices
-    lo, hi = shard_range(rank, world, world * B)
-    assert (lo, hi) == (rank * B, (rank + 1) * B)
-    p = scenes.config_problems(2, B, problem0=lo)
+    broadcast_params_(eng)
+    p = scenes.config_problems(4, B, problem0=rank * B)
     host = {k: torch.from_numpy(np.ascontiguousarray(p[k])).pin_memory() for k in scenes.SCENE_KEYS + ("q0", "target")}
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
-
-    def upload():
-        return {k: v.cuda(non_blocking=True) for k, v in host.items()}
-
-    d = upload()
+    d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
     sc = {k: d[k] for k in scenes.SCENE_KEYS}
     cloud = eng.build_cloud(sc, d["q0"], d["target"], problem0=rank * B)
-    traj = torch.empty(B, K + 1, 7, device="cuda")
-    metrics = torch.empty(B, _lib.METRICS_COLS, device="cuda")
+    qn = eng.normalize(d["q0"])
+    gen = torch.Generator(device="cuda").manual_seed(rank)
+    sup = torch.clamp(qn + 0.05 * torch.randn(qn.shape, generator=gen, device="cuda"), -1, 1)
+    grads = torch.empty(eng.param_count, device="cuda")
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(i, rec=None):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        losses, _, _ = eng.train_step_grads(sc, cloud, qn, sup, grads=grads, precision=prec)
+        e[1].record()
+        allreduce_mean_(grads)
+        e[2].record()
+        eng.adam_step(grads, i + 1)
+        e[3].record()
+        if rec is not None:
+            rec.append(e)
+        return losses
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (W untimed steps), then exactly K timed steps
-    eng.rollout(sc, cloud, d["q0"], d["target"], W, check_every_step=True, precision=prec)
+    for i in range(W):
+        step(i)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
-    eng.profile(True)
-    l0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rec, l0 = [], eng.launch_count
+    e0, e1 = ev(), ev()
     barrier()
-    ev0.record()
-    eng.rollout(sc, cloud, d["q0"], d["target"], K, check_every_step=True, precision=prec, traj=traj, metrics=metrics)
-    if world > 1:
-        gathered = gather_metrics(metrics, world * B)    # the single collective: final metrics table (NCCL all-gather)
-    ev1.record()
+    e0.record()
+    for i in range(K):
+        losses = step(W + i, rec)
+    e1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count - l0
-    stages = eng.profile_read()
-    eng.profile(False)
     clk = clocks.stop()
-    t = torch.tensor([ms], device="cuda")
+    launches = eng.launch_count - l0
+    ph = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in rec]).mean(axis=0)
+    # e2e: host-resident batch -> H2D -> cloud build (the data loader's per-item CPU work in the reference) -> step -> D2H of the losses
+    loss_h = torch.empty(2).pin_memory()
+    barrier()
+    x0, x1 = ev(), ev()
+    x0.record()
+    for i in range(K):
+        d2 = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+        sc2 = {k: d2[k] for k in scenes.SCENE_KEYS}
+        cloud2 = eng.build_cloud(sc2, d2["q0"], d2["target"], problem0=rank * B)
+        qn2 = eng.normalize(d2["q0"])
+        l2, _, _ = eng.train_step_grads(sc2, cloud2, qn2, sup, grads=grads, precision=prec)
+        allreduce_mean_(grads)
+        eng.adam_step(grads, W + K + i + 1)
+        loss_h.copy_(l2, non_blocking=True)
+    x1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1), x0.elapsed_time(x1), ph[0], ph[1], ph[2]], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    t = t.cpu().numpy()
+    if rank == 0:
+        peaks = load_peaks()
+        flop = 3 * FLOP_TOTAL * B   # forward + data gradients + weight gradients of the same contractions
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        line = {"metric": "training samples/sec (PointNetEncoder fwd+bwd + CollisionLoss + BC loss, DDP all-reduce, clip + Adam)",
+                "value": world * B * K / (t[0] / 1000.0), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": float(t[0] / K), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision,
+                "data": "synthetic", "gpu_launches": launches, "clocks": clk,
+                "config": {"workload": "configs[4]: training step, %d samples per GPU (mixed scenes), encoder + heads fwd+bwd, "
+                                       "CollisionAndBCLossContainer (1024 robot points, margin 0.03, weights 5/1), DDP all-reduce of 19.07 M "
+                                       "fp32 gradients, clip 1.0 + Adam 1e-4" % B,
+                           "samples_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
+                           "precision": precision + (" operands on tcgen05, fp32 master weights / accumulation / optimizer state" if precision == "bf16" else ""),
+                           "l2": "inputs larger than L2 (clouds %d MB/GPU)" % (B * 6272 * 16 // 2 ** 20), "weights": "random init, seed 0"},
+                "e2e": {"value": world * B * K / (t[1] / 1000.0), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                        "ms_total": float(t[1]), "note": "per step: pinned H2D of the problem SoA, GPU cloud build, training step, D2H of the losses"},
+                "phases_ms": {"forward_backward": float(t[2]), "grad_allreduce": float(t[3]), "clip_adam_repack": float(t[4])},
+                "roofline": {"kernel": "whole training step", "bound": "tensor", "achieved": flop / (t[0] / K / 1000.0) / 1e12,
+                             "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": flop / (t[0] / K / 1000.0) / 1e12 / peaks["bf16_sustained"],
+                             "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                             "algorithmic_flop_per_launch": flop, "note": "3 x the forward's algorithmic contraction flops per sample"},
+                "losses": [float(x) for x in losses.cpu()], "params": 19068103}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", type=int, default=0, choices=[0, 2, 3, 4, 5])
+    ap.add_argument("--precision", default=os.environ.get("MPN_BENCH_PRECISION", "auto"), choices=["auto", "bf16x3", "bf16", "fp32"])
+    ap.add_argument("--problems-per-gpu", type=int, default=PROBLEMS_PER_GPU)
+    ap.add_argument("--samples-per-gpu", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the fast-mode / extra-workload / parity legs (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world, rank, local = setup_dist()
+    if args.workload == 5:
+        return run_training(args, world, rank, local)
+    import torch
+    import torch.distributed as dist
+    from mpinets_b200 import scenes, _lib
+    from mpinets_b200.engine import Engine
+    from mpinets_b200.parallel import gather_metrics, shard_range
+    from oracle import oracle as O   # reference_state_dict (weights init), the parity checker and the cpu_baseline leg -- never timed as product
+
+    wl = args.workload or (2 if world == 1 else 4)
+    B, K, W = args.problems_per_gpu, args.steps, max(args.warmup, 3)
+    eng = Engine(device=local)
+    sd = O.reference_state_dict(0)
+    eng.load_state_dict(sd)
+    eng.reserve(B)
+    precision = "bf16x3" if args.precision == "auto" else args.precision
+    prec = _lib.PRECISIONS[precision]
+
+    # ---- problems: host (pinned) SoA, shard = rank's contiguous block of problem indices
+    lo, hi = shard_range(rank, world, world * B)
+    assert (lo, hi) == (rank * B, (rank + 1) * B)
+
+    def make_inputs(config):
+        p = scenes.config_problems(config, B, problem0=lo)
+        host = {k: torch.from_numpy(np.ascontiguousarray(p[k])).pin_memory() for k in scenes.SCENE_KEYS + ("q0", "target")}
+        return p, host
+
+    p, host = make_inputs(wl)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+
+    def upload(h):
+        return {k: v.cuda(non_blocking=True) for k, v in h.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_job(h, prec_, steps, warm, profile=False, sample_clocks=False):
+        """W untimed warm-up steps, then exactly `steps` timed lock-step steps on resident inputs (+ the metrics gather)"""
+        d = upload(h)
+        sc = {k: d[k] for k in scenes.SCENE_KEYS}
+        cloud = eng.build_cloud(sc, d["q0"], d["target"], problem0=rank * B)
+        traj = torch.empty(B, steps + 1, 7, device="cuda")
+        metrics = torch.empty(B, _lib.METRICS_COLS, device="cuda")
+        if warm:
+            eng.rollout(sc, cloud, d["q0"], d["target"], warm, check_every_step=True, precision=prec_)
+            cloud = eng.build_cloud(sc, d["q0"], d["target"], problem0=rank * B)   # the timed rollout starts from t = 0 again
+        barrier()
+        clocks = ClockSampler(local) if sample_clocks else None
+        if clocks:
+            clocks.start()
+        if profile:
+            eng.profile(True)
+        l0 = eng.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        eng.rollout(sc, cloud, d["q0"], d["target"], steps, check_every_step=True, precision=prec_, traj=traj, metrics=metrics)
+        gathered = gather_metrics(metrics, world * B) if world > 1 else metrics   # the single collective: final metrics table
+        ev1.record()
+        barrier()
+        out = {"ms": maxr(ev0.elapsed_time(ev1)), "launches": eng.launch_count - l0, "traj": traj, "metrics": metrics,
+               "gathered": gathered, "d": d, "sc": sc}
+        if profile:
+            out["stages"] = eng.profile_read()
+            eng.profile(False)
+        if clocks:
+            out["clocks"] = clocks.stop()
+        return out
+
+    main_run = timed_job(host, prec, K, W, profile=True, sample_clocks=True)
+    ms, stages, clk = main_run["ms"], main_run["stages"], main_run["clocks"]
     value = world * B * K / (ms / 1000.0)
+    d, sc, traj, metrics = main_run["d"], main_run["sc"], main_run["traj"], main_run["metrics"]
 
     # ---- e2e: host buffers -> H2D -> cloud build -> K steps -> D2H traj + metrics, all inside the timed region
     traj_h = torch.empty(B, K + 1, 7).pin_memory()
     metrics_h = torch.empty(B, _lib.METRICS_COLS).pin_memory()
-    # the one-off cloud build (FK + 6272 rows per problem), timed on its own with CUDA events
     bms = []
-    for _ in range(3):
+    for _ in range(3):   # the one-off cloud build (FK + 6272 rows per problem), timed on its own with CUDA events
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0.record()
         cloud_tmp = eng.build_cloud(sc, d["q0"], d["target"], problem0=rank * B)
@@ -269,46 +514,100 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    d2 = upload()
+    d2 = upload(host)
     sc2 = {k: d2[k] for k in scenes.SCENE_KEYS}
     cloud2 = eng.build_cloud(sc2, d2["q0"], d2["target"], problem0=rank * B)
     eng.rollout(sc2, cloud2, d2["q0"], d2["target"], K, check_every_step=True, precision=prec, traj=traj, metrics=metrics)
+    if world > 1:
+        gather_metrics(metrics, world * B)
     traj_h.copy_(traj, non_blocking=True)
     metrics_h.copy_(metrics, non_blocking=True)
     e1.record()
     barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t2.item())
+    e2e_ms = maxr(e0.elapsed_time(e1))
     e2e_value = world * B * K / (e2e_ms / 1000.0)
     d2h_bytes = traj_h.numel() * 4 + metrics_h.numel() * 4
+    del d2, sc2, cloud2
+
+    # ---- the same job in the bf16 throughput mode (every rank runs it: same barriers)
+    fast = None
+    if precision != "bf16" and not args.no_extra:
+        fr = timed_job(host, _lib.PREC_BF16, K, W, profile=True)
+        fast = {"dtype": "bf16", "value": world * B * K / (fr["ms"] / 1000.0), "unit": "env steps/s", "ms_per_step": fr["ms"] / K,
+                "gpu_launches": fr["launches"], "stage_ms_per_step": {k: v["ms"] / K for k, v in fr["stages"].items() if v["launches"]},
+                "collision_rate": float(fr["metrics"][:, 0].mean().item()), "_run": fr}
+
+    # ---- configs[2] next to the N = 1 default: cubby + dresser, the full T = 70 rollout with the per-step check
+    extra = {}
+    if world == 1 and wl == 2 and not args.no_extra:
+        p3, host3 = make_inputs(3)
+        r3 = timed_job(host3, prec, 70, 1, profile=False)
+        extra["configs[2]"] = {"workload": WORKLOADS[3]["desc"] + ", full 70-step rollout", "dtype": precision, "steps": 70,
+                               "value": B * 70 / (r3["ms"] / 1000.0), "unit": "env steps/s", "ms_per_step": r3["ms"] / 70,
+                               "collision_rate": float(r3["metrics"][:, 0].mean().item()),
+                               "collision_flag_match": float((O.sweep_flags(p3, r3["traj"].cpu().numpy(), eng.tables)[0] ==
+                                                              r3["metrics"][:, 0].cpu().numpy().astype(np.uint8)).mean())}
+        del r3, host3
+
+    # ---- match fields of the metric, against the CPU oracle, outside every timed region (rank 0's shard)
+    parity = None
+    if rank == 0 and not args.no_extra:
+        _host_threads()
+        th = traj.cpu().numpy()
+        gflags = metrics[:, 0].cpu().numpy().astype(np.uint8)
+        oflags, ofirst, _ = O.sweep_flags(p, th, eng.tables)                      # all B problems: GPU sweep vs CPU sweep of the same trajectories
+        n_sub = 64
+        sub = np.arange(0, B, max(1, B // n_sub))[:n_sub]
+        subt = torch.from_numpy(sub).cuda()
+        psub = {k: v[sub] for k, v in p.items() if isinstance(v, np.ndarray)}
+        cloud0 = eng.build_cloud(sc, d["q0"], d["target"], problem0=rank * B)      # the t = 0 clouds (the rollout rewrote the robot rows)
+        c_sub = cloud0[subt].contiguous()
+        oc = np.concatenate([O.build_cloud(psub["q0"][j:j + 1], psub["target"][j:j + 1], {k: v[j:j + 1] for k, v in psub.items()}, eng.tables,
+                                           eng.cfg.seed, problem0=rank * B + int(i)) for j, i in enumerate(sub)])
+        cloud_match = float(np.mean([np.array_equal(c_sub[j].cpu().numpy(), oc[j]) for j in range(len(sub))]))
+        fidx = eng.fps(c_sub, 512).cpu().numpy()
+        ofidx = O.fps(oc, 512)
+        qn_sub = O.normalize(psub["q0"], eng.tables.joint_limits)
+        odq = O.policy_forward(sd, oc, qn_sub).numpy()
+        qn_dev = torch.from_numpy(qn_sub).cuda()
+        dq_main = eng.policy_forward(c_sub, qn_dev, prec).cpu().numpy()
+        # the mode's rollout against the fp32 SIMT parity mode of the library on a 256-problem subset, K steps
+        n256 = min(256, B)
+        s256 = torch.arange(0, B, max(1, B // n256), device="cuda")[:n256]
+        sc256 = {k: sc[k][s256].contiguous() for k in scenes.SCENE_KEYS}
+        q256, t256 = d["q0"][s256].contiguous(), d["target"][s256].contiguous()
+        c256 = cloud0[s256].contiguous()
+        del cloud0
+        _, m32 = eng.rollout(sc256, c256, q256, t256, K, check_every_step=True, precision=_lib.PREC_FP32)
+        f32flags = m32[:, 0].cpu().numpy().astype(np.uint8)
+        parity = {"oracle": "oracle/ (CPU restatement; C geometry + torch-CPU fp32 network), outside the timed regions",
+                  "collision_flag_match": float((gflags == oflags).mean()), "first_collision_step_match": float((metrics[:, 1].cpu().numpy().astype(np.int32) == ofirst).mean()),
+                  "collision_flag_problems": int(B),
+                  "cloud_match": cloud_match, "fps_idx_match": float(np.mean([np.array_equal(fidx[j], ofidx[j]) for j in range(len(sub))])),
+                  "dq_max_abs_err": float(np.abs(dq_main - odq).max()), "dq_tolerance": 1e-5, "subset_problems": int(len(sub)),
+                  "flags_equal_fp32_mode_rollout": float((gflags[s256.cpu().numpy()] == f32flags).mean()), "fp32_mode_subset_problems": int(n256),
+                  "rollout_steps": K}
+        if fast is not None:
+            dq_fast = eng.policy_forward(c_sub, qn_dev, _lib.PREC_BF16).cpu().numpy()
+            fast["dq_max_abs_err"] = float(np.abs(dq_fast - odq).max())
+            ff = fast["_run"]["metrics"][:, 0].cpu().numpy().astype(np.uint8)
+            fast["flags_equal_fp32_mode_rollout"] = float((ff[s256.cpu().numpy()] == f32flags).mean())
+            fast["flags_equal_parity_mode"] = float((ff == gflags).mean())
+    if fast is not None:
+        fast.pop("_run", None)
 
     if rank == 0:
         peaks = load_peaks()
-        per_stage = {k: (v["ms"] / max(v["launches"], 1)) for k, v in stages.items() if v["launches"]}
-        total_stage_ms = sum(v["ms"] for v in stages.values())
-        dom = max((k for k in per_stage if k in FLOP_PER_STEP or k in BYTES_PER_STEP), key=lambda k: stages[k]["ms"])
         traffic = load_traffic()
-        dom_traffic = traffic[dom]["dram_bytes_per_problem"] * B if dom in traffic else None
-        if dom in FLOP_PER_STEP:
-            ach = FLOP_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e12
-            peak = peaks["bf16_sustained"]
-            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": dom_traffic, "peak_source": peaks["source"] + ", sustained bf16",
-                    "algorithmic_flop_per_launch": FLOP_PER_STEP[dom] * B, "avg_launch_ms": per_stage[dom],
-                    "share_of_step": stages[dom]["ms"] / total_stage_ms}
-        else:
-            ach = BYTES_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e9
-            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": dom_traffic, "peak_source": peaks["source"],
-                    "algorithmic_bytes_per_launch": BYTES_PER_STEP[dom] * B, "avg_launch_ms": per_stage[dom],
-                    "share_of_step": stages[dom]["ms"] / total_stage_ms}
+        per_stage = {k: (v["ms"] / max(v["launches"], 1)) for k, v in stages.items() if v["launches"]}
+        roof = roofline_of(stages, per_stage, B, peaks, precision, traffic)
         tensor_kernels = {}
         for k in ("sa1", "sa2", "sa3", "fc"):
             if k in per_stage:
                 tf = FLOP_PER_STEP[k] * B / (per_stage[k] / 1000.0) / 1e12
                 tensor_kernels[k] = {"TFLOPs": tf, "frac_of_bf16_sustained": tf / peaks["bf16_sustained"], "ms": per_stage[k]}
+                if precision == "bf16x3":
+                    tensor_kernels[k]["issued_mma_frac_of_bf16_sustained"] = tf * X3_MMA_FACTOR[k] / peaks["bf16_sustained"]
         hbm_kernels = {}
         for k in ("sample_robot", "sweep", "fps1"):
             if k in per_stage:
@@ -317,16 +616,19 @@ def main():
         g = (BYTES_PER_STEP["build_cloud"] + 3276) * B / (build_ms / 1000.0) / 1e9
         hbm_kernels["build_cloud"] = {"GBps": g, "frac_of_hbm_peak": g / peaks["hbm_gbs"], "avg_launch_ms": build_ms,
                                       "note": "one-off per problem (FK kernel + cloud kernel + output allocation), outside the timed regions"}
+        prec_desc = {"bf16x3": "bf16x3: split-bf16 operands (hi + lo, three MMAs per product) on tcgen05, fp32 accumulate -- the parity-grade mode",
+                     "bf16": "bf16 operands on tcgen05, fp32 accumulate -- the throughput mode", "fp32": "fp32 SIMT FMA parity mode"}[precision]
         line = {
             "metric": METRIC, "value": value, "unit": "env steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if precision == "bf16" else "fp32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 4096 tabletop PlanningProblems per GPU, 6272-pt clouds (2048 robot + 4096 obstacle + 128 target), "
+            "dtype": precision, "data": "synthetic",
+            "config": {"workload": f"{WORKLOADS[wl]['baseline']}: {WORKLOADS[wl]['desc']}; 6272-pt clouds (2048 robot + 4096 obstacle + 128 target), "
                                    "lock-step policy rollout (FK + cloud resample + PointNet++ + delta-q + per-step SDF sweep)",
                        "problems_per_gpu": B, "global_problems": world * B, "parallelism": f"problem-sharded x{world}",
-                       "precision": precision + (" (tcgen05, fp32 accumulate)" if precision == "bf16" else " (SIMT FMA parity mode)"),
+                       "rollout_length_of_config": WORKLOADS[wl]["rollout_T"], "timed_steps": K,
+                       "precision": prec_desc,
                        "l2": "inputs larger than L2 (clouds 411 MB/GPU per step)", "weights": "random init, seed 0"},
-            "gpu_launches": launches, "clocks": clk,
+            "gpu_launches": main_run["launches"], "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "env steps/s", "h2d_bytes_per_step": h2d_bytes / K, "d2h_bytes_per_step": d2h_bytes / K,
                     "ms_total": e2e_ms},
             "roofline": roof,
@@ -334,12 +636,25 @@ def main():
             "hbm_kernels": hbm_kernels, "tensor_kernels": tensor_kernels,
             "tensor_flops_per_step": FLOP_TOTAL * B,
             "achieved_tflops_whole_step": FLOP_TOTAL * B * K * world / (ms / 1000.0) / 1e12,
-            "collision_rate": float(metrics[:, 0].mean().item()),
+            "collision_rate": float(main_run["gathered"][:, 0].mean().item()),
         }
+        if world > 1:
+            line["nccl"] = {"version": ".".join(map(str, torch.cuda.nccl.version())), "nranks": world, "collectives_in_timed_region": 1,
+                            "gathered_rows": int(main_run["gathered"].shape[0])}
+        if parity is not None:
+            line["parity"] = parity
+            line["collision_flag_match"] = parity["collision_flag_match"]
+            line["fps_idx_match"] = parity["fps_idx_match"]
+            line["dq_max_abs_err"] = parity["dq_max_abs_err"]
+        if fast is not None:
+            line["fast_mode"] = fast
+        if extra:
+            line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only: the other ranks must not wait on 10 s of CPU work
-            line["cpu_baseline"] = cpu_baseline(eng.cfg.seed)
+            line["cpu_baseline"] = cpu_baseline(eng.cfg.seed, wl)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

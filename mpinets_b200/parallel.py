@@ -42,3 +42,15 @@ def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat.div_(dist.get_world_size())
     return flat
+
+
+def broadcast_params_(engine, src: int = 0) -> None:
+    """What DistributedDataParallel does when it wraps a module (run_training.py:71-77): every rank starts from rank `src`'s
+    parameters.  Broadcasts the engine's flat parameter vector and re-packs the tensor-core weight copies.  No-op for a single
+    process."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    flat = engine.get_params()
+    dist.broadcast(flat, src=src)
+    engine.set_params(flat)
+    engine.weights_sync()
