@@ -98,6 +98,11 @@ int mpn_sa_forward(mpn_ctx* ctx, void* stream, int module, int precision, const 
 int mpn_fk(mpn_ctx* ctx, void* stream, const float* q, int B, float* frames, float* eef);
 /* FrankaSampler.sample(q, n): writes rows [0,n) of cloud [B][rows][4] as (x,y,z,0); subset keyed by (seed, step) */
 int mpn_sample_robot(mpn_ctx* ctx, void* stream, const float* q, int B, int n, uint32_t step, float* cloud, int rows);
+/* FrankaSampler.sample_end_effector(poses, n, frame="right_gripper") (run_inference.py:113-116, data_loader.py:158-161,
+ * planning_node.py:71-74): n gripper-surface points (hand + fingers, table given in the right_gripper frame) transformed by each
+ * pose [B][12] (3x4 row-major) -> out [B][n][3].  The subset is keyed by (seed, problem0 + b) exactly like the target rows of
+ * mpn_build_cloud, i.e. out[b] == cloud[b][n_robot + n_obstacle : ][:, :3] for n = n_target. */
+int mpn_sample_end_effector(mpn_ctx* ctx, void* stream, const float* poses, int B, int n, uint32_t problem0, float* out);
 /* FrankaCollisionSampler.compute_spheres: q [B][7] -> world centres [B][S][3] */
 int mpn_compute_spheres(mpn_ctx* ctx, void* stream, const float* q, int B, float* centers);
 /* utils.(un)normalize_franka_joints with the loaded limits */

@@ -466,6 +466,13 @@ int mpn_sample_robot(mpn_ctx* c, void* stream, const float* q, int B, int n, uin
   return launch_sample_robot(c, (cudaStream_t)stream, c->ws.frames, B, n, step, cloud, rows);
 }
 
+int mpn_sample_end_effector(mpn_ctx* c, void* stream, const float* poses, int B, int n, uint32_t problem0, float* out) {
+  REQ_CTX(c); REQ_TABLES(c);
+  MPN_REQUIRE(poses && out && n >= 1 && n <= c->Pe, "mpn_sample_end_effector: need 1 <= n <= %d gripper points", c->Pe);
+  if (B == 0) return MPN_OK;
+  return launch_sample_end_effector(c, (cudaStream_t)stream, poses, B, n, problem0, out);
+}
+
 int mpn_compute_spheres(mpn_ctx* c, void* stream, const float* q, int B, float* centers) {
   REQ_CTX(c); REQ_TABLES(c);
   MPN_REQUIRE(q && centers, "mpn_compute_spheres: null pointer");

@@ -164,6 +164,7 @@ int launch_sdf_points(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, co
 int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* frames, const float* target,
                        uint32_t problem0, float* cloud, const float* obs_points = nullptr, const int32_t* obs_count = nullptr,
                        int obs_max = 0);
+int launch_sample_end_effector(mpn_ctx* c, cudaStream_t s, const float* poses, int B, int n, uint32_t problem0, float* out);
 int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T, int traj_stride_t,
                  int t0, int accumulate, uint8_t* flags, int32_t* first_step, const float* frames_in = nullptr);
 int launch_evaluate(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T1, const int32_t* num_poses,

@@ -327,6 +327,35 @@ int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, c
   return MPN_OK;
 }
 
+// FrankaSampler.sample_end_effector (run_inference.py:113-116; data_loader.py:158-161; planning_node.py:71-74): n gripper points
+// (hand + fingers, given in the right_gripper frame) transformed by each pose.  The subset is the same keyed Feistel permutation as
+// the target rows of build_cloud_kernel, so out[b] equals rows [Nr + No, Nr + No + n) of the cloud built for problem problem0 + b.
+__global__ void __launch_bounds__(128) sample_end_effector_kernel(const float* __restrict__ poses, int n, int Pe, const float* __restrict__ ee,
+                                                                   uint32_t seed_lo, uint32_t seed_hi, uint32_t problem0,
+                                                                   float* __restrict__ out) {
+  __shared__ float TG[12];
+  __shared__ uint32_t key[4];
+  const int b = blockIdx.x;
+  if (threadIdx.x < 12) TG[threadIdx.x] = poses[(size_t)b * 12 + threadIdx.x];
+  if (threadIdx.x == 0) philox4x32(0u, problem0 + (uint32_t)b, STREAM_TARGET_PERM, 0u, seed_lo, seed_hi, key);
+  __syncthreads();
+  const uint32_t half = feistel_bits((uint32_t)Pe) / 2;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const uint32_t e = feistel_perm((uint32_t)j, (uint32_t)Pe, half, key);
+    float x, y, z;
+    m34_apply(TG, __ldg(ee + 3 * e), __ldg(ee + 3 * e + 1), __ldg(ee + 3 * e + 2), x, y, z);
+    float* o = out + ((size_t)b * n + j) * 3;
+    o[0] = x; o[1] = y; o[2] = z;
+  }
+}
+
+int launch_sample_end_effector(mpn_ctx* c, cudaStream_t s, const float* poses, int B, int n, uint32_t problem0, float* out) {
+  sample_end_effector_kernel<<<B, 128, 0, s>>>(poses, n, c->Pe, c->ee_points, (uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32), problem0, out);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ collision sweep
 // One CTA per problem.  Primitive inverse frames + sphere table in shared memory; timesteps processed in chunks
 // of SWEEP_TCHUNK: one thread per timestep does FK into smem, then all threads sweep (timestep, sphere) pairs.

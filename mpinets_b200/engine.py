@@ -52,6 +52,8 @@ class Engine:
         self.tables = tables if tables is not None else default_tables(max(4096, n_robot))
         self.set_tables(self.tables)
         self._weights_loaded = False
+        self.weights_version = 0      # bumped by every load_state_dict: optimiser state in the library is reset with it
+        self._weights_owner = None    # weakref to the nn.Module whose parameters the context currently holds (model.py)
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -89,6 +91,8 @@ class Engine:
             _lib.check(self.lib.mpn_load_weight(self._ctx, name.encode(), a.ctypes.data, shape, a.ndim))
         _lib.check(self.lib.mpn_weights_finalize(self._ctx))
         self._weights_loaded = True
+        self.weights_version += 1
+        self._weights_owner = None
 
     def reserve(self, max_batch: int):
         _lib.check(self.lib.mpn_reserve(self._ctx, int(max_batch)))
@@ -216,6 +220,14 @@ class Engine:
         _check(cloud, "cloud", device=self.device)
         _lib.check(self.lib.mpn_sample_robot(self._ctx, self.stream, _p(q), B, n, step, _p(cloud), cloud.shape[1]))
         return cloud
+
+    def sample_end_effector(self, poses: torch.Tensor, n: int, problem0: int = 0) -> torch.Tensor:
+        """poses [B,3,4] (right_gripper frame) -> [B,n,3] gripper points; the keyed subset of build_cloud's target rows"""
+        _check(poses, "poses", device=self.device)
+        B = poses.shape[0]
+        out = self._empty(B, n, 3)
+        _lib.check(self.lib.mpn_sample_end_effector(self._ctx, self.stream, _p(poses), B, n, problem0, _p(out)))
+        return out
 
     def compute_spheres(self, q: torch.Tensor):
         _check(q, "q", device=self.device)

@@ -9,11 +9,14 @@ import torch
 from .engine import Engine
 
 _ENGINES: Dict[tuple, Engine] = {}
+_MAX_ENGINES = 16   # contexts are keyed by primitive-row counts; a bounded cache keeps odd shapes from accumulating device memory
 
 
 def _engine_for(device: torch.device, m1: int, m2: int) -> Engine:
     key = (device.index or 0, m1, m2)
     if key not in _ENGINES:
+        if len(_ENGINES) >= _MAX_ENGINES:
+            _ENGINES.pop(next(iter(_ENGINES))).close()
         _ENGINES[key] = Engine(device=key[0], max_cuboids=m1, max_cylinders=m2)
     return _ENGINES[key]
 
@@ -87,7 +90,12 @@ def construct_mixed_point_cloud(obstacles: Sequence, num_points: int, device: in
     cubs = [o for o in obstacles if hasattr(o, "dims")]
     cyls = [o for o in obstacles if hasattr(o, "radius")]
     m1, m2 = max(1, len(cubs)), max(1, len(cyls))
-    eng = Engine(device=device, n_robot=1, n_obstacle=num_points, n_target=0, max_cuboids=m1, max_cylinders=m2)
+    key = ("cloud", device, num_points, m1, m2)
+    if key not in _ENGINES:
+        if len(_ENGINES) >= _MAX_ENGINES:   # bounded cache: drop (and close) the oldest context
+            _ENGINES.pop(next(iter(_ENGINES))).close()
+        _ENGINES[key] = Engine(device=device, n_robot=1, n_obstacle=num_points, n_target=0, max_cuboids=m1, max_cylinders=m2)
+    eng = _ENGINES[key]
     f = lambda a: torch.tensor(np.asarray(a, dtype=np.float32), device=eng.device)
     scene = dict(cuboid_centers=torch.zeros(1, m1, 3), cuboid_dims=torch.zeros(1, m1, 3), cuboid_quats=torch.zeros(1, m1, 4),
                  cylinder_centers=torch.zeros(1, m2, 3), cylinder_radii=torch.zeros(1, m2, 1), cylinder_heights=torch.zeros(1, m2, 1),
@@ -103,6 +111,4 @@ def construct_mixed_point_cloud(obstacles: Sequence, num_points: int, device: in
     q0 = torch.zeros(1, 7, device=eng.device)
     target = torch.eye(4, device=eng.device)[:3].unsqueeze(0).contiguous()
     cloud = eng.build_cloud(scene, q0, target, problem0=seed_problem)
-    out = cloud[0, 1:1 + num_points].cpu().numpy().astype(np.float64)
-    eng.close()
-    return out
+    return cloud[0, 1:1 + num_points].cpu().numpy().astype(np.float64)

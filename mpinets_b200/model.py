@@ -3,6 +3,7 @@ state-dict keys as the reference, so a Lightning checkpoint's ``state_dict`` loa
 run in ``libmpinets_b200.so``."""
 from __future__ import annotations
 
+import weakref
 from typing import Callable, Dict, List, Optional
 
 import numpy as np
@@ -15,7 +16,7 @@ from .runtime import get_engine
 
 END_EFFECTOR_FRAME = "right_gripper"   # run_inference.py:51-55
 NUM_ROBOT_POINTS, NUM_OBSTACLE_POINTS, NUM_TARGET_POINTS, MAX_ROLLOUT_LENGTH = 2048, 4096, 128, 150
-PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+PRECISIONS = _lib.PRECISIONS   # "fp32" (SIMT parity mode), "bf16x3" (tensor cores, parity grade), "bf16" (tensor cores, throughput)
 
 
 class MPiNetsPointNet(nn.Module):
@@ -34,9 +35,10 @@ class MPiNetsPointNet(nn.Module):
 
 
 class MotionPolicyNetwork(nn.Module):
-    """model.py:35-91.  ``precision``: "fp32" (1e-5 parity mode) or "bf16" (tcgen05 throughput mode)."""
+    """model.py:35-91.  ``precision``: "bf16x3" (default: split-bf16 operands on tcgen05, delta-q within 1e-5 of the reference's fp32
+    forward), "bf16" (tcgen05 throughput mode, ~2e-4) or "fp32" (SIMT FMA parity mode)."""
 
-    def __init__(self, precision: str = "bf16"):
+    def __init__(self, precision: str = "bf16x3"):
         super().__init__()
         self.point_cloud_encoder = MPiNetsPointNet()
         self.feature_encoder = nn.Sequential(nn.Linear(7, 32), nn.LeakyReLU(), nn.Linear(32, 64), nn.LeakyReLU(),
@@ -44,20 +46,31 @@ class MotionPolicyNetwork(nn.Module):
                                              nn.Linear(128, 64))
         self.decoder = nn.Sequential(nn.Linear(2048 + 64, 512), nn.LeakyReLU(), nn.Linear(512, 256), nn.LeakyReLU(),
                                      nn.Linear(256, 128), nn.LeakyReLU(), nn.Linear(128, 7))
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
         self.precision = precision
         self._synced_device = None
+        self._dirty = False
 
     # -- weights -> engine
     def sync_engine(self, device: Optional[torch.device] = None):
+        """Loads this module's weights into the device's engine context.  The context holds ONE parameter set: if another module
+        owns it and has optimiser updates that exist only in the context, those are pulled back into that module first."""
         eng = get_engine(device)
+        prev = eng._weights_owner() if eng._weights_owner is not None else None
+        if prev is not None and prev is not self and getattr(prev, "_dirty", False):
+            prev.pull_weights()
         eng.load_state_dict(self.state_dict())
+        eng._weights_owner = weakref.ref(self)
         self._synced_device = eng.device
         return eng
 
     def _engine(self, like: torch.Tensor):
-        if self._synced_device != like.device:
+        eng = get_engine(like.device)
+        owner = eng._weights_owner() if eng._weights_owner is not None else None
+        if self._synced_device != like.device or owner is not self:   # never run on another module's weights
             return self.sync_engine(like.device)
-        return get_engine(like.device)
+        return eng
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -122,6 +135,7 @@ class FlatAdam:
         self.module, self.lr, self.betas, self.eps, self.clip_norm = module, lr, betas, eps, clip_norm
         self.steps = 0
         self.last_grad_norm = None
+        self._weights_version = None
 
     def zero_grad(self, set_to_none: bool = True):
         pass   # the training step overwrites the gradient vector
@@ -132,8 +146,14 @@ class FlatAdam:
         if m.grads is None:
             raise RuntimeError("FlatAdam.step() before training_step()")
         allreduce_mean_(m.grads)
+        eng = m._engine(m.grads)
+        if self._weights_version != eng.weights_version:   # the context's parameters were (re)loaded: its Adam moments start from zero
+            if self._weights_version is None:
+                from .parallel import broadcast_params_
+                broadcast_params_(eng)                      # DDP wraps the module with rank 0's parameters (run_training.py:71-77)
+            self._weights_version = eng.weights_version
+            self.steps = 0
         self.steps += 1
-        eng = get_engine(m.grads.device)
         self.last_grad_norm = eng.adam_step(m.grads, self.steps, self.lr, self.betas, self.eps, self.clip_norm)
         m._dirty = True
 
@@ -182,9 +202,23 @@ class TrainingMotionPolicyNetwork(MotionPolicyNetwork):
         if dev is None:
             return
         eng = get_engine(dev)
+        owner = eng._weights_owner() if eng._weights_owner is not None else None
+        if owner is not self:
+            raise RuntimeError("the engine context no longer holds this module's parameters")
         nn.Module.load_state_dict(self, {k: v for k, v in eng.state_dict().items()}, strict=False)
         eng.weights_sync()
         self._dirty = False
+
+    # the optimiser updates the engine's flat parameter vector; the nn.Module copies are refreshed whenever they are read
+    def state_dict(self, *args, **kwargs):
+        if self._dirty:
+            self.pull_weights()
+        return super().state_dict(*args, **kwargs)
+
+    def named_parameters(self, *args, **kwargs):
+        if self._dirty:
+            self.pull_weights()
+        return super().named_parameters(*args, **kwargs)
 
     # -- validation (model.py:252-352)
     VALIDATION_ROLLOUT_LENGTH = 69   # model.py:272

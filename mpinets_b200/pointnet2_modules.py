@@ -42,5 +42,13 @@ class PointnetSAModule(nn.Module):
         eng = get_engine(xyz.device)
         if not eng._weights_loaded:
             raise RuntimeError("load the network weights into the engine first (MotionPolicyNetwork.sync_engine())")
-        new_xyz, out = eng.sa_forward(self.module_index, xyz.contiguous(), features.transpose(1, 2).contiguous(), precision=_lib.PREC_FP32)
+        if precision != _lib.PREC_FP32 and self.module_index == 2:
+            raise NotImplementedError("the group-all module has a per-module entry in the fp32 mode only (the tensor-core modes run it "
+                                      "inside MotionPolicyNetwork.forward / MPiNetsPointNet)")
+        if precision != _lib.PREC_FP32 and self.module_index == 0:
+            # the tensor-core SA1 kernels read [B,N,4] cloud rows (xyz + the mask feature) as 16-byte rows: re-join _break_up_pc's halves
+            cloud = torch.cat([xyz[..., :3], features.transpose(1, 2)], dim=-1).contiguous()
+            new_xyz, out = eng.sa_forward(0, cloud, cloud[..., 3:], precision=precision)
+            return new_xyz, out.transpose(1, 2).contiguous()
+        new_xyz, out = eng.sa_forward(self.module_index, xyz.contiguous(), features.transpose(1, 2).contiguous(), precision=precision)
         return new_xyz, out.transpose(1, 2).contiguous()

@@ -281,6 +281,17 @@ def sample_robot(q, tables, n, seed, step, cloud=None):
     return cloud
 
 
+def sample_end_effector(poses, tables, n, seed, problem0=0):
+    """poses [B,3,4] right_gripper -> [B,n,3] (FrankaSampler.sample_end_effector; the keyed subset of build_cloud's target rows)"""
+    B = np.asarray(poses).shape[0]
+    ps, pp = _f(np.asarray(poses).reshape(B, 12))
+    ee, pee = _f(tables.ee_points)
+    out = np.zeros((B, n, 3), np.float32)
+    lib().mpn_oracle_sample_end_effector(C.c_int(B), pp, C.c_int(ee.shape[0]), pee, C.c_int(n), C.c_uint64(seed), C.c_uint32(problem0),
+                                         out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
 def build_cloud(q0, target, scene, tables, seed, n_robot=2048, n_obs=4096, n_tgt=128, problem0=0):
     """q0 [B,7] unnormalised, target [B,3,4] right_gripper pose -> cloud [B,N,4] (run_inference.py:93-134)."""
     keep, B, M1, M2, ps = _scene_args(scene)

@@ -70,6 +70,19 @@ def test_samplers_and_utils_surface(oracle, tables):
     assert pose.shape == (9, 4, 4) and np.array_equal(pose[:, :3].cpu().numpy(), oracle.fk(q.cpu().numpy())[1])
     ee = s.sample_end_effector(pose, num_points=128)
     assert ee.shape == (9, 128, 3)
+    # on the library (mpn_sample_end_effector): bit-exact against the oracle, and the same keyed subset as the cloud's target rows
+    assert np.array_equal(ee.cpu().numpy(), oracle.sample_end_effector(pose[:, :3].cpu().numpy(), tables, 128, s.engine.cfg.seed, problem0=0))
+    ee2 = s.sample_end_effector(pose, num_points=128)                  # a fresh subset per call, like robofin's np.random.choice
+    assert not torch.equal(ee, ee2)
+    assert np.array_equal(ee2.cpu().numpy(), oracle.sample_end_effector(pose[:, :3].cpu().numpy(), tables, 128, s.engine.cfg.seed, problem0=9))
+    p9 = _problems(9, 2)
+    sc9 = to_dev(p9)
+    cloud9 = s.engine.build_cloud({k: sc9[k] for k in sc9 if k.startswith(("cuboid", "cylinder"))}, sc9["q0"], sc9["target"], problem0=0)
+    assert torch.equal(s.engine.sample_end_effector(sc9["target"], 128, problem0=0), cloud9[:, 2048 + 4096:, :3])
+    with pytest.raises(NotImplementedError):
+        FrankaSampler("cuda:0", with_base_link=False)                  # the default link table carries panda_link0 points
+    with pytest.raises(RuntimeError):
+        FrankaCollisionSampler("cuda:0", with_base_link=True)          # the default sphere table has no panda_link0 sphere
     groups = FrankaCollisionSampler("cuda:0", with_base_link=False).compute_spheres(q)
     assert sum(c.shape[1] for _, c in groups) == tables.sphere_centers.shape[0]
     assert sorted(set(round(r, 4) for r, _ in groups)) == sorted(set(round(float(r), 4) for r in tables.sphere_radii))
@@ -107,7 +120,42 @@ def test_model_surface(oracle, tables, state_dict):
     assert torch.equal(batch["xyz"][:, 2048:], before[:, 2048:])
     mdl.precision = "bf16"
     dq16 = mdl(before, qn)
-    assert (dq16.cpu() - exp).abs().max().item() < 2e-2
+    assert (dq16.cpu() - exp).abs().max().item() < 3e-4
+    mdl.precision = "bf16x3"                                                                       # the default of inference modules
+    assert MotionPolicyNetwork().precision == "bf16x3"
+    assert (mdl(before, qn).cpu() - exp).abs().max().item() <= 1e-5
+    # PointnetSAModule.forward honours its precision argument (fp32 / bf16 / bf16x3 kernels of the same module)
+    from mpinets_b200 import _lib
+    sa1 = mdl.point_cloud_encoder.SA_modules[0]
+    xyz3, feat = before[..., :3].contiguous(), before[..., 3:].transpose(1, 2).contiguous()
+    nx32, f32 = sa1(xyz3, feat)
+    nx3, f3 = sa1(xyz3, feat, precision=_lib.PREC_BF16X3)
+    nxb, fb = sa1(xyz3, feat, precision=_lib.PREC_BF16)
+    assert torch.equal(nx3, nx32) and torch.equal(nxb, nx32)
+    scale = f32.abs().max().item()
+    assert (f3 - f32).abs().max().item() <= 2e-5 * scale and 1e-5 * scale < (fb - f32).abs().max().item() <= 2e-2 * scale
+
+
+def test_two_models_share_one_engine_context_safely(oracle, tables, state_dict):
+    """the per-device engine context holds ONE parameter set; a second module must never run on the first one's
+    weights, and optimiser updates that live only in the context are pulled back before another module takes it over."""
+    from mpinets_b200.model import MotionPolicyNetwork
+    from mpinets_b200.runtime import get_engine
+    a, b = MotionPolicyNetwork(precision="fp32"), MotionPolicyNetwork(precision="fp32")
+    a.load_state_dict(state_dict)
+    sd_b = {k: v.clone() for k, v in state_dict.items()}
+    sd_b["decoder.6.bias"] = sd_b["decoder.6.bias"] + 0.25
+    b.load_state_dict(sd_b)
+    p = _problems(2)
+    eng = get_engine(torch.device("cuda", 0))
+    sc = to_dev(p)
+    xyz = eng.build_cloud({k: sc[k] for k in sc if k.startswith(("cuboid", "cylinder"))}, sc["q0"], sc["target"])
+    qn = eng.normalize(sc["q0"])
+    da1 = a(xyz, qn)
+    db = b(xyz, qn)
+    da2 = a(xyz, qn)                                       # A again after B synced: must be A's weights, not B's
+    assert torch.equal(da1, da2)
+    assert ((db - da1) - 0.25).abs().max().item() < 1e-5
 
 
 def test_evaluator_surface(tables, oracle):

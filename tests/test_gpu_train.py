@@ -179,8 +179,14 @@ def test_training_loop_reduces_loss_and_weights_round_trip(oracle, tables, state
         opt.step()
     assert losses[-1] < losses[0] and min(losses) < 0.9 * losses[0], losses
     assert float(opt.last_grad_norm) > 0
-    net.pull_weights()
+    # no explicit pull_weights() -- state_dict() / parameters() refresh the nn.Module copies from the engine's flat vector
     sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    assert (sd["decoder.6.weight"] - state_dict["decoder.6.weight"]).abs().max().item() > 0
+    assert not net._dirty and (next(iter(net.parameters())).detach().cpu() - state_dict["point_cloud_encoder.SA_modules.0.mlps.0.0.weight"]).abs().max().item() > 0
+    # a second module taking over the context does not lose or leak the trained weights
+    other = M.MotionPolicyNetwork(precision="fp32")
+    other.load_state_dict(state_dict)
+    other(batch["xyz"], batch["configuration"])
     dq = net.forward(batch["xyz"], batch["configuration"]).cpu().numpy()      # default precision of the training module: fp32
     odq = oracle.policy_forward(sd, cloud, qn).numpy()
     assert np.abs(dq - odq).max() < 1e-5
