@@ -1,7 +1,9 @@
 // pointnet.cu -- pointnet2_ops._ext replacements: furthest point sampling, ball query, gather, group.
 //
 // Index outputs are bit-exact against the oracle's restatement of pointnet2_ops v3.2.0:
-//   * FPS: start at 0; temp = 1e10; points with |p|^2 <= 1e-3 are skipped; distance = fma(dz,dz,fma(dy,dy,dx*dx));
+//   * FPS: start at 0; temp = 1e10; points with |p|^2 <= 1e-3 are skipped -- upstream compares the float against the DOUBLE literal
+//     1e-3, i.e. (double)mag <= 0.001; 0.001f is the float just above 0.001, so that is exactly mag < 1e-3f (a point with
+//     mag == 0.001f is NOT skipped); distance = fma(dz,dz,fma(dy,dy,dx*dx));
 //     winner = max distance, ties -> smaller bit-reversed (k mod block) then smaller k.  That is the order the
 //     strided-thread scan + shared-memory tree reduction of sampling_gpu.cu induces (at stride s the lower slot
 //     wins ties, so the LAST stage compares bit 0 of the thread id, the one before bit 1, ...).  It is a total
@@ -54,7 +56,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int vbs
       px[i] = x; py[i] = y; pz[i] = z;
       spts[k] = make_float4(x, y, z, 0.f);
       float mag = ffma(z, z, ffma(y, y, fmul(x, x)));
-      if (!(mag <= 1e-3f)) temp[i] = 1e10f;
+      if (!(mag < 1e-3f)) temp[i] = 1e10f;   // (double)mag <= 1e-3, see the header
     }
   }
   int32_t* out = idx + (size_t)b * npoint;
@@ -201,7 +203,7 @@ fps_pruned_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, 
       px[i] = v.x; py[i] = v.y; pz[i] = v.z;
       low[i] = 0xFFFFFFFFu - (((__brev((uint32_t)(k & 511)) >> 23) << 23) | (uint32_t)k);
       const float mag = ffma(v.z, v.z, ffma(v.y, v.y, fmul(v.x, v.x)));
-      if (!(mag <= 1e-3f)) temp[i] = 1e10f;
+      if (!(mag < 1e-3f)) temp[i] = 1e10f;   // (double)mag <= 1e-3, see the header
       uint32_t o[3] = {f2ord(v.x), f2ord(v.y), f2ord(v.z)};
 #pragma unroll
       for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], o[a]); mx[a] = max(mx[a], o[a]); }

@@ -176,6 +176,17 @@ def test_fps_bit_exact_sizes_ties_and_skips(engine, oracle, N, m):
         assert np.array_equal(got, oracle.fps(a, m))
 
 
+def test_fps_origin_skip_boundary(engine, oracle):
+    """|p|^2 exactly 0.001f is selectable, the float below is skipped (upstream compares against the double literal 1e-3)"""
+    from test_oracle_cpu import _origin_boundary_cloud
+    xyz = _origin_boundary_cloud()
+    got = engine.fps(torch.from_numpy(xyz).cuda(), 3).cpu().numpy()
+    assert np.array_equal(got, oracle.fps(xyz, 3)) and got[0, 1] == 7
+    big = np.concatenate([xyz, np.tile(xyz[:, 1:2], (1, 6272 - 40, 1))], axis=1)      # the pruned large-cloud kernel
+    got = engine.fps(torch.from_numpy(np.ascontiguousarray(big)).cuda(), 64).cpu().numpy()
+    assert np.array_equal(got, oracle.fps(big, 64)) and got[0, 1] == 7
+
+
 def test_ball_query_bit_exact(engine, oracle, tables):
     cloud, _ = _clouds(engine, oracle, tables, 8)
     idx = oracle.fps(cloud, 512)

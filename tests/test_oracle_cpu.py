@@ -209,6 +209,31 @@ def test_fps_skips_points_near_origin(oracle):
     assert not set(range(100, 140)) & set(idx[0, 1:].tolist())
 
 
+def _origin_boundary_cloud():
+    """a cloud whose point 7 has |p|^2 == 0.001f EXACTLY (fma chain of the spec) and point 9 the float just below it"""
+    x, y = np.float32(0.020976269617676735), np.float32(0.023664237931370735)
+    mag = np.float32(np.float64(y) * np.float64(y) + np.float64(np.float32(x * x)))
+    assert mag == np.float32(0.001)
+    rng = np.random.RandomState(11)
+    xyz = (0.0005 * rng.uniform(-1, 1, size=(1, 40, 3))).astype(np.float32)   # everything else deep inside the skip radius
+    xyz[0, 0] = [0.5, 0.5, 0.5]
+    xyz[0, 7] = [x, y, 0.0]
+    y_lo = np.nextafter(y, np.float32(0))
+    while np.float32(np.float64(y_lo) * np.float64(y_lo) + np.float64(np.float32(x * x))) >= np.float32(0.001):
+        y_lo = np.nextafter(y_lo, np.float32(0))
+    xyz[0, 9] = [-x, -y_lo, 0.0]
+    return xyz
+
+
+def test_fps_origin_skip_compares_against_the_double_literal(oracle):
+    """sampling_gpu.cu writes `mag <= 1e-3` with a DOUBLE literal: (double)0.001f = 0.0010000000475 > 0.001, so a point whose
+    squared norm is exactly the float 0.001f is NOT skipped, while the next float below is"""
+    xyz = _origin_boundary_cloud()
+    idx = oracle.fps(xyz, 3)
+    assert idx[0, 0] == 0 and idx[0, 1] == 7          # the only other selectable point
+    assert idx[0, 2] == 0                             # nothing else is selectable: best = -1 / besti = 0 of the reference kernel
+
+
 def test_fps_tie_break_is_tree_order(oracle):
     # 4 points at equal distance from point 0 -> winner decided by the shared-memory tree, not by lowest index
     xyz = np.zeros((1, 8, 3), np.float32)
