@@ -128,6 +128,22 @@ int mpn_sdf_points(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, co
  * run_inference.py:93-134): q0 [B][7] unnormalised, target [B][12] right_gripper pose -> cloud [B][Nr+No+Nt][4] */
 int mpn_build_cloud(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* q0, const float* target,
                     uint32_t problem0, float* cloud);
+/* mpn_build_cloud with an explicit RNG counter per problem (problem_ids u32 [B], device) instead of problem0 + b: dataset batches
+ * (PointCloudBase.get_inputs, data_loader.py:237-278) key each item by its dataset index, so a sample's cloud does not depend on the
+ * batch it lands in, the worker or the rank. */
+int mpn_build_cloud_ids(mpn_ctx* ctx, void* stream, const mpn_scene* scene, int B, const float* q0, const float* target,
+                        const uint32_t* problem_ids, float* cloud);
+/* Training-time joint noise of PointCloudBase.get_inputs (data_loader.py:167-180): q_out = clamp(q + random_scale * N(0, 1),
+ * FrankaRealRobot.JOINT_LIMITS), q_norm_out = normalize(q_out); q, q_out, q_norm_out [B][7].  The normals are Box-Muller transforms
+ * of Philox4x32-10(counter = (sample id, epoch, 6, pair), key = seed); sample_ids u32 [B] (device; NULL: 0..B-1). */
+int mpn_augment_joints(mpn_ctx* ctx, void* stream, const float* q, int B, float random_scale, const uint32_t* sample_ids,
+                       uint32_t epoch, float* q_out, float* q_norm_out);
+/* Planner.clean_point_cloud (interactive_demo/mpinets_ros/nodes/planning_node.py:187-228): keep the points of xyz [N][3] inside the
+ * task-tabletop or mount-table box, then a random subset without replacement of n_out of them (keyed by (seed, cloud_id)) ->
+ * out_xyz [n_out][3] (and out_rgba [n_out][4] from rgba [N][4], both optional).  kept[0] (device int) receives the number of points
+ * inside the workspace; when it is < n_out nothing is written (np.random.choice raises there).  scratch: int32 [N] (device). */
+int mpn_clean_point_cloud(mpn_ctx* ctx, void* stream, const float* xyz, const float* rgba, int N, int n_out, uint32_t cloud_id,
+                          float* out_xyz, float* out_rgba, int32_t* kept, int32_t* scratch);
 /* run_inference.make_point_cloud_from_problem (run_inference.py:58-90), for problems that carry an obstacle point cloud
  * (PlanningProblem.obstacle_point_cloud, mpinets_types.py:44): obstacle rows = a random subset WITHOUT replacement of
  * obstacle_points [B][max_points][3] restricted to the first obstacle_counts[b] rows (counts >= n_obstacle, as

@@ -24,7 +24,7 @@ EXPORTS = (
     "mpn_last_error", "mpn_version", "mpn_ctx_create", "mpn_ctx_destroy", "mpn_reserve", "mpn_set_robot_tables",
     "mpn_load_weight", "mpn_weights_finalize", "mpn_fps", "mpn_ball_query", "mpn_gather_points", "mpn_group_points",
     "mpn_sa_forward", "mpn_fk", "mpn_sample_robot", "mpn_sample_end_effector", "mpn_compute_spheres", "mpn_normalize_joints",
-    "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_build_cloud_from_points", "mpn_render_depth_cloud", "mpn_sweep_flags", "mpn_evaluate", "mpn_sparc", "mpn_collision_loss", "mpn_point_match_loss", "mpn_bc_collision_losses", "mpn_encoder_forward",
+    "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_build_cloud_from_points", "mpn_build_cloud_ids", "mpn_augment_joints", "mpn_clean_point_cloud", "mpn_render_depth_cloud", "mpn_sweep_flags", "mpn_evaluate", "mpn_sparc", "mpn_collision_loss", "mpn_point_match_loss", "mpn_bc_collision_losses", "mpn_encoder_forward",
     "mpn_policy_forward", "mpn_rollout", "mpn_param_count", "mpn_param_info", "mpn_get_params", "mpn_set_params", "mpn_weights_sync",
     "mpn_train_step_grads", "mpn_train_tc_gemm", "mpn_train_tc_wgrad", "mpn_train_pooled_rows", "mpn_adam_step", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error", "mpn_tc_gemm_selftest",
 )
@@ -83,6 +83,9 @@ def load():
         "mpn_sdf_points": [P, P, SC, I, P, I, I, P],
         "mpn_build_cloud": [P, P, SC, I, P, P, U32, P],
         "mpn_build_cloud_from_points": [P, P, I, P, P, P, P, I, C.c_uint32, P],
+        "mpn_build_cloud_ids": [P, P, SC, I, P, P, P, P],
+        "mpn_augment_joints": [P, P, P, I, F, P, U32, P, P],
+        "mpn_clean_point_cloud": [P, P, P, P, I, I, U32, P, P, P, P],
         "mpn_sweep_flags": [P, P, SC, I, P, I, I, I, P, P],
         "mpn_render_depth_cloud": [P, P, SC, I, P, I, I, I, F, F, F, F, P, P],
         "mpn_evaluate": [P, P, SC, I, P, I, P, P, SC, I, I, SC, I, I, P],

@@ -528,6 +528,35 @@ int mpn_build_cloud(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, con
   return launch_build_cloud(c, (cudaStream_t)stream, *scene, B, c->ws.frames, target, problem0, cloud);
 }
 
+int mpn_build_cloud_ids(mpn_ctx* c, void* stream, const mpn_scene* scene, int B, const float* q0, const float* target,
+                        const uint32_t* problem_ids, float* cloud) {
+  REQ_CTX(c); REQ_TABLES(c);
+  int r;
+  if ((r = check_scene(c, scene))) return r;
+  MPN_REQUIRE(q0 && target && cloud && problem_ids, "mpn_build_cloud_ids: null pointer");
+  if (B == 0) return MPN_OK;
+  if ((r = ensure_workspace(c, B))) return r;
+  StageTimer t(c, (cudaStream_t)stream, MPN_ST_BUILD_CLOUD);
+  if ((r = launch_fk(c, (cudaStream_t)stream, q0, B, c->ws.frames, nullptr))) return r;
+  return launch_build_cloud(c, (cudaStream_t)stream, *scene, B, c->ws.frames, target, 0u, cloud, nullptr, nullptr, 0, problem_ids);
+}
+
+int mpn_augment_joints(mpn_ctx* c, void* stream, const float* q, int B, float random_scale, const uint32_t* sample_ids, uint32_t epoch,
+                       float* q_out, float* q_norm_out) {
+  REQ_CTX(c); REQ_TABLES(c);
+  MPN_REQUIRE(q && q_out && q_norm_out && random_scale >= 0.f, "mpn_augment_joints: bad arguments");
+  if (B == 0) return MPN_OK;
+  return launch_augment_joints(c, (cudaStream_t)stream, q, B, random_scale, sample_ids, epoch, q_out, q_norm_out);
+}
+
+int mpn_clean_point_cloud(mpn_ctx* c, void* stream, const float* xyz, const float* rgba, int N, int n_out, uint32_t cloud_id,
+                          float* out_xyz, float* out_rgba, int32_t* kept, int32_t* scratch) {
+  REQ_CTX(c);
+  MPN_REQUIRE(xyz && out_xyz && kept && scratch && N >= 1 && n_out >= 1, "mpn_clean_point_cloud: bad arguments");
+  MPN_REQUIRE((rgba == nullptr) == (out_rgba == nullptr), "mpn_clean_point_cloud: rgba and out_rgba go together");
+  return launch_clean_point_cloud(c, (cudaStream_t)stream, xyz, rgba, N, n_out, cloud_id, out_xyz, out_rgba, kept, scratch);
+}
+
 int mpn_build_cloud_from_points(mpn_ctx* c, void* stream, int B, const float* q0, const float* target, const float* obstacle_points,
                                 const int32_t* obstacle_counts, int max_points, uint32_t problem0, float* cloud) {
   REQ_CTX(c); REQ_TABLES(c);

@@ -163,7 +163,12 @@ int launch_normalize(mpn_ctx* c, cudaStream_t s, const float* in, int n, float* 
 int launch_sdf_points(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* pts, int N, int which, float* sdf);
 int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* frames, const float* target,
                        uint32_t problem0, float* cloud, const float* obs_points = nullptr, const int32_t* obs_count = nullptr,
-                       int obs_max = 0);
+                       int obs_max = 0, const uint32_t* problem_ids = nullptr);
+// ---- ingest.cu
+int launch_augment_joints(mpn_ctx* c, cudaStream_t s, const float* q, int B, float scale, const uint32_t* sample_ids, uint32_t epoch,
+                          float* q_out, float* qn_out);
+int launch_clean_point_cloud(mpn_ctx* c, cudaStream_t s, const float* xyz, const float* rgba, int N, int n_out, uint32_t cloud_id,
+                             float* out_xyz, float* out_rgba, int32_t* kept, int32_t* scratch);
 int launch_sample_end_effector(mpn_ctx* c, cudaStream_t s, const float* poses, int B, int n, uint32_t problem0, float* out);
 int launch_sweep(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* traj, int T, int traj_stride_t,
                  int t0, int accumulate, uint8_t* flags, int32_t* first_step, const float* frames_in = nullptr);

@@ -202,14 +202,14 @@ __global__ void __launch_bounds__(256) build_cloud_kernel(mpn_scene sc, int M1, 
                                                           int Pe, const float* __restrict__ ee, uint32_t seed_lo,
                                                           uint32_t seed_hi, uint32_t problem0, float4* __restrict__ cloud,
                                                           const float* __restrict__ obs_points, const int32_t* __restrict__ obs_count,
-                                                          int obs_max) {
+                                                          int obs_max, const uint32_t* __restrict__ problem_ids) {
   __shared__ float F[MPN_NLINK * 12];
   __shared__ float TG[12];
   __shared__ uint32_t start[MAX_PRIMS + 1];
   __shared__ int16_t pidx[MAX_PRIMS];  // >=0 cuboid index, <0 : -(cyl index)-1
   __shared__ int nvalid;
   int b = blockIdx.x;
-  uint32_t problem = problem0 + (uint32_t)b;
+  uint32_t problem = problem_ids ? problem_ids[b] : problem0 + (uint32_t)b;   // the RNG counter of this problem's sampling streams
   for (int i = threadIdx.x; i < MPN_NLINK * 12; i += blockDim.x) F[i] = frames[(size_t)b * MPN_NLINK * 12 + i];
   if (threadIdx.x < 12) TG[threadIdx.x] = target[(size_t)b * 12 + threadIdx.x];
   if (threadIdx.x == 0 && !obs_points) {
@@ -317,11 +317,12 @@ __global__ void __launch_bounds__(256) build_cloud_kernel(mpn_scene sc, int M1, 
 }
 
 int launch_build_cloud(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, const float* frames, const float* target,
-                       uint32_t problem0, float* cloud, const float* obs_points, const int32_t* obs_count, int obs_max) {
+                       uint32_t problem0, float* cloud, const float* obs_points, const int32_t* obs_count, int obs_max,
+                       const uint32_t* problem_ids) {
   build_cloud_kernel<<<B, 256, 0, s>>>(sc, c->cfg.max_cuboids, c->cfg.max_cylinders, frames, target, c->cfg.n_robot,
                                        c->cfg.n_obstacle, c->cfg.n_target, c->P, c->link_points, c->link_ids, c->Pe,
                                        c->ee_points, (uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32), problem0,
-                                       (float4*)cloud, obs_points, obs_count, obs_max);
+                                       (float4*)cloud, obs_points, obs_count, obs_max, problem_ids);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

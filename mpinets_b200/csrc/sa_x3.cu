@@ -376,6 +376,7 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
         bool hit = false;
         int k = 0;
         if (ci < C) { k = wcand[ci]; const float4 v = cl[k]; hit = dist2(qx, qy, qz, v.x, v.y, v.z) < r2; }
+        __syncwarp();   // every lane has read its candidate before any lane compacts in place
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
         if (hit) wcand[H + __popc(hm & lt)] = (uint16_t)k;         // in place: write position <= read position
         H += __popc(hm);

@@ -257,13 +257,54 @@ class Engine:
         _lib.check(self.lib.mpn_sdf_points(self._ctx, self.stream, C.byref(s), B, _p(points), N, which, _p(out)))
         return out
 
-    def build_cloud(self, scene, q0: torch.Tensor, target: torch.Tensor, problem0: int = 0):
+    def build_cloud(self, scene, q0: torch.Tensor, target: torch.Tensor, problem0: int = 0, problem_ids: Optional[torch.Tensor] = None,
+                    epoch: int = 0):
+        """problem b's sampling streams are keyed by problem0 + b, or by problem_ids[b] (+ epoch * 2^20, wrapping) when given"""
         _check(q0, "q0", device=self.device); _check(target, "target", device=self.device)
         B = q0.shape[0]
         s, keep = self._scene(scene, B)
         cloud = self._empty(B, self.n_points, 4)
-        _lib.check(self.lib.mpn_build_cloud(self._ctx, self.stream, C.byref(s), B, _p(q0), _p(target), problem0, _p(cloud)))
+        if problem_ids is None:
+            _lib.check(self.lib.mpn_build_cloud(self._ctx, self.stream, C.byref(s), B, _p(q0), _p(target), problem0, _p(cloud)))
+        else:
+            ids = self._ids(problem_ids, epoch)
+            _lib.check(self.lib.mpn_build_cloud_ids(self._ctx, self.stream, C.byref(s), B, _p(q0), _p(target), _p(ids), _p(cloud)))
         return cloud
+
+    def _ids(self, ids: torch.Tensor, epoch: int = 0) -> torch.Tensor:
+        """int64 / int32 indices -> the u32 counters (stored in an int32 tensor) of the per-sample RNG streams"""
+        if not ids.is_cuda:
+            raise RuntimeError("ids must be a CUDA tensor")
+        v = (ids.to(torch.int64) + (int(epoch) << 20)) & 0xFFFFFFFF
+        return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+
+    def augment_joints(self, q: torch.Tensor, random_scale: float, sample0: Optional[torch.Tensor] = None, epoch: int = 0):
+        """data_loader.py:167-180 on the device: (clamp(q + random_scale * N(0,1), limits), its normalisation), both [B,7]"""
+        _check(q, "q", device=self.device)
+        B = q.shape[0]
+        ids = None if sample0 is None else self._ids(sample0)
+        out, outn = torch.empty_like(q), torch.empty_like(q)
+        _lib.check(self.lib.mpn_augment_joints(self._ctx, self.stream, _p(q), B, float(random_scale), _p(ids), int(epoch) & 0xFFFFFFFF,
+                                               _p(out), _p(outn)))
+        return out, outn
+
+    def clean_point_cloud(self, xyz: torch.Tensor, rgba: Optional[torch.Tensor] = None, n_out: int = 4096, cloud_id: int = 0):
+        """planning_node.py:187-228: workspace crop + random subset without replacement -> (xyz [n_out,3], rgba [n_out,4] | None).
+        Raises ValueError when fewer than n_out points lie inside the workspace (np.random.choice does the same)."""
+        _check(xyz, "xyz", device=self.device)
+        if rgba is not None:
+            _check(rgba, "rgba", device=self.device)
+        N = xyz.shape[0]
+        out = self._empty(n_out, 3)
+        out_c = self._empty(n_out, 4) if rgba is not None else None
+        kept = self._empty(1, dtype=torch.int32)
+        scratch = self._empty(N, dtype=torch.int32)
+        _lib.check(self.lib.mpn_clean_point_cloud(self._ctx, self.stream, _p(xyz), _p(rgba), N, n_out, cloud_id, _p(out), _p(out_c),
+                                                  _p(kept), _p(scratch)))
+        k = int(kept.item())
+        if k < n_out:
+            raise ValueError(f"Cannot take a larger sample than population when 'replace=False' ({k} points in the workspace, {n_out} wanted)")
+        return out, out_c
 
     def build_cloud_from_points(self, q0: torch.Tensor, target: torch.Tensor, obstacle_points: torch.Tensor,
                                 obstacle_counts: torch.Tensor, problem0: int = 0):

@@ -281,6 +281,37 @@ def sample_robot(q, tables, n, seed, step, cloud=None):
     return cloud
 
 
+def augment_joints(q, tables, scale, seed, ids=None, epoch=0):
+    """data_loader.py:167-180 -> (clamp(q + scale * N(0,1), limits), its normalisation)"""
+    q, pq = _f(q)
+    lim, pl = _f(tables.joint_limits)
+    B = q.shape[0]
+    if ids is not None:
+        ida = np.ascontiguousarray(np.asarray(ids, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32)
+        pid = ida.ctypes.data_as(C.POINTER(C.c_uint32))
+    else:
+        pid = C.POINTER(C.c_uint32)()
+    out = np.empty_like(q); outn = np.empty_like(q)
+    lib().mpn_oracle_augment_joints(pq, C.c_int(B), C.c_float(scale), pid, C.c_uint32(epoch), pl, C.c_uint64(seed),
+                                    out.ctypes.data_as(C.POINTER(C.c_float)), outn.ctypes.data_as(C.POINTER(C.c_float)))
+    return out, outn
+
+
+def clean_point_cloud(xyz, rgba, n_out, seed, cloud_id=0):
+    """planning_node.py:187-228 -> (kept count, xyz [n_out,3] | None, rgba [n_out,4] | None)"""
+    xyz, px = _f(xyz)
+    out = np.zeros((n_out, 3), np.float32)
+    if rgba is not None:
+        rgba, pr = _f(rgba)
+        outc = np.zeros((n_out, 4), np.float32); pc = outc.ctypes.data_as(C.POINTER(C.c_float))
+    else:
+        pr = pc = C.POINTER(C.c_float)(); outc = None
+    fn = lib().mpn_oracle_clean_point_cloud
+    fn.restype = C.c_int
+    kept = fn(px, pr, C.c_int(xyz.shape[0]), C.c_int(n_out), C.c_uint64(seed), C.c_uint32(cloud_id), out.ctypes.data_as(C.POINTER(C.c_float)), pc)
+    return (kept, out, outc) if kept >= n_out else (kept, None, None)
+
+
 def sample_end_effector(poses, tables, n, seed, problem0=0):
     """poses [B,3,4] right_gripper -> [B,n,3] (FrankaSampler.sample_end_effector; the keyed subset of build_cloud's target rows)"""
     B = np.asarray(poses).shape[0]
