@@ -40,9 +40,14 @@ def run_problems(mdl: MotionPolicyNetwork, problems: Sequence[PlanningProblem], 
     return dict(trajectories=traj, num_poses=num_poses, eval=table, rollout_metrics=metrics)
 
 
-def calculate_metrics(mdl: MotionPolicyNetwork, problem_set: ProblemSet, device: Optional[torch.device] = None,
-                      max_steps: int = MAX_ROLLOUT_LENGTH) -> Evaluator:
-    """run_inference.calculate_metrics (run_inference.py:426-516): one metric group per (environment, problem type)"""
+def calculate_metrics(mdl: MotionPolicyNetwork, problem_set, device: Optional[torch.device] = None,
+                      max_steps: int = MAX_ROLLOUT_LENGTH, environment_type: str = "all", problem_type: str = "all") -> Evaluator:
+    """run_inference.calculate_metrics (run_inference.py:426-516): one metric group per (environment, problem type).
+    ``problem_set``: a ProblemSet, or the path of a reference problem pickle (read as run_inference.py:460-468 does, through
+    problem_io.load_problem_set -- no geometrout needed)."""
+    if isinstance(problem_set, (str, bytes)) or hasattr(problem_set, "__fspath__"):
+        from .problem_io import load_problem_set
+        problem_set = load_problem_set(problem_set, environment_type, problem_type)
     ev = Evaluator()
     flat = flatten_problem_set(problem_set)
     groups: Dict[str, List[int]] = {}

@@ -17,11 +17,11 @@ def test_augment_joints_matches_oracle(engine, oracle, tables):
     ids = rng.randint(0, 2 ** 31 - 1, size=3000).astype(np.int64)
     out, outn = engine.augment_joints(torch.from_numpy(q).cuda(), 0.015, sample0=torch.from_numpy(ids).cuda(), epoch=3)
     eo, eon = oracle.augment_joints(q, tables, 0.015, engine.cfg.seed, ids=ids, epoch=3)
-    assert np.abs(out.cpu().numpy() - eo).max() <= 2e-7 and np.abs(outn.cpu().numpy() - eon).max() <= 5e-7
+    assert np.abs(out.cpu().numpy() - eo).max() <= 5e-7 and np.abs(outn.cpu().numpy() - eon).max() <= 5e-7   # one float32 ulp at |q| <= 4
     assert (out.cpu().numpy() <= lim[:, 1]).all() and (out.cpu().numpy() >= lim[:, 0]).all()
     assert np.array_equal(outn.cpu().numpy(), oracle.normalize(out.cpu().numpy(), lim))      # normalisation itself is bit-exact
     d, _ = engine.augment_joints(torch.from_numpy(q[:8]).cuda(), 0.015)                        # default ids = row index
-    assert np.abs(d.cpu().numpy() - oracle.augment_joints(q[:8], tables, 0.015, engine.cfg.seed)[0]).max() <= 2e-7
+    assert np.abs(d.cpu().numpy() - oracle.augment_joints(q[:8], tables, 0.015, engine.cfg.seed)[0]).max() <= 5e-7
 
 
 def test_build_cloud_with_sample_ids(engine, oracle, tables):
