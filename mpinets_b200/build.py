@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmpinets_b200.so")
-SOURCES = ["engine.cu", "geometry.cu", "pointnet.cu", "sa_simt.cu", "linear.cu", "sa_tc.cu", "sa_x3.cu", "tc_probe.cu", "gemm_tc.cu", "loss.cu", "ingest.cu", "train.cu", "train_tc.cu"]
+SOURCES = ["engine.cu", "geometry.cu", "pointnet.cu", "sa_simt.cu", "linear.cu", "heads.cu", "sa_tc.cu", "sa_x3.cu", "tc_probe.cu", "gemm_tc.cu", "loss.cu", "ingest.cu", "train.cu", "train_tc.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -25,6 +25,7 @@ int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int 
                   int N, const float* new_xyz, float* new_feats, int32_t* ball_idx);
 int tc_probe(mpn_ctx* c, cudaStream_t s, const void* A, const void* B, float* D, int N, int K, int mode, int* status);
 void tc_free(mpn_ctx* c);
+int tc_decoder0(mpn_ctx* c, cudaStream_t s, int precision, const __nv_bfloat16* operand, int B, float* h0);
 // split-bf16 parity-grade tensor-core path, sa_x3.cu
 int x3_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, int N, float* out, int ldo);
 int x3_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
@@ -77,6 +78,7 @@ static int ensure_workspace(mpn_ctx* c, int B) {
   r |= dev_alloc(&w.done, b);
   r |= dev_alloc(&w.first_step, b);
   r |= dev_alloc(&w.flags, b);
+  r |= dev_alloc(&w.head_op, b * 2 * (ENC_DIM + QF_DIM));
   if (w.tc_scratch) { cudaFree(w.tc_scratch); w.tc_scratch = nullptr; }
   w.tc_scratch_bytes = tc_scratch_bytes(B);
   if (w.tc_scratch_bytes) {
@@ -209,6 +211,13 @@ static int encoder_forward(mpn_ctx* c, cudaStream_t s, int precision, const floa
   { StageTimer t(c, s, MPN_ST_SA3);
     if ((r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr))) return r; }
   StageTimer tfc(c, s, MPN_ST_FC);
+  if (B <= SKINNY_MAX_ROWS) {
+    if ((r = launch_linear_skinny(c, s, w.feat3, 1024, 0, c->w.fc[0], B, w.fc_a, 4096, 0))) return r;
+    if ((r = launch_groupnorm_lrelu(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0]))) return r;
+    if ((r = launch_linear_skinny(c, s, w.fc_a, 4096, 0, c->w.fc[1], B, w.fc_b, 2048, 0))) return r;
+    if ((r = launch_groupnorm_lrelu(c, s, w.fc_b, B, 2048, 16, c->w.gn_w[1], c->w.gn_b[1]))) return r;
+    return launch_linear_skinny(c, s, w.fc_b, 2048, 0, c->w.fc[2], B, out, ldo, 0);
+  }
   if ((r = launch_linear(c, s, c->w.fc[0], w.feat3, 1024, B, w.fc_a, 4096, 0))) return r;
   if ((r = launch_groupnorm_lrelu(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0]))) return r;
   if ((r = launch_linear(c, s, c->w.fc[1], w.fc_a, 4096, B, w.fc_b, 2048, 0))) return r;
@@ -221,18 +230,19 @@ static int policy_forward(mpn_ctx* c, cudaStream_t s, int precision, const float
   int r;
   const int CAT = ENC_DIM + QF_DIM;
   if ((r = encoder_forward(c, s, precision, cloud, B, N, w.cat, CAT))) return r;
-  // feature_encoder (model.py:47-57)
+  // feature_encoder (model.py:47-57) -> cat(encoder, q features) (model.py:90) -> decoder (model.py:58-66): three launches
   StageTimer th(c, s, MPN_ST_HEADS);
-  if ((r = launch_linear(c, s, c->w.fe[0], qn, 7, B, w.h_a, 32, 1))) return r;
-  if ((r = launch_linear(c, s, c->w.fe[1], w.h_a, 32, B, w.h_b, 64, 1))) return r;
-  if ((r = launch_linear(c, s, c->w.fe[2], w.h_b, 64, B, w.h_a, 128, 1))) return r;
-  if ((r = launch_linear(c, s, c->w.fe[3], w.h_a, 128, B, w.h_b, 128, 1))) return r;
-  if ((r = launch_linear(c, s, c->w.fe[4], w.h_b, 128, B, w.cat + ENC_DIM, CAT, 0))) return r;
-  // decoder (model.py:58-66)
-  if ((r = launch_linear(c, s, c->w.dec[0], w.cat, CAT, B, w.h_a, 512, 1))) return r;
-  if ((r = launch_linear(c, s, c->w.dec[1], w.h_a, 512, B, w.h_b, 256, 1))) return r;
-  if ((r = launch_linear(c, s, c->w.dec[2], w.h_b, 256, B, w.h_a, 128, 1))) return r;
-  return launch_linear(c, s, c->w.dec[3], w.h_a, 128, B, dq, 7, 0);
+  const bool skinny = B <= SKINNY_MAX_ROWS;
+  const bool tc = precision != MPN_PREC_FP32 && !skinny;
+  if ((r = launch_feature_encoder(c, s, qn, B, w.cat, CAT, tc ? (precision == MPN_PREC_BF16 ? 1 : 2) : 0, w.head_op))) return r;
+  if (skinny) {
+    if ((r = launch_linear_skinny(c, s, w.cat, CAT, 0, c->w.dec[0], B, w.h_a, 512, 1))) return r;
+  } else if (tc) {
+    if ((r = tc_decoder0(c, s, precision, w.head_op, B, w.h_a))) return r;
+  } else {
+    if ((r = launch_linear(c, s, c->w.dec[0], w.cat, CAT, B, w.h_a, 512, 1))) return r;
+  }
+  return launch_decoder_tail(c, s, w.h_a, B, dq);
 }
 
 }  // namespace mpn
@@ -286,6 +296,7 @@ int mpn_ctx_destroy(mpn_ctx* c) {
   if (c->ws.done) cudaFree(c->ws.done);
   if (c->ws.first_step) cudaFree(c->ws.first_step);
   if (c->ws.flags) cudaFree(c->ws.flags);
+  if (c->ws.head_op) cudaFree(c->ws.head_op);
   if (c->ws.tc_scratch) cudaFree(c->ws.tc_scratch);
   if (c->ws.x3_scratch) cudaFree(c->ws.x3_scratch);
   tc_free(c);

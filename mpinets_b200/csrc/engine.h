@@ -79,6 +79,7 @@ struct Workspace {
   void* tc_scratch = nullptr;               // tensor-core path scratch (bf16 hand-off tensors)
   size_t tc_scratch_bytes = 0;
   void* x3_scratch = nullptr;               // split-bf16 mode scratch (sa_x3.cu)
+  __nv_bfloat16* head_op = nullptr;         // [B][2 x 2112] operand rows of decoder.0's tensor-core GEMM (bf16 or [hi | lo])
 };
 
 // buffers of the training step (train.cu): everything the backward pass needs from the forward pass, for B samples,
@@ -204,6 +205,11 @@ int launch_groupnorm_lrelu_train(mpn_ctx* c, cudaStream_t s, const float* z, int
                                  const float* beta, float* out, float* stats);
 int launch_groupnorm_lrelu_bf16(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta,
                                 __nv_bfloat16* out);
+// ---- heads.cu
+int launch_feature_encoder(mpn_ctx* c, cudaStream_t s, const float* qn, int B, float* cat, int ldcat, int operand_mode, __nv_bfloat16* operand);
+int launch_decoder_tail(mpn_ctx* c, cudaStream_t s, const float* h0, int B, float* dq);
+int launch_linear_skinny(mpn_ctx* c, cudaStream_t s, const void* X, int ldx, int x_mode, const Linear& L, int M, float* Y, int ldy, int act);
+constexpr int SKINNY_MAX_ROWS = 16;   // batches up to this size take the fp32 weight-streaming dense layers
 // ---- gemm_tc.cu (epi: 0 relu->bf16, 1 fp32, 2 relu + max over each 128-row tile -> bf16)
 int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int K, const float* bias,
                    int M, int N, void* C, int ldc, uint8_t* arg_out = nullptr);

@@ -24,7 +24,8 @@ using namespace tc;
 // 3: max-pool + winning row per column (training); 4 / 5: the split-bf16 ("bf16x3") mode's hand-off formats -- the fp32 result is
 // written as TWO bf16 values hi = bf16(x), lo = bf16(x - hi) (hi at column n, lo at column c_lo_off + n of the same row), which the
 // next GEMM consumes as its [hi | lo] A operand
-enum { EPI_RELU_BF16 = 0, EPI_F32 = 1, EPI_MAXPOOL = 2, EPI_MAXPOOL_ARG = 3, EPI_RELU_SPLIT = 4, EPI_MAXPOOL_SPLIT = 5 };
+// 6: fp32 rows with LeakyReLU(0.01) (decoder.0 of the policy head, model.py:58-60)
+enum { EPI_RELU_BF16 = 0, EPI_F32 = 1, EPI_MAXPOOL = 2, EPI_MAXPOOL_ARG = 3, EPI_RELU_SPLIT = 4, EPI_MAXPOOL_SPLIT = 5, EPI_LRELU_F32 = 6 };
 constexpr int G_BN = 256;
 
 __device__ __forceinline__ uint32_t cvt_relu_pack(float first, float second) {
@@ -121,7 +122,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // tile).  Rows therefore go through the (now idle) operand ring, 16-byte chunks XOR-swizzled by row so that both the
   // row-per-thread writes and the row-per-warp reads are conflict-free, and leave as full 512-byte row segments.
   const int q = warp & 3, h = warp >> 2, row = q * 32 + (tid & 31);
-  constexpr int ROW_CHUNKS = (EPI == EPI_F32 || EPI == EPI_RELU_SPLIT) ? 64 : 32;   // 16-byte chunks per 256-column output row
+  constexpr int ROW_CHUNKS = (EPI == EPI_F32 || EPI == EPI_LRELU_F32 || EPI == EPI_RELU_SPLIT) ? 64 : 32;   // 16-byte chunks per 256-column output row
   constexpr bool POOL = EPI == EPI_MAXPOOL || EPI == EPI_MAXPOOL_ARG || EPI == EPI_MAXPOOL_SPLIT;
 #pragma unroll 1
   for (int sub = 0; sub < 2; ++sub) {
@@ -160,15 +161,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = hi;
           *reinterpret_cast<uint4*>(rowp + (((32 + chunk) ^ (row & 7)) << 4)) = lo;
         }
-      } else if (EPI == EPI_F32) {
+      } else if (EPI == EPI_F32 || EPI == EPI_LRELU_F32) {
         uint8_t* rowp = smem + (size_t)row * (ROW_CHUNKS * 16);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 bb = bt[j / 4];
           const int chunk = (nl + j) >> 2;
-          *reinterpret_cast<float4*>(rowp + ((chunk ^ (row & 7)) << 4)) =
-              make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y, __uint_as_float(v[j + 2]) + bb.z,
-                          __uint_as_float(v[j + 3]) + bb.w);
+          float4 o = make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y, __uint_as_float(v[j + 2]) + bb.z,
+                                 __uint_as_float(v[j + 3]) + bb.w);
+          if (EPI == EPI_LRELU_F32) {
+            o.x = o.x > 0.f ? o.x : 0.01f * o.x; o.y = o.y > 0.f ? o.y : 0.01f * o.y;
+            o.z = o.z > 0.f ? o.z : 0.01f * o.z; o.w = o.w > 0.f ? o.w : 0.01f * o.w;
+          }
+          *reinterpret_cast<float4*>(rowp + ((chunk ^ (row & 7)) << 4)) = o;
         }
       } else {   // POOL
         int keep = 0;
@@ -220,7 +225,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else {
       // warp w streams rows w, w + 8, ... of this 128-row sub-tile: one row = ROW_CHUNKS x 16 B, a lane per chunk
       const int lane = tid & 31;
-      constexpr int ESZ = EPI == EPI_F32 ? 4 : 2;
+      constexpr int ESZ = (EPI == EPI_F32 || EPI == EPI_LRELU_F32) ? 4 : 2;
       const int valid_chunks = min(256, N - n0) * ESZ / 16;   // N tail of the last column tile (N % 8 == 0)
       for (int rr = warp; rr < 128; rr += 8) {
         const int mr = m0 + sub * 128 + rr;
@@ -309,6 +314,7 @@ int launch_gemm_tc_ex(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* 
   else if (epi == EPI_MAXPOOL_ARG) GEMM_TMA(EPI_MAXPOOL_ARG);
   else if (epi == EPI_RELU_SPLIT) GEMM_TMA(EPI_RELU_SPLIT);
   else if (epi == EPI_MAXPOOL_SPLIT) GEMM_TMA(EPI_MAXPOOL_SPLIT);
+  else if (epi == EPI_LRELU_F32) GEMM_TMA(EPI_LRELU_F32);
   else GEMM_TMA(EPI_MAXPOOL);
 #undef GEMM_TMA
   c->launches++;

@@ -166,25 +166,29 @@ fps_pruned_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, 
   for (int k = tid; k < N; k += THREADS) atomicAdd(&cnt[cell_of(spts[k])], 1u);
   __syncthreads();
   {
-    constexpr int PER = FPSP_CELLS / THREADS;
+    constexpr int SCAN = THREADS >= 1024 ? 1024 : 512;   // threads taking part in the exclusive scan of the cell histogram
+    constexpr int PER = FPSP_CELLS / SCAN;
+    const bool scanner = tid < SCAN;
     uint32_t loc[PER], sum = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { loc[i] = cnt[tid * PER + i]; sum += loc[i]; }
+    for (int i = 0; i < PER; ++i) { loc[i] = scanner ? cnt[tid * PER + i] : 0u; sum += loc[i]; }
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-    if (lane == 31) wsum[warp] = inc;
+    if (lane == 31 && scanner) wsum[warp] = inc;
     __syncthreads();
     if (tid < 32) {
-      uint32_t v = lane < THREADS / 32 ? wsum[lane] : 0u, iv = v;
+      uint32_t v = lane < SCAN / 32 ? wsum[lane] : 0u, iv = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
-      if (lane < THREADS / 32) wsum[lane] = iv - v;
+      if (lane < SCAN / 32) wsum[lane] = iv - v;
     }
     __syncthreads();
-    uint32_t run = wsum[warp] + inc - sum;
+    if (scanner) {
+      uint32_t run = wsum[warp] + inc - sum;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { cnt[tid * PER + i] = run; run += loc[i]; }
+      for (int i = 0; i < PER; ++i) { cnt[tid * PER + i] = run; run += loc[i]; }
+    }
   }
   __syncthreads();
   for (int k = tid; k < N; k += THREADS) order[atomicAdd(&cnt[cell_of(spts[k])], 1u)] = (uint16_t)k;
@@ -281,8 +285,18 @@ int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int s
   static const bool no_prune = getenv("MPN_FPS_NO_PRUNE") != nullptr;
   if (!no_prune && ppt > 8 && ppt <= 13 && npoint >= 64) {   // large clouds: exact pruned variant
     size_t smem_p = smem + FPSP_CELLS * sizeof(uint32_t) + (size_t)N * sizeof(uint16_t) + 16;
-    MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<512, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-    fps_pruned_kernel<512, 13><<<B, 512, smem_p, s>>>(xyz, N, stride, npoint, idx, new_xyz);
+    const char* var = getenv("MPN_FPS_VARIANT");   // A/B switch of the thread / points-per-thread split (read per launch)
+    const int v = var ? atoi(var) : 3;   // 640 x 10 measured fastest (5.07 vs 5.28 ms per 4096 problems; 768 x 9: 5.25, 1024 x 7: 5.73)
+#define FPSP_LAUNCH(T, P)                                                                                                 \
+  do {                                                                                                                    \
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
+    fps_pruned_kernel<T, P><<<B, T, smem_p, s>>>(xyz, N, stride, npoint, idx, new_xyz);                                   \
+  } while (0)
+    if (v == 1) FPSP_LAUNCH(1024, 7);
+    else if (v == 2) FPSP_LAUNCH(768, 9);
+    else if (v == 0) FPSP_LAUNCH(512, 13);
+    else FPSP_LAUNCH(640, 10);
+#undef FPSP_LAUNCH
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;

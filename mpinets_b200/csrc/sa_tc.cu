@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(SA2W_THREADS, 1)
 sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __restrict__ feat_bf16, const float* __restrict__ new_xyz,
                 float r2, const __nv_bfloat16* __restrict__ gw1, const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3,
                 const float* __restrict__ gb2, const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16, int out_stride,
-                int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out) {
+                int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out, int split) {
   using S = Sa2wSmem;
   constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT, KC = SA2W_KC;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -210,7 +210,7 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * SA2W_NWG);
 
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / split, part = blockIdx.x % split;   // small batches: a problem's centroid rounds are dealt to `split` CTAs
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int g = warp >> 2, wq = warp & 3, lane = threadIdx.x & 31;
   const int t = threadIdx.x & 127;
@@ -296,13 +296,13 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
 
   // centroids of warpgroup g: rounds of 4 consecutive centroids, rounds interleaved over the warpgroups
   int r = 0;
-  const int base0 = g * 4;
+  const int base0 = (g * split + part) * 4;
   if (base0 < NCENT) {
     bq_round(base0, 0);
     wg_sync(g);
     prefetch(base0, 0, 0);
   }
-  for (int base = base0; base < NCENT && ok; base += SA2W_NWG * 4, ++r) {
+  for (int base = base0; base < NCENT && ok; base += SA2W_NWG * split * 4, ++r) {
     const int slot = r & 1;
 #pragma unroll 1
     for (int cc = 0; cc < 4 && ok; ++cc) {
@@ -348,7 +348,7 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
       // next centroid: its ball-query round (if this was the last of the round) and its feature rows, under the MMAs
       {
         int jn = j + 1, nslot = slot, ncc = cc + 1;
-        if (cc == 3) { jn = base + SA2W_NWG * 4; nslot = slot ^ 1; ncc = 0; }
+        if (cc == 3) { jn = base + SA2W_NWG * split * 4; nslot = slot ^ 1; ncc = 0; }
         if (jn < NCENT) {
           if (cc == 3) { bq_round(jn, nslot); wg_sync(g); }
           prefetch(jn, nslot, ncc);
@@ -769,7 +769,7 @@ template <bool ARG>
 __global__ void __launch_bounds__(128 * SA1T_NWG, 1)
 sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
                const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
-               int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out) {
+               int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out, int split) {
   using S = Sa1tSmem;
   constexpr int KC = SA1_XK / 8, NS = NSAMPLE, NWG = SA1T_NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -784,7 +784,7 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
   uint16_t* sidx = reinterpret_cast<uint16_t*>(smem + S::sidx(N));
   float* cxyz = reinterpret_cast<float*>(smem + S::cxyz);
 
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / split, part = blockIdx.x % split;   // small batches: a problem's centroid rounds are dealt to `split` CTAs
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int g = warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
   uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 4 * 128;
@@ -960,8 +960,8 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
     tmem_st_wait();
   };
 
-  for (int round = g; round * 4 < SA1_NPOINT && ok;) {
-    const int base = round * 4;
+  for (int round = g; (round * split + part) * 4 < SA1_NPOINT && ok;) {
+    const int base = (round * split + part) * 4;
     if (base + wq < SA1_NPOINT) warp_ball_query(base + wq);
     wg_sync(g);
 #pragma unroll 1
@@ -1094,6 +1094,14 @@ __global__ void narrow_kernel(const float* __restrict__ src, size_t rows, int sr
   dst[i] = __float2bfloat16_rn(src[r * src_stride + cc]);
 }
 
+// Small batches leave most SMs without a problem: deal each problem's rounds of 4 centroids to `split` CTAs (each rebuilds the
+// problem's shared-memory state) so that about one CTA per SM is in flight.  max_split: rounds per warpgroup of an unsplit CTA.
+int sa_split(const mpn_ctx* c, int B, int max_split) {
+  int sp = c->sm_count / (B > 0 ? B : 1);
+  if (sp > max_split) sp = max_split;
+  return sp < 1 ? 1 : sp;
+}
+
 template <int MODULE>
 static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride, int N, const __nv_bfloat16* feat, const float* new_xyz,
                         int B, __nv_bfloat16* out, int out_stride, int32_t* ball_idx = nullptr, uint8_t* arg_out = nullptr) {
@@ -1106,8 +1114,9 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     if (!sa1_ss && smem_t + 2048 <= 227 * 1024) {
       auto kern = arg_out ? sa1t_tc_kernel<true> : sa1t_tc_kernel<false>;
       MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-      kern<<<B, 128 * SA1T_NWG, smem_t, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
-                                             tc_error_flag(c), ball_idx, arg_out);
+      const int split = sa_split(c, B, 128 / SA1T_NWG);
+      kern<<<B * split, 128 * SA1T_NWG, smem_t, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
+                                                     tc_error_flag(c), ball_idx, arg_out, split);
     } else {
       size_t smem7 = Sa1wSmem<7>::total(N);
       MPN_REQUIRE(smem7 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
@@ -1125,8 +1134,9 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     size_t smem3 = Sa2wSmem::total;
     auto kern = arg_out ? sa2w3_tc_kernel<true> : sa2w3_tc_kernel<false>;
     MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    kern<<<B, SA2W_THREADS, smem3, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.w2_nofold, tw.sa[1][2],
-                                        c->w.sa[1][1].b, c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx, arg_out);
+    const int split = sa_split(c, B, 32 / SA2W_NWG);
+    kern<<<B * split, SA2W_THREADS, smem3, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.w2_nofold, tw.sa[1][2],
+                                                c->w.sa[1][1].b, c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx, arg_out, split);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;
@@ -1220,6 +1230,13 @@ int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, in
     if ((r = launch_gemm_tc(c, s, 0, h1, 512, tw.sa[2][1], 512, c->w.sa[2][1].b, M3, 512, h2, 512))) return r;
     if ((r = launch_gemm_tc(c, s, 2, h2, 512, tw.sa[2][2], 512, c->w.sa[2][2].b, M3, 1024, f3, 1024))) return r; }
   StageTimer tfc(c, s, MPN_ST_FC);
+  if (B <= SKINNY_MAX_ROWS) {   // a handful of problems: fp32 weight streaming on every SM instead of N / 256 tensor-core tiles
+    if ((r = launch_linear_skinny(c, s, f3, 1024, 1, c->w.fc[0], B, w.fc_a, 4096, 0))) return r;
+    if ((r = launch_groupnorm_lrelu(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0]))) return r;
+    if ((r = launch_linear_skinny(c, s, w.fc_a, 4096, 0, c->w.fc[1], B, w.fc_b, 2048, 0))) return r;
+    if ((r = launch_groupnorm_lrelu(c, s, w.fc_b, B, 2048, 16, c->w.gn_w[1], c->w.gn_b[1]))) return r;
+    return launch_linear_skinny(c, s, w.fc_b, 2048, 0, c->w.fc[2], B, out, ldo, 0);
+  }
   if ((r = launch_gemm_tc(c, s, 1, f3, 1024, tw.fc[0], 1024, c->w.fc[0].b, B, 4096, w.fc_a, 4096))) return r;
   if ((r = launch_groupnorm_lrelu_bf16(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0], g1))) return r;
   if ((r = launch_gemm_tc(c, s, 1, g1, 4096, tw.fc[1], 4096, c->w.fc[1].b, B, 2048, w.fc_b, 2048))) return r;

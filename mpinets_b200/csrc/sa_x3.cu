@@ -29,11 +29,12 @@ namespace mpn {
 using namespace tc;
 
 int* tc_error_flag(mpn_ctx* c);
+int sa_split(const mpn_ctx* c, int B, int max_split);
 int launch_gemm_tc_ex(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, int a_lo_off, const __nv_bfloat16* W, int ldw,
                       int w_lo_off, int K, const float* bias, int M, int N, void* C, int ldc, int c_lo_off, int split, uint8_t* arg_out);
 int launch_groupnorm_lrelu_split(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta,
                                  __nv_bfloat16* out);
-enum { X3_EPI_F32 = 1, X3_EPI_RELU_SPLIT = 4, X3_EPI_MAXPOOL_SPLIT = 5 };   // gemm_tc.cu's epilogue ids
+enum { X3_EPI_F32 = 1, X3_EPI_RELU_SPLIT = 4, X3_EPI_MAXPOOL_SPLIT = 5, X3_EPI_LRELU_F32 = 6 };   // gemm_tc.cu's epilogue ids
 
 // ---------------------------------------------------------------------------------------------- weights
 constexpr int A1_K = 80;     // SA1 output rows / per-point GEMM operand: [64 features | x y z | 0 x13], then the same as lo parts
@@ -48,6 +49,7 @@ struct X3Weights {
   __nv_bfloat16* sa2_w3 = nullptr;               // [256][2*128]
   __nv_bfloat16* sa3[3] = {nullptr, nullptr, nullptr};   // [N][2*Kpad], layer 1 K order [256 features, x, y, z, 0-pad]
   __nv_bfloat16* fc[3] = {nullptr, nullptr, nullptr};    // [out][2*in]
+  __nv_bfloat16* dec0 = nullptr;                         // decoder.0 [512][2*2112] (its hi half doubles as the bf16 mode's copy)
   bool ready = false;
 };
 static std::map<mpn_ctx*, X3Weights> g_x3;
@@ -148,6 +150,7 @@ int x3_pack_weights(mpn_ctx* c, cudaStream_t s) {
   if ((r = pack(c->w.sa[2][2], 512, 0, &t.sa3[2]))) return r;
   for (int l = 0; l < 3; ++l)
     if ((r = pack(c->w.fc[l], c->w.fc[l].in, 0, &t.fc[l]))) return r;
+  if ((r = pack(c->w.dec[0], c->w.dec[0].in, 0, &t.dec0))) return r;
   MPN_CHECK_CUDA(cudaGetLastError());
   t.ready = true;
   return MPN_OK;
@@ -158,7 +161,7 @@ void x3_free(mpn_ctx* c) {
   if (it == g_x3.end()) return;
   X3Weights& t = it->second;
   __nv_bfloat16* ps[] = {t.sa1_l1, t.sa1_hi[0], t.sa1_hi[1], t.sa1_lo[0], t.sa1_lo[1], t.sa2_w1p, t.sa2_w2, t.sa2_w3,
-                         t.sa3[0], t.sa3[1], t.sa3[2], t.fc[0], t.fc[1], t.fc[2]};
+                         t.sa3[0], t.sa3[1], t.sa3[2], t.fc[0], t.fc[1], t.fc[2], t.dec0};
   for (auto p : ps) if (p) cudaFree(p);
   if (t.sa2_w1x) cudaFree(t.sa2_w1x);
   g_x3.erase(it);
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(128 * S1X_NWG, 1)
 sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gl1,
                 const __nv_bfloat16* __restrict__ ghi2, const __nv_bfloat16* __restrict__ glo2, const __nv_bfloat16* __restrict__ ghi3,
                 const __nv_bfloat16* __restrict__ glo3, __nv_bfloat16* __restrict__ out_rows, float* __restrict__ out_f32,
-                int* __restrict__ err, int32_t* __restrict__ ball_idx) {
+                int* __restrict__ err, int32_t* __restrict__ ball_idx, int split) {
   using S = Sa1xSmem;
   constexpr int NS = NSAMPLE, NWG = S1X_NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -262,7 +265,7 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
   uint16_t* sidx = reinterpret_cast<uint16_t*>(smem + S::sidx(N));
   float* cxyz = reinterpret_cast<float*>(smem + S::cxyz);
 
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / split, part = blockIdx.x % split;   // small batches: rounds dealt to `split` CTAs per problem (sa_split)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int g = warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
   uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 4 * 128;
@@ -445,8 +448,8 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
     tmem_st_wait();
   };
 
-  for (int round = g; round * 4 < SA1_NPOINT && ok;) {
-    const int base = round * 4;
+  for (int round = g; (round * split + part) * 4 < SA1_NPOINT && ok;) {
+    const int base = (round * split + part) * 4;
     if (base + wq < SA1_NPOINT) warp_ball_query(base + wq);
     wg_sync_x(g);
 #pragma unroll 1
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(S2X_THREADS, 1)
 sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restrict__ pre, const float* __restrict__ new_xyz, float r2,
                 const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, const float* __restrict__ gb2,
                 const float* __restrict__ gb3, const float* __restrict__ gw1x, __nv_bfloat16* __restrict__ out_rows,
-                float* __restrict__ out_f32, int* __restrict__ err, int32_t* __restrict__ ball_idx) {
+                float* __restrict__ out_f32, int* __restrict__ err, int32_t* __restrict__ ball_idx, int split) {
   using S = Sa2xSmem;
   constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT, NWG = S2X_NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -564,7 +567,7 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * NWG);
 
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / split, part = blockIdx.x % split;   // small batches: rounds dealt to `split` CTAs per problem (sa_split)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int g = warp >> 2, wq = warp & 3, lane = threadIdx.x & 31, t = threadIdx.x & 127;
   uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 2 * 4 * 128;
@@ -647,9 +650,9 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
   };
 
   int r = 0;
-  const int base0 = g * 4;
+  const int base0 = (g * split + part) * 4;
   if (base0 < NCENT) { bq_round(base0, 0); wg_sync_x(g); }
-  for (int base = base0; base < NCENT && ok; base += NWG * 4, ++r) {
+  for (int base = base0; base < NCENT && ok; base += NWG * split * 4, ++r) {
     const int slot = r & 1;
 #pragma unroll 1
     for (int cc = 0; cc < 4 && ok; ++cc) {
@@ -711,7 +714,7 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
       wg_sync_x(g);
       issue(dW3h, dW3l, 0);                                      // layer 3, channels 0..127
       // the next round's ball query under the MMAs
-      if (cc == 3 && base + NWG * 4 < NCENT) bq_round(base + NWG * 4, slot ^ 1);
+      if (cc == 3 && base + NWG * split * 4 < NCENT) bq_round(base + NWG * split * 4, slot ^ 1);
       __nv_bfloat16* o = out_rows + ((size_t)b * NCENT + j) * (2 * A3_KX);
 #pragma unroll 1
       for (int tile = 0; tile < 2; ++tile) {
@@ -781,8 +784,9 @@ static int launch_sa1x3(mpn_ctx* c, cudaStream_t s, const float* cloud, int N, c
   const size_t smem = Sa1xSmem::total(N);
   MPN_REQUIRE(smem + 1024 <= 227 * 1024, "bf16x3 SA1: %d points do not fit in shared memory (use MPN_PREC_FP32)", N);
   MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sa1x3_tc_kernel<<<B, 128 * S1X_NWG, smem, s>>>(cloud, N, new_xyz, SA1_RADIUS * SA1_RADIUS, w.sa1_l1, w.sa1_hi[0], w.sa1_lo[0], w.sa1_hi[1],
-                                                 w.sa1_lo[1], out_rows, out_f32, tc_error_flag(c), ball_idx);
+  const int split = sa_split(c, B, 128 / S1X_NWG);
+  sa1x3_tc_kernel<<<B * split, 128 * S1X_NWG, smem, s>>>(cloud, N, new_xyz, SA1_RADIUS * SA1_RADIUS, w.sa1_l1, w.sa1_hi[0], w.sa1_lo[0], w.sa1_hi[1],
+                                                         w.sa1_lo[1], out_rows, out_f32, tc_error_flag(c), ball_idx, split);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
@@ -800,8 +804,9 @@ static int launch_sa2x3(mpn_ctx* c, cudaStream_t s, const float* xyz1, const flo
   X3Weights& w = g_x3[c];
   MPN_REQUIRE(w.ready, "bf16x3 weights not packed");
   MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sa2xSmem::total));
-  sa2x3_tc_kernel<<<B, S2X_THREADS, Sa2xSmem::total, s>>>(xyz1, 3, pre, xyz2, SA2_RADIUS * SA2_RADIUS, w.sa2_w2, w.sa2_w3, c->w.sa[1][1].b,
-                                                          c->w.sa[1][2].b, w.sa2_w1x, out_rows, out_f32, tc_error_flag(c), ball_idx);
+  const int split = sa_split(c, B, 32 / S2X_NWG);
+  sa2x3_tc_kernel<<<B * split, S2X_THREADS, Sa2xSmem::total, s>>>(xyz1, 3, pre, xyz2, SA2_RADIUS * SA2_RADIUS, w.sa2_w2, w.sa2_w3, c->w.sa[1][1].b,
+                                                                  c->w.sa[1][2].b, w.sa2_w1x, out_rows, out_f32, tc_error_flag(c), ball_idx, split);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
@@ -891,11 +896,29 @@ int x3_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, in
     if ((r = launch_gemm_tc_ex(c, s, X3_EPI_MAXPOOL_SPLIT, sc.h2, 1024, 512, xw.sa3[2], 1024, 512, 512, c->w.sa[2][2].b, M3, 1024, sc.f3, 2048, 1024,
                                1, nullptr))) return r; }
   StageTimer tfc(c, s, MPN_ST_FC);
+  if (B <= SKINNY_MAX_ROWS) {   // a handful of problems: fp32 weight streaming on every SM instead of N / 256 tensor-core tiles
+    if ((r = launch_linear_skinny(c, s, sc.f3, 2048, 2, c->w.fc[0], B, w.fc_a, 4096, 0))) return r;
+    if ((r = launch_groupnorm_lrelu(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0]))) return r;
+    if ((r = launch_linear_skinny(c, s, w.fc_a, 4096, 0, c->w.fc[1], B, w.fc_b, 2048, 0))) return r;
+    if ((r = launch_groupnorm_lrelu(c, s, w.fc_b, B, 2048, 16, c->w.gn_w[1], c->w.gn_b[1]))) return r;
+    return launch_linear_skinny(c, s, w.fc_b, 2048, 0, c->w.fc[2], B, out, ldo, 0);
+  }
   if ((r = launch_gemm_tc_ex(c, s, X3_EPI_F32, sc.f3, 2048, 1024, xw.fc[0], 2048, 1024, 1024, c->w.fc[0].b, B, 4096, w.fc_a, 4096, 0, 1, nullptr))) return r;
   if ((r = launch_groupnorm_lrelu_split(c, s, w.fc_a, B, 4096, 16, c->w.gn_w[0], c->w.gn_b[0], sc.g1))) return r;
   if ((r = launch_gemm_tc_ex(c, s, X3_EPI_F32, sc.g1, 8192, 4096, xw.fc[1], 8192, 4096, 4096, c->w.fc[1].b, B, 2048, w.fc_b, 2048, 0, 1, nullptr))) return r;
   if ((r = launch_groupnorm_lrelu_split(c, s, w.fc_b, B, 2048, 16, c->w.gn_w[1], c->w.gn_b[1], sc.g2))) return r;
   return launch_gemm_tc_ex(c, s, X3_EPI_F32, sc.g2, 4096, 2048, xw.fc[2], 4096, 2048, 2048, c->w.fc[2].b, B, 2048, out, ldo, 0, 1, nullptr);
+}
+
+// decoder.0 (2112 -> 512, LeakyReLU; model.py:58-60) of the tensor-core modes: operand rows prepared by feature_encoder_kernel
+int tc_decoder0(mpn_ctx* c, cudaStream_t s, int precision, const __nv_bfloat16* operand, int B, float* h0) {
+  X3Weights& xw = g_x3[c];
+  MPN_REQUIRE(xw.ready, "tensor-core weights not packed");
+  constexpr int K = ENC_DIM + QF_DIM;
+  const Linear& L = c->w.dec[0];
+  if (precision == MPN_PREC_BF16)
+    return launch_gemm_tc_ex(c, s, X3_EPI_LRELU_F32, operand, K, 0, xw.dec0, 2 * K, 0, K, L.b, B, 512, h0, 512, 0, 0, nullptr);
+  return launch_gemm_tc_ex(c, s, X3_EPI_LRELU_F32, operand, 2 * K, K, xw.dec0, 2 * K, K, K, L.b, B, 512, h0, 512, 0, 1, nullptr);
 }
 
 }  // namespace mpn
