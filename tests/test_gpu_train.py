@@ -109,14 +109,15 @@ def test_train_step_grads_match_oracle(engine_w, oracle, tables, state_dict, chu
 
 
 def test_train_forward_equals_policy_forward(engine_w, oracle, tables):
-    """the training forward is the fp32 parity path: y_hat == clamp(q + mpn_policy_forward(fp32)) bit for bit"""
+    """the training forward is the fp32 parity path: y_hat == clamp(q + mpn_policy_forward(fp32)) -- same set-abstraction kernels bit for
+    bit; the FC head / policy head of the inference path run as differently-tiled fp32 kernels (heads.cu), i.e. another summation order"""
     B = 5
     p, cloud, qn, sup = _batch(oracle, tables, B, seed=1)
     c = torch.from_numpy(cloud).cuda()
     q = torch.from_numpy(qn).cuda()
     losses, y_hat, _ = engine_w.train_step_grads(to_dev(p), c, q, torch.from_numpy(sup).cuda(), need_grad=False)
     dq = engine_w.policy_forward(c, q)
-    assert torch.equal(y_hat, torch.clamp(q + dq, -1, 1))
+    assert (y_hat - torch.clamp(q + dq, -1, 1)).abs().max().item() <= 1e-6
     l2, _ = engine_w.bc_collision_losses(to_dev(p), y_hat, torch.from_numpy(sup).cuda())
     assert torch.equal(l2, losses)
 
