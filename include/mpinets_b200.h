@@ -184,7 +184,10 @@ enum { MPN_M_COLLISION = 0, MPN_M_FIRST_COLLISION_STEP = 1, MPN_M_STEPS = 2, MPN
  * run_inference.rollout_until_success (run_inference.py:137-191) in lock-step with a per-problem done mask.
  * cloud [B][N][4] is updated in place (robot rows), like the reference (model.py:181).
  * q0 [B][7] unnormalised start; target [B][12]; traj [B][T+1][7] unnormalised (incl. start); metrics [B][8] fp32.
- * check_every_step != 0 evaluates the collision flag after every step (config 3) instead of once at the end. */
+ * check_every_step != 0 evaluates the collision flag after every step (config 3) instead of once at the end.
+ * early_exit: 0 = exactly T steps for everybody; 1 = per-problem done mask (stopped problems keep their configuration) and the host
+ * polls every 8 steps whether every problem has stopped, ending the loop early like rollout_until_success's break (the only host
+ * synchronisation of this call; skipped while the stream is being captured); 2 = done mask only, never synchronises. */
 int mpn_rollout(mpn_ctx* ctx, void* stream, int precision, const mpn_scene* scene, int B, int N, float* cloud,
                 const float* q0, const float* target, int T, int early_exit, int check_every_step, float* traj,
                 float* metrics);

@@ -78,6 +78,8 @@ static int ensure_workspace(mpn_ctx* c, int B) {
   r |= dev_alloc(&w.done, b);
   r |= dev_alloc(&w.first_step, b);
   r |= dev_alloc(&w.flags, b);
+  r |= dev_alloc(&w.live, 1);
+  if (!w.live_host && cudaMallocHost((void**)&w.live_host, sizeof(int32_t)) != cudaSuccess) r |= MPN_ERR_NOMEM;
   r |= dev_alloc(&w.head_op, b * 2 * (ENC_DIM + QF_DIM));
   if (w.tc_scratch) { cudaFree(w.tc_scratch); w.tc_scratch = nullptr; }
   w.tc_scratch_bytes = tc_scratch_bytes(B);
@@ -296,6 +298,8 @@ int mpn_ctx_destroy(mpn_ctx* c) {
   if (c->ws.done) cudaFree(c->ws.done);
   if (c->ws.first_step) cudaFree(c->ws.first_step);
   if (c->ws.flags) cudaFree(c->ws.flags);
+  if (c->ws.live) cudaFree(c->ws.live);
+  if (c->ws.live_host) cudaFreeHost(c->ws.live_host);
   if (c->ws.head_op) cudaFree(c->ws.head_op);
   if (c->ws.tc_scratch) cudaFree(c->ws.tc_scratch);
   if (c->ws.x3_scratch) cudaFree(c->ws.x3_scratch);
@@ -800,6 +804,13 @@ int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene,
   if ((r = launch_fk(c, s, q0, B, w.frames, w.eef))) return r;
   if (check_every_step && (r = launch_sweep(c, s, *scene, B, traj, 1, stride, 0, 0, w.flags, w.first_step, w.frames))) return r;
   if ((r = launch_robot_subsets(c, s, c->cfg.n_robot, 1u, T))) return r;   // the per-step robot subsets, all at once
+  // early_exit == 1: every EARLY_EXIT_POLL steps the host reads the number of problems still running and stops launching once every
+  // problem has stopped (rollout_until_success breaks out of its loop, run_inference.py:180-187) -- the one place this call
+  // synchronises the stream; early_exit == 2 keeps the done mask without polling (capturable in a CUDA graph).
+  constexpr int EARLY_EXIT_POLL = 8;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  const bool poll = early_exit == 1 && cap == cudaStreamCaptureStatusNone;
   for (int i = 1; i <= T; ++i) {
     if ((r = policy_forward(c, s, precision, cloud, w.qn, B, N, w.dq))) return r;
     { StageTimer t(c, s, MPN_ST_UPDATE);
@@ -809,6 +820,15 @@ int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene,
     if (check_every_step) {
       StageTimer t(c, s, MPN_ST_SWEEP);
       if ((r = launch_sweep(c, s, *scene, B, traj + (size_t)i * 7, 1, stride, i, 1, w.flags, w.first_step, w.frames))) return r;
+    }
+    if (poll && i % EARLY_EXIT_POLL == 0 && i < T) {
+      if ((r = launch_count_live(c, s, B, w.done, w.live))) return r;
+      MPN_CHECK_CUDA(cudaMemcpyAsync(w.live_host, w.live, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      MPN_CHECK_CUDA(cudaStreamSynchronize(s));
+      if (*w.live_host == 0) {   // everybody has stopped: the remaining rows repeat the frozen configurations
+        if ((r = launch_fill_traj_tail(c, s, B, w.qu, traj, stride, i + 1, T))) return r;
+        break;
+      }
     }
   }
   if (!check_every_step) {

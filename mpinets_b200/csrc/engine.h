@@ -76,6 +76,8 @@ struct Workspace {
   int32_t* done = nullptr;                  // [B]
   int32_t* first_step = nullptr;            // [B]
   uint8_t* flags = nullptr;                 // [B]
+  int32_t* live = nullptr;                  // [1] problems still running (early-exit polling)
+  int32_t* live_host = nullptr;             // pinned copy
   void* tc_scratch = nullptr;               // tensor-core path scratch (bf16 hand-off tensors)
   size_t tc_scratch_bytes = 0;
   void* x3_scratch = nullptr;               // split-bf16 mode scratch (sa_x3.cu)
@@ -216,6 +218,8 @@ int launch_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, 
 int launch_step_update(mpn_ctx* c, cudaStream_t s, int B, const float* dq, float* qn, float* qu, const float* target,
                        int32_t* done, int early_exit, float* traj_out, int traj_stride, float* frames, float* eef,
                        float* metrics, int step);
+int launch_count_live(mpn_ctx* c, cudaStream_t s, int B, const int32_t* done, int32_t* live);
+int launch_fill_traj_tail(mpn_ctx* c, cudaStream_t s, int B, const float* qu, float* traj, int traj_stride, int from, int T);
 int launch_finalize_metrics(mpn_ctx* c, cudaStream_t s, int B, const float* eef, const float* target, const uint8_t* flags,
                             const int32_t* first_step, const int32_t* done, int T, float* metrics);
 // ---- train.cu : training step (model.py:185-240) in fp32 -- forward with saved state, losses, backward, Adam

@@ -217,6 +217,35 @@ int launch_step_update(mpn_ctx* c, cudaStream_t s, int B, const float* dq, float
   return MPN_OK;
 }
 
+// early-exit rollouts: number of problems that have not stopped yet, and the trajectory tail of a rollout that ended early
+__global__ void count_live_kernel(int B, const int32_t* __restrict__ done, int32_t* __restrict__ live) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int alive = (b < B && done[b] < 0) ? 1 : 0;
+  alive = __reduce_add_sync(0xffffffffu, alive);
+  if ((threadIdx.x & 31) == 0 && alive) atomicAdd(live, alive);
+}
+__global__ void fill_traj_tail_kernel(int B, const float* __restrict__ qu, float* __restrict__ traj, int traj_stride, int from, int T) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 7) return;
+  const int b = i / 7, j = i % 7;
+  const float v = qu[i];
+  for (int t = from; t <= T; ++t) traj[(size_t)b * traj_stride + (size_t)t * 7 + j] = v;
+}
+int launch_count_live(mpn_ctx* c, cudaStream_t s, int B, const int32_t* done, int32_t* live) {
+  MPN_CHECK_CUDA(cudaMemsetAsync(live, 0, sizeof(int32_t), s));
+  count_live_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, done, live);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+int launch_fill_traj_tail(mpn_ctx* c, cudaStream_t s, int B, const float* qu, float* traj, int traj_stride, int from, int T) {
+  if (from > T) return MPN_OK;
+  fill_traj_tail_kernel<<<(B * 7 + 255) / 256, 256, 0, s>>>(B, qu, traj, traj_stride, from, T);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
 __global__ void finalize_metrics_kernel(int B, const float* __restrict__ eef, const float* __restrict__ target,
                                         const uint8_t* __restrict__ flags, const int32_t* __restrict__ first_step,
                                         const int32_t* __restrict__ done, int T, float* __restrict__ metrics) {

@@ -649,9 +649,19 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
     }
   };
 
-  int r = 0;
+  // The gather of a centroid reads 128 rows x 512 B of `pre` from L2; the first quarter of the NEXT centroid's row is fetched into
+  // registers under the current centroid's layer-3 MMAs, and the other quarters are requested one step ahead of their use.
+  int r = 0, kpre = 0;
+  float4 xpre[8];
   const int base0 = (g * split + part) * 4;
-  if (base0 < NCENT) { bq_round(base0, 0); wg_sync_x(g); }
+  auto prefetch = [&](int jn, int nslot, int ncc) {
+    kpre = lists[(nslot * 4 + ncc) * 128 + t];
+    const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + kpre) * 128);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xpre[q] = __ldg(prow + q);
+    if (ball_idx) ball_idx[((size_t)b * NCENT + jn) * NSAMPLE + t] = kpre;
+  };
+  if (base0 < NCENT) { bq_round(base0, 0); wg_sync_x(g); prefetch(base0, 0, 0); }
   for (int base = base0; base < NCENT && ok; base += NWG * split * 4, ++r) {
     const int slot = r & 1;
 #pragma unroll 1
@@ -664,20 +674,23 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
       wg_sync_x(g);
       // ---- layer 1 (per-point pre-activation - centroid term), ReLU, split, straight into the operand columns
       {
-        const int k = lists[(slot * 4 + cc) * 128 + t];
-        if (ball_idx) ball_idx[((size_t)b * NCENT + j) * NSAMPLE + t] = k;
-        const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + k) * 128);
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          float4 x[8];
+        const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + kpre) * 128);
+        float4 xa[8], xb[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) x[q] = __ldg(prow + (c0 >> 2) + q);
+        for (int q = 0; q < 8; ++q) xa[q] = xpre[q];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int c0 = ch * 32;
+          if (ch < 3) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) xb[q] = __ldg(prow + (c0 >> 2) + 8 + q);
+          }
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 xv = x[q * 4 + i];
+              const float4 xv = xa[q * 4 + i];
               const float4 uv = *reinterpret_cast<const float4*>(sU + c0 + q * 16 + i * 4);
               split_relu_pack(xv.x - uv.x, xv.y - uv.y, hi[2 * i], lo[2 * i]);
               split_relu_pack(xv.z - uv.z, xv.w - uv.w, hi[2 * i + 1], lo[2 * i + 1]);
@@ -685,6 +698,8 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
             tmem_st8(tmemAh + lane_off + (c0 >> 1) + q * 8, hi);
             tmem_st8(tmemAl + lane_off + (c0 >> 1) + q * 8, lo);
           }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) xa[q] = xb[q];
         }
         tmem_st_wait();
       }
@@ -713,8 +728,15 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
       tc_fence_before();
       wg_sync_x(g);
       issue(dW3h, dW3l, 0);                                      // layer 3, channels 0..127
-      // the next round's ball query under the MMAs
-      if (cc == 3 && base + NWG * split * 4 < NCENT) bq_round(base + NWG * split * 4, slot ^ 1);
+      // under the layer-3 MMAs: the next round's ball query (when this was the round's last centroid) and the next centroid's rows
+      {
+        int jn = j + 1, nslot = slot, ncc = cc + 1;
+        if (cc == 3) { jn = base + NWG * split * 4; nslot = slot ^ 1; ncc = 0; }
+        if (jn < NCENT) {
+          if (cc == 3) { bq_round(jn, nslot); wg_sync_x(g); }
+          prefetch(jn, nslot, ncc);
+        }
+      }
       __nv_bfloat16* o = out_rows + ((size_t)b * NCENT + j) * (2 * A3_KX);
 #pragma unroll 1
       for (int tile = 0; tile < 2; ++tile) {
@@ -766,7 +788,6 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
         o[256 + t] = h;
         o[A3_KX + 256 + t] = l;
       }
-      if (cc == 3) wg_sync_x(g);                                 // the next round's lists are complete
     }
   }
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);

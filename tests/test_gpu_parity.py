@@ -320,6 +320,29 @@ def test_rollout_early_exit_mask(engine_w, oracle, tables):
     assert (m[1:, 2] == 3).all()
 
 
+def test_rollout_early_exit_stops_launching(engine_w, oracle, tables):
+    """rollout_until_success breaks out of its loop (run_inference.py:180-187): once EVERY problem of the batch has stopped, the
+    library stops enqueuing steps (host poll every 8 steps) and the remaining trajectory rows repeat the frozen configurations"""
+    p = _problems(2, 3)
+    sc = to_dev(p)
+    q0, tg = torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda()
+    cloud = engine_w.build_cloud(sc, q0, tg)
+    traj1, _ = engine_w.rollout(sc, cloud.clone(), q0, tg, 1)
+    _, eef = engine_w.fk(traj1[:, 1].contiguous())                 # every target = where the first step lands
+    T = 40
+    l0 = engine_w.launch_count
+    traj, metrics = engine_w.rollout(sc, cloud.clone(), q0, eef.contiguous(), T, early_exit=True)
+    per_step = (engine_w.launch_count - l0)
+    l1 = engine_w.launch_count
+    traj_full, metrics_full = engine_w.rollout(sc, cloud.clone(), q0, eef.contiguous(), T, early_exit=2)   # done mask only: all T steps
+    full = engine_w.launch_count - l1
+    assert per_step < 0.35 * full                                   # 8 of 40 steps were enqueued
+    m = metrics.cpu().numpy()
+    assert (m[:, 2] == 1).all() and (m[:, 5] == 1).all()
+    assert torch.equal(traj, traj_full) and torch.equal(metrics, metrics_full)
+    assert all(torch.equal(traj[:, t], traj[:, 1]) for t in range(2, T + 1))
+
+
 # ----------------------------------------------------------------------------- full-size properties (BASELINE configs)
 def test_full_size_properties(engine, oracle, tables):
     """4096 problems (configs[1]): size-independent properties of the GPU path + spot parity on a subset."""
