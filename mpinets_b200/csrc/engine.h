@@ -104,6 +104,9 @@ struct TrainWs {
   int32_t* src = nullptr; uint8_t* slot = nullptr;
   float* partial = nullptr; size_t partial_floats = 0;   // split-reduction partials of the weight-gradient kernels
   __nv_bfloat16* tcw = nullptr; float* b2dup = nullptr;  // bf16 weight tiles of the tensor-core backward (rebuilt per step)
+  // bf16 mode, dense layers on the TMA GEMM: operand copies of one layer at a time (activation / gradient, their transposes, W, W^T)
+  __nv_bfloat16 *dx = nullptr, *dgy = nullptr, *dgyT = nullptr, *daT = nullptr, *dw = nullptr, *dwT = nullptr;
+  float* zeros = nullptr;                                 // [4096] zero bias of the gradient GEMMs
   float* adam_m = nullptr; float* adam_v = nullptr; float* norm = nullptr;
   // bf16 mode: hidden activations of the group-all level saved by the forward GEMMs, [B*128][512] each (null in the fp32 mode)
   const __nv_bfloat16 *sa3_h1 = nullptr, *sa3_h2 = nullptr;

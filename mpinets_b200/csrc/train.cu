@@ -805,6 +805,7 @@ static int talloc(T** p, size_t n) {
 void free_train_ws(mpn_ctx* c) {
   TrainWs& t = c->tw;
   void** ptrs[] = {(void**)&t.fps_idx, (void**)&t.ball1, (void**)&t.ball2, (void**)&t.arg1, (void**)&t.arg2, (void**)&t.arg3,
+                   (void**)&t.dx, (void**)&t.dgy, (void**)&t.dgyT, (void**)&t.daT, (void**)&t.dw, (void**)&t.dwT, (void**)&t.zeros,
                    (void**)&t.z1, (void**)&t.a1, (void**)&t.z2, (void**)&t.a2, (void**)&t.st1, (void**)&t.st2, (void**)&t.f[0],
                    (void**)&t.f[1], (void**)&t.f[2], (void**)&t.f[3], (void**)&t.d[0], (void**)&t.d[1], (void**)&t.d[2],
                    (void**)&t.yhat, (void**)&t.gy, (void**)&t.ga, (void**)&t.gb, (void**)&t.gcat, (void**)&t.gfeat3, (void**)&t.gfeat2,
@@ -858,11 +859,81 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
   r |= talloc(&t.tcw, (size_t)8 * 128 * 128 + 512 * 512 + 256 * 512);   // + transposed bf16 tiles of SA3 layers 2 / 1 (data gradients)
   r |= talloc(&t.b2dup, (size_t)256 + 512);                              // + 512 zeros (bias of the data-gradient GEMMs)
   if (!r) cudaMemset(t.b2dup, 0, (256 + 512) * sizeof(float));
+  r |= talloc(&t.dx, b * 4096); r |= talloc(&t.dgy, b * 4096); r |= talloc(&t.dgyT, b * 4096); r |= talloc(&t.daT, b * 4096);
+  r |= talloc(&t.dw, (size_t)4096 * 2112); r |= talloc(&t.dwT, (size_t)4096 * 2112);
+  r |= talloc(&t.zeros, (size_t)4096);
+  if (!r) cudaMemset(t.zeros, 0, 4096 * sizeof(float));
   t.partial_floats = (size_t)20 << 20;   // >= the largest single weight tensor (fc_layer.3: 8.4 M) + bias
   r |= talloc(&t.partial, t.partial_floats);
   if (r) { free_train_ws(c); return MPN_ERR_NOMEM; }
   t.capacity = B; t.chunk = chunk; t.n_points = N;
   return MPN_OK;
+}
+
+static inline float* gw(const mpn_ctx* c, float* grads, const Linear& L) { return grads + (L.w - c->w.params); }
+static inline float* gbias(const mpn_ctx* c, float* grads, const Linear& L) { return grads + (L.b - c->w.params); }
+
+// ---------------------------------------------------------------------------------------------- dense layers on the TMA GEMM (bf16 mode)
+// The FC head (1024 -> 4096 -> 2048 -> 2048) and decoder.0 (2112 -> 512) hold 97 % of the dense-stack MACs.  In the bf16 training mode
+// their forward, data-gradient and weight-gradient products run on gemm_tma_kernel (bf16 operands, fp32 accumulate / outputs):
+//   forward  Y [M][out] = X [M][in] W^T           A = X,      B rows = W [out][in],   K = in
+//   dgrad    gX [M][in] = gY [M][out] W            A = gY,     B rows = W^T [in][out], K = out
+//   wgrad    gW [out][in] = gY^T X                 A = gY^T,   B rows = X^T [in][M],   K = M  (needs M % 16 == 0)
+int launch_gemm_tc_ex(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, int a_lo_off, const __nv_bfloat16* W, int ldw,
+                      int w_lo_off, int K, const float* bias, int M, int N, void* C, int ldc, int c_lo_off, int split, uint8_t* arg_out);
+
+__global__ void __launch_bounds__(256) narrow_rows_kernel(const float* __restrict__ src, int ld, long long rows, int cols, __nv_bfloat16* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  dst[i] = __float2bfloat16_rn(src[r * ld + (i - r * cols)]);
+}
+// dst [cols][rows] bf16 = transpose of src [rows][cols] fp32 (row pitch ld): 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) narrow_transpose_kernel(const float* __restrict__ src, int ld, int rows, int cols, __nv_bfloat16* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) tile[i][tx] = (r0 + i < rows && c0 + tx < cols) ? src[(size_t)(r0 + i) * ld + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < rows) dst[(size_t)(c0 + i) * rows + r0 + tx] = __float2bfloat16_rn(tile[tx][i]);
+}
+static int narrow_rows(mpn_ctx* c, cudaStream_t s, const float* src, int ld, long long rows, int cols, __nv_bfloat16* dst) {
+  narrow_rows_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, s>>>(src, ld, rows, cols, dst);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+static int narrow_transpose(mpn_ctx* c, cudaStream_t s, const float* src, int ld, int rows, int cols, __nv_bfloat16* dst) {
+  narrow_transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, s>>>(src, ld, rows, cols, dst);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+static bool dense_tc_ok(const Linear& L, int M) { return M % 16 == 0 && M >= 16 && L.in % 16 == 0 && L.out % 16 == 0 && L.in <= 4096 && L.out <= 4096; }
+
+// act: 0 none, 1 LeakyReLU(0.01)
+static int dense_forward_tc(mpn_ctx* c, cudaStream_t s, const Linear& L, const float* X, int ldx, int M, float* Y, int ldy, int act) {
+  TrainWs& t = c->tw;
+  int r;
+  if ((r = narrow_rows(c, s, X, ldx, M, L.in, t.dx))) return r;
+  if ((r = narrow_rows(c, s, L.w, L.in, L.out, L.in, t.dw))) return r;
+  return launch_gemm_tc_ex(c, s, act ? 6 : 1, t.dx, L.in, 0, t.dw, L.in, 0, L.in, L.b, M, L.out, Y, ldy, 0, 0, nullptr);
+}
+
+static int dense_backward_tc(mpn_ctx* c, cudaStream_t s, const Linear& L, float* grads, const float* gY, int ldgy, const float* a_in, int lda,
+                             int M, float* gX, int ldgx) {
+  TrainWs& t = c->tw;
+  int r;
+  if ((r = narrow_transpose(c, s, gY, ldgy, M, L.out, t.dgyT))) return r;         // [out][M]
+  if ((r = narrow_transpose(c, s, a_in, lda, M, L.in, t.daT))) return r;          // [in][M]
+  if ((r = launch_gemm_tc_ex(c, s, 1, t.dgyT, M, 0, t.daT, M, 0, M, t.zeros, L.out, L.in, gw(c, grads, L), L.in, 0, 0, nullptr))) return r;
+  colsum_kernel<<<(L.out + 31) / 32, 256, 0, s>>>(gY, ldgy, M, L.out, gbias(c, grads, L));
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  if (!gX) return MPN_OK;
+  if ((r = narrow_rows(c, s, gY, ldgy, M, L.out, t.dgy))) return r;               // [M][out]
+  if ((r = narrow_rows(c, s, L.wt, L.out, L.in, L.out, t.dwT))) return r;         // W^T [in][out]
+  return launch_gemm_tc_ex(c, s, 1, t.dgy, L.out, 0, t.dwT, L.out, 0, L.out, t.zeros, M, L.in, gX, ldgx, 0, 0, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------- forward (saves state)
@@ -957,25 +1028,27 @@ static int train_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, const f
     if ((r = launch_sa_simt(c, s, 1, w.xyz1, 3, w.feat1, 64, B, SA1_NPOINT, w.xyz2, w.feat2, t.ball2, t.arg2))) return r;
   }
   if (!tcp && (r = launch_sa_simt(c, s, 2, w.xyz2, 3, w.feat2, 256, B, SA2_NPOINT, nullptr, w.feat3, nullptr, t.arg3))) return r;
-  if ((r = launch_linear(c, s, W.fc[0], w.feat3, 1024, B, t.z1, 4096, 0))) return r;
+  const bool dtc = tcp && dense_tc_ok(W.fc[0], B);   // bf16 mode: the big dense layers on the tensor-core GEMM
+  auto dense = [&](const Linear& L, const float* X, int ldx, float* Y, int ldy, int act) {
+    return dtc ? dense_forward_tc(c, s, L, X, ldx, B, Y, ldy, act) : launch_linear(c, s, L, X, ldx, B, Y, ldy, act);
+  };
+  if ((r = dense(W.fc[0], w.feat3, 1024, t.z1, 4096, 0))) return r;
   if ((r = launch_groupnorm_lrelu_train(c, s, t.z1, B, 4096, 16, W.gn_w[0], W.gn_b[0], t.a1, t.st1))) return r;
-  if ((r = launch_linear(c, s, W.fc[1], t.a1, 4096, B, t.z2, 2048, 0))) return r;
+  if ((r = dense(W.fc[1], t.a1, 4096, t.z2, 2048, 0))) return r;
   if ((r = launch_groupnorm_lrelu_train(c, s, t.z2, B, 2048, 16, W.gn_w[1], W.gn_b[1], t.a2, t.st2))) return r;
-  if ((r = launch_linear(c, s, W.fc[2], t.a2, 2048, B, w.cat, CAT, 0))) return r;
+  if ((r = dense(W.fc[2], t.a2, 2048, w.cat, CAT, 0))) return r;
   if ((r = launch_linear(c, s, W.fe[0], qn, 7, B, t.f[0], 32, 1))) return r;
   if ((r = launch_linear(c, s, W.fe[1], t.f[0], 32, B, t.f[1], 64, 1))) return r;
   if ((r = launch_linear(c, s, W.fe[2], t.f[1], 64, B, t.f[2], 128, 1))) return r;
   if ((r = launch_linear(c, s, W.fe[3], t.f[2], 128, B, t.f[3], 128, 1))) return r;
   if ((r = launch_linear(c, s, W.fe[4], t.f[3], 128, B, w.cat + ENC_DIM, CAT, 0))) return r;
-  if ((r = launch_linear(c, s, W.dec[0], w.cat, CAT, B, t.d[0], 512, 1))) return r;
+  if ((r = dense(W.dec[0], w.cat, CAT, t.d[0], 512, 1))) return r;
   if ((r = launch_linear(c, s, W.dec[1], t.d[0], 512, B, t.d[1], 256, 1))) return r;
   if ((r = launch_linear(c, s, W.dec[2], t.d[1], 256, B, t.d[2], 128, 1))) return r;
   return launch_linear(c, s, W.dec[3], t.d[2], 128, B, w.dq, 7, 0);
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-static inline float* gw(const mpn_ctx* c, float* grads, const Linear& L) { return grads + (L.w - c->w.params); }
-static inline float* gbias(const mpn_ctx* c, float* grads, const Linear& L) { return grads + (L.b - c->w.params); }
 
 // one dense layer: gW, gb += ; gX[M][in] = (gY W) * f'(a_in)  (mask_mode 0: none)
 static int dense_backward(mpn_ctx* c, cudaStream_t s, const Linear& L, float* grads, const float* gY, int ldgy, const float* a_in,
@@ -1268,7 +1341,12 @@ int train_step_grads(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int
   if ((r = dense_backward(c, s, W.dec[3], grads, t.gy, 7, t.d[2], 128, B, t.ga, 128, 1))) return r;
   if ((r = dense_backward(c, s, W.dec[2], grads, t.ga, 128, t.d[1], 256, B, t.gb, 256, 1))) return r;
   if ((r = dense_backward(c, s, W.dec[1], grads, t.gb, 256, t.d[0], 512, B, t.ga, 512, 1))) return r;
-  if ((r = dense_backward(c, s, W.dec[0], grads, t.ga, 512, w.cat, CAT, B, t.gcat, CAT, 0))) return r;
+  const bool dtc = tcp && dense_tc_ok(W.fc[0], B);
+  auto dense_bwd = [&](const Linear& L, const float* gY, int ldgy, const float* a_in, int lda, float* gX, int ldgx) {
+    return dtc ? dense_backward_tc(c, s, L, grads, gY, ldgy, a_in, lda, B, gX, ldgx)
+               : dense_backward(c, s, L, grads, gY, ldgy, a_in, lda, B, gX, ldgx, 0);
+  };
+  if ((r = dense_bwd(W.dec[0], t.ga, 512, w.cat, CAT, t.gcat, CAT))) return r;
   // feature_encoder (model.py:47-57): 7 -> 32 -> 64 -> 128 -> 128 -> 64
   if ((r = dense_backward(c, s, W.fe[4], grads, t.gcat + ENC_DIM, CAT, t.f[3], 128, B, t.ga, 128, 1))) return r;
   if ((r = dense_backward(c, s, W.fe[3], grads, t.ga, 128, t.f[2], 128, B, t.gb, 128, 1))) return r;
@@ -1276,11 +1354,11 @@ int train_step_grads(mpn_ctx* c, cudaStream_t s, const mpn_scene& sc, int B, int
   if ((r = dense_backward(c, s, W.fe[1], grads, t.ga, 64, t.f[0], 32, B, t.gb, 32, 1))) return r;
   if ((r = dense_backward(c, s, W.fe[0], grads, t.gb, 32, q_norm, 7, B, nullptr, 0, 0))) return r;
   // FC head (model.py:385-393)
-  if ((r = dense_backward(c, s, W.fc[2], grads, t.gcat, CAT, t.a2, 2048, B, t.ga, 2048, 0))) return r;
+  if ((r = dense_bwd(W.fc[2], t.gcat, CAT, t.a2, 2048, t.ga, 2048))) return r;
   if ((r = gn_backward(c, s, t.z2, t.st2, W.gn_w[1], W.gn_b[1], t.ga, B, 2048, grads + (W.gn_w[1] - W.params), grads + (W.gn_b[1] - W.params)))) return r;
-  if ((r = dense_backward(c, s, W.fc[1], grads, t.ga, 2048, t.a1, 4096, B, t.gb, 4096, 0))) return r;
+  if ((r = dense_bwd(W.fc[1], t.ga, 2048, t.a1, 4096, t.gb, 4096))) return r;
   if ((r = gn_backward(c, s, t.z1, t.st1, W.gn_w[0], W.gn_b[0], t.gb, B, 4096, grads + (W.gn_w[0] - W.params), grads + (W.gn_b[0] - W.params)))) return r;
-  if ((r = dense_backward(c, s, W.fc[0], grads, t.gb, 4096, w.feat3, 1024, B, t.gfeat3, 1024, 0))) return r;
+  if ((r = dense_bwd(W.fc[0], t.gb, 4096, w.feat3, 1024, t.gfeat3, 1024))) return r;
   // set abstraction levels, last to first, in chunks of samples
   MPN_CHECK_CUDA(cudaMemsetAsync(t.gfeat2, 0, (size_t)B * SA2_NPOINT * 256 * 4, s));
   MPN_CHECK_CUDA(cudaMemsetAsync(t.gfeat1, 0, (size_t)B * SA1_NPOINT * 64 * 4, s));
