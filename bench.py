@@ -243,11 +243,27 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line of the run, on the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def setup_dist():
-    """torch.distributed over NCCL when launched by torchrun.  NCCL's own log lines (NCCL_DEBUG set by the caller) are sent to
-    stderr so that stdout stays the single JSON line and the communicator lines remain checkable."""
-    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+    """torch.distributed over NCCL when launched by torchrun.  Everything libraries print on fd 1 during the run (NCCL's version banner
+    and its NCCL_DEBUG lines) is sent to stderr, so that stdout stays the single JSON line and the communicator lines remain checkable."""
+    global _REAL_STDOUT
+    if not os.environ.get("NCCL_DEBUG_FILE"):
         os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -394,7 +410,7 @@ def run_training(args, world, rank, local):
                              "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
                              "algorithmic_flop_per_launch": flop, "note": "3 x the forward's algorithmic contraction flops per sample"},
                 "losses": [float(x) for x in losses.cpu()], "params": 19068103}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -652,7 +668,7 @@ def main():
             line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only: the other ranks must not wait on 10 s of CPU work
             line["cpu_baseline"] = cpu_baseline(eng.cfg.seed, wl)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
