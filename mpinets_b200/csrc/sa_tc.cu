@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(SA2W_THREADS, 1)
 sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* __restrict__ feat_bf16, const float* __restrict__ new_xyz,
                 float r2, const __nv_bfloat16* __restrict__ gw1, const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3,
                 const float* __restrict__ gb2, const float* __restrict__ gb3, __nv_bfloat16* __restrict__ out_bf16, int out_stride,
-                int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out, int split) {
+                int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out, int split, int pack) {
   using S = Sa2wSmem;
   constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT, KC = SA2W_KC;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -249,6 +249,8 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
   uint32_t phase = 0;
   bool ok = true;
   const unsigned lt = (1u << lane) - 1u;
+  __shared__ int hcnt_s[SA2W_NWG * 2 * 4];   // [NWG][2 slots][4]: distinct hits (<= 128) of a round's ball queries
+  int* hcnt = hcnt_s + g * 8;
 
   // one warp = one centroid: in-order scan of the 512 points, first 128 hits, first-hit padding (pointnet2 semantics)
   auto bq_round = [&](int base, int slot) {
@@ -269,16 +271,27 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
         cnt += __popc(hm);
       }
       for (int l = min(cnt, NSAMPLE) + lane; l < NSAMPLE; l += 32) out[l] = (uint16_t)first;
+      if (lane == 0) hcnt[slot * 4 + wq] = max(1, min(cnt, NSAMPLE));
     }
   };
-  float cx, cy, cz, dx, dy, dz;
+  // A round's four neighbourhoods are packed into as few 128-row tiles as their distinct rows need (TilePack, tc_common.cuh); the rows
+  // of the next tile (coordinates + 64 features) are fetched into registers under the current tile's layer-3 MMAs.
+  constexpr int STEP = SA2W_NWG * 4;
+  float dx, dy, dz;
   uint4 fr[8];
-  auto prefetch = [&](int jn, int slot, int cc) {
-    const float* cp = new_xyz + ((size_t)b * NCENT + jn) * 3;
-    cx = cp[0]; cy = cp[1]; cz = cp[2];
-    const int k = lists[(slot * 4 + cc) * 128 + t];
-    if (ball_idx) ball_idx[((size_t)b * NCENT + jn) * NSAMPLE + t] = k;
-    dx = fsub(px[k], cx); dy = fsub(py[k], cy); dz = fsub(pz[k], cz);
+  TilePack tp{0u, 0u, 0}, tpn{0u, 0u, 0};
+  int nvalid = 0, nvalid_n = 0;
+  auto open_round = [&](int nb, int nslot, TilePack& p, int& nv) {
+    nv = min(4, NCENT - nb);
+    p = pack_round(hcnt + nslot * 4, nv, pack);
+    if (ball_idx)
+      for (int c = 0; c < nv; ++c) ball_idx[((size_t)b * NCENT + nb + c) * NSAMPLE + t] = lists[(nslot * 4 + c) * 128 + t];
+  };
+  auto prefetch = [&](const TilePack& p, int nv, int nb, int nslot, int ntile) {
+    const int mc = pack_owner(p, nv, ntile, wq);
+    const float* cp = new_xyz + ((size_t)b * NCENT + nb + mc) * 3;
+    const int k = lists[(nslot * 4 + mc) * 128 + (wq - pack_q0(p, mc)) * 32 + lane];
+    dx = fsub(px[k], cp[0]); dy = fsub(py[k], cp[1]); dz = fsub(pz[k], cp[2]);
     const uint4* f = reinterpret_cast<const uint4*>(feat_bf16 + ((size_t)b * N + k) * 64);
 #pragma unroll
     for (int q = 0; q < 8; ++q) fr[q] = __ldg(f + q);
@@ -300,15 +313,13 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
   if (base0 < NCENT) {
     bq_round(base0, 0);
     wg_sync(g);
-    prefetch(base0, 0, 0);
+    open_round(base0, 0, tp, nvalid);
+    prefetch(tp, nvalid, base0, 0, 0);
   }
-  for (int base = base0; base < NCENT && ok; base += SA2W_NWG * split * 4, ++r) {
+  for (int base = base0; base < NCENT && ok; base += STEP * split, ++r) {
     const int slot = r & 1;
 #pragma unroll 1
-    for (int cc = 0; cc < 4 && ok; ++cc) {
-      const int j = base + cc;
-      if (j >= NCENT) break;
-      const float ccx = cx, ccy = cy, ccz = cz;
+    for (int tile = 0; tile < tp.ntiles && ok; ++tile) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, q, KC)) = fr[q];
       *reinterpret_cast<uint4*>(X + kmajor_chunk_off(t, 8, KC)) = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 1.0f), 0u, 0u);
@@ -345,56 +356,63 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
       tc_fence_before();
       wg_sync(g);
       issue(dW3, 0, dX, 0, 8);                                  // layer 3, channel tile 0 (transposed)
-      // next centroid: its ball-query round (if this was the last of the round) and its feature rows, under the MMAs
-      {
-        int jn = j + 1, nslot = slot, ncc = cc + 1;
-        if (cc == 3) { jn = base + SA2W_NWG * split * 4; nslot = slot ^ 1; ncc = 0; }
-        if (jn < NCENT) {
-          if (cc == 3) { bq_round(jn, nslot); wg_sync(g); }
-          prefetch(jn, nslot, ncc);
-        }
+      // next tile: its ball-query round (if this was the last tile of the round) and its rows, under the MMAs
+      if (tile + 1 < tp.ntiles) {
+        prefetch(tp, nvalid, base, slot, tile + 1);
+      } else {
+        const int nb = base + STEP * split;
+        if (nb < NCENT) { bq_round(nb, slot ^ 1); wg_sync(g); open_round(nb, slot ^ 1, tpn, nvalid_n); prefetch(tpn, nvalid_n, nb, slot ^ 1, 0); }
       }
-      __nv_bfloat16* o = out_bf16 + ((size_t)b * NCENT + j) * out_stride;
 #pragma unroll 1
-      for (int tile = 0; tile < 2; ++tile) {
+      for (int half = 0; half < 2; ++half) {
         ok = ok && mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
-        float m = -3.0e38f;
+        // transposed accumulator: lane = channel, column = tile row; the max over each quarter's 32 columns
+        float mq[4];
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 64) {
+        for (int q = 0; q < 4; q += 2) {
           uint32_t v[32], u[32];
-          tmem_ld32(tlane + c0, v);
-          tmem_ld32(tlane + c0 + 32, u);
+          tmem_ld32(tlane + q * 32, v);
+          tmem_ld32(tlane + q * 32 + 32, u);
           tmem_ld_wait();
+          float mv = __uint_as_float(v[0]), mu = __uint_as_float(u[0]);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) m = fmaxf(m, fmaxf(__uint_as_float(v[q]), __uint_as_float(u[q])));
+          for (int i = 1; i < 32; ++i) { mv = fmaxf(mv, __uint_as_float(v[i])); mu = fmaxf(mu, __uint_as_float(u[i])); }
+          mq[q] = mv;
+          mq[q + 1] = mu;
         }
-        o[tile * 128 + t] = __float2bfloat16_rn(fmaxf(m + sB3[tile * 128 + t], 0.f));
-        if constexpr (ARG) {   // training forward: the winning neighbour slot of this channel (first column attaining the maximum)
-          int arg = 0;
+        for (int c = 0; c < nvalid; ++c) {
+          if (pack_tile(tp, c) != tile) continue;
+          const int q0 = pack_q0(tp, c), q1 = pack_q1(tp, nvalid, c);
+          float m = -3.0e38f;
 #pragma unroll
-          for (int c0 = 64; c0 >= 0; c0 -= 64) {
-            uint32_t v[32], u[32];
-            tmem_ld32(tlane + c0, v);
-            tmem_ld32(tlane + c0 + 32, u);
-            tmem_ld_wait();
+          for (int q = 0; q < 4; ++q) m = (q >= q0 && q < q1) ? fmaxf(m, mq[q]) : m;
+          out_bf16[((size_t)b * NCENT + base + c) * out_stride + half * 128 + t] = __float2bfloat16_rn(fmaxf(m + sB3[half * 128 + t], 0.f));
+          if constexpr (ARG) {   // training forward: the winning row of this channel (first row of the centroid's list attaining the maximum)
+            int arg = 0;
+            for (int q = q1 - 1; q >= q0; --q) {
+              uint32_t v[32];
+              tmem_ld32(tlane + q * 32, v);
+              tmem_ld_wait();
 #pragma unroll
-            for (int q = 31; q >= 0; --q) arg = __uint_as_float(u[q]) == m ? c0 + 32 + q : arg;
-#pragma unroll
-            for (int q = 31; q >= 0; --q) arg = __uint_as_float(v[q]) == m ? c0 + q : arg;
+              for (int i = 31; i >= 0; --i) arg = __uint_as_float(v[i]) == m ? (q - q0) * 32 + i : arg;
+            }
+            arg_out[((size_t)b * NCENT + base + c) * 256 + half * 128 + t] = (uint8_t)arg;
           }
-          arg_out[((size_t)b * NCENT + j) * 256 + tile * 128 + t] = (uint8_t)arg;
         }
         tc_fence_before();
         wg_sync(g);                                             // every lane of the accumulator has been read
-        if (tile == 0) issue(dW3, W3_TILE1, dX, 0, 8);           // channel tile 1 into the same TMEM columns
+        if (half == 0) issue(dW3, W3_TILE1, dX, 0, 8);           // channel tile 1 into the same TMEM columns
       }
-      if (t < 8) {
-        float v = t == 0 ? ccx : (t == 1 ? ccy : (t == 2 ? ccz : 0.f));
-        o[256 + t] = __float2bfloat16_rn(v);
-        o[256 + 8 + t] = __float2bfloat16_rn(0.f);
+      for (int i = t; i < nvalid * 16; i += 128) {   // [x y z | 0-pad] columns of the tile's centroids
+        const int c = i >> 4, d = i & 15;
+        if (pack_tile(tp, c) != tile) continue;
+        const float v = d < 3 ? new_xyz[((size_t)b * NCENT + base + c) * 3 + d] : 0.f;
+        out_bf16[((size_t)b * NCENT + base + c) * out_stride + 256 + d] = __float2bfloat16_rn(v);
       }
     }
+    tp = tpn;
+    nvalid = nvalid_n;
   }
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
@@ -756,8 +774,8 @@ struct Sa1tSmem {
   static constexpr size_t cnt = ones + 128 * 16 * 2;                       // u32 [BUCKETS] grid-build counters
   static constexpr size_t lists = cnt + SA1_BUCKETS * 4;                   // [NWG][4][128] u16
   static constexpr size_t cand = lists + (size_t)SA1T_NWG * 4 * 128 * 2;   // [NWG][4][256] u16
-  static constexpr size_t red = cand + (size_t)SA1T_NWG * 4 * 256 * 2;     // [NWG][256] int
-  static constexpr size_t cxyz = red + (size_t)SA1T_NWG * 256 * 4;         // f32 [512][3]
+  static constexpr size_t red = cand + (size_t)SA1T_NWG * 4 * 256 * 2;     // [NWG][512] int
+  static constexpr size_t cxyz = red + (size_t)SA1T_NWG * 512 * 4;         // f32 [512][3]
   static constexpr size_t bars = cxyz + (size_t)SA1_NPOINT * 3 * 4;
   static constexpr size_t bstart = (bars + 64 + 15) / 16 * 16;             // u16 [BUCKETS + 1]
   static constexpr size_t cloud = (bstart + (SA1_BUCKETS + 1) * 2 + 15) / 16 * 16;   // float4 [N]
@@ -769,7 +787,7 @@ template <bool ARG>
 __global__ void __launch_bounds__(128 * SA1T_NWG, 1)
 sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gw1,
                const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, __nv_bfloat16* __restrict__ out_bf16,
-               int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out, int split) {
+               int* __restrict__ err, int32_t* __restrict__ ball_idx, uint8_t* __restrict__ arg_out, int split, int pack) {
   using S = Sa1tSmem;
   constexpr int KC = SA1_XK / 8, NS = NSAMPLE, NWG = SA1T_NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -789,7 +807,7 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
   const int g = warp >> 2, wq = warp & 3, t = threadIdx.x & 127, lane = threadIdx.x & 31;
   uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 4 * 128;
   uint16_t* wcand = reinterpret_cast<uint16_t*>(smem + S::cand) + (size_t)(g * 4 + wq) * 256;
-  int* red = reinterpret_cast<int*>(smem + S::red) + g * 256;
+  int* red = reinterpret_cast<int*>(smem + S::red) + g * 512;   // [0,128) per-warp pooled pairs | [128,256) per-centroid pooled pairs | [256,512) winning rows
   const float4* gcl = reinterpret_cast<const float4*>(cloud) + (size_t)b * N;
 
   stage_weight(gw1, 64, SA1_XK, sW1);
@@ -840,8 +858,10 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
     }
   }
   __shared__ int round_ctr[1 + 8];
+  __shared__ int hcnt_s[SA1T_NWG * 4];   // distinct hits (<= 128) of the round's four ball queries
   int* next_round = round_ctr;
   int* rsel = round_ctr + 1;
+  int* hcnt = hcnt_s + g * 4;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NWG; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
@@ -912,6 +932,7 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
       __syncwarp();
       const uint16_t first = H > 0 ? widx[0] : (uint16_t)0;
       for (int l = min(H, NS) + lane; l < NS; l += 32) widx[l] = first;
+      if (lane == 0) hcnt[wq] = max(1, min(H, NS));
     } else {
       int cnt = 0;
       uint16_t first = 0;
@@ -926,6 +947,7 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
         cnt += __popc(hm);
       }
       for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
+      if (lane == 0) hcnt[wq] = max(1, min(cnt, NS));
     }
     __syncwarp();
   };
@@ -962,15 +984,19 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
 
   for (int round = g; (round * split + part) * 4 < SA1_NPOINT && ok;) {
     const int base = (round * split + part) * 4;
-    if (base + wq < SA1_NPOINT) warp_ball_query(base + wq);
+    const int nvalid = min(4, SA1_NPOINT - base);
+    if (wq < nvalid) warp_ball_query(base + wq);
     wg_sync(g);
+    const TilePack tp = pack_round(hcnt, nvalid, pack);   // the round's distinct rows packed into 128-row tiles (tc_common.cuh)
+    if (ball_idx)
+      for (int c = 0; c < nvalid; ++c) ball_idx[((size_t)b * SA1_NPOINT + base + c) * NS + t] = lists[c * 128 + t];
 #pragma unroll 1
-    for (int cc = 0; cc < 4 && ok; ++cc) {
-      const int j = base + cc;
-      if (j >= SA1_NPOINT) break;
+    for (int tile = 0; tile < tp.ntiles && ok; ++tile) {
+      const int mc = pack_owner(tp, nvalid, tile, wq);   // this warp's quarter of the tile belongs to centroid base + mc
+      const int mq0 = pack_q0(tp, mc);
       {
-        const int k = lists[cc * 128 + t];
-        if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = k;
+        const int j = base + mc;
+        const int k = lists[mc * 128 + (wq - mq0) * 32 + lane];
         const float4 p = cl[k];
         const float dx = fsub(p.x, cxyz[3 * j]), dy = fsub(p.y, cxyz[3 * j + 1]), dz = fsub(p.z, cxyz[3 * j + 2]);
         const uint32_t row[8] = {pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u, 0u, 0u, 0u, 0u};
@@ -1021,13 +1047,17 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
       }
       tc_fence_before();
       wg_sync(g);
-      if (t < 32) {
-        const uint32_t m = bf16x2_max(bf16x2_max((uint32_t)red[t], (uint32_t)red[32 + t]), bf16x2_max((uint32_t)red[64 + t], (uint32_t)red[96 + t]));
-        reinterpret_cast<uint32_t*>(out_bf16 + ((size_t)b * SA1_NPOINT + j) * 64)[t] = m;
-        if constexpr (ARG) red[128 + t] = (int)m;
+      {   // the tile's centroids: warp c finishes centroid c (max over the quarters it owns)
+        const int c = wq;
+        if (c < nvalid && pack_tile(tp, c) == tile) {
+          const int q0 = pack_q0(tp, c), q1 = pack_q1(tp, nvalid, c);
+          uint32_t m = (uint32_t)red[q0 * 32 + lane];
+          for (int q = q0 + 1; q < q1; ++q) m = bf16x2_max(m, (uint32_t)red[q * 32 + lane]);
+          reinterpret_cast<uint32_t*>(out_bf16 + ((size_t)b * SA1_NPOINT + base + c) * 64)[lane] = m;
+          if constexpr (ARG) { red[128 + c * 32 + lane] = (int)m; red[256 + c * 64 + lane] = 255; red[256 + c * 64 + 32 + lane] = 255; }
+        }
       }
       if constexpr (ARG) {
-        if (t < 64) red[160 + t] = 255;
         wg_sync(g);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -1037,24 +1067,26 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
           tmem_ld_wait();
 #pragma unroll
           for (int rep = 0; rep < 4; ++rep) {
-            const uint32_t fin = (uint32_t)red[128 + 4 * (h * 4 + rep) + (lane & 3)];
+            const uint32_t fin = (uint32_t)red[128 + mc * 32 + 4 * (h * 4 + rep) + (lane & 3)];
             const int ch0 = 8 * (h * 4 + rep) + 2 * (lane & 3);
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
               const uint32_t* src = rr < 2 ? va : vb;
               const int o = rep * 4 + (rr & 1) * 2;
               const uint32_t pv = cvt_relu_bf16x2(__uint_as_float(src[o]), __uint_as_float(src[o + 1]));
-              const int row = wq * 32 + (lane >> 2) + 8 * rr;
-              if ((fin & 0xFFFFu) != 0u && (pv & 0xFFFFu) == (fin & 0xFFFFu)) atomicMin(&red[160 + ch0], row);
-              if ((fin >> 16) != 0u && (pv >> 16) == (fin >> 16)) atomicMin(&red[160 + ch0 + 1], row);
+              const int row = (wq - mq0) * 32 + (lane >> 2) + 8 * rr;   // row of the centroid's (padded) neighbour list
+              if ((fin & 0xFFFFu) != 0u && (pv & 0xFFFFu) == (fin & 0xFFFFu)) atomicMin(&red[256 + mc * 64 + ch0], row);
+              if ((fin >> 16) != 0u && (pv >> 16) == (fin >> 16)) atomicMin(&red[256 + mc * 64 + ch0 + 1], row);
             }
           }
         }
         tc_fence_before();
         wg_sync(g);
-        if (t < 64) {
-          const int a = red[160 + t];
-          arg_out[((size_t)b * SA1_NPOINT + j) * 64 + t] = (uint8_t)(a > 127 ? 0 : a);
+        for (int i = t; i < nvalid * 64; i += 128) {
+          const int c = i >> 6;
+          if (pack_tile(tp, c) != tile) continue;
+          const int a = red[256 + i];
+          arg_out[((size_t)b * SA1_NPOINT + base + c) * 64 + (i & 63)] = (uint8_t)(a > 127 ? 0 : a);
         }
       }
     }
@@ -1094,6 +1126,9 @@ __global__ void narrow_kernel(const float* __restrict__ src, size_t rows, int sr
   dst[i] = __float2bfloat16_rn(src[r * src_stride + cc]);
 }
 
+// A/B switch of the packed row tiles (tc_common.cuh: TilePack), read per launch: MPN_SA_NOPACK=1 gives every centroid its own 128-row tile
+int sa_pack() { return getenv("MPN_SA_NOPACK") == nullptr; }
+
 // Small batches leave most SMs without a problem: deal each problem's rounds of 4 centroids to `split` CTAs (each rebuilds the
 // problem's shared-memory state) so that about one CTA per SM is in flight.  max_split: rounds per warpgroup of an unsplit CTA.
 int sa_split(const mpn_ctx* c, int B, int max_split) {
@@ -1116,7 +1151,7 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
       MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
       const int split = sa_split(c, B, 128 / SA1T_NWG);
       kern<<<B * split, 128 * SA1T_NWG, smem_t, s>>>(xyz, N, new_xyz, SA1_RADIUS * SA1_RADIUS, tw.sa[0][0], tw.sa[0][1], tw.sa[0][2], out,
-                                                     tc_error_flag(c), ball_idx, arg_out, split);
+                                                     tc_error_flag(c), ball_idx, arg_out, split, sa_pack());
     } else {
       size_t smem7 = Sa1wSmem<7>::total(N);
       MPN_REQUIRE(smem7 <= 227 * 1024, "tensor-core SA1: %d points do not fit", N);
@@ -1136,7 +1171,7 @@ static int launch_sa_tc(mpn_ctx* c, cudaStream_t s, const float* xyz, int stride
     MPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     const int split = sa_split(c, B, 32 / SA2W_NWG);
     kern<<<B * split, SA2W_THREADS, smem3, s>>>(xyz, stride, feat, new_xyz, SA2_RADIUS * SA2_RADIUS, tw.sa[1][0], tw.w2_nofold, tw.sa[1][2],
-                                                c->w.sa[1][1].b, c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx, arg_out, split);
+                                                c->w.sa[1][1].b, c->w.sa[1][2].b, out, out_stride, tc_error_flag(c), ball_idx, arg_out, split, sa_pack());
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;

@@ -30,6 +30,7 @@ using namespace tc;
 
 int* tc_error_flag(mpn_ctx* c);
 int sa_split(const mpn_ctx* c, int B, int max_split);
+int sa_pack();
 int launch_gemm_tc_ex(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, int lda, int a_lo_off, const __nv_bfloat16* W, int ldw,
                       int w_lo_off, int K, const float* bias, int M, int N, void* C, int ldc, int c_lo_off, int split, uint8_t* arg_out);
 int launch_groupnorm_lrelu_split(mpn_ctx* c, cudaStream_t s, float* x, int M, int C, int groups, const float* gamma, const float* beta,
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(128 * S1X_NWG, 1)
 sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz, float r2, const __nv_bfloat16* __restrict__ gl1,
                 const __nv_bfloat16* __restrict__ ghi2, const __nv_bfloat16* __restrict__ glo2, const __nv_bfloat16* __restrict__ ghi3,
                 const __nv_bfloat16* __restrict__ glo3, __nv_bfloat16* __restrict__ out_rows, float* __restrict__ out_f32,
-                int* __restrict__ err, int32_t* __restrict__ ball_idx, int split) {
+                int* __restrict__ err, int32_t* __restrict__ ball_idx, int split, int pack) {
   using S = Sa1xSmem;
   constexpr int NS = NSAMPLE, NWG = S1X_NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -322,8 +323,10 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
     }
   }
   __shared__ int round_ctr[1 + 8];
+  __shared__ int hcnt_s[S1X_NWG * 4];   // distinct hits (<= 128) of the round's four ball queries
   int* next_round = round_ctr;
   int* rsel = round_ctr + 1;
+  int* hcnt = hcnt_s + g * 4;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NWG; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
@@ -394,6 +397,7 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
       __syncwarp();
       const uint16_t first = H > 0 ? widx[0] : (uint16_t)0;
       for (int l = min(H, NS) + lane; l < NS; l += 32) widx[l] = first;
+      if (lane == 0) hcnt[wq] = max(1, min(H, NS));
     } else {
       int cnt = 0;
       uint16_t first = 0;
@@ -408,6 +412,7 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
         cnt += __popc(hm);
       }
       for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
+      if (lane == 0) hcnt[wq] = max(1, min(cnt, NS));
     }
     __syncwarp();
   };
@@ -450,15 +455,18 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
 
   for (int round = g; (round * split + part) * 4 < SA1_NPOINT && ok;) {
     const int base = (round * split + part) * 4;
-    if (base + wq < SA1_NPOINT) warp_ball_query(base + wq);
+    const int nvalid = min(4, SA1_NPOINT - base);
+    if (wq < nvalid) warp_ball_query(base + wq);
     wg_sync_x(g);
+    const TilePack tp = pack_round(hcnt, nvalid, pack);   // the round's distinct rows packed into 128-row tiles (tc_common.cuh)
+    if (ball_idx)
+      for (int c = 0; c < nvalid; ++c) ball_idx[((size_t)b * SA1_NPOINT + base + c) * NS + t] = lists[c * 128 + t];
 #pragma unroll 1
-    for (int cc = 0; cc < 4 && ok; ++cc) {
-      const int j = base + cc;
-      if (j >= SA1_NPOINT) break;
+    for (int tile = 0; tile < tp.ntiles && ok; ++tile) {
       {
-        const int k = lists[cc * 128 + t];
-        if (ball_idx) ball_idx[((size_t)b * SA1_NPOINT + j) * NS + t] = k;
+        const int mc = pack_owner(tp, nvalid, tile, wq);   // this warp's quarter of the tile belongs to centroid base + mc
+        const int j = base + mc;
+        const int k = lists[mc * 128 + (wq - pack_q0(tp, mc)) * 32 + lane];
         const float4 p = cl[k];
         const float dx = fsub(p.x, cxyz[3 * j]), dy = fsub(p.y, cxyz[3 * j + 1]), dz = fsub(p.z, cxyz[3 * j + 2]);
         uint32_t h0, l0, h1, l1;
@@ -486,7 +494,7 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
       }
       ok = ok && mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
-      // fp32 max over the 128 neighbour rows: accumulator-fragment loads (a thread holds 4 rows x 16 channels) -> in-thread max ->
+      // fp32 max over each warp's 32 rows: accumulator-fragment loads (a thread holds 4 rows x 16 channels) -> in-thread max ->
       // halving butterfly over the warp's 8 row classes -> lane L holds channels 2L, 2L + 1 of the warp's 32 rows
       {
         float v[16];
@@ -509,18 +517,27 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
       }
       tc_fence_before();
       wg_sync_x(g);
-      if (t < A1_K) {
+      // the tile's centroids: max over the quarters each one owns, ReLU, split, output row [64 features | x y z | 0-pad]
+      for (int i = t; i < nvalid * A1_K; i += 128) {
+        const int c = i / A1_K, ch = i - c * A1_K;
+        if (pack_tile(tp, c) != tile) continue;
+        const int j = base + c;
         float m = 0.f;
-        if (t < 64) m = fmaxf(fmaxf(fmaxf(red[t], red[64 + t]), fmaxf(red[128 + t], red[192 + t])), 0.f);
-        else if (t < 67) m = cxyz[3 * j + t - 64];
+        if (ch < 64) {
+          const int q0 = pack_q0(tp, c), q1 = pack_q1(tp, nvalid, c);
+          m = red[q0 * 64 + ch];
+          for (int q = q0 + 1; q < q1; ++q) m = fmaxf(m, red[q * 64 + ch]);
+          m = fmaxf(m, 0.f);
+        } else if (ch < 67) {
+          m = cxyz[3 * j + ch - 64];
+        }
         __nv_bfloat16 h, l;
         split_bf16(m, h, l);
         __nv_bfloat16* o = out_rows + ((size_t)b * SA1_NPOINT + j) * (2 * A1_K);
-        o[t] = h;
-        o[A1_K + t] = l;
-        if (out_f32 && t < 64) out_f32[((size_t)b * SA1_NPOINT + j) * 64 + t] = m;
+        o[ch] = h;
+        o[A1_K + ch] = l;
+        if (out_f32 && ch < 64) out_f32[((size_t)b * SA1_NPOINT + j) * 64 + ch] = m;
       }
-      wg_sync_x(g);   // red is rewritten by the next centroid's pooling
     }
     if (t == 0) rsel[g] = atomicAdd(next_round, 1);
     wg_sync_x(g);   // the lists are rewritten by the next round
@@ -544,8 +561,8 @@ struct Sa2xSmem {
   static constexpr size_t w1x = b3 + 256 * 4;                           // [3][128] f32
   static constexpr size_t pts = w1x + 3 * 128 * 4;                      // x[512] | y[512] | z[512]
   static constexpr size_t lists = pts + 3 * SA1_NPOINT * 4;             // [NWG][2 slots][4][128] u16
-  static constexpr size_t u = lists + (size_t)S2X_NWG * 2 * 4 * 128 * 2;   // [NWG][128] f32: W1x c_i
-  static constexpr size_t pool = u + (size_t)S2X_NWG * 128 * 4;         // [NWG][2 tiles][4 warps][128] f32
+  static constexpr size_t u = lists + (size_t)S2X_NWG * 2 * 4 * 128 * 2;   // [NWG][4 quarters][128] f32: W1x c_i of the quarter's centroid
+  static constexpr size_t pool = u + (size_t)S2X_NWG * 4 * 128 * 4;     // [NWG][2 tiles][4 warps][128] f32
   static constexpr size_t bars = pool + (size_t)S2X_NWG * 2 * 4 * 128 * 4;
   static constexpr size_t total = bars + 64;
 };
@@ -554,7 +571,7 @@ __global__ void __launch_bounds__(S2X_THREADS, 1)
 sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restrict__ pre, const float* __restrict__ new_xyz, float r2,
                 const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, const float* __restrict__ gb2,
                 const float* __restrict__ gb3, const float* __restrict__ gw1x, __nv_bfloat16* __restrict__ out_rows,
-                float* __restrict__ out_f32, int* __restrict__ err, int32_t* __restrict__ ball_idx, int split) {
+                float* __restrict__ out_f32, int* __restrict__ err, int32_t* __restrict__ ball_idx, int split, int pack) {
   using S = Sa2xSmem;
   constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT, NWG = S2X_NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -571,7 +588,7 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int g = warp >> 2, wq = warp & 3, lane = threadIdx.x & 31, t = threadIdx.x & 127;
   uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 2 * 4 * 128;
-  float* sU = reinterpret_cast<float*>(smem + S::u) + g * 128;
+  float* sU = reinterpret_cast<float*>(smem + S::u) + g * 4 * 128;
   float* sPool = reinterpret_cast<float*>(smem + S::pool) + (size_t)g * 2 * 4 * 128;
 
   stage_weight_ld(gw2, 128, 128, 256, smem + S::w2h);
@@ -610,6 +627,8 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
   uint32_t phase = 0;
   bool ok = true;
   const unsigned lt = (1u << lane) - 1u;
+  __shared__ int hcnt_s[S2X_NWG * 2 * 4];   // [NWG][2 slots][4]: distinct hits (<= 128) of a round's ball queries
+  int* hcnt = hcnt_s + g * 8;
 
   // one warp = one centroid: in-order scan of the 512 points, first 128 hits, first-hit padding (pointnet2 semantics)
   auto bq_round = [&](int base, int slot) {
@@ -630,6 +649,7 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
         cnt += __popc(hm);
       }
       for (int l = min(cnt, NSAMPLE) + lane; l < NSAMPLE; l += 32) out[l] = (uint16_t)first;
+      if (lane == 0) hcnt[slot * 4 + wq] = max(1, min(cnt, NSAMPLE));
     }
   };
   // A_lo W_h + A_hi W_l + A_hi W_h (small terms first), K = 128 each, into the chain's accumulator
@@ -649,32 +669,46 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
     }
   };
 
-  // The gather of a centroid reads 128 rows x 512 B of `pre` from L2; the first quarter of the NEXT centroid's row is fetched into
-  // registers under the current centroid's layer-3 MMAs, and the other quarters are requested one step ahead of their use.
+  // The gather of a tile reads 128 rows x 512 B of `pre` from L2; the first quarter of the NEXT tile's row is fetched into
+  // registers under the current tile's layer-3 MMAs, and the other quarters are requested one step ahead of their use.
+  // A round's four neighbourhoods are packed into as few 128-row tiles as their distinct rows need (TilePack, tc_common.cuh).
+  constexpr int STEP = NWG * 4;
   int r = 0, kpre = 0;
   float4 xpre[8];
   const int base0 = (g * split + part) * 4;
-  auto prefetch = [&](int jn, int nslot, int ncc) {
-    kpre = lists[(nslot * 4 + ncc) * 128 + t];
+  TilePack tp{0u, 0u, 0}, tpn{0u, 0u, 0};
+  int nvalid = 0, nvalid_n = 0;
+  // after the ball queries of round (nb, nslot): counts -> packing, neighbour lists -> ball_idx
+  auto open_round = [&](int nb, int nslot, TilePack& p, int& nv) {
+    nv = min(4, NCENT - nb);
+    p = pack_round(hcnt + nslot * 4, nv, pack);
+    if (ball_idx)
+      for (int c = 0; c < nv; ++c) ball_idx[((size_t)b * NCENT + nb + c) * NSAMPLE + t] = lists[(nslot * 4 + c) * 128 + t];
+  };
+  auto prefetch = [&](const TilePack& p, int nv, int nslot, int ntile) {
+    const int mc = pack_owner(p, nv, ntile, wq);
+    kpre = lists[(nslot * 4 + mc) * 128 + (wq - pack_q0(p, mc)) * 32 + lane];
     const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + kpre) * 128);
 #pragma unroll
     for (int q = 0; q < 8; ++q) xpre[q] = __ldg(prow + q);
-    if (ball_idx) ball_idx[((size_t)b * NCENT + jn) * NSAMPLE + t] = kpre;
   };
-  if (base0 < NCENT) { bq_round(base0, 0); wg_sync_x(g); prefetch(base0, 0, 0); }
-  for (int base = base0; base < NCENT && ok; base += NWG * split * 4, ++r) {
+  if (base0 < NCENT) { bq_round(base0, 0); wg_sync_x(g); open_round(base0, 0, tp, nvalid); prefetch(tp, nvalid, 0, 0); }
+  for (int base = base0; base < NCENT && ok; base += STEP * split, ++r) {
     const int slot = r & 1;
 #pragma unroll 1
-    for (int cc = 0; cc < 4 && ok; ++cc) {
-      const int j = base + cc;
-      if (j >= NCENT) break;
-      const float* cp = new_xyz + ((size_t)b * NCENT + j) * 3;
-      const float cx = cp[0], cy = cp[1], cz = cp[2];
-      sU[t] = fmaf(sW1x[256 + t], cz, fmaf(sW1x[128 + t], cy, sW1x[t] * cx));   // W1x c_i
+    for (int tile = 0; tile < tp.ntiles && ok; ++tile) {
+      {   // W1x c of the centroid that owns each quarter of this tile
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* cp = new_xyz + ((size_t)b * NCENT + base + pack_owner(tp, nvalid, tile, q)) * 3;
+          sU[q * 128 + t] = fmaf(sW1x[256 + t], cp[2], fmaf(sW1x[128 + t], cp[1], sW1x[t] * cp[0]));
+        }
+      }
       wg_sync_x(g);
       // ---- layer 1 (per-point pre-activation - centroid term), ReLU, split, straight into the operand columns
       {
         const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + kpre) * 128);
+        const float* uq = sU + wq * 128;
         float4 xa[8], xb[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) xa[q] = xpre[q];
@@ -691,7 +725,7 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 xv = xa[q * 4 + i];
-              const float4 uv = *reinterpret_cast<const float4*>(sU + c0 + q * 16 + i * 4);
+              const float4 uv = *reinterpret_cast<const float4*>(uq + c0 + q * 16 + i * 4);
               split_relu_pack(xv.x - uv.x, xv.y - uv.y, hi[2 * i], lo[2 * i]);
               split_relu_pack(xv.z - uv.z, xv.w - uv.w, hi[2 * i + 1], lo[2 * i + 1]);
             }
@@ -728,23 +762,20 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
       tc_fence_before();
       wg_sync_x(g);
       issue(dW3h, dW3l, 0);                                      // layer 3, channels 0..127
-      // under the layer-3 MMAs: the next round's ball query (when this was the round's last centroid) and the next centroid's rows
-      {
-        int jn = j + 1, nslot = slot, ncc = cc + 1;
-        if (cc == 3) { jn = base + NWG * split * 4; nslot = slot ^ 1; ncc = 0; }
-        if (jn < NCENT) {
-          if (cc == 3) { bq_round(jn, nslot); wg_sync_x(g); }
-          prefetch(jn, nslot, ncc);
-        }
+      // under the layer-3 MMAs: the next round's ball query (when this was the round's last tile) and the next tile's rows
+      if (tile + 1 < tp.ntiles) {
+        prefetch(tp, nvalid, slot, tile + 1);
+      } else {
+        const int nb = base + STEP * split;
+        if (nb < NCENT) { bq_round(nb, slot ^ 1); wg_sync_x(g); open_round(nb, slot ^ 1, tpn, nvalid_n); prefetch(tpn, nvalid_n, slot ^ 1, 0); }
       }
-      __nv_bfloat16* o = out_rows + ((size_t)b * NCENT + j) * (2 * A3_KX);
 #pragma unroll 1
-      for (int tile = 0; tile < 2; ++tile) {
+      for (int half = 0; half < 2; ++half) {
         ok = ok && mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
-        // fp32 max over the 128 neighbour rows (= TMEM lanes): accumulator-fragment loads, in-thread max over a thread's 4 rows,
-        // halving butterfly over the warp's 8 row classes, 4 warps meet in shared memory
-        float* pl = sPool + tile * 4 * 128;
+        // fp32 max over each warp's 32 rows (= TMEM lanes): accumulator-fragment loads, in-thread max over a thread's 4 rows,
+        // halving butterfly over the warp's 8 row classes; the quarters of a centroid meet in shared memory
+        float* pl = sPool + half * 4 * 128;
         {
           float v[32];
 #pragma unroll
@@ -771,24 +802,34 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
         }
         tc_fence_before();
         wg_sync_x(g);                                            // every lane of the accumulator has been read
-        if (tile == 0) issue(dW3h, dW3l, W3_TILE1);              // channels 128..255 into the same TMEM columns
-        {
-          const float m = fmaxf(fmaxf(fmaxf(pl[t], pl[128 + t]), fmaxf(pl[256 + t], pl[384 + t])) + sB3[tile * 128 + t], 0.f);
+        if (half == 0) issue(dW3h, dW3l, W3_TILE1);              // channels 128..255 into the same TMEM columns
+        for (int c = 0; c < nvalid; ++c) {
+          if (pack_tile(tp, c) != tile) continue;
+          const int q0 = pack_q0(tp, c), q1 = pack_q1(tp, nvalid, c);
+          float m = pl[q0 * 128 + t];
+          for (int q = q0 + 1; q < q1; ++q) m = fmaxf(m, pl[q * 128 + t]);
+          m = fmaxf(m + sB3[half * 128 + t], 0.f);
           __nv_bfloat16 h, l;
           split_bf16(m, h, l);
-          o[tile * 128 + t] = h;
-          o[A3_KX + tile * 128 + t] = l;
-          if (out_f32) out_f32[((size_t)b * NCENT + j) * 256 + tile * 128 + t] = m;
+          __nv_bfloat16* o = out_rows + ((size_t)b * NCENT + base + c) * (2 * A3_KX);
+          o[half * 128 + t] = h;
+          o[A3_KX + half * 128 + t] = l;
+          if (out_f32) out_f32[((size_t)b * NCENT + base + c) * 256 + half * 128 + t] = m;
         }
       }
-      if (t < 16) {
-        const float v = t == 0 ? cx : (t == 1 ? cy : (t == 2 ? cz : 0.f));
+      for (int i = t; i < nvalid * 16; i += 128) {   // [x y z | 0-pad] columns of the tile's centroids
+        const int c = i >> 4, d = i & 15;
+        if (pack_tile(tp, c) != tile) continue;
+        const float v = d < 3 ? new_xyz[((size_t)b * NCENT + base + c) * 3 + d] : 0.f;
         __nv_bfloat16 h, l;
         split_bf16(v, h, l);
-        o[256 + t] = h;
-        o[A3_KX + 256 + t] = l;
+        __nv_bfloat16* o = out_rows + ((size_t)b * NCENT + base + c) * (2 * A3_KX);
+        o[256 + d] = h;
+        o[A3_KX + 256 + d] = l;
       }
     }
+    tp = tpn;
+    nvalid = nvalid_n;
   }
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
@@ -807,7 +848,7 @@ static int launch_sa1x3(mpn_ctx* c, cudaStream_t s, const float* cloud, int N, c
   MPN_CHECK_CUDA(cudaFuncSetAttribute(sa1x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int split = sa_split(c, B, 128 / S1X_NWG);
   sa1x3_tc_kernel<<<B * split, 128 * S1X_NWG, smem, s>>>(cloud, N, new_xyz, SA1_RADIUS * SA1_RADIUS, w.sa1_l1, w.sa1_hi[0], w.sa1_lo[0], w.sa1_hi[1],
-                                                         w.sa1_lo[1], out_rows, out_f32, tc_error_flag(c), ball_idx, split);
+                                                         w.sa1_lo[1], out_rows, out_f32, tc_error_flag(c), ball_idx, split, sa_pack());
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;
@@ -827,7 +868,7 @@ static int launch_sa2x3(mpn_ctx* c, cudaStream_t s, const float* xyz1, const flo
   MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sa2xSmem::total));
   const int split = sa_split(c, B, 32 / S2X_NWG);
   sa2x3_tc_kernel<<<B * split, S2X_THREADS, Sa2xSmem::total, s>>>(xyz1, 3, pre, xyz2, SA2_RADIUS * SA2_RADIUS, w.sa2_w2, w.sa2_w3, c->w.sa[1][1].b,
-                                                                  c->w.sa[1][2].b, w.sa2_w1x, out_rows, out_f32, tc_error_flag(c), ball_idx, split);
+                                                                  c->w.sa[1][2].b, w.sa2_w1x, out_rows, out_f32, tc_error_flag(c), ball_idx, split, sa_pack());
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

@@ -186,5 +186,46 @@ __device__ __forceinline__ uint32_t kmajor_chunk_off(int r, int kc, int kchunks)
   return (uint32_t)(((r >> 3) * kchunks + kc) * 128 + (r & 7) * 16);
 }
 
+// ---- packed row tiles of the set-abstraction kernels.  pointnet2's ball query pads a neighbourhood of H < nsample hits with copies
+// of its first hit, and the max-pool over a group ignores duplicates -- so only the H distinct rows of a group need to go through the
+// shared MLP.  A round of (up to) 4 centroids is therefore packed into as few 128-row MMA tiles as possible at a granularity of one
+// QUARTER (32 rows = one warp = 32 TMEM lanes): centroid c takes ceil(H_c / 32) consecutive quarters of one tile (first fit in centroid
+// order, a centroid never straddles tiles); quarters left over at the end of a tile continue the last centroid's (padded) list, so every
+// row of every tile is a valid row of the centroid that owns its quarter and the pooled result is bit-identical to the unpacked one.
+struct TilePack {
+  uint32_t tl;   // 2 bits per centroid: its tile
+  uint32_t qs;   // 2 bits per centroid: its first quarter inside the tile
+  int ntiles;
+};
+__device__ __forceinline__ TilePack pack_round(const int* hcnt, int nvalid, int pack) {
+  TilePack p{0u, 0u, 1};
+  int tile = 0, fill = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (c < nvalid) {
+      const int q = pack ? (hcnt[c] + 31) >> 5 : 4;
+      if (fill + q > 4) { ++tile; fill = 0; }
+      p.tl |= (uint32_t)tile << (2 * c);
+      p.qs |= (uint32_t)fill << (2 * c);
+      fill += q;
+    }
+  p.ntiles = tile + 1;
+  return p;
+}
+__device__ __forceinline__ int pack_tile(const TilePack& p, int c) { return (int)((p.tl >> (2 * c)) & 3u); }
+__device__ __forceinline__ int pack_q0(const TilePack& p, int c) { return (int)((p.qs >> (2 * c)) & 3u); }
+// one past the last quarter of centroid c inside its tile (a tile's last centroid also owns the left-over quarters)
+__device__ __forceinline__ int pack_q1(const TilePack& p, int nvalid, int c) {
+  return (c + 1 < nvalid && pack_tile(p, c + 1) == pack_tile(p, c)) ? pack_q0(p, c + 1) : 4;
+}
+// the centroid (0..3 within the round) that owns quarter q of tile `tile`
+__device__ __forceinline__ int pack_owner(const TilePack& p, int nvalid, int tile, int q) {
+  int mc = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (c < nvalid && pack_tile(p, c) == tile && pack_q0(p, c) <= q) mc = c;
+  return mc;
+}
+
 }  // namespace tc
 }  // namespace mpn
