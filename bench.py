@@ -45,6 +45,16 @@ FLOP_TOTAL = 2 * 1_635_159_136
 # bf16 MMA flops the bf16x3 mode actually issues per algorithmic flop (three products per MAC; SA2's first layer is evaluated per
 # point instead of per pair, so its 67-wide layer costs 1/32 of the pairwise form)
 X3_MMA_FACTOR = {"sa1": 3.0, "sa2": 3.0 * (128 * 128 + 128 * 256) / (67 * 128 + 128 * 128 + 128 * 256), "sa3": 3.0, "fc": 3.0}
+# The fused SA kernels push only the DISTINCT neighbour rows of a group through the shared MLP, packed into 128-row MMA tiles
+# (mpn_sa_tile_counts): groups per problem, and the bf16 MMA flops ONE tile issues in each mode (count of tcgen05.mma x 2*M*N*K):
+SA_GROUPS = {"sa1": 512, "sa2": 128}
+MMA_FLOP_PER_TILE = {
+    "bf16": {"sa1": 12 * 2 * 128 * 64 * 16,        # 3 x (bias step + K steps): 2 + 5 + 5
+             "sa2": 29 * 2 * 128 * 128 * 16},      # 5 + 8 + 2 x 8
+    "bf16x3": {"sa1": 27 * 2 * 128 * 64 * 16,      # 1 + 2 x (bias step + 3 x 4)
+               "sa2": 72 * 2 * 128 * 128 * 16},    # 3 x 8 + 2 x 3 x 8; layer 1 = the per-point GEMM below
+}
+SA2_PRE_MMA_FLOP = 3 * 2 * 512 * 80 * 128          # bf16x3: per-point layer-1 GEMM of SA2, per problem
 BYTES_PER_STEP = {"sample_robot": 2048 * 16 + 11 * 48, "sweep": 28 + 3200 + 1, "build_cloud": 6272 * 16,
                   "fps1": 6272 * 16 + 512 * 16, "fps2": 512 * 12 + 128 * 16}
 WORKLOADS = {
@@ -281,30 +291,81 @@ def setup_dist():
     return world, rank, local
 
 
-def roofline_of(stages, per_stage, B, peaks, mode, traffic):
+def sa_work(k, B, mode, tiles_per_launch):
+    """executed work of one SA launch: rows really pushed through the shared MLP (tiles x 128) vs the reference's 128 rows per group"""
+    ratio = tiles_per_launch / float(SA_GROUPS[k] * B)            # 128-row tiles per group (1.0 = the reference formulation)
+    issued = tiles_per_launch * MMA_FLOP_PER_TILE[mode][k] + (SA2_PRE_MMA_FLOP * B if (k == "sa2" and mode == "bf16x3") else 0)
+    return {"tiles_per_group": ratio, "executed_flop": FLOP_PER_STEP[k] * B * ratio, "issued_mma_flop": issued}
+
+
+def roofline_of(stages, per_stage, B, peaks, mode, traffic, tiles=None):
+    """tiles: {"sa1": tiles per launch, "sa2": ...} from mpn_sa_tile_counts (None for the fp32 mode)"""
     total_stage_ms = sum(v["ms"] for v in stages.values())
     dom = max((k for k in per_stage if k in FLOP_PER_STEP or k in BYTES_PER_STEP), key=lambda k: stages[k]["ms"])
     tkey = dom + ("_x3" if mode == "bf16x3" else "")
     dom_traffic = traffic[tkey]["dram_bytes_per_problem"] * B if tkey in traffic else None
     if dom in FLOP_PER_STEP:
-        ach = FLOP_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e12
+        sec = per_stage[dom] / 1000.0
+        ref_flop = FLOP_PER_STEP[dom] * B
         peak = peaks["bf16_sustained"]
+        if tiles and dom in SA_GROUPS and mode in MMA_FLOP_PER_TILE:
+            w = sa_work(dom, B, mode, tiles[dom])
+            flop, issued = w["executed_flop"], w["issued_mma_flop"]
+        else:
+            flop, issued = ref_flop, ref_flop * (X3_MMA_FACTOR.get(dom, 3.0) if mode == "bf16x3" else 1.0)
+        ach = flop / sec / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": dom_traffic, "peak_source": peaks["source"] + ", sustained bf16",
-                "algorithmic_flop_per_launch": FLOP_PER_STEP[dom] * B, "avg_launch_ms": per_stage[dom],
-                "share_of_step": stages[dom]["ms"] / total_stage_ms}
+                "algorithmic_flop_per_launch": flop, "avg_launch_ms": per_stage[dom],
+                "share_of_step": stages[dom]["ms"] / total_stage_ms,
+                "issued_mma_flop_per_launch": issued, "issued_mma_frac_of_peak": issued / sec / 1e12 / peak,
+                "reference_formulation_flop_per_launch": ref_flop, "reference_formulation_tflops": ref_flop / sec / 1e12}
+        note = []
+        if tiles and dom in SA_GROUPS:
+            roof["tiles_per_group"] = tiles[dom] / float(SA_GROUPS[dom] * B)
+            note.append("algorithmic flops = the fp32 formulation of the rows the kernel really evaluates: a ball-query group holds H <= 128 "
+                        "distinct neighbours (the rest are copies of the first hit, which the max-pool ignores), the kernel packs the distinct "
+                        "rows of several groups into 128-row MMA tiles (%.3f tiles per group, counted on the device), so achieved = reference "
+                        "flops x tiles per group / time; reference_formulation_tflops counts all 128 rows per group and is NOT a hardware rate"
+                        % roof["tiles_per_group"])
         if mode == "bf16x3":
-            f = X3_MMA_FACTOR.get(dom, 3.0)
-            roof["note"] = ("algorithmic flops = the fp32 reference formulation; the bf16x3 mode issues %.2f bf16 MMA flops per "
-                            "algorithmic flop (a_hi w_hi + a_lo w_hi + a_hi w_lo), so the tensor pipe runs at frac x %.2f" % (f, f))
-            roof["issued_mma_frac_of_peak"] = ach * f / peak
+            note.append("the bf16x3 mode issues three bf16 MMAs per product (a_hi w_hi + a_lo w_hi + a_hi w_lo): the tensor pipe runs at "
+                        "issued_mma_frac_of_peak")
+        if note:
+            roof["note"] = "; ".join(note)
     else:
         ach = BYTES_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": dom_traffic, "peak_source": peaks["source"],
                 "algorithmic_bytes_per_launch": BYTES_PER_STEP[dom] * B, "avg_launch_ms": per_stage[dom],
                 "share_of_step": stages[dom]["ms"] / total_stage_ms}
+        if dom.startswith("fps"):
+            roof["note"] = ("latency-bound kernel: %d dependent selection rounds per problem; the HBM figure only says that its traffic "
+                            "(the cloud once) is not what limits it" % (511 if dom == "fps1" else 127))
     return roof
+
+
+def tensor_kernels_of(stages, tiles, B, mode, peaks):
+    """per tensor stage: ms per launch, executed (distinct-row) algorithmic TFLOP/s, issued bf16 MMA rate, reference-formulation rate"""
+    out = {}
+    for k in ("sa1", "sa2", "sa3", "fc"):
+        v = stages.get(k)
+        if not v or not v["launches"]:
+            continue
+        ms = v["ms"] / v["launches"]
+        sec = ms / 1000.0
+        ref = FLOP_PER_STEP[k] * B
+        if tiles and k in SA_GROUPS and mode in MMA_FLOP_PER_TILE:
+            w = sa_work(k, B, mode, tiles[k])
+            flop, issued = w["executed_flop"], w["issued_mma_flop"]
+        else:
+            flop, issued = ref, ref * (X3_MMA_FACTOR[k] if mode == "bf16x3" else 1.0)
+        out[k] = {"ms": ms, "TFLOPs": flop / sec / 1e12, "frac_of_bf16_sustained": flop / sec / 1e12 / peaks["bf16_sustained"],
+                  "issued_mma_frac_of_bf16_sustained": issued / sec / 1e12 / peaks["bf16_sustained"],
+                  "reference_formulation_tflops": ref / sec / 1e12}
+        if tiles and k in SA_GROUPS:
+            out[k]["tiles_per_group"] = tiles[k] / float(SA_GROUPS[k] * B)
+    return out
 
 
 def run_training(args, world, rank, local):
@@ -492,6 +553,7 @@ def main():
             clocks.start()
         if profile:
             eng.profile(True)
+            eng.sa_tile_counts(reset=True)
         l0 = eng.launch_count
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -505,6 +567,9 @@ def main():
         if profile:
             out["stages"] = eng.profile_read()
             eng.profile(False)
+            t1, t2 = eng.sa_tile_counts(reset=True)
+            n1, n2 = out["stages"]["sa1"]["launches"], out["stages"]["sa2"]["launches"]
+            out["tiles"] = {"sa1": t1 / max(n1, 1), "sa2": t2 / max(n2, 1)} if prec_ != _lib.PREC_FP32 else None
         if clocks:
             out["clocks"] = clocks.stop()
         return out
@@ -551,6 +616,7 @@ def main():
         fr = timed_job(host, _lib.PREC_BF16, K, W, profile=True)
         fast = {"dtype": "bf16", "value": world * B * K / (fr["ms"] / 1000.0), "unit": "env steps/s", "ms_per_step": fr["ms"] / K,
                 "gpu_launches": fr["launches"], "stage_ms_per_step": {k: v["ms"] / K for k, v in fr["stages"].items() if v["launches"]},
+                "tensor_kernels": tensor_kernels_of(fr["stages"], fr["tiles"], B, "bf16", load_peaks()),
                 "collision_rate": float(fr["metrics"][:, 0].mean().item()), "_run": fr}
 
     # ---- configs[2] next to the N = 1 default: cubby + dresser, the full T = 70 rollout with the per-step check
@@ -616,14 +682,8 @@ def main():
         peaks = load_peaks()
         traffic = load_traffic()
         per_stage = {k: (v["ms"] / max(v["launches"], 1)) for k, v in stages.items() if v["launches"]}
-        roof = roofline_of(stages, per_stage, B, peaks, precision, traffic)
-        tensor_kernels = {}
-        for k in ("sa1", "sa2", "sa3", "fc"):
-            if k in per_stage:
-                tf = FLOP_PER_STEP[k] * B / (per_stage[k] / 1000.0) / 1e12
-                tensor_kernels[k] = {"TFLOPs": tf, "frac_of_bf16_sustained": tf / peaks["bf16_sustained"], "ms": per_stage[k]}
-                if precision == "bf16x3":
-                    tensor_kernels[k]["issued_mma_frac_of_bf16_sustained"] = tf * X3_MMA_FACTOR[k] / peaks["bf16_sustained"]
+        roof = roofline_of(stages, per_stage, B, peaks, precision, traffic, main_run.get("tiles"))
+        tensor_kernels = tensor_kernels_of(stages, main_run.get("tiles"), B, precision, peaks)
         hbm_kernels = {}
         for k in ("sample_robot", "sweep", "fps1"):
             if k in per_stage:
@@ -650,8 +710,8 @@ def main():
             "roofline": roof,
             "stage_ms_per_step": {k: v["ms"] / K for k, v in stages.items() if v["launches"]},
             "hbm_kernels": hbm_kernels, "tensor_kernels": tensor_kernels,
-            "tensor_flops_per_step": FLOP_TOTAL * B,
-            "achieved_tflops_whole_step": FLOP_TOTAL * B * K * world / (ms / 1000.0) / 1e12,
+            "reference_formulation_flops_per_step": FLOP_TOTAL * B,
+            "reference_formulation_tflops_whole_step": FLOP_TOTAL * B * K * world / (ms / 1000.0) / 1e12,
             "collision_rate": float(main_run["gathered"][:, 0].mean().item()),
         }
         if world > 1:

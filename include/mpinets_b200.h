@@ -295,6 +295,12 @@ int mpn_profile_read(mpn_ctx* ctx, float* ms /*[MPN_NUM_STAGES]*/, int64_t* laun
  * status (device int) is set to 1 when the MMA completion barrier timed out. */
 /* synchronises and returns the tensor-core path's sticky error flag (1 = an MMA completion barrier timed out) */
 int mpn_tc_error(mpn_ctx* ctx, int* out);
+/* executed-work accounting of the tensor-core set-abstraction kernels (replaces nothing in the reference; bench.py's roofline leg):
+ * the fused SA kernels pack the DISTINCT neighbour rows of several groups into shared 128-row MMA tiles (pointnet2's ball query pads a
+ * group with copies of its first hit -- ball_query_gpu.cu semantics, SURVEY App. A.1 -- and the max-pool ignores duplicates), so the
+ * tensor work they issue is (tiles) x (MMA flops per tile), not the reference's 128 rows per group.  out[0] / out[1] = number of tiles
+ * issued by the SA1 / SA2 kernels of this context since the last reset; synchronises the device. */
+int mpn_sa_tile_counts(mpn_ctx* ctx, uint64_t* out /*[2]*/, int reset);
 int mpn_tc_selftest(mpn_ctx* ctx, void* stream, const void* a_bf16, const void* b_bf16, float* d, int N, int K, int mode,
                     int* status);
 

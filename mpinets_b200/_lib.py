@@ -26,7 +26,7 @@ EXPORTS = (
     "mpn_sa_forward", "mpn_fk", "mpn_sample_robot", "mpn_sample_end_effector", "mpn_compute_spheres", "mpn_normalize_joints",
     "mpn_unnormalize_joints", "mpn_sdf_points", "mpn_build_cloud", "mpn_build_cloud_from_points", "mpn_build_cloud_ids", "mpn_augment_joints", "mpn_clean_point_cloud", "mpn_render_depth_cloud", "mpn_sweep_flags", "mpn_evaluate", "mpn_sparc", "mpn_collision_loss", "mpn_point_match_loss", "mpn_bc_collision_losses", "mpn_encoder_forward",
     "mpn_policy_forward", "mpn_rollout", "mpn_param_count", "mpn_param_info", "mpn_get_params", "mpn_set_params", "mpn_weights_sync",
-    "mpn_train_step_grads", "mpn_train_tc_gemm", "mpn_train_tc_wgrad", "mpn_train_pooled_rows", "mpn_adam_step", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error", "mpn_tc_gemm_selftest",
+    "mpn_train_step_grads", "mpn_train_tc_gemm", "mpn_train_tc_wgrad", "mpn_train_pooled_rows", "mpn_adam_step", "mpn_launch_count", "mpn_profile", "mpn_profile_read", "mpn_tc_selftest", "mpn_tc_error", "mpn_tc_gemm_selftest", "mpn_sa_tile_counts",
 )
 
 
@@ -109,6 +109,7 @@ def load():
         "mpn_train_tc_wgrad": [P, P, P, P, C.c_int64, P, C.c_int64, C.POINTER(C.c_int), I],
         "mpn_profile": [P, I],
         "mpn_tc_error": [P, C.POINTER(C.c_int)],
+        "mpn_sa_tile_counts": [P, C.POINTER(C.c_uint64), I],
         "mpn_tc_selftest": [P, P, P, P, P, I, I, I, P],
         "mpn_tc_gemm_selftest": [P, P, P, P, P, I, I, I, P, I],
         "mpn_profile_read": [P, C.POINTER(C.c_float), C.POINTER(C.c_int64)],

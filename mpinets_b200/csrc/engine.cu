@@ -21,6 +21,7 @@ int tc_encoder_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, in
 int tc_prepare_weights(mpn_ctx* c);
 size_t tc_scratch_bytes(int B);
 int* tc_error_flag(mpn_ctx* c);
+int sa_tile_counts(mpn_ctx* c, unsigned long long* out, int reset);
 int tc_sa_forward(mpn_ctx* c, cudaStream_t s, int module, const float* xyz, int stride, const float* feats, int feat_stride, int B,
                   int N, const float* new_xyz, float* new_feats, int32_t* ball_idx);
 int tc_probe(mpn_ctx* c, cudaStream_t s, const void* A, const void* B, float* D, int N, int K, int mode, int* status);
@@ -388,6 +389,16 @@ int mpn_tc_error(mpn_ctx* c, int* out) {
   MPN_CHECK_CUDA(cudaDeviceSynchronize());
   MPN_CHECK_CUDA(cudaMemcpy(out, tc_error_flag(c), sizeof(int), cudaMemcpyDeviceToHost));
   return MPN_OK;
+}
+
+int mpn_sa_tile_counts(mpn_ctx* c, uint64_t* out, int reset) {
+  REQ_CTX(c);
+  MPN_REQUIRE(out, "mpn_sa_tile_counts: null output");
+  unsigned long long v[2] = {0ull, 0ull};
+  int r = sa_tile_counts(c, v, reset);
+  out[0] = v[0];
+  out[1] = v[1];
+  return r;
 }
 
 int mpn_profile(mpn_ctx* c, int enable) {

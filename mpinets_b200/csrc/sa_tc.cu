@@ -280,7 +280,7 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
   float dx, dy, dz;
   uint4 fr[8];
   TilePack tp{0u, 0u, 0}, tpn{0u, 0u, 0};
-  int nvalid = 0, nvalid_n = 0;
+  int nvalid = 0, nvalid_n = 0, ntiles_done = 0;
   auto open_round = [&](int nb, int nslot, TilePack& p, int& nv) {
     nv = min(4, NCENT - nb);
     p = pack_round(hcnt + nslot * 4, nv, pack);
@@ -411,9 +411,11 @@ sa2w3_tc_kernel(const float* __restrict__ xyz, int stride, const __nv_bfloat16* 
         out_bf16[((size_t)b * NCENT + base + c) * out_stride + 256 + d] = __float2bfloat16_rn(v);
       }
     }
+    ntiles_done += tp.ntiles;
     tp = tpn;
     nvalid = nvalid_n;
   }
+  if (t == 0 && ntiles_done) atomicAdd(sa_tile_counter(err, 1), (unsigned long long)ntiles_done);
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
   __syncthreads();
@@ -885,7 +887,11 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
   constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
   const unsigned lt = (1u << lane) - 1u;
 
-  // complete ball query of centroid jc by this warp -> lists[wq][0..127]   (same algorithm as sa1w_tc_kernel, cloud in smem)
+  // complete ball query of centroid jc by this warp -> lists[wq][0..H), H = hcnt[wq] distinct hits (same algorithm as sa1w_tc_kernel,
+  // cloud in smem).  Hits are ranked by original point index (the linear scan's first-128 order) only when more than 128 were found or
+  // the caller wants the index lists / winning rows (training); otherwise the max-pool takes the set in bucket order.  pointnet2's
+  // first-hit padding is never materialised: rows beyond H re-read row H - 1 (a duplicate either way).
+  const bool need_order = ARG || ball_idx != nullptr;
   auto warp_ball_query = [&](int jc) {
     uint16_t* widx = lists + wq * 128;
     const float qx = cxyz[3 * jc], qy = cxyz[3 * jc + 1], qz = cxyz[3 * jc + 2];
@@ -923,16 +929,17 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
         H += __popc(hm);
         __syncwarp();
       }
-      for (int h = lane; h < H; h += 32) {
-        const int my = wcand[h];
-        int rank = 0;
-        for (int i = 0; i < H; ++i) rank += wcand[i] < my;
-        if (rank < NS) widx[rank] = (uint16_t)my;
+      if (need_order || H > NS) {   // rank by original index: the linear scan's order (which 128 survive; ball_idx output)
+        for (int h = lane; h < H; h += 32) {
+          const int my = wcand[h];
+          int rank = 0;
+          for (int i = 0; i < H; ++i) rank += wcand[i] < my;
+          if (rank < NS) widx[rank] = (uint16_t)my;
+        }
+      } else {                      // the max-pool only needs the SET of (at most 128) hits
+        for (int h = lane; h < H; h += 32) widx[h] = wcand[h];
       }
-      __syncwarp();
-      const uint16_t first = H > 0 ? widx[0] : (uint16_t)0;
-      for (int l = min(H, NS) + lane; l < NS; l += 32) widx[l] = first;
-      if (lane == 0) hcnt[wq] = max(1, min(H, NS));
+      if (lane == 0) { hcnt[wq] = max(1, min(H, NS)); if (H == 0) widx[0] = 0; }
     } else {
       int cnt = 0;
       uint16_t first = 0;
@@ -946,8 +953,7 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
         if (hit && pos < NS) widx[pos] = (uint16_t)k;
         cnt += __popc(hm);
       }
-      for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
-      if (lane == 0) hcnt[wq] = max(1, min(cnt, NS));
+      if (lane == 0) { hcnt[wq] = max(1, min(cnt, NS)); if (cnt == 0) widx[0] = first; }
     }
     __syncwarp();
   };
@@ -982,21 +988,22 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
     tmem_st_wait();
   };
 
+  int ntiles_done = 0;
   for (int round = g; (round * split + part) * 4 < SA1_NPOINT && ok;) {
     const int base = (round * split + part) * 4;
     const int nvalid = min(4, SA1_NPOINT - base);
     if (wq < nvalid) warp_ball_query(base + wq);
     wg_sync(g);
     const TilePack tp = pack_round(hcnt, nvalid, pack);   // the round's distinct rows packed into 128-row tiles (tc_common.cuh)
-    if (ball_idx)
-      for (int c = 0; c < nvalid; ++c) ball_idx[((size_t)b * SA1_NPOINT + base + c) * NS + t] = lists[c * 128 + t];
+    if (ball_idx)   // pointnet2's output format: first-hit padding
+      for (int c = 0; c < nvalid; ++c) ball_idx[((size_t)b * SA1_NPOINT + base + c) * NS + t] = lists[c * 128 + (t < hcnt[c] ? t : 0)];
 #pragma unroll 1
     for (int tile = 0; tile < tp.ntiles && ok; ++tile) {
       const int mc = pack_owner(tp, nvalid, tile, wq);   // this warp's quarter of the tile belongs to centroid base + mc
       const int mq0 = pack_q0(tp, mc);
       {
         const int j = base + mc;
-        const int k = lists[mc * 128 + (wq - mq0) * 32 + lane];
+        const int k = lists[mc * 128 + min((wq - mq0) * 32 + lane, hcnt[mc] - 1)];
         const float4 p = cl[k];
         const float dx = fsub(p.x, cxyz[3 * j]), dy = fsub(p.y, cxyz[3 * j + 1]), dz = fsub(p.z, cxyz[3 * j + 2]);
         const uint32_t row[8] = {pack_bf16(dx, dy), pack_bf16(dz, p.w), 0u, 0u, 0u, 0u, 0u, 0u};
@@ -1090,10 +1097,12 @@ sa1t_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict__
         }
       }
     }
+    ntiles_done += tp.ntiles;
     if (t == 0) rsel[g] = atomicAdd(next_round, 1);
     wg_sync(g);   // the lists are rewritten by the next round
     round = rsel[g];
   }
+  if (t == 0 && ntiles_done) atomicAdd(sa_tile_counter(err, 0), (unsigned long long)ntiles_done);
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
   __syncthreads();
@@ -1112,11 +1121,19 @@ int* tc_error_flag(mpn_ctx* c) {
   static std::map<mpn_ctx*, int*> flags;
   auto it = flags.find(c);
   if (it != flags.end()) return it->second;
-  int* p = nullptr;
-  cudaMalloc(&p, sizeof(int));
-  cudaMemset(p, 0, sizeof(int));
+  int* p = nullptr;   // [0] sticky error flag | [2..5] two 64-bit counters: 128-row MMA tiles issued by the SA1 / SA2 kernels (sa_tile_counter)
+  cudaMalloc(&p, 32);
+  cudaMemset(p, 0, 32);
   flags[c] = p;
   return p;
+}
+// executed-work accounting of the packed SA kernels (bench.py's roofline: issued MMA flops = tiles x flops per tile)
+int sa_tile_counts(mpn_ctx* c, unsigned long long* out, int reset) {
+  int* p = tc_error_flag(c);
+  MPN_CHECK_CUDA(cudaDeviceSynchronize());
+  MPN_CHECK_CUDA(cudaMemcpy(out, p + 2, 16, cudaMemcpyDeviceToHost));
+  if (reset) MPN_CHECK_CUDA(cudaMemset(p + 2, 0, 16));
+  return MPN_OK;
 }
 
 __global__ void narrow_kernel(const float* __restrict__ src, size_t rows, int src_stride, int cols, __nv_bfloat16* __restrict__ dst) {

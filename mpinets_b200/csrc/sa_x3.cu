@@ -353,9 +353,12 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
   constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
   const unsigned lt = (1u << lane) - 1u;
 
-  // complete ball query of centroid jc by this warp -> lists[wq][0..127]: the 27 hash cells around the centroid, candidates
-  // tested against the cloud in shared memory, hits ranked by ORIGINAL point index (= the linear scan's first-128 order), first-hit
-  // padding; linear scan when a neighbourhood holds more than 256 candidates.  Same algorithm as sa1t_tc_kernel (sa_tc.cu).
+  // complete ball query of centroid jc by this warp -> lists[wq][0..H), H = hcnt[wq] distinct hits: the 27 hash cells around the
+  // centroid, candidates tested against the cloud in shared memory; hits ranked by ORIGINAL point index (= the linear scan's
+  // first-128 order) when more than 128 were found or the caller wants the index lists, otherwise left in bucket order (the max-pool
+  // takes the set).  pointnet2's first-hit padding is never materialised: rows beyond H re-read row H - 1 (a duplicate either way).
+  // Linear scan when a neighbourhood holds more than 256 candidates.  Same algorithm as sa1t_tc_kernel (sa_tc.cu).
+  const bool need_order = ball_idx != nullptr;
   auto warp_ball_query = [&](int jc) {
     uint16_t* widx = lists + wq * 128;
     const float qx = cxyz[3 * jc], qy = cxyz[3 * jc + 1], qz = cxyz[3 * jc + 2];
@@ -388,16 +391,17 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
         H += __popc(hm);
         __syncwarp();
       }
-      for (int h = lane; h < H; h += 32) {
-        const int my = wcand[h];
-        int rank = 0;
-        for (int i = 0; i < H; ++i) rank += wcand[i] < my;
-        if (rank < NS) widx[rank] = (uint16_t)my;
+      if (need_order || H > NS) {   // rank by original index: the linear scan's order (which 128 survive; ball_idx output)
+        for (int h = lane; h < H; h += 32) {
+          const int my = wcand[h];
+          int rank = 0;
+          for (int i = 0; i < H; ++i) rank += wcand[i] < my;
+          if (rank < NS) widx[rank] = (uint16_t)my;
+        }
+      } else {                      // the max-pool only needs the SET of (at most 128) hits
+        for (int h = lane; h < H; h += 32) widx[h] = wcand[h];
       }
-      __syncwarp();
-      const uint16_t first = H > 0 ? widx[0] : (uint16_t)0;
-      for (int l = min(H, NS) + lane; l < NS; l += 32) widx[l] = first;
-      if (lane == 0) hcnt[wq] = max(1, min(H, NS));
+      if (lane == 0) { hcnt[wq] = max(1, min(H, NS)); if (H == 0) widx[0] = 0; }
     } else {
       int cnt = 0;
       uint16_t first = 0;
@@ -411,8 +415,7 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
         if (hit && pos < NS) widx[pos] = (uint16_t)k;
         cnt += __popc(hm);
       }
-      for (int l = min(cnt, NS) + lane; l < NS; l += 32) widx[l] = first;
-      if (lane == 0) hcnt[wq] = max(1, min(cnt, NS));
+      if (lane == 0) { hcnt[wq] = max(1, min(cnt, NS)); if (cnt == 0) widx[0] = first; }
     }
     __syncwarp();
   };
@@ -453,20 +456,21 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
     tmem_st_wait();
   };
 
+  int ntiles_done = 0;
   for (int round = g; (round * split + part) * 4 < SA1_NPOINT && ok;) {
     const int base = (round * split + part) * 4;
     const int nvalid = min(4, SA1_NPOINT - base);
     if (wq < nvalid) warp_ball_query(base + wq);
     wg_sync_x(g);
     const TilePack tp = pack_round(hcnt, nvalid, pack);   // the round's distinct rows packed into 128-row tiles (tc_common.cuh)
-    if (ball_idx)
-      for (int c = 0; c < nvalid; ++c) ball_idx[((size_t)b * SA1_NPOINT + base + c) * NS + t] = lists[c * 128 + t];
+    if (ball_idx)   // pointnet2's output format: first-hit padding
+      for (int c = 0; c < nvalid; ++c) ball_idx[((size_t)b * SA1_NPOINT + base + c) * NS + t] = lists[c * 128 + (t < hcnt[c] ? t : 0)];
 #pragma unroll 1
     for (int tile = 0; tile < tp.ntiles && ok; ++tile) {
       {
         const int mc = pack_owner(tp, nvalid, tile, wq);   // this warp's quarter of the tile belongs to centroid base + mc
         const int j = base + mc;
-        const int k = lists[mc * 128 + (wq - pack_q0(tp, mc)) * 32 + lane];
+        const int k = lists[mc * 128 + min((wq - pack_q0(tp, mc)) * 32 + lane, hcnt[mc] - 1)];
         const float4 p = cl[k];
         const float dx = fsub(p.x, cxyz[3 * j]), dy = fsub(p.y, cxyz[3 * j + 1]), dz = fsub(p.z, cxyz[3 * j + 2]);
         uint32_t h0, l0, h1, l1;
@@ -517,32 +521,36 @@ sa1x3_tc_kernel(const float* __restrict__ cloud, int N, const float* __restrict_
       }
       tc_fence_before();
       wg_sync_x(g);
-      // the tile's centroids: max over the quarters each one owns, ReLU, split, output row [64 features | x y z | 0-pad]
-      for (int i = t; i < nvalid * A1_K; i += 128) {
-        const int c = i / A1_K, ch = i - c * A1_K;
-        if (pack_tile(tp, c) != tile) continue;
-        const int j = base + c;
-        float m = 0.f;
-        if (ch < 64) {
-          const int q0 = pack_q0(tp, c), q1 = pack_q1(tp, nvalid, c);
-          m = red[q0 * 64 + ch];
-          for (int q = q0 + 1; q < q1; ++q) m = fmaxf(m, red[q * 64 + ch]);
-          m = fmaxf(m, 0.f);
-        } else if (ch < 67) {
-          m = cxyz[3 * j + ch - 64];
+      // the tile's centroids: warp c finishes centroid c -- max over the quarters it owns, ReLU, split, output row
+      // [64 features | x y z | 0-pad] as (hi | lo) bf16 pairs
+      if (wq < nvalid && pack_tile(tp, wq) == tile) {
+        const int q0 = pack_q0(tp, wq), q1 = pack_q1(tp, nvalid, wq), j = base + wq;
+        float2 m = *reinterpret_cast<const float2*>(red + q0 * 64 + 2 * lane);
+        for (int q = q0 + 1; q < q1; ++q) {
+          const float2 o = *reinterpret_cast<const float2*>(red + q * 64 + 2 * lane);
+          m.x = fmaxf(m.x, o.x); m.y = fmaxf(m.y, o.y);
         }
-        __nv_bfloat16 h, l;
-        split_bf16(m, h, l);
-        __nv_bfloat16* o = out_rows + ((size_t)b * SA1_NPOINT + j) * (2 * A1_K);
-        o[ch] = h;
-        o[A1_K + ch] = l;
-        if (out_f32 && ch < 64) out_f32[((size_t)b * SA1_NPOINT + j) * 64 + ch] = m;
+        m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f);
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out_rows + ((size_t)b * SA1_NPOINT + j) * (2 * A1_K));
+        uint32_t hi, lo;
+        split_pack(m.x, m.y, hi, lo);
+        o32[lane] = hi;
+        o32[A1_K / 2 + lane] = lo;
+        if (lane < 8) {
+          const float x0 = 2 * lane < 3 ? cxyz[3 * j + 2 * lane] : 0.f, x1 = 2 * lane + 1 < 3 ? cxyz[3 * j + 2 * lane + 1] : 0.f;
+          split_pack(x0, x1, hi, lo);
+          o32[32 + lane] = hi;
+          o32[A1_K / 2 + 32 + lane] = lo;
+        }
+        if (out_f32) *reinterpret_cast<float2*>(out_f32 + ((size_t)b * SA1_NPOINT + j) * 64 + 2 * lane) = m;
       }
     }
+    ntiles_done += tp.ntiles;
     if (t == 0) rsel[g] = atomicAdd(next_round, 1);
     wg_sync_x(g);   // the lists are rewritten by the next round
     round = rsel[g];
   }
+  if (t == 0 && ntiles_done) atomicAdd(sa_tile_counter(err, 0), (unsigned long long)ntiles_done);
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
   __syncthreads();
@@ -677,7 +685,7 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
   float4 xpre[8];
   const int base0 = (g * split + part) * 4;
   TilePack tp{0u, 0u, 0}, tpn{0u, 0u, 0};
-  int nvalid = 0, nvalid_n = 0;
+  int nvalid = 0, nvalid_n = 0, ntiles_done = 0;
   // after the ball queries of round (nb, nslot): counts -> packing, neighbour lists -> ball_idx
   auto open_round = [&](int nb, int nslot, TilePack& p, int& nv) {
     nv = min(4, NCENT - nb);
@@ -828,9 +836,11 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
         o[A3_KX + 256 + d] = l;
       }
     }
+    ntiles_done += tp.ntiles;
     tp = tpn;
     nvalid = nvalid_n;
   }
+  if (t == 0 && ntiles_done) atomicAdd(sa_tile_counter(err, 1), (unsigned long long)ntiles_done);
   if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
   tc_fence_before();
   __syncthreads();

@@ -227,5 +227,10 @@ __device__ __forceinline__ int pack_owner(const TilePack& p, int nvalid, int til
   return mc;
 }
 
+// the context's 64-bit tile counters live behind its sticky error flag (tc_error_flag, sa_tc.cu): module 0 = SA1, 1 = SA2
+__device__ __forceinline__ unsigned long long* sa_tile_counter(int* err, int module) {
+  return reinterpret_cast<unsigned long long*>(err + 2) + module;
+}
+
 }  // namespace tc
 }  // namespace mpn

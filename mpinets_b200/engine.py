@@ -133,6 +133,12 @@ class Engine:
         _lib.check(self.lib.mpn_tc_error(self._ctx, C.byref(v)))
         return bool(v.value)
 
+    def sa_tile_counts(self, reset: bool = False):
+        """(SA1, SA2) 128-row MMA tiles issued by the tensor-core set-abstraction kernels since the last reset (mpn_sa_tile_counts)."""
+        v = (C.c_uint64 * 2)()
+        _lib.check(self.lib.mpn_sa_tile_counts(self._ctx, v, 1 if reset else 0))
+        return int(v[0]), int(v[1])
+
     def tc_selftest(self, a: torch.Tensor, b: torch.Tensor, mode: int):
         """D = A[128,K] @ B[N,K]^T on one CTA via tcgen05 (bf16 in, fp32 out); returns (D, timed_out)."""
         _check(a, "a", torch.bfloat16, self.device); _check(b, "b", torch.bfloat16, self.device)

@@ -1,5 +1,5 @@
 """Per-source-line instruction counts and stall samples of one kernel in an .ncu-rep (needs --import-source on and -lineinfo).
-usage: python scripts/ncu_inst_by_line.py report.ncu-rep kernel_substring [top_n] [file_substring]"""
+usage: python scripts/ncu_inst_by_line.py report.ncu-rep kernel_substring [top_n] [samples]   (sorted by instructions, or by stall samples)"""
 import csv, io, subprocess, sys
 
 rep, want = sys.argv[1], sys.argv[2]
@@ -28,6 +28,7 @@ for fn, path, rows in blocks:
 tot = sum(a[0] for a in agg.values()) or 1
 tots = sum(a[1] for a in agg.values()) or 1
 print("total warp instructions:", tot, " samples:", tots)
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+bysmpl = len(sys.argv) > 4 and sys.argv[4] == "samples"
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1 if bysmpl else 0])[:top]:
     st = sorted(a[3].items(), key=lambda x: -x[1])[:2]
     print(f"{100 * a[0] / tot:5.1f}% inst {100 * a[1] / tots:5.1f}% smpl  {k[0]}:{k[1]:<4d} {a[2].strip()[:90]}  {st}")
