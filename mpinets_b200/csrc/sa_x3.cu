@@ -847,6 +847,281 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
+// ---------------------------------------------------------------------------------------------- SA2, split-bf16, 8 warps per chain
+// sa2x3_tc_kernel's chains were bound by their own SIMT phases: between two MMA batches the 4 warps of a chain gather, subtract, ReLU,
+// split and store 128 columns per row (~2000 instructions per thread and tile), so with two chains per SM the tensor pipe idled ~40 %
+// of the time (ncu: 51 % tensor-active, 30 % issue-active, 8 resident warps).  Here a chain is EIGHT warps: warp w owns TMEM lane
+// quarter w % 4 (the hardware's lane restriction) and column half w / 4, i.e. every SIMT phase is split over twice the threads.
+// Same arithmetic, same packing, same outputs as sa2x3_tc_kernel (kept as the A/B reference: MPN_SA2X3_V1=1).
+constexpr int S2H_THREADS = 256 * S2X_NWG;
+__device__ __forceinline__ void chain_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+
+__global__ void __launch_bounds__(S2H_THREADS, 1)
+sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restrict__ pre, const float* __restrict__ new_xyz, float r2,
+                 const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, const float* __restrict__ gb2,
+                 const float* __restrict__ gb3, const float* __restrict__ gw1x, __nv_bfloat16* __restrict__ out_rows,
+                 float* __restrict__ out_f32, int* __restrict__ err, int32_t* __restrict__ ball_idx, int split, int pack) {
+  using S = Sa2xSmem;
+  constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT, NWG = S2X_NWG;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* sB2 = reinterpret_cast<float*>(smem + S::b2);
+  float* sB3 = reinterpret_cast<float*>(smem + S::b3);
+  float* sW1x = reinterpret_cast<float*>(smem + S::w1x);
+  float* px = reinterpret_cast<float*>(smem + S::pts);
+  float* py = px + N;
+  float* pz = py + N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bars + 8 * NWG);
+
+  const int b = blockIdx.x / split, part = blockIdx.x % split;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int g = warp >> 3, wc = warp & 7, wq = wc & 3, hh = wc >> 2, lane = threadIdx.x & 31, u = threadIdx.x & 255;
+  const int row = wq * 32 + lane;                       // this thread's row of the tile (= TMEM lane)
+  uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 2 * 4 * 128;
+  float* sU = reinterpret_cast<float*>(smem + S::u) + g * 4 * 128;
+  float* sPool = reinterpret_cast<float*>(smem + S::pool) + (size_t)g * 2 * 4 * 128;
+
+  stage_weight_ld(gw2, 128, 128, 256, smem + S::w2h);
+  stage_weight_ld(gw2 + 128, 128, 128, 256, smem + S::w2l);
+  stage_weight_ld(gw3, 256, 128, 256, smem + S::w3h);
+  stage_weight_ld(gw3 + 128, 256, 128, 256, smem + S::w3l);
+  for (int i = threadIdx.x; i < 128; i += S2H_THREADS) sB2[i] = gb2[i];
+  for (int i = threadIdx.x; i < 256; i += S2H_THREADS) sB3[i] = gb3[i];
+  for (int i = threadIdx.x; i < 3 * 128; i += S2H_THREADS) sW1x[i] = gw1x[i];
+  {
+    const float* p = xyz + (size_t)b * N * stride;
+    for (int k = threadIdx.x; k < N; k += S2H_THREADS) {
+      px[k] = __ldg(p + (size_t)k * stride); py[k] = __ldg(p + (size_t)k * stride + 1); pz[k] = __ldg(p + (size_t)k * stride + 2);
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NWG; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemD = *tmem_slot + (uint32_t)g * 256;              // accumulator: 128 columns
+  const uint32_t tmemAh = tmemD + 128, tmemAl = tmemD + 192;           // operand hi / lo: 64 columns (128 bf16 per row) each
+  const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+  const uint32_t tlane = tmemD + lane_off;
+  const uint64_t dW2h = make_smem_desc(smem_u32(smem + S::w2h), 128, 16 * 128, LAYOUT_NONE);
+  const uint64_t dW2l = make_smem_desc(smem_u32(smem + S::w2l), 128, 16 * 128, LAYOUT_NONE);
+  const uint64_t dW3h = make_smem_desc(smem_u32(smem + S::w3h), 128, 16 * 128, LAYOUT_NONE);
+  const uint64_t dW3l = make_smem_desc(smem_u32(smem + S::w3l), 128, 16 * 128, LAYOUT_NONE);
+  constexpr uint32_t W3_TILE1 = (128 / 8) * 16 * 128 / 16;             // rows 128..255 of W3, in 16-byte units
+  constexpr uint32_t ID128 = make_idesc_bf16(128, 128);
+  uint64_t* bar = &bars[g];
+  uint32_t phase = 0;
+  bool ok = true;
+  const unsigned lt = (1u << lane) - 1u;
+  __shared__ int hcnt_s[S2X_NWG * 2 * 4];
+  int* hcnt = hcnt_s + g * 8;
+
+  // warps 0..3 of the chain: one centroid each, in-order scan of the 512 points (pointnet2 semantics, see sa2x3_tc_kernel)
+  auto bq_round = [&](int base, int slot) {
+    const int jc = base + wc;
+    if (wc < 4 && jc < NCENT) {
+      const float* cp = new_xyz + ((size_t)b * NCENT + jc) * 3;
+      const float qx = cp[0], qy = cp[1], qz = cp[2];
+      uint16_t* out = lists + (slot * 4 + wc) * 128;
+      int cnt = 0, first = 0;
+#pragma unroll 4
+      for (int k0 = 0; k0 < N; k0 += 32) {
+        const int k = k0 + lane;
+        const bool hit = dist2(qx, qy, qz, px[k], py[k], pz[k]) < r2;
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (cnt == 0 && hm) first = k0 + __ffs(hm) - 1;
+        const int pos = cnt + __popc(hm & lt);
+        if (hit && pos < NSAMPLE) out[pos] = (uint16_t)k;
+        cnt += __popc(hm);
+      }
+      for (int l = min(cnt, NSAMPLE) + lane; l < NSAMPLE; l += 32) out[l] = (uint16_t)first;
+      if (lane == 0) hcnt[slot * 4 + wc] = max(1, min(cnt, NSAMPLE));
+    }
+  };
+  auto issue = [&](uint64_t dWh, uint64_t dWl, uint32_t woff) {
+    if (wc == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) mma_bf16_ts(tmemD, tmemAl + ks * 8, dWh + (uint64_t)(woff + ks * 16), ID128, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) mma_bf16_ts(tmemD, tmemAh + ks * 8, dWl + (uint64_t)(woff + ks * 16), ID128, 1);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) mma_bf16_ts(tmemD, tmemAh + ks * 8, dWh + (uint64_t)(woff + ks * 16), ID128, 1);
+        mma_commit(bar);
+      }
+      __syncwarp();
+    }
+  };
+
+  constexpr int STEP = NWG * 4;
+  int r = 0, kpre = 0;
+  float4 xpre[8];                                      // channels [64 hh, 64 hh + 32) of the next tile's row
+  const int base0 = (g * split + part) * 4;
+  TilePack tp{0u, 0u, 0}, tpn{0u, 0u, 0};
+  int nvalid = 0, nvalid_n = 0, ntiles_done = 0;
+  auto open_round = [&](int nb, int nslot, TilePack& p, int& nv) {
+    nv = min(4, NCENT - nb);
+    p = pack_round(hcnt + nslot * 4, nv, pack);
+    if (ball_idx && u < 128)
+      for (int c = 0; c < nv; ++c) ball_idx[((size_t)b * NCENT + nb + c) * NSAMPLE + u] = lists[(nslot * 4 + c) * 128 + u];
+  };
+  auto prefetch = [&](const TilePack& p, int nv, int nslot, int ntile) {
+    const int mc = pack_owner(p, nv, ntile, wq);
+    kpre = lists[(nslot * 4 + mc) * 128 + (wq - pack_q0(p, mc)) * 32 + lane];
+    const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + kpre) * 128) + 16 * hh;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xpre[q] = __ldg(prow + q);
+  };
+  if (base0 < NCENT) { bq_round(base0, 0); chain_sync(g); open_round(base0, 0, tp, nvalid); prefetch(tp, nvalid, 0, 0); }
+  for (int base = base0; base < NCENT && ok; base += STEP * split, ++r) {
+    const int slot = r & 1;
+#pragma unroll 1
+    for (int tile = 0; tile < tp.ntiles && ok; ++tile) {
+      {   // W1x c of the centroid that owns each quarter of this tile: 4 x 128 values over the chain's 256 threads
+        const int ch = u & 127;
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int q = (u >> 7) * 2 + qq;
+          const float* cp = new_xyz + ((size_t)b * NCENT + base + pack_owner(tp, nvalid, tile, q)) * 3;
+          sU[q * 128 + ch] = fmaf(sW1x[256 + ch], cp[2], fmaf(sW1x[128 + ch], cp[1], sW1x[ch] * cp[0]));
+        }
+      }
+      chain_sync(g);
+      // ---- layer 1 (per-point pre-activation - centroid term), ReLU, split: this thread's 64 channels of its row
+      {
+        const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + kpre) * 128) + 16 * hh;
+        const float* uq = sU + wq * 128 + 64 * hh;
+        float4 xb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xb[q] = __ldg(prow + 8 + q);
+#pragma unroll
+        for (int part2 = 0; part2 < 2; ++part2) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 xv = part2 ? xb[q * 4 + i] : xpre[q * 4 + i];
+              const float4 uv = *reinterpret_cast<const float4*>(uq + part2 * 32 + q * 16 + i * 4);
+              split_relu_pack(xv.x - uv.x, xv.y - uv.y, hi[2 * i], lo[2 * i]);
+              split_relu_pack(xv.z - uv.z, xv.w - uv.w, hi[2 * i + 1], lo[2 * i + 1]);
+            }
+            tmem_st8(tmemAh + lane_off + 32 * hh + part2 * 16 + q * 8, hi);
+            tmem_st8(tmemAl + lane_off + 32 * hh + part2 * 16 + q * 8, lo);
+          }
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      chain_sync(g);
+      issue(dW2h, dW2l, 0);                                      // layer 2
+      ok = ok && mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 64 * hh; c0 < 64 * hh + 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tlane + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t hi[8], lo[8];
+          const float* bb = sB2 + c0 + q * 16;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            split_relu_pack(__uint_as_float(v[q * 16 + 2 * i]) + bb[2 * i], __uint_as_float(v[q * 16 + 2 * i + 1]) + bb[2 * i + 1], hi[i], lo[i]);
+          tmem_st8(tmemAh + lane_off + (c0 >> 1) + q * 8, hi);
+          tmem_st8(tmemAl + lane_off + (c0 >> 1) + q * 8, lo);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      chain_sync(g);
+      issue(dW3h, dW3l, 0);                                      // layer 3, channels 0..127
+      // under the layer-3 MMAs: the next round's ball query (when this was the round's last tile) and the next tile's rows
+      if (tile + 1 < tp.ntiles) {
+        prefetch(tp, nvalid, slot, tile + 1);
+      } else {
+        const int nb = base + STEP * split;
+        if (nb < NCENT) { bq_round(nb, slot ^ 1); chain_sync(g); open_round(nb, slot ^ 1, tpn, nvalid_n); prefetch(tpn, nvalid_n, slot ^ 1, 0); }
+      }
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        ok = ok && mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        // fp32 max over each warp's 32 rows x 64 columns: accumulator-fragment loads, in-thread max over a thread's 4 rows, halving
+        // butterfly over the warp's 8 row classes; the quarters of a centroid meet in shared memory
+        float* pl = sPool + half * 4 * 128;
+        {
+          float v[16];
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            uint32_t va[16], vb[16];
+            tmem_ld_16x256b_x4(tlane + 64 * hh + blk * 32, va);
+            tmem_ld_16x256b_x4(tlane + (16u << 16) + 64 * hh + blk * 32, vb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+              v[(blk * 4 + rep) * 2] = fmaxf(fmaxf(__uint_as_float(va[rep * 4]), __uint_as_float(va[rep * 4 + 2])),
+                                             fmaxf(__uint_as_float(vb[rep * 4]), __uint_as_float(vb[rep * 4 + 2])));
+              v[(blk * 4 + rep) * 2 + 1] = fmaxf(fmaxf(__uint_as_float(va[rep * 4 + 1]), __uint_as_float(va[rep * 4 + 3])),
+                                                 fmaxf(__uint_as_float(vb[rep * 4 + 1]), __uint_as_float(vb[rep * 4 + 3])));
+            }
+          }
+          rows_max_butterfly<16>(v, lane);
+          // entries i = 2 * (lane >> 2) + jj: column block i / 8, rep (i % 8) / 2, element i % 2 of the fragment layout
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int i = 2 * (lane >> 2) + jj;
+            pl[wq * 128 + 64 * hh + 32 * (i >> 3) + 8 * ((i & 7) >> 1) + 2 * (lane & 3) + (i & 1)] = v[jj];
+          }
+        }
+        tc_fence_before();
+        chain_sync(g);                                           // every lane of the accumulator has been read
+        if (half == 0) issue(dW3h, dW3l, W3_TILE1);              // channels 128..255 into the same TMEM columns
+        {
+          const int ch = u & 127;
+          for (int c = u >> 7; c < nvalid; c += 2) {             // centroids dealt to the chain's two thread halves
+            if (pack_tile(tp, c) != tile) continue;
+            const int q0 = pack_q0(tp, c), q1 = pack_q1(tp, nvalid, c);
+            float m = pl[q0 * 128 + ch];
+            for (int q = q0 + 1; q < q1; ++q) m = fmaxf(m, pl[q * 128 + ch]);
+            m = fmaxf(m + sB3[half * 128 + ch], 0.f);
+            __nv_bfloat16 h, l;
+            split_bf16(m, h, l);
+            __nv_bfloat16* o = out_rows + ((size_t)b * NCENT + base + c) * (2 * A3_KX);
+            o[half * 128 + ch] = h;
+            o[A3_KX + half * 128 + ch] = l;
+            if (out_f32) out_f32[((size_t)b * NCENT + base + c) * 256 + half * 128 + ch] = m;
+          }
+        }
+      }
+      for (int i = u; i < nvalid * 16; i += 256) {   // [x y z | 0-pad] columns of the tile's centroids
+        const int c = i >> 4, d = i & 15;
+        if (pack_tile(tp, c) != tile) continue;
+        const float v = d < 3 ? new_xyz[((size_t)b * NCENT + base + c) * 3 + d] : 0.f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        __nv_bfloat16* o = out_rows + ((size_t)b * NCENT + base + c) * (2 * A3_KX);
+        o[256 + d] = h;
+        o[A3_KX + 256 + d] = l;
+      }
+    }
+    ntiles_done += tp.ntiles;
+    tp = tpn;
+    nvalid = nvalid_n;
+  }
+  if (u == 0 && ntiles_done) atomicAdd(sa_tile_counter(err, 1), (unsigned long long)ntiles_done);
+  if (!ok && (threadIdx.x & 31) == 0) atomicExch(err, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
 // ---------------------------------------------------------------------------------------------- launchers
 static int launch_sa1x3(mpn_ctx* c, cudaStream_t s, const float* cloud, int N, const float* new_xyz, int B, __nv_bfloat16* out_rows,
                         float* out_f32, int32_t* ball_idx) {
@@ -875,8 +1150,16 @@ static int launch_sa2x3(mpn_ctx* c, cudaStream_t s, const float* xyz1, const flo
                         float* out_f32, int32_t* ball_idx) {
   X3Weights& w = g_x3[c];
   MPN_REQUIRE(w.ready, "bf16x3 weights not packed");
-  MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sa2xSmem::total));
   const int split = sa_split(c, B, 32 / S2X_NWG);
+  if (getenv("MPN_SA2X3_V1") == nullptr) {   // default: 8 warps per chain (A/B switch read per launch)
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2x3h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sa2xSmem::total));
+    sa2x3h_tc_kernel<<<B * split, S2H_THREADS, Sa2xSmem::total, s>>>(xyz1, 3, pre, xyz2, SA2_RADIUS * SA2_RADIUS, w.sa2_w2, w.sa2_w3, c->w.sa[1][1].b,
+                                                                     c->w.sa[1][2].b, w.sa2_w1x, out_rows, out_f32, tc_error_flag(c), ball_idx, split, sa_pack());
+    c->launches++;
+    MPN_CHECK_CUDA(cudaGetLastError());
+    return MPN_OK;
+  }
+  MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sa2xSmem::total));
   sa2x3_tc_kernel<<<B * split, S2X_THREADS, Sa2xSmem::total, s>>>(xyz1, 3, pre, xyz2, SA2_RADIUS * SA2_RADIUS, w.sa2_w2, w.sa2_w3, c->w.sa[1][1].b,
                                                                   c->w.sa[1][2].b, w.sa2_w1x, out_rows, out_f32, tc_error_flag(c), ball_idx, split, sa_pack());
   c->launches++;
