@@ -102,6 +102,9 @@ struct TrainWs {
   // per chunk
   float *X = nullptr, *H1 = nullptr, *H2 = nullptr;
   int32_t* src = nullptr; uint8_t* slot = nullptr;
+  // bf16 mode: the active rows of a chunk compacted over its groups (row -> group, group -> first row, per-group row masks / counts,
+  // rows[0] = active rows, rows[1] = padded to a multiple of 256)
+  int32_t *row_grp = nullptr, *grp_off = nullptr, *grp_cnt = nullptr; uint4* grp_mask = nullptr; int* rows = nullptr;
   float* partial = nullptr; size_t partial_floats = 0;   // split-reduction partials of the weight-gradient kernels
   __nv_bfloat16* tcw = nullptr; float* b2dup = nullptr;  // bf16 weight tiles of the tensor-core backward (rebuilt per step)
   // bf16 mode, dense layers on the TMA GEMM: operand copies of one layer at a time (activation / gradient, their transposes, W, W^T)
@@ -235,9 +238,9 @@ int refresh_transposes(mpn_ctx* c, cudaStream_t s);
 // ---- train_tc.cu : tcgen05 GEMMs over compacted rows (bf16 operands)
 int launch_rows_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
                         const __nv_bfloat16* mask, long long M, int N, __nv_bfloat16* C, float* pool_out = nullptr,
-                        uint8_t* pool_arg = nullptr, int paired = 0);
+                        uint8_t* pool_arg = nullptr, int paired = 0, const int* rows_dev = nullptr, int rows_shift = 0);
 int launch_wgrad_tc(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, const __nv_bfloat16* X, long long R, float* partial,
-                    size_t partial_floats, int* n_ctas, int swap_lbo_sbo = 0);
+                    size_t partial_floats, int* n_ctas, int swap_lbo_sbo = 0, const int* rows_dev = nullptr, int rows_shift = 0);
 void free_train_ws(mpn_ctx* c);
 
 }  // namespace mpn

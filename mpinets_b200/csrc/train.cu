@@ -258,6 +258,108 @@ __global__ void __launch_bounds__(256) sa_prepare_kernel(const uint8_t* __restri
   }
 }
 
+// ---- compacted active rows (bf16 mode).  A group of SA1 has ~7 active rows of its 64 slots and a group of SA2 ~25 of 128 (the rows
+// that won at least one channel of the max-pool and carry a non-zero gradient), so instead of a fixed slot range per group the active
+// rows of a chunk are laid out back to back: pass 1 counts them per group (and masks the pooled-output gradient), a single-CTA scan
+// turns the counts into first-row offsets, pass 2 writes, per row, the source point and the owning group.  The row count stays on the
+// device (rows[0]; rows[1] = padded to `pad` with empty rows): the GEMMs behind read it there, no host synchronisation.  Slots inside
+// a group keep their ascending-row order, so every sum runs in a fixed order (deterministic like the fixed-slot layout).
+template <int C3>
+__global__ void __launch_bounds__(256) sa_rows_count_kernel(const uint8_t* __restrict__ arg, float* __restrict__ g,
+                                                            const float* __restrict__ out, int G, uint4* __restrict__ masks,
+                                                            int32_t* __restrict__ cnt) {
+  __shared__ unsigned mask_s[8][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.x * 8 + warp;
+  if (grp >= G) return;
+  unsigned* mk = mask_s[warp];
+  if (lane < 4) mk[lane] = 0u;
+  __syncwarp();
+  const size_t gc = (size_t)grp * C3;
+  for (int ch = lane; ch < C3; ch += 32) {
+    const float gv = g[gc + ch];
+    const bool act = gv != 0.f && out[gc + ch] > 0.f;
+    if (!act) g[gc + ch] = 0.f;
+    else { const int r = arg[gc + ch] & 127; atomicOr(&mk[r >> 5], 1u << (r & 31)); }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    masks[grp] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+    cnt[grp] = __popc(mk[0]) + __popc(mk[1]) + __popc(mk[2]) + __popc(mk[3]);
+  }
+}
+
+__global__ void __launch_bounds__(1024) sa_rows_scan_kernel(const int32_t* __restrict__ cnt, int G, int32_t* __restrict__ off,
+                                                            int* __restrict__ rows, int32_t* __restrict__ src,
+                                                            int32_t* __restrict__ row_grp, int pad) {
+  __shared__ int wsum[32];
+  __shared__ int total_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (G + 1023) / 1024;
+  const int i0 = min(G, tid * per), i1 = min(G, i0 + per);
+  int sum = 0;
+  for (int i = i0; i < i1; ++i) sum += cnt[i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int v = wsum[lane];
+    int iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+    wsum[lane] = iv - v;
+    if (lane == 31) total_s = iv;
+  }
+  __syncthreads();
+  int run = wsum[warp] + incl - sum;
+  for (int i = i0; i < i1; ++i) { off[i] = run; run += cnt[i]; }
+  const int total = total_s, padded = (total + pad - 1) / pad * pad;
+  if (tid == 0) { off[G] = total; rows[0] = total; rows[1] = padded; }
+  for (int r = total + tid; r < padded; r += 1024) { src[r] = -1; row_grp[r] = -1; }
+}
+
+// the padding rows [rows[0], rows[1]) of dZ2 belong to no group, so the sparse layer-3 kernel never writes them: zero them here and every
+// product behind it (weight gradients, bias sums, dZ1, dX) may run over the padded count
+__global__ void __launch_bounds__(1024) zero_pad_rows_kernel(__nv_bfloat16* __restrict__ H, int C, const int* __restrict__ rows) {
+  const int r0 = rows[0], r1 = rows[1];
+  for (int i = threadIdx.x; i < (r1 - r0) * C; i += 1024) H[(size_t)r0 * C + i] = __float2bfloat16_rn(0.f);
+}
+
+template <int C3>
+__global__ void __launch_bounds__(256) sa_rows_fill_kernel(const uint8_t* __restrict__ arg, const float* __restrict__ g,
+                                                           const int32_t* __restrict__ ball, int G, const uint4* __restrict__ masks,
+                                                           const int32_t* __restrict__ off, uint8_t* __restrict__ slot_of_ch,
+                                                           int32_t* __restrict__ src, int32_t* __restrict__ row_grp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.x * 8 + warp;
+  if (grp >= G) return;
+  const uint4 mk = masks[grp];
+  const unsigned m0 = mk.x, m1 = mk.y, m2 = mk.z, m3 = mk.w;
+  const int b1 = __popc(m0), b2 = b1 + __popc(m1), b3 = b2 + __popc(m2);
+  auto slot_of_row = [&](int r) {
+    const int wd = r >> 5;
+    const unsigned w = wd == 0 ? m0 : wd == 1 ? m1 : wd == 2 ? m2 : m3;
+    const int base = wd == 0 ? 0 : wd == 1 ? b1 : wd == 2 ? b2 : b3;
+    return base + __popc(w & ((1u << (r & 31)) - 1u));
+  };
+  const int o = off[grp];
+#pragma unroll
+  for (int wd = 0; wd < 4; ++wd) {
+    const unsigned w = wd == 0 ? m0 : wd == 1 ? m1 : wd == 2 ? m2 : m3;
+    if ((w >> lane) & 1u) {
+      const int r = wd * 32 + lane;
+      const int row = o + slot_of_row(r);
+      src[row] = ball[(size_t)grp * NSAMPLE + r];
+      row_grp[row] = grp;
+    }
+  }
+  const size_t gc = (size_t)grp * C3;
+  for (int ch = lane; ch < C3; ch += 32)
+    slot_of_ch[gc + ch] = g[gc + ch] != 0.f ? (uint8_t)slot_of_row(arg[gc + ch] & 127) : (uint8_t)255;
+}
+
 // Group-all level with saved activations (bf16 mode): rows keep their natural order, so slot = pooled row and src = row.
 __global__ void __launch_bounds__(256) sa3_identity_prepare_kernel(const uint8_t* __restrict__ arg, float* __restrict__ g,
                                                                    const float* __restrict__ out, int G, uint8_t* __restrict__ slot_of_ch,
@@ -348,7 +450,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int C2, int C3, int SLOTS, typename T>
 __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict__ geff, const uint8_t* __restrict__ slot_of_ch,
                                                         const float* __restrict__ W3, T* __restrict__ H2, int G,
-                                                        float* __restrict__ pW, float* __restrict__ pb) {
+                                                        float* __restrict__ pW, float* __restrict__ pb,
+                                                        const int32_t* __restrict__ grp_off = nullptr) {
+  // grp_off != null: compacted rows -- group grp owns rows [grp_off[grp], grp_off[grp + 1]) of H2 instead of a fixed SLOTS range
   constexpr int NT = 512, Q = NT / C2, CPT = C3 / Q, PER = SLOTS / 32;
   constexpr int NBUF = sizeof(T) == 2 ? 2 : 1, CHUNKS = SLOTS * C2 * (int)sizeof(T) / 16, PARTS = NT / SLOTS, CPP = C3 / PARTS;
   static_assert(NT % C2 == 0 && C3 % Q == 0 && SLOTS % 32 == 0 && SLOTS <= 128 && C3 <= NT && NT % SLOTS == 0 && C3 % PARTS == 0, "layout");
@@ -367,9 +471,11 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
   float accb = 0.f;
   for (int i = tid; i < C3 * C2; i += NT) W3s[i] = W3[i];
   auto stage = [&](int grp, int buf) {
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(H2 + (size_t)grp * SLOTS * C2);
+    const size_t row0 = grp_off ? (size_t)grp_off[grp] : (size_t)grp * SLOTS;
+    const int chunks = grp_off ? (grp_off[grp + 1] - grp_off[grp]) * C2 * (int)sizeof(T) / 16 : CHUNKS;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(H2 + row0 * C2);
     uint8_t* dst = reinterpret_cast<uint8_t*>(Hbuf + (size_t)buf * SLOTS * C2);
-    for (int i = tid; i < CHUNKS; i += NT) cp_async16(dst + (size_t)i * 16, src + (size_t)i * 16);
+    for (int i = tid; i < chunks; i += NT) cp_async16(dst + (size_t)i * 16, src + (size_t)i * 16);
     cp_async_commit();
   };
   if (NBUF == 2 && (int)blockIdx.x < G) stage(blockIdx.x, 0);
@@ -382,7 +488,8 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
       gs[c] = geff[(size_t)grp * C3 + c];
       sl[c] = slot_of_ch[(size_t)grp * C3 + c];
     }
-    T* Hg = H2 + (size_t)grp * SLOTS * C2;
+    T* Hg = H2 + (grp_off ? (size_t)grp_off[grp] : (size_t)grp * SLOTS) * C2;
+    const int nrows = grp_off ? grp_off[grp + 1] - grp_off[grp] : SLOTS;
     if (NBUF == 2) {
       const int next = grp + gridDim.x;
       if (next < G) { stage(next, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
@@ -431,7 +538,7 @@ __global__ void __launch_bounds__(512) sa_l3_bwd_kernel(const float* __restrict_
     }
     __syncthreads();
     // dZ2[slot] = (sum over the slot's channels of g_c W3[c]) masked by ReLU
-    for (int s = q; s < SLOTS; s += Q) {
+    for (int s = q; s < nrows; s += Q) {
       float a = 0.f;
       const int e1 = start[s + 1];
       for (int e = start[s]; e < e1; ++e) {
@@ -546,15 +653,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Y
 // previous level's feature gradient: dfeat[b][src][f] += dX[row][f]   (pointnet2's group_points_grad)
 template <typename T>
 __global__ void __launch_bounds__(256) sa_scatter_add_kernel(const T* __restrict__ dX, const int32_t* __restrict__ src, long long R,
-                                                             int slots, int npoint, int N, int CF, float* __restrict__ dfeat) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * CF) return;
-  const long long row = i / CF;
-  const int f = (int)(i - row * CF);
-  const int si = src[row];
-  if (si < 0) return;
-  const long long b = (row / slots) / npoint;
-  atomicAdd(dfeat + ((size_t)b * N + si) * CF + f, ldf(dX + i));
+                                                             int slots, int npoint, int N, int CF, float* __restrict__ dfeat,
+                                                             const int32_t* __restrict__ row_grp = nullptr,
+                                                             const int* __restrict__ rows_dev = nullptr) {
+  if (rows_dev) R = *rows_dev;   // compacted rows: count on the device, group of a row from row_grp
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * CF; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / CF;
+    const int f = (int)(i - row * CF);
+    const int si = src[row];
+    if (si < 0) continue;
+    const long long b = (row_grp ? (long long)row_grp[row] : row / slots) / npoint;
+    atomicAdd(dfeat + ((size_t)b * N + si) * CF + f, ldf(dX + i));
+  }
 }
 
 
@@ -566,31 +676,34 @@ __global__ void __launch_bounds__(256) sa_scatter_add_kernel(const T* __restrict
 // bias gradient of layer 1
 __global__ void __launch_bounds__(256) sa2_gather_bf16_kernel(const int32_t* __restrict__ src, long long R, int slots, int npoint,
                                                               const float* __restrict__ xyz, int N, const float* __restrict__ feats,
-                                                              const float* __restrict__ new_xyz, __nv_bfloat16* __restrict__ X) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * 16) return;
-  const long long row = i >> 4;
-  const int ch = (int)(i & 15);
-  const long long grp = row / slots, b = grp / npoint;
-  const int si = src[row];
-  float v[8];
+                                                              const float* __restrict__ new_xyz, __nv_bfloat16* __restrict__ X,
+                                                              const int32_t* __restrict__ row_grp = nullptr,
+                                                              const int* __restrict__ rows_dev = nullptr) {
+  if (rows_dev) R = *rows_dev;   // compacted rows (padded count on the device), group of a row from row_grp
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * 16; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i >> 4;
+    const int ch = (int)(i & 15);
+    const int si = src[row];
+    const long long grp = si < 0 ? 0 : (row_grp ? (long long)row_grp[row] : row / slots), b = grp / npoint;
+    float v[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  if (si >= 0) {
-    const float* p = xyz + ((size_t)b * N + si) * 3;
-    const float* f = feats + ((size_t)b * N + si) * 64;
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (si >= 0) {
+      const float* p = xyz + ((size_t)b * N + si) * 3;
+      const float* f = feats + ((size_t)b * N + si) * 64;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = ch * 8 + j;
-      if (k < 3) v[j] = p[k] - new_xyz[(size_t)grp * 3 + k];
-      else if (k < 67) v[j] = f[k - 3];
-      else if (k == 127) v[j] = 1.0f;
+      for (int j = 0; j < 8; ++j) {
+        const int k = ch * 8 + j;
+        if (k < 3) v[j] = p[k] - new_xyz[(size_t)grp * 3 + k];
+        else if (k < 67) v[j] = f[k - 3];
+        else if (k == 127) v[j] = 1.0f;
+      }
     }
-  }
-  __nv_bfloat162 o[4];
+    __nv_bfloat162 o[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-  *reinterpret_cast<uint4*>(X + (size_t)row * 128 + ch * 8) = *reinterpret_cast<uint4*>(o);
+    for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(X + (size_t)row * 128 + ch * 8) = *reinterpret_cast<uint4*>(o);
+  }
 }
 
 // SA1: operand rows X4 fp32 [R][4] = [dx dy dz mask] and layer 1 (4 -> 64, K too small for a tensor-core tile) computed on
@@ -598,40 +711,45 @@ __global__ void __launch_bounds__(256) sa2_gather_bf16_kernel(const int32_t* __r
 __global__ void __launch_bounds__(256) sa1_gather_h1_kernel(const int32_t* __restrict__ src, long long R, int slots, int npoint,
                                                             const float* __restrict__ cloud, int N, const float* __restrict__ new_xyz,
                                                             const float* __restrict__ W1, const float* __restrict__ b1,
-                                                            float* __restrict__ X4, __nv_bfloat16* __restrict__ H1) {
+                                                            float* __restrict__ X4, __nv_bfloat16* __restrict__ H1,
+                                                            const int32_t* __restrict__ row_grp = nullptr,
+                                                            const int* __restrict__ rows_dev = nullptr) {
   __shared__ float w[4][72], bs[64];   // w[k][c], rows padded: the 8 channel-chunk threads of a row read distinct banks
   w[threadIdx.x & 3][threadIdx.x >> 2] = W1[threadIdx.x];
   if (threadIdx.x < 64) bs[threadIdx.x] = b1[threadIdx.x];
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * 8) return;
-  const long long row = i >> 3;
-  const int ch = (int)(i & 7);
-  const long long grp = row / slots, b = grp / npoint;
-  const int si = src[row];
-  float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-  if (si >= 0) {
-    const float4 p = *reinterpret_cast<const float4*>(cloud + ((size_t)b * N + si) * 4);
-    x0 = p.x - new_xyz[(size_t)grp * 3]; x1 = p.y - new_xyz[(size_t)grp * 3 + 1]; x2 = p.z - new_xyz[(size_t)grp * 3 + 2]; x3 = p.w;
-  }
-  if (ch == 0 && X4) *reinterpret_cast<float4*>(X4 + (size_t)row * 4) = make_float4(x0, x1, x2, x3);
-  float h[8];
+  if (rows_dev) R = *rows_dev;   // compacted rows (padded count on the device), group of a row from row_grp
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * 8; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i >> 3;
+    const int ch = (int)(i & 7);
+    const int si = src[row];
+    const long long grp = si < 0 ? 0 : (row_grp ? (long long)row_grp[row] : row / slots), b = grp / npoint;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+    if (si >= 0) {
+      const float4 p = *reinterpret_cast<const float4*>(cloud + ((size_t)b * N + si) * 4);
+      x0 = p.x - new_xyz[(size_t)grp * 3]; x1 = p.y - new_xyz[(size_t)grp * 3 + 1]; x2 = p.z - new_xyz[(size_t)grp * 3 + 2]; x3 = p.w;
+    }
+    if (ch == 0 && X4) *reinterpret_cast<float4*>(X4 + (size_t)row * 4) = make_float4(x0, x1, x2, x3);
+    float h[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = ch * 8 + j;
-    const float z = fmaf(w[3][c], x3, fmaf(w[2][c], x2, fmaf(w[1][c], x1, fmaf(w[0][c], x0, bs[c]))));
-    h[j] = si >= 0 ? fmaxf(z, 0.f) : 0.f;
-  }
-  __nv_bfloat162 o[4];
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch * 8 + j;
+      const float z = fmaf(w[3][c], x3, fmaf(w[2][c], x2, fmaf(w[1][c], x1, fmaf(w[0][c], x0, bs[c]))));
+      h[j] = si >= 0 ? fmaxf(z, 0.f) : 0.f;
+    }
+    __nv_bfloat162 o[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(h[2 * j], h[2 * j + 1]);
-  *reinterpret_cast<uint4*>(H1 + (size_t)row * 64 + ch * 8) = *reinterpret_cast<uint4*>(o);
+    for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(h[2 * j], h[2 * j + 1]);
+    *reinterpret_cast<uint4*>(H1 + (size_t)row * 64 + ch * 8) = *reinterpret_cast<uint4*>(o);
+  }
 }
 
 // column sums of Y bf16 [R][128] over a CTA's row range -> partial[cta][128]
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ Y, long long R, long long rows_per_cta,
-                                                          float* __restrict__ partial) {
+                                                          float* __restrict__ partial, const int* __restrict__ rows_dev = nullptr,
+                                                          int rows_shift = 0) {
   __shared__ float red[4][128];
+  if (rows_dev) { R = (long long)(*rows_dev >> rows_shift); rows_per_cta = (R + gridDim.x - 1) / gridDim.x; }
   const int cp = threadIdx.x & 63, rl = threadIdx.x >> 6;
   const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
   float s0 = 0.f, s1 = 0.f;
@@ -677,8 +795,10 @@ __global__ void bias_extract_kernel(const float* __restrict__ P, int n, int out,
 
 // SA1 layer 1 (64 x 4): partial[cta][64][5] = sums over the CTA's rows of dZ1[r][c] * [x0 x1 x2 x3 1]
 __global__ void __launch_bounds__(256) sa1_wgrad1_kernel(const __nv_bfloat16* __restrict__ dZ1, const float* __restrict__ X4, long long R,
-                                                         long long rows_per_cta, float* __restrict__ partial) {
+                                                         long long rows_per_cta, float* __restrict__ partial,
+                                                         const int* __restrict__ rows_dev = nullptr) {
   __shared__ float red[4][64][5];
+  if (rows_dev) { R = *rows_dev; rows_per_cta = (R + gridDim.x - 1) / gridDim.x; }
   const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
   const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
@@ -810,7 +930,8 @@ void free_train_ws(mpn_ctx* c) {
                    (void**)&t.f[1], (void**)&t.f[2], (void**)&t.f[3], (void**)&t.d[0], (void**)&t.d[1], (void**)&t.d[2],
                    (void**)&t.yhat, (void**)&t.gy, (void**)&t.ga, (void**)&t.gb, (void**)&t.gcat, (void**)&t.gfeat3, (void**)&t.gfeat2,
                    (void**)&t.gfeat1, (void**)&t.X, (void**)&t.H1, (void**)&t.H2, (void**)&t.src, (void**)&t.slot, (void**)&t.partial,
-                   (void**)&t.tcw, (void**)&t.b2dup,
+                   (void**)&t.tcw, (void**)&t.b2dup, (void**)&t.row_grp, (void**)&t.grp_off, (void**)&t.grp_cnt, (void**)&t.grp_mask,
+                   (void**)&t.rows,
                    (void**)&t.adam_m, (void**)&t.adam_v, (void**)&t.norm};
   for (auto p : ptrs)
     if (*p) { cudaFree(*p); *p = nullptr; }
@@ -856,6 +977,11 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
   r |= talloc(&t.H2, k * SA2_NPOINT * 128 * 128);
   r |= talloc(&t.src, k * SA1_NPOINT * 64);
   r |= talloc(&t.slot, k * SA1_NPOINT * 64);
+  r |= talloc(&t.row_grp, k * SA1_NPOINT * 64);
+  r |= talloc(&t.grp_off, k * SA1_NPOINT + 1);
+  r |= talloc(&t.grp_cnt, k * SA1_NPOINT);
+  r |= talloc(&t.grp_mask, k * SA1_NPOINT);
+  r |= talloc(&t.rows, (size_t)4);
   r |= talloc(&t.tcw, (size_t)8 * 128 * 128 + 512 * 512 + 256 * 512);   // + transposed bf16 tiles of SA3 layers 2 / 1 (data gradients)
   r |= talloc(&t.b2dup, (size_t)256 + 512);                              // + 512 zeros (bias of the data-gradient GEMMs)
   if (!r) cudaMemset(t.b2dup, 0, (256 + 512) * sizeof(float));
@@ -1061,7 +1187,7 @@ static int dense_backward(mpn_ctx* c, cudaStream_t s, const Linear& L, float* gr
 
 template <int C2, int C3, int SLOTS, typename T>
 static int launch_sa_l3(mpn_ctx* c, cudaStream_t s, const float* geff, const uint8_t* slot, const Linear& L3, T* H2, int G,
-                        float* grads) {
+                        float* grads, const int32_t* grp_off = nullptr) {
   TrainWs& t = c->tw;
   auto k = sa_l3_bwd_kernel<C2, C3, SLOTS, T>;
   const size_t smem = (size_t)(C3 * C2 + C3) * 4 + (size_t)(sizeof(T) == 2 ? 2 : 1) * SLOTS * C2 * sizeof(T) + (size_t)(C3 + 512 + SLOTS + 1 + C3) * 4 + 16;
@@ -1072,7 +1198,7 @@ static int launch_sa_l3(mpn_ctx* c, cudaStream_t s, const float* geff, const uin
   grid = (int)std::min<size_t>(grid, t.partial_floats / per);
   float* pW = t.partial;
   float* pb = pW + (size_t)grid * C3 * C2;
-  k<<<grid, 512, smem, s>>>(geff, slot, L3.w, H2, G, pW, pb);
+  k<<<grid, 512, smem, s>>>(geff, slot, L3.w, H2, G, pW, pb, grp_off);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   int r;
@@ -1215,10 +1341,10 @@ int pack_w(mpn_ctx* c, cudaStream_t s, const float* src, int rows, int cols, int
 
 // dY^T X on tcgen05 -> gW (and the bias gradient from `bias_col` of the product, when >= 0)
 static int wgrad_tc_into(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, const __nv_bfloat16* X, long long R, int out, int in,
-                         int paired, float* gW, int bias_col, float* gb) {
+                         int paired, float* gW, int bias_col, float* gb, const int* rows_dev = nullptr, int rows_shift = 0) {
   TrainWs& t = c->tw;
   int n = 0, r;
-  if ((r = launch_wgrad_tc(c, s, dY, X, R, t.partial, t.partial_floats, &n))) return r;
+  if ((r = launch_wgrad_tc(c, s, dY, X, R, t.partial, t.partial_floats, &n, 0, rows_dev, rows_shift))) return r;
   const int total = out * in + (bias_col >= 0 ? out : 0);
   wgrad_extract_kernel<<<(total + 255) / 256, 256, 0, s>>>(t.partial, n, out, in, paired, gW, bias_col, gb);
   c->launches++;
@@ -1226,12 +1352,13 @@ static int wgrad_tc_into(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, co
   return MPN_OK;
 }
 
-static int colsum_bf16_into(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* Y, long long R, int out, int paired, float* gb) {
+static int colsum_bf16_into(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* Y, long long R, int out, int paired, float* gb,
+                            const int* rows_dev = nullptr, int rows_shift = 0) {
   TrainWs& t = c->tw;
   long long ctas = std::max(1LL, std::min<long long>(4LL * c->sm_count, (R + 255) / 256));
   long long rpc = (R + ctas - 1) / ctas;
   ctas = (R + rpc - 1) / rpc;
-  colsum_bf16_kernel<<<(unsigned)ctas, 256, 0, s>>>(Y, R, rpc, t.partial);
+  colsum_bf16_kernel<<<(unsigned)ctas, 256, 0, s>>>(Y, R, rpc, t.partial, rows_dev, rows_shift);
   bias_extract_kernel<<<1, 128, 0, s>>>(t.partial, (int)ctas, out, paired, gb);
   c->launches += 2;
   MPN_CHECK_CUDA(cudaGetLastError());
@@ -1245,7 +1372,7 @@ static int sa_backward_chunk_tc(mpn_ctx* c, cudaStream_t s, int m, int b0, int b
   const Linear* L = c->w.sa[m];
   const int npoint = m == 0 ? SA1_NPOINT : SA2_NPOINT, slots = m == 0 ? 64 : 128, C3 = L[2].out;
   const int G = bc * npoint;
-  const long long R = (long long)G * slots;
+  const long long R = (long long)G * slots;   // capacity: every slot of every group (the fixed-slot layout; grid sizing otherwise)
   int r;
   const float* xyz_c = xyz + (size_t)b0 * N_in * stride;
   const float* feats_c = feats + (size_t)b0 * N_in * fstride;
@@ -1261,32 +1388,50 @@ static int sa_backward_chunk_tc(mpn_ctx* c, cudaStream_t s, int m, int b0, int b
   __nv_bfloat16* Wb = t.tcw + 128 * 128;     // layer-2 weight transposed [128][128]
   __nv_bfloat16* Wc = t.tcw + 2 * 128 * 128; // SA2: layer-1 weight, K padded to 128
   __nv_bfloat16* Wd = t.tcw + 3 * 128 * 128; // SA2: feature columns of layer 1, transposed [64][128]
+  // active rows compacted over the chunk's groups (default) or one fixed slot range per group (MPN_TRAIN_NOCOMPACT=1, the A/B reference)
+  const bool compact = getenv("MPN_TRAIN_NOCOMPACT") == nullptr;
+  const int32_t* row_grp = compact ? t.row_grp : nullptr;
+  const int32_t* grp_off = compact ? t.grp_off : nullptr;
+  const int* rows_exact = compact ? t.rows : nullptr;       // active rows
+  const int* rows_pad = compact ? t.rows + 1 : nullptr;     // ... padded with empty rows to a multiple of 256
   {
     const int grid = (G + 7) / 8;
-    if (m == 0) sa_prepare_kernel<64, 64><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
-    else sa_prepare_kernel<256, 128><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
-    c->launches++;
+    if (compact) {
+      if (m == 0) sa_rows_count_kernel<64><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, G, t.grp_mask, t.grp_cnt);
+      else sa_rows_count_kernel<256><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, G, t.grp_mask, t.grp_cnt);
+      sa_rows_scan_kernel<<<1, 1024, 0, s>>>(t.grp_cnt, G, t.grp_off, t.rows, t.src, t.row_grp, 256);
+      if (m == 0) sa_rows_fill_kernel<64><<<grid, 256, 0, s>>>(arg_c, g_c, ball_c, G, t.grp_mask, t.grp_off, t.slot, t.src, t.row_grp);
+      else sa_rows_fill_kernel<256><<<grid, 256, 0, s>>>(arg_c, g_c, ball_c, G, t.grp_mask, t.grp_off, t.slot, t.src, t.row_grp);
+      c->launches += 3;
+    } else {
+      if (m == 0) sa_prepare_kernel<64, 64><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
+      else sa_prepare_kernel<256, 128><<<grid, 256, 0, s>>>(arg_c, g_c, out_c, ball_c, G, t.slot, t.src);
+      c->launches++;
+    }
     MPN_CHECK_CUDA(cudaGetLastError());
   }
+  const unsigned stride_grid = (unsigned)(8 * c->sm_count);   // grid-stride kernels over a row count that lives on the device
   if (m == 1) {
     if ((r = pack_w(c, s, L[1].w, 128, 128, 128, 0, 128, Wa))) return r;
     if ((r = pack_w(c, s, L[1].wt, 128, 128, 128, 0, 128, Wb))) return r;
     if ((r = pack_w(c, s, L[0].w, 128, 67, 67, 0, 128, Wc))) return r;
     if ((r = pack_w(c, s, L[0].wt + (size_t)3 * 128, 64, 128, 128, 0, 64, Wd))) return r;
-    sa2_gather_bf16_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, N_in, feats_c, nx_c, Xb);
+    sa2_gather_bf16_kernel<<<compact ? stride_grid : (unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, N_in, feats_c, nx_c,
+                                                                                                    Xb, row_grp, rows_pad);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
-    if ((r = launch_rows_gemm_tc(c, s, 0, Xb, Wc, L[0].b, nullptr, R, 128, H1b))) return r;
-    if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, L[1].b, nullptr, R, 128, H2b))) return r;
-    if ((r = launch_sa_l3<128, 256, 128, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads))) return r;
-    if ((r = wgrad_tc_into(c, s, H2b, H1b, R, 128, 128, 0, gw(c, grads, L[1]), -1, nullptr))) return r;
-    if ((r = colsum_bf16_into(c, s, H2b, R, 128, 0, gbias(c, grads, L[1])))) return r;
-    if ((r = launch_rows_gemm_tc(c, s, 2, H2b, Wb, nullptr, H1b, R, 128, H1b))) return r;              // dZ1 over H1
-    if ((r = wgrad_tc_into(c, s, H1b, Xb, R, 128, 67, 0, gw(c, grads, L[0]), 127, gbias(c, grads, L[0])))) return r;
-    if ((r = launch_rows_gemm_tc(c, s, 1, H1b, Wd, nullptr, nullptr, R, 64, H2b))) return r;            // dX features [R][64]
+    if ((r = launch_rows_gemm_tc(c, s, 0, Xb, Wc, L[0].b, nullptr, R, 128, H1b, nullptr, nullptr, 0, rows_pad, 0))) return r;
+    if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, L[1].b, nullptr, R, 128, H2b, nullptr, nullptr, 0, rows_pad, 0))) return r;
+    if ((r = launch_sa_l3<128, 256, 128, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads, grp_off))) return r;
+    if (compact) { zero_pad_rows_kernel<<<1, 1024, 0, s>>>(H2b, 128, t.rows); c->launches++; }
+    if ((r = wgrad_tc_into(c, s, H2b, H1b, R, 128, 128, 0, gw(c, grads, L[1]), -1, nullptr, rows_exact, 0))) return r;
+    if ((r = colsum_bf16_into(c, s, H2b, R, 128, 0, gbias(c, grads, L[1]), rows_exact, 0))) return r;
+    if ((r = launch_rows_gemm_tc(c, s, 2, H2b, Wb, nullptr, H1b, R, 128, H1b, nullptr, nullptr, 0, rows_pad, 0))) return r;   // dZ1 over H1
+    if ((r = wgrad_tc_into(c, s, H1b, Xb, R, 128, 67, 0, gw(c, grads, L[0]), 127, gbias(c, grads, L[0]), rows_exact, 0))) return r;
+    if ((r = launch_rows_gemm_tc(c, s, 1, H1b, Wd, nullptr, nullptr, R, 64, H2b, nullptr, nullptr, 0, rows_pad, 0))) return r;  // dX features [R][64]
     const long long n = R * 64;
-    sa_scatter_add_kernel<__nv_bfloat16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(H2b, t.src, R, slots, npoint, SA1_NPOINT, 64,
-                                                                                    dfeat_prev + (size_t)b0 * SA1_NPOINT * 64);
+    sa_scatter_add_kernel<__nv_bfloat16><<<compact ? stride_grid : (unsigned)((n + 255) / 256), 256, 0, s>>>(
+        H2b, t.src, R, slots, npoint, SA1_NPOINT, 64, dfeat_prev + (size_t)b0 * SA1_NPOINT * 64, row_grp, rows_exact);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
   } else {
@@ -1295,19 +1440,21 @@ static int sa_backward_chunk_tc(mpn_ctx* c, cudaStream_t s, int m, int b0, int b
     MPN_CHECK_CUDA(cudaMemcpyAsync(t.b2dup, L[1].b, 64 * 4, cudaMemcpyDeviceToDevice, s));
     MPN_CHECK_CUDA(cudaMemcpyAsync(t.b2dup + 64, L[1].b, 64 * 4, cudaMemcpyDeviceToDevice, s));
     float* X4 = t.X;
-    sa1_gather_h1_kernel<<<(unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, N_in, nx_c, L[0].w, L[0].b, X4, H1b);
+    sa1_gather_h1_kernel<<<compact ? stride_grid : (unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(t.src, R, slots, npoint, xyz_c, N_in, nx_c, L[0].w,
+                                                                                                 L[0].b, X4, H1b, row_grp, rows_pad);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     const long long R2 = R / 2;                                                                          // rows in pairs: [R/2][128]
-    if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, t.b2dup, nullptr, R2, 128, H2b))) return r;
-    if ((r = launch_sa_l3<64, 64, 64, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads))) return r;
-    if ((r = wgrad_tc_into(c, s, H2b, H1b, R2, 64, 64, 1, gw(c, grads, L[1]), -1, nullptr))) return r;
-    if ((r = colsum_bf16_into(c, s, H2b, R2, 64, 1, gbias(c, grads, L[1])))) return r;
-    if ((r = launch_rows_gemm_tc(c, s, 2, H2b, Wb, nullptr, H1b, R2, 128, H1b))) return r;             // dZ1 over H1
+    if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, t.b2dup, nullptr, R2, 128, H2b, nullptr, nullptr, 0, rows_pad, 1))) return r;
+    if ((r = launch_sa_l3<64, 64, 64, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads, grp_off))) return r;
+    if (compact) { zero_pad_rows_kernel<<<1, 1024, 0, s>>>(H2b, 64, t.rows); c->launches++; }
+    if ((r = wgrad_tc_into(c, s, H2b, H1b, R2, 64, 64, 1, gw(c, grads, L[1]), -1, nullptr, rows_pad, 1))) return r;
+    if ((r = colsum_bf16_into(c, s, H2b, R2, 64, 1, gbias(c, grads, L[1]), rows_pad, 1))) return r;
+    if ((r = launch_rows_gemm_tc(c, s, 2, H2b, Wb, nullptr, H1b, R2, 128, H1b, nullptr, nullptr, 0, rows_pad, 1))) return r;  // dZ1 over H1
     long long ctas = std::max(1LL, std::min<long long>(4LL * c->sm_count, (R + 1023) / 1024));
     long long rpc = (R + ctas - 1) / ctas;
     ctas = (R + rpc - 1) / rpc;
-    sa1_wgrad1_kernel<<<(unsigned)ctas, 256, 0, s>>>(H1b, X4, R, rpc, t.partial);
+    sa1_wgrad1_kernel<<<(unsigned)ctas, 256, 0, s>>>(H1b, X4, R, rpc, t.partial, rows_pad);
     sa1_w1_extract_kernel<<<2, 256, 0, s>>>(t.partial, (int)ctas, gw(c, grads, L[0]), gbias(c, grads, L[0]));
     c->launches += 2;
     MPN_CHECK_CUDA(cudaGetLastError());

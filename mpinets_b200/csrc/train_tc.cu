@@ -50,8 +50,9 @@ template <int N, int EPI>
 __global__ void __launch_bounds__(128 * RowsCfg<N>::NWG, 1)
 rows_gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias,
                     const __nv_bfloat16* mask, long long ntiles, __nv_bfloat16* C, float* __restrict__ pool_out,
-                    uint8_t* __restrict__ pool_arg, int paired, int* __restrict__ err) {
+                    uint8_t* __restrict__ pool_arg, int paired, int* __restrict__ err, const int* __restrict__ rows_dev, int rows_shift) {
   using Cfg = RowsCfg<N>;
+  if (rows_dev) ntiles = (long long)((*rows_dev >> rows_shift) / 128);   // row count decided on the device (compacted active rows, train.cu)
   constexpr int NWG = Cfg::NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
@@ -209,8 +210,12 @@ __device__ __forceinline__ uint32_t mnmajor_chunk_off(int r, int c) { return (ui
 
 __global__ void __launch_bounds__(256, 2)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ X, long long R, long long rows_per_cta,
-                float* __restrict__ partial, int swap_lbo_sbo, int* __restrict__ err) {
+                float* __restrict__ partial, int swap_lbo_sbo, int* __restrict__ err, const int* __restrict__ rows_dev, int rows_shift) {
   extern __shared__ __align__(1024) uint8_t smem[];           // [2 stages][dY tile | X tile]
+  if (rows_dev) {   // row count decided on the device: the launch's CTAs share the rows evenly, in whole stages
+    R = (long long)(*rows_dev >> rows_shift);
+    rows_per_cta = ((R + gridDim.x - 1) / gridDim.x + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+  }
   __shared__ uint64_t empty[2], accum;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = tid & 31;
@@ -295,10 +300,11 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __res
 
 }  // namespace
 
-// C[M][N] (bf16) = epi(A[M][128] W[N][128]^T + bias); M % 128 == 0; epi: 0 relu, 1 plain, 2 multiply by relu'(mask[M][N])
+// C[M][N] (bf16) = epi(A[M][128] W[N][128]^T + bias); M % 128 == 0; epi: 0 relu, 1 plain, 2 multiply by relu'(mask[M][N]).
+// rows_dev != null: M is only the capacity (grid sizing); the kernel processes (*rows_dev >> rows_shift) / 128 tiles
 int launch_rows_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias,
                         const __nv_bfloat16* mask, long long M, int N, __nv_bfloat16* C, float* pool_out, uint8_t* pool_arg,
-                        int paired) {
+                        int paired, const int* rows_dev, int rows_shift) {
   MPN_REQUIRE(M % 128 == 0 && (N == 64 || N == 128 || N == 256), "rows_gemm_tc: M %% 128 == 0 and N in {64,128,256} required");
   MPN_REQUIRE(epi != EPI_MASK || mask, "rows_gemm_tc: mask epilogue without a mask");
   MPN_REQUIRE(epi != EPI_POOL || (pool_out && pool_arg && (paired ? N == 128 : N >= 128)), "rows_gemm_tc: bad pool arguments");
@@ -312,7 +318,7 @@ int launch_rows_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16
     MPN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
     const long long want = (ntiles + RowsCfg<NN>::NWG - 1) / RowsCfg<NN>::NWG;                                           \
     const int grid = (int)std::min<long long>(want, c->sm_count);                                                        \
-    k<<<grid, 128 * RowsCfg<NN>::NWG, smem, s>>>(A, W, bias, mask, ntiles, C, pool_out, pool_arg, paired, errf);         \
+    k<<<grid, 128 * RowsCfg<NN>::NWG, smem, s>>>(A, W, bias, mask, ntiles, C, pool_out, pool_arg, paired, errf, rows_dev, rows_shift); \
   } while (0)
 #define ROWS_EPI(NN)                                       \
   do {                                                     \
@@ -333,14 +339,14 @@ int launch_rows_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16
 
 // partial[ctas][128][128] (fp32) = per-CTA sums of dY[r][:]^T X[r][:] over the CTA's row range; returns the CTA count
 int launch_wgrad_tc(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, const __nv_bfloat16* X, long long R, float* partial,
-                    size_t partial_floats, int* n_ctas, int swap_lbo_sbo) {
+                    size_t partial_floats, int* n_ctas, int swap_lbo_sbo, const int* rows_dev, int rows_shift) {
   long long ctas = std::min<long long>(2LL * c->sm_count, (R + 4 * WG_ROWS - 1) / (4 * WG_ROWS));
   ctas = std::max(1LL, std::min<long long>(ctas, (long long)(partial_floats / (128 * 128))));
   long long rows_per_cta = ((R + ctas - 1) / ctas + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
   ctas = std::max(1LL, (R + rows_per_cta - 1) / rows_per_cta);
   const size_t smem = (size_t)2 * 2 * WG_TILE;
   MPN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  wgrad_tc_kernel<<<(unsigned)ctas, 256, smem, s>>>(dY, X, R, rows_per_cta, partial, swap_lbo_sbo, tc_error_flag(c));
+  wgrad_tc_kernel<<<(unsigned)ctas, 256, smem, s>>>(dY, X, R, rows_per_cta, partial, swap_lbo_sbo, tc_error_flag(c), rows_dev, rows_shift);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   *n_ctas = (int)ctas;

@@ -288,3 +288,35 @@ def test_train_step_grads_bf16_mode_at_batch_64(engine_w, oracle, tables):
     os.makedirs("gpurun_out", exist_ok=True)
     open(os.path.join("gpurun_out", "train_grads_bf16_b64.txt"), "w").write("\n".join(lines) + "\n")
     assert not bad, "bf16-mode gradients (B = 64) vs the fp32 mode:\n" + "\n".join(bad)
+
+
+@pytest.mark.parametrize("chunk", [256, 24])
+def test_train_step_compacted_rows_equal_fixed_slots(engine_w, oracle, tables, chunk):
+    """bf16 training mode: the set-abstraction backward over the chunk's ACTIVE rows laid out back to back (device-side count, scan and
+    fill; the default) against the fixed 64 / 128 slots per group it replaces (MPN_TRAIN_NOCOMPACT=1).  Same rows, same per-row
+    arithmetic and the same order inside every group -- only the association of the fp32 partial sums of the weight gradients differs
+    (other CTA boundaries), so the two agree to fp32 summation noise.  chunk = 24 splits the 64 samples into 24 + 24 + 16."""
+    from mpinets_b200 import _lib
+    B = 64
+    p, cloud, qn, sup = _batch(oracle, tables, B, seed=9)
+    args = (to_dev(p), torch.from_numpy(cloud).cuda(), torch.from_numpy(qn).cuda(), torch.from_numpy(sup).cuda())
+    os.environ["MPN_TRAIN_CHUNK"] = str(chunk)
+    try:
+        la, ya, ga = engine_w.train_step_grads(*args, precision=_lib.PREC_BF16)
+        ga = ga.clone()
+        os.environ["MPN_TRAIN_NOCOMPACT"] = "1"
+        lb, yb, gb = engine_w.train_step_grads(*args, precision=_lib.PREC_BF16)
+        gb = gb.clone()
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("MPN_TRAIN_NOCOMPACT", None)
+        os.environ.pop("MPN_TRAIN_CHUNK", None)
+    assert not engine_w.tc_error()
+    assert torch.equal(la, lb) and torch.equal(ya, yb)
+    a, b = engine_w.unflatten(ga), engine_w.unflatten(gb)
+    worst = 0.0
+    for k in b:
+        rel = float((a[k] - b[k]).abs().max() / max(float(b[k].abs().max()), 1e-30))
+        worst = max(worst, rel)
+        assert rel < 2e-4, f"{k}: compacted vs fixed-slot gradient differs by {rel:.2e} of its max"
+    print(f"compacted rows vs fixed slots, chunk {chunk}: worst per-tensor max-norm difference {worst:.2e}")
