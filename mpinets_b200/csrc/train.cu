@@ -292,39 +292,89 @@ __global__ void __launch_bounds__(256) sa_rows_count_kernel(const uint8_t* __res
 __global__ void __launch_bounds__(1024) sa_rows_scan_kernel(const int32_t* __restrict__ cnt, int G, int32_t* __restrict__ off,
                                                             int* __restrict__ rows, int32_t* __restrict__ src,
                                                             int32_t* __restrict__ row_grp, int pad) {
-  __shared__ int wsum[32];
+  // one CTA, warp w owns the contiguous segment [w seg, (w + 1) seg): coalesced 32-wide loads, a first pass for the warp totals, a
+  // second one for the running offsets (the counts of a chunk stay in L2 between the passes)
+  __shared__ int wtot[32];
   __shared__ int total_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (G + 1023) / 1024;
-  const int i0 = min(G, tid * per), i1 = min(G, i0 + per);
+  const int seg = ((G + 31) / 32 + 31) / 32 * 32;
+  const int s0 = min(G, warp * seg), s1 = min(G, s0 + seg);
   int sum = 0;
-  for (int i = i0; i < i1; ++i) sum += cnt[i];
-  int incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  if (lane == 31) wsum[warp] = incl;
+#pragma unroll 4
+  for (int i = s0 + lane; i < s1; i += 32) sum += cnt[i];
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  if (lane == 0) wtot[warp] = sum;
   __syncthreads();
   if (warp == 0) {
-    const int v = wsum[lane];
+    const int v = wtot[lane];
     int iv = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
-    wsum[lane] = iv - v;
+    wtot[lane] = iv - v;
     if (lane == 31) total_s = iv;
   }
   __syncthreads();
-  int run = wsum[warp] + incl - sum;
-  for (int i = i0; i < i1; ++i) { off[i] = run; run += cnt[i]; }
+  int carry = wtot[warp];
+#pragma unroll 2
+  for (int i0 = s0; i0 < s1; i0 += 32) {
+    const int i = i0 + lane;
+    const int v = i < s1 ? cnt[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (i < s1) off[i] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
   const int total = total_s, padded = (total + pad - 1) / pad * pad;
   if (tid == 0) { off[G] = total; rows[0] = total; rows[1] = padded; }
   for (int r = total + tid; r < padded; r += 1024) { src[r] = -1; row_grp[r] = -1; }
 }
 
-// the padding rows [rows[0], rows[1]) of dZ2 belong to no group, so the sparse layer-3 kernel never writes them: zero them here and every
-// product behind it (weight gradients, bias sums, dZ1, dX) may run over the padded count
-__global__ void __launch_bounds__(1024) zero_pad_rows_kernel(__nv_bfloat16* __restrict__ H, int C, const int* __restrict__ rows) {
-  const int r0 = rows[0], r1 = rows[1];
-  for (int i = threadIdx.x; i < (r1 - r0) * C; i += 1024) H[(size_t)r0 * C + i] = __float2bfloat16_rn(0.f);
+// ---- layer 3 of a grouped level on the tensor cores (bf16 mode, compacted rows).  The gradient of the pooled output reaches, per
+// channel, ONE row of its group; written out as a matrix dY3 [rows][C3] (bf16, zero elsewhere) it is an ordinary operand:
+//   dW3 = dY3^T H2 (wgrad_tc_kernel),  db3 = column sums,  dZ2 = (dY3 W3) * relu'(H2) (rows_gemm_tc_kernel).
+// With the rows compacted dY3 is small (SA1 ~1 M rows x 64, SA2 ~0.8 M rows x 256 per chunk of 256 samples) and the three products cost
+// a fraction of the per-group list building of sa_l3_bwd_kernel (which stays for the fp32 mode and the fixed-slot layout).
+__global__ void __launch_bounds__(256) zero_rows_kernel(uint4* __restrict__ p, int chunks_per_row, const int* __restrict__ rows_dev) {
+  const long long n = (long long)(*rows_dev) * chunks_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+// dY3[grp_off[grp] + slot_of_ch][ch] = g[grp][ch]; C3 = 64: one matrix [rows][64]; C3 = 256: two matrices [rows][128] (channel halves)
+template <int C3>
+__global__ void __launch_bounds__(256) sa_dy3_scatter_kernel(const float* __restrict__ g, const uint8_t* __restrict__ slot_of_ch,
+                                                             const int32_t* __restrict__ grp_off, long long n, __nv_bfloat16* __restrict__ da,
+                                                             __nv_bfloat16* __restrict__ db) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int sl = slot_of_ch[i];
+    if (sl == 255) continue;
+    const long long grp = i / C3;
+    const int ch = (int)(i - grp * C3);
+    const size_t row = (size_t)grp_off[grp] + sl;
+    const __nv_bfloat16 v = __float2bfloat16_rn(g[i]);
+    if (C3 == 64) da[row * 64 + ch] = v;
+    else if (ch < 128) da[row * 128 + ch] = v;
+    else db[row * 128 + ch - 128] = v;
+  }
+}
+// H2 <- (T1 + T2) * relu'(H2), rows [0, *rows_dev) x 128 bf16
+__global__ void __launch_bounds__(256) add_mask_rows_kernel(const uint4* __restrict__ t1, const uint4* __restrict__ t2, uint4* __restrict__ h2,
+                                                            const int* __restrict__ rows_dev) {
+  const long long n = (long long)(*rows_dev) * 16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = t1[i], b = t2[i], m = h2[i];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, mw[4] = {m.x, m.y, m.z, m.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = __uint_as_float(aw[k] << 16) + __uint_as_float(bw[k] << 16);
+      const float hi = __uint_as_float(aw[k] & 0xFFFF0000u) + __uint_as_float(bw[k] & 0xFFFF0000u);
+      const bool mlo = (mw[k] & 0x7FFFu) != 0u && (mw[k] & 0x8000u) == 0u, mhi = (mw[k] & 0x7FFF0000u) != 0u && (mw[k] & 0x80000000u) == 0u;
+      __nv_bfloat162 v = __floats2bfloat162_rn(mlo ? lo : 0.f, mhi ? hi : 0.f);
+      o[k] = *reinterpret_cast<uint32_t*>(&v);
+    }
+    h2[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 template <int C3>
@@ -982,7 +1032,7 @@ static int ensure_train_ws(mpn_ctx* c, int B, int N) {
   r |= talloc(&t.grp_cnt, k * SA1_NPOINT);
   r |= talloc(&t.grp_mask, k * SA1_NPOINT);
   r |= talloc(&t.rows, (size_t)4);
-  r |= talloc(&t.tcw, (size_t)8 * 128 * 128 + 512 * 512 + 256 * 512);   // + transposed bf16 tiles of SA3 layers 2 / 1 (data gradients)
+  r |= talloc(&t.tcw, (size_t)8 * 128 * 128 + 512 * 512 + 256 * 512 + 2 * 128 * 128);   // + transposed bf16 tiles of SA3 layers 2 / 1 (data gradients)
   r |= talloc(&t.b2dup, (size_t)256 + 512);                              // + 512 zeros (bias of the data-gradient GEMMs)
   if (!r) cudaMemset(t.b2dup, 0, (256 + 512) * sizeof(float));
   r |= talloc(&t.dx, b * 4096); r |= talloc(&t.dgy, b * 4096); r |= talloc(&t.dgyT, b * 4096); r |= talloc(&t.daT, b * 4096);
@@ -1388,6 +1438,11 @@ static int sa_backward_chunk_tc(mpn_ctx* c, cudaStream_t s, int m, int b0, int b
   __nv_bfloat16* Wb = t.tcw + 128 * 128;     // layer-2 weight transposed [128][128]
   __nv_bfloat16* Wc = t.tcw + 2 * 128 * 128; // SA2: layer-1 weight, K padded to 128
   __nv_bfloat16* Wd = t.tcw + 3 * 128 * 128; // SA2: feature columns of layer 1, transposed [64][128]
+  __nv_bfloat16* We = t.tcw + (size_t)8 * 128 * 128 + 512 * 512 + 256 * 512;   // layer-3 weight transposed (SA2: two 128-channel halves)
+  // dY3 (see sa_dy3_scatter_kernel) lives in the upper halves of the H1 / H2 allocations: they are sized for fp32 rows, the bf16 rows of
+  // this path fill the lower halves even when every slot of every group is active
+  __nv_bfloat16* dYa = H1b + (size_t)R * (m == 0 ? 64 : 128);
+  __nv_bfloat16* dYb = H2b + (size_t)R * 128;
   // active rows compacted over the chunk's groups (default) or one fixed slot range per group (MPN_TRAIN_NOCOMPACT=1, the A/B reference)
   const bool compact = getenv("MPN_TRAIN_NOCOMPACT") == nullptr;
   const int32_t* row_grp = compact ? t.row_grp : nullptr;
@@ -1422,8 +1477,25 @@ static int sa_backward_chunk_tc(mpn_ctx* c, cudaStream_t s, int m, int b0, int b
     MPN_CHECK_CUDA(cudaGetLastError());
     if ((r = launch_rows_gemm_tc(c, s, 0, Xb, Wc, L[0].b, nullptr, R, 128, H1b, nullptr, nullptr, 0, rows_pad, 0))) return r;
     if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, L[1].b, nullptr, R, 128, H2b, nullptr, nullptr, 0, rows_pad, 0))) return r;
-    if ((r = launch_sa_l3<128, 256, 128, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads, grp_off))) return r;
-    if (compact) { zero_pad_rows_kernel<<<1, 1024, 0, s>>>(H2b, 128, t.rows); c->launches++; }
+    if (compact) {   // layer 3 as dense products over the compacted rows (see sa_dy3_scatter_kernel)
+      zero_rows_kernel<<<stride_grid, 256, 0, s>>>(reinterpret_cast<uint4*>(dYa), 16, rows_pad);
+      zero_rows_kernel<<<stride_grid, 256, 0, s>>>(reinterpret_cast<uint4*>(dYb), 16, rows_pad);
+      sa_dy3_scatter_kernel<256><<<stride_grid, 256, 0, s>>>(g_c, t.slot, t.grp_off, (long long)G * 256, dYa, dYb);
+      c->launches += 3;
+      MPN_CHECK_CUDA(cudaGetLastError());
+      if ((r = pack_w(c, s, L[2].wt, 128, 128, 256, 0, 128, We))) return r;                        // W3^T [j][c], c = 0..127
+      if ((r = pack_w(c, s, L[2].wt + 128, 128, 128, 256, 0, 128, We + 128 * 128))) return r;      // c = 128..255
+      if ((r = wgrad_tc_into(c, s, dYa, H2b, R, 128, 128, 0, gw(c, grads, L[2]), -1, nullptr, rows_pad, 0))) return r;
+      if ((r = wgrad_tc_into(c, s, dYb, H2b, R, 128, 128, 0, gw(c, grads, L[2]) + 128 * 128, -1, nullptr, rows_pad, 0))) return r;
+      if ((r = colsum_bf16_into(c, s, dYa, R, 128, 0, gbias(c, grads, L[2]), rows_pad, 0))) return r;
+      if ((r = colsum_bf16_into(c, s, dYb, R, 128, 0, gbias(c, grads, L[2]) + 128, rows_pad, 0))) return r;
+      if ((r = launch_rows_gemm_tc(c, s, 1, dYa, We, nullptr, nullptr, R, 128, dYa, nullptr, nullptr, 0, rows_pad, 0))) return r;              // T1 in place
+      if ((r = launch_rows_gemm_tc(c, s, 1, dYb, We + 128 * 128, nullptr, nullptr, R, 128, dYb, nullptr, nullptr, 0, rows_pad, 0))) return r;  // T2 in place
+      add_mask_rows_kernel<<<stride_grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(dYa), reinterpret_cast<const uint4*>(dYb),
+                                                       reinterpret_cast<uint4*>(H2b), rows_pad);                                            // dZ2 over H2
+      c->launches++;
+      MPN_CHECK_CUDA(cudaGetLastError());
+    } else if ((r = launch_sa_l3<128, 256, 128, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads, grp_off))) return r;
     if ((r = wgrad_tc_into(c, s, H2b, H1b, R, 128, 128, 0, gw(c, grads, L[1]), -1, nullptr, rows_exact, 0))) return r;
     if ((r = colsum_bf16_into(c, s, H2b, R, 128, 0, gbias(c, grads, L[1]), rows_exact, 0))) return r;
     if ((r = launch_rows_gemm_tc(c, s, 2, H2b, Wb, nullptr, H1b, R, 128, H1b, nullptr, nullptr, 0, rows_pad, 0))) return r;   // dZ1 over H1
@@ -1446,8 +1518,16 @@ static int sa_backward_chunk_tc(mpn_ctx* c, cudaStream_t s, int m, int b0, int b
     MPN_CHECK_CUDA(cudaGetLastError());
     const long long R2 = R / 2;                                                                          // rows in pairs: [R/2][128]
     if ((r = launch_rows_gemm_tc(c, s, 0, H1b, Wa, t.b2dup, nullptr, R2, 128, H2b, nullptr, nullptr, 0, rows_pad, 1))) return r;
-    if ((r = launch_sa_l3<64, 64, 64, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads, grp_off))) return r;
-    if (compact) { zero_pad_rows_kernel<<<1, 1024, 0, s>>>(H2b, 64, t.rows); c->launches++; }
+    if (compact) {   // layer 3 as dense products over the compacted rows, two 64-wide rows per 128-wide GEMM row
+      zero_rows_kernel<<<stride_grid, 256, 0, s>>>(reinterpret_cast<uint4*>(dYa), 8, rows_pad);
+      sa_dy3_scatter_kernel<64><<<stride_grid, 256, 0, s>>>(g_c, t.slot, t.grp_off, (long long)G * 64, dYa, nullptr);
+      c->launches += 2;
+      MPN_CHECK_CUDA(cudaGetLastError());
+      if ((r = pack_w(c, s, L[2].wt, 64, 64, 64, 1, 128, We))) return r;                            // diag(W3^T, W3^T)
+      if ((r = wgrad_tc_into(c, s, dYa, H2b, R2, 64, 64, 1, gw(c, grads, L[2]), -1, nullptr, rows_pad, 1))) return r;
+      if ((r = colsum_bf16_into(c, s, dYa, R2, 64, 1, gbias(c, grads, L[2]), rows_pad, 1))) return r;
+      if ((r = launch_rows_gemm_tc(c, s, 2, dYa, We, nullptr, H2b, R2, 128, H2b, nullptr, nullptr, 0, rows_pad, 1))) return r;   // dZ2 over H2
+    } else if ((r = launch_sa_l3<64, 64, 64, __nv_bfloat16>(c, s, g_c, t.slot, L[2], H2b, G, grads, grp_off))) return r;
     if ((r = wgrad_tc_into(c, s, H2b, H1b, R2, 64, 64, 1, gw(c, grads, L[1]), -1, nullptr, rows_pad, 1))) return r;
     if ((r = colsum_bf16_into(c, s, H2b, R2, 64, 1, gbias(c, grads, L[1]), rows_pad, 1))) return r;
     if ((r = launch_rows_gemm_tc(c, s, 2, H2b, Wb, nullptr, H1b, R2, 128, H1b, nullptr, nullptr, 0, rows_pad, 1))) return r;  // dZ1 over H1

@@ -293,9 +293,10 @@ def test_train_step_grads_bf16_mode_at_batch_64(engine_w, oracle, tables):
 @pytest.mark.parametrize("chunk", [256, 24])
 def test_train_step_compacted_rows_equal_fixed_slots(engine_w, oracle, tables, chunk):
     """bf16 training mode: the set-abstraction backward over the chunk's ACTIVE rows laid out back to back (device-side count, scan and
-    fill; the default) against the fixed 64 / 128 slots per group it replaces (MPN_TRAIN_NOCOMPACT=1).  Same rows, same per-row
-    arithmetic and the same order inside every group -- only the association of the fp32 partial sums of the weight gradients differs
-    (other CTA boundaries), so the two agree to fp32 summation noise.  chunk = 24 splits the 64 samples into 24 + 24 + 16."""
+    fill; layer 3 as dense tcgen05 products against the scattered pooled-output gradient -- the default) against the path it replaces
+    (MPN_TRAIN_NOCOMPACT=1: fixed 64 / 128 slots per group, sparse fp32 layer-3 kernel).  Same rows, same routing; the differences are
+    the association of the fp32 partial sums and the bf16 rounding of layer 3's operands (pooled-output gradient and W3, 2^-9 each) in
+    the dense products.  Measured: <= 5e-3 of a tensor's largest entry, cosine 1 - 1e-6.  chunk = 24 splits the 64 samples 24 + 24 + 16."""
     from mpinets_b200 import _lib
     B = 64
     p, cloud, qn, sup = _batch(oracle, tables, B, seed=9)
@@ -314,9 +315,11 @@ def test_train_step_compacted_rows_equal_fixed_slots(engine_w, oracle, tables, c
     assert not engine_w.tc_error()
     assert torch.equal(la, lb) and torch.equal(ya, yb)
     a, b = engine_w.unflatten(ga), engine_w.unflatten(gb)
-    worst = 0.0
+    worst, worst_cos = 0.0, 1.0
     for k in b:
-        rel = float((a[k] - b[k]).abs().max() / max(float(b[k].abs().max()), 1e-30))
-        worst = max(worst, rel)
-        assert rel < 2e-4, f"{k}: compacted vs fixed-slot gradient differs by {rel:.2e} of its max"
-    print(f"compacted rows vs fixed slots, chunk {chunk}: worst per-tensor max-norm difference {worst:.2e}")
+        x, y = a[k].double().flatten(), b[k].double().flatten()
+        rel = float((x - y).abs().max() / max(float(y.abs().max()), 1e-30))
+        cos = float((x * y).sum() / max(float(x.norm() * y.norm()), 1e-300))
+        worst, worst_cos = max(worst, rel), min(worst_cos, cos)
+        assert rel < 2e-2 and cos > 0.9999, f"{k}: compacted vs fixed-slot gradient: max-norm difference {rel:.2e}, cosine {cos:.6f}"
+    print(f"compacted rows vs fixed slots, chunk {chunk}: worst per-tensor max-norm difference {worst:.2e}, worst cosine {worst_cos:.7f}")
