@@ -113,6 +113,7 @@ struct TrainWs {
   float* adam_m = nullptr; float* adam_v = nullptr; float* norm = nullptr;
   // bf16 mode: hidden activations of the group-all level saved by the forward GEMMs, [B*128][512] each (null in the fp32 mode)
   const __nv_bfloat16 *sa3_h1 = nullptr, *sa3_h2 = nullptr;
+  const __nv_bfloat16* sa3_a3 = nullptr;   // ... and its operand rows [B*128][272] = [256 SA2 features | x y z | 0-pad] (SA2's output rows)
 };
 
 }  // namespace mpn
@@ -241,6 +242,8 @@ int launch_rows_gemm_tc(mpn_ctx* c, cudaStream_t s, int epi, const __nv_bfloat16
                         uint8_t* pool_arg = nullptr, int paired = 0, const int* rows_dev = nullptr, int rows_shift = 0);
 int launch_wgrad_tc(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, const __nv_bfloat16* X, long long R, float* partial,
                     size_t partial_floats, int* n_ctas, int swap_lbo_sbo = 0, const int* rows_dev = nullptr, int rows_shift = 0);
+int launch_wgrad_tc2d(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, int ldy, int y_cols, const __nv_bfloat16* X, int ldx, int x_cols,
+                      long long R, float* partial, size_t partial_floats, int* n_ctas);
 void free_train_ws(mpn_ctx* c);
 
 }  // namespace mpn

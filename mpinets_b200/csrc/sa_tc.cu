@@ -1253,6 +1253,7 @@ int tc_train_forward_sa(mpn_ctx* c, cudaStream_t s, const float* cloud, int B, i
   MPN_CHECK_CUDA(cudaGetLastError());
   c->tw.sa3_h1 = h1;   // the SA3 backward reads them instead of recomputing layers 1-2
   c->tw.sa3_h2 = h2;
+  c->tw.sa3_a3 = a3;
   return MPN_OK;
 }
 

@@ -700,6 +700,55 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Y
   }
 }
 
+// column sums over many rows: grid (column blocks of 32, row splits) -> partial[split][N], summed in split order by colsum_finish_kernel
+__global__ void __launch_bounds__(256) colsum_split_kernel(const float* __restrict__ Y, int ld, int M, int N, int rows_per_split,
+                                                           float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const int m0 = blockIdx.y * rows_per_split, m1 = min(M, m0 + rows_per_split);
+  float s0 = 0.f, s1 = 0.f;
+  if (col < N) {
+    int m = m0 + rl;
+    for (; m + 8 < m1; m += 16) { s0 += Y[(size_t)m * ld + col]; s1 += Y[(size_t)(m + 8) * ld + col]; }
+    if (m < m1) s0 += Y[(size_t)m * ld + col];
+  }
+  red[rl][threadIdx.x & 31] = s0 + s1;
+  __syncthreads();
+  if (rl == 0 && col < N) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tsum += red[i][threadIdx.x];
+    partial[(size_t)blockIdx.y * N + col] = tsum;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int splits, int N, float* __restrict__ dst) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < splits; ++i) s += partial[(size_t)i * N + col];
+  dst[col] += s;
+}
+// dst[col] += sum over the M rows of Y[:, col]; deterministic (fixed split, ordered finish).  Uses the tail of the partial buffer so that
+// it can follow a weight-gradient launch whose partials are still being reduced on the stream.
+static int colsum_into(mpn_ctx* c, cudaStream_t s, const float* Y, int ld, int M, int N, float* dst) {
+  TrainWs& t = c->tw;
+  if (M <= 512) {
+    colsum_kernel<<<(N + 31) / 32, 256, 0, s>>>(Y, ld, M, N, dst);
+    c->launches++;
+  } else {
+    int splits = std::min(64, (M + 255) / 256);
+    const int rps = (M + splits - 1) / splits;
+    splits = (M + rps - 1) / rps;
+    float* p = t.partial + t.partial_floats - (size_t)64 * 4096;
+    MPN_REQUIRE(N <= 4096, "colsum_into: at most 4096 columns");
+    colsum_split_kernel<<<dim3((N + 31) / 32, splits), 256, 0, s>>>(Y, ld, M, N, rps, p);
+    colsum_finish_kernel<<<(N + 255) / 256, 256, 0, s>>>(p, splits, N, dst);
+    c->launches += 2;
+  }
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+
 // previous level's feature gradient: dfeat[b][src][f] += dX[row][f]   (pointnet2's group_points_grad)
 template <typename T>
 __global__ void __launch_bounds__(256) sa_scatter_add_kernel(const T* __restrict__ dX, const int32_t* __restrict__ src, long long R,
@@ -832,15 +881,20 @@ __global__ void wgrad_extract_kernel(const float* __restrict__ P, int n, int out
     gb[o] += s;
   }
 }
-__global__ void bias_extract_kernel(const float* __restrict__ P, int n, int out, int paired, float* __restrict__ gb) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= out) return;
+// one CTA of 1024 threads = 8 partial lanes x 128 columns; lanes summed in order (deterministic)
+__global__ void __launch_bounds__(1024) bias_extract_kernel(const float* __restrict__ P, int n, int out, int paired, float* __restrict__ gb) {
+  __shared__ float red[8][128];
+  const int o = threadIdx.x & 127, rl = threadIdx.x >> 7;
   float s = 0.f;
-  for (int sp = 0; sp < n; ++sp) {
-    s += P[(size_t)sp * 128 + o];
-    if (paired) s += P[(size_t)sp * 128 + o + 64];
+  for (int sp = rl; sp < n; sp += 8) s += P[(size_t)sp * 128 + o];
+  red[rl][o] = s;
+  __syncthreads();
+  if (rl == 0 && o < out) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tsum += red[i][o] + (paired ? red[i][o + 64] : 0.f);
+    gb[o] += tsum;
   }
-  gb[o] += s;
 }
 
 // SA1 layer 1 (64 x 4): partial[cta][64][5] = sums over the CTA's rows of dZ1[r][c] * [x0 x1 x2 x3 1]
@@ -1103,7 +1157,7 @@ static int dense_backward_tc(mpn_ctx* c, cudaStream_t s, const Linear& L, float*
   if ((r = narrow_transpose(c, s, gY, ldgy, M, L.out, t.dgyT))) return r;         // [out][M]
   if ((r = narrow_transpose(c, s, a_in, lda, M, L.in, t.daT))) return r;          // [in][M]
   if ((r = launch_gemm_tc_ex(c, s, 1, t.dgyT, M, 0, t.daT, M, 0, M, t.zeros, L.out, L.in, gw(c, grads, L), L.in, 0, 0, nullptr))) return r;
-  colsum_kernel<<<(L.out + 31) / 32, 256, 0, s>>>(gY, ldgy, M, L.out, gbias(c, grads, L));
+  { int rr = colsum_into(c, s, gY, ldgy, M, L.out, gbias(c, grads, L)); if (rr) return rr; }
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   if (!gX) return MPN_OK;
@@ -1194,7 +1248,7 @@ static int train_forward(mpn_ctx* c, cudaStream_t s, const float* cloud, const f
   const Weights& W = c->w;
   const int CAT = ENC_DIM + QF_DIM;
   int r;
-  t.sa3_h1 = t.sa3_h2 = nullptr;
+  t.sa3_h1 = t.sa3_h2 = t.sa3_a3 = nullptr;
   if (tcp) {
     if ((r = train_forward_sa_tc(c, s, cloud, B, N))) return r;
   } else {
@@ -1254,6 +1308,30 @@ static int launch_sa_l3(mpn_ctx* c, cudaStream_t s, const float* geff, const uin
   int r;
   if ((r = reduce_partials(c, s, pW, grid, (long long)C3 * C2, gw(c, grads, L3), 1))) return r;
   return reduce_partials(c, s, pb, grid, C3, gbias(c, grads, L3), 1);
+}
+
+// gW[o][k] += sum over the row CTAs of partial[(o / 128) * nx + col / 128][cta][o % 128][col % 128], col = the operand column that holds
+// input k: k itself, or (rot > 0) the rotated order [features.. | x y z] of the SA2 output rows: k < 3 -> rot + k, else k - 3
+__global__ void wgrad_extract2d_kernel(const float* __restrict__ P, int n, int nx, int out, int in, int rot, float* __restrict__ gW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out * in) return;
+  const int o = i / in, k = i - o * in;
+  const int col = rot > 0 ? (k < 3 ? rot + k : k - 3) : k;
+  const float* p = P + ((size_t)((o >> 7) * nx + (col >> 7)) * n * 128 + (o & 127)) * 128 + (col & 127);
+  float sum = 0.f;
+  for (int sp = 0; sp < n; ++sp) sum += p[(size_t)sp * 128 * 128];
+  gW[i] += sum;
+}
+// weight gradient of a wide layer on tcgen05: gW [out][in] += dY[R][out]^T X[R][..] (bf16 operands, fp32 accumulation and partials)
+static int wgrad_tc2d_into(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, int ldy, int out, const __nv_bfloat16* X, int ldx, int x_cols,
+                           long long R, int in, int rot, float* gW) {
+  TrainWs& t = c->tw;
+  int n = 0, r;
+  if ((r = launch_wgrad_tc2d(c, s, dY, ldy, out, X, ldx, x_cols, R, t.partial, t.partial_floats, &n))) return r;
+  wgrad_extract2d_kernel<<<(out * in + 255) / 256, 256, 0, s>>>(t.partial, n, (x_cols + 127) / 128, out, in, rot, gW);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
 }
 
 // module m backward over samples [b0, b0 + bc): g = d loss / d pooled output [bc][npoint][C3] (masked in place)
@@ -1327,7 +1405,8 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
     MPN_CHECK_CUDA(cudaGetLastError());
   }
   // 4. layer 2: gW2 += dZ2^T H1 ; dZ1 = (dZ2 W2) * relu'(H1), in place over H1
-  if ((r = wgrad(c, s, t.H2, C2, t.H1, C1, R, C2, C1, gw(c, grads, L[1]), gbias(c, grads, L[1])))) return r;
+  const bool wtc = saved && t.sa3_a3 && R >= 512 && getenv("MPN_TRAIN_SA3_SIMT_WGRAD") == nullptr;   // group-all level, bf16 mode: on tcgen05
+  if (!wtc && (r = wgrad(c, s, t.H2, C2, t.H1, C1, R, C2, C1, gw(c, grads, L[1]), gbias(c, grads, L[1])))) return r;
   // bf16 mode, group-all level: the two data-gradient GEMMs (R x 512 x 512, R x 256 x 512) run on the TMA / tcgen05 GEMM with
   // transposed bf16 weight tiles; the saved activations' slots in the forward scratch hold the bf16 operands
   __nv_bfloat16* w2t = t.tcw + 8 * 128 * 128;
@@ -1344,6 +1423,10 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
     narrow_bf16_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, s>>>(t.H2, n, dz_bf);
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
+    if (wtc) {   // gW2 = dZ2^T H1 on the saved bf16 activations (16 tile pairs x row CTAs), gb2 = column sums of the fp32 dZ2
+      if ((r = wgrad_tc2d_into(c, s, dz_bf, 512, 512, t.sa3_h1 + (size_t)b0 * SA2_NPOINT * 512, 512, 512, R, 512, 0, gw(c, grads, L[1])))) return r;
+      if ((r = colsum_into(c, s, t.H2, 512, (int)R, 512, gbias(c, grads, L[1])))) return r;
+    }
     if ((r = launch_gemm_tc(c, s, 1, dz_bf, 512, w2t, 512, zero_bias, (int)R, 512, t.H2, 512))) return r;   // dZ2 W2 -> H2 (fp32)
     relu_mask_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(t.H1, t.H2, n);                            // dZ1 over H1
     c->launches++;
@@ -1352,7 +1435,7 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
     if ((r = launch_linear_ex(c, s, t.H2, C2, L[1].wt, C2, nullptr, R, C1, C2, t.H1, C1, 0, t.H1, C1, 2))) return r;
   }
   //    layer 1: gW1 += dZ1^T X
-  if ((r = wgrad(c, s, t.H1, C1, t.X, CINP[m], R, C1, CIN, gw(c, grads, L[0]), gbias(c, grads, L[0])))) return r;
+  if (!wtc && (r = wgrad(c, s, t.H1, C1, t.X, CINP[m], R, C1, CIN, gw(c, grads, L[0]), gbias(c, grads, L[0])))) return r;
   // 5. feature part of dX = dZ1 W1[:, 3:]  ->  previous level's feature gradient
   if (m == 2) {
     float* dst = dfeat_prev + (size_t)b0 * SA2_NPOINT * 256;   // group-all: rows are the SA2 centroids themselves
@@ -1363,6 +1446,10 @@ static int sa_backward_chunk(mpn_ctx* c, cudaStream_t s, int m, int b0, int bc, 
       narrow_bf16_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, s>>>(t.H1, n, dz1_bf);
       c->launches++;
       MPN_CHECK_CUDA(cudaGetLastError());
+      if (wtc) {   // gW1 = dZ1^T X against SA2's bf16 output rows [256 features | x y z | pad] (column order rotated back on extraction)
+        if ((r = wgrad_tc2d_into(c, s, dz1_bf, 512, 512, t.sa3_a3 + (size_t)b0 * SA2_NPOINT * 272, 272, 272, R, CIN, 256, gw(c, grads, L[0])))) return r;
+        if ((r = colsum_into(c, s, t.H1, 512, (int)R, 512, gbias(c, grads, L[0])))) return r;
+      }
       if ((r = launch_gemm_tc(c, s, 1, dz1_bf, 512, w1t, 512, zero_bias, (int)R, 256, t.H2, 256))) return r;
     } else if ((r = launch_linear_ex(c, s, t.H1, C1, L[0].wt + (size_t)3 * C1, C1, nullptr, R, CFEAT[m], C1, t.H2, CFEAT[m], 0))) return r;
     const long long n = R * CFEAT[m];
@@ -1409,7 +1496,7 @@ static int colsum_bf16_into(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* Y, 
   long long rpc = (R + ctas - 1) / ctas;
   ctas = (R + rpc - 1) / rpc;
   colsum_bf16_kernel<<<(unsigned)ctas, 256, 0, s>>>(Y, R, rpc, t.partial, rows_dev, rows_shift);
-  bias_extract_kernel<<<1, 128, 0, s>>>(t.partial, (int)ctas, out, paired, gb);
+  bias_extract_kernel<<<1, 1024, 0, s>>>(t.partial, (int)ctas, out, paired, gb);
   c->launches += 2;
   MPN_CHECK_CUDA(cudaGetLastError());
   return MPN_OK;

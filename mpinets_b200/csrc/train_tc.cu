@@ -210,8 +210,15 @@ __device__ __forceinline__ uint32_t mnmajor_chunk_off(int r, int c) { return (ui
 
 __global__ void __launch_bounds__(256, 2)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ X, long long R, long long rows_per_cta,
-                float* __restrict__ partial, int swap_lbo_sbo, int* __restrict__ err, const int* __restrict__ rows_dev, int rows_shift) {
+                float* __restrict__ partial, int swap_lbo_sbo, int* __restrict__ err, const int* __restrict__ rows_dev, int rows_shift,
+                int ldy, int ldx, int nx_tiles, int x_cols) {
+  // blockIdx.y = (ty, tx): the 128 x 128 tile dY[:, 128 ty ..]^T X[:, 128 tx ..] of a wider product (row pitches ldy / ldx elements,
+  // X columns >= x_cols read as zero); the plain 128-wide call has ldy = ldx = x_cols = 128 and one tile
   extern __shared__ __align__(1024) uint8_t smem[];           // [2 stages][dY tile | X tile]
+  const int ty = blockIdx.y / nx_tiles, tx = blockIdx.y - ty * nx_tiles;
+  dY += (size_t)ty * 128;
+  X += (size_t)tx * 128;
+  const int x_chunks = max(0, min(16, (x_cols - tx * 128) / 8));   // valid 8-column chunks of this X tile
   if (rows_dev) {   // row count decided on the device: the launch's CTAs share the rows evenly, in whole stages
     R = (long long)(*rows_dev >> rows_shift);
     rows_per_cta = ((R + gridDim.x - 1) / gridDim.x + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
@@ -246,8 +253,8 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __res
     for (int u = 0; u < 4; ++u) {
       const int r = warp * 8 + (lane & 7), c = u * 4 + (lane >> 3);
       const bool in = r0 + r < r_end;
-      vy[u] = in ? __ldg(reinterpret_cast<const uint4*>(dY + (size_t)(r0 + r) * 128) + c) : make_uint4(0u, 0u, 0u, 0u);
-      vx[u] = in ? __ldg(reinterpret_cast<const uint4*>(X + (size_t)(r0 + r) * 128) + c) : make_uint4(0u, 0u, 0u, 0u);
+      vy[u] = in ? __ldg(reinterpret_cast<const uint4*>(dY + (size_t)(r0 + r) * ldy) + c) : make_uint4(0u, 0u, 0u, 0u);
+      vx[u] = (in && c < x_chunks) ? __ldg(reinterpret_cast<const uint4*>(X + (size_t)(r0 + r) * ldx) + c) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -277,7 +284,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __res
   }
   if (!ok && lane == 0) atomicExch(err, 1);
   if (warp < 4) {
-    float* prow = partial + ((size_t)blockIdx.x * 128 + tid) * 128;
+    float* prow = partial + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + tid) * 128;
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
       uint32_t a[32];
@@ -346,7 +353,28 @@ int launch_wgrad_tc(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, const _
   ctas = std::max(1LL, (R + rows_per_cta - 1) / rows_per_cta);
   const size_t smem = (size_t)2 * 2 * WG_TILE;
   MPN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  wgrad_tc_kernel<<<(unsigned)ctas, 256, smem, s>>>(dY, X, R, rows_per_cta, partial, swap_lbo_sbo, tc_error_flag(c), rows_dev, rows_shift);
+  wgrad_tc_kernel<<<(unsigned)ctas, 256, smem, s>>>(dY, X, R, rows_per_cta, partial, swap_lbo_sbo, tc_error_flag(c), rows_dev, rows_shift,
+                                                    128, 128, 1, 128);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  *n_ctas = (int)ctas;
+  return MPN_OK;
+}
+
+// wide product: partial[ty * nx + tx][cta][128][128] = per-CTA sums of dY[r][128 ty ..]^T X[r][128 tx ..] over the CTA's rows; dY [R][ldy]
+// with y_cols (multiple of 128) columns used, X [R][ldx] with x_cols (multiple of 8) columns used.  Returns the row-CTA count.
+int launch_wgrad_tc2d(mpn_ctx* c, cudaStream_t s, const __nv_bfloat16* dY, int ldy, int y_cols, const __nv_bfloat16* X, int ldx, int x_cols,
+                      long long R, float* partial, size_t partial_floats, int* n_ctas) {
+  MPN_REQUIRE(y_cols % 128 == 0 && x_cols % 8 == 0 && ldy % 8 == 0 && ldx % 8 == 0 && R >= 1, "wgrad_tc2d: bad shapes");
+  const int ny = y_cols / 128, nx = (x_cols + 127) / 128;
+  long long ctas = std::max(1LL, std::min<long long>(R / (8 * WG_ROWS), (2LL * c->sm_count + ny * nx - 1) / (ny * nx)));
+  ctas = std::max(1LL, std::min<long long>(ctas, (long long)(partial_floats / ((size_t)128 * 128 * ny * nx))));
+  long long rows_per_cta = ((R + ctas - 1) / ctas + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+  ctas = std::max(1LL, (R + rows_per_cta - 1) / rows_per_cta);
+  const size_t smem = (size_t)2 * 2 * WG_TILE;
+  MPN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  wgrad_tc_kernel<<<dim3((unsigned)ctas, (unsigned)(ny * nx)), 256, smem, s>>>(dY, X, R, rows_per_cta, partial, 0, tc_error_flag(c), nullptr, 0, ldy,
+                                                                              ldx, nx, x_cols);
   c->launches++;
   MPN_CHECK_CUDA(cudaGetLastError());
   *n_ctas = (int)ctas;
