@@ -469,7 +469,12 @@ def run_training(args, world, rank, local):
                 "roofline": {"kernel": "whole training step", "bound": "tensor", "achieved": flop / (t[0] / K / 1000.0) / 1e12,
                              "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": flop / (t[0] / K / 1000.0) / 1e12 / peaks["bf16_sustained"],
                              "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
-                             "algorithmic_flop_per_launch": flop, "note": "3 x the forward's algorithmic contraction flops per sample"},
+                             "algorithmic_flop_per_launch": flop,
+                             "note": "reference formulation: 3 x the forward's contraction flops per sample (forward + data gradients + weight "
+                                     "gradients over all 128 rows of every group).  NOT a hardware rate: the forward evaluates only the distinct rows "
+                                     "of a group (packed tiles, ~0.3-0.6 tiles per group) and the backward only the rows that won a channel of the "
+                                     "max-pool (SA1 ~7 of 128, SA2 ~25 of 128), compacted over the chunk; the executed tensor work is a small "
+                                     "fraction of this figure and the step is bound by HBM-side row traffic and launch count, not by the tensor pipe"},
                 "losses": [float(x) for x in losses.cpu()], "params": 19068103}
         emit(line)
     if world > 1:

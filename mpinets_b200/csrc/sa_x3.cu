@@ -852,8 +852,25 @@ sa2x3_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restri
 // split and store 128 columns per row (~2000 instructions per thread and tile), so with two chains per SM the tensor pipe idled ~40 %
 // of the time (ncu: 51 % tensor-active, 30 % issue-active, 8 resident warps).  Here a chain is EIGHT warps: warp w owns TMEM lane
 // quarter w % 4 (the hardware's lane restriction) and column half w / 4, i.e. every SIMT phase is split over twice the threads.
-// Same arithmetic, same packing, same outputs as sa2x3_tc_kernel (kept as the A/B reference: MPN_SA2X3_V1=1).
+// Eight warps also mean eight ball queries per round, and the two 16-lane halves of a warp's accumulator fragment are pooled
+// separately, so a round of EIGHT centroids is packed at a granularity of 16 rows (TilePack8): 0.33 instead of 0.39 tiles per group on
+// tabletop scenes.  Same arithmetic and outputs as sa2x3_tc_kernel (kept as the A/B reference: MPN_SA2X3_V1=1).
 constexpr int S2H_THREADS = 256 * S2X_NWG;
+struct Sa2hSmem {
+  static constexpr size_t w2h = 0;                                      // [128][128] bf16, K-major core matrices
+  static constexpr size_t w2l = w2h + 128 * 128 * 2;
+  static constexpr size_t w3h = w2l + 128 * 128 * 2;                    // [256][128]
+  static constexpr size_t w3l = w3h + 256 * 128 * 2;
+  static constexpr size_t b2 = w3l + 256 * 128 * 2;                     // [128] f32
+  static constexpr size_t b3 = b2 + 128 * 4;                            // [256] f32
+  static constexpr size_t w1x = b3 + 256 * 4;                           // [3][128] f32
+  static constexpr size_t pts = w1x + 3 * 128 * 4;                      // x[512] | y[512] | z[512]
+  static constexpr size_t lists = pts + 3 * SA1_NPOINT * 4;             // [NWG][2 slots][8][128] u16
+  static constexpr size_t u = lists + (size_t)S2X_NWG * 2 * 8 * 128 * 2;   // [NWG][8 eighths][128] f32: W1x c_i of the eighth's centroid
+  static constexpr size_t pool = u + (size_t)S2X_NWG * 8 * 128 * 4;     // [NWG][8 eighths][128] f32
+  static constexpr size_t bars = pool + (size_t)S2X_NWG * 8 * 128 * 4;
+  static constexpr size_t total = bars + 64;
+};
 __device__ __forceinline__ void chain_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
 __global__ void __launch_bounds__(S2H_THREADS, 1)
@@ -861,7 +878,7 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
                  const __nv_bfloat16* __restrict__ gw2, const __nv_bfloat16* __restrict__ gw3, const float* __restrict__ gb2,
                  const float* __restrict__ gb3, const float* __restrict__ gw1x, __nv_bfloat16* __restrict__ out_rows,
                  float* __restrict__ out_f32, int* __restrict__ err, int32_t* __restrict__ ball_idx, int split, int pack) {
-  using S = Sa2xSmem;
+  using S = Sa2hSmem;
   constexpr int N = SA1_NPOINT, NCENT = SA2_NPOINT, NWG = S2X_NWG;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* sB2 = reinterpret_cast<float*>(smem + S::b2);
@@ -876,10 +893,10 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
   const int b = blockIdx.x / split, part = blockIdx.x % split;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int g = warp >> 3, wc = warp & 7, wq = wc & 3, hh = wc >> 2, lane = threadIdx.x & 31, u = threadIdx.x & 255;
-  const int row = wq * 32 + lane;                       // this thread's row of the tile (= TMEM lane)
-  uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 2 * 4 * 128;
-  float* sU = reinterpret_cast<float*>(smem + S::u) + g * 4 * 128;
-  float* sPool = reinterpret_cast<float*>(smem + S::pool) + (size_t)g * 2 * 4 * 128;
+  const int me = wq * 2 + (lane >> 4);                  // this thread's row sits in eighth `me` of the tile (TMEM lane 32 wq + lane)
+  uint16_t* lists = reinterpret_cast<uint16_t*>(smem + S::lists) + (size_t)g * 2 * 8 * 128;
+  float* sU = reinterpret_cast<float*>(smem + S::u) + g * 8 * 128;
+  float* pl = reinterpret_cast<float*>(smem + S::pool) + (size_t)g * 8 * 128;
 
   stage_weight_ld(gw2, 128, 128, 256, smem + S::w2h);
   stage_weight_ld(gw2 + 128, 128, 128, 256, smem + S::w2l);
@@ -917,16 +934,16 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
   uint32_t phase = 0;
   bool ok = true;
   const unsigned lt = (1u << lane) - 1u;
-  __shared__ int hcnt_s[S2X_NWG * 2 * 4];
-  int* hcnt = hcnt_s + g * 8;
+  __shared__ int hcnt_s[S2X_NWG * 2 * 8];   // [NWG][2 slots][8]: distinct hits (<= 128) of a round's ball queries
+  int* hcnt = hcnt_s + g * 16;
 
-  // warps 0..3 of the chain: one centroid each, in-order scan of the 512 points (pointnet2 semantics, see sa2x3_tc_kernel)
+  // every warp of the chain: one centroid, in-order scan of the 512 points (pointnet2 semantics, see sa2x3_tc_kernel)
   auto bq_round = [&](int base, int slot) {
     const int jc = base + wc;
-    if (wc < 4 && jc < NCENT) {
+    if (jc < NCENT) {
       const float* cp = new_xyz + ((size_t)b * NCENT + jc) * 3;
       const float qx = cp[0], qy = cp[1], qz = cp[2];
-      uint16_t* out = lists + (slot * 4 + wc) * 128;
+      uint16_t* out = lists + (slot * 8 + wc) * 128;
       int cnt = 0, first = 0;
 #pragma unroll 4
       for (int k0 = 0; k0 < N; k0 += 32) {
@@ -939,7 +956,7 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
         cnt += __popc(hm);
       }
       for (int l = min(cnt, NSAMPLE) + lane; l < NSAMPLE; l += 32) out[l] = (uint16_t)first;
-      if (lane == 0) hcnt[slot * 4 + wc] = max(1, min(cnt, NSAMPLE));
+      if (lane == 0) hcnt[slot * 8 + wc] = max(1, min(cnt, NSAMPLE));
     }
   };
   auto issue = [&](uint64_t dWh, uint64_t dWl, uint32_t woff) {
@@ -958,21 +975,21 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
     }
   };
 
-  constexpr int STEP = NWG * 4;
+  constexpr int STEP = NWG * 8;
   int r = 0, kpre = 0;
   float4 xpre[8];                                      // channels [64 hh, 64 hh + 32) of the next tile's row
-  const int base0 = (g * split + part) * 4;
-  TilePack tp{0u, 0u, 0}, tpn{0u, 0u, 0};
+  const int base0 = (g * split + part) * 8;
+  TilePack8 tp{0u, 0u, 0}, tpn{0u, 0u, 0};
   int nvalid = 0, nvalid_n = 0, ntiles_done = 0;
-  auto open_round = [&](int nb, int nslot, TilePack& p, int& nv) {
-    nv = min(4, NCENT - nb);
-    p = pack_round(hcnt + nslot * 4, nv, pack);
+  auto open_round = [&](int nb, int nslot, TilePack8& p, int& nv) {
+    nv = min(8, NCENT - nb);
+    p = pack_round8(hcnt + nslot * 8, nv, pack);
     if (ball_idx && u < 128)
-      for (int c = 0; c < nv; ++c) ball_idx[((size_t)b * NCENT + nb + c) * NSAMPLE + u] = lists[(nslot * 4 + c) * 128 + u];
+      for (int c = 0; c < nv; ++c) ball_idx[((size_t)b * NCENT + nb + c) * NSAMPLE + u] = lists[(nslot * 8 + c) * 128 + u];
   };
-  auto prefetch = [&](const TilePack& p, int nv, int nslot, int ntile) {
-    const int mc = pack_owner(p, nv, ntile, wq);
-    kpre = lists[(nslot * 4 + mc) * 128 + (wq - pack_q0(p, mc)) * 32 + lane];
+  auto prefetch = [&](const TilePack8& p, int nv, int nslot, int ntile) {
+    const int mc = pack8_owner(p, nv, ntile, me);
+    kpre = lists[(nslot * 8 + mc) * 128 + (me - pack8_e0(p, mc)) * 16 + (lane & 15)];
     const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + kpre) * 128) + 16 * hh;
 #pragma unroll
     for (int q = 0; q < 8; ++q) xpre[q] = __ldg(prow + q);
@@ -982,20 +999,20 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
     const int slot = r & 1;
 #pragma unroll 1
     for (int tile = 0; tile < tp.ntiles && ok; ++tile) {
-      {   // W1x c of the centroid that owns each quarter of this tile: 4 x 128 values over the chain's 256 threads
+      {   // W1x c of the centroid that owns each eighth of this tile: 8 x 128 values over the chain's 256 threads
         const int ch = u & 127;
 #pragma unroll
-        for (int qq = 0; qq < 2; ++qq) {
-          const int q = (u >> 7) * 2 + qq;
-          const float* cp = new_xyz + ((size_t)b * NCENT + base + pack_owner(tp, nvalid, tile, q)) * 3;
-          sU[q * 128 + ch] = fmaf(sW1x[256 + ch], cp[2], fmaf(sW1x[128 + ch], cp[1], sW1x[ch] * cp[0]));
+        for (int qq = 0; qq < 4; ++qq) {
+          const int e = (u >> 7) * 4 + qq;
+          const float* cp = new_xyz + ((size_t)b * NCENT + base + pack8_owner(tp, nvalid, tile, e)) * 3;
+          sU[e * 128 + ch] = fmaf(sW1x[256 + ch], cp[2], fmaf(sW1x[128 + ch], cp[1], sW1x[ch] * cp[0]));
         }
       }
       chain_sync(g);
       // ---- layer 1 (per-point pre-activation - centroid term), ReLU, split: this thread's 64 channels of its row
       {
         const float4* prow = reinterpret_cast<const float4*>(pre + ((size_t)b * N + kpre) * 128) + 16 * hh;
-        const float* uq = sU + wq * 128 + 64 * hh;
+        const float* uq = sU + me * 128 + 64 * hh;
         float4 xb[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) xb[q] = __ldg(prow + 8 + q);
@@ -1053,11 +1070,11 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
       for (int half = 0; half < 2; ++half) {
         ok = ok && mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
-        // fp32 max over each warp's 32 rows x 64 columns: accumulator-fragment loads, in-thread max over a thread's 4 rows, halving
-        // butterfly over the warp's 8 row classes; the quarters of a centroid meet in shared memory
-        float* pl = sPool + half * 4 * 128;
+        if (half == 1) chain_sync(g);                            // the first half's maxima have been combined: pl may be rewritten
+        // fp32 max over each 16-lane half of the warp's accumulator fragment (= one eighth of the tile) x 64 columns: in-thread max
+        // over a thread's 2 rows, halving butterfly over the 8 row classes; the eighths of a centroid meet in shared memory
         {
-          float v[16];
+          float va_[16], vb_[16];
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
             uint32_t va[16], vb[16];
@@ -1066,18 +1083,21 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
             tmem_ld_wait();
 #pragma unroll
             for (int rep = 0; rep < 4; ++rep) {
-              v[(blk * 4 + rep) * 2] = fmaxf(fmaxf(__uint_as_float(va[rep * 4]), __uint_as_float(va[rep * 4 + 2])),
-                                             fmaxf(__uint_as_float(vb[rep * 4]), __uint_as_float(vb[rep * 4 + 2])));
-              v[(blk * 4 + rep) * 2 + 1] = fmaxf(fmaxf(__uint_as_float(va[rep * 4 + 1]), __uint_as_float(va[rep * 4 + 3])),
-                                                 fmaxf(__uint_as_float(vb[rep * 4 + 1]), __uint_as_float(vb[rep * 4 + 3])));
+              va_[(blk * 4 + rep) * 2] = fmaxf(__uint_as_float(va[rep * 4]), __uint_as_float(va[rep * 4 + 2]));
+              va_[(blk * 4 + rep) * 2 + 1] = fmaxf(__uint_as_float(va[rep * 4 + 1]), __uint_as_float(va[rep * 4 + 3]));
+              vb_[(blk * 4 + rep) * 2] = fmaxf(__uint_as_float(vb[rep * 4]), __uint_as_float(vb[rep * 4 + 2]));
+              vb_[(blk * 4 + rep) * 2 + 1] = fmaxf(__uint_as_float(vb[rep * 4 + 1]), __uint_as_float(vb[rep * 4 + 3]));
             }
           }
-          rows_max_butterfly<16>(v, lane);
+          rows_max_butterfly<16>(va_, lane);
+          rows_max_butterfly<16>(vb_, lane);
           // entries i = 2 * (lane >> 2) + jj: column block i / 8, rep (i % 8) / 2, element i % 2 of the fragment layout
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             const int i = 2 * (lane >> 2) + jj;
-            pl[wq * 128 + 64 * hh + 32 * (i >> 3) + 8 * ((i & 7) >> 1) + 2 * (lane & 3) + (i & 1)] = v[jj];
+            const int col = 64 * hh + 32 * (i >> 3) + 8 * ((i & 7) >> 1) + 2 * (lane & 3) + (i & 1);
+            pl[(2 * wq) * 128 + col] = va_[jj];
+            pl[(2 * wq + 1) * 128 + col] = vb_[jj];
           }
         }
         tc_fence_before();
@@ -1086,10 +1106,10 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
         {
           const int ch = u & 127;
           for (int c = u >> 7; c < nvalid; c += 2) {             // centroids dealt to the chain's two thread halves
-            if (pack_tile(tp, c) != tile) continue;
-            const int q0 = pack_q0(tp, c), q1 = pack_q1(tp, nvalid, c);
-            float m = pl[q0 * 128 + ch];
-            for (int q = q0 + 1; q < q1; ++q) m = fmaxf(m, pl[q * 128 + ch]);
+            if (pack8_tile(tp, c) != tile) continue;
+            const int e0 = pack8_e0(tp, c), e1 = pack8_e1(tp, nvalid, c);
+            float m = pl[e0 * 128 + ch];
+            for (int e = e0 + 1; e < e1; ++e) m = fmaxf(m, pl[e * 128 + ch]);
             m = fmaxf(m + sB3[half * 128 + ch], 0.f);
             __nv_bfloat16 h, l;
             split_bf16(m, h, l);
@@ -1102,7 +1122,7 @@ sa2x3h_tc_kernel(const float* __restrict__ xyz, int stride, const float* __restr
       }
       for (int i = u; i < nvalid * 16; i += 256) {   // [x y z | 0-pad] columns of the tile's centroids
         const int c = i >> 4, d = i & 15;
-        if (pack_tile(tp, c) != tile) continue;
+        if (pack8_tile(tp, c) != tile) continue;
         const float v = d < 3 ? new_xyz[((size_t)b * NCENT + base + c) * 3 + d] : 0.f;
         __nv_bfloat16 h, l;
         split_bf16(v, h, l);
@@ -1150,15 +1170,16 @@ static int launch_sa2x3(mpn_ctx* c, cudaStream_t s, const float* xyz1, const flo
                         float* out_f32, int32_t* ball_idx) {
   X3Weights& w = g_x3[c];
   MPN_REQUIRE(w.ready, "bf16x3 weights not packed");
-  const int split = sa_split(c, B, 32 / S2X_NWG);
-  if (getenv("MPN_SA2X3_V1") == nullptr) {   // default: 8 warps per chain (A/B switch read per launch)
-    MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2x3h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sa2xSmem::total));
-    sa2x3h_tc_kernel<<<B * split, S2H_THREADS, Sa2xSmem::total, s>>>(xyz1, 3, pre, xyz2, SA2_RADIUS * SA2_RADIUS, w.sa2_w2, w.sa2_w3, c->w.sa[1][1].b,
+  if (getenv("MPN_SA2X3_V1") == nullptr) {   // default: 8 warps per chain, rounds of 8 centroids (A/B switch read per launch)
+    const int split = sa_split(c, B, 16 / S2X_NWG);
+    MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2x3h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sa2hSmem::total));
+    sa2x3h_tc_kernel<<<B * split, S2H_THREADS, Sa2hSmem::total, s>>>(xyz1, 3, pre, xyz2, SA2_RADIUS * SA2_RADIUS, w.sa2_w2, w.sa2_w3, c->w.sa[1][1].b,
                                                                      c->w.sa[1][2].b, w.sa2_w1x, out_rows, out_f32, tc_error_flag(c), ball_idx, split, sa_pack());
     c->launches++;
     MPN_CHECK_CUDA(cudaGetLastError());
     return MPN_OK;
   }
+  const int split = sa_split(c, B, 32 / S2X_NWG);
   MPN_CHECK_CUDA(cudaFuncSetAttribute(sa2x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sa2xSmem::total));
   sa2x3_tc_kernel<<<B * split, S2X_THREADS, Sa2xSmem::total, s>>>(xyz1, 3, pre, xyz2, SA2_RADIUS * SA2_RADIUS, w.sa2_w2, w.sa2_w3, c->w.sa[1][1].b,
                                                                   c->w.sa[1][2].b, w.sa2_w1x, out_rows, out_f32, tc_error_flag(c), ball_idx, split, sa_pack());

@@ -227,6 +227,41 @@ __device__ __forceinline__ int pack_owner(const TilePack& p, int nvalid, int til
   return mc;
 }
 
+// The same packing for rounds of EIGHT centroids at a granularity of one EIGHTH (16 rows) of a tile -- sa2x3h_tc_kernel, whose chains
+// have eight warps (one ball query each) and pool the two 16-lane halves of a warp's accumulator fragment separately.
+struct TilePack8 {
+  uint32_t tl;   // 3 bits per centroid: its tile
+  uint32_t es;   // 3 bits per centroid: its first eighth inside the tile
+  int ntiles;
+};
+__device__ __forceinline__ TilePack8 pack_round8(const int* hcnt, int nvalid, int pack) {
+  TilePack8 p{0u, 0u, 1};
+  int tile = 0, fill = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < nvalid) {
+      const int q = pack ? (hcnt[c] + 15) >> 4 : 8;
+      if (fill + q > 8) { ++tile; fill = 0; }
+      p.tl |= (uint32_t)tile << (3 * c);
+      p.es |= (uint32_t)fill << (3 * c);
+      fill += q;
+    }
+  p.ntiles = tile + 1;
+  return p;
+}
+__device__ __forceinline__ int pack8_tile(const TilePack8& p, int c) { return (int)((p.tl >> (3 * c)) & 7u); }
+__device__ __forceinline__ int pack8_e0(const TilePack8& p, int c) { return (int)((p.es >> (3 * c)) & 7u); }
+__device__ __forceinline__ int pack8_e1(const TilePack8& p, int nvalid, int c) {
+  return (c + 1 < nvalid && pack8_tile(p, c + 1) == pack8_tile(p, c)) ? pack8_e0(p, c + 1) : 8;
+}
+__device__ __forceinline__ int pack8_owner(const TilePack8& p, int nvalid, int tile, int e) {
+  int mc = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < nvalid && pack8_tile(p, c) == tile && pack8_e0(p, c) <= e) mc = c;
+  return mc;
+}
+
 // the context's 64-bit tile counters live behind its sticky error flag (tc_error_flag, sa_tc.cu): module 0 = SA1, 1 = SA2
 __device__ __forceinline__ unsigned long long* sa_tile_counter(int* err, int module) {
   return reinterpret_cast<unsigned long long*>(err + 2) + module;
