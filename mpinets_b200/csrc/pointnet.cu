@@ -11,9 +11,12 @@
 //   * ball query: first nsample indices in index order with d2 < r*r, padded with the first hit.
 #include "engine.h"
 #include "spec_math.cuh"
+#include "tc_common.cuh"
 #include <cstdlib>
 
 namespace mpn {
+
+int* tc_error_flag(mpn_ctx* c);
 
 __host__ __device__ inline int opt_n_threads(int work) {
   int p = 1;
@@ -275,6 +278,388 @@ fps_pruned_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ pruned FPS, two problems per SM
+// fps_pruned_kernel keeps a problem's points in registers (40 per thread), so one 640-thread CTA fills an SM's register file and the
+// 511 dependent selection rounds of ONE problem run at ~57 % issue utilisation with nothing to overlap them.  Here the coordinates live
+// in shared memory (sorted by Morton cell, laid out [point-of-thread][thread] so that a warp's loads are conflict-free) and only the
+// running min-distances stay in registers: ~48 registers and ~110 KB per CTA, i.e. TWO problems per SM whose rounds interleave.
+// Same pruning test, same distances, same total order on (distance, tie word) as fps_pruned_kernel -> identical indices.
+constexpr int FPS2_CELLS = 2048;   // 16 x 16 x 8 Morton cells (x, y: 4 bits, z: 3 bits)
+
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS, 2)
+fps_smem_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int32_t* __restrict__ idx, float* __restrict__ new_xyz) {
+  constexpr int NP = THREADS * PPT;                         // padded point count
+  extern __shared__ __align__(16) uint8_t fsm[];
+  float* sx = reinterpret_cast<float*>(fsm);                // [PPT][THREADS]: point i of thread t at i * THREADS + t
+  float* sy = sx + NP;
+  float* sz = sy + NP;
+  uint16_t* ord = reinterpret_cast<uint16_t*>(sz + NP);     // [NP] slot -> original index
+  uint16_t* inv = ord + NP;                                 // [N]  original index -> slot
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(inv + ((N + 7) & ~7));   // [CELLS] histogram / cursors (setup only)
+  __shared__ uint2 slot[2][THREADS / 32];
+  __shared__ uint32_t bb[6];
+  __shared__ uint32_t wsum[16];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = xyz + (size_t)b * N * stride;
+  auto load = [&](int k, float& x, float& y, float& z) {
+    if (stride == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p) + k); x = v.x; y = v.y; z = v.z; }
+    else { x = __ldg(p + (size_t)k * stride); y = __ldg(p + (size_t)k * stride + 1); z = __ldg(p + (size_t)k * stride + 2); }
+  };
+  // ---- bounding box
+  if (tid < 3) bb[tid] = 0xFFFFFFFFu;
+  if (tid >= 3 && tid < 6) bb[tid] = 0u;
+  for (int i = tid; i < FPS2_CELLS; i += THREADS) cnt[i] = 0u;
+  for (int i = tid; i < NP; i += THREADS) { sx[i] = 0.f; sy[i] = 0.f; sz[i] = 0.f; ord[i] = 0xFFFFu; }
+  __syncthreads();
+  {
+    uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+    for (int k = tid; k < N; k += THREADS) {
+      float x, y, z;
+      load(k, x, y, z);
+      const uint32_t o[3] = {f2ord(x), f2ord(y), f2ord(z)};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], o[a]); mx[a] = max(mx[a], o[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const uint32_t m0 = __reduce_min_sync(0xffffffffu, mn[a]), m1 = __reduce_max_sync(0xffffffffu, mx[a]);
+      if (lane == 0) { atomicMin(&bb[a], m0); atomicMax(&bb[3 + a], m1); }
+    }
+  }
+  __syncthreads();
+  const float lo_x = ord2f(bb[0]), lo_y = ord2f(bb[1]), lo_z = ord2f(bb[2]);
+  const float sx_ = 15.999f / fmaxf(ord2f(bb[3]) - lo_x, 1e-6f), sy_ = 15.999f / fmaxf(ord2f(bb[4]) - lo_y, 1e-6f),
+              sz_ = 7.999f / fmaxf(ord2f(bb[5]) - lo_z, 1e-6f);
+  auto cell_of = [&](float x, float y, float z) -> uint32_t {
+    const uint32_t cx = (uint32_t)min(15, max(0, (int)((x - lo_x) * sx_))), cy = (uint32_t)min(15, max(0, (int)((y - lo_y) * sy_))),
+                   cz = (uint32_t)min(7, max(0, (int)((z - lo_z) * sz_)));
+    // 11-bit Morton-like key: z2 y3 x3 | z1 y2 x2 | z0 y1 x1 | y0 x0
+    return (cx & 1u) | ((cy & 1u) << 1) | ((cx & 2u) << 1) | ((cy & 2u) << 2) | ((cz & 1u) << 4) | ((cx & 4u) << 3) | ((cy & 4u) << 4) |
+           ((cz & 2u) << 6) | ((cx & 8u) << 5) | ((cy & 8u) << 6) | ((cz & 4u) << 8);
+  };
+  // ---- counting sort by cell
+  for (int k = tid; k < N; k += THREADS) { float x, y, z; load(k, x, y, z); atomicAdd(&cnt[cell_of(x, y, z)], 1u); }
+  __syncthreads();
+  {
+    constexpr int PER = FPS2_CELLS / 512;
+    const bool scanner = tid < 512;
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = scanner ? cnt[tid * PER + i] : 0u; sum += loc[i]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31 && scanner) wsum[warp] = inc;
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t v = lane < 16 ? wsum[lane] : 0u;
+      uint32_t iv = v;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+      if (lane < 16) wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    if (scanner) {
+      uint32_t run = wsum[warp] + inc - sum;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { cnt[tid * PER + i] = run; run += loc[i]; }
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < N; k += THREADS) {
+    float x, y, z;
+    load(k, x, y, z);
+    const uint32_t s = atomicAdd(&cnt[cell_of(x, y, z)], 1u);          // sorted position: thread s / PPT, its point s % PPT
+    const uint32_t sl = (s % PPT) * THREADS + s / PPT;
+    sx[sl] = x; sy[sl] = y; sz[sl] = z;
+    ord[sl] = (uint16_t)k;
+    inv[k] = (uint16_t)sl;
+  }
+  __syncthreads();
+  // ---- registers: the running min-distance of the thread's PPT points (skipped / padding slots: -1, can never win)
+  float temp[PPT];
+  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int sl = i * THREADS + tid;
+    temp[i] = -1.0f;
+    if (ord[sl] != 0xFFFFu) {
+      const float x = sx[sl], y = sy[sl], z = sz[sl];
+      const float mag = ffma(z, z, ffma(y, y, fmul(x, x)));
+      if (!(mag < 1e-3f)) temp[i] = 1e10f;   // (double)mag <= 1e-3, see the header
+      const uint32_t o[3] = {f2ord(x), f2ord(y), f2ord(z)};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], o[a]); mx[a] = max(mx[a], o[a]); }
+    }
+  }
+  float wlo[3], whi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const uint32_t m0 = __reduce_min_sync(0xffffffffu, mn[a]), m1 = __reduce_max_sync(0xffffffffu, mx[a]);
+    const float l = m0 <= m1 ? ord2f(m0) : 1e30f, h = m0 <= m1 ? ord2f(m1) : 1e30f;
+    wlo[a] = l - (fabsf(l) * 1e-5f + 1e-6f);
+    whi[a] = h + (fabsf(h) * 1e-5f + 1e-6f);
+  }
+  int32_t* out = idx + (size_t)b * npoint;
+  float* oxyz = new_xyz ? new_xyz + (size_t)b * npoint * 3 : nullptr;
+  int old = 0;
+  if (tid == 0) {
+    out[0] = 0;
+    if (oxyz) { const int sl = inv[0]; oxyz[0] = sx[sl]; oxyz[1] = sy[sl]; oxyz[2] = sz[sl]; }
+  }
+  uint32_t wm = 0x7F800000u, wl_ = 0u;   // cached warp best (distance bits, tie word); +inf forces the first update
+  for (int j = 1; j < npoint; ++j) {
+    const int os = inv[old];
+    const float cx = sx[os], cy = sy[os], cz = sz[os];
+    const float gx = fmaxf(0.f, fmaxf(wlo[0] - cx, cx - whi[0])), gy = fmaxf(0.f, fmaxf(wlo[1] - cy, cy - whi[1])),
+                gz = fmaxf(0.f, fmaxf(wlo[2] - cz, cz - whi[2]));
+    const bool skip = (gx * gx + gy * gy + gz * gz) * 0.9999f > __uint_as_float(wm);
+    if (!skip) {
+      float bd = -1.0f;
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        const int sl = i * THREADS + tid;
+        temp[i] = fminf(dist2(sx[sl], sy[sl], sz[sl], cx, cy, cz), temp[i]);
+        bd = fmaxf(bd, temp[i]);
+      }
+      const uint32_t dbits = bd >= 0.0f ? __float_as_uint(bd) : 0u;
+      wm = __reduce_max_sync(0xffffffffu, dbits);
+      uint32_t lw = 0u;
+      if (dbits == wm && bd >= 0.0f) {   // usually one lane: the largest tie word among its points that attain the maximum
+#pragma unroll
+        for (int i = 0; i < PPT; ++i)
+          if (temp[i] == bd) {
+            const uint32_t k = ord[i * THREADS + tid];
+            lw = max(lw, 0xFFFFFFFFu - (((__brev(k & 511u) >> 23) << 23) | k));
+          }
+      }
+      wl_ = __reduce_max_sync(0xffffffffu, lw);
+    }
+    if (lane == 0) slot[j & 1][warp] = make_uint2(wm, wl_);
+    __syncthreads();
+    const uint2 v = lane < THREADS / 32 ? slot[j & 1][lane] : make_uint2(0u, 0u);
+    const uint32_t M = __reduce_max_sync(0xffffffffu, v.x);
+    const uint32_t L = __reduce_max_sync(0xffffffffu, v.x == M ? v.y : 0u);
+    old = (M == 0u && L == 0u) ? 0 : (int)((0xFFFFFFFFu - L) & 0x7FFFFFu);
+    if (tid == 0) {
+      out[j] = old;
+      if (oxyz) { const int sl = inv[old]; oxyz[3 * j] = sx[sl]; oxyz[3 * j + 1] = sy[sl]; oxyz[3 * j + 2] = sz[sl]; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pruned FPS with a director warp
+// fps_pruned_kernel is ISSUE-bound: every one of its 20 warps spends ~50 instructions per round on the skip test, the block barrier and
+// the (redundant) final reduction, although only ~28 % of them have points to update; putting two problems on an SM (fps_smem_kernel)
+// only adds instructions.  Here the 20 worker warps SLEEP on one mbarrier each (a suspended `mbarrier.try_wait` issues nothing) and a
+// 21st warp directs the round: lane w holds worker w's bounding box and cached best, tests all boxes at once, wakes exactly the warps
+// that can change, tops the round's arrival count up for the others, and does the final reduction alone.  Per round ~60 director
+// instructions + ~170 per ACTIVE worker instead of ~50 per warp + ~130 per active one -- and with the coordinates in shared memory
+// (fps_smem_kernel's layout) two problems per SM interleave their rounds.  Same distances, same total order -> identical indices.
+template <int WTHREADS, int PPT>
+__global__ void __launch_bounds__(WTHREADS + 32, 2)
+fps_dir_kernel(const float* __restrict__ xyz, int N, int stride, int npoint, int32_t* __restrict__ idx, float* __restrict__ new_xyz,
+               int* __restrict__ err) {
+  using namespace tc;
+  constexpr int NP = WTHREADS * PPT, NW = WTHREADS / 32, THREADS = WTHREADS + 32;
+  static_assert(NW <= 32, "one director lane per worker warp");
+  extern __shared__ __align__(16) uint8_t fsm[];
+  float* sx = reinterpret_cast<float*>(fsm);                // [PPT][WTHREADS]: point i of worker thread t at i * WTHREADS + t
+  float* sy = sx + NP;
+  float* sz = sy + NP;
+  uint16_t* ord = reinterpret_cast<uint16_t*>(sz + NP);     // [NP] slot -> original index
+  uint16_t* inv = ord + NP;                                 // [N]  original index -> slot
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(inv + ((N + 7) & ~7));   // [CELLS] histogram / cursors (setup only)
+  __shared__ uint2 slot[NW];
+  __shared__ float wbox[NW][6];
+  __shared__ float cbuf[4];
+  __shared__ uint32_t bb[6];
+  __shared__ uint32_t wsum[16];
+  __shared__ int quit;
+  __shared__ __align__(8) uint64_t go[NW];
+  __shared__ __align__(8) uint64_t done;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = xyz + (size_t)b * N * stride;
+  auto load = [&](int k, float& x, float& y, float& z) {
+    if (stride == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p) + k); x = v.x; y = v.y; z = v.z; }
+    else { x = __ldg(p + (size_t)k * stride); y = __ldg(p + (size_t)k * stride + 1); z = __ldg(p + (size_t)k * stride + 2); }
+  };
+  // ---- setup (all 21 warps): bounding box, counting sort by Morton cell into the [point-of-thread][thread] layout
+  if (tid < 3) bb[tid] = 0xFFFFFFFFu;
+  if (tid >= 3 && tid < 6) bb[tid] = 0u;
+  if (tid == 0) {
+    for (int w = 0; w < NW; ++w) mbar_init(&go[w], 1);
+    mbar_init(&done, NW);
+    mbar_fence_init();
+    quit = 0;
+  }
+  for (int i = tid; i < FPS2_CELLS; i += THREADS) cnt[i] = 0u;
+  for (int i = tid; i < NP; i += THREADS) { sx[i] = 0.f; sy[i] = 0.f; sz[i] = 0.f; ord[i] = 0xFFFFu; }
+  __syncthreads();
+  {
+    uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+    for (int k = tid; k < N; k += THREADS) {
+      float x, y, z;
+      load(k, x, y, z);
+      const uint32_t o[3] = {f2ord(x), f2ord(y), f2ord(z)};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], o[a]); mx[a] = max(mx[a], o[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const uint32_t m0 = __reduce_min_sync(0xffffffffu, mn[a]), m1 = __reduce_max_sync(0xffffffffu, mx[a]);
+      if (lane == 0) { atomicMin(&bb[a], m0); atomicMax(&bb[3 + a], m1); }
+    }
+  }
+  __syncthreads();
+  const float lo_x = ord2f(bb[0]), lo_y = ord2f(bb[1]), lo_z = ord2f(bb[2]);
+  const float sx_ = 15.999f / fmaxf(ord2f(bb[3]) - lo_x, 1e-6f), sy_ = 15.999f / fmaxf(ord2f(bb[4]) - lo_y, 1e-6f),
+              sz_ = 7.999f / fmaxf(ord2f(bb[5]) - lo_z, 1e-6f);
+  auto cell_of = [&](float x, float y, float z) -> uint32_t {
+    const uint32_t cx = (uint32_t)min(15, max(0, (int)((x - lo_x) * sx_))), cy = (uint32_t)min(15, max(0, (int)((y - lo_y) * sy_))),
+                   cz = (uint32_t)min(7, max(0, (int)((z - lo_z) * sz_)));
+    return (cx & 1u) | ((cy & 1u) << 1) | ((cx & 2u) << 1) | ((cy & 2u) << 2) | ((cz & 1u) << 4) | ((cx & 4u) << 3) | ((cy & 4u) << 4) |
+           ((cz & 2u) << 6) | ((cx & 8u) << 5) | ((cy & 8u) << 6) | ((cz & 4u) << 8);
+  };
+  for (int k = tid; k < N; k += THREADS) { float x, y, z; load(k, x, y, z); atomicAdd(&cnt[cell_of(x, y, z)], 1u); }
+  __syncthreads();
+  {
+    constexpr int PER = FPS2_CELLS / 512;
+    const bool scanner = tid < 512;
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = scanner ? cnt[tid * PER + i] : 0u; sum += loc[i]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31 && scanner) wsum[warp] = inc;
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t v = lane < 16 ? wsum[lane] : 0u;
+      uint32_t iv = v;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += y; }
+      if (lane < 16) wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    if (scanner) {
+      uint32_t run = wsum[warp] + inc - sum;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { cnt[tid * PER + i] = run; run += loc[i]; }
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < N; k += THREADS) {
+    float x, y, z;
+    load(k, x, y, z);
+    const uint32_t s = atomicAdd(&cnt[cell_of(x, y, z)], 1u);          // sorted position: worker thread s / PPT, its point s % PPT
+    const uint32_t sl = (s % PPT) * WTHREADS + s / PPT;
+    sx[sl] = x; sy[sl] = y; sz[sl] = z;
+    ord[sl] = (uint16_t)k;
+    inv[k] = (uint16_t)sl;
+  }
+  __syncthreads();
+  int32_t* out = idx + (size_t)b * npoint;
+  float* oxyz = new_xyz ? new_xyz + (size_t)b * npoint * 3 : nullptr;
+  bool ok = true;
+  if (warp < NW) {
+    // ================================================================= worker warp: sleeps until the director wakes it for a round
+    float temp[PPT];
+    uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int sl = i * WTHREADS + tid;
+      temp[i] = -1.0f;
+      if (ord[sl] != 0xFFFFu) {
+        const float x = sx[sl], y = sy[sl], z = sz[sl];
+        const float mag = ffma(z, z, ffma(y, y, fmul(x, x)));
+        if (!(mag < 1e-3f)) temp[i] = 1e10f;   // (double)mag <= 1e-3, see the header
+        const uint32_t o[3] = {f2ord(x), f2ord(y), f2ord(z)};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], o[a]); mx[a] = max(mx[a], o[a]); }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {   // warp bounding box (slightly inflated); an empty warp gets an inverted box far away
+      const uint32_t m0 = __reduce_min_sync(0xffffffffu, mn[a]), m1 = __reduce_max_sync(0xffffffffu, mx[a]);
+      const float l = m0 <= m1 ? ord2f(m0) : 1e30f, h = m0 <= m1 ? ord2f(m1) : 1e30f;
+      if (lane == 0) { wbox[warp][a] = l - (fabsf(l) * 1e-5f + 1e-6f); wbox[warp][3 + a] = h + (fabsf(h) * 1e-5f + 1e-6f); }
+    }
+    if (lane == 0) slot[warp] = make_uint2(0x7F800000u, 0u);   // +inf: the first round updates every warp
+    __syncthreads();
+    uint32_t ph = 0;
+    while (true) {
+      ok = mbar_wait(&go[warp], ph);
+      ph ^= 1u;
+      if (!ok || *reinterpret_cast<volatile int*>(&quit)) break;
+      const float cx = cbuf[0], cy = cbuf[1], cz = cbuf[2];
+      float bd = -1.0f;
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        const int sl = i * WTHREADS + tid;
+        temp[i] = fminf(dist2(sx[sl], sy[sl], sz[sl], cx, cy, cz), temp[i]);
+        bd = fmaxf(bd, temp[i]);
+      }
+      const uint32_t dbits = bd >= 0.0f ? __float_as_uint(bd) : 0u;
+      const uint32_t wm = __reduce_max_sync(0xffffffffu, dbits);
+      uint32_t lw = 0u;
+      if (dbits == wm && bd >= 0.0f) {   // usually one lane: the largest tie word among its points that attain the maximum
+#pragma unroll
+        for (int i = 0; i < PPT; ++i)
+          if (temp[i] == bd) {
+            const uint32_t k = ord[i * WTHREADS + tid];
+            lw = max(lw, 0xFFFFFFFFu - (((__brev(k & 511u) >> 23) << 23) | k));
+          }
+      }
+      const uint32_t wl = __reduce_max_sync(0xffffffffu, lw);
+      if (lane == 0) { slot[warp] = make_uint2(wm, wl); mbar_arrive(&done); }
+    }
+  } else {
+    // ================================================================= director warp
+    __syncthreads();   // boxes and initial slots are in shared memory
+    float bl[3] = {0.f, 0.f, 0.f}, bh[3] = {0.f, 0.f, 0.f};
+    if (lane < NW) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { bl[a] = wbox[lane][a]; bh[a] = wbox[lane][3 + a]; }
+    }
+    uint32_t wm_w = lane < NW ? 0x7F800000u : 0u, wl_w = 0u;
+    int old = 0;
+    if (lane == 0) {
+      out[0] = 0;
+      if (oxyz) { const int sl = inv[0]; oxyz[0] = sx[sl]; oxyz[1] = sy[sl]; oxyz[2] = sz[sl]; }
+    }
+    for (int j = 1; j < npoint && ok; ++j) {
+      const int os = inv[old];
+      const float cx = sx[os], cy = sy[os], cz = sz[os];
+      const float gx = fmaxf(0.f, fmaxf(bl[0] - cx, cx - bh[0])), gy = fmaxf(0.f, fmaxf(bl[1] - cy, cy - bh[1])),
+                  gz = fmaxf(0.f, fmaxf(bl[2] - cz, cz - bh[2]));
+      const bool act = lane < NW && !((gx * gx + gy * gy + gz * gz) * 0.9999f > __uint_as_float(wm_w));
+      const unsigned am = __ballot_sync(0xffffffffu, act);
+      const int nact = __popc(am);
+      if (act) {   // every waking lane publishes the (identical) centroid before its release-arrive
+        cbuf[0] = cx; cbuf[1] = cy; cbuf[2] = cz;
+        mbar_arrive(&go[lane]);
+      }
+      if (lane == 0 && nact < NW) mbar_arrive_n(&done, (uint32_t)(NW - nact));
+      ok = mbar_wait(&done, (uint32_t)((j - 1) & 1));
+      if (act) { const uint2 v = slot[lane]; wm_w = v.x; wl_w = v.y; }
+      const uint32_t M = __reduce_max_sync(0xffffffffu, wm_w);
+      const uint32_t L = __reduce_max_sync(0xffffffffu, (lane < NW && wm_w == M) ? wl_w : 0u);
+      old = (M == 0u && L == 0u) ? 0 : (int)((0xFFFFFFFFu - L) & 0x7FFFFFu);
+      if (lane == 0) {
+        out[j] = old;
+        if (oxyz) { const int sl = inv[old]; oxyz[3 * j] = sx[sl]; oxyz[3 * j + 1] = sy[sl]; oxyz[3 * j + 2] = sz[sl]; }
+      }
+    }
+    if (lane == 0) *reinterpret_cast<volatile int*>(&quit) = 1;
+    __syncwarp();
+    __threadfence_block();
+    if (lane < NW) mbar_arrive(&go[lane]);
+  }
+  if (!ok && lane == 0 && err) atomicExch(err, 2);
+}
+
 int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int stride, int npoint, int32_t* idx, float* new_xyz) {
   MPN_REQUIRE(N >= 1 && N <= 16 * FPS_THREADS, "mpn_fps: N=%d unsupported (1..%d)", N, 16 * FPS_THREADS);
   MPN_REQUIRE(npoint >= 1 && npoint <= N, "mpn_fps: npoint=%d out of range for N=%d", npoint, N);
@@ -292,7 +677,17 @@ int launch_fps(mpn_ctx* c, cudaStream_t s, const float* xyz, int B, int N, int s
     MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
     fps_pruned_kernel<T, P><<<B, T, smem_p, s>>>(xyz, N, stride, npoint, idx, new_xyz);                                   \
   } while (0)
-    if (v == 1) FPSP_LAUNCH(1024, 7);
+    if (v == 5 && N <= 640 * 10) {   // director warp + sleeping workers, coordinates in shared memory, two problems per SM
+      const size_t smem2 = (size_t)3 * 6400 * 4 + (size_t)6400 * 2 + (size_t)((N + 7) & ~7) * 2 + FPS2_CELLS * 4 + 16;
+      MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_dir_kernel<640, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      fps_dir_kernel<640, 10><<<B, 672, smem2, s>>>(xyz, N, stride, npoint, idx, new_xyz, tc_error_flag(c));
+    }
+    else if (v == 4 && N <= 640 * 10) {   // coordinates in shared memory, two problems per SM
+      const size_t smem2 = (size_t)3 * 6400 * 4 + (size_t)6400 * 2 + (size_t)((N + 7) & ~7) * 2 + FPS2_CELLS * 4 + 16;
+      MPN_CHECK_CUDA(cudaFuncSetAttribute(fps_smem_kernel<640, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      fps_smem_kernel<640, 10><<<B, 640, smem2, s>>>(xyz, N, stride, npoint, idx, new_xyz);
+    }
+    else if (v == 1) FPSP_LAUNCH(1024, 7);
     else if (v == 2) FPSP_LAUNCH(768, 9);
     else if (v == 0) FPSP_LAUNCH(512, 13);
     else FPSP_LAUNCH(640, 10);

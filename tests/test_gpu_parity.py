@@ -187,6 +187,30 @@ def test_fps_origin_skip_boundary(engine, oracle):
     assert np.array_equal(got, oracle.fps(big, 64)) and got[0, 1] == 7
 
 
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5"])
+def test_fps_kernel_variants_agree(engine, oracle, tables, variant):
+    """every variant of the large-cloud FPS (MPN_FPS_VARIANT: thread / points-per-thread splits of the register-resident pruned kernel,
+    4 = coordinates in shared memory with two problems per SM, 5 = director warp + workers sleeping on mbarriers) against the oracle
+    on scene clouds, a tie-heavy lattice cloud and a cloud with skipped near-origin points: the index sequence is a property of the
+    (distance, tie word) total order, not of the reduction shape.  3 is the default (fastest measured: DESIGN.md section 13)."""
+    cloud, _ = _clouds(engine, oracle, tables, 6)
+    rng = np.random.RandomState(3)
+    extra = rng.uniform(-1, 1, size=(2, 6272, 4)).astype(np.float32)
+    extra[0, :, :3] = np.round(extra[0, :, :3] * 6) / 6
+    extra[1, :2000, :3] *= 0.02
+    allc = np.ascontiguousarray(np.concatenate([cloud, extra]))
+    os.environ["MPN_FPS_VARIANT"] = variant
+    try:
+        idx, new_xyz = engine.fps(torch.from_numpy(allc).cuda(), 512, return_xyz=True)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("MPN_FPS_VARIANT", None)
+    assert not engine.tc_error()
+    exp = oracle.fps(allc, 512)
+    assert np.array_equal(idx.cpu().numpy(), exp)
+    assert np.array_equal(new_xyz.cpu().numpy(), np.stack([allc[b, exp[b], :3] for b in range(len(allc))]))
+
+
 def test_ball_query_bit_exact(engine, oracle, tables):
     cloud, _ = _clouds(engine, oracle, tables, 8)
     idx = oracle.fps(cloud, 512)
