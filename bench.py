@@ -313,26 +313,25 @@ def roofline_of(stages, per_stage, B, peaks, mode, traffic, tiles=None):
             flop, issued = w["executed_flop"], w["issued_mma_flop"]
         else:
             flop, issued = ref_flop, ref_flop * (X3_MMA_FACTOR.get(dom, 3.0) if mode == "bf16x3" else 1.0)
-        ach = flop / sec / 1e12
+        ach = ref_flop / sec / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": dom_traffic, "peak_source": peaks["source"] + ", sustained bf16",
-                "algorithmic_flop_per_launch": flop, "avg_launch_ms": per_stage[dom],
+                "algorithmic_flop_per_launch": ref_flop, "avg_launch_ms": per_stage[dom],
                 "share_of_step": stages[dom]["ms"] / total_stage_ms,
-                "issued_mma_flop_per_launch": issued, "issued_mma_frac_of_peak": issued / sec / 1e12 / peak,
-                "reference_formulation_flop_per_launch": ref_flop, "reference_formulation_tflops": ref_flop / sec / 1e12}
-        note = []
+                "executed_flop_per_launch": flop, "executed_tflops": flop / sec / 1e12, "executed_frac_of_peak": flop / sec / 1e12 / peak,
+                "issued_mma_flop_per_launch": issued, "issued_mma_frac_of_peak": issued / sec / 1e12 / peak}
+        note = ["achieved = SURVEY 8(d)'s algorithmic flops of the stage (the reference formulation: all 128 rows of every ball-query group) "
+                "x problems per launch / the launch time measured with CUDA events"]
         if tiles and dom in SA_GROUPS:
             roof["tiles_per_group"] = tiles[dom] / float(SA_GROUPS[dom] * B)
-            note.append("algorithmic flops = the fp32 formulation of the rows the kernel really evaluates: a ball-query group holds H <= 128 "
-                        "distinct neighbours (the rest are copies of the first hit, which the max-pool ignores), the kernel packs the distinct "
-                        "rows of several groups into 128-row MMA tiles (%.3f tiles per group, counted on the device), so achieved = reference "
-                        "flops x tiles per group / time; reference_formulation_tflops counts all 128 rows per group and is NOT a hardware rate"
-                        % roof["tiles_per_group"])
+            note.append("the kernel does not execute all of that work: a group holds H <= 128 distinct neighbours (the rest are copies of the "
+                        "first hit, which the max-pool ignores) and the distinct rows of several groups are packed into 128-row MMA tiles "
+                        "(%.3f tiles per group, counted on the device) -- executed_* = the fp32 formulation of the rows really evaluated, "
+                        "issued_mma_* = the bf16 MMA flops behind them, i.e. the tensor pipe's real load (its utilisation is "
+                        "issued_mma_frac_of_peak, not frac)" % roof["tiles_per_group"])
         if mode == "bf16x3":
-            note.append("the bf16x3 mode issues three bf16 MMAs per product (a_hi w_hi + a_lo w_hi + a_hi w_lo): the tensor pipe runs at "
-                        "issued_mma_frac_of_peak")
-        if note:
-            roof["note"] = "; ".join(note)
+            note.append("the bf16x3 mode issues three bf16 MMAs per product (a_hi w_hi + a_lo w_hi + a_hi w_lo)")
+        roof["note"] = "; ".join(note)
     else:
         ach = BYTES_PER_STEP[dom] * B / (per_stage[dom] / 1000.0) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -346,7 +345,8 @@ def roofline_of(stages, per_stage, B, peaks, mode, traffic, tiles=None):
 
 
 def tensor_kernels_of(stages, tiles, B, mode, peaks):
-    """per tensor stage: ms per launch, executed (distinct-row) algorithmic TFLOP/s, issued bf16 MMA rate, reference-formulation rate"""
+    """per tensor stage: ms per launch, algorithmic TFLOP/s (SURVEY 8(d)'s figure: all 128 rows per group), executed TFLOP/s (the fp32
+    formulation of the distinct rows really evaluated) and the issued bf16 MMA rate (the tensor pipe's real load)"""
     out = {}
     for k in ("sa1", "sa2", "sa3", "fc"):
         v = stages.get(k)
@@ -360,9 +360,9 @@ def tensor_kernels_of(stages, tiles, B, mode, peaks):
             flop, issued = w["executed_flop"], w["issued_mma_flop"]
         else:
             flop, issued = ref, ref * (X3_MMA_FACTOR[k] if mode == "bf16x3" else 1.0)
-        out[k] = {"ms": ms, "TFLOPs": flop / sec / 1e12, "frac_of_bf16_sustained": flop / sec / 1e12 / peaks["bf16_sustained"],
-                  "issued_mma_frac_of_bf16_sustained": issued / sec / 1e12 / peaks["bf16_sustained"],
-                  "reference_formulation_tflops": ref / sec / 1e12}
+        out[k] = {"ms": ms, "TFLOPs": ref / sec / 1e12, "frac_of_bf16_sustained": ref / sec / 1e12 / peaks["bf16_sustained"],
+                  "executed_tflops": flop / sec / 1e12, "executed_frac_of_bf16_sustained": flop / sec / 1e12 / peaks["bf16_sustained"],
+                  "issued_mma_frac_of_bf16_sustained": issued / sec / 1e12 / peaks["bf16_sustained"]}
         if tiles and k in SA_GROUPS:
             out[k]["tiles_per_group"] = tiles[k] / float(SA_GROUPS[k] * B)
     return out
