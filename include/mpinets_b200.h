@@ -187,7 +187,9 @@ enum { MPN_M_COLLISION = 0, MPN_M_FIRST_COLLISION_STEP = 1, MPN_M_STEPS = 2, MPN
  * check_every_step != 0 evaluates the collision flag after every step (config 3) instead of once at the end.
  * early_exit: 0 = exactly T steps for everybody; 1 = per-problem done mask (stopped problems keep their configuration) and the host
  * polls every 8 steps whether every problem has stopped, ending the loop early like rollout_until_success's break (the only host
- * synchronisation of this call; skipped while the stream is being captured); 2 = done mask only, never synchronises. */
+ * synchronisation of this call; skipped while the stream is being captured) and, once at most half of the current problems are still
+ * running, carries only those on in a compact set (results scattered back; a stopped problem's rows of `cloud` keep the robot points of
+ * the last step it was carried through); 2 = done mask only, never synchronises. */
 int mpn_rollout(mpn_ctx* ctx, void* stream, int precision, const mpn_scene* scene, int B, int N, float* cloud,
                 const float* q0, const float* target, int T, int early_exit, int check_every_step, float* traj,
                 float* metrics);

@@ -251,6 +251,10 @@ static int policy_forward(mpn_ctx* c, cudaStream_t s, int precision, const float
 }  // namespace mpn
 
 using namespace mpn;
+void free_live_sets(mpn_ctx* c);
+#ifndef MPN_NLINK
+#define MPN_NLINK 11   // link frames per configuration (spec_math.cuh)
+#endif
 
 #define REQ_CTX(c)                                              \
   do {                                                          \
@@ -311,6 +315,7 @@ int mpn_ctx_destroy(mpn_ctx* c) {
   if (c->robot_sel_steps) cudaFree(c->robot_sel_steps);
   if (c->loss_partial) cudaFree(c->loss_partial);
   free_train_ws(c);
+  free_live_sets(c);
   if (c->w.params) cudaFree(c->w.params);
   delete c;
   return MPN_OK;
@@ -794,6 +799,106 @@ int mpn_adam_step(mpn_ctx* c, void* stream, const float* grads, float lr, float 
   return adam_step(c, (cudaStream_t)stream, grads, lr, beta1, beta2, eps, clip_norm, step, grad_norm);
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- early exit: compaction of the live problems
+// rollout_until_success (run_inference.py:137-191) stops a problem when it reaches its target; in a lock-step batch the stopped problems
+// would keep costing a full policy step.  At a poll point where at most half of the current problems are still running, their state
+// (cloud, joint state, frames, target, scene rows, flags) is gathered into a compact set and the loop goes on over that set only; what the
+// abandoned set produced is scattered back to the caller's arrays first.  Problems are independent and the per-step robot subset is
+// shared by the batch, so the order inside the compact set does not matter and results equal the uncompacted rollout's bit for bit.
+namespace {
+struct LiveSet {
+  int cap = 0, n_points = 0, m1 = 0, m2 = 0, stride = 0;
+  float *cloud = nullptr, *target = nullptr, *qn = nullptr, *qu = nullptr, *frames = nullptr, *eef = nullptr, *traj = nullptr;
+  float *cub_c = nullptr, *cub_d = nullptr, *cub_q = nullptr, *cyl_c = nullptr, *cyl_r = nullptr, *cyl_h = nullptr, *cyl_q = nullptr;
+  int32_t *done = nullptr, *first = nullptr, *map = nullptr, *sel = nullptr;
+  uint8_t* flags = nullptr;
+};
+struct LiveSets { LiveSet s[2]; };
+
+void free_live_set(LiveSet& L) {
+  void* ps[] = {L.cloud, L.target, L.qn, L.qu, L.frames, L.eef, L.traj, L.cub_c, L.cub_d, L.cub_q, L.cyl_c, L.cyl_r, L.cyl_h, L.cyl_q,
+                L.done, L.first, L.map, L.sel, L.flags};
+  for (void* q : ps) if (q) cudaFree(q);
+  L = LiveSet();
+}
+int ensure_live_set(LiveSet& L, int cap, int N, int m1, int m2, int stride) {
+  if (cap <= L.cap && N <= L.n_points && m1 <= L.m1 && m2 <= L.m2 && stride <= L.stride) return MPN_OK;
+  free_live_set(L);
+  const size_t b = (size_t)cap;
+  bool ok = true;
+  auto A = [&](auto** q, size_t n) { ok = ok && cudaMalloc((void**)q, n * sizeof(**q)) == cudaSuccess; };
+  A(&L.cloud, b * N * 4); A(&L.target, b * 12); A(&L.qn, b * 7); A(&L.qu, b * 7); A(&L.frames, b * MPN_NLINK * 12); A(&L.eef, b * 12);
+  A(&L.traj, b * stride); A(&L.cub_c, b * m1 * 3); A(&L.cub_d, b * m1 * 3); A(&L.cub_q, b * m1 * 4); A(&L.cyl_c, b * m2 * 3);
+  A(&L.cyl_r, b * m2); A(&L.cyl_h, b * m2); A(&L.cyl_q, b * m2 * 4); A(&L.done, b); A(&L.first, b); A(&L.map, b); A(&L.sel, b); A(&L.flags, b);
+  if (!ok) { free_live_set(L); mpn::set_error("early-exit compaction: cudaMalloc failed"); return MPN_ERR_NOMEM; }
+  L.cap = cap; L.n_points = N; L.m1 = m1; L.m2 = m2; L.stride = stride;
+  return MPN_OK;
+}
+
+// sel[0..live) = indices of the problems that are still running (any order)
+__global__ void select_live_kernel(int B, const int32_t* __restrict__ done, int32_t* __restrict__ sel, int32_t* __restrict__ counter) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const bool alive = b < B && done[b] < 0;
+  const unsigned m = __ballot_sync(0xffffffffu, alive);
+  int base = 0;
+  if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (alive) sel[base + __popc(m & ((1u << lane) - 1u))] = b;
+}
+// dst[i][0..cols) = src[idx ? idx[i] : i][col0 .. col0 + cols)   (row pitches in elements)
+template <typename T>
+__global__ void gather_rows_kernel(T* __restrict__ dst, int dst_pitch, const T* __restrict__ src, int src_pitch, const int32_t* __restrict__ idx,
+                                   int rows, int cols) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * cols; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), k = (int)(i - (long long)r * cols);
+    dst[(size_t)r * dst_pitch + k] = src[(size_t)idx[r] * src_pitch + k];
+  }
+}
+// dst[idx[i]][col0 .. col0 + cols) = src[i][col0 .. col0 + cols)
+template <typename T>
+__global__ void scatter_rows_kernel(T* __restrict__ dst, int dst_pitch, const T* __restrict__ src, int src_pitch, const int32_t* __restrict__ idx,
+                                    int rows, int col0, int cols) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * cols; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), k = col0 + (int)(i - (long long)r * cols);
+    dst[(size_t)idx[r] * dst_pitch + k] = src[(size_t)r * src_pitch + k];
+  }
+}
+__global__ void compose_map_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ outer, const int32_t* __restrict__ sel, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = outer ? outer[sel[i]] : sel[i];
+}
+template <typename T>
+int gather_rows(mpn_ctx* c, cudaStream_t s, T* dst, int dst_pitch, const T* src, int src_pitch, const int32_t* idx, int rows, int cols) {
+  const long long n = (long long)rows * cols;
+  gather_rows_kernel<T><<<(unsigned)std::min<long long>((n + 255) / 256, 8LL * c->sm_count), 256, 0, s>>>(dst, dst_pitch, src, src_pitch, idx, rows, cols);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+template <typename T>
+int scatter_rows(mpn_ctx* c, cudaStream_t s, T* dst, int dst_pitch, const T* src, int src_pitch, const int32_t* idx, int rows, int col0, int cols) {
+  const long long n = (long long)rows * cols;
+  if (n <= 0) return MPN_OK;
+  scatter_rows_kernel<T><<<(unsigned)std::min<long long>((n + 255) / 256, 8LL * c->sm_count), 256, 0, s>>>(dst, dst_pitch, src, src_pitch, idx, rows, col0, cols);
+  c->launches++;
+  MPN_CHECK_CUDA(cudaGetLastError());
+  return MPN_OK;
+}
+}  // namespace
+
+void free_live_sets(mpn_ctx* c) {
+  if (!c->live_sets) return;
+  LiveSets* ls = static_cast<LiveSets*>(c->live_sets);
+  free_live_set(ls->s[0]);
+  free_live_set(ls->s[1]);
+  delete ls;
+  c->live_sets = nullptr;
+}
+
+extern "C" {
+
 int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene, int B, int N, float* cloud, const float* q0,
                 const float* target, int T, int early_exit, int check_every_step, float* traj, float* metrics) {
   REQ_CTX(c); REQ_TABLES(c); REQ_WEIGHTS(c);
@@ -822,26 +927,91 @@ int mpn_rollout(mpn_ctx* c, void* stream, int precision, const mpn_scene* scene,
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s, &cap);
   const bool poll = early_exit == 1 && cap == cudaStreamCaptureStatusNone;
+  const bool allow_compact = poll && getenv("MPN_NO_LIVE_COMPACTION") == nullptr;
+  // the CURRENT set of problems: the caller's arrays at first, a compact LiveSet after a compaction (cmap: its row -> caller's row)
+  int cb = B, cstart = 0;                 // problems in the current set; the step after which it was formed
+  float* ccloud = cloud; const float* ctarget = target; mpn_scene cscene = *scene; float* ctraj = traj;
+  float *cqn = w.qn, *cqu = w.qu, *cframes = w.frames, *ceef = w.eef;
+  int32_t *cdone = w.done, *cfirst = w.first_step; uint8_t* cflags = w.flags; const int32_t* cmap = nullptr;
+  int cur_set = -1;
+  const int nrob4 = c->cfg.n_robot * 4;
+  // what a compact set produced since it was formed goes back to the caller's arrays (trajectory columns, robot rows of the cloud,
+  // joint state, end-effector pose, done / collision bookkeeping)
+  auto scatter_back = [&](int upto_step) -> int {
+    if (!cmap) return MPN_OK;
+    int rr;
+    if ((rr = scatter_rows<float>(c, s, traj, stride, ctraj, stride, cmap, cb, (cstart + 1) * 7, (upto_step - cstart) * 7))) return rr;
+    if ((rr = scatter_rows<float>(c, s, cloud, N * 4, ccloud, N * 4, cmap, cb, 0, nrob4))) return rr;
+    if ((rr = scatter_rows<float>(c, s, w.qn, 7, cqn, 7, cmap, cb, 0, 7))) return rr;
+    if ((rr = scatter_rows<float>(c, s, w.qu, 7, cqu, 7, cmap, cb, 0, 7))) return rr;
+    if ((rr = scatter_rows<float>(c, s, w.eef, 12, ceef, 12, cmap, cb, 0, 12))) return rr;
+    if ((rr = scatter_rows<float>(c, s, w.frames, MPN_NLINK * 12, cframes, MPN_NLINK * 12, cmap, cb, 0, MPN_NLINK * 12))) return rr;
+    if ((rr = scatter_rows<int32_t>(c, s, w.done, 1, cdone, 1, cmap, cb, 0, 1))) return rr;
+    if ((rr = scatter_rows<int32_t>(c, s, w.first_step, 1, cfirst, 1, cmap, cb, 0, 1))) return rr;
+    return scatter_rows<uint8_t>(c, s, w.flags, 1, cflags, 1, cmap, cb, 0, 1);
+  };
+  int last_step = T;
   for (int i = 1; i <= T; ++i) {
-    if ((r = policy_forward(c, s, precision, cloud, w.qn, B, N, w.dq))) return r;
+    if ((r = policy_forward(c, s, precision, ccloud, cqn, cb, N, w.dq))) return r;
     { StageTimer t(c, s, MPN_ST_UPDATE);
-      if ((r = launch_step_update(c, s, B, w.dq, w.qn, w.qu, target, w.done, early_exit, traj, stride, w.frames, w.eef, nullptr, i))) return r; }
+      if ((r = launch_step_update(c, s, cb, w.dq, cqn, cqu, ctarget, cdone, early_exit, ctraj, stride, cframes, ceef, nullptr, i))) return r; }
     { StageTimer t(c, s, MPN_ST_SAMPLE_ROBOT);
-      if ((r = launch_sample_robot_slab(c, s, w.frames, B, c->cfg.n_robot, i - 1, cloud, N))) return r; }
+      if ((r = launch_sample_robot_slab(c, s, cframes, cb, c->cfg.n_robot, i - 1, ccloud, N))) return r; }
     if (check_every_step) {
       StageTimer t(c, s, MPN_ST_SWEEP);
-      if ((r = launch_sweep(c, s, *scene, B, traj + (size_t)i * 7, 1, stride, i, 1, w.flags, w.first_step, w.frames))) return r;
+      if ((r = launch_sweep(c, s, cscene, cb, ctraj + (size_t)i * 7, 1, stride, i, 1, cflags, cfirst, cframes))) return r;
     }
     if (poll && i % EARLY_EXIT_POLL == 0 && i < T) {
-      if ((r = launch_count_live(c, s, B, w.done, w.live))) return r;
+      if ((r = launch_count_live(c, s, cb, cdone, w.live))) return r;
       MPN_CHECK_CUDA(cudaMemcpyAsync(w.live_host, w.live, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
       MPN_CHECK_CUDA(cudaStreamSynchronize(s));
-      if (*w.live_host == 0) {   // everybody has stopped: the remaining rows repeat the frozen configurations
-        if ((r = launch_fill_traj_tail(c, s, B, w.qu, traj, stride, i + 1, T))) return r;
+      const int live = *w.live_host;
+      if (live == 0) {   // everybody has stopped: the remaining rows repeat the frozen configurations
+        if ((r = launch_fill_traj_tail(c, s, cb, cqu, ctraj, stride, i + 1, T))) return r;
+        last_step = T;   // the tail columns of the current set are final
         break;
+      }
+      if (allow_compact && live <= cb / 2) {
+        // the stopped problems of the current set are finished: their tails repeat the frozen configuration; hand everything the set
+        // produced back, then carry only the running problems on
+        if ((r = launch_fill_traj_tail(c, s, cb, cqu, ctraj, stride, i + 1, T))) return r;
+        if ((r = scatter_back(T))) return r;
+        if (!c->live_sets) c->live_sets = new LiveSets();
+        LiveSets* ls = static_cast<LiveSets*>(c->live_sets);
+        const int nxt = cur_set == 0 ? 1 : 0;
+        LiveSet& L = ls->s[nxt];
+        if ((r = ensure_live_set(L, cur_set < 0 ? (B + 1) / 2 : live, N, c->cfg.max_cuboids, c->cfg.max_cylinders, stride))) return r;
+        MPN_CHECK_CUDA(cudaMemsetAsync(w.live, 0, sizeof(int32_t), s));
+        select_live_kernel<<<(cb + 255) / 256, 256, 0, s>>>(cb, cdone, L.sel, w.live);
+        compose_map_kernel<<<(live + 255) / 256, 256, 0, s>>>(L.map, cmap, L.sel, live);
+        c->launches += 2;
+        MPN_CHECK_CUDA(cudaGetLastError());
+        const int m1 = c->cfg.max_cuboids, m2 = c->cfg.max_cylinders;
+        if ((r = gather_rows<float>(c, s, L.cloud, N * 4, ccloud, N * 4, L.sel, live, N * 4))) return r;
+        if ((r = gather_rows<float>(c, s, L.target, 12, ctarget, 12, L.sel, live, 12))) return r;
+        if ((r = gather_rows<float>(c, s, L.qn, 7, cqn, 7, L.sel, live, 7))) return r;
+        if ((r = gather_rows<float>(c, s, L.qu, 7, cqu, 7, L.sel, live, 7))) return r;
+        if ((r = gather_rows<float>(c, s, L.frames, MPN_NLINK * 12, cframes, MPN_NLINK * 12, L.sel, live, MPN_NLINK * 12))) return r;
+        if ((r = gather_rows<float>(c, s, L.eef, 12, ceef, 12, L.sel, live, 12))) return r;
+        if ((r = gather_rows<int32_t>(c, s, L.done, 1, cdone, 1, L.sel, live, 1))) return r;
+        if ((r = gather_rows<int32_t>(c, s, L.first, 1, cfirst, 1, L.sel, live, 1))) return r;
+        if ((r = gather_rows<uint8_t>(c, s, L.flags, 1, cflags, 1, L.sel, live, 1))) return r;
+        if ((r = gather_rows<float>(c, s, L.cub_c, m1 * 3, cscene.cuboid_centers, m1 * 3, L.sel, live, m1 * 3))) return r;
+        if ((r = gather_rows<float>(c, s, L.cub_d, m1 * 3, cscene.cuboid_dims, m1 * 3, L.sel, live, m1 * 3))) return r;
+        if ((r = gather_rows<float>(c, s, L.cub_q, m1 * 4, cscene.cuboid_quats, m1 * 4, L.sel, live, m1 * 4))) return r;
+        if ((r = gather_rows<float>(c, s, L.cyl_c, m2 * 3, cscene.cylinder_centers, m2 * 3, L.sel, live, m2 * 3))) return r;
+        if ((r = gather_rows<float>(c, s, L.cyl_r, m2, cscene.cylinder_radii, m2, L.sel, live, m2))) return r;
+        if ((r = gather_rows<float>(c, s, L.cyl_h, m2, cscene.cylinder_heights, m2, L.sel, live, m2))) return r;
+        if ((r = gather_rows<float>(c, s, L.cyl_q, m2 * 4, cscene.cylinder_quats, m2 * 4, L.sel, live, m2 * 4))) return r;
+        cb = live; cstart = i; cur_set = nxt; cmap = L.map;
+        ccloud = L.cloud; ctarget = L.target; ctraj = L.traj; cqn = L.qn; cqu = L.qu; cframes = L.frames; ceef = L.eef;
+        cdone = L.done; cfirst = L.first; cflags = L.flags;
+        cscene.cuboid_centers = L.cub_c; cscene.cuboid_dims = L.cub_d; cscene.cuboid_quats = L.cub_q; cscene.cylinder_centers = L.cyl_c;
+        cscene.cylinder_radii = L.cyl_r; cscene.cylinder_heights = L.cyl_h; cscene.cylinder_quats = L.cyl_q;
       }
     }
   }
+  if ((r = scatter_back(last_step))) return r;
   if (!check_every_step) {
     StageTimer t(c, s, MPN_ST_SWEEP);
     if ((r = launch_sweep(c, s, *scene, B, traj, T + 1, stride, 0, 0, w.flags, w.first_step))) return r;

@@ -138,6 +138,8 @@ struct mpn_ctx {
   mpn::Weights w;
   mpn::Workspace ws;
   mpn::TrainWs tw;
+  // early-exit rollouts: two ping-pong sets of per-problem state for the compacted still-running problems (engine.cu: LiveSet)
+  void* live_sets = nullptr;
   int64_t launches = 0;
   // stage profiler
   bool prof = false;

@@ -367,6 +367,48 @@ def test_rollout_early_exit_stops_launching(engine_w, oracle, tables):
     assert all(torch.equal(traj[:, t], traj[:, 1]) for t in range(2, T + 1))
 
 
+def test_rollout_early_exit_compacts_live_problems(engine_w, oracle, tables):
+    """rollout_until_success on a batch (run_inference.py:137-191): problems stop at different steps; once at most half of the current
+    set is still running the library carries only the running ones on (state gathered into a compact set, results scattered back).
+    120 of 160 problems stop at step 1, 20 more at step 12, 20 never: compaction at the polls of step 8 (160 -> 40) and 16 (40 -> 20).
+    Trajectories, metrics and the final clouds must equal the uncompacted rollout (MPN_NO_LIVE_COMPACTION=1) bit for bit, with the
+    per-step collision check on.  (The sets stay above 16 problems: at <= 16 the FC head switches to its fp32 weight-streaming
+    kernels, DESIGN.md section 9c, and the two runs would differ by that kernel's rounding.)"""
+    from mpinets_b200 import _lib
+    B, T = 160, 30
+    p = _problems(4, B)
+    sc = to_dev(p)
+    q0, tg = torch.from_numpy(p["q0"]).cuda(), torch.from_numpy(p["target"]).cuda()
+    cloud0 = engine_w.build_cloud(sc, q0, tg)
+    ref_traj, _ = engine_w.rollout(sc, cloud0.clone(), q0, tg, T, precision=_lib.PREC_BF16X3)      # no early exit: where every step lands
+    _, eef1 = engine_w.fk(ref_traj[:, 1].contiguous())
+    _, eef12 = engine_w.fk(ref_traj[:, 12].contiguous())
+    tg2 = tg.clone()
+    tg2[:120] = eef1[:120]          # reached after the first step
+    tg2[120:140] = eef12[120:140]   # reached at step 12 (unless the arm passed through that pose before)
+    outs = []
+    for nocompact in (True, False):
+        if nocompact:
+            os.environ["MPN_NO_LIVE_COMPACTION"] = "1"
+        try:
+            c = cloud0.clone()
+            traj, metrics = engine_w.rollout(sc, c, q0, tg2, T, early_exit=True, check_every_step=True, precision=_lib.PREC_BF16X3)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("MPN_NO_LIVE_COMPACTION", None)
+        assert not engine_w.tc_error()
+        outs.append((traj.clone(), metrics.clone(), c))
+    (t0, m0, c0), (t1, m1, c1) = outs
+    steps = m0[:, 2].cpu().numpy()
+    assert (steps[:120] == 1).all() and (steps[120:140] <= 12).all() and (steps[140:] == T).all()
+    print("compacted vs uncompacted: max |traj diff|", float((t0 - t1).abs().max()), " metrics", float((m0 - m1).abs().max()),
+          " cloud", float((c0 - c1).abs().max()))
+    # a stopped problem's cloud keeps the robot rows of the last step it was carried through (the subset of surface points changes per
+    # step even for a frozen pose), so the in-place cloud is compared for the problems that run to the end
+    assert torch.equal(t0, t1) and torch.equal(m0, m1) and torch.equal(c0[140:], c1[140:])
+    assert torch.equal(t1[140:], ref_traj[140:])                      # the problems that never stop follow the plain rollout
+
+
 # ----------------------------------------------------------------------------- full-size properties (BASELINE configs)
 def test_full_size_properties(engine, oracle, tables):
     """4096 problems (configs[1]): size-independent properties of the GPU path + spot parity on a subset."""
