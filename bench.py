@@ -635,6 +635,14 @@ def main():
                                "collision_flag_match": float((O.sweep_flags(p3, r3["traj"].cpu().numpy(), eng.tables)[0] ==
                                                               r3["metrics"][:, 0].cpu().numpy().astype(np.uint8)).mean())}
         del r3, host3
+        # the N > 1 default is configs[3] (mixed scenes, denser SA2 neighbourhoods than tabletop): one GPU's shard of it, so that the
+        # scaling efficiency of the N-GPU lines can be read against the SAME workload
+        p4, host4 = make_inputs(4)
+        r4 = timed_job(host4, prec, K, W, profile=False)
+        extra["configs[3] shard"] = {"workload": WORKLOADS[4]["desc"] + " -- one GPU's 4096-problem shard (what every rank of the N > 1 default runs)",
+                                     "dtype": precision, "steps": K, "value": B * K / (r4["ms"] / 1000.0), "unit": "env steps/s",
+                                     "ms_per_step": r4["ms"] / K, "collision_rate": float(r4["metrics"][:, 0].mean().item())}
+        del r4, host4
 
     # ---- match fields of the metric, against the CPU oracle, outside every timed region (rank 0's shard)
     parity = None
@@ -706,6 +714,8 @@ def main():
             "config": {"workload": f"{WORKLOADS[wl]['baseline']}: {WORKLOADS[wl]['desc']}; 6272-pt clouds (2048 robot + 4096 obstacle + 128 target), "
                                    "lock-step policy rollout (FK + cloud resample + PointNet++ + delta-q + per-step SDF sweep)",
                        "problems_per_gpu": B, "global_problems": world * B, "parallelism": f"problem-sharded x{world}",
+                       "scaling_note": ("N = 1 defaults to configs[1] (tabletop), N > 1 to configs[3] (mixed scenes, ~20 % more SA2 work per "
+                                        "problem): the same-workload one-GPU rate is extra['configs[3] shard'] of the N = 1 line"),
                        "rollout_length_of_config": WORKLOADS[wl]["rollout_T"], "timed_steps": K,
                        "precision": prec_desc,
                        "l2": "inputs larger than L2 (clouds 411 MB/GPU per step)", "weights": "random init, seed 0"},
