@@ -370,6 +370,31 @@ def ball_query(radius, nsample, xyz, new_xyz):
     return idx
 
 
+def distinct_neighbour_counts(ball_idx):
+    """ball_idx [B,m,nsample] (pointnet2 first-hit padding) -> distinct neighbours per group [B,m]: the rows of a group that are not
+    copies (the max-pool of PointnetSAModule, model.py:365-382, cannot see the copies)."""
+    a = np.sort(np.asarray(ball_idx), axis=-1)
+    return 1 + (a[..., 1:] != a[..., :-1]).sum(-1)
+
+
+def packed_tile_count(counts, per_round=4, gran=32, tile_rows=128):
+    """Tiles the fused SA kernels issue for groups with `counts` distinct rows (1-D, one problem): rounds of `per_round` consecutive
+    centroids, each taking ceil(count / gran) units of `gran` rows, first fit in centroid order, never straddling a tile
+    (mpinets_b200/csrc/tc_common.cuh: pack_round / pack_round8) -- test infrastructure, mirrors the device rule."""
+    units_per_tile = tile_rows // gran
+    tiles = 0
+    counts = np.asarray(counts)
+    for r0 in range(0, len(counts), per_round):
+        fill, n = 0, 1
+        for h in counts[r0:r0 + per_round]:
+            q = max(1, -(-int(min(h, tile_rows)) // gran))
+            if fill + q > units_per_tile:
+                n, fill = n + 1, 0
+            fill += q
+        tiles += n
+    return tiles
+
+
 def gather_operation(feat, idx):
     """feat [B,C,N], idx [B,m] -> [B,C,m]"""
     B = feat.shape[0]

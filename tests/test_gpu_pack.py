@@ -64,18 +64,8 @@ def test_packed_tiles_equal_unpacked(engine_w, oracle, tables, mode, case):
     assert torch.equal(f_ref, f_pk) and torch.equal(f_ref, f_set)
     assert t_pk == t_set and B * 512 / 4 <= t_pk[0] <= B * 512
     # the packing is the first fit the header describes: recompute the tile count from the neighbour lists
-    counts = np.array([[len(set(r.tolist())) for r in bi_ref[b].cpu().numpy()] for b in range(B)])
-    q = np.maximum(1, np.ceil(counts / 32).astype(int))
-    exp = 0
-    for b in range(B):
-        for r0 in range(0, 512, 4):
-            fill, n = 0, 1
-            for c in q[b, r0:r0 + 4]:
-                if fill + c > 4:
-                    n, fill = n + 1, 0
-                fill += c
-            exp += n
-    assert t_pk[0] == exp
+    counts = oracle.distinct_neighbour_counts(bi_ref.cpu().numpy())
+    assert t_pk[0] == sum(oracle.packed_tile_count(counts[b], per_round=4, gran=32) for b in range(B))
     print(f"SA1 {mode} {case}: {t_pk[0] / (B * 512):.3f} tiles per group (distinct neighbours: mean {counts.mean():.1f}, max {counts.max()})")
     # ---- SA2 on SA1's output
     xyz1 = nx.contiguous()
@@ -84,7 +74,9 @@ def test_packed_tiles_equal_unpacked(engine_w, oracle, tables, mode, case):
     (_, g_set), _ = _run(engine_w, 1, xyz1, f_ref.contiguous(), prec, False, False)
     assert u_ref[1] == B * 128 and torch.equal(bj_ref, bj_pk)
     assert torch.equal(g_ref, g_pk) and torch.equal(g_ref, g_set)
-    assert B * 128 / 8 <= u_pk[1] <= B * 128          # bf16: quarters of 4 centroids; bf16x3: eighths of 8 centroids per round
+    counts2 = oracle.distinct_neighbour_counts(bj_ref.cpu().numpy())
+    rule = dict(per_round=8, gran=16) if mode == "bf16x3" else dict(per_round=4, gran=32)   # sa2x3h: eighths of 8 centroids; sa2w3: quarters of 4
+    assert u_pk[1] == sum(oracle.packed_tile_count(counts2[b], **rule) for b in range(B))
     print(f"SA2 {mode} {case}: {u_pk[1] / (B * 128):.3f} tiles per group")
 
 

@@ -601,3 +601,19 @@ def test_depth_render_eval_cameras_see_the_scenes(oracle):
         assert (cnt > 200).all(), (env, cnt)
         for b in range(3):
             assert np.abs(oracle.sdf_points({k: v[b:b + 1] for k, v in p.items() if k in scenes.SCENE_KEYS}, pts[b:b + 1, :cnt[b]])).max() < 1e-4
+
+
+def test_packed_tile_rule_of_the_sa_kernels(oracle):
+    """the first-fit rule by which the fused set-abstraction kernels pack the distinct rows of a round's groups into 128-row tiles
+    (oracle.packed_tile_count mirrors tc_common.cuh; the GPU tests compare the device's tile counters against it)"""
+    assert oracle.packed_tile_count([5, 9, 31, 32]) == 1                      # four quarters
+    assert oracle.packed_tile_count([33, 1, 1, 1]) == 2                       # 2 + 1 + 1 quarters, the fourth group opens a tile
+    assert oracle.packed_tile_count([128, 128, 128, 128]) == 4                # full groups: the reference formulation
+    assert oracle.packed_tile_count([65, 64, 1, 1]) == 2                      # 3 | 2 + 1 + 1
+    assert oracle.packed_tile_count([1] * 8) == 2                             # a round never spans more than four centroids ...
+    assert oracle.packed_tile_count([1] * 8, per_round=8, gran=16) == 1       # ... eight at 16-row granularity
+    assert oracle.packed_tile_count([17, 16, 100, 3, 40, 40, 40, 40], per_round=8, gran=16) == 4   # eighths: 2+1 | 7+1 | 3+3 | 3+3
+    idx = np.zeros((1, 2, 128), np.int32)
+    idx[0, 0, :5] = [3, 7, 9, 11, 400]; idx[0, 0, 5:] = 3                      # 5 hits padded with the first
+    idx[0, 1] = np.arange(128)
+    assert oracle.distinct_neighbour_counts(idx).tolist() == [[5, 128]]
