@@ -163,8 +163,8 @@ def test_fps_bit_exact_on_scene_clouds(engine, oracle, tables):
     assert np.array_equal(idx2.cpu().numpy(), oracle.fps(gathered, 128))
 
 
-@pytest.mark.parametrize("N,m", [(1, 1), (5, 3), (31, 31), (33, 8), (100, 64), (512, 128), (513, 200), (1000, 512),
-                                 (4097, 64), (6272, 512), (8192, 16)])
+@pytest.mark.parametrize("N,m", [(1, 1), (5, 3), (31, 31), (33, 8), (100, 64), (129, 100), (300, 300), (512, 128), (512, 512), (513, 200),
+                                 (1000, 512), (4097, 64), (6272, 512), (8192, 16)])
 def test_fps_bit_exact_sizes_ties_and_skips(engine, oracle, N, m):
     rng = np.random.RandomState(N)
     xyz = rng.uniform(-1, 1, size=(3, N, 3)).astype(np.float32)
@@ -174,6 +174,23 @@ def test_fps_bit_exact_sizes_ties_and_skips(engine, oracle, N, m):
         a = xyz if stride == 3 else np.concatenate([xyz, np.ones((3, N, 1), np.float32)], -1)
         got = engine.fps(torch.from_numpy(np.ascontiguousarray(a)).cuda(), m).cpu().numpy()
         assert np.array_equal(got, oracle.fps(a, m))
+
+
+@pytest.mark.parametrize("N,m", [(129, 100), (300, 300), (512, 128), (512, 512)])
+def test_fps_warp_per_problem_kernel(engine, oracle, N, m):
+    """the warp-per-problem FPS of small clouds (taken for batches >= 1024; forced here with MPN_FPS_WARP=1) on the same tie / skip cases"""
+    rng = np.random.RandomState(N + 1)
+    xyz = rng.uniform(-1, 1, size=(3, N, 3)).astype(np.float32)
+    xyz[1] = np.round(xyz[1] * 4) / 4
+    xyz[2, : N // 3] *= 0.02
+    os.environ["MPN_FPS_WARP"] = "1"
+    try:
+        for stride in (3, 4):
+            a = xyz if stride == 3 else np.concatenate([xyz, np.ones((3, N, 1), np.float32)], -1)
+            got = engine.fps(torch.from_numpy(np.ascontiguousarray(a)).cuda(), m).cpu().numpy()
+            assert np.array_equal(got, oracle.fps(a, m))
+    finally:
+        os.environ.pop("MPN_FPS_WARP", None)
 
 
 def test_fps_origin_skip_boundary(engine, oracle):
